@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — air-sea flux points/s (F64) for the atmosphere–surface interface step.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+Workload (BASELINE.json configs[3]): the 1/12° (4320x1680) exchange grid with a JRA55-shaped
+synthetic atmosphere (640x320, Float32, 3-hourly), sharded in latitude bands over N GPUs (strong
+scaling: the global grid is fixed).  One *step* = one pass of the hot path: radiation + atmosphere
+interpolation -> atmosphere–ocean similarity-theory solve -> net ocean flux assembly -> radiative
+flux application -> global flux diagnostics (local sum + all-reduce when N > 1).
+
+`value`   points/s with all inputs resident in HBM (CUDA events, max over ranks).
+`e2e`     the same through the public API with HOST buffers: every step copies the ocean surface
+          state (T, S, u, v) from pinned host memory to the device and reads the diagnostics back.
+`roofline` the dominant kernel (the a–o solve) against the measured FP64 DFMA peak;
+`roofline_hbm` the interpolation kernel against the measured HBM copy bandwidth.
+`cpu_baseline` the CPU oracle (a port of the reference algorithm; Julia is not installed) on the
+          host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+import ne_b200  # noqa: E402,F401  (registers the package as numericalearth_jl_b200)
+
+# algorithmic FP64 work of the default a–o variant (oracle op census x SURVEY §8(d) weights)
+F_ITER = 4112.5
+F_EPI = 150.0
+BYTES_INTERP_ATM = 2 * 4 + 7 * 8      # 2 Float32 fractional indices in, 7 Float64 fields out
+BYTES_INTERP_RAD = 2 * 4 + 2 * 8
+DT_STEP = 1200.0
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--config", default="C4")
+    p.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    p.add_argument("--atm-dtype", default="f32", choices=["f64", "f32"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    return p.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# -------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle (port of the reference algorithm) on the host cores
+# -------------------------------------------------------------------------------------------------
+def cpu_step_factory(args, sample_ny):
+    import ne_b200
+    import oracle
+    from numericalearth_jl_b200 import synthetic
+    lib = oracle.load()
+    host = ne_b200.NumpyHostBackend()
+    cfg = dict(synthetic.CONFIGS[args.config])
+    cfg["ny"] = sample_ny       # same longitudes and latitude range, rows subsampled
+    ci = synthetic.build_case(cfg, host, FT=args.dtype, atm_FT=args.atm_dtype, lib=lib)
+    ci.initialize()
+    state = {"t": 0.0}
+
+    def step():
+        ci.update_state(state["t"])
+        state["t"] += DT_STEP
+    return ci, step, lib
+
+
+def run_cpu(args, seconds_per_step=1.5, steps=None, warmup=1):
+    """Time the oracle interface step on a bounded latitude-subsampled sample of the workload."""
+    import oracle
+    from numericalearth_jl_b200 import synthetic
+    lib = oracle.load()
+    threads = lib.dll.neo_max_threads()
+    full_ny = synthetic.CONFIGS[args.config]["ny"]
+    ci, step, _ = cpu_step_factory(args, 8)
+    t0 = time.perf_counter(); step(); dt = time.perf_counter() - t0
+    rate = ci.grid.launch_points() / max(dt, 1e-9)
+    nx = ci.grid.nx
+    ny = int(min(full_ny, max(8, seconds_per_step * rate / (nx + 2))))
+    ci, step, _ = cpu_step_factory(args, ny)
+    for _ in range(warmup):
+        step()
+    times = []
+    n = steps if steps is not None else 5
+    for _ in range(n):
+        t0 = time.perf_counter(); step(); times.append(time.perf_counter() - t0)
+    pts = ci.grid.launch_points()
+    total = float(np.sum(times))
+    return {"value": pts * n / total, "unit": "points/s", "cores": int(threads), "kind": "port",
+            "sample": f"{args.config} subsampled in latitude to {nx}x{ny} ({pts} launch points/step), {n} steps, "
+                      f"OpenMP oracle, {threads} threads", "ms_per_step": 1e3 * total / n, "points_per_step": pts}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = run_cpu(args, seconds_per_step=2.0, steps=args.steps, warmup=max(args.warmup, 1))
+    line = {"impl": "reference", "metric": "air-sea flux points/s", "value": r["value"], "unit": "points/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": r["value"], "unit": "points/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "Julia is not installed: the reference arm is the C++/OpenMP oracle restating the reference algorithm"}
+    print(json.dumps(line))
+
+
+def workload_config(args, n):
+    from numericalearth_jl_b200 import synthetic
+    c = synthetic.CONFIGS[args.config]
+    return {"workload": f"{args.config}: {c['nx']}x{c['ny']} exchange grid (lat {c['latitude']}), JRA55-shaped 640x320 "
+                        f"{args.atm_dtype} atmosphere + radiation, SimilarityTheoryFluxes defaults, OceanOnlyModel interface step",
+            "exchange_dtype": args.dtype, "atmosphere_dtype": args.atm_dtype,
+            "partition": f"{n} latitude band(s), one-ring overcompute, no data-path collective",
+            "l2": "inputs larger than L2 (≈35 fields x 58 MB at N=1); no explicit flush",
+            "points_per_step": (c["nx"] + 2) * (c["ny"] + 2)}
+
+
+# -------------------------------------------------------------------------------------------------
+# this repo's arm
+# -------------------------------------------------------------------------------------------------
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    import ne_b200
+    from numericalearth_jl_b200 import sharding, synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    backend = ne_b200.TorchCudaBackend(f"cuda:{local_rank}")
+    lib = ne_b200.get_library()
+    cfg = synthetic.CONFIGS[args.config]
+    grid = sharding.band_grid(cfg["nx"], cfg["ny"], cfg["latitude"], rank, world, FT=args.dtype)
+    ci = synthetic.build_case(args.config, backend, FT=args.dtype, atm_FT=args.atm_dtype, grid=grid, with_iterations=True)
+    ci.initialize()
+    f = ci.ao_fluxes
+    diag = sharding.FluxDiagnostics(ci, [f.latent_heat, f.sensible_heat, f.water_vapor, f.x_momentum, f.y_momentum,
+                                         ci.net_ocean.T, ci.net_ocean.eta])
+    stream = backend.stream()
+    global_points = (cfg["nx"] + 2) * (cfg["ny"] + 2)
+    local_points = grid.launch_points()
+
+    # cached descriptor: only the time interpolator changes from step to step
+    fused = ci.fused_step_desc(0.0)
+    atm_times = ci.atmosphere.times
+
+    def set_time(t):
+        nt, n1, n2 = ne_b200.interpolating_time_indices(atm_times, t, "cyclical")
+        for d in (fused.atmosphere, fused.radiation):
+            d.time.frac, d.time.m1, d.time.m2, d.time.same = nt, n1, n2, int(n1 == n2)
+
+    state = {"t": 0.37 * 10800.0}
+
+    def step():
+        set_time(state["t"])
+        lib.call("fused_interface_step", args.dtype, fused, stream)
+        diag.reduce()
+        state["t"] += DT_STEP
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=backend.device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident throughput ---------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = global_points / (ms_per_step * 1e-3)
+
+    # ---- per-kernel timings for the rooflines (same inputs, kernel timed alone on the launch stream) ---
+    ao_desc = ci.atmosphere_ocean_desc()
+    ao_desc.iterations = None
+    atm_desc, rad_desc = fused.atmosphere, fused.radiation
+    reps = max(5, min(args.steps, 20))
+    ms_ao = timed(lambda: lib.call("atmosphere_ocean_fluxes", args.dtype, ao_desc, stream), reps) / reps
+    ms_ia = timed(lambda: lib.call("interp_state", args.dtype, atm_desc, stream), reps) / reps
+    ms_ir = timed(lambda: lib.call("interp_state", args.dtype, rad_desc, stream), reps) / reps
+    ms_as = timed(lambda: lib.call("assemble_net_ocean_fluxes", args.dtype, fused.assemble, stream), reps) / reps
+    ms_ap = timed(lambda: lib.call("apply_radiative_fluxes", args.dtype, fused.apply_radiation, stream), reps) / reps
+    it = backend.to_numpy(grid.interior(ci.ao_iterations))
+    iters_sum = float(it.sum())
+    if world > 1:
+        t = torch.tensor([iters_sum, float(local_points)], device=backend.device, dtype=torch.float64)
+        dist.all_reduce(t)
+        iters_sum_g, pts_g = float(t[0]), float(t[1])
+    else:
+        iters_sum_g, pts_g = iters_sum, float(local_points)
+    active = it > 0
+    flops_local = iters_sum * F_ITER + float(active.sum()) * F_EPI
+    fp64_peak, _ = lib.measure_fp64_peak()
+    peaks, peak_src = load_peaks()
+    achieved_tf = flops_local / (ms_ao * 1e-3) / 1e12
+    wbytes = 8 if args.dtype == "f64" else 4
+    ibytes = 4 if args.atm_dtype == "f32" else 8
+    interp_bytes = local_points * (2 * ibytes + 7 * wbytes)
+    hbm_achieved = interp_bytes / (ms_ia * 1e-3) / 1e9
+
+    # ---- end to end with host buffers -----------------------------------------------------------------
+    o = ci._host_inputs["ocean"]
+    pinned = {k: torch.from_numpy(o[k]).pin_memory() for k in ("T", "S", "u", "v")}
+    dev_t = {"T": ci.ocean_state.T, "S": ci.ocean_state.S, "u": ci.ocean_state.u, "v": ci.ocean_state.v}
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    result_host = torch.empty(diag.result.shape, dtype=torch.float64).pin_memory()
+    d2h = result_host.numel() * 8
+
+    def e2e_step():
+        for k in ("T", "S", "u", "v"):
+            dev_t[k].copy_(pinned[k], non_blocking=True)
+        step()
+        result_host.copy_(diag.result, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    e2e_value = global_points / (ms_e2e * 1e-3)
+    torch.cuda.synchronize()
+    diag_values = [float(x) for x in result_host.tolist()]
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_cpu(args, seconds_per_step=args.cpu_seconds / 6.0, steps=5, warmup=1)
+        cpu = {"value": r["value"], "unit": "points/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        n_active = int(active.sum())
+        line = {
+            "metric": "air-sea flux points/s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(7 * args.steps),
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "kernel": "ao_flux_kernel", "achieved": achieved_tf, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                         "peak_source": "measured in this run by ne_measure_fp64_peak (DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
+                         "ms_per_launch": ms_ao, "algorithmic_flop_per_iteration": F_ITER, "algorithmic_flop_epilogue": F_EPI,
+                         "mean_iterations_active": iters_sum / max(n_active, 1), "max_iterations": int(it.max()),
+                         "active_points": n_active, "points_per_launch": int(local_points)},
+            "roofline_hbm": {"bound": "hbm", "kernel": "interp_state_kernel(atmosphere)", "achieved": hbm_achieved,
+                             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / peaks["hbm_gbs"],
+                             "peak_source": peak_src, "ms_per_launch": ms_ia, "traffic": None},
+            "kernel_ms": {"interp_radiation": ms_ir, "interp_atmosphere": ms_ia, "atmosphere_ocean_fluxes": ms_ao,
+                          "assemble_net_ocean_fluxes": ms_as, "apply_radiative_fluxes": ms_ap},
+            "diagnostics": diag_values,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,92 @@
+"""Latitude-band sharding of the exchange grid over the GPUs of one box.
+
+Every kernel on the path is pointwise apart from 2-point stencils, and — exactly like the reference,
+which computes fluxes on (0:N+1) so that no halo exchange is needed afterwards
+(EarthSystemModels/InterfaceComputations/InterfaceComputations.jl:108-112) — each band overcomputes
+one ring, so there is NO data-path collective.  The only collective is the global flux /
+conservation diagnostics sum (src/Diagnostics/interface_fluxes.jl:90-195): per-band partial sums on
+the device (ne_diag_reduce, fixed summation order) followed by one small all-reduce (NCCL over
+NVLink on the GPU box, gloo in the CPU tests).  The reference itself issues no collective on this
+path: each MPI rank holds the whole atmosphere
+(DataWrangling/JRA55/JRA55_prescribed_atmosphere.jl:7-8) — as does each band here.
+"""
+import numpy as np
+
+from . import abi as A
+from .interface import ExchangeGrid
+
+
+def latitude_bands(ny, world_size, weights=None):
+    """Split rows 1..ny into `world_size` contiguous bands [(j0, j1)] (1-based, inclusive).
+    With `weights` (per-row expected cost: active points x expected iterations) the split balances
+    cumulative weight instead of row count."""
+    if world_size < 1 or ny < world_size:
+        raise ValueError("need at least one row per band")
+    if weights is None:
+        edges = [round(r * ny / world_size) for r in range(world_size + 1)]
+    else:
+        w = np.asarray(weights, dtype=np.float64)
+        if w.shape != (ny,):
+            raise ValueError("weights must have one entry per row")
+        c = np.concatenate([[0.0], np.cumsum(w)])
+        edges = [0]
+        for r in range(1, world_size):
+            e = int(np.searchsorted(c, c[-1] * r / world_size))
+            e = min(max(e, edges[-1] + 1), ny - (world_size - r))
+            edges.append(e)
+        edges.append(ny)
+    return [(edges[r] + 1, edges[r + 1]) for r in range(world_size)]
+
+
+def band_grid(nx, ny, latitude, rank, world_size, FT="f64", hx=7, hy=7, weights=None):
+    j0, j1 = latitude_bands(ny, world_size, weights)[rank]
+    return ExchangeGrid(nx=nx, ny=j1 - j0 + 1, hx=hx, hy=hy, latitude=latitude, FT=FT, j_offset=j0 - 1, ny_global=ny)
+
+
+def band_rows(global_parent, grid: ExchangeGrid):
+    """Rows of a GLOBAL exchange-layout parent array (ny_global+2hy, nx+2hx) that make up the band's
+    parent (its interior + hy halo rows each side, i.e. the neighbours' data: the one-row ocean halo
+    the overcomputed ring reads)."""
+    return global_parent[..., grid.j_offset:grid.j_offset + grid.ny + 2 * grid.hy, :]
+
+
+class FluxDiagnostics:
+    """Area-weighted global integrals of flux fields: local deterministic two-stage sum on the device
+    + one all-reduce of n_fields doubles."""
+
+    def __init__(self, interfaces, fields, n_blocks=296):
+        self.ci = interfaces
+        b, g = interfaces.backend, interfaces.grid
+        self.fields = fields
+        phi = np.deg2rad(g.phi.astype(np.float64))
+        area = (np.cos(phi)[:, None] * np.ones((1, g.shape[1]))).astype(np.float64 if g.FT == "f64" else np.float32)
+        self.area = b.from_numpy(area)
+        self.partial = b.zeros((n_blocks * len(fields),), "f64")
+        self.result = b.zeros((len(fields),), "f64")
+        d = A.NeDiagDesc()
+        d.grid = g.pod(False)
+        d.n_fields = len(fields)
+        for k, f in enumerate(fields):
+            d.fields[k] = b.ptr(f)
+        d.area = b.ptr(self.area)
+        d.inactive = b.ptr(interfaces.inactive) if interfaces.inactive is not None else None
+        d.partial, d.n_blocks, d.result = b.ptr(self.partial), n_blocks, b.ptr(self.result)
+        self.desc = d
+
+    def reduce(self, group=None):
+        """Enqueue the local reduction and (world_size > 1) the all-reduce; returns the device/host
+        result array without synchronising."""
+        self.ci.lib.call("diag_reduce", self.ci.grid.FT, self.desc, self.ci.backend.stream())
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                r = self.result
+                if isinstance(r, np.ndarray):
+                    import torch
+                    t = torch.from_numpy(r)
+                    dist.all_reduce(t, group=group)
+                else:
+                    dist.all_reduce(r, group=group)
+        except ImportError:
+            pass
+        return self.result

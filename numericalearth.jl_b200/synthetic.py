@@ -104,8 +104,7 @@ def ocean_arrays(grid: ExchangeGrid, rng, sea_ice=False):
     inactive = low > np.quantile(low, 0.70)
     j = np.arange(shape[0])
     outside = (j < grid.hy) | (j >= grid.hy + grid.ny)
-    if grid.ny_global is None:
-        inactive[outside, :] = True
+    inactive[outside, :] = True
     o["inactive"] = inactive.astype(np.uint8)
     if sea_ice:
         latd = np.abs(np.rad2deg(phi))
@@ -139,7 +138,12 @@ def build_case(config, backend, FT="f64", atm_FT="f64", nt=2, seed_offset=0, sea
                                rain=(dev["rain"],), snow=(dev["snow"],))
     rad = PrescribedRadiation(grid=src, times=times, downwelling_shortwave=dev["sw"], downwelling_longwave=dev["lw"]) \
         if radiation else None
-    o = ocean_arrays(grid, rng, sea_ice=sea_ice)
+    if grid.ny_global is not None:   # latitude band: generate the GLOBAL surface state, keep this band's rows
+        gg = ExchangeGrid(nx=grid.nx, ny=grid.ny_global, hx=grid.hx, hy=grid.hy, latitude=grid.latitude, FT=grid.FT)
+        og = ocean_arrays(gg, rng, sea_ice=sea_ice)
+        o = {k: np.ascontiguousarray(v[grid.j_offset:grid.j_offset + grid.ny + 2 * grid.hy, :]) for k, v in og.items()}
+    else:
+        o = ocean_arrays(grid, rng, sea_ice=sea_ice)
     ci = ComponentInterfaces(grid, backend, atm, rad, sea_ice=sea_ice, lib=lib, inactive=backend.from_numpy(o["inactive"]),
                              with_iterations=with_iterations, **interface_kwargs)
     ci.ocean_state.u, ci.ocean_state.v = backend.from_numpy(o["u"]), backend.from_numpy(o["v"])
@@ -160,7 +164,7 @@ def ocean_column(grid: ExchangeGrid, backend, nz=10, seed_offset=0):
     rng = np.random.default_rng(BASE_SEED + 1000 + seed_offset)
     shape = (nz,) + grid.shape
     phi = np.deg2rad(grid.phi.astype(np.float64))[None, :, None]
-    T = 28 * np.cos(phi) ** 2 - 1.9 + rng.normal(0, 0.4, shape)
+    T = 28 * np.cos(phi) ** 2 - 3.6 + rng.normal(0, 0.4, shape)   # supercooled at the highest latitudes
     S = 35 + rng.normal(0, 0.6, shape)
     dz = np.linspace(50.0, 5.0, nz)   # k = 1 (bottom) .. nz (top)
     return backend.from_numpy(T.astype(npd)), backend.from_numpy(S.astype(npd)), backend.from_numpy(dz.astype(npd))

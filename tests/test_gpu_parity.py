@@ -1,0 +1,213 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): interpolation indices / weights / interpolated values bit-exact;
+fluxes within 1e-10 relative in Float64 (1e-5 in Float32) at the same iteration count."""
+import numpy as np
+import pytest
+
+import ne_b200
+from numericalearth_jl_b200 import synthetic
+from parity import build_pair, compare_fields, converged_mask
+
+pytestmark = pytest.mark.gpu
+
+F64_TOL = 1e-10
+F32_TOL = 1e-5
+T_STEP = 0.37 * 10800.0
+
+
+def _check_iterations(ref, dev, backend, max_mismatch_rate=2e-4):
+    g = ref.grid
+    ri = g.interior(ref.ao_iterations)
+    di = g.interior(backend.to_numpy(dev.ao_iterations))
+    mism = float((ri != di).mean())
+    assert mism <= max_mismatch_rate, f"iteration-count mismatch rate {mism}"
+    assert np.abs(ri.astype(int) - di.astype(int)).max() <= 1
+    return mism
+
+
+@pytest.mark.parametrize("atm_FT,stretched", [("f64", False), ("f32", False), ("f64", True), ("f32", True)])
+def test_fractional_indices_and_interpolation_bit_exact(oracle_lib, cuda_backend, cuda_lib, atm_FT, stretched):
+    ref, dev = build_pair("C1", oracle_lib, cuda_backend, FT="f64", atm_FT=atm_FT, stretched_latitude=stretched)
+    ref.initialize(); dev.initialize()
+    for t in (0.0, T_STEP, 10800.0, 1.5 * 10800.0):   # ñ = 0, 0.37, exactly on a snapshot (wrap), mid wrap interval
+        ref.interpolate_state(t); dev.interpolate_state(t)
+        cuda_backend.synchronize()
+        for bag_r, bag_d in ((ref.frac, dev.frac), (ref.rad_frac, dev.rad_frac), (ref.atmos_state, dev.atmos_state),
+                             (ref.rad_state, dev.rad_state)):
+            res = compare_fields(bag_r, bag_d, ref.grid, cuda_backend)
+            for n, (_, _, exact) in res.items():
+                assert exact, f"{n} not bit-exact (atm {atm_FT}, stretched={stretched}, t={t})"
+
+
+@pytest.mark.parametrize("config", ["C1", "C2"])
+def test_atmosphere_ocean_fluxes_f64(oracle_lib, cuda_backend, cuda_lib, config):
+    ref, dev = build_pair(config, oracle_lib, cuda_backend, FT="f64", atm_FT="f64")
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP); dev.update_state(T_STEP)
+    cuda_backend.synchronize()
+    res = compare_fields(ref.ao_fluxes, dev.ao_fluxes, ref.grid, cuda_backend)
+    for n, (r, fr, _) in res.items():
+        assert fr <= F64_TOL, f"{n}: field-relative error {fr}"
+    # interface temperature and the net fluxes downstream
+    t = compare_fields(ne_b200.package.interface._Fields(T=ref.ao_temperature), ne_b200.package.interface._Fields(T=dev.ao_temperature),
+                       ref.grid, cuda_backend)
+    assert t["T"][1] <= F64_TOL
+    res = compare_fields(ref.net_ocean, dev.net_ocean, ref.grid, cuda_backend, with_halo_ring=False)
+    for n, (r, fr, _) in res.items():
+        assert fr <= F64_TOL, f"net {n}: {fr}"
+    res = compare_fields(ref.rad_fluxes_ocean, dev.rad_fluxes_ocean, ref.grid, cuda_backend, with_halo_ring=False)
+    for n, (r, fr, _) in res.items():
+        assert fr <= F64_TOL, f"radiative {n}: {fr}"
+    _check_iterations(ref, dev, cuda_backend)
+
+
+def test_atmosphere_ocean_fluxes_jra55_faithful_mixed_precision(oracle_lib, cuda_backend, cuda_lib):
+    """Float64 ocean + Float32 atmosphere: q_sat is evaluated in Float32 (interface_states.jl:56-59)."""
+    ref, dev = build_pair("C1", oracle_lib, cuda_backend, FT="f64", atm_FT="f32")
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP); dev.update_state(T_STEP)
+    cuda_backend.synchronize()
+    res = compare_fields(ref.ao_fluxes, dev.ao_fluxes, ref.grid, cuda_backend)
+    for n, (r, fr, _) in res.items():
+        assert fr <= 2e-6, f"{n}: {fr}"   # Float32 p_sat (powf/expf differ by ulps of Float32 between libms)
+
+
+def test_atmosphere_ocean_fluxes_f32(oracle_lib, cuda_backend, cuda_lib):
+    ref, dev = build_pair("C1", oracle_lib, cuda_backend, FT="f32", atm_FT="f32")
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP); dev.update_state(T_STEP)
+    cuda_backend.synchronize()
+    res = compare_fields(ref.ao_fluxes, dev.ao_fluxes, ref.grid, cuda_backend)
+    for n, (r, fr, _) in res.items():
+        assert fr <= F32_TOL, f"{n}: {fr}"
+
+
+VARIANTS = {
+    "large_yeager_psi": dict(atmosphere_ocean_fluxes=lambda: ne_b200.SimilarityTheoryFluxes(
+        stability_functions=ne_b200.large_yeager_stability_functions())),
+    "fixed_iterations": dict(atmosphere_ocean_fluxes=lambda: ne_b200.SimilarityTheoryFluxes(
+        solver_stop_criteria=ne_b200.FixedIterations(5))),
+    "wind_velocity_coare_profile": dict(
+        atmosphere_ocean_fluxes=lambda: ne_b200.SimilarityTheoryFluxes(similarity_form=ne_b200.COARELogarithmicSimilarityProfile()),
+        atmosphere_ocean_velocity_difference=lambda: ne_b200.WindVelocity()),
+    "wave_formulation_temperature_viscosity": dict(atmosphere_ocean_fluxes=lambda: ne_b200.SimilarityTheoryFluxes(
+        momentum_roughness_length=ne_b200.MomentumRoughnessLength(wave_formulation=ne_b200.WindDependentWaveFormulation(),
+                                                                  air_kinematic_viscosity=ne_b200.TemperatureDependentAirViscosity()),
+        temperature_roughness_length=ne_b200.ScalarRoughnessLength(air_kinematic_viscosity=ne_b200.TemperatureDependentAirViscosity()),
+        water_vapor_roughness_length=ne_b200.ScalarRoughnessLength(air_kinematic_viscosity=ne_b200.TemperatureDependentAirViscosity()))),
+    "constant_roughness_no_gustiness_neutral": dict(atmosphere_ocean_fluxes=lambda: ne_b200.SimilarityTheoryFluxes(
+        stability_functions=None, subgrid_velocities=None, momentum_roughness_length=1e-4,
+        temperature_roughness_length=1e-4, water_vapor_roughness_length=1e-4)),
+    "mesoscale_subgrid_velocity": dict(atmosphere_ocean_fluxes=lambda: ne_b200.SimilarityTheoryFluxes(
+        subgrid_velocities=ne_b200.SubgridVelocityCorrection(mesoscale=ne_b200.mahrt_sun_subgrid_velocity(100e3)))),
+    "skin_temperature_diffusive": dict(
+        atmosphere_ocean_interface_temperature=lambda: ne_b200.SkinTemperature(ne_b200.DiffusiveFlux(1e-2, 1.0))),
+    "salinity_dependent_mole_fraction": dict(
+        atmosphere_ocean_interface_specific_humidity=lambda: ne_b200.ImpureSaturationSpecificHumidity(
+            ne_b200.Liquid(), ne_b200.WaterMoleFraction())),
+    "coefficient_based_constant": dict(atmosphere_ocean_fluxes=lambda: ne_b200.CoefficientBasedFluxes(
+        transfer_coefficients=(1e-2, 1e-3, 1e-3))),
+    "coefficient_based_polynomial_drag": dict(atmosphere_ocean_fluxes=lambda: ne_b200.CoefficientBasedFluxes(
+        transfer_coefficients=(ne_b200.PolynomialNeutralDragCoefficient(), 1.1e-3, 1.2e-3))),
+    "large_yeager_coefficients": dict(atmosphere_ocean_fluxes=lambda: ne_b200.CoefficientBasedFluxes(
+        transfer_coefficients=ne_b200.LargeYeagerTransferCoefficients(), solver_stop_criteria=ne_b200.FixedIterations(5))),
+}
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_atmosphere_ocean_variants(oracle_lib, cuda_backend, cuda_lib, name):
+    kw = {k: v() for k, v in VARIANTS[name].items()}
+    ref, dev = build_pair("C1", oracle_lib, cuda_backend, FT="f64", atm_FT="f64", **kw)
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP); dev.update_state(T_STEP)
+    cuda_backend.synchronize()
+    maxiter = dev.ao_flux_formulation.solver_stop_criteria.maxiter if hasattr(dev.ao_flux_formulation.solver_stop_criteria, "maxiter") else 10**9
+    res = compare_fields(ref.ao_fluxes, dev.ao_fluxes, ref.grid, cuda_backend,
+                         mask=converged_mask(ref.ao_iterations, ref.grid, maxiter, dilate=False))
+    for n, (r, fr, _) in res.items():
+        assert fr <= F64_TOL, f"{name}/{n}: {fr}"
+    _check_iterations(ref, dev, cuda_backend, max_mismatch_rate=1e-3)
+
+
+@pytest.mark.parametrize("asi_temperature", ["conductive", "ice_snow", "bulk"])
+def test_ocean_sea_ice_model_step(oracle_lib, cuda_backend, cuda_lib, asi_temperature):
+    """Config C3: atmosphere-ocean, atmosphere-sea-ice and sea-ice-ocean kernels together."""
+    tf = {"conductive": lambda: ne_b200.SkinTemperature(ne_b200.ConductiveFlux(2.0)),
+          "ice_snow": lambda: ne_b200.SkinTemperature(ne_b200.IceSnowConductiveFlux(0.31, 2.0)),
+          "bulk": lambda: ne_b200.BulkTemperature()}[asi_temperature]
+    ref, dev = build_pair("C1", oracle_lib, cuda_backend, FT="f64", atm_FT="f64", sea_ice=True,
+                          atmosphere_sea_ice_interface_temperature=tf())
+    ref.initialize(); dev.initialize()
+    host = ne_b200.NumpyHostBackend()
+    colr = synthetic.ocean_column(ref.grid, host, nz=10) + (1200.0, 10, 0)
+    cold = synthetic.ocean_column(dev.grid, cuda_backend, nz=10) + (1200.0, 10, 0)
+    ref.update_state(T_STEP, ocean_column=colr); dev.update_state(T_STEP, ocean_column=cold)
+    cuda_backend.synchronize()
+    it = np.maximum(ref.asi_iterations, ref.ao_iterations)
+    for bag_r, bag_d, ring in ((ref.asi_fluxes, dev.asi_fluxes, True), (ref.sio_fluxes, dev.sio_fluxes, False),
+                               (ref.net_sea_ice, dev.net_sea_ice, False), (ref.net_ocean, dev.net_ocean, False),
+                               (ref.rad_fluxes_sea_ice, dev.rad_fluxes_sea_ice, False)):
+        res = compare_fields(bag_r, bag_d, ref.grid, cuda_backend, with_halo_ring=ring,
+                             mask=converged_mask(it, ref.grid, 100, with_halo_ring=ring))
+        for n, (r, fr, _) in res.items():
+            assert fr <= F64_TOL, f"{asi_temperature}/{n}: {fr}"
+        res = compare_fields(bag_r, bag_d, ref.grid, cuda_backend, with_halo_ring=ring)   # incl. limit-cycle points
+        for n, (r, fr, _) in res.items():
+            assert fr <= 1e-3, f"{asi_temperature}/{n} (non-converged points): {fr}"
+    ri, di = ref.grid.interior(ref.asi_iterations), ref.grid.interior(cuda_backend.to_numpy(dev.asi_iterations))
+    assert float((ri != di).mean()) <= 1e-3
+    # frazil clamp: the whole T column is bit-exact (pure compare/select)
+    assert np.array_equal(colr[0], cuda_backend.to_numpy(cold[0]))
+    Ts_r, Ts_d = ref.sea_ice_state.top_temperature, cuda_backend.to_numpy(dev.sea_ice_state.top_temperature)
+    m = converged_mask(it, ref.grid, 100)
+    assert np.nanmax(np.abs(ref.grid.interior(Ts_r) - ref.grid.interior(Ts_d))[m]) <= 1e-8
+
+
+def test_fused_interface_step_matches_unfused(oracle_lib, cuda_backend, cuda_lib):
+    ref, dev = build_pair("C1", oracle_lib, cuda_backend, FT="f64", atm_FT="f64")
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP); dev.fused_interface_step(T_STEP)
+    cuda_backend.synchronize()
+    for bag_r, bag_d, ring in ((ref.ao_fluxes, dev.ao_fluxes, True), (ref.net_ocean, dev.net_ocean, False)):
+        res = compare_fields(bag_r, bag_d, ref.grid, cuda_backend, with_halo_ring=ring)
+        for n, (r, fr, _) in res.items():
+            assert fr <= F64_TOL, f"{n}: {fr}"
+
+
+def test_no_kernel_variant_raises(cuda_backend, cuda_lib):
+    with pytest.raises(ne_b200.NoKernelVariantError):
+        ne_b200.SimilarityTheoryFluxes(momentum_roughness_length=lambda u: 1e-4).pod()
+    # the library itself refuses an unknown kind as well (no CPU fallback anywhere)
+    dev = synthetic.build_case("tiny", cuda_backend)
+    d = dev.atmosphere_ocean_desc()
+    d.flux.psi_momentum.a.kind = 99
+    with pytest.raises(ne_b200.NoKernelVariantError):
+        cuda_lib.call("atmosphere_ocean_fluxes", "f64", d, cuda_backend.stream())
+
+
+def test_full_size_properties_C4(cuda_backend, cuda_lib):
+    """BASELINE 1/12° size: size-independent properties (no oracle at this size).
+    (i) masked points are exactly zero / 0 °C; (ii) u★ ≥ 0, τ opposes Δu; (iii) the fixed point is
+    reproduced: re-running is idempotent bit-for-bit; (iv) iteration counts within [1, maxiter]."""
+    dev = synthetic.build_case("C4", cuda_backend, FT="f64", atm_FT="f32", with_iterations=True)
+    dev.initialize()
+    dev.update_state(T_STEP)
+    cuda_backend.synchronize()
+    g = dev.grid
+    to = cuda_backend.to_numpy
+    inactive = g.interior(to(dev.inactive)).astype(bool)
+    for n in dev.ao_fluxes.names():
+        a = g.interior(to(getattr(dev.ao_fluxes, n)))
+        assert np.isfinite(a).all(), n
+        assert (a[inactive] == 0).all(), n
+    assert (g.interior(to(dev.ao_temperature))[inactive] == 0).all()
+    us = g.interior(to(dev.ao_fluxes.friction_velocity))
+    assert (us >= 0).all() and (us[~inactive] > 0).all()
+    it = g.interior(to(dev.ao_iterations))
+    assert it[~inactive].min() >= 1 and it.max() <= 100 and (it[inactive] == 0).all()
+    first = {n: to(getattr(dev.ao_fluxes, n)).copy() for n in dev.ao_fluxes.names()}
+    dev.update_state(T_STEP)
+    cuda_backend.synchronize()
+    for n, a in first.items():
+        assert np.array_equal(a, to(getattr(dev.ao_fluxes, n))), n
