@@ -20,6 +20,10 @@ OBJ = os.path.join(HERE, "_obj")
 SOURCES = {
     "ne_api.cu": [],
     "ne_flux_kernels.cu": [],
+    "ne_flux_generic_ao_f64.cu": [],
+    "ne_flux_generic_ao_f32.cu": [],
+    "ne_flux_generic_asi_f64.cu": [],
+    "ne_flux_generic_asi_f32.cu": [],
     "ne_interp_kernels.cu": ["-fmad=false"],
     "ne_surface_kernels.cu": ["-fmad=false"],
     "ne_fused.cu": [],
@@ -27,6 +31,14 @@ SOURCES = {
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
           "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 DEPS = ["ne_common.cuh", "ne_physics.cuh", os.path.join("..", "..", "include", "ne_b200.h")]
+EXTRA_DEPS = {
+    "ne_flux_kernels.cu": ["ne_flux_fast.cuh"],
+    "ne_flux_generic_ao_f64.cu": ["ne_flux_generic.cuh"],
+    "ne_flux_generic_ao_f32.cu": ["ne_flux_generic.cuh"],
+    "ne_flux_generic_asi_f64.cu": ["ne_flux_generic.cuh"],
+    "ne_flux_generic_asi_f32.cu": ["ne_flux_generic.cuh"],
+    "ne_fused.cu": ["ne_flux_fast.cuh"],
+}
 
 
 def _nvcc():
@@ -46,14 +58,14 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
-    deps = [os.path.join(HERE, d) for d in DEPS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(HERE, d) for d in DEPS]
     jobs = []
     objs = []
     for src, extra in SOURCES.items():
         s = os.path.join(HERE, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
-        if force or _stale(o, [s] + deps):
+        if force or _stale(o, [s] + deps + [os.path.join(HERE, d) for d in EXTRA_DEPS.get(src, [])]):
             jobs.append((src, [nvcc] + COMMON + extra + ["-c", s, "-o", o]))
 
     def run(job):

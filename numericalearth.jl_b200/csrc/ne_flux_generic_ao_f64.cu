@@ -1,0 +1,7 @@
+// ne_flux_generic_ao_f64.cu — explicit instantiations of the generic flux kernels (see ne_flux_generic.cuh).
+#include "ne_flux_generic.cuh"
+
+namespace ne {
+template int launch_ao<double, double, double>(const NeAtmosOceanDesc&, cudaStream_t);
+template int launch_ao<double, float, double>(const NeAtmosOceanDesc&, cudaStream_t);
+}  // namespace ne

@@ -282,4 +282,23 @@ __device__ __forceinline__ RadState<FT> radiation_state(const NeSurfaceRadiation
   return s;
 }
 
+template <class FT, class CT>
+struct FluxEpilogue {
+  FT Qv, Qc, Jv, tx, ty;
+  __device__ __forceinline__ FluxEpilogue(const Thermo<CT>& th, const AtmosState<FT>& a, FT ustar, FT theta_star,
+                                          FT q_star, FT du, FT dv, bool ice) {
+    FT dU = m_sqrt(sq(du) + sq(dv));
+    FT taux = (dU == 0) ? (FT)0 : -sq(ustar) * du / dU;
+    FT tauy = (dU == 0) ? (FT)0 : -sq(ustar) * dv / dU;
+    auto rho_a = th.air_density(a.T, a.p, a.q);
+    auto cpm = th.cp_m(a.q);
+    if (ice) Qv = (FT)(-rho_a * ustar * q_star * th.latent_heat_sublim(a.T));  // atmosphere_sea_ice_fluxes.jl:178
+    else Qv = (FT)(-rho_a * th.latent_heat_vapor(a.T) * ustar * q_star);       // atmosphere_ocean_fluxes.jl:186
+    Qc = (FT)(-rho_a * cpm * ustar * theta_star);
+    Jv = (FT)(-rho_a * ustar * q_star);
+    tx = (FT)(rho_a * taux);
+    ty = (FT)(rho_a * tauy);
+  }
+};
+
 }  // namespace ne

@@ -110,8 +110,8 @@ sea_ice_ocean_stress_kernel(const __grid_constant__ NeSeaIceOceanStressDesc d, c
   const FT* uo = (const FT*)d.uo; const FT* vo = (const FT*)d.vo;
   const FT rho = (FT)d.ocean_density, Cd = (FT)d.drag_coefficient;
   const int64_t sx = L.sx;
-  auto dvv = [&](int64_t a) { return __ldg(vi + a) - __ldg(vo + a); };
-  auto duu = [&](int64_t a) { return __ldg(ui + a) - __ldg(uo + a); };
+  auto dvv = [&](int64_t a) { return __ldg(vo + a) - __ldg(vi + a); };  // Δu = uₑ − uᵢ (test/test_surface_fluxes.jl:334-335)
+  auto duu = [&](int64_t a) { return __ldg(uo + a) - __ldg(ui + a); };
   FT du = duu(idx);
   FT dv4 = (dvv(idx) + dvv(idx - 1) + dvv(idx + sx) + dvv(idx - 1 + sx)) / 4;
   ((FT*)d.x_momentum)[idx] = rho * Cd * m_sqrt(sq(du) + sq(dv4)) * du;

@@ -862,7 +862,7 @@ void sea_ice_ocean(const NeSeaIceOceanDesc& d) {
 }
 
 // _compute_sea_ice_ocean_stress! with [3rd-party ClimaSeaIce SemiImplicitStress]:
-// tau_x at (Face,Center): rho Cd |Δu| (ui - uo) with v averaged to the u point, and vice versa.
+// tau_x at (Face,Center): rho Cd |Δu| (uo - ui) with v averaged to the u point, and vice versa.
 template <class FT>
 void sea_ice_ocean_stress(const NeSeaIceOceanStressDesc& d) {
   const Layout L(d.grid);
@@ -874,13 +874,13 @@ void sea_ice_ocean_stress(const NeSeaIceOceanStressDesc& d) {
     for (int64_t i = d.grid.i_lo; i <= d.grid.i_hi; ++i) {
       const int64_t idx = L.at(i, j);
       // x-stress at (f, c): Δu local, Δv = ℑxyᶠᶜᵃ(vi - vo)
-      FT du = ui[idx] - uo[idx];
-      FT dv4 = ((vi[idx] - vo[idx]) + (vi[idx - 1] - vo[idx - 1]) + (vi[idx + L.sx] - vo[idx + L.sx]) +
-                (vi[idx - 1 + L.sx] - vo[idx - 1 + L.sx])) / 4;
+      FT du = uo[idx] - ui[idx];   // Δu = uₑ − uᵢ (sign pinned by test/test_surface_fluxes.jl:334-335)
+      FT dv4 = ((vo[idx] - vi[idx]) + (vo[idx - 1] - vi[idx - 1]) + (vo[idx + L.sx] - vi[idx + L.sx]) +
+                (vo[idx - 1 + L.sx] - vi[idx - 1 + L.sx])) / 4;
       ((FT*)d.x_momentum)[idx] = rho * Cd * m_sqrt(sq(du) + sq(dv4)) * du;
-      FT dv = vi[idx] - vo[idx];
-      FT du4 = ((ui[idx] - uo[idx]) + (ui[idx + 1] - uo[idx + 1]) + (ui[idx - L.sx] - uo[idx - L.sx]) +
-                (ui[idx + 1 - L.sx] - uo[idx + 1 - L.sx])) / 4;
+      FT dv = vo[idx] - vi[idx];
+      FT du4 = ((uo[idx] - ui[idx]) + (uo[idx + 1] - ui[idx + 1]) + (uo[idx - L.sx] - ui[idx - L.sx]) +
+                (uo[idx + 1 - L.sx] - ui[idx + 1 - L.sx])) / 4;
       ((FT*)d.y_momentum)[idx] = rho * Cd * m_sqrt(sq(du4) + sq(dv)) * dv;
     }
 }

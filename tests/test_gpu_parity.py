@@ -62,6 +62,41 @@ def test_atmosphere_ocean_fluxes_f64(oracle_lib, cuda_backend, cuda_lib, config)
     _check_iterations(ref, dev, cuda_backend)
 
 
+def test_generic_kernel_on_default_tree(oracle_lib, cuda_backend, cuda_lib, monkeypatch):
+    """The default plugin tree normally takes the specialised kernel; NE_B200_FORCE_GENERIC routes it
+    through the generic variant kernel, which must agree with the oracle as well."""
+    monkeypatch.setenv("NE_B200_FORCE_GENERIC", "1")
+    ref, dev = build_pair("C1", oracle_lib, cuda_backend, FT="f64", atm_FT="f64")
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP); dev.update_state(T_STEP)
+    cuda_backend.synchronize()
+    res = compare_fields(ref.ao_fluxes, dev.ao_fluxes, ref.grid, cuda_backend)
+    for n, (r, fr, _) in res.items():
+        assert fr <= F64_TOL, f"{n}: {fr}"
+    _check_iterations(ref, dev, cuda_backend)
+
+
+def test_sea_ice_ocean_stress_known_answer(cuda_backend, cuda_lib):
+    """test/test_surface_fluxes.jl:294-336: ocean (0.1, 0.2), ice at rest, Cᴰ=1e-3, ρₑ=1000
+    => τˣ == sqrt(0.1²+0.2²)·0.1, τʸ == sqrt(0.1²+0.2²)·0.2 (exact)."""
+    import ctypes
+    A = ne_b200.abi
+    g = ne_b200.ExchangeGrid(nx=4, ny=4, hx=2, hy=2)
+    b = cuda_backend
+    uo, vo = b.from_numpy(np.full(g.shape, 0.1)), b.from_numpy(np.full(g.shape, 0.2))
+    ui, vi = b.zeros(g.shape, "f64"), b.zeros(g.shape, "f64")
+    tx, ty = b.zeros(g.shape, "f64"), b.zeros(g.shape, "f64")
+    d = A.NeSeaIceOceanStressDesc()
+    d.grid = g.pod(True)
+    d.ui, d.vi, d.uo, d.vo = b.ptr(ui), b.ptr(vi), b.ptr(uo), b.ptr(vo)
+    d.ocean_density, d.drag_coefficient = 1000.0, 0.001
+    d.x_momentum, d.y_momentum = b.ptr(tx), b.ptr(ty)
+    cuda_lib.call("sea_ice_ocean_stress", "f64", d, b.stream())
+    b.synchronize()
+    assert (g.interior(b.to_numpy(tx)) == np.sqrt(0.1 ** 2 + 0.2 ** 2) * 0.1).all()
+    assert (g.interior(b.to_numpy(ty)) == np.sqrt(0.1 ** 2 + 0.2 ** 2) * 0.2).all()
+
+
 def test_atmosphere_ocean_fluxes_jra55_faithful_mixed_precision(oracle_lib, cuda_backend, cuda_lib):
     """Float64 ocean + Float32 atmosphere: q_sat is evaluated in Float32 (interface_states.jl:56-59)."""
     ref, dev = build_pair("C1", oracle_lib, cuda_backend, FT="f64", atm_FT="f32")
