@@ -26,8 +26,8 @@ template <class FT, class CT, class VT> int launch_ao(const NeAtmosOceanDesc& d,
 template <class FT, class CT, class VT> int launch_asi(const NeAtmosSeaIceDesc& d, cudaStream_t stream);
 
 // ---- atmosphere–ocean kernel, default plugin tree (Float64), see ne_flux_fast.cuh --------------------
-template <class CT>
-__global__ void __launch_bounds__(128, 4)
+template <class CT, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 ao_flux_fast_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_constant__ Layout L,
                     const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,8 +173,18 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
       Layout L = make_layout(d->grid);
       FastParams P = make_fast_params(d->flux, d->gravitational_acceleration);
       const int64_t n = (int64_t)L.ni * L.nj;
-      if (ct64) ao_flux_fast_kernel<double><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(*d, L, Thermo<double>::make(d->thermo), P);
-      else ao_flux_fast_kernel<float><<<(unsigned)((n + 127) / 128), 128, 0, s>>>(*d, L, Thermo<float>::make(d->thermo), P);
+      const char* mb = std::getenv("NE_B200_FAST_MINB");   // occupancy experiment knob
+      const int minb = mb ? std::atoi(mb) : 8;   // 64 registers/thread measured fastest on B200 (profiles/r01_notes.md)
+      const unsigned nb = (unsigned)((n + 127) / 128);
+#define NE_LAUNCH_FAST(MB)                                                                                   \
+  do {                                                                                                       \
+    if (ct64) ao_flux_fast_kernel<double, MB><<<nb, 128, 0, s>>>(*d, L, Thermo<double>::make(d->thermo), P); \
+    else ao_flux_fast_kernel<float, MB><<<nb, 128, 0, s>>>(*d, L, Thermo<float>::make(d->thermo), P);        \
+  } while (0)
+      if (minb == 4) NE_LAUNCH_FAST(4);
+      else if (minb == 6) NE_LAUNCH_FAST(6);
+      else NE_LAUNCH_FAST(8);
+#undef NE_LAUNCH_FAST
       NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(fast)");
       return NE_OK;
     }
