@@ -1,0 +1,47 @@
+"""Oracle (CPU) and CUDA path (GPU) against the committed golden fixtures of tests/golden/."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+import ne_b200
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+make_golden = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(make_golden)
+
+
+def _check(got, ref, exact_prefixes, tol):
+    for k in ref.files:
+        a, b = got[k], ref[k]
+        if any(k.startswith(p) for p in exact_prefixes) or b.dtype.kind in "iu":
+            if k.endswith("iterations"):
+                assert float((a != b).mean()) <= 2e-3, k
+            else:
+                assert np.array_equal(a, b), f"{k} not bit-exact"
+        else:
+            s = float(np.max(np.abs(b))) or 1.0
+            assert float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))) / s <= tol, k
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.CASES))
+def test_oracle_reproduces_golden_bit_for_bit(oracle_lib, host_backend, name):
+    ref = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    ci, col = make_golden.run_case(oracle_lib, host_backend, make_golden.CASES[name])
+    got = make_golden.collect(ci, col, np.asarray)
+    for k in ref.files:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(make_golden.CASES))
+def test_cuda_path_matches_golden(cuda_backend, cuda_lib, name):
+    ref = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    kw = make_golden.CASES[name]
+    ci, col = make_golden.run_case(None, cuda_backend, kw)
+    cuda_backend.synchronize()
+    got = make_golden.collect(ci, col, cuda_backend.to_numpy)
+    tol = 1e-10 if kw["FT"] == "f64" and kw["atm_FT"] == "f64" else (2e-6 if kw["FT"] == "f64" else 1e-5)
+    _check(got, ref, exact_prefixes=("frac.", "atmos.", "rad.", "column."), tol=tol)
