@@ -13,12 +13,15 @@ make_golden = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(make_golden)
 
 
-def _check(got, ref, exact_prefixes, tol):
+def _check(got, ref, exact_prefixes, tol, check_iterations=True):
     for k in ref.files:
         a, b = got[k], ref[k]
         if any(k.startswith(p) for p in exact_prefixes) or b.dtype.kind in "iu":
             if k.endswith("iterations"):
-                assert float((a != b).mean()) <= 2e-3, k
+                # Float32 models: tol = 1e-8 is below eps(Float32), so the loop stops when the rounded
+                # iterate stops changing — the trip count then depends on last-bit libm differences.
+                if check_iterations:
+                    assert float((a != b).mean()) <= 2e-3, k
             else:
                 assert np.array_equal(a, b), f"{k} not bit-exact"
         else:
@@ -44,4 +47,4 @@ def test_cuda_path_matches_golden(cuda_backend, cuda_lib, name):
     cuda_backend.synchronize()
     got = make_golden.collect(ci, col, cuda_backend.to_numpy)
     tol = 1e-10 if kw["FT"] == "f64" and kw["atm_FT"] == "f64" else (2e-6 if kw["FT"] == "f64" else 1e-5)
-    _check(got, ref, exact_prefixes=("frac.", "atmos.", "rad.", "column."), tol=tol)
+    _check(got, ref, exact_prefixes=("frac.", "atmos.", "rad.", "column."), tol=tol, check_iterations=kw["FT"] == "f64")
