@@ -16,7 +16,11 @@
 //   * B⁻ = 2 (the only value the reference ships) merges two logs of the unstable momentum ψ.
 #pragma once
 
+#include <cstdlib>
+
 #include "ne_physics.cuh"
+
+#define NE_FAST_PSI_DEG 12
 
 namespace ne {
 
@@ -33,6 +37,10 @@ struct FastParams {
   double kappa, d_zero, g;
   double tol;
   int32_t maxiter, fixed;
+  // small-|ζ| unstable branch: ψ(ζ) ≈ Σ c_k (ζ/ζs)^k on [-ζs, 0], fitted on the host at Chebyshev nodes in
+  // long double from the closed forms (max abs error ≲ 2e-16, checked at fit time; zsmall = 0 disables it)
+  double zsmall, zsmall_inv;
+  double pm[NE_FAST_PSI_DEG + 1], ps[NE_FAST_PSI_DEG + 1];
 };
 
 inline bool fast_path_eligible(const NeFluxFormulation& f, const NeInterfaceProperties& ip, const NeThermoParams& th) {
@@ -55,6 +63,74 @@ inline bool fast_path_eligible(const NeFluxFormulation& f, const NeInterfaceProp
   const double* ps = f.psi_temperature.a.p;
   if (!(pm[9] > 0) || !(ps[10] > 0) || !(ps[7] > 0) || !(pm[6] > 0)) return false;  // E⁻, B⁻ > 0
   return true;
+}
+
+// ---- host: closed forms in long double and the Chebyshev fit of the small-|ζ| unstable branch -------------
+inline long double psi_m_unstable_ld(const double* p, long double z) {
+  const long double Am = p[5], Bm = p[6], Cm = p[7], Dm = p[8], Em = p[9], Fm = p[10];
+  const long double f1 = sqrtl(sqrtl(1 - Am * z));
+  const long double psi1 = Bm * logl((1 + f1) / Bm) + logl((1 + f1 * f1) / Bm) - Bm * atanl(f1) + Cm;
+  const long double f2 = cbrtl(1 - Dm * z);
+  const long double psi2 = Em / 2 * logl((1 + f2 + f2 * f2) / Em) - sqrtl(Em) * atanl((1 + 2 * f2) / sqrtl(Em)) + Fm;
+  const long double fw = z * z / (1 + z * z);
+  return (1 - fw) * psi1 + fw * psi2;
+}
+inline long double psi_s_unstable_ld(const double* p, long double z) {
+  const long double Am = p[6], Bm = p[7], Cm = p[8], Dm = p[9], Em = p[10], Fm = p[11];
+  const long double f1 = sqrtl(1 - Am * z);
+  const long double psi1 = Bm * logl((1 + f1) / Bm) + Cm;
+  const long double f2 = cbrtl(1 - Dm * z);
+  const long double psi2 = Em / 2 * logl((1 + f2 + f2 * f2) / Em) - sqrtl(Em) * atanl((1 + 2 * f2) / sqrtl(Em)) + Fm;
+  const long double fw = z * z / (1 + z * z);
+  return (1 - fw) * psi1 + fw * psi2;
+}
+
+// Interpolate f(w·zs), w ∈ [-1, 0], at the N = DEG+1 Chebyshev nodes and convert to monomials in w (long double).
+// Returns the max abs error of the double-precision Horner evaluation against the long-double closed form.
+template <class F>
+inline double fit_small_zeta(F f, double zs, double* coef) {
+  constexpr int N = NE_FAST_PSI_DEG + 1;
+  const long double PI = 3.141592653589793238462643383279502884L;
+  long double y[N], c[N];
+  for (int k = 0; k < N; ++k) {
+    const long double x = cosl(PI * (2 * k + 1) / (2 * N));
+    y[k] = f((x - 1) / 2 * (long double)zs);
+  }
+  for (int j = 0; j < N; ++j) {
+    long double a = 0;
+    for (int k = 0; k < N; ++k) a += y[k] * cosl(PI * j * (2 * k + 1) / (2 * N));
+    c[j] = a * 2 / N;
+  }
+  c[0] /= 2;
+  // Chebyshev -> monomial in x
+  long double T0[N] = {0}, T1[N] = {0}, T2[N], px[N] = {0};
+  T0[0] = 1; T1[1] = 1;
+  px[0] += c[0];
+  for (int m = 0; m < N; ++m) px[m] += c[1] * T1[m];
+  for (int j = 2; j < N; ++j) {
+    for (int m = 0; m < N; ++m) T2[m] = (m > 0 ? 2 * T1[m - 1] : 0) - T0[m];
+    for (int m = 0; m < N; ++m) { px[m] += c[j] * T2[m]; T0[m] = T1[m]; T1[m] = T2[m]; }
+  }
+  // x = 2w + 1
+  long double pw[N] = {0};
+  for (int m = 0; m < N; ++m) {
+    long double binom = 1;   // C(m, r)
+    for (int r = 0; r <= m; ++r) {
+      pw[r] += px[m] * binom * powl(2.0L, r);
+      binom = binom * (m - r) / (r + 1);
+    }
+  }
+  for (int m = 0; m < N; ++m) coef[m] = (double)pw[m];
+  double err = 0;
+  for (int i = 0; i <= 4000; ++i) {
+    const double w = -((double)i / 4000.0) * ((double)i / 4000.0);   // denser near 0
+    double r = coef[N - 1];
+    for (int m = N - 2; m >= 0; --m) r = r * w + coef[m];
+    const long double t = f((long double)w * (long double)zs);
+    const double e = (double)fabsl((long double)r - t);
+    if (e > err) err = e;
+  }
+  return err;
 }
 
 inline FastParams make_fast_params(const NeFluxFormulation& f, double g) {
@@ -81,12 +157,50 @@ inline FastParams make_fast_params(const NeFluxFormulation& f, double g) {
   P.beta = f.subgrid_velocities.gustiness_parameter; P.gmin = f.subgrid_velocities.minimum_gustiness;
   P.kappa = f.von_karman_constant; P.d_zero = f.zero_plane_displacement; P.g = g;
   P.tol = f.stop.tolerance; P.maxiter = f.stop.maxiter; P.fixed = f.stop.kind == NE_STOP_FIXED_ITERATIONS;
+  // small-|ζ| polynomials (ψ(ℓ/L★) always lands here: |ℓ/L★| ≲ 1e-3), cached per parameter set
+  static thread_local double cache_key[24];
+  static thread_local double cache_val[2 * (NE_FAST_PSI_DEG + 1) + 1];
+  static thread_local bool cache_ok = false;
+  const char* off = std::getenv("NE_B200_NO_SMALL_ZETA_POLY");
+  const bool disabled = off && off[0] == '1';
+  double key[24];
+  for (int k = 0; k < 12; ++k) { key[k] = p[k]; key[12 + k] = q[k]; }
+  if (disabled) {
+    P.zsmall = 0; P.zsmall_inv = 0;
+    for (int k = 0; k <= NE_FAST_PSI_DEG; ++k) { P.pm[k] = 0; P.ps[k] = 0; }
+    return P;
+  }
+  if (!(cache_ok && std::memcmp(key, cache_key, sizeof(key)) == 0)) {
+    double zs = 1.0 / 64;
+    while (zs > 1e-6) {
+      const double em = fit_small_zeta([&](long double z) { return psi_m_unstable_ld(p, z); }, zs, cache_val);
+      const double es = fit_small_zeta([&](long double z) { return psi_s_unstable_ld(q, z); }, zs, cache_val + NE_FAST_PSI_DEG + 1);
+      if (em <= 4e-16 && es <= 4e-16) break;
+      zs *= 0.5;
+    }
+    if (!(zs > 1e-6)) zs = 0;
+    cache_val[2 * (NE_FAST_PSI_DEG + 1)] = zs;
+    std::memcpy(cache_key, key, sizeof(key));
+    cache_ok = true;
+  }
+  for (int k = 0; k <= NE_FAST_PSI_DEG; ++k) { P.pm[k] = cache_val[k]; P.ps[k] = cache_val[NE_FAST_PSI_DEG + 1 + k]; }
+  P.zsmall = cache_val[2 * (NE_FAST_PSI_DEG + 1)];
+  P.zsmall_inv = P.zsmall > 0 ? 1.0 / P.zsmall : 0.0;
   return P;
+
 }
 
 // ψ_m(ζ), Edson et al. (2013) — similarity_theory_turbulent_fluxes.jl:501-532
+__device__ __forceinline__ double fast_psi_poly(const double* c, double w) {
+  double r = c[NE_FAST_PSI_DEG];
+#pragma unroll
+  for (int m = NE_FAST_PSI_DEG - 1; m >= 0; --m) r = fma(r, w, c[m]);
+  return r;
+}
+
 __device__ __forceinline__ double fast_psi_m(const FastParams& P, double z) {
   if (z < 0) {
+    if (z >= -P.zsmall) return fast_psi_poly(P.pm, z * P.zsmall_inv);
     const double f1 = sqrt(sqrt(1.0 - P.m_Am * z));
     const double f1s = f1 * f1;
     double psi1;
@@ -105,6 +219,7 @@ __device__ __forceinline__ double fast_psi_m(const FastParams& P, double z) {
 // ψ_s(ζ) — :586-618
 __device__ __forceinline__ double fast_psi_s(const FastParams& P, double z) {
   if (z < 0) {
+    if (z >= -P.zsmall) return fast_psi_poly(P.ps, z * P.zsmall_inv);
     const double f1 = sqrt(1.0 - P.s_Am * z);
     const double psi1 = P.s_Bm * log((1.0 + f1) * P.s_iBm) + P.s_Cm;
     const double f2 = cbrt(1.0 - P.s_Dm * z);
