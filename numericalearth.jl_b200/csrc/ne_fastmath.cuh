@@ -1,0 +1,212 @@
+// ne_fastmath.cuh — branch-free Float64 elementary functions and the piecewise-polynomial ψ tables
+// of the specialised a–o solve (ne_flux_fast.cuh).
+//
+// Why: ncu on the libdevice-based solve (profiles/r01_notes.md, "v2") shows only 37 % of the issued
+// instructions are FP64 arithmetic; 32 % are UMOV/IMAD/MOV that materialise libdevice's 64-bit
+// polynomial constants and 8 % are the special-case branches of log/exp/cbrt/atan.  The functions
+// below take their coefficients from the kernel-parameter constant bank (direct c[][] operands),
+// assume the argument ranges the solve guarantees (positive, normal), and are accurate to ≲ 2 ulp —
+// NOT fast-math: no approximate-only MUFU result is ever returned, every seed is refined to full
+// double precision by Newton steps.  The same code compiles on the host (seeds emulated in Float32)
+// so tests/test_fastmath.py checks every function against long double without a GPU.
+//
+// ψ tables: the Edson et al. (2013) stability functions (similarity_theory_turbulent_fluxes.jl:501-532,
+// 586-618) are smooth on ζ < 0; on quarter-octave intervals 2^-6 ≤ |ζ| < 2^7 (plus one interval
+// [−2^-6, 0) and one [0, 2^-6) for the stable side) they are replaced by degree-13 polynomials
+// interpolated at Chebyshev nodes from the closed forms evaluated in long double; the fit is
+// verified on the host at build time (max abs error ≤ 1e-15 required, else the closed-form kernel
+// is used).  ψ_m and ψ_s coefficients are interleaved so one 16-byte load feeds both Horner chains.
+#pragma once
+
+#include <stdint.h>
+
+#include <cmath>
+#include <cstring>
+
+#if defined(__CUDACC__)
+#define NE_HD __host__ __device__ __forceinline__
+#else
+#define NE_HD inline
+#endif
+
+namespace ne {
+namespace fm {
+
+constexpr int LOG_N = 64;       // log table entries (invc, logc)
+constexpr int LOG_DEG = 6;      // log1p(r) = r + r²·P(r), P has LOG_DEG coefficients (|r| ≤ 2^-7)
+constexpr int EXP_DEG = 11;     // e^r on |r| ≤ ln2/2
+constexpr int PSI_DEG = 13;
+constexpr int PSI_OCT_LO = -6;  // table covers 2^-6 ≤ |ζ| < 2^7 on the unstable side
+constexpr int PSI_OCT_HI = 7;
+constexpr int PSI_NQ = 4 * (PSI_OCT_HI - PSI_OCT_LO);  // quarter-octave intervals
+constexpr int PSI_NI = PSI_NQ + 2;                     // + [−2^-6, 0) (index 0) + [0, 2^-6) (index NQ+1)
+constexpr int PSI_REC = 2 + 2 * (PSI_DEG + 1);         // (a, b) of w = a|ζ| + b, then (c_m, c_s) pairs
+constexpr int TAB_LOG = 0;
+constexpr int TAB_PSI = 2 * LOG_N;
+constexpr int TAB_SIZE = TAB_PSI + PSI_NI * PSI_REC;   // doubles (1748 = 13 984 B)
+
+struct MathConsts {
+  double logp[LOG_DEG];      // P(r) = Σ logp[k] r^k
+  double expp[EXP_DEG + 1];  // e^r ≈ Σ expp[k] r^k
+};
+
+// ---- bit access -----------------------------------------------------------------------------------
+NE_HD int32_t hi32(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(x);
+#else
+  int64_t b; std::memcpy(&b, &x, 8); return (int32_t)(b >> 32);
+#endif
+}
+NE_HD int32_t lo32(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2loint(x);
+#else
+  int64_t b; std::memcpy(&b, &x, 8); return (int32_t)(b & 0xffffffffLL);
+#endif
+}
+NE_HD double mk64(int32_t hi, int32_t lo) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(hi, lo);
+#else
+  int64_t b = ((int64_t)hi << 32) | (int64_t)(uint32_t)lo; double x; std::memcpy(&x, &b, 8); return x;
+#endif
+}
+NE_HD double fma_(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return std::fma(a, b, c);
+#endif
+}
+
+// ---- seeds (≈ 20 bits on the device; the host emulation rounds to Float32) ------------------------
+NE_HD double rcp_seed(double x) {
+#if defined(__CUDA_ARCH__)
+  double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); return r;
+#else
+  return (double)(1.0f / (float)x) * (1.0 + 3e-7);
+#endif
+}
+NE_HD double rsqrt_seed(double x) {
+#if defined(__CUDA_ARCH__)
+  double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); return r;
+#else
+  return (double)(1.0f / std::sqrt((float)x)) * (1.0 - 3e-7);
+#endif
+}
+
+// 1/x, x finite, normal, non-zero (either sign): seed + two Newton steps
+NE_HD double rcp(double x) {
+  double r = rcp_seed(x);
+  double e = fma_(-x, r, 1.0);
+  r = fma_(r, e, r);
+  e = fma_(-x, r, 1.0);
+  return fma_(r, e, r);
+}
+// a/b with one residual correction (≲ 1 ulp)
+NE_HD double div(double a, double b) {
+  const double r = rcp(b);
+  const double q = a * r;
+  return fma_(fma_(-b, q, a), r, q);
+}
+// sqrt(x), x > 0 normal: coupled Goldschmidt iteration + residual correction
+NE_HD double sqrt_pos(double x) {
+  const double r = rsqrt_seed(x);
+  double g = x * r, h = 0.5 * r;
+  double e = fma_(-h, g, 0.5);
+  g = fma_(g, e, g); h = fma_(h, e, h);
+  e = fma_(-h, g, 0.5);
+  g = fma_(g, e, g); h = fma_(h, e, h);
+  return fma_(fma_(-g, g, x), h, g);
+}
+// cbrt(x), x > 0 normal.  x = 2^(3q)·m with m ∈ [1, 8): seed m^(-1/3) in Float32 (MUFU lg2/ex2 on the
+// device), two Newton steps on r ↦ r + r(1 − m r³)/3, result m·r²·2^q.
+NE_HD double cbrt_pos(double x) {
+  const int32_t hi = hi32(x);
+  const int32_t e = (hi >> 20) - 1023;                 // unbiased exponent
+  const int32_t q = (e + 3072) * 21846 >> 16;          // floor((e + 3072)/3), exact for |e| ≤ 1100
+  const int32_t q3 = q - 1024;                         // floor(e/3)
+  const double m = mk64(hi - ((3 * q3) << 20), lo32(x));  // [1, 8)
+#if defined(__CUDA_ARCH__)
+  double r = (double)exp2f(-0.333333333f * __log2f((float)m));
+#else
+  double r = (double)(float)std::exp2(-std::log2((float)m) / 3.0f) * (1.0 + 4e-7);
+#endif
+  const double third = 0.33333333333333333;
+  double r2 = r * r;
+  double e1 = fma_(-m * r, r2, 1.0);
+  r = fma_(r * third, e1, r);
+  r2 = r * r;
+  e1 = fma_(-m * r, r2, 1.0);
+  r = fma_(r * third, e1, r);
+  double y = (m * r) * r;                              // m^(1/3) ∈ [1, 2)
+  // one residual step on y: y ← y − (y³ − m)/(3y²) = y + (m − y³)·r²/3  (r ≈ 1/y)
+  const double y2 = y * y;
+  y = fma_(fma_(-y2, y, m), (r * r) * third, y);
+  return mk64(hi32(y) + (q3 << 20), lo32(y));
+}
+
+// log(x), x > 0 normal.  x = 2^k z, z ∈ [√½, √2); z = c_i(1 + r), |r| ≤ 2^-7; table holds 1/c_i and log c_i.
+NE_HD double log_pos(const double* __restrict__ tab, const MathConsts& C, double x) {
+  const int32_t hi = hi32(x);
+  const int32_t tmp = hi - 0x3fe6a09e;
+  const int32_t k = tmp >> 20;
+  const int32_t i = (tmp >> 14) & (LOG_N - 1);
+  const double z = mk64(hi - (k << 20), lo32(x));
+  const double invc = tab[TAB_LOG + 2 * i], logc = tab[TAB_LOG + 2 * i + 1];
+  const double r = fma_(z, invc, -1.0);
+  double p = C.logp[LOG_DEG - 1];
+#pragma unroll
+  for (int n = LOG_DEG - 2; n >= 0; --n) p = fma_(p, r, C.logp[n]);
+  const double r2 = r * r;
+  const double base = fma_((double)k, 0.693147180559945309417, logc);
+  return base + fma_(r2, p, r);
+}
+
+// exp(x), |x| ≤ 700.  x = k ln2 + r; 2^k applied by exponent arithmetic (result stays normal).
+NE_HD double exp_mid(const MathConsts& C, double x) {
+  const double magic = 6755399441055744.0;  // 1.5·2^52
+  const double t = fma_(x, 1.44269504088896340736, magic);
+  const int32_t k = lo32(t);
+  const double kf = t - magic;
+  double r = fma_(kf, -6.93147180369123816490e-01, x);
+  r = fma_(kf, -1.90821492927058770002e-10, r);
+  double p = C.expp[EXP_DEG];
+#pragma unroll
+  for (int n = EXP_DEG - 1; n >= 0; --n) p = fma_(p, r, C.expp[n]);
+  return mk64(hi32(p) + (k << 20), lo32(p));
+}
+
+// ---- ψ table lookup --------------------------------------------------------------------------------
+// interval of ζ, or −1 when ζ is outside the table (|ζ| ≥ 2^7 unstable, ζ ≥ 2^-6 stable, NaN)
+NE_HD int psi_interval(double zeta) {
+  const int32_t q = ((hi32(zeta) & 0x7fffffff) >> 18) - ((1023 + PSI_OCT_LO) << 2);
+  if (zeta < 0) return q < 0 ? 0 : (q < PSI_NQ ? q + 1 : -1);
+  return (q < 0) ? PSI_NQ + 1 : -1;   // NaN: q is huge → −1
+}
+
+// both ψ_m and ψ_s at the same |ζ| from interval record `rec`
+NE_HD void psi_pair(const double* __restrict__ rec, double az, double& pm, double& ps) {
+  const double w = fma_(az, rec[0], rec[1]);
+  const double* c = rec + 2;
+  double m = c[2 * PSI_DEG], s = c[2 * PSI_DEG + 1];
+#pragma unroll
+  for (int k = PSI_DEG - 1; k >= 0; --k) {
+    m = fma_(m, w, c[2 * k]);
+    s = fma_(s, w, c[2 * k + 1]);
+  }
+  pm = m; ps = s;
+}
+// one of them (which = 0: ψ_m, 1: ψ_s)
+NE_HD double psi_one(const double* __restrict__ rec, double az, int which) {
+  const double w = fma_(az, rec[0], rec[1]);
+  const double* c = rec + 2 + which;
+  double m = c[2 * PSI_DEG];
+#pragma unroll
+  for (int k = PSI_DEG - 1; k >= 0; --k) m = fma_(m, w, c[2 * k]);
+  return m;
+}
+
+}  // namespace fm
+}  // namespace ne

@@ -14,9 +14,14 @@
 // predicate stops at, the warp reconverges after its slowest lane.  Iteration-invariant terms of
 // the BulkTemperature variant (qₛ, Δq, θₐ, Δθ, 𝒯ₛ, g/𝒯ₛ, Δu, Δv) are hoisted.  No tensor cores:
 // nothing here is a contraction.  FP64 transcendentals are libdevice (no fast-math).
+#include <algorithm>
 #include <cstdlib>
 
+#include <mutex>
+#include <vector>
+
 #include "ne_flux_fast.cuh"
+#include "ne_flux_tab.cuh"
 #include "ne_physics.cuh"
 
 namespace ne {
@@ -91,6 +96,124 @@ ao_flux_fast_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
   ((FT*)d.temperature_scale)[idx] = theta_star;
   ((FT*)d.water_vapor_scale)[idx] = q_star;
   if (d.iterations) d.iterations[idx] = iters;
+}
+
+// ---- atmosphere–ocean kernel, default plugin tree, table-driven iteration (ne_flux_tab.cuh) -----------
+// 256-thread CTAs; each CTA stages the 14 KB solver table (log table + ψ polynomials) in shared memory once
+// and then walks 256-point tiles with a grid stride, so the staging cost is amortised over several tiles.
+template <class CT, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+ao_flux_tab_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_constant__ Layout L,
+                   const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P,
+                   const __grid_constant__ TabParams T, const double* __restrict__ gtab) {
+  __shared__ __align__(16) double tab[fm::TAB_SIZE];
+  for (int k = threadIdx.x; k < fm::TAB_SIZE / 2; k += 256)
+    reinterpret_cast<double2*>(tab)[k] = __ldg(reinterpret_cast<const double2*>(gtab) + k);
+  __syncthreads();
+  using FT = double;
+  const int64_t n = (int64_t)L.ni * L.nj;
+  const bool celsius = d.ocean.temperature_units == NE_DEGREES_CELSIUS;
+  const bool relative = d.properties.velocity_formulation == NE_VEL_RELATIVE;
+  for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (int64_t)gridDim.x * 256) {
+    const int32_t jj = (int32_t)(t / L.ni);
+    const int32_t i = L.i_lo + (int32_t)(t - (int64_t)jj * L.ni);
+    const int32_t j = L.j_lo + jj;
+    const int64_t idx = L.at(i, j);
+
+    AtmosState<FT> a;
+    a.u = __ldg((const FT*)d.ua + idx);
+    a.v = __ldg((const FT*)d.va + idx);
+    a.T = __ldg((const FT*)d.Ta + idx);
+    a.p = __ldg((const FT*)d.pa + idx);
+    a.q = __ldg((const FT*)d.qa + idx);
+    a.z = slot_at<FT>(d.surface_layer_height, idx);
+    a.h_bl = slot_at<FT>(d.boundary_layer_height, idx);
+    FT uo = d.uo.ptr ? (slot_at<FT>(d.uo, idx) + slot_at<FT>(d.uo, idx + 1)) / 2 : (FT)d.uo.value;
+    FT vo = d.vo.ptr ? (slot_at<FT>(d.vo, idx) + slot_at<FT>(d.vo, idx + L.sx)) / 2 : (FT)d.vo.value;
+    FT To = slot_at<FT>(d.To, idx);
+    if (celsius) To = To + 273.15;
+    const FT So = slot_at<FT>(d.So, idx);
+    const bool not_water = d.inactive ? (d.inactive[idx] != 0) : false;
+    const bool skip = not_water && !P.fixed;   // needs_to_converge && not_water (:144)
+
+    FT ustar = 0, theta_star = 0, q_star = 0, Ts = To;
+    int iters = 0;
+    FT du, dv;
+    if (relative) { du = a.u - uo; dv = a.v - vo; } else { du = a.u; dv = a.v; }
+    if (!skip) {
+      FastPoint s;
+      const FT qs = surface_specific_humidity<FT, CT>(d.properties, th, a.p, To, So);
+      const FT Tv = th.virtual_temperature(To, qs);
+      s.gTv = P.g / Tv;
+      s.c1 = 1 + th.delta * qs;
+      s.c2 = th.delta * Tv;
+      s.dudv2 = du * du + dv * dv;
+      s.h_bl = a.h_bl;
+      s.hd = a.z - P.d_zero;
+      s.log_hd = log(s.hd);
+      s.dtheta = (a.T + P.g * a.z / th.cp_m(a.q)) - To;
+      s.dq = a.q - qs;
+      s.ustar = s.theta_star = s.q_star = 1e-4;
+      iters = tab_solve(P, T, tab, s);
+      ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
+    }
+    if (not_water) {  // zero_interface_state (interface_states.jl:800-803)
+      ustar = 0; theta_star = 0; q_star = 0; Ts = 273.15;
+      if (relative) { du = a.u; dv = a.v; }
+    }
+    FluxEpilogue<FT, CT> e(th, a, ustar, theta_star, q_star, du, dv, false);
+    ((FT*)d.latent_heat)[idx] = e.Qv;
+    ((FT*)d.sensible_heat)[idx] = e.Qc;
+    ((FT*)d.water_vapor)[idx] = e.Jv;
+    ((FT*)d.x_momentum)[idx] = e.tx;
+    ((FT*)d.y_momentum)[idx] = e.ty;
+    ((FT*)d.interface_temperature)[idx] = celsius ? Ts - 273.15 : Ts;
+    ((FT*)d.friction_velocity)[idx] = ustar;
+    ((FT*)d.temperature_scale)[idx] = theta_star;
+    ((FT*)d.water_vapor_scale)[idx] = q_star;
+    if (d.iterations) d.iterations[idx] = iters;
+  }
+}
+
+// Device-resident solver tables, built once per (device, ψ parameter set) and kept for the life of the
+// process (14 KB each).  The first call for a parameter set allocates and copies synchronously, so it
+// must happen outside CUDA-graph capture; later calls only enqueue the kernel.
+struct SolverTables {
+  int device;
+  double key[26];
+  double* dptr;
+  TabParams T;
+  double fit_error;
+};
+static std::mutex g_tab_mutex;
+static std::vector<SolverTables> g_tabs;
+
+static const SolverTables* solver_tables(const NeFluxFormulation& f) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  double key[26];
+  for (int k = 0; k < 12; ++k) { key[k] = f.psi_momentum.a.p[k]; key[12 + k] = f.psi_temperature.a.p[k]; }
+  key[24] = f.subgrid_velocities.gustiness_parameter;
+  key[25] = f.subgrid_velocities.minimum_gustiness;
+  std::lock_guard<std::mutex> lock(g_tab_mutex);
+  for (const SolverTables& t : g_tabs)
+    if (t.device == dev && std::memcmp(t.key, key, sizeof(key)) == 0) return t.dptr ? &t : nullptr;
+  SolverTables t;
+  t.device = dev;
+  std::memcpy(t.key, key, sizeof(key));
+  t.dptr = nullptr;
+  std::vector<double> host(fm::TAB_SIZE);
+  t.fit_error = build_solver_tables(f, host.data(), t.T);
+  if (t.fit_error <= 2e-15) {   // else: ψ parameters the polynomials cannot represent → closed-form kernel
+    if (cudaMalloc(&t.dptr, sizeof(double) * fm::TAB_SIZE) != cudaSuccess ||
+        cudaMemcpy(t.dptr, host.data(), sizeof(double) * fm::TAB_SIZE, cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaGetLastError();
+      if (t.dptr) cudaFree(t.dptr);
+      t.dptr = nullptr;
+    }
+  }
+  g_tabs.push_back(t);
+  return g_tabs.back().dptr ? &g_tabs.back() : nullptr;
 }
 
 // ---- host-side validation + dispatch -----------------------------------------------------------------
@@ -173,6 +296,31 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
       Layout L = make_layout(d->grid);
       FastParams P = make_fast_params(d->flux, d->gravitational_acceleration);
       const int64_t n = (int64_t)L.ni * L.nj;
+      // NE_B200_CLOSED_FORM_PSI=1 keeps the libdevice closed-form iteration (parity-tested both ways)
+      const char* closed = std::getenv("NE_B200_CLOSED_FORM_PSI");
+      const SolverTables* tabs = (closed && closed[0] == '1') || !tab_path_eligible(d->flux) ? nullptr : solver_tables(d->flux);
+      if (tabs) {
+        int sms = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const char* tm = std::getenv("NE_B200_TAB_MINB");
+        const int tminb = tm ? std::atoi(tm) : 4;
+        const char* tw = std::getenv("NE_B200_TAB_WAVES");
+        const int waves = tw ? std::atoi(tw) : 8;
+        const int64_t tiles = (n + 255) / 256;
+        const unsigned tb = (unsigned)std::min<int64_t>(tiles, (int64_t)sms * tminb * waves);
+#define NE_LAUNCH_TAB(MB)                                                                                              \
+  do {                                                                                                                 \
+    if (ct64) ao_flux_tab_kernel<double, MB><<<tb, 256, 0, s>>>(*d, L, Thermo<double>::make(d->thermo), P, tabs->T, tabs->dptr); \
+    else ao_flux_tab_kernel<float, MB><<<tb, 256, 0, s>>>(*d, L, Thermo<float>::make(d->thermo), P, tabs->T, tabs->dptr);        \
+  } while (0)
+        if (tminb == 2) NE_LAUNCH_TAB(2);
+        else if (tminb == 3) NE_LAUNCH_TAB(3);
+        else NE_LAUNCH_TAB(4);
+#undef NE_LAUNCH_TAB
+        NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(tab)");
+        return NE_OK;
+      }
       const char* mb = std::getenv("NE_B200_FAST_MINB");   // occupancy experiment knob
       const int minb = mb ? std::atoi(mb) : 8;   // 64 registers/thread measured fastest on B200 (profiles/r01_notes.md)
       const unsigned nb = (unsigned)((n + 127) / 128);

@@ -1,0 +1,214 @@
+// ne_flux_tab.cuh — table-driven iteration of the specialised a–o solve (default plugin tree).
+//
+// Same fixed point, same stopping rule and iteration count as ne_flux_fast.cuh (and therefore as
+// compute_interface_state.jl:5-58 / similarity_theory_turbulent_fluxes.jl:315-385); what changes is
+// HOW the elementary functions are evaluated (ne_fastmath.cuh): branch-free log/exp/cbrt/sqrt/rcp
+// whose coefficients are constant-bank operands, and the unstable Edson ψ_m, ψ_s read from
+// piecewise degree-13 polynomial tables staged in shared memory.  One iteration is ~190 FP64
+// instructions with no data-dependent branch except (i) the stable side ζ ≥ 2^-6 (closed form with
+// the custom exp) and (ii) |ζ| ≥ 2^7 on the unstable side (closed form through libdevice, rare).
+#pragma once
+
+#include "ne_fastmath.cuh"
+#include "ne_flux_fast.cuh"
+
+namespace ne {
+
+struct TabParams {
+  fm::MathConsts mc;
+  double cbrt_floor;     // (gmin/β)³/8: below it β·cbrt(x) < gmin, so the clamp cannot change U_G
+  int32_t same_exp;      // ψ_m and ψ_s stable branches share exp(−min(ζmax, A⁺ζ))
+  int32_t pad_;
+};
+
+// ---- host: Chebyshev interpolation → monomials in w ∈ [−1, 1] (long double) -------------------------
+template <class F>
+inline void cheb_fit_monomial(F f, long double lo, long double hi, int deg, double* coef) {
+  constexpr int MAXN = 24;
+  const int N = deg + 1;
+  const long double PI = 3.141592653589793238462643383279502884L;
+  const long double mid = (lo + hi) / 2, half = (hi - lo) / 2;
+  long double y[MAXN], c[MAXN];
+  for (int k = 0; k < N; ++k) y[k] = f(mid + half * cosl(PI * (2 * k + 1) / (2 * N)));
+  for (int j = 0; j < N; ++j) {
+    long double a = 0;
+    for (int k = 0; k < N; ++k) a += y[k] * cosl(PI * j * (2 * k + 1) / (2 * N));
+    c[j] = a * 2 / N;
+  }
+  c[0] /= 2;
+  long double T0[MAXN] = {0}, T1[MAXN] = {0}, T2[MAXN], px[MAXN] = {0};
+  T0[0] = 1; T1[1] = 1;
+  px[0] += c[0];
+  if (N > 1) for (int m = 0; m < N; ++m) px[m] += c[1] * T1[m];
+  for (int j = 2; j < N; ++j) {
+    for (int m = 0; m < N; ++m) T2[m] = (m > 0 ? 2 * T1[m - 1] : 0) - T0[m];
+    for (int m = 0; m < N; ++m) { px[m] += c[j] * T2[m]; T0[m] = T1[m]; T1[m] = T2[m]; }
+  }
+  for (int m = 0; m < N; ++m) coef[m] = (double)px[m];
+}
+
+inline long double psi_m_stable_ld(const double* p, long double z) {
+  const long double zmax = p[0], Ap = p[1], Bp = p[2], Cp = p[3], Dp = p[4];
+  const long double dz = fminl(zmax, Ap * z);
+  return -Bp * z - Cp * (z - Dp) * expl(-dz) - Cp * Dp;
+}
+inline long double psi_s_stable_ld(const double* p, long double z) {
+  const long double zmax = p[0], Ap = p[1], Bp = p[2], Cp = p[3], Dp = p[4], Ep = p[5];
+  const long double dz = fminl(zmax, Ap * z);
+  return -powl(1 + Bp * z, Cp) - Bp * (z - Dp) * expl(-dz) - Ep;
+}
+
+// Fills tab[TAB_SIZE] and T; returns the max abs error of the ψ polynomials (double Horner vs the
+// long-double closed forms) over all intervals.
+inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabParams& T) {
+  using namespace fm;
+  // log table
+  for (int i = 0; i < LOG_N; ++i) {
+    const double zlo = mk64(0x3fe6a09e + (i << 14), 0), zhi = mk64(0x3fe6a09e + ((i + 1) << 14), 0);
+    const double c = 0.5 * (zlo + zhi);
+    const double invc = 1.0 / c;
+    tab[TAB_LOG + 2 * i] = invc;
+    tab[TAB_LOG + 2 * i + 1] = (double)(-logl((long double)invc));
+  }
+  for (int k = 0; k < LOG_DEG; ++k) T.mc.logp[k] = ((k & 1) ? 1.0 : -1.0) / (double)(k + 2);   // −1/2, +1/3, −1/4 …
+  {  // e^r on |r| ≤ 0.35, monomials in r
+    double cw[EXP_DEG + 1];
+    const long double h = 0.35L;
+    cheb_fit_monomial([](long double x) { return expl(x); }, -h, h, EXP_DEG, cw);
+    long double s = 1;
+    for (int k = 0; k <= EXP_DEG; ++k) { T.mc.expp[k] = (double)((long double)cw[k] / s); s *= h; }
+  }
+  const double* pm = f.psi_momentum.a.p;
+  const double* ps = f.psi_temperature.a.p;
+  double worst = 0;
+  for (int iv = 0; iv < PSI_NI; ++iv) {
+    long double lo, hi;
+    bool stable = false;
+    if (iv == 0) { lo = 0; hi = ldexpl(1, PSI_OCT_LO); }
+    else if (iv == PSI_NQ + 1) { lo = 0; hi = ldexpl(1, PSI_OCT_LO); stable = true; }
+    else {
+      const int q = iv - 1, e = PSI_OCT_LO + (q >> 2), s = q & 3;
+      lo = ldexpl(1 + s / 4.0L, e); hi = ldexpl(1 + (s + 1) / 4.0L, e);
+    }
+    double* rec = tab + TAB_PSI + iv * PSI_REC;
+    const long double half = (hi - lo) / 2, mid = (hi + lo) / 2;
+    rec[0] = (double)(1 / half);
+    rec[1] = (double)(-mid / half);
+    double cm[PSI_DEG + 1], cs[PSI_DEG + 1];
+    auto fmf = [&](long double az) { return stable ? psi_m_stable_ld(pm, az) : psi_m_unstable_ld(pm, -az); };
+    auto fsf = [&](long double az) { return stable ? psi_s_stable_ld(ps, az) : psi_s_unstable_ld(ps, -az); };
+    cheb_fit_monomial(fmf, lo, hi, PSI_DEG, cm);
+    cheb_fit_monomial(fsf, lo, hi, PSI_DEG, cs);
+    for (int k = 0; k <= PSI_DEG; ++k) { rec[2 + 2 * k] = cm[k]; rec[2 + 2 * k + 1] = cs[k]; }
+    for (int n = 0; n <= 48; ++n) {
+      const double az = (double)(lo + (hi - lo) * n / 48.0L);
+      double m, s;
+      psi_pair(rec, az, m, s);
+      const double em = (double)fabsl((long double)m - fmf(az)), es = (double)fabsl((long double)s - fsf(az));
+      if (!(em <= worst)) worst = em;   // also catches NaN
+      if (!(es <= worst)) worst = es;
+    }
+  }
+  const NeSubgridVelocity& g = f.subgrid_velocities;
+  const double ratio = g.minimum_gustiness / g.gustiness_parameter;
+  T.cbrt_floor = ratio * ratio * ratio / 8;
+  T.same_exp = (pm[0] == ps[0] && pm[1] == ps[1]);
+  T.pad_ = 0;
+  return worst;
+}
+
+inline bool tab_path_eligible(const NeFluxFormulation& f) {
+  const NeSubgridVelocity& g = f.subgrid_velocities;
+  const double ratio = g.minimum_gustiness / g.gustiness_parameter;
+  if (!(g.gustiness_parameter > 0) || !(ratio * ratio * ratio / 8 > 1e-290)) return false;
+  return true;
+}
+
+#if defined(__CUDACC__)
+// unstable closed forms through libdevice for |ζ| ≥ 2^7 (free-convection limit; rare)
+__device__ __noinline__ void psi_far_unstable(const FastParams& P, double z, double& pm, double& ps) {
+  pm = fast_psi_m(P, z);   // |z| ≥ 2^7 > P.zsmall: the closed-form branch
+  ps = fast_psi_s(P, z);
+}
+
+__device__ __noinline__ double pow_general(double x, double y) { return pow(x, y); }
+
+// stable closed forms (ζ ≥ 2^-6) with the custom exp/sqrt
+__device__ __forceinline__ void psi_stable_pair(const FastParams& P, const TabParams& T, double z, double& pm, double& ps) {
+  const double em = fm::exp_mid(T.mc, -fmin(P.m_zmax, P.m_Ap * z));
+  const double es = T.same_exp ? em : fm::exp_mid(T.mc, -fmin(P.s_zmax, P.s_Ap * z));
+  pm = -P.m_Bp * z - P.m_Cp * (z - P.m_Dp) * em - P.m_CpDp;
+  const double x = 1.0 + P.s_Bp * z;
+  const double xp = P.s_C15 ? x * fm::sqrt_pos(x) : pow_general(x, P.s_Cp);
+  ps = -xp - P.s_Bp * (z - P.s_Dp) * es - P.s_Ep;
+}
+
+// ψ_m(ζ), ψ_s(ζ) at the same ζ
+__device__ __forceinline__ void tab_psi_pair(const FastParams& P, const TabParams& T, const double* tab, double z,
+                                             double& pm, double& ps) {
+  const int iv = fm::psi_interval(z);
+  if (iv >= 0) fm::psi_pair(tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(z), pm, ps);
+  else if (z > 0) psi_stable_pair(P, T, z, pm, ps);
+  else psi_far_unstable(P, z, pm, ps);
+}
+
+// out-of-line copy for the rare case where ψ(ℓ/L★) leaves the small-|ζ| intervals
+__device__ __noinline__ void tab_psi_pair_rare(const FastParams& P, const TabParams& T, const double* tab, double z,
+                                               double& pm, double& ps) {
+  tab_psi_pair(P, T, tab, z, pm, ps);
+}
+
+__device__ __forceinline__ void tab_iteration(const FastParams& P, const TabParams& T, const double* tab, FastPoint& s) {
+  const double bstar = s.gTv * (s.theta_star * s.c1 + s.c2 * s.q_star);
+  const double Jb = -s.ustar * bstar;
+  const double UG = fmax(P.gmin, P.beta * fm::cbrt_pos(fmax(fmax(0.0, Jb) * s.h_bl, T.cbrt_floor)));
+  const double U = fm::sqrt_pos(s.dudv2 + UG * UG);
+  const double ru = fm::rcp(s.ustar);
+  const double lu = fmin(P.a1 * s.ustar * s.ustar + P.a2 * ru, P.lmax);
+  const double log_lu = fm::log_pos(tab, T.mc, lu);
+  const double log_Rs = fm::log_pos(tab, T.mc, lu * s.ustar * P.nu_inv);
+  const double log_ls_un = P.log_rA - P.rb * log_Rs;
+  const bool clipped = log_ls_un > P.log_ls_max;
+  const double log_ls = clipped ? P.log_ls_max : log_ls_un;
+  const double ls = clipped ? P.ls_max : fm::exp_mid(T.mc, fmax(log_ls_un, -700.0));
+  const bool lifted = 2.0 * lu > s.hd;
+  const double dh = lifted ? 2.0 * lu : s.hd;
+  const double log_dh = lifted ? 0.6931471805599453 + log_lu : s.log_hd;
+  const double Linv = P.kappa * bstar * ru * ru;   // 1/L★ (0 when b★ == 0, i.e. L★ = Inf)
+  double pm_h, ps_h, pm_l, ps_l;
+  tab_psi_pair(P, T, tab, dh * Linv, pm_h, ps_h);
+  // ψ(ℓ/L★): |ℓ/L★| ≪ 2^-6 in practice → both land in a small-|ζ| interval; general lookup otherwise
+  const double zu = lu * Linv, zs = ls * Linv;
+  const int ivu = fm::psi_interval(zu), ivs = fm::psi_interval(zs);
+  if (ivu >= 0 && ivs >= 0) {
+    pm_l = fm::psi_one(tab + fm::TAB_PSI + ivu * fm::PSI_REC, fabs(zu), 0);
+    ps_l = fm::psi_one(tab + fm::TAB_PSI + ivs * fm::PSI_REC, fabs(zs), 1);
+  } else {
+    double dummy;
+    tab_psi_pair_rare(P, T, tab, zu, pm_l, dummy);
+    tab_psi_pair_rare(P, T, tab, zs, dummy, ps_l);
+  }
+  const double Pi_u = (log_dh - log_lu) - pm_h + pm_l;
+  const double Pi_s = (log_dh - log_ls) - ps_h + ps_l;
+  const double chi_s = fm::div(P.kappa, Pi_s);
+  s.ustar = fm::div(P.kappa, Pi_u) * U;
+  s.theta_star = chi_s * s.dtheta;
+  s.q_star = chi_s * s.dq;
+}
+
+__device__ __forceinline__ int tab_solve(const FastParams& P, const TabParams& T, const double* tab, FastPoint& s) {
+  int it = 0;
+  double drift = 0;
+  for (;;) {
+    const bool go = P.fixed ? (it < P.maxiter) : (!((drift < P.tol) | (it >= P.maxiter)) | (it == 0));
+    if (!go) break;
+    const double pu = s.ustar, pt = s.theta_star, pq = s.q_star;
+    tab_iteration(P, T, tab, s);
+    drift = fabs(s.ustar - pu) + fabs(s.theta_star - pt) + fabs(s.q_star - pq);
+    ++it;
+  }
+  return it;
+}
+#endif  // __CUDACC__
+
+}  // namespace ne

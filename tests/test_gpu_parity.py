@@ -76,6 +76,20 @@ def test_generic_kernel_on_default_tree(oracle_lib, cuda_backend, cuda_lib, monk
     _check_iterations(ref, dev, cuda_backend)
 
 
+def test_closed_form_kernel_on_default_tree(oracle_lib, cuda_backend, cuda_lib, monkeypatch):
+    """The default tree normally runs the table-driven iteration (ne_flux_tab.cuh); NE_B200_CLOSED_FORM_PSI
+    keeps the libdevice closed-form iteration (the fallback for ψ parameters the tables cannot fit)."""
+    monkeypatch.setenv("NE_B200_CLOSED_FORM_PSI", "1")
+    ref, dev = build_pair("C1", oracle_lib, cuda_backend, FT="f64", atm_FT="f64")
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP); dev.update_state(T_STEP)
+    cuda_backend.synchronize()
+    res = compare_fields(ref.ao_fluxes, dev.ao_fluxes, ref.grid, cuda_backend)
+    for n, (r, fr, _) in res.items():
+        assert fr <= F64_TOL, f"{n}: {fr}"
+    _check_iterations(ref, dev, cuda_backend)
+
+
 def test_sea_ice_ocean_stress_known_answer(cuda_backend, cuda_lib):
     """test/test_surface_fluxes.jl:294-336: ocean (0.1, 0.2), ice at rest, Cᴰ=1e-3, ρₑ=1000
     => τˣ == sqrt(0.1²+0.2²)·0.1, τʸ == sqrt(0.1²+0.2²)·0.2 (exact)."""

@@ -1,0 +1,97 @@
+// fastmath_check.cu — host-side accuracy check of ne_fastmath.cuh / ne_flux_tab.cuh (no GPU needed).
+//   nvcc -O2 -std=c++17 -o /tmp/fastmath_check tools/fastmath_check.cu && /tmp/fastmath_check
+// Prints one JSON object: max relative error (in units of 2^-53) of each elementary function against
+// long double, and the max abs error of the ψ tables for the default Edson parameters.
+#include <cstdio>
+#include <random>
+
+#include "../numericalearth.jl_b200/csrc/ne_flux_tab.cuh"
+
+using namespace ne;
+
+static void default_formulation(NeFluxFormulation& f) {
+  std::memset(&f, 0, sizeof(f));
+  double m[11] = {50, 0.35, 0.7, 0.75, 5 / 0.35, 15, 2, 3.141592653589793 / 2, 10.15, 3, 3.141592653589793 / std::sqrt(3.0)};
+  double s[12] = {50, 0.35, 2.0 / 3, 1.5, 14.28, 8.525, 15, 2, 0, 34.15, 3, 3.141592653589793 / std::sqrt(3.0)};
+  for (int k = 0; k < 11; ++k) f.psi_momentum.a.p[k] = m[k];
+  for (int k = 0; k < 12; ++k) { f.psi_temperature.a.p[k] = s[k]; f.psi_water_vapor.a.p[k] = s[k]; }
+  f.subgrid_velocities.gustiness_parameter = 1.2;
+  f.subgrid_velocities.minimum_gustiness = 0.01;
+}
+
+template <class F, class G>
+static double max_ulp(F f, G truth, double lo, double hi, bool logspace, int n, std::mt19937_64& rng) {
+  std::uniform_real_distribution<double> u(0, 1);
+  double worst = 0;
+  for (int i = 0; i < n; ++i) {
+    double t = u(rng);
+    double x = logspace ? std::exp(std::log(lo) + t * (std::log(hi) - std::log(lo))) : lo + t * (hi - lo);
+    long double ref = truth((long double)x);
+    double got = f(x);
+    double e = (double)(fabsl((long double)got - ref) / fabsl(ref)) * 9007199254740992.0;
+    if (!(e <= worst)) worst = e;
+  }
+  return worst;
+}
+
+int main() {
+  NeFluxFormulation f;
+  default_formulation(f);
+  static double tab[fm::TAB_SIZE];
+  TabParams T;
+  double fit = build_solver_tables(f, tab, T);
+  std::mt19937_64 rng(20261017);
+  double e_rcp = max_ulp([](double x) { return fm::rcp(x); }, [](long double x) { return 1 / x; }, 1e-6, 1e6, true, 400000, rng);
+  double e_div = max_ulp([](double x) { return fm::div(0.4, x); }, [](long double x) { return 0.4L * 1 / x * 1.0L == 0 ? 0 : (long double)0.4 / x; }, 1e-3, 1e3, true, 400000, rng);
+  double e_sqrt = max_ulp([](double x) { return fm::sqrt_pos(x); }, [](long double x) { return sqrtl(x); }, 1e-8, 1e8, true, 400000, rng);
+  double e_cbrt = max_ulp([](double x) { return fm::cbrt_pos(x); }, [](long double x) { return cbrtl(x); }, 1e-12, 1e12, true, 400000, rng);
+  double e_cbrt2 = max_ulp([](double x) { return fm::cbrt_pos(x); }, [](long double x) { return cbrtl(x); }, 1e-300, 1e300, true, 400000, rng);
+  // log: relative error away from 1, absolute error (in units of 2^-53) near 1
+  double e_log = max_ulp([&](double x) { return fm::log_pos(tab, T.mc, x); }, [](long double x) { return logl(x); }, 1e-12, 0.5, true, 400000, rng);
+  double e_log_hi = max_ulp([&](double x) { return fm::log_pos(tab, T.mc, x); }, [](long double x) { return logl(x); }, 2.0, 1e12, true, 400000, rng);
+  double e_log_abs = 0;
+  {
+    std::uniform_real_distribution<double> u(0.5, 2.0);
+    for (int i = 0; i < 400000; ++i) {
+      double x = u(rng);
+      double e = (double)fabsl((long double)fm::log_pos(tab, T.mc, x) - logl((long double)x)) * 9007199254740992.0;
+      if (!(e <= e_log_abs)) e_log_abs = e;
+    }
+  }
+  double e_exp = max_ulp([&](double x) { return fm::exp_mid(T.mc, x); }, [](long double x) { return expl(x); }, -700, 700, false, 400000, rng);
+  double e_exp2 = max_ulp([&](double x) { return fm::exp_mid(T.mc, x); }, [](long double x) { return expl(x); }, -30, 1, false, 400000, rng);
+  // ψ tables: dense independent check
+  const double* pm = f.psi_momentum.a.p;
+  const double* ps = f.psi_temperature.a.p;
+  double e_psi = 0;
+  {
+    std::uniform_real_distribution<double> u(0, 1);
+    for (int i = 0; i < 400000; ++i) {
+      double az = std::exp(std::log(1e-9) + u(rng) * (std::log(127.99) - std::log(1e-9)));
+      int iv = fm::psi_interval(-az);
+      if (iv < 0) { e_psi = 1e300; break; }
+      double m, s;
+      fm::psi_pair(tab + fm::TAB_PSI + iv * fm::PSI_REC, az, m, s);
+      double em = (double)fabsl((long double)m - psi_m_unstable_ld(pm, -(long double)az));
+      double es = (double)fabsl((long double)s - psi_s_unstable_ld(ps, -(long double)az));
+      if (!(em <= e_psi)) e_psi = em;
+      if (!(es <= e_psi)) e_psi = es;
+      if (az < 0.015625) {
+        iv = fm::psi_interval(az);
+        fm::psi_pair(tab + fm::TAB_PSI + iv * fm::PSI_REC, az, m, s);
+        em = (double)fabsl((long double)m - psi_m_stable_ld(pm, (long double)az));
+        es = (double)fabsl((long double)s - psi_s_stable_ld(ps, (long double)az));
+        if (!(em <= e_psi)) e_psi = em;
+        if (!(es <= e_psi)) e_psi = es;
+      }
+    }
+  }
+  int iv_ok = fm::psi_interval(-128.0) == -1 && fm::psi_interval(0.5) == -1 && fm::psi_interval(0.0) == fm::PSI_NQ + 1 &&
+              fm::psi_interval(-1e-300) == 0 && fm::psi_interval(-0.015625) == 1 && fm::psi_interval(-127.9) == fm::PSI_NQ &&
+              fm::psi_interval(NAN) == -1;
+  printf("{\"rcp_ulp\": %.3f, \"div_ulp\": %.3f, \"sqrt_ulp\": %.3f, \"cbrt_ulp\": %.3f, \"cbrt_wide_ulp\": %.3f, "
+         "\"log_ulp_small\": %.3f, \"log_ulp_large\": %.3f, \"log_abs_near1_ulp1\": %.3f, \"exp_ulp\": %.3f, \"exp_ulp_mid\": %.3f, "
+         "\"psi_fit_abs\": %.3e, \"psi_dense_abs\": %.3e, \"interval_logic_ok\": %d, \"cbrt_floor\": %.6e, \"same_exp\": %d}\n",
+         e_rcp, e_div, e_sqrt, e_cbrt, e_cbrt2, e_log, e_log_hi, e_log_abs, e_exp, e_exp2, fit, e_psi, iv_ok, T.cbrt_floor, T.same_exp);
+  return 0;
+}
