@@ -11,10 +11,10 @@
 // so tests/test_fastmath.py checks every function against long double without a GPU.
 //
 // ψ tables: the Edson et al. (2013) stability functions (similarity_theory_turbulent_fluxes.jl:501-532,
-// 586-618) are smooth on ζ < 0; on quarter-octave intervals 2^-6 ≤ |ζ| < 2^7 (plus one interval
-// [−2^-6, 0) and one [0, 2^-6) for the stable side) they are replaced by degree-13 polynomials
+// 586-618) are smooth on each side of ζ = 0; on quarter-octave intervals 2^-6 ≤ |ζ| < 2^7 (plus one
+// interval |ζ| < 2^-6 per side) they are replaced by degree-13 polynomials
 // interpolated at Chebyshev nodes from the closed forms evaluated in long double; the fit is
-// verified on the host at build time (max abs error ≤ 1e-15 required, else the closed-form kernel
+// verified on the host at build time (max abs error ≤ 2e-15 required, else the closed-form kernel
 // is used).  ψ_m and ψ_s coefficients are interleaved so one 16-byte load feeds both Horner chains.
 #pragma once
 
@@ -39,16 +39,34 @@ constexpr int PSI_DEG = 13;
 constexpr int PSI_OCT_LO = -6;  // table covers 2^-6 ≤ |ζ| < 2^7 on the unstable side
 constexpr int PSI_OCT_HI = 7;
 constexpr int PSI_NQ = 4 * (PSI_OCT_HI - PSI_OCT_LO);  // quarter-octave intervals
-constexpr int PSI_NI = PSI_NQ + 2;                     // + [−2^-6, 0) (index 0) + [0, 2^-6) (index NQ+1)
+constexpr int PSI_NS = PSI_NQ + 1;                     // records per side: [0, 2^-6) then the quarter octaves
+constexpr int PSI_NI = 2 * PSI_NS;                     // unstable side (ζ < 0) first, then the stable side
 constexpr int PSI_REC = 2 + 2 * (PSI_DEG + 1);         // (a, b) of w = a|ζ| + b, then (c_m, c_s) pairs
+constexpr int TINY_DEG = 9;                            // |ζ| < 2^TINY_EXP (the ψ(ℓ/L★) terms): low-degree records
+constexpr int TINY_EXP = -7;
+constexpr int TINY_REC = 2 + 2 * (TINY_DEG + 1);       // record 0: unstable side, record 1: stable side
 constexpr int TAB_LOG = 0;
 constexpr int TAB_PSI = 2 * LOG_N;
-constexpr int TAB_SIZE = TAB_PSI + PSI_NI * PSI_REC;   // doubles (1748 = 13 984 B)
+constexpr int TAB_TINY = TAB_PSI + PSI_NI * PSI_REC;
+constexpr int TAB_SIZE = TAB_TINY + 2 * TINY_REC;      // doubles (3344 = 26 752 B)
 
 struct MathConsts {
   double logp[LOG_DEG];      // P(r) = Σ logp[k] r^k
   double expp[EXP_DEG + 1];  // e^r ≈ Σ expp[k] r^k
+  // 64-bit literals kept in the constant bank (an immediate costs two extra moves per use)
+  double ln2, log2e, ln2_hi, ln2_lo, third;
 };
+inline void fill_literals(MathConsts& C) {
+  C.ln2 = 0.693147180559945309417;
+  C.log2e = 1.44269504088896340736;
+  C.ln2_hi = 6.93147180369123816490e-01;
+  C.ln2_lo = 1.90821492927058770002e-10;
+  C.third = 0.33333333333333333;
+}
+
+// select-based min/max (inputs are never NaN here; IEEE fmin/fmax cost 6-7 instructions in FP64)
+NE_HD double dmin(double a, double b) { return a < b ? a : b; }
+NE_HD double dmax(double a, double b) { return a > b ? a : b; }
 
 // ---- bit access -----------------------------------------------------------------------------------
 NE_HD int32_t hi32(double x) {
@@ -122,18 +140,21 @@ NE_HD double sqrt_pos(double x) {
 }
 // cbrt(x), x > 0 normal.  x = 2^(3q)·m with m ∈ [1, 8): seed m^(-1/3) in Float32 (MUFU lg2/ex2 on the
 // device), two Newton steps on r ↦ r + r(1 − m r³)/3, result m·r²·2^q.
-NE_HD double cbrt_pos(double x) {
+NE_HD double cbrt_pos(const MathConsts& C, double x) {
   const int32_t hi = hi32(x);
   const int32_t e = (hi >> 20) - 1023;                 // unbiased exponent
   const int32_t q = (e + 3072) * 21846 >> 16;          // floor((e + 3072)/3), exact for |e| ≤ 1100
   const int32_t q3 = q - 1024;                         // floor(e/3)
   const double m = mk64(hi - ((3 * q3) << 20), lo32(x));  // [1, 8)
 #if defined(__CUDA_ARCH__)
-  double r = (double)exp2f(-0.333333333f * __log2f((float)m));
+  float lg, ex;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float)m));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-0.333333333f * lg));
+  double r = (double)ex;
 #else
   double r = (double)(float)std::exp2(-std::log2((float)m) / 3.0f) * (1.0 + 4e-7);
 #endif
-  const double third = 0.33333333333333333;
+  const double third = C.third;
   double r2 = r * r;
   double e1 = fma_(-m * r, r2, 1.0);
   r = fma_(r * third, e1, r);
@@ -160,18 +181,18 @@ NE_HD double log_pos(const double* __restrict__ tab, const MathConsts& C, double
 #pragma unroll
   for (int n = LOG_DEG - 2; n >= 0; --n) p = fma_(p, r, C.logp[n]);
   const double r2 = r * r;
-  const double base = fma_((double)k, 0.693147180559945309417, logc);
+  const double base = fma_((double)k, C.ln2, logc);
   return base + fma_(r2, p, r);
 }
 
 // exp(x), |x| ≤ 700.  x = k ln2 + r; 2^k applied by exponent arithmetic (result stays normal).
 NE_HD double exp_mid(const MathConsts& C, double x) {
   const double magic = 6755399441055744.0;  // 1.5·2^52
-  const double t = fma_(x, 1.44269504088896340736, magic);
+  const double t = fma_(x, C.log2e, magic);
   const int32_t k = lo32(t);
   const double kf = t - magic;
-  double r = fma_(kf, -6.93147180369123816490e-01, x);
-  r = fma_(kf, -1.90821492927058770002e-10, r);
+  double r = fma_(-kf, C.ln2_hi, x);
+  r = fma_(-kf, C.ln2_lo, r);
   double p = C.expp[EXP_DEG];
 #pragma unroll
   for (int n = EXP_DEG - 1; n >= 0; --n) p = fma_(p, r, C.expp[n]);
@@ -179,33 +200,43 @@ NE_HD double exp_mid(const MathConsts& C, double x) {
 }
 
 // ---- ψ table lookup --------------------------------------------------------------------------------
-// interval of ζ, or −1 when ζ is outside the table (|ζ| ≥ 2^7 unstable, ζ ≥ 2^-6 stable, NaN)
-NE_HD int psi_interval(double zeta) {
+// record index of ζ (branch-free); `outside` is set when |ζ| ≥ 2^7 or ζ is NaN (closed forms then)
+NE_HD int psi_interval(double zeta, bool& outside) {
   const int32_t q = ((hi32(zeta) & 0x7fffffff) >> 18) - ((1023 + PSI_OCT_LO) << 2);
-  if (zeta < 0) return q < 0 ? 0 : (q < PSI_NQ ? q + 1 : -1);
-  return (q < 0) ? PSI_NQ + 1 : -1;   // NaN: q is huge → −1
+  outside = q >= PSI_NQ;
+  int32_t i = q + 1;
+  i = i < 0 ? 0 : i;
+  i = i > PSI_NQ ? PSI_NQ : i;
+  return zeta < 0 ? i : i + PSI_NS;
+}
+NE_HD bool psi_is_tiny(double zeta) {
+  return ((hi32(zeta) & 0x7fffffff) >> 20) < 1023 + TINY_EXP;
+}
+
+// Horner split into even and odd parts (two half-length dependency chains per polynomial)
+template <int DEG>
+NE_HD double poly_eo(const double* __restrict__ c, int stride, double w, double w2) {
+  constexpr int TE = DEG & ~1, TO = (DEG & 1) ? DEG : DEG - 1;   // top even / odd degree
+  double e = c[TE * stride], o = c[TO * stride];
+#pragma unroll
+  for (int k = TE - 2; k >= 0; k -= 2) e = fma_(e, w2, c[k * stride]);
+#pragma unroll
+  for (int k = TO - 2; k >= 1; k -= 2) o = fma_(o, w2, c[k * stride]);
+  return fma_(o, w, e);
 }
 
 // both ψ_m and ψ_s at the same |ζ| from interval record `rec`
 NE_HD void psi_pair(const double* __restrict__ rec, double az, double& pm, double& ps) {
   const double w = fma_(az, rec[0], rec[1]);
-  const double* c = rec + 2;
-  double m = c[2 * PSI_DEG], s = c[2 * PSI_DEG + 1];
-#pragma unroll
-  for (int k = PSI_DEG - 1; k >= 0; --k) {
-    m = fma_(m, w, c[2 * k]);
-    s = fma_(s, w, c[2 * k + 1]);
-  }
-  pm = m; ps = s;
+  const double w2 = w * w;
+  pm = poly_eo<PSI_DEG>(rec + 2, 2, w, w2);
+  ps = poly_eo<PSI_DEG>(rec + 3, 2, w, w2);
 }
-// one of them (which = 0: ψ_m, 1: ψ_s)
-NE_HD double psi_one(const double* __restrict__ rec, double az, int which) {
-  const double w = fma_(az, rec[0], rec[1]);
-  const double* c = rec + 2 + which;
-  double m = c[2 * PSI_DEG];
-#pragma unroll
-  for (int k = PSI_DEG - 1; k >= 0; --k) m = fma_(m, w, c[2 * k]);
-  return m;
+// ψ_m(|ζ_u|) and ψ_s(|ζ_s|) for |ζ| < 2^TINY_EXP, both on the side (record) `rec`
+NE_HD void psi_tiny_pair(const double* __restrict__ rec, double azu, double azs, double& pm, double& ps) {
+  const double wu = fma_(azu, rec[0], rec[1]), ws = fma_(azs, rec[0], rec[1]);
+  pm = poly_eo<TINY_DEG>(rec + 2, 2, wu, wu * wu);
+  ps = poly_eo<TINY_DEG>(rec + 3, 2, ws, ws * ws);
 }
 
 }  // namespace fm

@@ -99,9 +99,12 @@ ao_flux_fast_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
 }
 
 // ---- atmosphere–ocean kernel, default plugin tree, table-driven iteration (ne_flux_tab.cuh) -----------
-// 256-thread CTAs; each CTA stages the 14 KB solver table (log table + ψ polynomials) in shared memory once
+// 256-thread CTAs; each CTA stages the 27 KB solver table (log table + ψ polynomials) in shared memory once
 // and then walks 256-point tiles with a grid stride, so the staging cost is amortised over several tiles.
-template <class CT, int MINB>
+// Register budget: only the 9 per-point invariants and the 3-component iterate live across the loop; the
+// atmosphere state needed by the flux epilogue is re-read from global memory (L2 hits) after the solve.
+// HS: surface-layer and boundary-layer heights are scalars (PrescribedAtmosphere default) → uniform.
+template <class CT, int MINB, bool HS>
 __global__ void __launch_bounds__(256, MINB)
 ao_flux_tab_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_constant__ Layout L,
                    const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P,
@@ -116,50 +119,58 @@ ao_flux_tab_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_cons
   const bool relative = d.properties.velocity_formulation == NE_VEL_RELATIVE;
   for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (int64_t)gridDim.x * 256) {
     const int32_t jj = (int32_t)(t / L.ni);
-    const int32_t i = L.i_lo + (int32_t)(t - (int64_t)jj * L.ni);
-    const int32_t j = L.j_lo + jj;
-    const int64_t idx = L.at(i, j);
+    const int64_t idx = L.at(L.i_lo + (int32_t)(t - (int64_t)jj * L.ni), L.j_lo + jj);
+    const bool not_water = d.inactive ? (d.inactive[idx] != 0) : false;
+    const bool skip = not_water && !P.fixed;   // needs_to_converge && not_water (:144)
 
+    FT ustar = 0, theta_star = 0, q_star = 0;
+    int iters = 0;
+    if (!skip) {
+      FastPoint s;
+      {
+        const FT au = __ldg((const FT*)d.ua + idx), av = __ldg((const FT*)d.va + idx);
+        const FT aT = __ldg((const FT*)d.Ta + idx), ap = __ldg((const FT*)d.pa + idx), aq = __ldg((const FT*)d.qa + idx);
+        const FT az = HS ? (FT)d.surface_layer_height.value : slot_at<FT>(d.surface_layer_height, idx);
+        FT du = au, dv = av;
+        if (relative) {
+          du -= d.uo.ptr ? (slot_at<FT>(d.uo, idx) + slot_at<FT>(d.uo, idx + 1)) / 2 : (FT)d.uo.value;
+          dv -= d.vo.ptr ? (slot_at<FT>(d.vo, idx) + slot_at<FT>(d.vo, idx + L.sx)) / 2 : (FT)d.vo.value;
+        }
+        FT To = slot_at<FT>(d.To, idx);
+        if (celsius) To = To + 273.15;
+        const FT qs = surface_specific_humidity<FT, CT>(d.properties, th, ap, To, slot_at<FT>(d.So, idx));
+        const FT Tv = th.virtual_temperature(To, qs);
+        s.gTv = P.g / Tv;
+        s.c1 = 1 + th.delta * qs;
+        s.c2 = th.delta * Tv;
+        s.dudv2 = du * du + dv * dv;
+        s.h_bl = HS ? (FT)d.boundary_layer_height.value : slot_at<FT>(d.boundary_layer_height, idx);
+        s.hd = az - P.d_zero;
+        s.log_hd = HS ? T.log_hd : log(s.hd);
+        s.dtheta = (aT + P.g * az / th.cp_m(aq)) - To;
+        s.dq = aq - qs;
+        s.ustar = s.theta_star = s.q_star = 1e-4;
+      }
+      iters = tab_solve(P, T, tab, s);
+      ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
+    }
+    // epilogue (atmosphere_ocean_fluxes.jl:160-196): atmosphere state re-read
     AtmosState<FT> a;
     a.u = __ldg((const FT*)d.ua + idx);
     a.v = __ldg((const FT*)d.va + idx);
     a.T = __ldg((const FT*)d.Ta + idx);
     a.p = __ldg((const FT*)d.pa + idx);
     a.q = __ldg((const FT*)d.qa + idx);
-    a.z = slot_at<FT>(d.surface_layer_height, idx);
-    a.h_bl = slot_at<FT>(d.boundary_layer_height, idx);
-    FT uo = d.uo.ptr ? (slot_at<FT>(d.uo, idx) + slot_at<FT>(d.uo, idx + 1)) / 2 : (FT)d.uo.value;
-    FT vo = d.vo.ptr ? (slot_at<FT>(d.vo, idx) + slot_at<FT>(d.vo, idx + L.sx)) / 2 : (FT)d.vo.value;
-    FT To = slot_at<FT>(d.To, idx);
-    if (celsius) To = To + 273.15;
-    const FT So = slot_at<FT>(d.So, idx);
-    const bool not_water = d.inactive ? (d.inactive[idx] != 0) : false;
-    const bool skip = not_water && !P.fixed;   // needs_to_converge && not_water (:144)
-
-    FT ustar = 0, theta_star = 0, q_star = 0, Ts = To;
-    int iters = 0;
-    FT du, dv;
-    if (relative) { du = a.u - uo; dv = a.v - vo; } else { du = a.u; dv = a.v; }
-    if (!skip) {
-      FastPoint s;
-      const FT qs = surface_specific_humidity<FT, CT>(d.properties, th, a.p, To, So);
-      const FT Tv = th.virtual_temperature(To, qs);
-      s.gTv = P.g / Tv;
-      s.c1 = 1 + th.delta * qs;
-      s.c2 = th.delta * Tv;
-      s.dudv2 = du * du + dv * dv;
-      s.h_bl = a.h_bl;
-      s.hd = a.z - P.d_zero;
-      s.log_hd = log(s.hd);
-      s.dtheta = (a.T + P.g * a.z / th.cp_m(a.q)) - To;
-      s.dq = a.q - qs;
-      s.ustar = s.theta_star = s.q_star = 1e-4;
-      iters = tab_solve(P, T, tab, s);
-      ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
-    }
-    if (not_water) {  // zero_interface_state (interface_states.jl:800-803)
+    FT du = a.u, dv = a.v, Ts;
+    if (not_water) {  // zero_interface_state (interface_states.jl:800-803): Δu = uₐ − 0
       ustar = 0; theta_star = 0; q_star = 0; Ts = 273.15;
-      if (relative) { du = a.u; dv = a.v; }
+    } else {
+      if (relative) {
+        du -= d.uo.ptr ? (slot_at<FT>(d.uo, idx) + slot_at<FT>(d.uo, idx + 1)) / 2 : (FT)d.uo.value;
+        dv -= d.vo.ptr ? (slot_at<FT>(d.vo, idx) + slot_at<FT>(d.vo, idx + L.sx)) / 2 : (FT)d.vo.value;
+      }
+      Ts = slot_at<FT>(d.To, idx);
+      if (celsius) Ts = Ts + 273.15;
     }
     FluxEpilogue<FT, CT> e(th, a, ustar, theta_star, q_star, du, dv, false);
     ((FT*)d.latent_heat)[idx] = e.Qv;
@@ -309,15 +320,24 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
         const int waves = tw ? std::atoi(tw) : 8;
         const int64_t tiles = (n + 255) / 256;
         const unsigned tb = (unsigned)std::min<int64_t>(tiles, (int64_t)sms * tminb * waves);
-#define NE_LAUNCH_TAB(MB)                                                                                              \
-  do {                                                                                                                 \
-    if (ct64) ao_flux_tab_kernel<double, MB><<<tb, 256, 0, s>>>(*d, L, Thermo<double>::make(d->thermo), P, tabs->T, tabs->dptr); \
-    else ao_flux_tab_kernel<float, MB><<<tb, 256, 0, s>>>(*d, L, Thermo<float>::make(d->thermo), P, tabs->T, tabs->dptr);        \
+        const bool hs = !d->surface_layer_height.ptr && !d->boundary_layer_height.ptr;
+        TabParams TP = tabs->T;
+        TP.log_hd = std::log(d->surface_layer_height.value - P.d_zero);
+#define NE_LAUNCH_TAB2(MB, HS)                                                                                          \
+  do {                                                                                                                  \
+    if (ct64) ao_flux_tab_kernel<double, MB, HS><<<tb, 256, 0, s>>>(*d, L, Thermo<double>::make(d->thermo), P, TP, tabs->dptr); \
+    else ao_flux_tab_kernel<float, MB, HS><<<tb, 256, 0, s>>>(*d, L, Thermo<float>::make(d->thermo), P, TP, tabs->dptr);        \
+  } while (0)
+#define NE_LAUNCH_TAB(MB)          \
+  do {                             \
+    if (hs) NE_LAUNCH_TAB2(MB, true); \
+    else NE_LAUNCH_TAB2(MB, false);   \
   } while (0)
         if (tminb == 2) NE_LAUNCH_TAB(2);
         else if (tminb == 3) NE_LAUNCH_TAB(3);
         else NE_LAUNCH_TAB(4);
 #undef NE_LAUNCH_TAB
+#undef NE_LAUNCH_TAB2
         NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(tab)");
         return NE_OK;
       }

@@ -17,6 +17,7 @@ namespace ne {
 struct TabParams {
   fm::MathConsts mc;
   double cbrt_floor;     // (gmin/β)³/8: below it β·cbrt(x) < gmin, so the clamp cannot change U_G
+  double log_hd;         // log(surface_layer_height − d) when the height is a scalar (set per launch)
   int32_t same_exp;      // ψ_m and ψ_s stable branches share exp(−min(ζmax, A⁺ζ))
   int32_t pad_;
 };
@@ -58,8 +59,8 @@ inline long double psi_s_stable_ld(const double* p, long double z) {
   return -powl(1 + Bp * z, Cp) - Bp * (z - Dp) * expl(-dz) - Ep;
 }
 
-// Fills tab[TAB_SIZE] and T; returns the max abs error of the ψ polynomials (double Horner vs the
-// long-double closed forms) over all intervals.
+// Fills tab[TAB_SIZE] and T; returns the max error of the ψ polynomials (double evaluation vs the
+// long-double closed forms, relative to max(1, |ψ|)) over all intervals.
 inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabParams& T) {
   using namespace fm;
   // log table
@@ -70,6 +71,7 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
     tab[TAB_LOG + 2 * i] = invc;
     tab[TAB_LOG + 2 * i + 1] = (double)(-logl((long double)invc));
   }
+  fill_literals(T.mc);
   for (int k = 0; k < LOG_DEG; ++k) T.mc.logp[k] = ((k & 1) ? 1.0 : -1.0) / (double)(k + 2);   // −1/2, +1/3, −1/4 …
   {  // e^r on |r| ≤ 0.35, monomials in r
     double cw[EXP_DEG + 1];
@@ -83,11 +85,11 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
   double worst = 0;
   for (int iv = 0; iv < PSI_NI; ++iv) {
     long double lo, hi;
-    bool stable = false;
-    if (iv == 0) { lo = 0; hi = ldexpl(1, PSI_OCT_LO); }
-    else if (iv == PSI_NQ + 1) { lo = 0; hi = ldexpl(1, PSI_OCT_LO); stable = true; }
+    const bool stable = iv >= PSI_NS;
+    const int r = stable ? iv - PSI_NS : iv;
+    if (r == 0) { lo = 0; hi = ldexpl(1, PSI_OCT_LO); }
     else {
-      const int q = iv - 1, e = PSI_OCT_LO + (q >> 2), s = q & 3;
+      const int q = r - 1, e = PSI_OCT_LO + (q >> 2), s = q & 3;
       lo = ldexpl(1 + s / 4.0L, e); hi = ldexpl(1 + (s + 1) / 4.0L, e);
     }
     double* rec = tab + TAB_PSI + iv * PSI_REC;
@@ -104,8 +106,32 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
       const double az = (double)(lo + (hi - lo) * n / 48.0L);
       double m, s;
       psi_pair(rec, az, m, s);
-      const double em = (double)fabsl((long double)m - fmf(az)), es = (double)fabsl((long double)s - fsf(az));
+      const long double tm = fmf(az), ts = fsf(az);   // error relative to max(1, |ψ|): Π = log(h/ℓ) − ψ + ψ is O(1…|ψ|)
+      const double em = (double)(fabsl((long double)m - tm) / fmaxl(1, fabsl(tm)));
+      const double es = (double)(fabsl((long double)s - ts) / fmaxl(1, fabsl(ts)));
       if (!(em <= worst)) worst = em;   // also catches NaN
+      if (!(es <= worst)) worst = es;
+    }
+  }
+  for (int side = 0; side < 2; ++side) {   // |ζ| < 2^TINY_EXP records
+    const bool stable = side == 1;
+    const long double lo = 0, hi = ldexpl(1, TINY_EXP);
+    double* rec = tab + TAB_TINY + side * TINY_REC;
+    const long double half = (hi - lo) / 2, mid = (hi + lo) / 2;
+    rec[0] = (double)(1 / half);
+    rec[1] = (double)(-mid / half);
+    double cm[TINY_DEG + 1], cs[TINY_DEG + 1];
+    auto fmf = [&](long double az) { return stable ? psi_m_stable_ld(pm, az) : psi_m_unstable_ld(pm, -az); };
+    auto fsf = [&](long double az) { return stable ? psi_s_stable_ld(ps, az) : psi_s_unstable_ld(ps, -az); };
+    cheb_fit_monomial(fmf, lo, hi, TINY_DEG, cm);
+    cheb_fit_monomial(fsf, lo, hi, TINY_DEG, cs);
+    for (int k = 0; k <= TINY_DEG; ++k) { rec[2 + 2 * k] = cm[k]; rec[2 + 2 * k + 1] = cs[k]; }
+    for (int n = 0; n <= 48; ++n) {
+      const double az = (double)(lo + (hi - lo) * n / 48.0L);
+      double m, s;
+      psi_tiny_pair(rec, az, az, m, s);
+      const double em = (double)fabsl((long double)m - fmf(az)), es = (double)fabsl((long double)s - fsf(az));
+      if (!(em <= worst)) worst = em;
       if (!(es <= worst)) worst = es;
     }
   }
@@ -114,6 +140,7 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
   T.cbrt_floor = ratio * ratio * ratio / 8;
   T.same_exp = (pm[0] == ps[0] && pm[1] == ps[1]);
   T.pad_ = 0;
+  T.log_hd = 0;
   return worst;
 }
 
@@ -126,7 +153,7 @@ inline bool tab_path_eligible(const NeFluxFormulation& f) {
 
 #if defined(__CUDACC__)
 // unstable closed forms through libdevice for |ζ| ≥ 2^7 (free-convection limit; rare)
-__device__ __noinline__ void psi_far_unstable(const FastParams& P, double z, double& pm, double& ps) {
+__device__ __forceinline__ void psi_far_unstable(const FastParams& P, double z, double& pm, double& ps) {
   pm = fast_psi_m(P, z);   // |z| ≥ 2^7 > P.zsmall: the closed-form branch
   ps = fast_psi_s(P, z);
 }
@@ -143,50 +170,64 @@ __device__ __forceinline__ void psi_stable_pair(const FastParams& P, const TabPa
   ps = -xp - P.s_Bp * (z - P.s_Dp) * es - P.s_Ep;
 }
 
+// closed forms outside the table: stable side with the custom exp, far unstable side through libdevice.
+// Out of line and returning by value, so the common path keeps ψ in registers.
+__device__ __noinline__ double2 psi_outside(const FastParams& P, const TabParams& T, double z) {
+  double pm, ps;
+  if (z > 0) psi_stable_pair(P, T, z, pm, ps);
+  else psi_far_unstable(P, z, pm, ps);
+  return make_double2(pm, ps);
+}
+
 // ψ_m(ζ), ψ_s(ζ) at the same ζ
 __device__ __forceinline__ void tab_psi_pair(const FastParams& P, const TabParams& T, const double* tab, double z,
                                              double& pm, double& ps) {
-  const int iv = fm::psi_interval(z);
-  if (iv >= 0) fm::psi_pair(tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(z), pm, ps);
-  else if (z > 0) psi_stable_pair(P, T, z, pm, ps);
-  else psi_far_unstable(P, z, pm, ps);
+  bool outside;
+  const int iv = fm::psi_interval(z, outside);
+  if (!outside) {
+    fm::psi_pair(tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(z), pm, ps);
+  } else {
+    const double2 r = psi_outside(P, T, z);
+    pm = r.x; ps = r.y;
+  }
 }
 
-// out-of-line copy for the rare case where ψ(ℓ/L★) leaves the small-|ζ| intervals
-__device__ __noinline__ void tab_psi_pair_rare(const FastParams& P, const TabParams& T, const double* tab, double z,
-                                               double& pm, double& ps) {
+// out-of-line general lookup for the rare case where ψ(ℓ/L★) leaves the tiny-|ζ| records
+__device__ __noinline__ double2 tab_psi_pair_rare(const FastParams& P, const TabParams& T, const double* tab, double z) {
+  double pm, ps;
   tab_psi_pair(P, T, tab, z, pm, ps);
+  return make_double2(pm, ps);
 }
 
 __device__ __forceinline__ void tab_iteration(const FastParams& P, const TabParams& T, const double* tab, FastPoint& s) {
+  using fm::dmax;
+  using fm::dmin;
   const double bstar = s.gTv * (s.theta_star * s.c1 + s.c2 * s.q_star);
   const double Jb = -s.ustar * bstar;
-  const double UG = fmax(P.gmin, P.beta * fm::cbrt_pos(fmax(fmax(0.0, Jb) * s.h_bl, T.cbrt_floor)));
+  const double UG = dmax(P.gmin, P.beta * fm::cbrt_pos(T.mc, dmax(dmax(0.0, Jb) * s.h_bl, T.cbrt_floor)));
   const double U = fm::sqrt_pos(s.dudv2 + UG * UG);
   const double ru = fm::rcp(s.ustar);
-  const double lu = fmin(P.a1 * s.ustar * s.ustar + P.a2 * ru, P.lmax);
+  const double lu = dmin(P.a1 * s.ustar * s.ustar + P.a2 * ru, P.lmax);
   const double log_lu = fm::log_pos(tab, T.mc, lu);
   const double log_Rs = fm::log_pos(tab, T.mc, lu * s.ustar * P.nu_inv);
   const double log_ls_un = P.log_rA - P.rb * log_Rs;
   const bool clipped = log_ls_un > P.log_ls_max;
   const double log_ls = clipped ? P.log_ls_max : log_ls_un;
-  const double ls = clipped ? P.ls_max : fm::exp_mid(T.mc, fmax(log_ls_un, -700.0));
+  const double ls_un = fm::exp_mid(T.mc, dmax(log_ls_un, -700.0));
+  const double ls = clipped ? P.ls_max : ls_un;
   const bool lifted = 2.0 * lu > s.hd;
   const double dh = lifted ? 2.0 * lu : s.hd;
-  const double log_dh = lifted ? 0.6931471805599453 + log_lu : s.log_hd;
+  const double log_dh = lifted ? T.mc.ln2 + log_lu : s.log_hd;
   const double Linv = P.kappa * bstar * ru * ru;   // 1/L★ (0 when b★ == 0, i.e. L★ = Inf)
   double pm_h, ps_h, pm_l, ps_l;
   tab_psi_pair(P, T, tab, dh * Linv, pm_h, ps_h);
-  // ψ(ℓ/L★): |ℓ/L★| ≪ 2^-6 in practice → both land in a small-|ζ| interval; general lookup otherwise
+  // ψ(ℓ/L★): |ℓ/L★| < 2^-12 except in the first trips from the 1e-4 initial guess
   const double zu = lu * Linv, zs = ls * Linv;
-  const int ivu = fm::psi_interval(zu), ivs = fm::psi_interval(zs);
-  if (ivu >= 0 && ivs >= 0) {
-    pm_l = fm::psi_one(tab + fm::TAB_PSI + ivu * fm::PSI_REC, fabs(zu), 0);
-    ps_l = fm::psi_one(tab + fm::TAB_PSI + ivs * fm::PSI_REC, fabs(zs), 1);
+  if (fm::psi_is_tiny(zu) && fm::psi_is_tiny(zs)) {
+    fm::psi_tiny_pair(tab + fm::TAB_TINY + (Linv < 0 ? 0 : fm::TINY_REC), fabs(zu), fabs(zs), pm_l, ps_l);
   } else {
-    double dummy;
-    tab_psi_pair_rare(P, T, tab, zu, pm_l, dummy);
-    tab_psi_pair_rare(P, T, tab, zs, dummy, ps_l);
+    pm_l = tab_psi_pair_rare(P, T, tab, zu).x;
+    ps_l = tab_psi_pair_rare(P, T, tab, zs).y;
   }
   const double Pi_u = (log_dh - log_lu) - pm_h + pm_l;
   const double Pi_s = (log_dh - log_ls) - ps_h + ps_l;
@@ -196,17 +237,20 @@ __device__ __forceinline__ void tab_iteration(const FastParams& P, const TabPara
   s.q_star = chi_s * s.dq;
 }
 
+// compute_interface_state.jl:10-18: the first trip always runs; then until drift < tol or it ≥ maxiter
+// (FixedIterations: exactly maxiter trips)
 __device__ __forceinline__ int tab_solve(const FastParams& P, const TabParams& T, const double* tab, FastPoint& s) {
+  if (P.fixed && P.maxiter <= 0) return 0;
+  const double tol = P.fixed ? -1.0 : P.tol;   // drift ≥ 0 > −1: never "converged" under FixedIterations
+  const int maxiter = P.maxiter;
   int it = 0;
-  double drift = 0;
-  for (;;) {
-    const bool go = P.fixed ? (it < P.maxiter) : (!((drift < P.tol) | (it >= P.maxiter)) | (it == 0));
-    if (!go) break;
+  double drift;
+  do {
     const double pu = s.ustar, pt = s.theta_star, pq = s.q_star;
     tab_iteration(P, T, tab, s);
     drift = fabs(s.ustar - pu) + fabs(s.theta_star - pt) + fabs(s.q_star - pq);
     ++it;
-  }
+  } while (!(drift < tol) && it < maxiter);
   return it;
 }
 #endif  // __CUDACC__

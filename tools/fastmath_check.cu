@@ -44,8 +44,8 @@ int main() {
   double e_rcp = max_ulp([](double x) { return fm::rcp(x); }, [](long double x) { return 1 / x; }, 1e-6, 1e6, true, 400000, rng);
   double e_div = max_ulp([](double x) { return fm::div(0.4, x); }, [](long double x) { return 0.4L * 1 / x * 1.0L == 0 ? 0 : (long double)0.4 / x; }, 1e-3, 1e3, true, 400000, rng);
   double e_sqrt = max_ulp([](double x) { return fm::sqrt_pos(x); }, [](long double x) { return sqrtl(x); }, 1e-8, 1e8, true, 400000, rng);
-  double e_cbrt = max_ulp([](double x) { return fm::cbrt_pos(x); }, [](long double x) { return cbrtl(x); }, 1e-12, 1e12, true, 400000, rng);
-  double e_cbrt2 = max_ulp([](double x) { return fm::cbrt_pos(x); }, [](long double x) { return cbrtl(x); }, 1e-300, 1e300, true, 400000, rng);
+  double e_cbrt = max_ulp([&](double x) { return fm::cbrt_pos(T.mc, x); }, [](long double x) { return cbrtl(x); }, 1e-12, 1e12, true, 400000, rng);
+  double e_cbrt2 = max_ulp([&](double x) { return fm::cbrt_pos(T.mc, x); }, [](long double x) { return cbrtl(x); }, 1e-300, 1e300, true, 400000, rng);
   // log: relative error away from 1, absolute error (in units of 2^-53) near 1
   double e_log = max_ulp([&](double x) { return fm::log_pos(tab, T.mc, x); }, [](long double x) { return logl(x); }, 1e-12, 0.5, true, 400000, rng);
   double e_log_hi = max_ulp([&](double x) { return fm::log_pos(tab, T.mc, x); }, [](long double x) { return logl(x); }, 2.0, 1e12, true, 400000, rng);
@@ -68,30 +68,53 @@ int main() {
     std::uniform_real_distribution<double> u(0, 1);
     for (int i = 0; i < 400000; ++i) {
       double az = std::exp(std::log(1e-9) + u(rng) * (std::log(127.99) - std::log(1e-9)));
-      int iv = fm::psi_interval(-az);
-      if (iv < 0) { e_psi = 1e300; break; }
+      bool outside;
+      int iv = fm::psi_interval(-az, outside);
+      if (outside) { e_psi = 1e300; break; }
       double m, s;
       fm::psi_pair(tab + fm::TAB_PSI + iv * fm::PSI_REC, az, m, s);
-      double em = (double)fabsl((long double)m - psi_m_unstable_ld(pm, -(long double)az));
-      double es = (double)fabsl((long double)s - psi_s_unstable_ld(ps, -(long double)az));
+      auto rel = [](double got, long double t) { return (double)(fabsl((long double)got - t) / fmaxl(1, fabsl(t))); };
+      double em = rel(m, psi_m_unstable_ld(pm, -(long double)az));
+      double es = rel(s, psi_s_unstable_ld(ps, -(long double)az));
       if (!(em <= e_psi)) e_psi = em;
       if (!(es <= e_psi)) e_psi = es;
-      if (az < 0.015625) {
-        iv = fm::psi_interval(az);
+      {
+        iv = fm::psi_interval(az, outside);
+        if (outside) { e_psi = 1e300; break; }
         fm::psi_pair(tab + fm::TAB_PSI + iv * fm::PSI_REC, az, m, s);
-        em = (double)fabsl((long double)m - psi_m_stable_ld(pm, (long double)az));
-        es = (double)fabsl((long double)s - psi_s_stable_ld(ps, (long double)az));
+        em = rel(m, psi_m_stable_ld(pm, (long double)az));
+        es = rel(s, psi_s_stable_ld(ps, (long double)az));
         if (!(em <= e_psi)) e_psi = em;
         if (!(es <= e_psi)) e_psi = es;
       }
     }
   }
-  int iv_ok = fm::psi_interval(-128.0) == -1 && fm::psi_interval(0.5) == -1 && fm::psi_interval(0.0) == fm::PSI_NQ + 1 &&
-              fm::psi_interval(-1e-300) == 0 && fm::psi_interval(-0.015625) == 1 && fm::psi_interval(-127.9) == fm::PSI_NQ &&
-              fm::psi_interval(NAN) == -1;
+  auto iv = [](double z) { bool o; int i = fm::psi_interval(z, o); return o ? -1 : i; };
+  int iv_ok = iv(-128.0) == -1 && iv(128.0) == -1 && iv(0.5) == fm::PSI_NS + 21 && iv(0.0) == fm::PSI_NS && iv(-1e-300) == 0 &&
+              iv(-0.015625) == 1 && iv(-127.9) == fm::PSI_NQ && iv(NAN) == -1 && iv(-1e300) == -1 && iv(0.015) == fm::PSI_NS &&
+              iv(127.9) == fm::PSI_NS + fm::PSI_NQ &&
+              fm::psi_is_tiny(std::ldexp(0.99, fm::TINY_EXP)) && !fm::psi_is_tiny(std::ldexp(1.0, fm::TINY_EXP)) && fm::psi_is_tiny(-1e-9) && !fm::psi_is_tiny(NAN);
+  double e_tiny = 0;
+  {
+    std::uniform_real_distribution<double> u(0, 1);
+    for (int i = 0; i < 200000; ++i) {
+      double az = std::exp(std::log(1e-12) + u(rng) * (std::log(std::ldexp(0.9999, fm::TINY_EXP)) - std::log(1e-12)));
+      double m, s;
+      fm::psi_tiny_pair(tab + fm::TAB_TINY, az, az * 0.7, m, s);
+      double em = (double)fabsl((long double)m - psi_m_unstable_ld(pm, -(long double)az));
+      double es = (double)fabsl((long double)s - psi_s_unstable_ld(ps, -(long double)(az * 0.7)));
+      if (!(em <= e_tiny)) e_tiny = em;
+      if (!(es <= e_tiny)) e_tiny = es;
+      fm::psi_tiny_pair(tab + fm::TAB_TINY + fm::TINY_REC, az, az * 0.7, m, s);
+      em = (double)fabsl((long double)m - psi_m_stable_ld(pm, (long double)az));
+      es = (double)fabsl((long double)s - psi_s_stable_ld(ps, (long double)(az * 0.7)));
+      if (!(em <= e_tiny)) e_tiny = em;
+      if (!(es <= e_tiny)) e_tiny = es;
+    }
+  }
   printf("{\"rcp_ulp\": %.3f, \"div_ulp\": %.3f, \"sqrt_ulp\": %.3f, \"cbrt_ulp\": %.3f, \"cbrt_wide_ulp\": %.3f, "
          "\"log_ulp_small\": %.3f, \"log_ulp_large\": %.3f, \"log_abs_near1_ulp1\": %.3f, \"exp_ulp\": %.3f, \"exp_ulp_mid\": %.3f, "
-         "\"psi_fit_abs\": %.3e, \"psi_dense_abs\": %.3e, \"interval_logic_ok\": %d, \"cbrt_floor\": %.6e, \"same_exp\": %d}\n",
-         e_rcp, e_div, e_sqrt, e_cbrt, e_cbrt2, e_log, e_log_hi, e_log_abs, e_exp, e_exp2, fit, e_psi, iv_ok, T.cbrt_floor, T.same_exp);
+         "\"psi_fit_err\": %.3e, \"psi_dense_err\": %.3e, \"psi_tiny_abs\": %.3e, \"interval_logic_ok\": %d, \"cbrt_floor\": %.6e, \"same_exp\": %d}\n",
+         e_rcp, e_div, e_sqrt, e_cbrt, e_cbrt2, e_log, e_log_hi, e_log_abs, e_exp, e_exp2, fit, e_psi, e_tiny, iv_ok, T.cbrt_floor, T.same_exp);
   return 0;
 }
