@@ -453,6 +453,11 @@ int ne_apply_radiative_fluxes_f32(const NeApplyRadiationDesc*, void* stream);
 
 int ne_fused_interface_step_f64(const NeFusedStepDesc*, void* stream);
 int ne_fused_interface_step_f32(const NeFusedStepDesc*, void* stream);
+/* Phases 1-2 of the fused step only (both interpolations + the a–o solve; `assemble` and
+ * `apply_radiation` are ignored): interpolate_state! + compute_atmosphere_ocean_fluxes!
+ * (time_step_earth_system_model.jl:38-62) as one kernel when the configuration qualifies. */
+int ne_interp_and_ao_fluxes_f64(const NeFusedStepDesc*, void* stream);
+int ne_interp_and_ao_fluxes_f32(const NeFusedStepDesc*, void* stream);
 
 int ne_diag_reduce_f64(const NeDiagDesc*, void* stream);
 int ne_diag_reduce_f32(const NeDiagDesc*, void* stream);

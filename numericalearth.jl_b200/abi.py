@@ -247,6 +247,7 @@ DESC_ENTRY_POINTS = {
     "ne_assemble_net_sea_ice_fluxes": NeAssembleSeaIceDesc,
     "ne_apply_radiative_fluxes": NeApplyRadiationDesc,
     "ne_fused_interface_step": NeFusedStepDesc,
+    "ne_interp_and_ao_fluxes": NeFusedStepDesc,
     "ne_diag_reduce": NeDiagDesc,
 }
 OTHER_ENTRY_POINTS = ["ne_version", "ne_last_error", "ne_device_count", "ne_memcpy_h2d", "ne_memcpy_d2h",

@@ -22,6 +22,7 @@
 
 #include "ne_flux_fast.cuh"
 #include "ne_flux_tab.cuh"
+#include "ne_interp_device.cuh"
 #include "ne_physics.cuh"
 
 namespace ne {
@@ -186,6 +187,153 @@ ao_flux_tab_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_cons
   }
 }
 
+// ---- fused interpolation + atmosphere–ocean solve (update_state! phases 1 and 2 in one pass) ----------
+// Per point: fractional indices → gathers of the 7 atmosphere series (+ 2 radiation series) at the two
+// bracketing time levels from the L2-resident source → optional stores of the interpolated state (an
+// output pointer left NULL is never materialised in HBM) → table-driven solve → 9 flux outputs.  The
+// interpolated (T, p, q, Δu, Δv) the flux epilogue needs are parked in shared memory during the solve so
+// they do not occupy registers across the iteration.  The solve never reads the interpolated state back
+// from HBM: 5 field reads per point fewer than the unfused sequence, and one launch instead of three.
+template <class CT, class AT, class TT, int MINB, bool HS>
+__global__ void __launch_bounds__(256, MINB)
+ao_fused_tab_kernel(const __grid_constant__ NeInterpDesc atm, const __grid_constant__ NeInterpDesc rad,
+                    const __grid_constant__ NeAtmosOceanDesc d, const __grid_constant__ Layout L,
+                    const __grid_constant__ InterpSource Sa, const __grid_constant__ InterpSource Sr,
+                    const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P,
+                    const __grid_constant__ TabParams T, const double* __restrict__ gtab) {
+  __shared__ __align__(16) double tab[fm::TAB_SIZE];
+  __shared__ double park[5][256];
+  for (int k = threadIdx.x; k < fm::TAB_SIZE / 2; k += 256)
+    reinterpret_cast<double2*>(tab)[k] = __ldg(reinterpret_cast<const double2*>(gtab) + k);
+  __syncthreads();
+  using FT = double;
+  const int64_t n = (int64_t)L.ni * L.nj;
+  const bool celsius = d.ocean.temperature_units == NE_DEGREES_CELSIUS;
+  const bool relative = d.properties.velocity_formulation == NE_VEL_RELATIVE;
+  const TT nta = (TT)atm.time.frac, ntr = (TT)rad.time.frac;
+  const bool same_a = atm.time.same != 0, same_r = rad.time.same != 0;
+  const int tid = threadIdx.x;
+  const bool has_rad = rad.n_fields > 0;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  auto index_of = [&](int64_t t) {
+    const int32_t jj = (int32_t)(t / L.ni);
+    return L.at(L.i_lo + (int32_t)(t - (int64_t)jj * L.ni), L.j_lo + jj);
+  };
+  int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  // the fractional indices of the NEXT tile are requested before the current solve starts, so their
+  // DRAM latency is hidden behind ~10^4 cycles of arithmetic
+  FracPair<AT> fa = {0, 0}, fr = {0, 0};
+  if (t < n) {
+    const int64_t idx0 = index_of(t);
+    fa = load_frac<AT>(atm.frac_i, atm.frac_j, idx0);
+    if (has_rad) fr = load_frac<AT>(rad.frac_i, rad.frac_j, idx0);
+  }
+  for (; t < n; t += stride) {
+    const int64_t idx = index_of(t);
+    const bool not_water = d.inactive ? (d.inactive[idx] != 0) : false;
+    const bool skip = not_water && !P.fixed;   // needs_to_converge && not_water (:144)
+
+    FT ustar = 0, theta_star = 0, q_star = 0;
+    int iters = 0;
+    {
+      // ---- phase 1: interpolation (interpolate_atmospheric_state.jl:91-137, interpolate_radiation_state.jl:43-69)
+      // all gathers of the point are issued before any of them is consumed
+      const InterpPoint<AT> pa = interp_point<AT>(atm.frac_i != nullptr, atm.frac_j != nullptr, fa, Sa);
+      const InterpPoint<AT> pr = interp_point<AT>(rad.frac_i != nullptr, rad.frac_j != nullptr, fr, Sr);
+      if (t + stride < n) {
+        const int64_t idxn = index_of(t + stride);
+        fa = load_frac<AT>(atm.frac_i, atm.frac_j, idxn);
+        if (has_rad) fr = load_frac<AT>(rad.frac_i, rad.frac_j, idxn);
+      }
+      Corners8<AT> c[5];
+#pragma unroll
+      for (int f = 0; f < 5; ++f) c[f] = gather8<AT>((const AT*)atm.series[f][0].data, pa, Sa, same_a);   // u v T q p
+      Corners8<AT> cr[2], cp[2];
+      bool simple_r[2], simple_p[2];
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        simple_r[f] = has_rad && f < rad.n_fields && rad.out[f] && rad.n_summands[f] == 1 && rad.series[f][0].data;
+        if (simple_r[f]) cr[f] = gather8<AT>((const AT*)rad.series[f][0].data, pr, Sr, same_r);
+        simple_p[f] = 5 + f < atm.n_fields && atm.out[5 + f] && atm.n_summands[5 + f] == 1 && atm.series[5 + f][0].data;
+        if (simple_p[f]) cp[f] = gather8<AT>((const AT*)atm.series[5 + f][0].data, pa, Sa, same_a);
+      }
+      FT st[5];
+#pragma unroll
+      for (int f = 0; f < 5; ++f) {
+        st[f] = (FT)blend8<AT, TT>(c[f], pa, nta, same_a);
+        if (atm.out[f]) ((FT*)atm.out[f])[idx] = st[f];
+      }
+      if (atm.potential) {
+        const int pf = atm.potential_from;
+        const FT v = pf == 0 ? st[0] : pf == 1 ? st[1] : pf == 2 ? st[2] : pf == 3 ? st[3] : st[4];
+        ((FT*)atm.potential)[idx] = div_rn(v, (FT)atm.ocean_reference_density);
+      }
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        if (simple_r[f]) ((FT*)rad.out[f])[idx] = (FT)blend8<AT, TT>(cr[f], pr, ntr, same_r);
+        else if (has_rad && f < rad.n_fields && rad.out[f]) ((FT*)rad.out[f])[idx] = (FT)interp_field<AT, TT>(rad, f, pr, Sr, ntr, same_r);
+        if (simple_p[f]) ((FT*)atm.out[5 + f])[idx] = (FT)blend8<AT, TT>(cp[f], pa, nta, same_a);   // rain, snow: only written
+        else if (5 + f < atm.n_fields && atm.out[5 + f]) ((FT*)atm.out[5 + f])[idx] = (FT)interp_field<AT, TT>(atm, 5 + f, pa, Sa, nta, same_a);
+      }
+      const FT au = st[0], av = st[1], aT = st[2], aq = st[3], ap = st[4];
+      // ---- phase 2: the solve (atmosphere_ocean_fluxes.jl:80-197)
+      FT du = au, dv = av;
+      if (relative && !not_water) {
+        du -= d.uo.ptr ? (slot_at<FT>(d.uo, idx) + slot_at<FT>(d.uo, idx + 1)) / 2 : (FT)d.uo.value;
+        dv -= d.vo.ptr ? (slot_at<FT>(d.vo, idx) + slot_at<FT>(d.vo, idx + L.sx)) / 2 : (FT)d.vo.value;
+      }
+      park[0][tid] = du; park[1][tid] = dv; park[2][tid] = aT; park[3][tid] = ap; park[4][tid] = aq;
+      if (!skip) {
+        FastPoint s;
+        if (relative && not_water) {   // FixedIterations solves inactive cells too, with the ocean velocity
+          du -= d.uo.ptr ? (slot_at<FT>(d.uo, idx) + slot_at<FT>(d.uo, idx + 1)) / 2 : (FT)d.uo.value;
+          dv -= d.vo.ptr ? (slot_at<FT>(d.vo, idx) + slot_at<FT>(d.vo, idx + L.sx)) / 2 : (FT)d.vo.value;
+        }
+        const FT az = HS ? (FT)d.surface_layer_height.value : slot_at<FT>(d.surface_layer_height, idx);
+        FT To = slot_at<FT>(d.To, idx);
+        if (celsius) To = To + 273.15;
+        const FT qs = surface_specific_humidity<FT, CT>(d.properties, th, ap, To, slot_at<FT>(d.So, idx));
+        const FT Tv = th.virtual_temperature(To, qs);
+        s.gTv = P.g / Tv;
+        s.c1 = 1 + th.delta * qs;
+        s.c2 = th.delta * Tv;
+        s.dudv2 = du * du + dv * dv;
+        s.h_bl = HS ? (FT)d.boundary_layer_height.value : slot_at<FT>(d.boundary_layer_height, idx);
+        s.hd = az - P.d_zero;
+        s.log_hd = HS ? T.log_hd : log(s.hd);
+        s.dtheta = (aT + P.g * az / th.cp_m(aq)) - To;
+        s.dq = aq - qs;
+        s.ustar = s.theta_star = s.q_star = 1e-4;
+        iters = tab_solve(P, T, tab, s);
+        ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
+      }
+    }
+    // ---- epilogue (atmosphere_ocean_fluxes.jl:160-196)
+    AtmosState<FT> a;
+    a.u = 0; a.v = 0; a.z = 0; a.h_bl = 0;
+    const FT du = park[0][tid], dv = park[1][tid];
+    a.T = park[2][tid]; a.p = park[3][tid]; a.q = park[4][tid];
+    FT Ts;
+    if (not_water) {  // zero_interface_state (interface_states.jl:800-803): Δu = uₐ − 0 (parked as such)
+      ustar = 0; theta_star = 0; q_star = 0; Ts = 273.15;
+    } else {
+      Ts = slot_at<FT>(d.To, idx);
+      if (celsius) Ts = Ts + 273.15;
+    }
+    FluxEpilogue<FT, CT> e(th, a, ustar, theta_star, q_star, du, dv, false);
+    ((FT*)d.latent_heat)[idx] = e.Qv;
+    ((FT*)d.sensible_heat)[idx] = e.Qc;
+    ((FT*)d.water_vapor)[idx] = e.Jv;
+    ((FT*)d.x_momentum)[idx] = e.tx;
+    ((FT*)d.y_momentum)[idx] = e.ty;
+    ((FT*)d.interface_temperature)[idx] = celsius ? Ts - 273.15 : Ts;
+    ((FT*)d.friction_velocity)[idx] = ustar;
+    ((FT*)d.temperature_scale)[idx] = theta_star;
+    ((FT*)d.water_vapor_scale)[idx] = q_star;
+    if (d.iterations) d.iterations[idx] = iters;
+  }
+}
+
 // Device-resident solver tables, built once per (device, ψ parameter set) and kept for the life of the
 // process (14 KB each).  The first call for a parameter set allocates and copies synchronously, so it
 // must happen outside CUDA-graph capture; later calls only enqueue the kernel.
@@ -284,11 +432,11 @@ static bool viscosity_is_f64_literal(const NeFluxFormulation& f) {
   return false;
 }
 
-template <class FT>
-static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
+static int validate_ao(const NeAtmosOceanDesc* d, bool need_atmosphere_arrays) {
   NE_REQUIRE(d != nullptr, "null descriptor");
   NE_REQUIRE(grid_ok(d->grid, 0, 1), "atmosphere-ocean: launch range + (i+1, j+1) stencil leaves the parent array");
-  NE_REQUIRE(d->ua && d->va && d->Ta && d->pa && d->qa, "atmosphere-ocean: null atmosphere state array");
+  if (need_atmosphere_arrays)
+    NE_REQUIRE(d->ua && d->va && d->Ta && d->pa && d->qa, "atmosphere-ocean: null atmosphere state array");
   NE_REQUIRE(d->latent_heat && d->sensible_heat && d->water_vapor && d->x_momentum && d->y_momentum &&
              d->interface_temperature && d->friction_velocity && d->temperature_scale && d->water_vapor_scale,
              "atmosphere-ocean: null output array");
@@ -297,29 +445,48 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
   if (d->properties.temperature_formulation == NE_TEMP_SKIN_DIFFUSIVE_INTERIOR)
     NE_REQUIRE(d->kappa != nullptr, "InteriorDiffusivity needs the kappa array");
   if (d->radiation.enabled) NE_REQUIRE(d->radiation.downwelling_shortwave && d->radiation.downwelling_longwave, "radiation enabled without SW/LW arrays");
+  return NE_OK;
+}
+
+static bool env_flag(const char* name) {
+  const char* v = std::getenv(name);
+  return v && v[0] == '1';
+}
+
+// grid size of the table-driven kernels: enough 256-thread CTAs for `waves` rounds of full residency
+static unsigned tab_grid(int64_t n, int minb) {
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const char* tw = std::getenv("NE_B200_TAB_WAVES");
+  const int waves = tw ? std::atoi(tw) : 8;
+  const int64_t tiles = (n + 255) / 256;
+  return (unsigned)std::min<int64_t>(tiles, (int64_t)sms * minb * waves);
+}
+static int tab_minb() {
+  const char* tm = std::getenv("NE_B200_TAB_MINB");   // occupancy experiment knob (profiles/r01_notes.md)
+  const int m = tm ? std::atoi(tm) : 3;
+  return (m == 2 || m == 4) ? m : 3;
+}
+
+template <class FT>
+static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
+  int rc = validate_ao(d, true);
+  if (rc != NE_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const bool ct64 = d->thermo.dtype == NE_F64;
   const bool v64 = std::is_same<FT, double>::value || viscosity_is_f64_literal(d->flux);
   if (std::is_same<FT, double>::value) {
     // NE_B200_FORCE_GENERIC=1 routes the default tree through the generic kernel (used by the parity tests)
-    const char* force = std::getenv("NE_B200_FORCE_GENERIC");
-    if (fast_path_eligible(d->flux, d->properties, d->thermo) && !(force && force[0] == '1')) {
+    if (fast_path_eligible(d->flux, d->properties, d->thermo) && !env_flag("NE_B200_FORCE_GENERIC")) {
       Layout L = make_layout(d->grid);
       FastParams P = make_fast_params(d->flux, d->gravitational_acceleration);
       const int64_t n = (int64_t)L.ni * L.nj;
       // NE_B200_CLOSED_FORM_PSI=1 keeps the libdevice closed-form iteration (parity-tested both ways)
-      const char* closed = std::getenv("NE_B200_CLOSED_FORM_PSI");
-      const SolverTables* tabs = (closed && closed[0] == '1') || !tab_path_eligible(d->flux) ? nullptr : solver_tables(d->flux);
+      const SolverTables* tabs = env_flag("NE_B200_CLOSED_FORM_PSI") || !tab_path_eligible(d->flux) ? nullptr : solver_tables(d->flux);
       if (tabs) {
-        int sms = 148, dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const char* tm = std::getenv("NE_B200_TAB_MINB");
-        const int tminb = tm ? std::atoi(tm) : 4;
-        const char* tw = std::getenv("NE_B200_TAB_WAVES");
-        const int waves = tw ? std::atoi(tw) : 8;
-        const int64_t tiles = (n + 255) / 256;
-        const unsigned tb = (unsigned)std::min<int64_t>(tiles, (int64_t)sms * tminb * waves);
+        const int tminb = tab_minb();
+        const unsigned tb = tab_grid(n, tminb);
         const bool hs = !d->surface_layer_height.ptr && !d->boundary_layer_height.ptr;
         TabParams TP = tabs->T;
         TP.log_hd = std::log(d->surface_layer_height.value - P.d_zero);
@@ -334,8 +501,8 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
     else NE_LAUNCH_TAB2(MB, false);   \
   } while (0)
         if (tminb == 2) NE_LAUNCH_TAB(2);
-        else if (tminb == 3) NE_LAUNCH_TAB(3);
-        else NE_LAUNCH_TAB(4);
+        else if (tminb == 4) NE_LAUNCH_TAB(4);
+        else NE_LAUNCH_TAB(3);
 #undef NE_LAUNCH_TAB
 #undef NE_LAUNCH_TAB2
         NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(tab)");
@@ -361,6 +528,78 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
     if (ct64) return v64 ? launch_ao<float, double, double>(*d, s) : launch_ao<float, double, float>(*d, s);
     return v64 ? launch_ao<float, float, double>(*d, s) : launch_ao<float, float, float>(*d, s);
   }
+}
+
+static bool same_launch(const NeExchangeGrid& a, const NeExchangeGrid& b) {
+  return a.nx == b.nx && a.ny == b.ny && a.hx == b.hx && a.hy == b.hy && a.i_lo == b.i_lo && a.i_hi == b.i_hi &&
+         a.j_lo == b.j_lo && a.j_hi == b.j_hi;
+}
+
+// Fused interpolation + a–o solve for the default plugin tree in Float64.  Returns NE_OK when the fused kernel
+// was enqueued, +1 when this step does not qualify (the caller then enqueues the component kernels), < 0 on error.
+int fused_interp_ao_f64(const NeInterpDesc* atm, const NeInterpDesc* rad, const NeAtmosOceanDesc* d, void* stream) {
+  // Opt-in (NE_B200_FUSE_INTERP=1): measured on B200 the single-pass kernel is slower than the component
+  // kernels (2.85 vs 2.16 ms on C4): warps parked in the gather phase lower the occupancy the FP64-latency-bound
+  // iteration needs, and the larger code thrashes the instruction cache (profiles/r01_notes.md).
+  if (!env_flag("NE_B200_FUSE_INTERP") || env_flag("NE_B200_FORCE_GENERIC") || env_flag("NE_B200_CLOSED_FORM_PSI")) return 1;
+  if (!atm || !d || !fast_path_eligible(d->flux, d->properties, d->thermo) || !tab_path_eligible(d->flux)) return 1;
+  const bool has_rad = rad && rad->n_fields > 0;
+  if (atm->n_fields < 5 || atm->n_fields > 7 || !same_launch(atm->grid, d->grid)) return 1;
+  for (int f = 0; f < 5; ++f)
+    if (atm->n_summands[f] != 1 || !atm->series[f][0].data) return 1;
+  if (atm->potential && (atm->potential_from < 0 || atm->potential_from > 4)) return 1;
+  if (has_rad && (rad->n_fields > 2 || !same_launch(rad->grid, d->grid) || rad->src_dtype != atm->src_dtype ||
+                  rad->time.frac_dtype != atm->time.frac_dtype)) return 1;
+  int rc = validate_ao(d, false);
+  if (rc != NE_OK) return rc;
+  for (const NeInterpDesc* x : {atm, has_rad ? rad : atm}) {
+    NE_REQUIRE(x->src_nx > 0 && x->src_ny > 0 && x->src_nt > 0, "interp: bad source extents");
+    NE_REQUIRE((x->src_nx + 2 * x->src_hx) * (x->src_ny + 2 * x->src_hy) < (int64_t)1 << 31, "interp: source plane exceeds 2^31 elements");
+    NE_REQUIRE(x->time.m1 >= 1 && x->time.m1 <= x->src_nt && x->time.m2 >= 1 && x->time.m2 <= x->src_nt,
+               "interp: time memory slots out of range");
+    for (int f = 0; f < x->n_fields; ++f)
+      NE_REQUIRE(x->n_summands[f] >= 0 && x->n_summands[f] <= NE_MAX_SUMMANDS, "interp: too many summands");
+  }
+  const SolverTables* tabs = solver_tables(d->flux);
+  if (!tabs) return 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  Layout L = make_layout(d->grid);
+  FastParams P = make_fast_params(d->flux, d->gravitational_acceleration);
+  const int64_t n = (int64_t)L.ni * L.nj;
+  const int tminb = tab_minb() == 4 ? 3 : tab_minb();
+  const unsigned tb = tab_grid(n, tminb);
+  const bool hs = !d->surface_layer_height.ptr && !d->boundary_layer_height.ptr;
+  TabParams TP = tabs->T;
+  TP.log_hd = std::log(d->surface_layer_height.value - P.d_zero);
+  NeInterpDesc norad;
+  std::memset(&norad, 0, sizeof(norad));
+  const NeInterpDesc& r = has_rad ? *rad : norad;
+  const InterpSource Sa = make_interp_source(*atm);
+  InterpSource Sr = Sa;
+  if (has_rad) Sr = make_interp_source(*rad);
+  const bool ct64 = d->thermo.dtype == NE_F64, a64 = atm->src_dtype == NE_F64, t64 = atm->time.frac_dtype == NE_F64;
+#define NE_FUSED4(CT, AT, TT, MB, HS) \
+  ao_fused_tab_kernel<CT, AT, TT, MB, HS><<<tb, 256, 0, s>>>(*atm, r, *d, L, Sa, Sr, Thermo<CT>::make(d->thermo), P, TP, tabs->dptr)
+#define NE_FUSED3(CT, AT, TT)                     \
+  do {                                            \
+    if (tminb == 2) {                             \
+      if (hs) NE_FUSED4(CT, AT, TT, 2, true);     \
+      else NE_FUSED4(CT, AT, TT, 2, false);       \
+    } else {                                      \
+      if (hs) NE_FUSED4(CT, AT, TT, 3, true);     \
+      else NE_FUSED4(CT, AT, TT, 3, false);       \
+    }                                             \
+  } while (0)
+  // thermodynamics default to the atmosphere's element type (prescribed_atmosphere.jl:224): the mixed
+  // (CT ≠ AT) combinations and a time fraction narrower than the data are left to the component kernels
+  if (ct64 && a64 && t64) NE_FUSED3(double, double, double);
+  else if (!ct64 && !a64 && t64) NE_FUSED3(float, float, double);
+  else if (!ct64 && !a64 && !t64) NE_FUSED3(float, float, float);
+  else return 1;
+#undef NE_FUSED3
+#undef NE_FUSED4
+  NE_CUDA_CHECK_LAUNCH("ne_fused_interface_step(interp+solve)");
+  return NE_OK;
 }
 
 template <class FT>

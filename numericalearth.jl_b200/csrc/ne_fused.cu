@@ -1,21 +1,36 @@
-// ne_fused.cu — fused interface step (interpolation -> a–o solve -> assembly -> radiation).
-// Round-1 first cut: enqueues the component kernels back-to-back on the caller's stream (one host
-// call, no synchronisation).  The single-pass kernel that never materialises the interpolated
-// atmosphere state replaces this body once the component kernels are parity-green.
+// ne_fused.cu — fused interface step (interpolation -> a–o solve -> assembly -> radiation), one host
+// call, no synchronisation.  For the default plugin tree in Float64 phases 1-2 (both interpolations
+// and the solve) run as ONE kernel (ao_fused_tab_kernel, ne_flux_kernels.cu) that never reads the
+// interpolated state back from HBM and skips every output left NULL; any other configuration enqueues
+// the component kernels back-to-back.  Phase 3-4 (net flux assembly, radiation) need the (i-1, j-1)
+// neighbours of the just-computed stresses and stay separate, HBM-bound kernels.
 #include "ne_common.cuh"
+
+namespace ne {
+int fused_interp_ao_f64(const NeInterpDesc* atm, const NeInterpDesc* rad, const NeAtmosOceanDesc* d, void* stream);
+}
 
 extern "C" {
 
-static int fused_step(const NeFusedStepDesc* d, void* stream, bool f64) {
+static int interp_and_ao(const NeFusedStepDesc* d, void* stream, bool f64) {
   NE_REQUIRE(d != nullptr, "null descriptor");
-  int rc;
-  if (d->radiation.n_fields > 0) {
-    rc = f64 ? ne_interp_state_f64(&d->radiation, stream) : ne_interp_state_f32(&d->radiation, stream);
+  int rc = f64 ? ne::fused_interp_ao_f64(&d->atmosphere, &d->radiation, &d->ao, stream) : 1;
+  if (rc < 0) return rc;
+  if (rc > 0) {   // not eligible for the single-pass kernel: component kernels
+    if (d->radiation.n_fields > 0) {
+      rc = f64 ? ne_interp_state_f64(&d->radiation, stream) : ne_interp_state_f32(&d->radiation, stream);
+      if (rc) return rc;
+    }
+    rc = f64 ? ne_interp_state_f64(&d->atmosphere, stream) : ne_interp_state_f32(&d->atmosphere, stream);
+    if (rc) return rc;
+    rc = f64 ? ne_atmosphere_ocean_fluxes_f64(&d->ao, stream) : ne_atmosphere_ocean_fluxes_f32(&d->ao, stream);
     if (rc) return rc;
   }
-  rc = f64 ? ne_interp_state_f64(&d->atmosphere, stream) : ne_interp_state_f32(&d->atmosphere, stream);
-  if (rc) return rc;
-  rc = f64 ? ne_atmosphere_ocean_fluxes_f64(&d->ao, stream) : ne_atmosphere_ocean_fluxes_f32(&d->ao, stream);
+  return NE_OK;
+}
+
+static int fused_step(const NeFusedStepDesc* d, void* stream, bool f64) {
+  int rc = interp_and_ao(d, stream, f64);
   if (rc) return rc;
   rc = f64 ? ne_assemble_net_ocean_fluxes_f64(&d->assemble, stream) : ne_assemble_net_ocean_fluxes_f32(&d->assemble, stream);
   if (rc) return rc;
@@ -28,4 +43,6 @@ static int fused_step(const NeFusedStepDesc* d, void* stream, bool f64) {
 
 int ne_fused_interface_step_f64(const NeFusedStepDesc* d, void* stream) { return fused_step(d, stream, true); }
 int ne_fused_interface_step_f32(const NeFusedStepDesc* d, void* stream) { return fused_step(d, stream, false); }
+int ne_interp_and_ao_fluxes_f64(const NeFusedStepDesc* d, void* stream) { return interp_and_ao(d, stream, true); }
+int ne_interp_and_ao_fluxes_f32(const NeFusedStepDesc* d, void* stream) { return interp_and_ao(d, stream, false); }
 }

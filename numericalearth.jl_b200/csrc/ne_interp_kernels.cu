@@ -11,93 +11,45 @@
 // THIS TRANSLATION UNIT IS COMPILED WITH -fmad=false: indices and weights must be bit-exact
 // with the reference, which never contracts a*b+c.
 //
-// Design: HBM-bound streaming kernel.  One thread per exchange point, 32x4 tiles so that a block
-// touches a compact window of the (small, L2-resident: 646x326x4 B per field and time level)
-// source grid; the 4 corner gathers of a warp collapse to 1-2 sectors each and are served by
-// L1/L2 through the read-only path, so DRAM traffic is the 2 fractional indices in and the
-// n_fields values out.  Interpolators (i⁻, i⁺, ξ) are computed once per point and shared by all
+// Design: HBM-bound streaming kernel.  One thread per exchange point, consecutive threads along x;
+// the source grid is small and L2-resident (646x326x4 B per field and time level), the 4 corner
+// gathers of a warp collapse to 1-2 sectors each and are served by L1/L2 through the read-only
+// path, so DRAM traffic is the 2 fractional indices in and the n_fields values out.  Interpolators (i⁻, i⁺, ξ) are computed once per point and shared by all
 // fields and both time levels.
-#include "ne_common.cuh"
+#include "ne_interp_device.cuh"
 
 namespace ne {
 
-template <class AT> struct Interpolator { int64_t im, ip; AT xi; };
-
-__device__ __forceinline__ double m_trunc(double x) { return trunc(x); }
-__device__ __forceinline__ float m_trunc(float x) { return truncf(x); }
-
-// Base.mod(x, one(x)) for floats: rem, then shift negatives into [0, 1)
-template <class AT> __device__ __forceinline__ AT julia_mod1(AT x) {
-  AT r = x - m_trunc(x);  // exact: equals fmod(x, 1)
-  if (r == 0) return (AT)0;
-  if (!(r > 0)) return r + (AT)1;
-  return r;
-}
-
-// interpolator(fractional_idx): (unsafe_trunc(Int, f) + 1, i⁻ + Int(sign(f)), mod(f, 1))
-template <class AT> __device__ __forceinline__ Interpolator<AT> interpolator(AT f) {
-  Interpolator<AT> it;
-  it.im = (int64_t)f + 1;
-  it.ip = it.im + ((f > 0) ? 1 : ((f < 0) ? -1 : 0));
-  it.xi = julia_mod1(f);
-  return it;
-}
-
-struct InterpSource {
-  int64_t ssx;     // source row stride
-  int64_t off;     // (hx-1) + (hy-1)*ssx : 1-based source index -> parent offset
-  int64_t o1, o2;  // time-slot offsets
-};
-
+// One thread per exchange point, consecutive threads along x: a block writes one contiguous 2 KB run
+// per field (DRAM-friendly streams; measured 2.3x faster than 32x4 tiles on B200, profiles/r01_notes.md).
+// Fully unrolled over the (at most 9) fields so every pointer is a constant-bank operand;
+// single-summand fields (everything except tuple-valued precipitation) skip the summand loop.
 template <class FT, class AT, class TT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 interp_state_kernel(const __grid_constant__ NeInterpDesc d, const __grid_constant__ Layout L,
                     const __grid_constant__ InterpSource S) {
-  // 32 x 4 tile per block
-  const int32_t tiles_x = (L.ni + 31) / 32;
-  const int32_t bx = blockIdx.x % tiles_x, by = blockIdx.x / tiles_x;
-  const int32_t li = bx * 32 + (threadIdx.x & 31), lj = by * 4 + (threadIdx.x >> 5);
-  if (li >= L.ni || lj >= L.nj) return;
-  const int32_t i = L.i_lo + li, j = L.j_lo + lj;
-  const int64_t idx = L.at(i, j);
-
-  Interpolator<AT> ix = {1, 1, (AT)0}, iy = {1, 1, (AT)0};  // interpolator(nothing) = (1, 1, 0)
-  if (d.frac_i) ix = interpolator<AT>(__ldg((const AT*)d.frac_i + idx));
-  if (d.frac_j) iy = interpolator<AT>(__ldg((const AT*)d.frac_j + idx));
-  const AT xi = ix.xi, eta = iy.xi;
-  // ϕ₁, ϕ₃, ϕ₅, ϕ₇ with ζ = 0; the k⁺ terms are exact zeros and do not change the sum
-  const AT w1 = (1 - xi) * (1 - eta), w3 = (1 - xi) * eta, w5 = xi * (1 - eta), w7 = xi * eta;
-  const int64_t a_mm = S.off + ix.im + iy.im * S.ssx;
-  const int64_t a_mp = S.off + ix.im + iy.ip * S.ssx;
-  const int64_t a_pm = S.off + ix.ip + iy.im * S.ssx;
-  const int64_t a_pp = S.off + ix.ip + iy.ip * S.ssx;
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (int64_t)L.ni * L.nj) return;
+  const int32_t jj = (int32_t)(t / L.ni);
+  const int64_t idx = L.at(L.i_lo + (int32_t)(t - (int64_t)jj * L.ni), L.j_lo + jj);
+  const InterpPoint<AT> p = interp_point<AT>(d.frac_i, d.frac_j, idx, S);
   const TT nt = (TT)d.time.frac;
   const bool same = d.time.same != 0;
   using W = decltype(AT() * TT());
-
-#pragma unroll 1
-  for (int f = 0; f < d.n_fields; ++f) {
+#pragma unroll
+  for (int f = 0; f < 9; ++f) {
+    if (f >= d.n_fields) break;
     FT* out = (FT*)d.out[f];
     if (!out) continue;
-    W total = 0;
-    for (int s = 0; s < d.n_summands[f]; ++s) {
-      const AT* data = (const AT*)d.series[f][s].data;
-      W val = 0;  // `nothing` contributes the literal 0 (:143)
-      if (data) {
-        const AT* d1 = data + S.o1;
-        AT p1 = w1 * __ldg(d1 + a_mm) + w3 * __ldg(d1 + a_mp) + w5 * __ldg(d1 + a_pm) + w7 * __ldg(d1 + a_pp);
-        if (same) {
-          val = (W)p1;
-        } else {
-          const AT* d2 = data + S.o2;
-          AT p2 = w1 * __ldg(d2 + a_mm) + w3 * __ldg(d2 + a_mp) + w5 * __ldg(d2 + a_pm) + w7 * __ldg(d2 + a_pp);
-          val = p2 * nt + p1 * (1 - nt);
-        }
-      }
-      total = (s == 0) ? val : total + val;
+    W total;
+    if (d.n_summands[f] == 1) {
+      const AT* data = (const AT*)d.series[f][0].data;
+      total = data ? interp_series<AT, TT>(data, p, S, nt, same) : (W)0;
+    } else {
+      total = interp_field<AT, TT>(d, f, p, S, nt, same);
     }
     out[idx] = (FT)total;
-    if (d.potential && f == d.potential_from) ((FT*)d.potential)[idx] = (FT)total / (FT)d.ocean_reference_density;
+    if (d.potential && f == d.potential_from) ((FT*)d.potential)[idx] = div_rn((FT)total, (FT)d.ocean_reference_density);
   }
 }
 
@@ -156,14 +108,9 @@ frac_indices_kernel(const __grid_constant__ NeFracIndexDesc d, const __grid_cons
 template <class FT, class AT, class TT>
 static int launch_interp(const NeInterpDesc& d, cudaStream_t stream) {
   Layout L = make_layout(d.grid);
-  InterpSource S;
-  S.ssx = d.src_nx + 2 * d.src_hx;
-  const int64_t plane = S.ssx * (d.src_ny + 2 * d.src_hy);
-  S.off = (d.src_hx - 1) + (d.src_hy - 1) * S.ssx;
-  S.o1 = (int64_t)(d.time.m1 - 1) * plane;
-  S.o2 = (int64_t)(d.time.m2 - 1) * plane;
-  const int64_t tiles = (int64_t)((L.ni + 31) / 32) * ((L.nj + 3) / 4);
-  interp_state_kernel<FT, AT, TT><<<(unsigned)tiles, 128, 0, stream>>>(d, L, S);
+  InterpSource S = make_interp_source(d);
+  const int64_t n = (int64_t)L.ni * L.nj;
+  interp_state_kernel<FT, AT, TT><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d, L, S);
   NE_CUDA_CHECK_LAUNCH("ne_interp_state");
   return NE_OK;
 }
@@ -174,6 +121,7 @@ static int interp_entry(const NeInterpDesc* d, void* stream) {
   NE_REQUIRE(grid_ok(d->grid, 0, 0), "interp: launch range leaves the parent array");
   NE_REQUIRE(d->n_fields >= 0 && d->n_fields <= 9, "interp: n_fields out of range");
   NE_REQUIRE(d->src_nx > 0 && d->src_ny > 0 && d->src_nt > 0, "interp: bad source extents");
+  NE_REQUIRE((d->src_nx + 2 * d->src_hx) * (d->src_ny + 2 * d->src_hy) < (int64_t)1 << 31, "interp: source plane exceeds 2^31 elements");
   NE_REQUIRE(d->time.m1 >= 1 && d->time.m1 <= d->src_nt && d->time.m2 >= 1 && d->time.m2 <= d->src_nt,
              "interp: time memory slots out of range");
   for (int f = 0; f < d->n_fields; ++f)
