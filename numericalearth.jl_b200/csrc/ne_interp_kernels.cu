@@ -16,6 +16,9 @@
 // gathers of a warp collapse to 1-2 sectors each and are served by L1/L2 through the read-only
 // path, so DRAM traffic is the 2 fractional indices in and the n_fields values out.  Interpolators (i⁻, i⁺, ξ) are computed once per point and shared by all
 // fields and both time levels.
+#include <cstdlib>
+#include <cstring>
+
 #include "ne_interp_device.cuh"
 
 namespace ne {
@@ -51,6 +54,159 @@ interp_state_kernel(const __grid_constant__ NeInterpDesc d, const __grid_constan
     out[idx] = (FT)total;
     if (d.potential && f == d.potential_from) ((FT*)d.potential)[idx] = div_rn((FT)total, (FT)d.ocean_reference_density);
   }
+}
+
+// ---- shared-memory staged variant --------------------------------------------------------------------
+// When the exchange grid is (much) finer than the source grid — 1/12°: 6.75 exchange points per JRA55
+// cell, 1/48°: 27 — the 256 consecutive points of a block fall into a window of a few dozen source
+// columns and two source rows.  The block finds that window (min/max of the interpolator indices),
+// copies it once for every series and both time levels into shared memory with coalesced loads, and the
+// per-point gathers become LDS with immediate plane offsets: 1 instruction per corner instead of 3
+// (LEA + LEA.HI.X + LDG) and ~25 cycles of latency instead of an L1/L2 round trip.  A block whose window
+// does not fit (periodic wrap inside the block, curvilinear exchange rows) takes the direct-gather path;
+// the arithmetic is the same __*_rn sequence either way, so results are bit-identical.
+// The staged kernel is specialised on the number of series NS (every field a single non-null series
+// with a non-null output: 7 for the atmosphere, 2 for the radiation, 5 when precipitation is not
+// requested) so the per-series code carries no run-time flags; anything else takes the direct kernel.
+constexpr int STG_W = 64, STG_H = 4;
+
+template <int NS> struct StagedPlan {
+  const void* series[NS];
+  void* out[NS];
+  int32_t potential_series;             // series whose value also feeds the barotropic potential, −1: none
+  int32_t chunks_x;                     // blocks per row
+};
+
+template <class FT, class AT, class TT, int NS>
+__global__ void __launch_bounds__(256)
+interp_staged_kernel(const __grid_constant__ NeInterpDesc d, const __grid_constant__ Layout L,
+                     const __grid_constant__ InterpSource S, const __grid_constant__ StagedPlan<NS> P) {
+  constexpr int PL = STG_H * STG_W;
+  __shared__ AT win[NS * 2 * PL];          // [series][time level][STG_H][STG_W]
+  __shared__ int32_t red[4][8];
+  __shared__ int32_t box[4];
+  const int tid = threadIdx.x;
+  const int32_t lj = blockIdx.x / P.chunks_x;
+  const int32_t li = (blockIdx.x - lj * P.chunks_x) * 256 + tid;
+  const bool in = li < L.ni;
+  const int64_t idx = L.at(L.i_lo + (in ? li : L.ni - 1), L.j_lo + lj);
+  int32_t im, ip, jm, jp;
+  AT xi, eta;
+  {
+    const FracPair<AT> fr = load_frac<AT>(d.frac_i, d.frac_j, idx);
+    interpolator<AT>(d.frac_i != nullptr, fr.i, im, ip, xi);
+    interpolator<AT>(d.frac_j != nullptr, fr.j, jm, jp, eta);
+  }
+  // window of the block: min/max over both x indices and both y indices
+  {
+    int32_t x0 = min(im, ip), x1 = max(im, ip), y0 = min(jm, jp), y1 = max(jm, jp);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+      x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+      y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+      y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = x0; red[1][tid >> 5] = x1; red[2][tid >> 5] = y0; red[3][tid >> 5] = y1; }
+    __syncthreads();
+    if (tid < 4) {
+      int32_t v = red[tid][0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) v = (tid & 1) ? max(v, red[tid][w]) : min(v, red[tid][w]);
+      box[tid] = v;
+    }
+    __syncthreads();
+  }
+  const int32_t x0 = box[0], y0 = box[2];
+  const int32_t Wd = box[1] - x0 + 1, Hd = box[3] - y0 + 1;
+  const bool staged = Wd <= STG_W && Hd <= STG_H;
+  const bool same = d.time.same != 0;
+  if (staged) {
+    // the four 64-thread groups copy window rows 0..3 of every (series, level) plane: no index arithmetic
+    const int g = tid >> 6, c = tid & 63;
+    if (g < Hd && c < Wd) {
+      const int64_t o = S.off + x0 + c + (int64_t)(y0 + g) * S.ssx;
+#pragma unroll
+      for (int sidx = 0; sidx < NS; ++sidx) {
+        const AT* src = (const AT*)P.series[sidx] + o;
+        win[(sidx * 2) * PL + g * STG_W + c] = __ldg(src + S.o1);
+        if (!same) win[(sidx * 2 + 1) * PL + g * STG_W + c] = __ldg(src + S.o2);
+      }
+    }
+    __syncthreads();
+  }
+  if (!in) return;
+  const TT nt = (TT)d.time.frac;
+  using W = decltype(AT() * TT());
+  const AT cx = sub_rn((AT)1, xi), cy = sub_rn((AT)1, eta);
+  const AT w1 = mul_rn(cx, cy), w3 = mul_rn(cx, eta), w5 = mul_rn(xi, cy), w7 = mul_rn(xi, eta);
+  if (staged) {
+    const AT* b_mm = win + (jm - y0) * STG_W + (im - x0);
+    const AT* b_mp = win + (jp - y0) * STG_W + (im - x0);
+    const AT* b_pm = win + (jm - y0) * STG_W + (ip - x0);
+    const AT* b_pp = win + (jp - y0) * STG_W + (ip - x0);
+    const W cnt = (W)sub_rn((TT)1, nt);
+#pragma unroll
+    for (int sidx = 0; sidx < NS; ++sidx) {
+      constexpr int o2 = PL;
+      const int o = sidx * 2 * PL;
+      const AT p1 = add_rn(add_rn(add_rn(mul_rn(w1, b_mm[o]), mul_rn(w3, b_mp[o])), mul_rn(w5, b_pm[o])), mul_rn(w7, b_pp[o]));
+      W val;
+      if (same) val = (W)p1;
+      else {
+        const AT p2 = add_rn(add_rn(add_rn(mul_rn(w1, b_mm[o + o2]), mul_rn(w3, b_mp[o + o2])), mul_rn(w5, b_pm[o + o2])),
+                             mul_rn(w7, b_pp[o + o2]));
+        val = add_rn(mul_rn((W)p2, (W)nt), mul_rn((W)p1, cnt));
+      }
+      ((FT*)P.out[sidx])[idx] = (FT)val;
+      if (sidx == P.potential_series) ((FT*)d.potential)[idx] = div_rn((FT)val, (FT)d.ocean_reference_density);
+    }
+  } else {
+    InterpPoint<AT> p;
+    p.w1 = w1; p.w3 = w3; p.w5 = w5; p.w7 = w7;
+    p.o_mm = S.off + im + jm * S.ssx;
+    p.o_mp = S.off + im + jp * S.ssx;
+    p.o_pm = S.off + ip + jm * S.ssx;
+    p.o_pp = S.off + ip + jp * S.ssx;
+#pragma unroll
+    for (int sidx = 0; sidx < NS; ++sidx) {
+      const W val = interp_series<AT, TT>((const AT*)P.series[sidx], p, S, nt, same);
+      ((FT*)P.out[sidx])[idx] = (FT)val;
+      if (sidx == P.potential_series) ((FT*)d.potential)[idx] = div_rn((FT)val, (FT)d.ocean_reference_density);
+    }
+  }
+}
+
+// Host: can this descriptor take the staged kernel with NS series?
+template <int NS>
+static bool make_staged_plan(const NeInterpDesc& d, const Layout& L, StagedPlan<NS>& P) {
+  const char* off = std::getenv("NE_B200_INTERP_DIRECT");
+  if (off && off[0] == '1') return false;
+  // staging pays when a 256-point block spans few source columns: exchange grid at least 4x finer than the source
+  if (d.grid.nx < 4 * d.src_nx) return false;
+  std::memset(&P, 0, sizeof(P));
+  P.potential_series = -1;
+  int ns = 0;
+  for (int f = 0; f < d.n_fields; ++f) {
+    if (!d.out[f]) continue;
+    if (d.n_summands[f] != 1 || !d.series[f][0].data || ns >= NS) return false;
+    P.series[ns] = d.series[f][0].data;
+    P.out[ns] = d.out[f];
+    if (d.potential && f == d.potential_from) P.potential_series = ns;
+    ++ns;
+  }
+  if (ns != NS) return false;
+  if (d.potential && P.potential_series < 0) return false;
+  P.chunks_x = (L.ni + 255) / 256;
+  return true;
+}
+
+template <class FT, class AT, class TT, int NS>
+static bool try_staged(const NeInterpDesc& d, const Layout& L, const InterpSource& S, cudaStream_t stream) {
+  StagedPlan<NS> P;
+  if (!make_staged_plan<NS>(d, L, P)) return false;
+  interp_staged_kernel<FT, AT, TT, NS><<<(unsigned)((int64_t)P.chunks_x * L.nj), 256, 0, stream>>>(d, L, S, P);
+  return true;
 }
 
 // ---- fractional indices ---------------------------------------------------------------------------
@@ -109,6 +265,18 @@ template <class FT, class AT, class TT>
 static int launch_interp(const NeInterpDesc& d, cudaStream_t stream) {
   Layout L = make_layout(d.grid);
   InterpSource S = make_interp_source(d);
+  if (std::is_same<FT, double>::value) {   // staged variants are built for Float64 exchange grids
+    int active = 0;
+    for (int f = 0; f < d.n_fields; ++f) active += d.out[f] != nullptr;
+    bool done = false;
+    if (active == 7) done = try_staged<double, AT, TT, 7>(d, L, S, stream);
+    else if (active == 5) done = try_staged<double, AT, TT, 5>(d, L, S, stream);
+    else if (active == 2) done = try_staged<double, AT, TT, 2>(d, L, S, stream);
+    if (done) {
+      NE_CUDA_CHECK_LAUNCH("ne_interp_state(staged)");
+      return NE_OK;
+    }
+  }
   const int64_t n = (int64_t)L.ni * L.nj;
   interp_state_kernel<FT, AT, TT><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d, L, S);
   NE_CUDA_CHECK_LAUNCH("ne_interp_state");

@@ -40,6 +40,21 @@ def test_fractional_indices_and_interpolation_bit_exact(oracle_lib, cuda_backend
                 assert exact, f"{n} not bit-exact (atm {atm_FT}, stretched={stretched}, t={t})"
 
 
+@pytest.mark.parametrize("atm_FT", ["f64", "f32"])
+def test_staged_interpolation_bit_exact(oracle_lib, cuda_backend, cuda_lib, atm_FT):
+    """Exchange grid >= 4x finer than the source: the shared-memory staged kernel runs (blocks whose window wraps the
+    periodic seam take its direct path).  Same bar as the direct kernel: bit-exact against the oracle."""
+    cfg = dict(nx=600, ny=40, latitude=(-60.0, 60.0), src_nx=64, src_ny=32)
+    ref, dev = build_pair(cfg, oracle_lib, cuda_backend, FT="f64", atm_FT=atm_FT)
+    ref.initialize(); dev.initialize()
+    for t in (0.0, T_STEP, 10800.0):
+        ref.interpolate_state(t); dev.interpolate_state(t)
+        cuda_backend.synchronize()
+        for bag_r, bag_d in ((ref.atmos_state, dev.atmos_state), (ref.rad_state, dev.rad_state)):
+            for n, (_, _, exact) in compare_fields(bag_r, bag_d, ref.grid, cuda_backend).items():
+                assert exact, f"{n} not bit-exact (staged, atm {atm_FT}, t={t})"
+
+
 @pytest.mark.parametrize("config", ["C1", "C2"])
 def test_atmosphere_ocean_fluxes_f64(oracle_lib, cuda_backend, cuda_lib, config):
     ref, dev = build_pair(config, oracle_lib, cuda_backend, FT="f64", atm_FT="f64")
@@ -302,7 +317,18 @@ def test_full_size_properties_C4(cuda_backend, cuda_lib):
     it = g.interior(to(dev.ao_iterations))
     assert it[~inactive].min() >= 1 and it.max() <= 100 and (it[inactive] == 0).all()
     first = {n: to(getattr(dev.ao_fluxes, n)).copy() for n in dev.ao_fluxes.names()}
+    staged = {n: to(getattr(dev.atmos_state, n)).copy() for n in dev.atmos_state.names()}
     dev.update_state(T_STEP)
     cuda_backend.synchronize()
     for n, a in first.items():
         assert np.array_equal(a, to(getattr(dev.ao_fluxes, n))), n
+    # (v) the shared-memory staged interpolation (taken at this size) equals the direct-gather kernel bit for bit
+    import os
+    os.environ["NE_B200_INTERP_DIRECT"] = "1"
+    try:
+        dev.interpolate_state(T_STEP)
+        cuda_backend.synchronize()
+    finally:
+        os.environ.pop("NE_B200_INTERP_DIRECT", None)
+    for n, a in staged.items():
+        assert np.array_equal(a, to(getattr(dev.atmos_state, n)), equal_nan=True), f"staged vs direct interpolation: {n}"
