@@ -219,14 +219,22 @@ diag_partial_kernel(const __grid_constant__ NeDiagDesc d, const __grid_constant_
 #pragma unroll
   for (int f = 0; f < NE_DIAG_MAX_FIELDS; ++f) acc[f] = 0;
   // fixed assignment of points to blocks/threads => run-to-run and rank-count independent order
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
     const int32_t jj = (int32_t)(t / L.ni);
     const int64_t idx = L.at(L.i_lo + (int32_t)(t - (int64_t)jj * L.ni), L.j_lo + jj);
-    if (d.inactive && d.inactive[idx]) continue;
-    const double w = d.area ? (double)__ldg((const FT*)d.area + idx) : 1.0;
+    const bool active = !(d.inactive && d.inactive[idx]);
+    // every load is issued unconditionally (predicated on the field count only), then masked: the loads of
+    // a point do not wait for its mask byte
+    const double w = !active ? 0.0 : (d.area ? (double)__ldg((const FT*)d.area + idx) : 1.0);
+    double x[NE_DIAG_MAX_FIELDS];
 #pragma unroll
-    for (int f = 0; f < NE_DIAG_MAX_FIELDS; ++f)
-      if (f < d.n_fields) acc[f] += w * (double)__ldg((const FT*)d.fields[f] + idx);
+    for (int f = 0; f < NE_DIAG_MAX_FIELDS; ++f) x[f] = f < d.n_fields ? (double)__ldg((const FT*)d.fields[f] + idx) : 0.0;
+    if (active) {
+#pragma unroll
+      for (int f = 0; f < NE_DIAG_MAX_FIELDS; ++f)
+        if (f < d.n_fields) acc[f] += w * x[f];
+    }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -244,12 +252,17 @@ diag_partial_kernel(const __grid_constant__ NeDiagDesc d, const __grid_constant_
   }
 }
 
-__global__ void diag_final_kernel(const double* partial, int64_t n_blocks, int n_fields, double* result) {
-  const int f = threadIdx.x;
+// one warp per field: lane l sums blocks l, l+32, … in order, then a fixed shuffle tree — the order depends
+// only on n_blocks, never on scheduling
+__global__ void __launch_bounds__(32 * NE_DIAG_MAX_FIELDS)
+diag_final_kernel(const double* __restrict__ partial, int64_t n_blocks, int n_fields, double* __restrict__ result) {
+  const int f = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (f >= n_fields) return;
   double v = 0;
-  for (int64_t b = 0; b < n_blocks; ++b) v += partial[b * n_fields + f];
-  result[f] = v;
+  for (int64_t b = lane; b < n_blocks; b += 32) v += partial[b * n_fields + f];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) result[f] = v;
 }
 
 template <class K, class D>
@@ -297,7 +310,7 @@ static int diag_entry(const NeDiagDesc* d, void* stream) {
   Layout L = make_layout(d->grid);
   diag_partial_kernel<FT><<<(unsigned)d->n_blocks, 256, 0, (cudaStream_t)stream>>>(*d, L);
   NE_CUDA_CHECK_LAUNCH("ne_diag_reduce(partial)");
-  diag_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d->partial, d->n_blocks, d->n_fields, d->result);
+  diag_final_kernel<<<1, 32 * NE_DIAG_MAX_FIELDS, 0, (cudaStream_t)stream>>>(d->partial, d->n_blocks, d->n_fields, d->result);
   NE_CUDA_CHECK_LAUNCH("ne_diag_reduce(final)");
   return NE_OK;
 }

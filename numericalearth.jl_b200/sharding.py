@@ -54,7 +54,7 @@ class FluxDiagnostics:
     """Area-weighted global integrals of flux fields: local deterministic two-stage sum on the device
     + one all-reduce of n_fields doubles."""
 
-    def __init__(self, interfaces, fields, n_blocks=296):
+    def __init__(self, interfaces, fields, n_blocks=1184):   # 8 resident 256-thread blocks per SM on a 148-SM B200
         self.ci = interfaces
         b, g = interfaces.backend, interfaces.grid
         self.fields = fields

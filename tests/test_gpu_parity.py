@@ -285,6 +285,58 @@ def test_fused_interface_step_without_materialised_atmosphere_state(oracle_lib, 
             assert fr <= 2e-6, f"{n}: {fr}"   # Float32 q_sat, see the mixed-precision test
 
 
+@pytest.mark.parametrize("n_blocks", [3, 296, 1184])
+def test_diagnostics_reduction_matches_numpy_and_is_deterministic(cuda_backend, cuda_lib, n_blocks):
+    """ne_diag_reduce (src/Diagnostics/interface_fluxes.jl:90-195 integrals): area-weighted masked sums against
+    numpy in Float64, bit-identical from run to run (fixed two-stage order)."""
+    from numericalearth_jl_b200 import sharding
+    dev = synthetic.build_case("C1", cuda_backend, FT="f64", atm_FT="f64")
+    dev.initialize()
+    dev.update_state(T_STEP)
+    f = dev.ao_fluxes
+    fields = [f.latent_heat, f.sensible_heat, f.water_vapor, f.x_momentum, f.y_momentum, dev.net_ocean.T]
+    diag = sharding.FluxDiagnostics(dev, fields, n_blocks=n_blocks)
+    r1 = cuda_backend.to_numpy(diag.reduce()).copy()
+    cuda_backend.synchronize()
+    r1 = cuda_backend.to_numpy(diag.result).copy()
+    diag.reduce()
+    cuda_backend.synchronize()
+    r2 = cuda_backend.to_numpy(diag.result).copy()
+    assert np.array_equal(r1, r2)
+    g = dev.grid
+    rows, cols = slice(g.hy, g.hy + g.ny), slice(g.hx, g.hx + g.nx)
+    act = ~cuda_backend.to_numpy(dev.inactive)[rows, cols].astype(bool)
+    area = cuda_backend.to_numpy(diag.area)[rows, cols]
+    for k, x in enumerate(fields):
+        v = cuda_backend.to_numpy(x)[rows, cols]
+        ref = float((v * area)[act].sum(dtype=np.float64))
+        scale = float(np.abs(v * area)[act].sum())
+        assert abs(r1[k] - ref) <= 1e-12 * scale, (k, r1[k], ref)
+
+
+@pytest.mark.parametrize("n_chunks", [1, 3, 8])
+def test_host_pipelined_step_equals_update_state(cuda_backend, cuda_lib, n_chunks):
+    """Ocean state in pinned host buffers, chunked H2D overlapped with the band-restricted kernels: every flux field is
+    bit-identical to the plain device-resident update_state!."""
+    import torch
+    a = synthetic.build_case("C1", cuda_backend, FT="f64", atm_FT="f32")
+    b = synthetic.build_case("C1", cuda_backend, FT="f64", atm_FT="f32")
+    a.initialize(); b.initialize()
+    a.update_state(T_STEP)
+    host = {k: torch.from_numpy(np.ascontiguousarray(b._host_inputs["ocean"][k])).pin_memory() for k in ("T", "S", "u", "v")}
+    for k in ("T", "S", "u", "v"):
+        getattr(b.ocean_state, k).fill_(float("nan"))      # the device copies must really come from the host buffers
+    pipe = ne_b200.HostPipelinedStep(b, n_chunks=n_chunks)
+    pipe.step(T_STEP, host)
+    pipe.step(T_STEP, host)                                 # a second step reuses the events/streams
+    cuda_backend.synchronize()
+    for bag in ("ao_fluxes", "net_ocean", "rad_fluxes_ocean", "atmos_state"):
+        x, y = getattr(a, bag), getattr(b, bag)
+        for n in x.names():
+            assert np.array_equal(cuda_backend.to_numpy(getattr(x, n)), cuda_backend.to_numpy(getattr(y, n)), equal_nan=True), \
+                f"{bag}.{n} differs (n_chunks={n_chunks})"
+
+
 def test_no_kernel_variant_raises(cuda_backend, cuda_lib):
     with pytest.raises(ne_b200.NoKernelVariantError):
         ne_b200.SimilarityTheoryFluxes(momentum_roughness_length=lambda u: 1e-4).pod()
