@@ -210,14 +210,15 @@ apply_radiation_kernel(const __grid_constant__ NeApplyRadiationDesc d, const __g
 }
 
 // ---- diagnostics: deterministic two-stage area-weighted sums (FP64 accumulation) ---------------------
-template <class FT>
+// NF: compile-time bound on the field count (4, 8 or 16) so the accumulators of unused slots cost no registers
+template <class FT, int NF>
 __global__ void __launch_bounds__(256)
 diag_partial_kernel(const __grid_constant__ NeDiagDesc d, const __grid_constant__ Layout L) {
-  __shared__ double sm[8][NE_DIAG_MAX_FIELDS];
+  __shared__ double sm[8][NF];
   const int64_t n = (int64_t)L.ni * L.nj;
-  double acc[NE_DIAG_MAX_FIELDS];
+  double acc[NF];
 #pragma unroll
-  for (int f = 0; f < NE_DIAG_MAX_FIELDS; ++f) acc[f] = 0;
+  for (int f = 0; f < NF; ++f) acc[f] = 0;
   // fixed assignment of points to blocks/threads => run-to-run and rank-count independent order
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
@@ -226,19 +227,19 @@ diag_partial_kernel(const __grid_constant__ NeDiagDesc d, const __grid_constant_
     const bool active = !(d.inactive && d.inactive[idx]);
     // every load is issued unconditionally (predicated on the field count only), then masked: the loads of
     // a point do not wait for its mask byte
-    const double w = !active ? 0.0 : (d.area ? (double)__ldg((const FT*)d.area + idx) : 1.0);
-    double x[NE_DIAG_MAX_FIELDS];
+    const double w = d.area ? (double)__ldg((const FT*)d.area + idx) : 1.0;
+    double x[NF];
 #pragma unroll
-    for (int f = 0; f < NE_DIAG_MAX_FIELDS; ++f) x[f] = f < d.n_fields ? (double)__ldg((const FT*)d.fields[f] + idx) : 0.0;
+    for (int f = 0; f < NF; ++f) x[f] = f < d.n_fields ? (double)__ldg((const FT*)d.fields[f] + idx) : 0.0;
     if (active) {
 #pragma unroll
-      for (int f = 0; f < NE_DIAG_MAX_FIELDS; ++f)
+      for (int f = 0; f < NF; ++f)
         if (f < d.n_fields) acc[f] += w * x[f];
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int f = 0; f < NE_DIAG_MAX_FIELDS; ++f) {
+  for (int f = 0; f < NF; ++f) {
     double v = acc[f];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -308,7 +309,9 @@ static int diag_entry(const NeDiagDesc* d, void* stream) {
   NE_REQUIRE(d->partial && d->result && d->n_blocks >= 1, "diag: null scratch/result");
   for (int f = 0; f < d->n_fields; ++f) NE_REQUIRE(d->fields[f] != nullptr, "diag: null field");
   Layout L = make_layout(d->grid);
-  diag_partial_kernel<FT><<<(unsigned)d->n_blocks, 256, 0, (cudaStream_t)stream>>>(*d, L);
+  if (d->n_fields <= 4) diag_partial_kernel<FT, 4><<<(unsigned)d->n_blocks, 256, 0, (cudaStream_t)stream>>>(*d, L);
+  else if (d->n_fields <= 8) diag_partial_kernel<FT, 8><<<(unsigned)d->n_blocks, 256, 0, (cudaStream_t)stream>>>(*d, L);
+  else diag_partial_kernel<FT, NE_DIAG_MAX_FIELDS><<<(unsigned)d->n_blocks, 256, 0, (cudaStream_t)stream>>>(*d, L);
   NE_CUDA_CHECK_LAUNCH("ne_diag_reduce(partial)");
   diag_final_kernel<<<1, 32 * NE_DIAG_MAX_FIELDS, 0, (cudaStream_t)stream>>>(d->partial, d->n_blocks, d->n_fields, d->result);
   NE_CUDA_CHECK_LAUNCH("ne_diag_reduce(final)");

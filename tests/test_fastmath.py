@@ -1,0 +1,42 @@
+"""Host-side accuracy check of the branch-free FP64 elementary functions and the ψ polynomial tables of the
+table-driven solve (numericalearth.jl_b200/csrc/ne_fastmath.cuh, ne_flux_tab.cuh).  The header compiles for the
+host (MUFU seeds emulated in Float32); tools/fastmath_check.cu compares every function with long double on
+400 000 samples and the ψ tables with the long-double closed forms of the Edson functions
+(similarity_theory_turbulent_fluxes.jl:501-532, 586-618).  No GPU needed: nvcc builds a host executable."""
+import json
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def report(tmp_path_factory):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path_factory.mktemp("fm") / "fastmath_check")
+    r = subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", exe,
+                        os.path.join(ROOT, "tools", "fastmath_check.cu")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    return json.loads(out)
+
+
+def test_elementary_functions_within_a_few_ulp(report):
+    # units: 2^-53 relative (half an ulp of a number in [1, 2))
+    assert report["rcp_ulp"] <= 2.0 and report["div_ulp"] <= 2.0 and report["sqrt_ulp"] <= 2.0
+    assert report["cbrt_ulp"] <= 3.0 and report["cbrt_wide_ulp"] <= 3.0
+    assert report["log_ulp_small"] <= 4.0 and report["log_ulp_large"] <= 4.0 and report["log_abs_near1_ulp1"] <= 3.0
+    assert report["exp_ulp"] <= 3.0 and report["exp_ulp_mid"] <= 3.0
+
+
+def test_psi_tables_reproduce_the_closed_forms(report):
+    # error relative to max(1, |ψ|); the library refuses tables worse than 2e-15 and falls back to the closed forms
+    assert report["psi_fit_err"] <= 1e-15
+    assert report["psi_dense_err"] <= 1e-15
+    assert report["psi_tiny_abs"] <= 1e-15
+    assert report["interval_logic_ok"] == 1
