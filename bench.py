@@ -28,6 +28,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rank 0 prints exactly ONE line on stdout: keep NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NE_BENCH_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 import numpy as np  # noqa: E402
 
@@ -328,13 +331,13 @@ def b200_arm(args):
                     "gpu_launches_per_step": int(pipe.launches_per_step())},
             "gpu_launches": int(7 * args.steps),
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "ao_flux_kernel", "achieved": achieved_tf, "peak": fp64_peak,
+            "roofline": {"bound": "fp64", "kernel": "ao_flux_tab_kernel", "achieved": achieved_tf, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
                          "peak_source": "measured in this run by ne_measure_fp64_peak (DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
                          "ms_per_launch": ms_ao, "algorithmic_flop_per_iteration": F_ITER, "algorithmic_flop_epilogue": F_EPI,
                          "mean_iterations_active": iters_sum / max(n_active, 1), "max_iterations": int(it.max()),
                          "active_points": n_active, "points_per_launch": int(local_points)},
-            "roofline_hbm": {"bound": "hbm", "kernel": "interp_state_kernel(atmosphere)", "achieved": hbm_achieved,
+            "roofline_hbm": {"bound": "hbm", "kernel": "interp_staged_kernel(atmosphere)", "achieved": hbm_achieved,
                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / peaks["hbm_gbs"],
                              "peak_source": peak_src, "ms_per_launch": ms_ia, "traffic": None},
             "kernel_ms": {"interp_radiation": ms_ir, "interp_atmosphere": ms_ia, "atmosphere_ocean_fluxes": ms_ao,

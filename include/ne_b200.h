@@ -393,6 +393,21 @@ typedef struct NeApplyRadiationDesc {
   void *upwelling_longwave, *downwelling_longwave, *downwelling_shortwave;
 } NeApplyRadiationDesc;
 
+/* ---- ElevationCorrection (phase 1.5 of update_state!,
+ * src/EarthSystemModels/InterfaceComputations/atmosphere_state_correction.jl:39-146):
+ * T <- T - G dz ; p <- p exp(-g dz / (Rd (T - G dz / 2))) in place on the regridded exchange state;
+ * q is conserved.  dz = surface - atmosphere elevation, materialised on the exchange grid
+ * (:89-110).  lapse_rate / g / Rd are converted to the exchange element type in the kernel (:135-143). */
+typedef struct NeElevationCorrectionDesc {
+  NeExchangeGrid grid;
+  void* T;                       /* READ-MODIFY-WRITE, exchange layout */
+  void* p;                       /* READ-MODIFY-WRITE */
+  const void* elevation_difference;
+  double lapse_rate;             /* default 6.5e-3 K/m (:49) */
+  double gravitational_acceleration;
+  double dry_air_gas_constant;   /* Parameters.R_d of the atmosphere's thermodynamics (:71) */
+} NeElevationCorrectionDesc;
+
 /* ---- fused interface step: interpolation -> a–o solve -> assembly -> radiation in ONE pass
  * (update_state! phases 1-4 for an OceanOnlyModel,
  *  src/EarthSystemModels/time_step_earth_system_model.jl:38-83).  Intermediate atmosphere
@@ -431,6 +446,9 @@ int ne_frac_indices_f32(const NeFracIndexDesc*, void* stream);
 
 int ne_interp_state_f64(const NeInterpDesc*, void* stream);   /* atmosphere (7) or radiation (2) */
 int ne_interp_state_f32(const NeInterpDesc*, void* stream);
+
+int ne_correct_atmosphere_elevation_f64(const NeElevationCorrectionDesc*, void* stream);
+int ne_correct_atmosphere_elevation_f32(const NeElevationCorrectionDesc*, void* stream);
 
 int ne_atmosphere_ocean_fluxes_f64(const NeAtmosOceanDesc*, void* stream);
 int ne_atmosphere_ocean_fluxes_f32(const NeAtmosOceanDesc*, void* stream);

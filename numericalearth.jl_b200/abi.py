@@ -223,6 +223,11 @@ class NeFusedStepDesc(C.Structure):
                 ("assemble", NeAssembleOceanDesc), ("apply_radiation", NeApplyRadiationDesc)]
 
 
+class NeElevationCorrectionDesc(C.Structure):
+    _fields_ = [("grid", NeExchangeGrid), ("T", vp), ("p", vp), ("elevation_difference", vp), ("lapse_rate", f64),
+                ("gravitational_acceleration", f64), ("dry_air_gas_constant", f64)]
+
+
 class NeDiagDesc(C.Structure):
     _fields_ = [("grid", NeExchangeGrid), ("n_fields", i32), ("pad_", i32), ("fields", vp * NE_DIAG_MAX_FIELDS),
                 ("area", vp), ("inactive", vp), ("partial", vp), ("n_blocks", i64), ("result", vp)]
@@ -233,12 +238,13 @@ STRUCTS = {c.__name__: c for c in [
     NeStabilityProfile, NeRoughnessLength, NeSubgridVelocity, NeStopCriteria, NePolynomialDrag, NeTransferCoefficient,
     NeLargeYeager, NeFluxFormulation, NeInterfaceProperties, NeMediumProperties, NeSurfaceRadiation, NeAtmosOceanDesc,
     NeAtmosSeaIceDesc, NeSeaIceOceanDesc, NeSeaIceOceanStressDesc, NeAssembleOceanDesc, NeAssembleSeaIceDesc,
-    NeApplyRadiationDesc, NeFusedStepDesc, NeDiagDesc]}
+    NeApplyRadiationDesc, NeElevationCorrectionDesc, NeFusedStepDesc, NeDiagDesc]}
 
 # entry points declared in include/ne_b200.h: name -> descriptor struct (None: special signature)
 DESC_ENTRY_POINTS = {
     "ne_frac_indices": NeFracIndexDesc,
     "ne_interp_state": NeInterpDesc,
+    "ne_correct_atmosphere_elevation": NeElevationCorrectionDesc,
     "ne_atmosphere_ocean_fluxes": NeAtmosOceanDesc,
     "ne_atmosphere_sea_ice_fluxes": NeAtmosSeaIceDesc,
     "ne_sea_ice_ocean_fluxes": NeSeaIceOceanDesc,

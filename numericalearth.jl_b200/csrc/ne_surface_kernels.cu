@@ -209,6 +209,22 @@ apply_radiation_kernel(const __grid_constant__ NeApplyRadiationDesc d, const __g
   ((FT*)d.downwelling_shortwave)[idx] = -tr;
 }
 
+// ---- ElevationCorrection: _correct_atmosphere_elevation! (atmosphere_state_correction.jl:133-146) -------
+template <class FT>
+__global__ void __launch_bounds__(256)
+elevation_correction_kernel(const __grid_constant__ NeElevationCorrectionDesc d, const __grid_constant__ Layout L) {
+  NE_POINT_INDEX();
+  (void)j;
+  const FT dz = __ldg((const FT*)d.elevation_difference + idx);
+  const FT dT = (FT)d.lapse_rate * dz;
+  FT* T = (FT*)d.T;
+  FT* p = (FT*)d.p;
+  const FT T0 = T[idx];
+  const FT Tbar = T0 - dT / 2;   // layer-mean temperature for the hydrostatic integral
+  p[idx] = p[idx] * m_exp(-(FT)d.gravitational_acceleration * dz / ((FT)d.dry_air_gas_constant * Tbar));
+  T[idx] = T0 - dT;              // lapse-rate shift; q is conserved
+}
+
 // ---- diagnostics: deterministic two-stage area-weighted sums (FP64 accumulation) ---------------------
 // NF: compile-time bound on the field count (4, 8 or 16) so the accumulators of unused slots cost no registers
 template <class FT, int NF>
@@ -357,6 +373,14 @@ int ne_apply_radiative_fluxes_f32(const NeApplyRadiationDesc* d, void* s) {
   NE_REQUIRE(d && d->surface_temperature && d->heat_flux && d->upwelling_longwave && d->downwelling_longwave && d->downwelling_shortwave, "apply radiation: null array");
   NE_REQUIRE(!d->two_color || d->two_color_surface_flux, "apply radiation: two_color without surface_flux array");
   return ne::launch_points(ne::apply_radiation_kernel<float>, *d, 0, 0, (cudaStream_t)s, "ne_apply_radiative_fluxes");
+}
+int ne_correct_atmosphere_elevation_f64(const NeElevationCorrectionDesc* d, void* s) {
+  NE_REQUIRE(d && d->T && d->p && d->elevation_difference, "elevation correction: null array");
+  return ne::launch_points(ne::elevation_correction_kernel<double>, *d, 0, 0, (cudaStream_t)s, "ne_correct_atmosphere_elevation");
+}
+int ne_correct_atmosphere_elevation_f32(const NeElevationCorrectionDesc* d, void* s) {
+  NE_REQUIRE(d && d->T && d->p && d->elevation_difference, "elevation correction: null array");
+  return ne::launch_points(ne::elevation_correction_kernel<float>, *d, 0, 0, (cudaStream_t)s, "ne_correct_atmosphere_elevation");
 }
 int ne_diag_reduce_f64(const NeDiagDesc* d, void* s) { return ne::diag_entry<double>(d, s); }
 int ne_diag_reduce_f32(const NeDiagDesc* d, void* s) { return ne::diag_entry<float>(d, s); }

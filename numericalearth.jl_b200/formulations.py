@@ -689,6 +689,16 @@ class AtmosphereThermodynamicsParameters:  # ../../Atmospheres/thermodynamic_par
             T_freeze=self.water_freezing_temperature, T_icenuc=self.total_ice_nucleation_temperature)
 
 
+@dataclass
+class ElevationCorrection:  # atmosphere_state_correction.jl:39-59
+    """ElevationCorrection(surface_elevation, atmosphere_elevation; lapse_rate = 6.5e-3): elevations are numbers or
+    exchange-grid arrays (interior (ny, nx) or parent layout); g and Rᵈ come from the atmosphere when the correction
+    is materialised on the exchange grid (atmosphere_state_correction.jl:89-110)."""
+    surface_elevation: Any = 0.0
+    atmosphere_elevation: Any = 0.0
+    lapse_rate: float = 6.5e-3
+
+
 class DegreesCelsius:  # ../components.jl:7
     pass
 

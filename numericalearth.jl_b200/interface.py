@@ -203,7 +203,7 @@ class ComponentInterfaces:
                  atmosphere_sea_ice_interface_temperature=None, atmosphere_sea_ice_velocity_difference=None,
                  sea_ice_ocean_heat_flux=None,
                  ocean_properties=None, sea_ice_properties=None,
-                 gravitational_acceleration=9.80665, inactive=None, with_iterations=False):
+                 gravitational_acceleration=9.80665, inactive=None, with_iterations=False, atmosphere_correction=None):
         self.grid, self.backend = grid, backend
         self.lib = lib if lib is not None else get_library()
         if getattr(self.lib, "is_device", True) != backend.is_device:
@@ -232,6 +232,7 @@ class ComponentInterfaces:
 
         # StateExchanger state (prescribed_atmosphere_regridder.jl:1-22)
         self.atmos_state = _Fields(u=Z(), v=Z(), T=Z(), p=Z(), q=Z(), Jrn=Z(), Jsn=Z())
+        self.atmosphere_correction = self._materialize_correction(atmosphere_correction)
         self.frac = None
         if atmosphere is not None:
             self.frac = _Fields(i=backend.zeros(grid.shape, atmosphere.grid.FT), j=backend.zeros(grid.shape, atmosphere.grid.FT))
@@ -331,6 +332,50 @@ class ComponentInterfaces:
             d.series[f][0].data = b.ptr(s)
             d.out[f] = b.ptr(out)
         return d
+
+    # ---- ElevationCorrection (atmosphere_state_correction.jl) -----------------------------------------------
+    def _materialize_correction(self, c):
+        """materialize_correction (:89-110): Δz = zˢ − zᵃ on the exchange grid; g, Rᵈ from the atmosphere's
+        thermodynamics (Rᵈ = R / Mᵈ in the thermodynamics element type, thermodynamic_parameters.jl:73)."""
+        if c is None:
+            return None
+        if not isinstance(c, F.ElevationCorrection):
+            raise F.NoKernelVariantError(f"atmosphere-state correction {type(c).__name__} has no kernel variant")
+        g = self.grid
+        ft = np.float64 if g.FT == "f64" else np.float32
+
+        def field(x):
+            out = np.zeros(g.shape, dtype=ft)
+            if callable(x):
+                raise F.NoKernelVariantError("function-valued elevations must be evaluated by the caller (no closures on the device)")
+            x = np.asarray(x, dtype=ft)
+            if x.shape == tuple(g.shape):
+                out[...] = x
+            else:   # number or interior array: set!(field, ·) fills the interior only
+                out[g.hy:g.hy + g.ny, g.hx:g.hx + g.nx] = x
+            return out
+        dz = np.zeros(g.shape, dtype=ft)
+        zs, za = field(c.surface_elevation), field(c.atmosphere_elevation)
+        dz[g.hy:g.hy + g.ny, g.hx:g.hx + g.nx] = (zs - za)[g.hy:g.hy + g.ny, g.hx:g.hx + g.nx]
+        th = self.atmosphere.thermodynamics_parameters if self.atmosphere is not None else F.AtmosphereThermodynamicsParameters(FT=g.FT)
+        ct = np.float64 if th.FT == "f64" else np.float32
+        R_d = ct(th.gas_constant) / ct(th.dry_air_molar_mass)
+        return _Fields(dz=self.backend.from_numpy(dz), lapse_rate=float(c.lapse_rate),
+                       gravitational_acceleration=float(ft(9.80665)),       # default_gravitational_acceleration (:72)
+                       dry_air_gas_constant=float(ft(R_d)))
+
+    def elevation_correction_desc(self) -> A.NeElevationCorrectionDesc:
+        c, b = self.atmosphere_correction, self.backend
+        d = A.NeElevationCorrectionDesc()
+        d.grid = self.grid.pod(True)
+        d.T, d.p, d.elevation_difference = b.ptr(self.atmos_state.T), b.ptr(self.atmos_state.p), b.ptr(c.dz)
+        d.lapse_rate, d.gravitational_acceleration, d.dry_air_gas_constant = c.lapse_rate, c.gravitational_acceleration, c.dry_air_gas_constant
+        return d
+
+    def correct_state(self):
+        """Phase 1.5: correct_state!(exchanger.atmosphere, grid) (time_step_earth_system_model.jl:56-62)."""
+        if self.atmosphere_correction is not None:
+            self.lib.call("correct_atmosphere_elevation", self.grid.FT, self.elevation_correction_desc(), self.backend.stream())
 
     def interpolate_state(self, t):
         """interpolate_state!(exchanger.radiation, ...) then (exchanger.atmosphere, ...)
@@ -558,6 +603,7 @@ class ComponentInterfaces:
         """update_state!(model) phases 1-4 (time_step_earth_system_model.jl:38-83).
         ocean_column = (T3, S3, dz, dt, nz, hz) enables the sea-ice–ocean kernel."""
         self.interpolate_state(t)
+        self.correct_state()
         self.compute_atmosphere_ocean_fluxes()
         self.compute_atmosphere_sea_ice_fluxes()
         if ocean_column is not None and self.has_sea_ice:
@@ -579,4 +625,13 @@ class ComponentInterfaces:
 
     def fused_interface_step(self, t):
         """Interpolation -> a–o solve -> net ocean flux assembly -> radiation for an OceanOnlyModel, one C-ABI call."""
+        if self.atmosphere_correction is not None:   # phase 1.5 sits between the phases the fused call merges
+            d, s, FT = self.fused_step_desc(t), self.backend.stream(), self.grid.FT
+            self.interpolate_state(t)
+            self.correct_state()
+            self.lib.call("atmosphere_ocean_fluxes", FT, d.ao, s)
+            self.lib.call("assemble_net_ocean_fluxes", FT, d.assemble, s)
+            if self.radiation is not None:
+                self.lib.call("apply_radiative_fluxes", FT, d.apply_radiation, s)
+            return
         self.lib.call("fused_interface_step", self.grid.FT, self.fused_step_desc(t), self.backend.stream())

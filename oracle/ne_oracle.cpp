@@ -991,6 +991,25 @@ void apply_radiation(const NeApplyRadiationDesc& d) {
     }
 }
 
+// _correct_atmosphere_elevation! (EarthSystemModels/InterfaceComputations/atmosphere_state_correction.jl:133-146)
+template <class FT>
+void correct_atmosphere_elevation(const NeElevationCorrectionDesc& d) {
+  const Layout L(d.grid);
+#pragma omp parallel for schedule(static)
+  for (int64_t j = d.grid.j_lo; j <= d.grid.j_hi; ++j)
+    for (int64_t i = d.grid.i_lo; i <= d.grid.i_hi; ++i) {
+      const int64_t idx = L.at(i, j);
+      FT dz = ((const FT*)d.elevation_difference)[idx];          // δz = convert(FT, Δz[i, j, 1])
+      FT dT = (FT)d.lapse_rate * dz;                               // ΔT = convert(FT, Γ) * δz
+      FT* T = (FT*)d.T;
+      FT* p = (FT*)d.p;
+      FT T0 = T[idx];
+      FT Tbar = T0 - dT / 2;                                       // :141
+      p[idx] = p[idx] * std::exp(-(FT)d.gravitational_acceleration * dz / ((FT)d.dry_air_gas_constant * Tbar));   // :142
+      T[idx] = T0 - dT;                                            // :143
+    }
+}
+
 // viscosity element type: double when every constant-viscosity slot keeps the Float64 literal,
 // FT when all use TemperatureDependentAirViscosity{FT}.
 inline bool viscosity_is_f64_literal(const NeFluxFormulation& f) {
@@ -1065,6 +1084,8 @@ int neo_assemble_net_ocean_fluxes_f64(const NeAssembleOceanDesc* d) { assemble_o
 int neo_assemble_net_ocean_fluxes_f32(const NeAssembleOceanDesc* d) { assemble_ocean<float>(*d); return 0; }
 int neo_assemble_net_sea_ice_fluxes_f64(const NeAssembleSeaIceDesc* d) { assemble_sea_ice<double>(*d); return 0; }
 int neo_assemble_net_sea_ice_fluxes_f32(const NeAssembleSeaIceDesc* d) { assemble_sea_ice<float>(*d); return 0; }
+int neo_correct_atmosphere_elevation_f64(const NeElevationCorrectionDesc* d) { correct_atmosphere_elevation<double>(*d); return 0; }
+int neo_correct_atmosphere_elevation_f32(const NeElevationCorrectionDesc* d) { correct_atmosphere_elevation<float>(*d); return 0; }
 int neo_apply_radiative_fluxes_f64(const NeApplyRadiationDesc* d) { apply_radiation<double>(*d); return 0; }
 int neo_apply_radiative_fluxes_f32(const NeApplyRadiationDesc* d) { apply_radiation<float>(*d); return 0; }
 

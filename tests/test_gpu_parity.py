@@ -337,6 +337,26 @@ def test_host_pipelined_step_equals_update_state(cuda_backend, cuda_lib, n_chunk
                 f"{bag}.{n} differs (n_chunks={n_chunks})"
 
 
+@pytest.mark.parametrize("FT", ["f64", "f32"])
+def test_elevation_correction_parity(oracle_lib, cuda_backend, cuda_lib, FT):
+    """Phase 1.5 (atmosphere_state_correction.jl:133-146) and the fluxes downstream of the corrected state."""
+    g_kw = dict(nx=96, ny=40, latitude=(-70.0, 70.0))
+    rng = np.random.default_rng(11)
+    zs = rng.uniform(0.0, 1500.0, (40, 96))
+    kw = dict(FT=FT, atm_FT=FT, atmosphere_correction=ne_b200.ElevationCorrection(zs, 120.0))
+    ref, dev = build_pair(g_kw, oracle_lib, cuda_backend, **kw)
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP); dev.fused_interface_step(T_STEP)
+    cuda_backend.synchronize()
+    tol = 1e-14 if FT == "f64" else 2e-6
+    res = compare_fields(ref.atmos_state, dev.atmos_state, ref.grid, cuda_backend)
+    for n, (r, fr, exact) in res.items():
+        assert exact or (n in ("T", "p") and r <= tol), f"{n}: {r}"
+    res = compare_fields(ref.ao_fluxes, dev.ao_fluxes, ref.grid, cuda_backend)
+    for n, (r, fr, _) in res.items():
+        assert fr <= (F64_TOL if FT == "f64" else F32_TOL), f"{n}: {fr}"
+
+
 def test_no_kernel_variant_raises(cuda_backend, cuda_lib):
     with pytest.raises(ne_b200.NoKernelVariantError):
         ne_b200.SimilarityTheoryFluxes(momentum_roughness_length=lambda u: 1e-4).pod()

@@ -169,3 +169,34 @@ def test_ice_bath_and_frazil_clamp(oracle_lib, host_backend):
     frz = ci.sio_fluxes.frazil_heat[2, 2]
     assert frz == pytest.approx(-1025.0 * 3991.0 * (-0.054 * 35.0 + 2.5) * 1.0 / 1200.0, rel=1e-14) and frz < 0
     assert abs(Q) < 1e-9                               # after the clamp the ocean sits at the freezing point
+
+
+def test_elevation_correction_matches_the_closed_form(oracle_lib, host_backend):
+    """atmosphere_state_correction.jl:133-146: T <- T - G dz, p <- p exp(-g dz / (Rd (T - G dz/2))); q, u, v untouched;
+    dz = 0 (sea level) is the identity bit for bit."""
+    import ne_b200
+    from numericalearth_jl_b200 import synthetic
+    g = ne_b200.ExchangeGrid(nx=48, ny=20, hx=3, hy=3, latitude=(-60.0, 60.0), FT="f64")
+    rng = np.random.default_rng(7)
+    zs = rng.uniform(-50.0, 2500.0, (g.ny, g.nx))
+    zs[:, :10] = 0.0
+    corr = ne_b200.ElevationCorrection(surface_elevation=zs, atmosphere_elevation=0.0, lapse_rate=6.5e-3)
+    ci = synthetic.build_case(dict(nx=48, ny=20, hx=3, hy=3, latitude=(-60.0, 60.0)), host_backend, FT="f64", atm_FT="f64",
+                              lib=oracle_lib, grid=g, atmosphere_correction=corr)
+    ci.initialize()
+    ci.interpolate_state(4000.0)
+    T0, p0, q0 = ci.atmos_state.T.copy(), ci.atmos_state.p.copy(), ci.atmos_state.q.copy()
+    ci.correct_state()
+    rows, cols = slice(g.hy, g.hy + g.ny), slice(g.hx, g.hx + g.nx)
+    dz = zs
+    G, grav, Rd = 6.5e-3, 9.80665, 8.3144598 / 0.02897
+    T_ref = T0[rows, cols] - G * dz
+    p_ref = p0[rows, cols] * np.exp(-grav * dz / (Rd * (T0[rows, cols] - G * dz / 2)))
+    assert np.allclose(ci.atmos_state.T[rows, cols], T_ref, rtol=1e-15, atol=0)
+    assert np.allclose(ci.atmos_state.p[rows, cols], p_ref, rtol=1e-14, atol=0)
+    assert np.array_equal(ci.atmos_state.q, q0)
+    assert np.array_equal(ci.atmos_state.T[rows, cols][:, :10], T0[rows, cols][:, :10])
+    assert np.array_equal(ci.atmos_state.p[rows, cols][:, :10], p0[rows, cols][:, :10])
+    # a 1000 m lift cools by 6.5 K and drops the pressure by ~11 %
+    k = np.unravel_index(np.argmin(np.abs(dz - 1000.0)), dz.shape)
+    assert 0.85 < (ci.atmos_state.p[rows, cols][k] / p0[rows, cols][k]) ** (1000.0 / dz[k]) < 0.92
