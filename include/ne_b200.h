@@ -264,7 +264,36 @@ typedef struct NeMediumProperties {  /* ocean_properties / sea_ice_properties */
 } NeMediumProperties;
 
 /* radiation properties of one surface (src/Radiations/air_sea_interface_radiation_state.jl:4-39) */
-enum { NE_ALBEDO_CONSTANT = 0, NE_ALBEDO_LATITUDE_DEPENDENT = 1, NE_ALBEDO_FIELD = 2 };
+enum { NE_ALBEDO_CONSTANT = 0, NE_ALBEDO_LATITUDE_DEPENDENT = 1, NE_ALBEDO_FIELD = 2,
+       NE_ALBEDO_TABULATED = 3, NE_ALBEDO_SEA_ICE = 4 };
+
+/* SeaIceAlbedo (CCSM3; src/Radiations/sea_ice_albedo.jl:22-133): scalars converted to the exchange
+ * element type in the kernel; snow_thickness NULL => `nothing` => zero(grid) (:132). */
+typedef struct NeSeaIceAlbedo {
+  double ice_albedo, snow_albedo, ice_melt_reduction, snow_melt_reduction;
+  double melting_temperature, temperature_range, ocean_albedo;
+  double minimum_ice_thickness, minimum_snow_depth;
+  const void* ice_thickness;       /* exchange layout */
+  const void* snow_thickness;      /* exchange layout or NULL */
+  const void* surface_temperature; /* exchange layout, the units of the sea-ice model (deg C) */
+} NeSeaIceAlbedo;
+
+/* TabulatedAlbedo (src/Radiations/tabulated_albedo.jl:39-160): albedo(transmissivity, |latitude|) by
+ * bilinear table lookup.  The clock-dependent scalars (day, seconds in the day, solar declination
+ * :118-131 — host `sind`) are evaluated by the caller once per step and passed in. */
+typedef struct NeTabulatedAlbedo {
+  const void* table;               /* (n_t, n_phi) column-major, exchange element type          */
+  int32_t n_t, n_phi;
+  double t_values[2];              /* first two tabulated transmissivities (constant spacing)   */
+  double phi_values[2];            /* first two tabulated latitudes, radians                     */
+  double solar_constant;           /* S0, default 1365                                          */
+  double day_to_radians;           /* 2 pi / 86400                                              */
+  double noon_in_seconds;          /* 43200                                                     */
+  double seconds_in_day;           /* time - day*86400 (:115)                                   */
+  double declination;              /* delta, radians, already converted to the table eltype     */
+  const void* longitude;           /* lam[(nx+2hx)] degrees (nodes_2d: exchange layout)         */
+} NeTabulatedAlbedo;
+
 typedef struct NeSurfaceRadiation {
   int32_t enabled;          /* 0 => radiation === nothing => zero radiation state            */
   int32_t albedo_kind;
@@ -272,10 +301,14 @@ typedef struct NeSurfaceRadiation {
   double albedo;            /* constant; or `diffuse` of LatitudeDependentAlbedo             */
   double albedo_direct;     /* latitude_dependent_albedo.jl:48-53                            */
   const void* albedo_field; /* NE_ALBEDO_FIELD: exchange-layout array (pre-evaluated)        */
-  const void* latitude;     /* phi[(ny+2hy)] degrees, for LATITUDE_DEPENDENT                 */
+  const void* latitude;     /* phi[(ny+2hy)] degrees (nodes_2d: exchange layout), LATITUDE_DEPENDENT / TABULATED */
+  int32_t nodes_2d;         /* 0: 1-D lat-lon axes; 1: exchange-layout node arrays (curvilinear grids) */
+  int32_t pad_;
   double emissivity;
   const void* downwelling_shortwave;  /* exchange layout                                     */
   const void* downwelling_longwave;
+  NeSeaIceAlbedo sea_ice_albedo;       /* NE_ALBEDO_SEA_ICE   */
+  NeTabulatedAlbedo tabulated_albedo;  /* NE_ALBEDO_TABULATED */
 } NeSurfaceRadiation;
 
 /* ---- atmosphere–ocean turbulent fluxes (atmosphere_ocean_fluxes.jl:17-197) -------------- */

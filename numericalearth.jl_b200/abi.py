@@ -32,7 +32,7 @@ NE_VEL_RELATIVE, NE_VEL_WIND = range(2)
 (NE_TEMP_BULK, NE_TEMP_SKIN_DIFFUSIVE, NE_TEMP_SKIN_DIFFUSIVE_INTERIOR, NE_TEMP_SKIN_CONDUCTIVE,
  NE_TEMP_SKIN_ICE_SNOW) = range(5)
 NE_DEGREES_CELSIUS, NE_DEGREES_KELVIN = range(2)
-NE_ALBEDO_CONSTANT, NE_ALBEDO_LATITUDE_DEPENDENT, NE_ALBEDO_FIELD = range(3)
+NE_ALBEDO_CONSTANT, NE_ALBEDO_LATITUDE_DEPENDENT, NE_ALBEDO_FIELD, NE_ALBEDO_TABULATED, NE_ALBEDO_SEA_ICE = range(5)
 NE_SIO_ICE_BATH, NE_SIO_THREE_EQUATION, NE_SIO_FREEZE_ONLY = range(3)
 NE_USTAR_CONSTANT, NE_USTAR_MOMENTUM_BASED = range(2)
 
@@ -139,10 +139,24 @@ class NeMediumProperties(C.Structure):
                 ("liquidus_slope", f64), ("liquidus_freshwater_melting_temperature", f64)]
 
 
+class NeSeaIceAlbedo(C.Structure):
+    _fields_ = [("ice_albedo", f64), ("snow_albedo", f64), ("ice_melt_reduction", f64), ("snow_melt_reduction", f64),
+                ("melting_temperature", f64), ("temperature_range", f64), ("ocean_albedo", f64),
+                ("minimum_ice_thickness", f64), ("minimum_snow_depth", f64),
+                ("ice_thickness", vp), ("snow_thickness", vp), ("surface_temperature", vp)]
+
+
+class NeTabulatedAlbedo(C.Structure):
+    _fields_ = [("table", vp), ("n_t", i32), ("n_phi", i32), ("t_values", f64 * 2), ("phi_values", f64 * 2),
+                ("solar_constant", f64), ("day_to_radians", f64), ("noon_in_seconds", f64), ("seconds_in_day", f64),
+                ("declination", f64), ("longitude", vp)]
+
+
 class NeSurfaceRadiation(C.Structure):
     _fields_ = [("enabled", i32), ("albedo_kind", i32), ("stefan_boltzmann_constant", f64), ("albedo", f64),
-                ("albedo_direct", f64), ("albedo_field", vp), ("latitude", vp), ("emissivity", f64),
-                ("downwelling_shortwave", vp), ("downwelling_longwave", vp)]
+                ("albedo_direct", f64), ("albedo_field", vp), ("latitude", vp), ("nodes_2d", i32), ("pad_", i32),
+                ("emissivity", f64), ("downwelling_shortwave", vp), ("downwelling_longwave", vp),
+                ("sea_ice_albedo", NeSeaIceAlbedo), ("tabulated_albedo", NeTabulatedAlbedo)]
 
 
 class NeAtmosOceanDesc(C.Structure):
@@ -236,7 +250,7 @@ class NeDiagDesc(C.Structure):
 STRUCTS = {c.__name__: c for c in [
     NeSlot, NeExchangeGrid, NeTimeSeries, NeTimeInterp, NeInterpDesc, NeFracIndexDesc, NeThermoParams, NeStabilityFn,
     NeStabilityProfile, NeRoughnessLength, NeSubgridVelocity, NeStopCriteria, NePolynomialDrag, NeTransferCoefficient,
-    NeLargeYeager, NeFluxFormulation, NeInterfaceProperties, NeMediumProperties, NeSurfaceRadiation, NeAtmosOceanDesc,
+    NeLargeYeager, NeFluxFormulation, NeInterfaceProperties, NeMediumProperties, NeSeaIceAlbedo, NeTabulatedAlbedo, NeSurfaceRadiation, NeAtmosOceanDesc,
     NeAtmosSeaIceDesc, NeSeaIceOceanDesc, NeSeaIceOceanStressDesc, NeAssembleOceanDesc, NeAssembleSeaIceDesc,
     NeApplyRadiationDesc, NeElevationCorrectionDesc, NeFusedStepDesc, NeDiagDesc]}
 

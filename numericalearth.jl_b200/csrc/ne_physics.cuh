@@ -264,6 +264,68 @@ template <class FT> struct Interior { FT u, v, T, S, kappa, hi, hs, hc; };
 template <class FT> struct RadState { FT sigma, alpha, eps, sw, lw; };
 template <class FT> struct Scales { FT ustar, theta_star, q_star; };
 
+// SeaIceAlbedo stateindex (src/Radiations/sea_ice_albedo.jl:106-133)
+template <class FT>
+__device__ __forceinline__ FT sea_ice_albedo(const NeSeaIceAlbedo& a, int64_t idx) {
+  const FT hi = __ldg((const FT*)a.ice_thickness + idx);
+  const FT Ts = __ldg((const FT*)a.surface_temperature + idx);
+  const FT hs = a.snow_thickness ? __ldg((const FT*)a.snow_thickness + idx) : (FT)0;
+  const FT Tm = (FT)a.melting_temperature, dT = (FT)a.temperature_range;
+  const FT fT = clampv((Ts - Tm + dT) / dT, (FT)0, (FT)1);
+  FT alpha_i = (FT)a.ice_albedo - (FT)a.ice_melt_reduction * fT;
+  const FT alpha_s = (FT)a.snow_albedo - (FT)a.snow_melt_reduction * fT;
+  const FT alpha_o = (FT)a.ocean_albedo;
+  const FT fh = clampv(hi / (FT)a.minimum_ice_thickness, (FT)0, (FT)1);
+  alpha_i = alpha_o + (alpha_i - alpha_o) * fh;
+  const FT fs = clampv(hs / (FT)a.minimum_snow_depth, (FT)0, (FT)1);
+  return fs * alpha_s + (1 - fs) * alpha_i;
+}
+
+__device__ __forceinline__ float m_sin(float x) { return sinf(x); }
+__device__ __forceinline__ double m_sin(double x) { return sin(x); }
+
+// TabulatedAlbedo stateindex (src/Radiations/tabulated_albedo.jl:109-160); interpolator semantics as in
+// ne_interp_device.cuh (Oceananigans interpolator, third party)
+template <class FT>
+__device__ __forceinline__ FT tabulated_albedo(const NeTabulatedAlbedo& a, FT lam_deg, FT phi_deg, FT sw) {
+  const FT deg = (FT)3.141592653589793 / 180;       // deg2rad(x) = x * (π / 180) rounded to FT
+  const FT phi = phi_deg * deg, lam = lam_deg * deg;
+  const double h = (a.seconds_in_day - a.noon_in_seconds) * (FT)a.day_to_radians + lam;   // Float64 clock (:122)
+  const FT delta = (FT)a.declination;
+  auto cosz_raw = m_sin(phi) * m_sin(delta) + m_cos(h) * m_cos(delta) * m_cos(phi);
+  using W = decltype(cosz_raw);
+  const W cosz = cosz_raw > 0 ? cosz_raw : (W)0;
+  const W Qmax = (FT)a.solar_constant * cosz;
+  W tr = 0;
+  if (Qmax > 0) { tr = sw / Qmax; if (tr > 1) tr = 1; }
+  const FT t1 = (FT)a.t_values[0], dt = (FT)a.t_values[1] - t1;
+  const FT p1 = (FT)a.phi_values[0], dp = (FT)a.phi_values[1] - p1;
+  const W fi = (tr - t1) / dt;
+  const FT fj = (m_abs(phi) - p1) / dp;
+  auto interp1 = [](auto f, int32_t& im, int32_t& ip) {
+    using T = decltype(f);
+    im = (int32_t)f + 1;
+    ip = im + ((f > 0) ? 1 : ((f < 0) ? -1 : 0));
+    T r = f - trunc(f);
+    if (r == 0) r = (T)0;
+    else if (!(r > 0)) r = r + (T)1;
+    return r;
+  };
+  int32_t im, ip, jm, jp;
+  const W xi = interp1(fi, im, ip);
+  const FT eta = interp1(fj, jm, jp);
+  const FT* T = (const FT*)a.table;
+  const int64_t nt = a.n_t;
+  // i⁺/j⁺ one past the table edge (𝓉 = 1, |φ| = 90°) carry weight 0 in the reference, which reads them unchecked
+  // (@inbounds): clamp the index so that the zero-weighted read stays inside the table
+  auto at = [&](int32_t i, int32_t j) {
+    i = i > a.n_t ? a.n_t : (i < 1 ? 1 : i);
+    j = j > a.n_phi ? a.n_phi : (j < 1 ? 1 : j);
+    return __ldg(T + (i - 1) + (int64_t)(j - 1) * nt);
+  };
+  return (FT)((1 - xi) * (1 - eta) * at(im, jm) + (1 - xi) * eta * at(im, jp) + xi * (1 - eta) * at(ip, jm) + xi * eta * at(ip, jp));
+}
+
 // radiation state of one surface (src/Radiations/air_sea_interface_radiation_state.jl:4-39)
 template <class FT>
 __device__ __forceinline__ RadState<FT> radiation_state(const NeSurfaceRadiation& r, const Layout& L, int64_t idx, int32_t j) {
@@ -274,9 +336,17 @@ __device__ __forceinline__ RadState<FT> radiation_state(const NeSurfaceRadiation
   s.lw = __ldg((const FT*)r.downwelling_longwave + idx);
   if (r.albedo_kind == NE_ALBEDO_CONSTANT) s.alpha = (FT)r.albedo;
   else if (r.albedo_kind == NE_ALBEDO_FIELD) s.alpha = __ldg((const FT*)r.albedo_field + idx);
-  else {  // latitude_dependent_albedo.jl:48-53, hack_cosd radiation_kernels.jl:1
-    FT phi = __ldg((const FT*)r.latitude + (j + L.hy - 1));
-    s.alpha = (FT)r.albedo - (FT)r.albedo_direct * m_cos((FT)3.141592653589793 * (2 * phi) / 180);
+  else if (r.albedo_kind == NE_ALBEDO_SEA_ICE) s.alpha = sea_ice_albedo<FT>(r.sea_ice_albedo, idx);
+  else {
+    const FT phi = r.nodes_2d ? __ldg((const FT*)r.latitude + idx) : __ldg((const FT*)r.latitude + (j + L.hy - 1));
+    if (r.albedo_kind == NE_ALBEDO_TABULATED) {
+      const int64_t col = idx - (int64_t)(j + L.hy - 1) * L.sx;   // i + hx - 1
+      const FT lam = r.nodes_2d ? __ldg((const FT*)r.tabulated_albedo.longitude + idx)
+                                : __ldg((const FT*)r.tabulated_albedo.longitude + col);
+      s.alpha = tabulated_albedo<FT>(r.tabulated_albedo, lam, phi, s.sw);
+    } else {  // latitude_dependent_albedo.jl:48-53, hack_cosd radiation_kernels.jl:1
+      s.alpha = (FT)r.albedo - (FT)r.albedo_direct * m_cos((FT)3.141592653589793 * (2 * phi) / 180);
+    }
   }
   s.eps = (FT)r.emissivity;
   return s;

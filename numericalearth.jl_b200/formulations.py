@@ -737,6 +737,44 @@ class LatitudeDependentAlbedo:  # ../../Radiations/latitude_dependent_albedo.jl
 
 
 @dataclass
+class SeaIceAlbedo:  # ../../Radiations/sea_ice_albedo.jl:22-101 (CCSM3, Briegleb et al. 2004)
+    ice_thickness: Any = None       # exchange-layout arrays of the sea-ice model
+    snow_thickness: Any = None      # None: no snow model (get_snow_thickness(::Nothing) = 0)
+    surface_temperature: Any = None
+    ice_albedo: float = 0.54
+    snow_albedo: float = 0.83
+    ice_melt_reduction: float = 0.075
+    snow_melt_reduction: float = 0.10
+    melting_temperature: float = 0.0
+    temperature_range: float = 1.0
+    ocean_albedo: float = 0.06
+    minimum_ice_thickness: float = 0.5
+    minimum_snow_depth: float = 0.02
+
+
+@dataclass
+class TabulatedAlbedo:  # ../../Radiations/tabulated_albedo.jl:39-93
+    """albedo(transmissivity, |latitude|) by bilinear lookup in `table` ((n_t, n_phi); the reference's default is the
+    Payne (1972) table, which the caller supplies).  phi_values in radians, both axes with constant spacing."""
+    table: Any = None               # device/host array of shape (n_phi, n_t) in C order == (n_t, n_phi) column-major
+    phi_values: Any = None
+    t_values: Any = None
+    solar_constant: float = 1365.0
+    day_to_radians: float = 2 * math.pi / 86400
+    noon_in_seconds: int = 86400 // 2
+
+    @staticmethod
+    def clock_scalars(time_seconds):
+        """simulation_day, seconds_in_day (:104-105) and the solar declination (:125-127) for a clock in seconds."""
+        day = float(int(time_seconds // 86400)) if time_seconds >= 0 else -float(int((-time_seconds) // 86400))
+        sec = time_seconds - day * 86400
+        march_first = 80
+        x = 360 * (day - march_first) / 365.25
+        delta = math.radians((23 + 27 / 60) * math.sin(math.radians(math.fmod(x, 360.0))))
+        return day, sec, delta
+
+
+@dataclass
 class SurfaceRadiationProperties:  # ../../Radiations/surface_radiation_properties.jl ; defaults prescribed_radiation.jl:65-72
     albedo: Any = 0.05
     emissivity: float = 0.97

@@ -387,8 +387,10 @@ class ComponentInterfaces:
             self.lib.call("interp_state", self.grid.FT, self.atmosphere_interp_desc(t), s)
 
     # ---- radiation POD ---------------------------------------------------------------------------------
-    def _surface_radiation(self, surface) -> A.NeSurfaceRadiation:
+    def _surface_radiation(self, surface, time_seconds=None) -> A.NeSurfaceRadiation:
         r = A.NeSurfaceRadiation()
+        if time_seconds is None:
+            time_seconds = getattr(self, "clock_time", 0.0)
         rad = self.radiation
         if rad is None or surface not in rad.surface_properties:
             r.enabled = 0
@@ -402,6 +404,30 @@ class ComponentInterfaces:
         elif isinstance(sp.albedo, F.LatitudeDependentAlbedo):
             r.albedo_kind = A.NE_ALBEDO_LATITUDE_DEPENDENT
             r.albedo, r.albedo_direct = sp.albedo.diffuse, sp.albedo.direct
+            r.latitude = b.ptr(self.phi_dev)
+        elif isinstance(sp.albedo, F.SeaIceAlbedo):
+            al, sa = sp.albedo, r.sea_ice_albedo
+            r.albedo_kind = A.NE_ALBEDO_SEA_ICE
+            for n in ("ice_albedo", "snow_albedo", "ice_melt_reduction", "snow_melt_reduction", "melting_temperature",
+                      "temperature_range", "ocean_albedo", "minimum_ice_thickness", "minimum_snow_depth"):
+                setattr(sa, n, float(getattr(al, n)))
+            sa.ice_thickness, sa.snow_thickness = b.ptr(al.ice_thickness), _ptr(b, al.snow_thickness)
+            sa.surface_temperature = b.ptr(al.surface_temperature)
+        elif isinstance(sp.albedo, F.TabulatedAlbedo):
+            al, ta = sp.albedo, r.tabulated_albedo
+            r.albedo_kind = A.NE_ALBEDO_TABULATED
+            ta.table = b.ptr(al.table)
+            ta.n_phi, ta.n_t = int(al.table.shape[0]), int(al.table.shape[1])
+            ft = np.float64 if self.grid.FT == "f64" else np.float32
+            ta.t_values[0], ta.t_values[1] = float(ft(al.t_values[0])), float(ft(al.t_values[1]))
+            ta.phi_values[0], ta.phi_values[1] = float(ft(al.phi_values[0])), float(ft(al.phi_values[1]))
+            ta.solar_constant, ta.day_to_radians = float(al.solar_constant), float(ft(al.day_to_radians))
+            ta.noon_in_seconds = float(al.noon_in_seconds)
+            _, sec, delta = F.TabulatedAlbedo.clock_scalars(float(time_seconds))
+            ta.seconds_in_day, ta.declination = sec, float(ft(delta))
+            if not hasattr(self, "lam_dev"):
+                self.lam_dev = b.from_numpy(self.grid.lam)
+            ta.longitude = b.ptr(self.lam_dev)
             r.latitude = b.ptr(self.phi_dev)
         elif hasattr(sp.albedo, "shape"):
             r.albedo_kind = A.NE_ALBEDO_FIELD
@@ -602,6 +628,7 @@ class ComponentInterfaces:
     def update_state(self, t, ocean_column=None):
         """update_state!(model) phases 1-4 (time_step_earth_system_model.jl:38-83).
         ocean_column = (T3, S3, dz, dt, nz, hz) enables the sea-ice–ocean kernel."""
+        self.clock_time = t   # clock-dependent surface properties (TabulatedAlbedo) read it
         self.interpolate_state(t)
         self.correct_state()
         self.compute_atmosphere_ocean_fluxes()
@@ -625,6 +652,7 @@ class ComponentInterfaces:
 
     def fused_interface_step(self, t):
         """Interpolation -> a–o solve -> net ocean flux assembly -> radiation for an OceanOnlyModel, one C-ABI call."""
+        self.clock_time = t
         if self.atmosphere_correction is not None:   # phase 1.5 sits between the phases the fused call merges
             d, s, FT = self.fused_step_desc(t), self.backend.stream(), self.grid.FT
             self.interpolate_state(t)

@@ -524,6 +524,67 @@ State<FT> compute_interface_state(const NeFluxFormulation& ff, const NeInterface
   return cur;
 }
 
+template <class T> inline T clampv(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }   // Base.clamp
+
+// Oceananigans interpolator(fractional_idx) = (unsafe_trunc(Int, f) + 1, i⁻ + Int(sign(f)), mod(f, 1)) [3rd party]
+template <class T> inline void interpolator1(T f, int64_t& im, int64_t& ip, T& xi) {
+  im = (int64_t)f + 1;
+  ip = im + ((f > 0) ? 1 : ((f < 0) ? -1 : 0));
+  T r = f - std::trunc(f);
+  if (r == 0) r = (T)0;
+  else if (!(r > 0)) r = r + (T)1;
+  xi = r;
+}
+
+// SeaIceAlbedo stateindex: Radiations/sea_ice_albedo.jl:106-133
+template <class FT> FT sea_ice_albedo(const NeSeaIceAlbedo& a, int64_t idx) {
+  FT hi = static_cast<const FT*>(a.ice_thickness)[idx];
+  FT Ts = static_cast<const FT*>(a.surface_temperature)[idx];
+  FT hs = a.snow_thickness ? static_cast<const FT*>(a.snow_thickness)[idx] : (FT)0;   // get_snow_thickness(::Nothing) :132
+  FT Tm = (FT)a.melting_temperature, dT = (FT)a.temperature_range;
+  FT fT = clampv((Ts - Tm + dT) / dT, (FT)0, (FT)1);                                   // :115
+  FT ai = (FT)a.ice_albedo - (FT)a.ice_melt_reduction * fT;                            // :117
+  FT as = (FT)a.snow_albedo - (FT)a.snow_melt_reduction * fT;                          // :118
+  FT ao = (FT)a.ocean_albedo;
+  FT fh = clampv(hi / (FT)a.minimum_ice_thickness, (FT)0, (FT)1);                      // :122
+  ai = ao + (ai - ao) * fh;                                                            // :123
+  FT fs = clampv(hs / (FT)a.minimum_snow_depth, (FT)0, (FT)1);                         // :126
+  return fs * as + (1 - fs) * ai;                                                      // :127
+}
+
+// TabulatedAlbedo stateindex: Radiations/tabulated_albedo.jl:109-160.  day / seconds-in-day / declination
+// (:113-131) are clock-only scalars evaluated by the caller.
+template <class FT> FT tabulated_albedo(const NeTabulatedAlbedo& a, FT lam_deg, FT phi_deg, FT sw) {
+  const FT deg = (FT)M_PI / 180;
+  FT phi = phi_deg * deg, lam = lam_deg * deg;                                          // :113-114
+  double h = (a.seconds_in_day - a.noon_in_seconds) * (FT)a.day_to_radians + lam;      // :122
+  FT delta = (FT)a.declination;                                                        // :127
+  auto cosz_raw = std::sin(phi) * std::sin(delta) + std::cos(h) * std::cos(delta) * std::cos(phi);   // :130
+  using W = decltype(cosz_raw);
+  W cosz = cosz_raw > 0 ? cosz_raw : (W)0;
+  W Qmax = (FT)a.solar_constant * cosz;                                                // :134
+  W tr = 0;
+  if (Qmax > 0) { tr = sw / Qmax; if (tr > 1) tr = 1; }                                // :137
+  FT t1 = (FT)a.t_values[0], dt = (FT)a.t_values[1] - t1;                              // :141-142
+  FT p1 = (FT)a.phi_values[0], dp = (FT)a.phi_values[1] - p1;                          // :147-148
+  W fi = (tr - t1) / dt;
+  FT fj = (std::abs(phi) - p1) / dp;
+  int64_t im, ip, jm, jp;
+  W xi; FT eta;
+  interpolator1<W>(fi, im, ip, xi);                                                    // :143
+  interpolator1<FT>(fj, jm, jp, eta);                                                  // :149
+  const FT* T = static_cast<const FT*>(a.table);
+  const int64_t nt = a.n_t;
+  // i⁺/j⁺ one past the table edge carry weight 0 in the reference (@inbounds read): keep the read inside the table
+  auto at = [&](int64_t i, int64_t j) {
+    i = i > a.n_t ? a.n_t : (i < 1 ? 1 : i);
+    j = j > a.n_phi ? a.n_phi : (j < 1 ? 1 : j);
+    return T[(i - 1) + (j - 1) * nt];
+  };
+  return (FT)((1 - xi) * (1 - eta) * at(im, jm) + (1 - xi) * eta * at(im, jp) +        // :152-155
+              xi * (1 - eta) * at(ip, jm) + xi * eta * at(ip, jp));
+}
+
 // radiation state of one surface: Radiations/air_sea_interface_radiation_state.jl:4-39
 template <class FT> RadState<FT> radiation_state(const NeSurfaceRadiation& r, const Layout& L, int64_t i, int64_t j) {
   RadState<FT> s = {0, 0, 0, 0, 0};
@@ -534,10 +595,17 @@ template <class FT> RadState<FT> radiation_state(const NeSurfaceRadiation& r, co
   s.lw = static_cast<const FT*>(r.downwelling_longwave)[idx];
   if (r.albedo_kind == NE_ALBEDO_CONSTANT) s.alpha = (FT)r.albedo;
   else if (r.albedo_kind == NE_ALBEDO_FIELD) s.alpha = static_cast<const FT*>(r.albedo_field)[idx];
-  else {  // latitude_dependent_albedo.jl:48-53 ; hack_cosd(φ) = cos(π φ / 180) radiation_kernels.jl:1
-    FT phi = static_cast<const FT*>(r.latitude)[j + L.hy - 1];
-    FT x = 2 * phi;
-    s.alpha = (FT)r.albedo - (FT)r.albedo_direct * std::cos((FT)M_PI * x / 180);
+  else if (r.albedo_kind == NE_ALBEDO_SEA_ICE) s.alpha = sea_ice_albedo<FT>(r.sea_ice_albedo, idx);
+  else {
+    FT phi = r.nodes_2d ? static_cast<const FT*>(r.latitude)[idx] : static_cast<const FT*>(r.latitude)[j + L.hy - 1];
+    if (r.albedo_kind == NE_ALBEDO_TABULATED) {
+      FT lam = r.nodes_2d ? static_cast<const FT*>(r.tabulated_albedo.longitude)[idx]
+                          : static_cast<const FT*>(r.tabulated_albedo.longitude)[i + L.hx - 1];
+      s.alpha = tabulated_albedo<FT>(r.tabulated_albedo, lam, phi, s.sw);
+    } else {  // latitude_dependent_albedo.jl:48-53 ; hack_cosd(φ) = cos(π φ / 180) radiation_kernels.jl:1
+      FT x = 2 * phi;
+      s.alpha = (FT)r.albedo - (FT)r.albedo_direct * std::cos((FT)M_PI * x / 180);
+    }
   }
   s.eps = (FT)r.emissivity;
   return s;
