@@ -42,6 +42,17 @@ F_EPI = 150.0
 BYTES_INTERP_ATM = 2 * 4 + 7 * 8      # 2 Float32 fractional indices in, 7 Float64 fields out
 BYTES_INTERP_RAD = 2 * 4 + 2 * 8
 DT_STEP = 1200.0
+# One `ncu --set full` capture of this workload (C4, 1 GPU, f64 grid, f32 atmosphere), per launch:
+# profiles/r01_ncu_full_v3_summary.csv.  DRAM traffic = dram__bytes_read.sum + dram__bytes_write.sum; the executed view
+# of the solve = thread-level DFMA/DMUL/DADD counts (DFMA = 2 flop) over the ncu duration, next to the algorithmic
+# (as-written census) figure of `roofline.achieved`, which the table-driven kernel under-executes by ~8x.
+NCU_C4 = {
+    "ao_traffic_bytes": 470.2e6 + 537.5e6,
+    "interp_traffic_bytes": 67.8e6 + 350.6e6,
+    "ao_executed": {"tflops": 12.6, "frac_of_measured_dfma_peak": 0.37, "fp64_pipe_active": 0.558,
+                    "issue_slots_active": 0.630, "lane_efficiency": 0.80,
+                    "source": "profiles/r01_ncu_full_v3_summary.csv + profiles/r01_notes.md"},
+}
 
 
 def parse():
@@ -320,6 +331,7 @@ def b200_arm(args):
         r = run_cpu(args, seconds_per_step=args.cpu_seconds / 6.0, steps=5, warmup=1)
         cpu = {"value": r["value"], "unit": "points/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
+    ncu_applies = args.config == "C4" and world == 1 and args.dtype == "f64" and args.atm_dtype == "f32"
     if rank == 0:
         n_active = int(active.sum())
         line = {
@@ -332,14 +344,17 @@ def b200_arm(args):
             "gpu_launches": int(7 * args.steps),
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "ao_flux_tab_kernel", "achieved": achieved_tf, "peak": fp64_peak,
-                         "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
+                         "traffic": NCU_C4["ao_traffic_bytes"] if ncu_applies else None,
+                         "executed": dict(NCU_C4["ao_executed"], applies_to_this_run=ncu_applies),
                          "peak_source": "measured in this run by ne_measure_fp64_peak (DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
                          "ms_per_launch": ms_ao, "algorithmic_flop_per_iteration": F_ITER, "algorithmic_flop_epilogue": F_EPI,
                          "mean_iterations_active": iters_sum / max(n_active, 1), "max_iterations": int(it.max()),
                          "active_points": n_active, "points_per_launch": int(local_points)},
             "roofline_hbm": {"bound": "hbm", "kernel": "interp_staged_kernel(atmosphere)", "achieved": hbm_achieved,
                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / peaks["hbm_gbs"],
-                             "peak_source": peak_src, "ms_per_launch": ms_ia, "traffic": None},
+                             "peak_source": peak_src, "ms_per_launch": ms_ia,
+                             "traffic": NCU_C4["interp_traffic_bytes"] if ncu_applies else None},
             "kernel_ms": {"interp_radiation": ms_ir, "interp_atmosphere": ms_ia, "atmosphere_ocean_fluxes": ms_ao,
                           "assemble_net_ocean_fluxes": ms_as, "apply_radiative_fluxes": ms_ap},
             "diagnostics": diag_values,

@@ -231,8 +231,14 @@ __device__ __forceinline__ void tab_iteration(const FastParams& P, const TabPara
   }
   const double Pi_u = (log_dh - log_lu) - pm_h + pm_l;
   const double Pi_s = (log_dh - log_ls) - ps_h + ps_l;
-  const double chi_s = fm::div(P.kappa, Pi_s);
-  s.ustar = fm::div(P.kappa, Pi_u) * U;
+  // χ = ϰ/Π for both profiles from ONE reciprocal: r = 1/(Π_u Π_s), ϰ/Π_u = ϰ Π_s r, ϰ/Π_s = ϰ Π_u r (each with a
+  // residual correction, ≲ 1.5 ulp)
+  const double r = fm::rcp(Pi_u * Pi_s);
+  const double ru_ = Pi_s * r, rs_ = Pi_u * r;           // 1/Π_u, 1/Π_s
+  double chi_u = P.kappa * ru_, chi_s = P.kappa * rs_;
+  chi_u = fm::fma_(fm::fma_(-Pi_u, chi_u, P.kappa), ru_, chi_u);
+  chi_s = fm::fma_(fm::fma_(-Pi_s, chi_s, P.kappa), rs_, chi_s);
+  s.ustar = chi_u * U;
   s.theta_star = chi_s * s.dtheta;
   s.q_star = chi_s * s.dq;
 }
