@@ -98,6 +98,16 @@ NE_HD double fma_(double a, double b, double c) {
 #endif
 }
 
+// separately rounded product (never contracted into a neighbouring add, whatever the inlining context): the
+// table iteration gives bit-identical iterates in every kernel that embeds it
+NE_HD double mul_(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  volatile double p = a * b; return p;
+#endif
+}
+
 // ---- seeds (≈ 20 bits on the device; the host emulation rounds to Float32) ------------------------
 NE_HD double rcp_seed(double x) {
 #if defined(__CUDA_ARCH__)

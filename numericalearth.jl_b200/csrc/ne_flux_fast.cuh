@@ -66,21 +66,24 @@ inline bool fast_path_eligible(const NeFluxFormulation& f, const NeInterfaceProp
 }
 
 // ---- host: closed forms in long double and the Chebyshev fit of the small-|ζ| unstable branch -------------
-inline long double psi_m_unstable_ld(const double* p, long double z) {
+// f32: √E⁻ is a Float32 sqrt in the Float32 model (psi_edson_momentum<float, double>: FT rE = m_sqrt(Em))
+inline long double psi_m_unstable_ld(const double* p, long double z, bool f32 = false) {
   const long double Am = p[5], Bm = p[6], Cm = p[7], Dm = p[8], Em = p[9], Fm = p[10];
+  const long double rE = f32 ? (long double)std::sqrt((float)p[9]) : sqrtl(Em);
   const long double f1 = sqrtl(sqrtl(1 - Am * z));
   const long double psi1 = Bm * logl((1 + f1) / Bm) + logl((1 + f1 * f1) / Bm) - Bm * atanl(f1) + Cm;
   const long double f2 = cbrtl(1 - Dm * z);
-  const long double psi2 = Em / 2 * logl((1 + f2 + f2 * f2) / Em) - sqrtl(Em) * atanl((1 + 2 * f2) / sqrtl(Em)) + Fm;
+  const long double psi2 = Em / 2 * logl((1 + f2 + f2 * f2) / Em) - rE * atanl((1 + 2 * f2) / rE) + Fm;
   const long double fw = z * z / (1 + z * z);
   return (1 - fw) * psi1 + fw * psi2;
 }
-inline long double psi_s_unstable_ld(const double* p, long double z) {
+inline long double psi_s_unstable_ld(const double* p, long double z, bool f32 = false) {
   const long double Am = p[6], Bm = p[7], Cm = p[8], Dm = p[9], Em = p[10], Fm = p[11];
+  const long double rE = f32 ? (long double)std::sqrt((float)p[10]) : sqrtl(Em);
   const long double f1 = sqrtl(1 - Am * z);
   const long double psi1 = Bm * logl((1 + f1) / Bm) + Cm;
   const long double f2 = cbrtl(1 - Dm * z);
-  const long double psi2 = Em / 2 * logl((1 + f2 + f2 * f2) / Em) - sqrtl(Em) * atanl((1 + 2 * f2) / sqrtl(Em)) + Fm;
+  const long double psi2 = Em / 2 * logl((1 + f2 + f2 * f2) / Em) - rE * atanl((1 + 2 * f2) / rE) + Fm;
   const long double fw = z * z / (1 + z * z);
   return (1 - fw) * psi1 + fw * psi2;
 }
@@ -133,30 +136,42 @@ inline double fit_small_zeta(F f, double zs, double* coef) {
   return err;
 }
 
-inline FastParams make_fast_params(const NeFluxFormulation& f, double g) {
+// f32: parameters of the Float32 model's mixed-precision iteration (ne_flux_tab.cuh): every plugin parameter is
+// the Float32-rounded value promoted back to Float64, derived constants follow stability_fn<float, double>
+// (√E⁻ and C⁺D⁺ are Float32 operations); the air viscosity stays the Float64 literal.
+inline FastParams make_fast_params(const NeFluxFormulation& f, double g, bool f32 = false) {
   FastParams P;
+  auto R = [f32](double x) { return f32 ? (double)(float)x : x; };
   const double* p = f.psi_momentum.a.p;
-  P.m_zmax = p[0]; P.m_Ap = p[1]; P.m_Bp = p[2]; P.m_Cp = p[3]; P.m_Dp = p[4]; P.m_CpDp = p[3] * p[4];
-  P.m_Am = p[5]; P.m_Bm = p[6]; P.m_Cm = p[7]; P.m_Dm = p[8]; P.m_Em = p[9]; P.m_Fm = p[10];
-  P.m_rEm = std::sqrt(p[9]); P.m_irEm = 1.0 / P.m_rEm; P.m_halfEm = p[9] / 2; P.m_iEm = 1.0 / p[9];
-  P.m_B2 = (p[6] == 2.0);
+  P.m_zmax = R(p[0]); P.m_Ap = R(p[1]); P.m_Bp = R(p[2]); P.m_Cp = R(p[3]); P.m_Dp = R(p[4]);
+  P.m_CpDp = f32 ? (double)((float)p[3] * (float)p[4]) : p[3] * p[4];
+  P.m_Am = R(p[5]); P.m_Bm = R(p[6]); P.m_Cm = R(p[7]); P.m_Dm = R(p[8]); P.m_Em = R(p[9]); P.m_Fm = R(p[10]);
+  P.m_rEm = f32 ? (double)std::sqrt((float)p[9]) : std::sqrt(p[9]);
+  P.m_irEm = 1.0 / P.m_rEm; P.m_halfEm = P.m_Em / 2; P.m_iEm = 1.0 / P.m_Em;
+  P.m_B2 = (P.m_Bm == 2.0);
   const double* q = f.psi_temperature.a.p;
-  P.s_zmax = q[0]; P.s_Ap = q[1]; P.s_Bp = q[2]; P.s_Cp = q[3]; P.s_Dp = q[4]; P.s_Ep = q[5];
-  P.s_Am = q[6]; P.s_Bm = q[7]; P.s_Cm = q[8]; P.s_Dm = q[9]; P.s_Em = q[10]; P.s_Fm = q[11];
-  P.s_rEm = std::sqrt(q[10]); P.s_irEm = 1.0 / P.s_rEm; P.s_halfEm = q[10] / 2; P.s_iEm = 1.0 / q[10];
-  P.s_iBm = 1.0 / q[7];
-  P.s_C15 = (q[3] == 1.5);
+  P.s_zmax = R(q[0]); P.s_Ap = R(q[1]); P.s_Bp = R(q[2]); P.s_Cp = R(q[3]); P.s_Dp = R(q[4]); P.s_Ep = R(q[5]);
+  P.s_Am = R(q[6]); P.s_Bm = R(q[7]); P.s_Cm = R(q[8]); P.s_Dm = R(q[9]); P.s_Em = R(q[10]); P.s_Fm = R(q[11]);
+  P.s_rEm = f32 ? (double)std::sqrt((float)q[10]) : std::sqrt(q[10]);
+  P.s_irEm = 1.0 / P.s_rEm; P.s_halfEm = P.s_Em / 2; P.s_iEm = 1.0 / P.s_Em;
+  P.s_iBm = 1.0 / P.s_Bm;
+  P.s_C15 = (P.s_Cp == 1.5);
   const NeRoughnessLength& m = f.ell_momentum;
   const NeRoughnessLength& s = f.ell_temperature;
-  P.a1 = m.wave_constant / m.gravitational_acceleration;
-  P.a2 = m.smooth_wall_parameter * m.nu;
-  P.lmax = m.maximum_roughness_length;
+  P.a1 = m.wave_constant / m.gravitational_acceleration;   // Float64 model only (the Float32 front forms ℓ_W itself)
+  P.a2 = R(m.smooth_wall_parameter) * m.nu;
+  P.lmax = R(m.maximum_roughness_length);
   P.nu_inv = 1.0 / s.nu;
-  P.rA = s.reynolds_A; P.log_rA = std::log(s.reynolds_A); P.rb = s.reynolds_b;
-  P.ls_max = s.maximum_roughness_length; P.log_ls_max = std::log(s.maximum_roughness_length);
-  P.beta = f.subgrid_velocities.gustiness_parameter; P.gmin = f.subgrid_velocities.minimum_gustiness;
-  P.kappa = f.von_karman_constant; P.d_zero = f.zero_plane_displacement; P.g = g;
-  P.tol = f.stop.tolerance; P.maxiter = f.stop.maxiter; P.fixed = f.stop.kind == NE_STOP_FIXED_ITERATIONS;
+  P.rA = R(s.reynolds_A); P.log_rA = std::log(P.rA); P.rb = R(s.reynolds_b);
+  P.ls_max = R(s.maximum_roughness_length); P.log_ls_max = std::log(P.ls_max);
+  P.beta = R(f.subgrid_velocities.gustiness_parameter); P.gmin = R(f.subgrid_velocities.minimum_gustiness);
+  P.kappa = R(f.von_karman_constant); P.d_zero = R(f.zero_plane_displacement); P.g = R(g);
+  P.tol = R(f.stop.tolerance); P.maxiter = f.stop.maxiter; P.fixed = f.stop.kind == NE_STOP_FIXED_ITERATIONS;
+  if (f32) {   // the small-|ζ| closed-form polynomial belongs to the Float64 closed-form kernel only
+    P.zsmall = 0; P.zsmall_inv = 0;
+    for (int k = 0; k <= NE_FAST_PSI_DEG; ++k) { P.pm[k] = 0; P.ps[k] = 0; }
+    return P;
+  }
   // small-|ζ| polynomials (ψ(ℓ/L★) always lands here: |ℓ/L★| ≲ 1e-3), cached per parameter set
   static thread_local double cache_key[24];
   static thread_local double cache_val[2 * (NE_FAST_PSI_DEG + 1) + 1];

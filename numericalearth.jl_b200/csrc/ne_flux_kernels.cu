@@ -22,6 +22,7 @@
 
 #include "ne_flux_fast.cuh"
 #include "ne_flux_tab.cuh"
+#include "ne_flux_queue.cuh"
 #include "ne_interp_device.cuh"
 #include "ne_physics.cuh"
 
@@ -339,7 +340,7 @@ ao_fused_tab_kernel(const __grid_constant__ NeInterpDesc atm, const __grid_const
 // must happen outside CUDA-graph capture; later calls only enqueue the kernel.
 struct SolverTables {
   int device;
-  double key[26];
+  double key[27];
   double* dptr;
   TabParams T;
   double fit_error;
@@ -347,10 +348,11 @@ struct SolverTables {
 static std::mutex g_tab_mutex;
 static std::vector<SolverTables> g_tabs;
 
-static const SolverTables* solver_tables(const NeFluxFormulation& f) {
+static const SolverTables* solver_tables(const NeFluxFormulation& f, bool f32 = false) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  double key[26];
+  double key[27];
+  key[26] = f32 ? 1.0 : 0.0;
   for (int k = 0; k < 12; ++k) { key[k] = f.psi_momentum.a.p[k]; key[12 + k] = f.psi_temperature.a.p[k]; }
   key[24] = f.subgrid_velocities.gustiness_parameter;
   key[25] = f.subgrid_velocities.minimum_gustiness;
@@ -362,7 +364,7 @@ static const SolverTables* solver_tables(const NeFluxFormulation& f) {
   std::memcpy(t.key, key, sizeof(key));
   t.dptr = nullptr;
   std::vector<double> host(fm::TAB_SIZE);
-  t.fit_error = build_solver_tables(f, host.data(), t.T);
+  t.fit_error = build_solver_tables(f, host.data(), t.T, f32);
   if (t.fit_error <= 2e-15) {   // else: ψ parameters the polynomials cannot represent → closed-form kernel
     if (cudaMalloc(&t.dptr, sizeof(double) * fm::TAB_SIZE) != cudaSuccess ||
         cudaMemcpy(t.dptr, host.data(), sizeof(double) * fm::TAB_SIZE, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -469,6 +471,83 @@ static int tab_minb() {
   return (m == 2 || m == 4) ? m : 3;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+// the work-queue kernel indexes points with 32 bits
+static bool queue_path_ok(const NeExchangeGrid& g) {
+  if (env_flag("NE_B200_TAB_CLASSIC")) return false;
+  const int64_t parent = (int64_t)(g.nx + 2 * g.hx) * (int64_t)(g.ny + 2 * g.hy);
+  return parent < ((int64_t)1 << 31);
+}
+
+static FrontF32 make_front_f32(const NeAtmosOceanDesc& d) {
+  FrontF32 Q;
+  Q.gmin = (float)d.flux.subgrid_velocities.minimum_gustiness;
+  Q.beta = (float)d.flux.subgrid_velocities.gustiness_parameter;
+  Q.Cg = (float)d.flux.ell_momentum.wave_constant;
+  Q.g_rough = (float)d.flux.ell_momentum.gravitational_acceleration;
+  Q.kappa = (float)d.flux.von_karman_constant;
+  Q.tol = (float)d.flux.stop.tolerance;
+  Q.g = (float)d.gravitational_acceleration;
+  Q.d_zero = (float)d.flux.zero_plane_displacement;
+  return Q;
+}
+
+// Tile/CTA counters of the work-queue kernel: a per-device pool of zero-initialised {tile, cta} pairs used round
+// robin.  A kernel leaves its pair zeroed (last CTA out), so no per-launch memset is needed and launches can be
+// captured in CUDA graphs; two launches share a pair only if QUEUE_SLOTS launches are in flight at once.
+constexpr int QUEUE_SLOTS = 1024;
+struct QueueCounters { int device; uint32_t* dptr; unsigned next; };
+static std::vector<QueueCounters> g_qcounters;
+
+static uint32_t* queue_counters() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(g_tab_mutex);
+  for (QueueCounters& q : g_qcounters)
+    if (q.device == dev) return q.dptr + 2 * (q.next++ % QUEUE_SLOTS);
+  QueueCounters q = {dev, nullptr, 1};
+  if (cudaMalloc(&q.dptr, sizeof(uint32_t) * 2 * QUEUE_SLOTS) != cudaSuccess ||
+      cudaMemset(q.dptr, 0, sizeof(uint32_t) * 2 * QUEUE_SLOTS) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  g_qcounters.push_back(q);
+  return q.dptr;
+}
+
+// Work-queue solve (ne_flux_queue.cuh): persistent warps, grid = resident CTAs x NE_B200_QUEUE_WAVES
+template <class FT, class CT>
+static int launch_queue(const NeAtmosOceanDesc& d, const SolverTables* tabs, cudaStream_t s) {
+  Layout L = make_layout(d.grid);
+  const bool f32 = std::is_same<FT, float>::value;
+  FastParams P = make_fast_params(d.flux, d.gravitational_acceleration, f32);
+  FrontF32 Q = make_front_f32(d);
+  TabParams TP = tabs->T;
+  const bool hs = !d.surface_layer_height.ptr && !d.boundary_layer_height.ptr;
+  TP.log_hd = f32 ? std::log((double)((float)d.surface_layer_height.value - Q.d_zero))
+                  : std::log(d.surface_layer_height.value - P.d_zero);
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t n = (int64_t)L.ni * L.nj;
+  const int64_t ctas_needed = (n + 255) / 256;
+  const int waves = std::max(1, env_int("NE_B200_QUEUE_WAVES", 1));
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)sms * 3 * waves));
+  int theta = env_int("NE_B200_QUEUE_THETA", 12);
+  theta = theta < 0 ? 0 : (theta > 24 ? 24 : theta);
+  const Thermo<CT> th = Thermo<CT>::make(d.thermo);
+  uint32_t* counters = queue_counters();
+  NE_REQUIRE(counters != nullptr, "atmosphere-ocean: could not allocate the work-queue counters");
+  if (hs) ao_flux_queue_kernel<FT, CT, 3, true><<<grid, 256, 0, s>>>(d, L, th, P, TP, Q, tabs->dptr, theta, counters);
+  else ao_flux_queue_kernel<FT, CT, 3, false><<<grid, 256, 0, s>>>(d, L, th, P, TP, Q, tabs->dptr, theta, counters);
+  NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(queue)");
+  return NE_OK;
+}
+
 template <class FT>
 static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
   int rc = validate_ao(d, true);
@@ -484,6 +563,11 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
       const int64_t n = (int64_t)L.ni * L.nj;
       // NE_B200_CLOSED_FORM_PSI=1 keeps the libdevice closed-form iteration (parity-tested both ways)
       const SolverTables* tabs = env_flag("NE_B200_CLOSED_FORM_PSI") || !tab_path_eligible(d->flux) ? nullptr : solver_tables(d->flux);
+      // Float64: the work-queue kernel (opt-in, NE_B200_QUEUE=1) does not beat the one-thread-per-point kernel on
+      // B200 (1.78 vs 1.73 ms on C4: the trip counts only spread 7–24 and the desynchronised warps cost more in
+      // instruction-cache misses and exposed load latency than the denser rounds save, profiles/r01_notes.md)
+      if (tabs && env_flag("NE_B200_QUEUE") && queue_path_ok(d->grid))
+        return ct64 ? launch_queue<double, double>(*d, tabs, s) : launch_queue<double, float>(*d, tabs, s);
       if (tabs) {
         const int tminb = tab_minb();
         const unsigned tb = tab_grid(n, tminb);
@@ -525,6 +609,14 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
     }
     return ct64 ? launch_ao<double, double, double>(*d, s) : launch_ao<double, float, double>(*d, s);
   } else {
+    // Float32 model, default tree, Float32 thermodynamics, Float64-literal viscosity: the mixed-precision table
+    // iteration on the work-queue kernel; everything else (and NE_B200_FORCE_GENERIC=1) through the generic kernel
+    if (!ct64 && viscosity_is_f64_literal(d->flux) && fast_path_eligible(d->flux, d->properties, d->thermo) &&
+        tab_path_eligible(d->flux) && queue_path_ok(d->grid) && !env_flag("NE_B200_FORCE_GENERIC") &&
+        !env_flag("NE_B200_CLOSED_FORM_PSI")) {
+      const SolverTables* tabs = solver_tables(d->flux, true);
+      if (tabs) return launch_queue<float, float>(*d, tabs, s);
+    }
     if (ct64) return v64 ? launch_ao<float, double, double>(*d, s) : launch_ao<float, double, float>(*d, s);
     return v64 ? launch_ao<float, float, double>(*d, s) : launch_ao<float, float, float>(*d, s);
   }

@@ -48,10 +48,12 @@ inline void cheb_fit_monomial(F f, long double lo, long double hi, int deg, doub
   for (int m = 0; m < N; ++m) coef[m] = (double)px[m];
 }
 
-inline long double psi_m_stable_ld(const double* p, long double z) {
+// f32: the Float32 model evaluates Cp*Dp as a Float32 product before promotion (psi_edson_momentum<float, double>)
+inline long double psi_m_stable_ld(const double* p, long double z, bool f32 = false) {
   const long double zmax = p[0], Ap = p[1], Bp = p[2], Cp = p[3], Dp = p[4];
   const long double dz = fminl(zmax, Ap * z);
-  return -Bp * z - Cp * (z - Dp) * expl(-dz) - Cp * Dp;
+  const long double CpDp = f32 ? (long double)((float)p[3] * (float)p[4]) : Cp * Dp;
+  return -Bp * z - Cp * (z - Dp) * expl(-dz) - CpDp;
 }
 inline long double psi_s_stable_ld(const double* p, long double z) {
   const long double zmax = p[0], Ap = p[1], Bp = p[2], Cp = p[3], Dp = p[4], Ep = p[5];
@@ -61,7 +63,9 @@ inline long double psi_s_stable_ld(const double* p, long double z) {
 
 // Fills tab[TAB_SIZE] and T; returns the max error of the ψ polynomials (double evaluation vs the
 // long-double closed forms, relative to max(1, |ψ|)) over all intervals.
-inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabParams& T) {
+// f32: tables for the Float32 model — the ψ parameters are the Float32-rounded ones (and √E⁻, C⁺D⁺ are Float32
+// operations), exactly what stability_fn<float, double> evaluates.
+inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabParams& T, bool f32 = false) {
   using namespace fm;
   // log table
   for (int i = 0; i < LOG_N; ++i) {
@@ -80,8 +84,11 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
     long double s = 1;
     for (int k = 0; k <= EXP_DEG; ++k) { T.mc.expp[k] = (double)((long double)cw[k] / s); s *= h; }
   }
-  const double* pm = f.psi_momentum.a.p;
-  const double* ps = f.psi_temperature.a.p;
+  double pm[12], ps[12];
+  for (int k = 0; k < 12; ++k) {
+    pm[k] = f32 ? (double)(float)f.psi_momentum.a.p[k] : f.psi_momentum.a.p[k];
+    ps[k] = f32 ? (double)(float)f.psi_temperature.a.p[k] : f.psi_temperature.a.p[k];
+  }
   double worst = 0;
   for (int iv = 0; iv < PSI_NI; ++iv) {
     long double lo, hi;
@@ -97,8 +104,8 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
     rec[0] = (double)(1 / half);
     rec[1] = (double)(-mid / half);
     double cm[PSI_DEG + 1], cs[PSI_DEG + 1];
-    auto fmf = [&](long double az) { return stable ? psi_m_stable_ld(pm, az) : psi_m_unstable_ld(pm, -az); };
-    auto fsf = [&](long double az) { return stable ? psi_s_stable_ld(ps, az) : psi_s_unstable_ld(ps, -az); };
+    auto fmf = [&](long double az) { return stable ? psi_m_stable_ld(pm, az, f32) : psi_m_unstable_ld(pm, -az, f32); };
+    auto fsf = [&](long double az) { return stable ? psi_s_stable_ld(ps, az) : psi_s_unstable_ld(ps, -az, f32); };
     cheb_fit_monomial(fmf, lo, hi, PSI_DEG, cm);
     cheb_fit_monomial(fsf, lo, hi, PSI_DEG, cs);
     for (int k = 0; k <= PSI_DEG; ++k) { rec[2 + 2 * k] = cm[k]; rec[2 + 2 * k + 1] = cs[k]; }
@@ -121,8 +128,8 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
     rec[0] = (double)(1 / half);
     rec[1] = (double)(-mid / half);
     double cm[TINY_DEG + 1], cs[TINY_DEG + 1];
-    auto fmf = [&](long double az) { return stable ? psi_m_stable_ld(pm, az) : psi_m_unstable_ld(pm, -az); };
-    auto fsf = [&](long double az) { return stable ? psi_s_stable_ld(ps, az) : psi_s_unstable_ld(ps, -az); };
+    auto fmf = [&](long double az) { return stable ? psi_m_stable_ld(pm, az, f32) : psi_m_unstable_ld(pm, -az, f32); };
+    auto fsf = [&](long double az) { return stable ? psi_s_stable_ld(ps, az) : psi_s_unstable_ld(ps, -az, f32); };
     cheb_fit_monomial(fmf, lo, hi, TINY_DEG, cm);
     cheb_fit_monomial(fsf, lo, hi, TINY_DEG, cs);
     for (int k = 0; k <= TINY_DEG; ++k) { rec[2 + 2 * k] = cm[k]; rec[2 + 2 * k + 1] = cs[k]; }
@@ -199,30 +206,29 @@ __device__ __noinline__ double2 tab_psi_pair_rare(const FastParams& P, const Tab
   return make_double2(pm, ps);
 }
 
-__device__ __forceinline__ void tab_iteration(const FastParams& P, const TabParams& T, const double* tab, FastPoint& s) {
+// The Float64 core shared by the Float64 and the mixed-precision Float32 iterations: roughness lengths, the
+// two logarithmic profiles with their ψ corrections and the transfer coefficients χ = ϰ/Π.
+//   u★ (as a double), ru = 1/u★, ℓu (already clipped), 1/L★, Δh = z − d and log Δh  →  χ_u, χ_s
+__device__ __forceinline__ void tab_core(const FastParams& P, const TabParams& T, const double* tab, double ustar,
+                                         double ru, double lu, double Linv, double hd, double log_hd,
+                                         double& chi_u, double& chi_s) {
   using fm::dmax;
-  using fm::dmin;
-  const double bstar = s.gTv * (s.theta_star * s.c1 + s.c2 * s.q_star);
-  const double Jb = -s.ustar * bstar;
-  const double UG = dmax(P.gmin, P.beta * fm::cbrt_pos(T.mc, dmax(dmax(0.0, Jb) * s.h_bl, T.cbrt_floor)));
-  const double U = fm::sqrt_pos(s.dudv2 + UG * UG);
-  const double ru = fm::rcp(s.ustar);
-  const double lu = dmin(P.a1 * s.ustar * s.ustar + P.a2 * ru, P.lmax);
+  (void)ru;
   const double log_lu = fm::log_pos(tab, T.mc, lu);
-  const double log_Rs = fm::log_pos(tab, T.mc, lu * s.ustar * P.nu_inv);
-  const double log_ls_un = P.log_rA - P.rb * log_Rs;
+  using fm::mul_;
+  const double log_Rs = fm::log_pos(tab, T.mc, mul_(mul_(lu, ustar), P.nu_inv));
+  const double log_ls_un = fm::fma_(-P.rb, log_Rs, P.log_rA);
   const bool clipped = log_ls_un > P.log_ls_max;
   const double log_ls = clipped ? P.log_ls_max : log_ls_un;
   const double ls_un = fm::exp_mid(T.mc, dmax(log_ls_un, -700.0));
   const double ls = clipped ? P.ls_max : ls_un;
-  const bool lifted = 2.0 * lu > s.hd;
-  const double dh = lifted ? 2.0 * lu : s.hd;
-  const double log_dh = lifted ? T.mc.ln2 + log_lu : s.log_hd;
-  const double Linv = P.kappa * bstar * ru * ru;   // 1/L★ (0 when b★ == 0, i.e. L★ = Inf)
+  const bool lifted = 2.0 * lu > hd;
+  const double dh = lifted ? 2.0 * lu : hd;
+  const double log_dh = lifted ? T.mc.ln2 + log_lu : log_hd;
   double pm_h, ps_h, pm_l, ps_l;
-  tab_psi_pair(P, T, tab, dh * Linv, pm_h, ps_h);
+  tab_psi_pair(P, T, tab, mul_(dh, Linv), pm_h, ps_h);
   // ψ(ℓ/L★): |ℓ/L★| < 2^-12 except in the first trips from the 1e-4 initial guess
-  const double zu = lu * Linv, zs = ls * Linv;
+  const double zu = mul_(lu, Linv), zs = mul_(ls, Linv);
   if (fm::psi_is_tiny(zu) && fm::psi_is_tiny(zs)) {
     fm::psi_tiny_pair(tab + fm::TAB_TINY + (Linv < 0 ? 0 : fm::TINY_REC), fabs(zu), fabs(zs), pm_l, ps_l);
   } else {
@@ -233,14 +239,71 @@ __device__ __forceinline__ void tab_iteration(const FastParams& P, const TabPara
   const double Pi_s = (log_dh - log_ls) - ps_h + ps_l;
   // χ = ϰ/Π for both profiles from ONE reciprocal: r = 1/(Π_u Π_s), ϰ/Π_u = ϰ Π_s r, ϰ/Π_s = ϰ Π_u r (each with a
   // residual correction, ≲ 1.5 ulp)
-  const double r = fm::rcp(Pi_u * Pi_s);
-  const double ru_ = Pi_s * r, rs_ = Pi_u * r;           // 1/Π_u, 1/Π_s
-  double chi_u = P.kappa * ru_, chi_s = P.kappa * rs_;
+  const double r = fm::rcp(mul_(Pi_u, Pi_s));
+  const double ru_ = mul_(Pi_s, r), rs_ = mul_(Pi_u, r);   // 1/Π_u, 1/Π_s
+  chi_u = mul_(P.kappa, ru_); chi_s = mul_(P.kappa, rs_);
   chi_u = fm::fma_(fm::fma_(-Pi_u, chi_u, P.kappa), ru_, chi_u);
   chi_s = fm::fma_(fm::fma_(-Pi_s, chi_s, P.kappa), rs_, chi_s);
-  s.ustar = chi_u * U;
-  s.theta_star = chi_s * s.dtheta;
-  s.q_star = chi_s * s.dq;
+}
+
+__device__ __forceinline__ void tab_iteration(const FastParams& P, const TabParams& T, const double* tab, FastPoint& s) {
+  using fm::dmax;
+  using fm::dmin;
+  using fm::fma_;
+  using fm::mul_;
+  // every product is separately rounded or an explicit fma: the iterate does not depend on the kernel this is inlined in
+  const double bstar = mul_(s.gTv, fma_(s.theta_star, s.c1, mul_(s.c2, s.q_star)));
+  const double Jb = -mul_(s.ustar, bstar);
+  const double UG = dmax(P.gmin, mul_(P.beta, fm::cbrt_pos(T.mc, dmax(mul_(dmax(0.0, Jb), s.h_bl), T.cbrt_floor))));
+  const double U = fm::sqrt_pos(fma_(UG, UG, s.dudv2));
+  const double ru = fm::rcp(s.ustar);
+  const double lu = dmin(fma_(mul_(P.a1, s.ustar), s.ustar, mul_(P.a2, ru)), P.lmax);
+  const double Linv = mul_(mul_(mul_(P.kappa, bstar), ru), ru);   // 1/L★ (0 when b★ == 0, i.e. L★ = Inf)
+  double chi_u, chi_s;
+  tab_core(P, T, tab, s.ustar, ru, lu, Linv, s.hd, s.log_hd, chi_u, chi_s);
+  s.ustar = mul_(chi_u, U);
+  s.theta_star = mul_(chi_s, s.dtheta);
+  s.q_star = mul_(chi_s, s.dq);
+}
+
+// ---- Float32 model, default tree --------------------------------------------------------------------
+// The reference's promotion rules (the 1.5e-5 air viscosity is a Float64 literal,
+// roughness_lengths.jl:94,126) make the Float32 iteration a MIXED-precision one: b★, the gustiness, U and L★ are
+// Float32; the roughness lengths, log(Δh/ℓ), every ψ and χ = ϰ/Π are Float64 (with the Float32-rounded plugin
+// parameters); u★, θ★, q★ are rounded to Float32 at the end of every trip.  The Float32 front below keeps each
+// operation separately rounded (no FMA contraction), as the reference does.
+struct FrontF32 {
+  float gmin, beta, Cg, g_rough, kappa, tol;
+  float g, d_zero;
+};
+struct FastPointF {
+  float gTv, c1, c2, dudv2, h_bl, hd, dtheta, dq;
+  double log_hd;
+  float ustar, theta_star, q_star;
+};
+
+__device__ __forceinline__ void tab_iteration(const FastParams& P, const FrontF32& Q, const TabParams& T,
+                                              const double* tab, FastPointF& s) {
+  const float bstar = __fmul_rn(s.gTv, __fadd_rn(__fmul_rn(s.theta_star, s.c1), __fmul_rn(s.c2, s.q_star)));
+  const float Jb = -__fmul_rn(s.ustar, bstar);
+  const float Jp = Jb > 0.0f ? Jb : 0.0f;
+  const float ug = __fmul_rn(Q.beta, cbrtf(__fmul_rn(Jp, s.h_bl)));
+  const float UG = Q.gmin < ug ? ug : Q.gmin;
+  const float U = sqrtf(__fadd_rn(s.dudv2, __fmul_rn(UG, UG)));
+  const float u2 = __fmul_rn(s.ustar, s.ustar);
+  const double ud = (double)s.ustar;
+  const double ru = fm::rcp(ud);
+  const float lW = __fdiv_rn(__fmul_rn(Q.Cg, u2), Q.g_rough);
+  const double lu = fm::dmin(fm::fma_(P.a2, ru, (double)lW), P.lmax);
+  // L★ = u★²/(ϰ b★) in Float32 (Inf when b★ == 0 or the quotient overflows: 1/L★ = 0)
+  const float Lstar = __fdiv_rn(u2, __fmul_rn(Q.kappa, bstar));
+  const float aL = fabsf(Lstar);
+  const double Linv = (aL < 3.0e38f) ? ((aL > 1.0e-30f) ? fm::rcp((double)Lstar) : 1.0 / (double)Lstar) : 0.0;
+  double chi_u, chi_s;
+  tab_core(P, T, tab, ud, ru, lu, Linv, (double)s.hd, s.log_hd, chi_u, chi_s);
+  s.ustar = (float)fm::mul_(chi_u, (double)U);
+  s.theta_star = (float)fm::mul_(chi_s, (double)s.dtheta);
+  s.q_star = (float)fm::mul_(chi_s, (double)s.dq);
 }
 
 // compute_interface_state.jl:10-18: the first trip always runs; then until drift < tol or it ≥ maxiter

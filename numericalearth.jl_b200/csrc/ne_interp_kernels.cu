@@ -265,13 +265,13 @@ template <class FT, class AT, class TT>
 static int launch_interp(const NeInterpDesc& d, cudaStream_t stream) {
   Layout L = make_layout(d.grid);
   InterpSource S = make_interp_source(d);
-  if (std::is_same<FT, double>::value) {   // staged variants are built for Float64 exchange grids
+  {
     int active = 0;
     for (int f = 0; f < d.n_fields; ++f) active += d.out[f] != nullptr;
     bool done = false;
-    if (active == 7) done = try_staged<double, AT, TT, 7>(d, L, S, stream);
-    else if (active == 5) done = try_staged<double, AT, TT, 5>(d, L, S, stream);
-    else if (active == 2) done = try_staged<double, AT, TT, 2>(d, L, S, stream);
+    if (active == 7) done = try_staged<FT, AT, TT, 7>(d, L, S, stream);
+    else if (active == 5) done = try_staged<FT, AT, TT, 5>(d, L, S, stream);
+    else if (active == 2) done = try_staged<FT, AT, TT, 2>(d, L, S, stream);
     if (done) {
       NE_CUDA_CHECK_LAUNCH("ne_interp_state(staged)");
       return NE_OK;

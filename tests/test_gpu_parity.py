@@ -40,12 +40,12 @@ def test_fractional_indices_and_interpolation_bit_exact(oracle_lib, cuda_backend
                 assert exact, f"{n} not bit-exact (atm {atm_FT}, stretched={stretched}, t={t})"
 
 
-@pytest.mark.parametrize("atm_FT", ["f64", "f32"])
-def test_staged_interpolation_bit_exact(oracle_lib, cuda_backend, cuda_lib, atm_FT):
+@pytest.mark.parametrize("FT,atm_FT", [("f64", "f64"), ("f64", "f32"), ("f32", "f32")])
+def test_staged_interpolation_bit_exact(oracle_lib, cuda_backend, cuda_lib, FT, atm_FT):
     """Exchange grid >= 4x finer than the source: the shared-memory staged kernel runs (blocks whose window wraps the
     periodic seam take its direct path).  Same bar as the direct kernel: bit-exact against the oracle."""
     cfg = dict(nx=600, ny=40, latitude=(-60.0, 60.0), src_nx=64, src_ny=32)
-    ref, dev = build_pair(cfg, oracle_lib, cuda_backend, FT="f64", atm_FT=atm_FT)
+    ref, dev = build_pair(cfg, oracle_lib, cuda_backend, FT=FT, atm_FT=atm_FT)
     ref.initialize(); dev.initialize()
     for t in (0.0, T_STEP, 10800.0):
         ref.interpolate_state(t); dev.interpolate_state(t)
@@ -355,6 +355,82 @@ def test_elevation_correction_parity(oracle_lib, cuda_backend, cuda_lib, FT):
     res = compare_fields(ref.ao_fluxes, dev.ao_fluxes, ref.grid, cuda_backend)
     for n, (r, fr, _) in res.items():
         assert fr <= (F64_TOL if FT == "f64" else F32_TOL), f"{n}: {fr}"
+
+
+def _ao_outputs(ci, backend):
+    out = {n: backend.to_numpy(getattr(ci.ao_fluxes, n)).copy() for n in ci.ao_fluxes.names()}
+    out["interface_temperature"] = backend.to_numpy(ci.ao_temperature).copy()
+    out["iterations"] = backend.to_numpy(ci.ao_iterations).copy()
+    return out
+
+
+@pytest.mark.parametrize("atm_FT", ["f64", "f32"])
+@pytest.mark.parametrize("theta", ["0", "8", "20"])
+def test_work_queue_kernel_equals_one_thread_per_point_kernel_bitwise(cuda_backend, cuda_lib, monkeypatch, atm_FT, theta):
+    """ne_flux_queue.cuh carries every point's iterate across rounds bit for bit: outputs AND trip counts equal those
+    of the one-thread-per-point table kernel (NE_B200_TAB_CLASSIC=1), whatever the deferral threshold."""
+    dev = synthetic.build_case("C2", cuda_backend, FT="f64", atm_FT=atm_FT, with_iterations=True)
+    dev.initialize()
+    dev.interpolate_state(T_STEP)
+    monkeypatch.setenv("NE_B200_TAB_CLASSIC", "1")
+    dev.compute_atmosphere_ocean_fluxes()
+    cuda_backend.synchronize()
+    classic = _ao_outputs(dev, cuda_backend)
+    monkeypatch.delenv("NE_B200_TAB_CLASSIC")
+    monkeypatch.setenv("NE_B200_QUEUE", "1")
+    monkeypatch.setenv("NE_B200_QUEUE_THETA", theta)
+    for n in dev.ao_fluxes.names():
+        getattr(dev.ao_fluxes, n).fill_(float("nan"))
+    dev.ao_iterations.fill_(-1)
+    dev.compute_atmosphere_ocean_fluxes()
+    cuda_backend.synchronize()
+    queue = _ao_outputs(dev, cuda_backend)
+    g = dev.grid
+    # trip counts and the converged iterate: bit for bit; the flux epilogue is compiled once per kernel (FMA
+    # contraction may differ between the two inlining contexts): 1e-13
+    for n, a in classic.items():
+        x, y = g.interior(a), g.interior(queue[n])
+        if n in ("iterations", "friction_velocity", "temperature_scale", "water_vapor_scale", "interface_temperature"):
+            assert np.array_equal(x, y, equal_nan=True), f"{n} differs at {int((x != y).sum())} points (theta={theta})"
+        else:
+            s = float(np.abs(x).max()) or 1.0
+            assert float(np.abs(x - y).max()) / s <= 1e-13, f"{n} (theta={theta}): {float(np.abs(x - y).max()) / s}"
+
+
+def test_float32_model_fast_path_against_generic_kernel_and_oracle(oracle_lib, cuda_backend, cuda_lib, monkeypatch):
+    """Float32 model, default tree: the mixed-precision table iteration on the work-queue kernel against (i) the
+    generic kernel (same promotion rules, libdevice closed forms) and (ii) the oracle.  Bar: 1e-5 relative to the
+    field scale; the trip counts of points that converge agree except where a last-bit difference moves the
+    Float32 rounding of an iterate (tol = 1e-8 < eps(Float32): the loop stops on exact stationarity)."""
+    ref, dev = build_pair("C2", oracle_lib, cuda_backend, FT="f32", atm_FT="f32")
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP)
+    dev.interpolate_state(T_STEP)
+    dev.compute_atmosphere_ocean_fluxes()
+    cuda_backend.synchronize()
+    fast = _ao_outputs(dev, cuda_backend)
+    monkeypatch.setenv("NE_B200_FORCE_GENERIC", "1")
+    dev.compute_atmosphere_ocean_fluxes()
+    cuda_backend.synchronize()
+    generic = _ao_outputs(dev, cuda_backend)
+    monkeypatch.delenv("NE_B200_FORCE_GENERIC")
+    g = dev.grid
+    for n in dev.ao_fluxes.names():
+        a, b, r = g.interior(fast[n]).astype(np.float64), g.interior(generic[n]).astype(np.float64), \
+            g.interior(getattr(ref.ao_fluxes, n)).astype(np.float64)
+        s = float(np.abs(r).max()) or 1.0
+        assert np.isfinite(a).all(), n
+        assert np.abs(a - b).max() / s <= F32_TOL, f"{n}: fast vs generic {np.abs(a - b).max() / s}"
+        assert np.abs(a - r).max() / s <= F32_TOL, f"{n}: fast vs oracle {np.abs(a - r).max() / s}"
+    fi, gi, oi = (g.interior(x).astype(int) for x in (fast["iterations"], generic["iterations"], ref.ao_iterations))
+    assert ((fi > 0) == (oi > 0)).all()
+    # trip counts: statistically those of the reference algorithm (a last-bit difference in a Float64 intermediate
+    # moves the Float32 rounding of an iterate, and with it the trip at which the iterate becomes stationary)
+    conv = (oi < 100) & (gi < 100) & (fi < 100)
+    assert float((np.abs(fi[conv] - gi[conv]) > 2).mean()) <= 0.02, float((np.abs(fi[conv] - gi[conv]) > 2).mean())
+    assert abs(float(fi[oi > 0].mean()) - float(oi[oi > 0].mean())) <= 0.5
+    assert abs(float((fi == 100).mean()) - float((oi == 100).mean())) <= 0.005
+    assert fi.max() <= 100
 
 
 def test_no_kernel_variant_raises(cuda_backend, cuda_lib):

@@ -11,10 +11,11 @@ from numericalearth_jl_b200 import synthetic  # noqa: E402
 backend = ne_b200.TorchCudaBackend("cuda:0")
 lib = ne_b200.get_library()
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C4"
-ci = synthetic.build_case(cfg, backend, FT="f64", atm_FT="f32", with_iterations=False)
+FT = sys.argv[2] if len(sys.argv) > 2 else "f64"
+ci = synthetic.build_case(cfg, backend, FT=FT, atm_FT="f32", with_iterations=False)
 ci.initialize()
 ci.interpolate_state(0.37 * 10800.0)
 d = ci.atmosphere_ocean_desc()
 for _ in range(4):
-    lib.call("atmosphere_ocean_fluxes", "f64", d, backend.stream())
+    lib.call("atmosphere_ocean_fluxes", FT, d, backend.stream())
 torch.cuda.synchronize()

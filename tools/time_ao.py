@@ -12,10 +12,17 @@ from numericalearth_jl_b200 import synthetic  # noqa: E402
 
 
 def main():
-    settings = [dict(kv.split("=") for kv in s.split(",") if kv) for s in sys.argv[1:]] or [{}]
+    # usage: time_ao.py [--config C4] [--dtype f64] [--out name] ENV1=a,ENV2=b ENV1=c ...
+    argv = sys.argv[1:]
+    opts = {"--config": "C4", "--dtype": "f64", "--out": "time_ao"}
+    while argv and argv[0] in opts:
+        opts[argv[0]] = argv[1]
+        argv = argv[2:]
+    settings = [dict(kv.split("=") for kv in s.split(",") if kv) for s in argv] or [{}]
     backend = ne_b200.TorchCudaBackend("cuda:0")
     lib = ne_b200.get_library()
-    ci = synthetic.build_case("C4", backend, FT="f64", atm_FT="f32", with_iterations=False)
+    FT = opts["--dtype"]
+    ci = synthetic.build_case(opts["--config"], backend, FT=FT, atm_FT="f32", with_iterations=False)
     ci.initialize()
     ci.interpolate_state(0.37 * 10800.0)
     d = ci.atmosphere_ocean_desc()
@@ -25,20 +32,20 @@ def main():
         for k, v in env.items():
             os.environ[k] = v
         for _ in range(3):
-            lib.call("atmosphere_ocean_fluxes", "f64", d, stream)
+            lib.call("atmosphere_ocean_fluxes", FT, d, stream)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
         for _ in range(10):
-            lib.call("atmosphere_ocean_fluxes", "f64", d, stream)
+            lib.call("atmosphere_ocean_fluxes", FT, d, stream)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        out.append({"env": env, "ms": ms})
-        print(env, f"{ms:.3f} ms")
+        out.append({"env": env, "ms": ms, "config": opts["--config"], "dtype": FT})
+        print(opts["--config"], FT, env, f"{ms:.3f} ms", flush=True)
         for k in env:
             os.environ.pop(k, None)
-    json.dump(out, open("gpurun_out/time_ao.json", "w"))
+    json.dump(out, open(f"gpurun_out/{opts['--out']}.json", "w"))
 
 
 if __name__ == "__main__":
