@@ -67,6 +67,7 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--e2e-chunks", type=int, default=8)
+    p.add_argument("--equal-bands", action="store_true", help="equal row counts per band instead of cost-balanced bands")
     return p.parse_args()
 
 
@@ -194,7 +195,8 @@ def workload_config(args, n):
     return {"workload": f"{args.config}: {c['nx']}x{c['ny']} exchange grid (lat {c['latitude']}), JRA55-shaped 640x320 "
                         f"{args.atm_dtype} atmosphere + radiation, SimilarityTheoryFluxes defaults, OceanOnlyModel interface step",
             "exchange_dtype": args.dtype, "atmosphere_dtype": args.atm_dtype,
-            "partition": f"{n} latitude band(s), one-ring overcompute, no data-path collective",
+            "partition": f"{n} latitude band(s)" + ("" if n == 1 else (", equal row counts" if args.equal_bands else
+                         ", rows balanced by active-point count")) + ", one-ring overcompute, no data-path collective",
             "l2": "inputs larger than L2 (≈35 fields x 58 MB at N=1); no explicit flush",
             "points_per_step": (c["nx"] + 2) * (c["ny"] + 2)}
 
@@ -218,7 +220,9 @@ def b200_arm(args):
     backend = ne_b200.TorchCudaBackend(f"cuda:{local_rank}")
     lib = ne_b200.get_library()
     cfg = synthetic.CONFIGS[args.config]
-    grid = sharding.band_grid(cfg["nx"], cfg["ny"], cfg["latitude"], rank, world, FT=args.dtype)
+    # latitude bands balanced by estimated row cost (active-point count from the land mask: static information)
+    weights = synthetic.row_cost_weights(args.config, FT=args.dtype) if (world > 1 and not args.equal_bands) else None
+    grid = sharding.band_grid(cfg["nx"], cfg["ny"], cfg["latitude"], rank, world, FT=args.dtype, weights=weights)
     ci = synthetic.build_case(args.config, backend, FT=args.dtype, atm_FT=args.atm_dtype, grid=grid, with_iterations=True)
     ci.initialize()
     f = ci.ao_fluxes

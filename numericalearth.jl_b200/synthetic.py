@@ -87,6 +87,31 @@ def atmosphere_arrays(src: LatLonSourceGrid, nt, rng, hours=3.0):
     return out
 
 
+def inactive_mask(grid: ExchangeGrid):
+    """~30 % inactive from a thresholded low-wavenumber field (+ everything beyond the Bounded-y domain).
+    Deterministic (no random numbers): the mask of a latitude band is a slice of the global one."""
+    shape = grid.shape
+    phi = np.deg2rad(grid.phi.astype(np.float64))[:, None] * np.ones((1, shape[1]))
+    lam = np.deg2rad(grid.lam.astype(np.float64))[None, :] * np.ones((shape[0], 1))
+    low = (np.sin(2 * lam + 0.3) * np.cos(3 * phi) + 0.6 * np.sin(5 * lam - 1.0) * np.sin(2 * phi + 0.5) +
+           0.4 * np.cos(lam * 3 + phi * 4))
+    inactive = low > np.quantile(low, 0.70)
+    j = np.arange(shape[0])
+    outside = (j < grid.hy) | (j >= grid.hy + grid.ny)
+    inactive[outside, :] = True
+    return inactive.astype(np.uint8)
+
+
+def row_cost_weights(config, FT="f64", active_cost=4.3):
+    """Per-row cost estimate of the interface step on the GLOBAL grid of `config` for
+    sharding.latitude_bands(weights=...): every point pays the HBM-bound kernels (weight 1), an active
+    point additionally the similarity-theory solve (measured ~4.3x that on B200, profiles/r01_notes.md)."""
+    cfg = CONFIGS[config] if isinstance(config, str) else config
+    g = ExchangeGrid(nx=cfg["nx"], ny=cfg["ny"], hx=cfg.get("hx", 7), hy=cfg.get("hy", 7), latitude=cfg["latitude"], FT=FT)
+    m = inactive_mask(g)[g.hy:g.hy + g.ny, g.hx:g.hx + g.nx]
+    return g.nx + active_cost * (m == 0).sum(axis=1).astype(np.float64)
+
+
 def ocean_arrays(grid: ExchangeGrid, rng, sea_ice=False):
     """Exchange-layout (ny+2hy, nx+2hx) ocean surface / sea-ice state + inactive mask."""
     npd = np.float64 if grid.FT == "f64" else np.float32
@@ -98,14 +123,7 @@ def ocean_arrays(grid: ExchangeGrid, rng, sea_ice=False):
     o["S"] = 35 + rng.normal(0, 0.6, shape)
     o["u"] = rng.normal(0, 0.15, shape)
     o["v"] = rng.normal(0, 0.15, shape)
-    # ~30 % inactive from a thresholded low-wavenumber field (+ everything beyond the Bounded-y domain)
-    low = (np.sin(2 * lam + 0.3) * np.cos(3 * phi) + 0.6 * np.sin(5 * lam - 1.0) * np.sin(2 * phi + 0.5) +
-           0.4 * np.cos(lam * 3 + phi * 4))
-    inactive = low > np.quantile(low, 0.70)
-    j = np.arange(shape[0])
-    outside = (j < grid.hy) | (j >= grid.hy + grid.ny)
-    inactive[outside, :] = True
-    o["inactive"] = inactive.astype(np.uint8)
+    o["inactive"] = inactive_mask(grid)
     if sea_ice:
         latd = np.abs(np.rad2deg(phi))
         conc = np.clip((latd - 62) / 6, 0, 1) * rng.uniform(0.8, 1.0, shape)
