@@ -17,6 +17,7 @@
 #pragma once
 
 #include <cstdlib>
+#include <vector>
 
 #include "ne_physics.cuh"
 
@@ -167,42 +168,45 @@ inline FastParams make_fast_params(const NeFluxFormulation& f, double g, bool f3
   P.beta = R(f.subgrid_velocities.gustiness_parameter); P.gmin = R(f.subgrid_velocities.minimum_gustiness);
   P.kappa = R(f.von_karman_constant); P.d_zero = R(f.zero_plane_displacement); P.g = R(g);
   P.tol = R(f.stop.tolerance); P.maxiter = f.stop.maxiter; P.fixed = f.stop.kind == NE_STOP_FIXED_ITERATIONS;
-  if (f32) {   // the small-|ζ| closed-form polynomial belongs to the Float64 closed-form kernel only
-    P.zsmall = 0; P.zsmall_inv = 0;
-    for (int k = 0; k <= NE_FAST_PSI_DEG; ++k) { P.pm[k] = 0; P.ps[k] = 0; }
-    return P;
-  }
-  // small-|ζ| polynomials (ψ(ℓ/L★) always lands here: |ℓ/L★| ≲ 1e-3), cached per parameter set
-  static thread_local double cache_key[24];
-  static thread_local double cache_val[2 * (NE_FAST_PSI_DEG + 1) + 1];
-  static thread_local bool cache_ok = false;
+  // the small-|ζ| polynomial belongs to the closed-form kernel only: see add_small_zeta_poly
+  P.zsmall = 0; P.zsmall_inv = 0;
+  for (int k = 0; k <= NE_FAST_PSI_DEG; ++k) { P.pm[k] = 0; P.ps[k] = 0; }
+  return P;
+}
+
+// Small-|ζ| polynomials of the closed-form kernel (ao_flux_fast_kernel; ψ(ℓ/L★) always lands there: |ℓ/L★| ≲ 1e-3),
+// fitted once per Edson parameter set and kept in a small per-thread cache (the table-driven kernels do not use them).
+inline void add_small_zeta_poly(FastParams& P, const NeFluxFormulation& f) {
+  struct Entry { double key[24]; double val[2 * (NE_FAST_PSI_DEG + 1) + 1]; };
+  static thread_local std::vector<Entry> cache;
   const char* off = std::getenv("NE_B200_NO_SMALL_ZETA_POLY");
-  const bool disabled = off && off[0] == '1';
+  if (off && off[0] == '1') return;
+  const double* p = f.psi_momentum.a.p;
+  const double* q = f.psi_temperature.a.p;
   double key[24];
   for (int k = 0; k < 12; ++k) { key[k] = p[k]; key[12 + k] = q[k]; }
-  if (disabled) {
-    P.zsmall = 0; P.zsmall_inv = 0;
-    for (int k = 0; k <= NE_FAST_PSI_DEG; ++k) { P.pm[k] = 0; P.ps[k] = 0; }
-    return P;
-  }
-  if (!(cache_ok && std::memcmp(key, cache_key, sizeof(key)) == 0)) {
+  const Entry* hit = nullptr;
+  for (const Entry& e : cache)
+    if (std::memcmp(key, e.key, sizeof(key)) == 0) { hit = &e; break; }
+  if (!hit) {
+    Entry e;
+    std::memcpy(e.key, key, sizeof(key));
     double zs = 1.0 / 64;
     while (zs > 1e-6) {
-      const double em = fit_small_zeta([&](long double z) { return psi_m_unstable_ld(p, z); }, zs, cache_val);
-      const double es = fit_small_zeta([&](long double z) { return psi_s_unstable_ld(q, z); }, zs, cache_val + NE_FAST_PSI_DEG + 1);
+      const double em = fit_small_zeta([&](long double z) { return psi_m_unstable_ld(p, z); }, zs, e.val);
+      const double es = fit_small_zeta([&](long double z) { return psi_s_unstable_ld(q, z); }, zs, e.val + NE_FAST_PSI_DEG + 1);
       if (em <= 4e-16 && es <= 4e-16) break;
       zs *= 0.5;
     }
     if (!(zs > 1e-6)) zs = 0;
-    cache_val[2 * (NE_FAST_PSI_DEG + 1)] = zs;
-    std::memcpy(cache_key, key, sizeof(key));
-    cache_ok = true;
+    e.val[2 * (NE_FAST_PSI_DEG + 1)] = zs;
+    if (cache.size() >= 16) cache.clear();
+    cache.push_back(e);
+    hit = &cache.back();
   }
-  for (int k = 0; k <= NE_FAST_PSI_DEG; ++k) { P.pm[k] = cache_val[k]; P.ps[k] = cache_val[NE_FAST_PSI_DEG + 1 + k]; }
-  P.zsmall = cache_val[2 * (NE_FAST_PSI_DEG + 1)];
+  for (int k = 0; k <= NE_FAST_PSI_DEG; ++k) { P.pm[k] = hit->val[k]; P.ps[k] = hit->val[NE_FAST_PSI_DEG + 1 + k]; }
+  P.zsmall = hit->val[2 * (NE_FAST_PSI_DEG + 1)];
   P.zsmall_inv = P.zsmall > 0 ? 1.0 / P.zsmall : 0.0;
-  return P;
-
 }
 
 // ψ_m(ζ), Edson et al. (2013) — similarity_theory_turbulent_fluxes.jl:501-532

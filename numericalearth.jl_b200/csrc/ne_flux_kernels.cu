@@ -23,6 +23,7 @@
 #include "ne_flux_fast.cuh"
 #include "ne_flux_tab.cuh"
 #include "ne_flux_queue.cuh"
+#include "ne_flux_asi_fast.cuh"
 #include "ne_interp_device.cuh"
 #include "ne_physics.cuh"
 
@@ -338,9 +339,14 @@ ao_fused_tab_kernel(const __grid_constant__ NeInterpDesc atm, const __grid_const
 // Device-resident solver tables, built once per (device, ψ parameter set) and kept for the life of the
 // process (14 KB each).  The first call for a parameter set allocates and copies synchronously, so it
 // must happen outside CUDA-graph capture; later calls only enqueue the kernel.
+struct SolverTableKey {
+  NeStabilityProfile psi_momentum, psi_temperature;
+  double gustiness_parameter, minimum_gustiness;
+  int64_t f32;
+};
 struct SolverTables {
   int device;
-  double key[27];
+  SolverTableKey key;
   double* dptr;
   TabParams T;
   double fit_error;
@@ -351,21 +357,23 @@ static std::vector<SolverTables> g_tabs;
 static const SolverTables* solver_tables(const NeFluxFormulation& f, bool f32 = false) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  double key[27];
-  key[26] = f32 ? 1.0 : 0.0;
-  for (int k = 0; k < 12; ++k) { key[k] = f.psi_momentum.a.p[k]; key[12 + k] = f.psi_temperature.a.p[k]; }
-  key[24] = f.subgrid_velocities.gustiness_parameter;
-  key[25] = f.subgrid_velocities.minimum_gustiness;
+  SolverTableKey key;
+  std::memset(&key, 0, sizeof(key));
+  std::memcpy(&key.psi_momentum, &f.psi_momentum, sizeof(NeStabilityProfile));
+  std::memcpy(&key.psi_temperature, &f.psi_temperature, sizeof(NeStabilityProfile));
+  key.gustiness_parameter = f.subgrid_velocities.gustiness_parameter;
+  key.minimum_gustiness = f.subgrid_velocities.minimum_gustiness;
+  key.f32 = f32 ? 1 : 0;
   std::lock_guard<std::mutex> lock(g_tab_mutex);
   for (const SolverTables& t : g_tabs)
-    if (t.device == dev && std::memcmp(t.key, key, sizeof(key)) == 0) return t.dptr ? &t : nullptr;
+    if (t.device == dev && std::memcmp(&t.key, &key, sizeof(key)) == 0) return t.dptr ? &t : nullptr;
   SolverTables t;
   t.device = dev;
-  std::memcpy(t.key, key, sizeof(key));
+  std::memcpy(&t.key, &key, sizeof(key));
   t.dptr = nullptr;
   std::vector<double> host(fm::TAB_SIZE);
   t.fit_error = build_solver_tables(f, host.data(), t.T, f32);
-  if (t.fit_error <= 2e-15) {   // else: ψ parameters the polynomials cannot represent → closed-form kernel
+  if (t.fit_error <= 2e-15) {   // else: ψ parameters the polynomials cannot represent → closed-form / generic kernel
     if (cudaMalloc(&t.dptr, sizeof(double) * fm::TAB_SIZE) != cudaSuccess ||
         cudaMemcpy(t.dptr, host.data(), sizeof(double) * fm::TAB_SIZE, cudaMemcpyHostToDevice) != cudaSuccess) {
       cudaGetLastError();
@@ -519,33 +527,69 @@ static uint32_t* queue_counters() {
   return q.dptr;
 }
 
-// Work-queue solve (ne_flux_queue.cuh): persistent warps, grid = resident CTAs x NE_B200_QUEUE_WAVES
-template <class FT, class CT>
-static int launch_queue(const NeAtmosOceanDesc& d, const SolverTables* tabs, cudaStream_t s) {
-  Layout L = make_layout(d.grid);
-  const bool f32 = std::is_same<FT, float>::value;
-  FastParams P = make_fast_params(d.flux, d.gravitational_acceleration, f32);
-  FrontF32 Q = make_front_f32(d);
-  TabParams TP = tabs->T;
-  const bool hs = !d.surface_layer_height.ptr && !d.boundary_layer_height.ptr;
-  TP.log_hd = f32 ? std::log((double)((float)d.surface_layer_height.value - Q.d_zero))
-                  : std::log(d.surface_layer_height.value - P.d_zero);
+// grid of the persistent work-queue kernels: resident CTAs x NE_B200_QUEUE_WAVES, at most one CTA per 32*warps points
+static unsigned queue_grid(int64_t n, int warps, int ctas_per_sm) {
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t n = (int64_t)L.ni * L.nj;
-  const int64_t ctas_needed = (n + 255) / 256;
+  const int64_t ctas_needed = (n + 32 * warps - 1) / (32 * warps);
   const int waves = std::max(1, env_int("NE_B200_QUEUE_WAVES", 1));
-  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)sms * 3 * waves));
-  int theta = env_int("NE_B200_QUEUE_THETA", 12);
-  theta = theta < 0 ? 0 : (theta > 24 ? 24 : theta);
-  const Thermo<CT> th = Thermo<CT>::make(d.thermo);
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)sms * ctas_per_sm * waves));
+}
+static int queue_theta() {
+  const int theta = env_int("NE_B200_QUEUE_THETA", 12);
+  return theta < 0 ? 0 : (theta > 24 ? 24 : theta);
+}
+
+// Work-queue solve (ne_flux_queue.cuh), atmosphere–ocean default tree
+template <class FT, class CT, bool HS>
+static int launch_queue_hs(const NeAtmosOceanDesc& d, const SolverTables* tabs, cudaStream_t s) {
+  using Problem = AoProblem<FT, CT, HS>;
+  const bool f32 = std::is_same<FT, float>::value;
+  typename Problem::Params prm;
+  prm.d = d;
+  prm.L = make_layout(d.grid);
+  prm.th = Thermo<CT>::make(d.thermo);
+  prm.P = make_fast_params(d.flux, d.gravitational_acceleration, f32);
+  prm.Q = make_front_f32(d);
+  prm.T = tabs->T;
+  prm.T.log_hd = f32 ? std::log((double)((float)d.surface_layer_height.value - prm.Q.d_zero))
+                     : std::log(d.surface_layer_height.value - prm.P.d_zero);
   uint32_t* counters = queue_counters();
   NE_REQUIRE(counters != nullptr, "atmosphere-ocean: could not allocate the work-queue counters");
-  if (hs) ao_flux_queue_kernel<FT, CT, 3, true><<<grid, 256, 0, s>>>(d, L, th, P, TP, Q, tabs->dptr, theta, counters);
-  else ao_flux_queue_kernel<FT, CT, 3, false><<<grid, 256, 0, s>>>(d, L, th, P, TP, Q, tabs->dptr, theta, counters);
+  const unsigned grid = queue_grid((int64_t)prm.L.ni * prm.L.nj, 8, 3);
+  flux_queue_kernel<Problem, 8, 3><<<grid, 256, 0, s>>>(prm, tabs->dptr, queue_theta(), counters);
   NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(queue)");
   return NE_OK;
+}
+template <class FT, class CT>
+static int launch_queue(const NeAtmosOceanDesc& d, const SolverTables* tabs, cudaStream_t s) {
+  const bool hs = !d.surface_layer_height.ptr && !d.boundary_layer_height.ptr;
+  return hs ? launch_queue_hs<FT, CT, true>(d, tabs, s) : launch_queue_hs<FT, CT, false>(d, tabs, s);
+}
+
+// atmosphere–sea-ice default tree on the work-queue kernel (ne_flux_asi_fast.cuh)
+template <class CT, bool HS>
+static int launch_asi_queue_hs(const NeAtmosSeaIceDesc& d, const SolverTables* tabs, cudaStream_t s) {
+  using Problem = AsiProblem<CT, HS>;
+  typename Problem::Params prm;
+  prm.d = d;
+  prm.L = make_layout(d.grid);
+  prm.th = Thermo<CT>::make(d.thermo);
+  prm.P = make_fast_params(d.flux, d.gravitational_acceleration, false);
+  prm.T = tabs->T;
+  prm.T.log_hd = std::log(d.surface_layer_height.value - prm.P.d_zero);
+  uint32_t* counters = queue_counters();
+  NE_REQUIRE(counters != nullptr, "atmosphere-sea-ice: could not allocate the work-queue counters");
+  const unsigned grid = queue_grid((int64_t)prm.L.ni * prm.L.nj, 4, 4);
+  flux_queue_kernel<Problem, 4, 4><<<grid, 128, 0, s>>>(prm, tabs->dptr, queue_theta(), counters);
+  NE_CUDA_CHECK_LAUNCH("ne_atmosphere_sea_ice_fluxes(queue)");
+  return NE_OK;
+}
+template <class CT>
+static int launch_asi_queue(const NeAtmosSeaIceDesc& d, const SolverTables* tabs, cudaStream_t s) {
+  const bool hs = !d.surface_layer_height.ptr && !d.boundary_layer_height.ptr;
+  return hs ? launch_asi_queue_hs<CT, true>(d, tabs, s) : launch_asi_queue_hs<CT, false>(d, tabs, s);
 }
 
 template <class FT>
@@ -592,6 +636,7 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
         NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(tab)");
         return NE_OK;
       }
+      add_small_zeta_poly(P, d->flux);   // closed-form kernel only
       const char* mb = std::getenv("NE_B200_FAST_MINB");   // occupancy experiment knob
       const int minb = mb ? std::atoi(mb) : 8;   // 64 registers/thread measured fastest on B200 (profiles/r01_notes.md)
       const unsigned nb = (unsigned)((n + 127) / 128);
@@ -708,6 +753,12 @@ static int asi_entry(const NeAtmosSeaIceDesc* d, void* stream) {
   const bool ct64 = d->thermo.dtype == NE_F64;
   const bool v64 = std::is_same<FT, double>::value || viscosity_is_f64_literal(d->flux);
   if (std::is_same<FT, double>::value) {
+    // default tree: work-queue kernel with the table-driven similarity step (NE_B200_FORCE_GENERIC=1: generic kernel)
+    if (asi_fast_path_eligible(d->flux, d->properties) && queue_path_ok(d->grid) && !env_flag("NE_B200_FORCE_GENERIC") &&
+        !env_flag("NE_B200_CLOSED_FORM_PSI")) {
+      const SolverTables* tabs = solver_tables(d->flux, false);
+      if (tabs) return ct64 ? launch_asi_queue<double>(*d, tabs, s) : launch_asi_queue<float>(*d, tabs, s);
+    }
     return ct64 ? launch_asi<double, double, double>(*d, s) : launch_asi<double, float, double>(*d, s);
   } else {
     if (ct64) return v64 ? launch_asi<float, double, double>(*d, s) : launch_asi<float, double, float>(*d, s);

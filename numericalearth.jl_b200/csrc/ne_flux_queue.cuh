@@ -133,26 +133,71 @@ __device__ __forceinline__ void ao_prologue(const NeAtmosOceanDesc& d, const Lay
   s.dq = aq - qs;
 }
 
-__device__ __forceinline__ void q_iterate(const FastParams& P, const FrontF32&, const TabParams& T, const double* tab, FastPoint& s) {
-  tab_iteration(P, T, tab, s);
-}
-__device__ __forceinline__ void q_iterate(const FastParams& P, const FrontF32& Q, const TabParams& T, const double* tab, FastPointF& s) {
-  tab_iteration(P, Q, T, tab, s);
-}
+// ---- the problems the work-queue kernel runs ----------------------------------------------------------
+// A Problem supplies: Params (one __grid_constant__ POD), FT, Point, NSTATE (iterate components carried by a
+// deferred point), and the device functions used below.
 
-template <class FT, class CT, int MINB, bool HS>
-__global__ void __launch_bounds__(256, MINB)
-ao_flux_queue_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_constant__ Layout L,
-                     const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P,
-                     const __grid_constant__ TabParams T, const __grid_constant__ FrontF32 Q,
-                     const double* __restrict__ gtab, const int theta, uint32_t* __restrict__ counters) {
+// atmosphere–ocean, default tree (BulkTemperature): Float64 or Float32 model
+template <class FT_, class CT, bool HS>
+struct AoProblem {
+  using FT = FT_;
   using Point = typename QPointOf<FT>::type;
+  static constexpr int NSTATE = 3;
+  struct Params {
+    NeAtmosOceanDesc d;
+    Layout L;
+    Thermo<CT> th;
+    FastParams P;
+    TabParams T;
+    FrontF32 Q;
+  };
+  __device__ static __forceinline__ const Layout& layout(const Params& p) { return p.L; }
+  __device__ static __forceinline__ const FastParams& fast(const Params& p) { return p.P; }
+  __device__ static __forceinline__ FT tolerance(const Params& p) {
+    return std::is_same<FT, float>::value ? (FT)p.Q.tol : (FT)p.P.tol;
+  }
+  // true: the point iterates; false: its final state was written here
+  __device__ static __forceinline__ bool admit(const Params& p, int32_t idx) {
+    const bool not_water = p.d.inactive ? (p.d.inactive[idx] != 0) : false;
+    const bool no_trips = p.P.fixed && p.P.maxiter <= 0;
+    if ((not_water && !p.P.fixed) || no_trips) {   // untouched initial state (:131-137), zeroed when masked
+      ao_write_outputs<FT, CT>(p.d, p.L, p.th, idx, (FT)1e-4, (FT)1e-4, (FT)1e-4, not_water, 0);
+      return false;
+    }
+    return true;
+  }
+  __device__ static __forceinline__ void prologue(const Params& p, int32_t idx, Point& s, bool fresh) {
+    ao_prologue<CT, HS>(p.d, p.L, p.th, p.P, p.Q, p.T, idx, s);
+    if (fresh) s.ustar = s.theta_star = s.q_star = (FT)1e-4;
+  }
+  __device__ static __forceinline__ void get_state(const Point& s, FT* v) { v[0] = s.ustar; v[1] = s.theta_star; v[2] = s.q_star; }
+  __device__ static __forceinline__ void set_state(Point& s, const FT* v) { s.ustar = v[0]; s.theta_star = v[1]; s.q_star = v[2]; }
+  // one trip of iterate_interface_state; returns the drift |Δu★| + |Δθ★| + |Δq★|
+  __device__ static __forceinline__ FT trip(const Params& p, const double* tab, Point& s, int) {
+    const FT pu = s.ustar, pt = s.theta_star, pq = s.q_star;
+    if constexpr (std::is_same<FT, float>::value) tab_iteration(p.P, p.Q, p.T, tab, s);
+    else tab_iteration(p.P, p.T, tab, s);
+    return m_abs(s.ustar - pu) + m_abs(s.theta_star - pt) + m_abs(s.q_star - pq);
+  }
+  __device__ static __forceinline__ void finish(const Params& p, int32_t idx, const Point& s, int it) {
+    const bool not_water = (p.P.fixed && p.d.inactive) ? (p.d.inactive[idx] != 0) : false;   // FixedIterations iterates masked points too (:144)
+    ao_write_outputs<FT, CT>(p.d, p.L, p.th, idx, s.ustar, s.theta_star, s.q_star, not_water, it);
+  }
+};
+
+template <class Problem, int NWARPS, int MINB>
+__global__ void __launch_bounds__(NWARPS * 32, MINB)
+flux_queue_kernel(const __grid_constant__ typename Problem::Params p, const double* __restrict__ gtab, const int theta,
+                  uint32_t* __restrict__ counters) {
+  using FT = typename Problem::FT;
+  using Point = typename Problem::Point;
+  constexpr int NS = Problem::NSTATE;
   __shared__ __align__(16) double tab[fm::TAB_SIZE];
-  __shared__ int32_t f_idx[8][QRING];               // fresh points: only the point index
-  __shared__ int32_t d_idx[8][QRING];               // deferred points: index, trips so far, iterate
-  __shared__ int32_t d_it[8][QRING];
-  __shared__ FT d_st[8][3][QRING];
-  for (int k = threadIdx.x; k < fm::TAB_SIZE / 2; k += 256)
+  __shared__ int32_t f_idx[NWARPS][QRING];          // fresh points: only the point index
+  __shared__ int32_t d_idx[NWARPS][QRING];          // deferred points: index, trips so far, iterate
+  __shared__ int32_t d_it[NWARPS][QRING];
+  __shared__ FT d_st[NWARPS][NS][QRING];
+  for (int k = threadIdx.x; k < fm::TAB_SIZE / 2; k += NWARPS * 32)
     reinterpret_cast<double2*>(tab)[k] = __ldg(reinterpret_cast<const double2*>(gtab) + k);
   __syncthreads();
 
@@ -160,15 +205,14 @@ ao_flux_queue_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_co
   int32_t* const fidx = f_idx[warp];
   int32_t* const didx = d_idx[warp];
   int32_t* const dit = d_it[warp];
-  FT* const du_ = d_st[warp][0];
-  FT* const dt_ = d_st[warp][1];
-  FT* const dq_ = d_st[warp][2];
+  const Layout& L = Problem::layout(p);
+  const FastParams& P = Problem::fast(p);
   const uint32_t ni = (uint32_t)L.ni;
   const uint32_t n = ni * (uint32_t)L.nj;          // the host guarantees the parent array has < 2^31 elements
   const uint32_t ntiles = (n + 31u) >> 5;
   // Dynamic tile assignment: warps take the next 32-point tile from a global counter, so the moving front of
-  // tiles in flight is contiguous in memory and a warp that drew masked (land) tiles simply draws more.  The next
-  // tile index is requested one pull ahead; its latency hides behind the round in between.
+  // tiles in flight is contiguous in memory and a warp that drew masked (land, ice-free) tiles simply draws more.
+  // The next tile index is requested one pull ahead; its latency hides behind the round in between.
   uint32_t* const tile_counter = counters;
   uint32_t* const cta_counter = counters + 1;
   auto grab = [&]() {
@@ -181,9 +225,7 @@ ao_flux_queue_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_co
   const unsigned below = (1u << lane) - 1u;
   int fhead = 0, fcount = 0, dhead = 0, dcount = 0;   // warp-uniform ring state
   const int maxiter = P.maxiter;
-  const FT tol = P.fixed ? (FT)-1 : (std::is_same<FT, float>::value ? (FT)Q.tol : (FT)P.tol);
-  const bool solve_inactive = P.fixed != 0;         // FixedIterations also iterates masked points (:144)
-  const bool no_trips = P.fixed && maxiter <= 0;
+  const FT tol = P.fixed ? (FT)-1 : Problem::tolerance(p);   // drift ≥ 0 > −1: never "converged" under FixedIterations
 
   for (;;) {
     // ---- pull tiles until a full round (of deferred or of fresh points) is pending
@@ -196,10 +238,7 @@ ao_flux_queue_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_co
       if (t < n) {
         const uint32_t jj = t / ni;
         idx = (int32_t)L.at(L.i_lo + (int32_t)(t - jj * ni), L.j_lo + (int32_t)jj);
-        const bool not_water = d.inactive ? (d.inactive[idx] != 0) : false;
-        if ((not_water && !solve_inactive) || no_trips)   // untouched initial state (:131-137), zeroed when masked
-          ao_write_outputs<FT, CT>(d, L, th, idx, (FT)1e-4, (FT)1e-4, (FT)1e-4, not_water, 0);
-        else enq = true;
+        enq = Problem::admit(p, idx);
       }
       const unsigned m = __ballot_sync(0xffffffffu, enq);
       if (enq) fidx[(fhead + fcount + __popc(m & below)) & (QRING - 1)] = idx;
@@ -218,16 +257,19 @@ ao_flux_queue_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_co
     int it = 0;
     Point s;
     if (have) {
-      if (lane < nd) {
+      const bool fresh = lane >= nd;
+      FT st[NS];
+      if (!fresh) {
         const int slot = (dhead + lane) & (QRING - 1);
         idx = didx[slot];
         it = dit[slot];
-        s.ustar = du_[slot]; s.theta_star = dt_[slot]; s.q_star = dq_[slot];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) st[k] = d_st[warp][k][slot];
       } else {
         idx = fidx[(fhead + lane - nd) & (QRING - 1)];
-        s.ustar = s.theta_star = s.q_star = (FT)1e-4;
       }
-      ao_prologue<CT, HS>(d, L, th, P, Q, T, idx, s);
+      Problem::prologue(p, idx, s, fresh);
+      if (!fresh) Problem::set_state(s, st);
     }
     dhead = (dhead + nd) & (QRING - 1); dcount -= nd;
     fhead = (fhead + nf) & (QRING - 1); fcount -= nf;
@@ -237,9 +279,7 @@ ao_flux_queue_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_co
     bool done = !have;
     for (;;) {
       if (!done) {
-        const FT pu = s.ustar, pt = s.theta_star, pq = s.q_star;
-        q_iterate(P, Q, T, tab, s);
-        const FT drift = m_abs(s.ustar - pu) + m_abs(s.theta_star - pt) + m_abs(s.q_star - pq);
+        const FT drift = Problem::trip(p, tab, s, it);
         ++it;
         done = (drift < tol) || (it >= maxiter);
       }
@@ -251,13 +291,13 @@ ao_flux_queue_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_co
       const int pos = (dhead + dcount + __popc(dm & below)) & (QRING - 1);
       didx[pos] = idx;
       dit[pos] = it;
-      du_[pos] = s.ustar; dt_[pos] = s.theta_star; dq_[pos] = s.q_star;
+      FT st[NS];
+      Problem::get_state(s, st);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) d_st[warp][k][pos] = st[k];
     }
     dcount += __popc(dm);
-    if (have && done) {
-      const bool not_water = (solve_inactive && d.inactive) ? (d.inactive[idx] != 0) : false;
-      ao_write_outputs<FT, CT>(d, L, th, idx, s.ustar, s.theta_star, s.q_star, not_water, it);
-    }
+    if (have && done) Problem::finish(p, idx, s, it);
     __syncwarp();
   }
   // the last CTA out re-arms the counters for the next launch that uses this slot

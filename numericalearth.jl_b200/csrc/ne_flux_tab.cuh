@@ -19,7 +19,7 @@ struct TabParams {
   double cbrt_floor;     // (gmin/β)³/8: below it β·cbrt(x) < gmin, so the clamp cannot change U_G
   double log_hd;         // log(surface_layer_height − d) when the height is a scalar (set per launch)
   int32_t same_exp;      // ψ_m and ψ_s stable branches share exp(−min(ζmax, A⁺ζ))
-  int32_t pad_;
+  int32_t general_psi;   // tables fitted to non-Edson stability functions: outside the table → generic closed forms
 };
 
 // ---- host: Chebyshev interpolation → monomials in w ∈ [−1, 1] (long double) -------------------------
@@ -63,6 +63,52 @@ inline long double psi_s_stable_ld(const double* p, long double z) {
 
 // Fills tab[TAB_SIZE] and T; returns the max error of the ψ polynomials (double evaluation vs the
 // long-double closed forms, relative to max(1, |ψ|)) over all intervals.
+// ---- every stability-function kind in long double (host; follows stability_fn<double, double>, ne_physics.cuh) ----
+inline long double psi_fn_ld(const NeStabilityFn& f, long double z) {
+  const double* p = f.p;
+  switch (f.kind) {
+    case NE_PSI_ZERO: return 0;
+    case NE_PSI_EDSON_MOMENTUM: return z < 0 ? psi_m_unstable_ld(p, z) : psi_m_stable_ld(p, z);
+    case NE_PSI_EDSON_SCALAR: return z < 0 ? psi_s_unstable_ld(p, z) : psi_s_stable_ld(p, z);
+    case NE_PSI_SHEBA_MOMENTUM: {   // similarity_theory_turbulent_fluxes.jl:643-657
+      const long double a = p[0], b = p[1], zp = fmaxl(0, z);
+      const long double zz = cbrtl(1 + zp), B = cbrtl((1 - b) / b), rt3 = 1.7320508075688772;
+      const long double P1 = -3 * a * (zz - 1) / b;
+      const long double P2 = a * B / (2 * b) *
+          (2 * logl((zz + B) / (1 + B)) - logl((zz * zz - B * zz + B * B) / (1 - B + B * B)) +
+           2 * rt3 * (atanl((2 * zz - B) / (rt3 * B)) - atanl((2 - B) / (rt3 * B))));
+      return P1 + P2;
+    }
+    case NE_PSI_SHEBA_SCALAR: {     // :665-677
+      const long double a = p[0], b = p[1], c = p[2], B = sqrtl(c * c - 4), zp = fmaxl(0, z);
+      const long double P1 = -b / 2 * logl(1 + c * zp + zp * zp);
+      const long double P2 = (b * c / (2 * B) - a / B) * (logl((2 * zp + c - B) / (2 * zp + c + B)) - logl((c - B) / (c + B)));
+      return P1 + P2;
+    }
+    case NE_PSI_PAULSON_MOMENTUM: { // :688-699
+      const long double a = p[0], b = p[1], zm = fminl(0, z), zz = sqrtl(sqrtl(1 - a * zm));
+      return 2 * logl((1 + zz) / 2) + logl((1 + zz * zz) / 2) - 2 * atanl(zz) + b;
+    }
+    case NE_PSI_PAULSON_SCALAR: {   // :705-710
+      const long double a = p[0], zm = fminl(0, z), zz = sqrtl(sqrtl(1 - a * zm));
+      return 2 * logl((1 + zz * zz) / 2);
+    }
+    case NE_PSI_LINEAR_STABLE: {    // :747-752
+      const long double c = p[0], zmax = p[1], zp = fmaxl(0, z);
+      return -c * fminl(zp, zmax);
+    }
+  }
+  return NAN;
+}
+inline long double psi_profile_ld(const NeStabilityProfile& s, long double z) {   // SplitStabilityFunction :720-725
+  if (!s.split) return psi_fn_ld(s.a, z);
+  return z > 0 ? psi_fn_ld(s.a, z) : psi_fn_ld(s.b, z);
+}
+inline bool psi_is_plain_edson(const NeFluxFormulation& f) {
+  return !f.psi_momentum.split && f.psi_momentum.a.kind == NE_PSI_EDSON_MOMENTUM &&
+         !f.psi_temperature.split && f.psi_temperature.a.kind == NE_PSI_EDSON_SCALAR;
+}
+
 // f32: tables for the Float32 model — the ψ parameters are the Float32-rounded ones (and √E⁻, C⁺D⁺ are Float32
 // operations), exactly what stability_fn<float, double> evaluates.
 inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabParams& T, bool f32 = false) {
@@ -89,6 +135,10 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
     pm[k] = f32 ? (double)(float)f.psi_momentum.a.p[k] : f.psi_momentum.a.p[k];
     ps[k] = f32 ? (double)(float)f.psi_temperature.a.p[k] : f.psi_temperature.a.p[k];
   }
+  // any other combination of the shipped stability functions (SHEBA / Paulson / linear-stable / split / zero):
+  // the same piecewise polynomials fitted to the general closed forms (Float64 models only)
+  const bool general = !psi_is_plain_edson(f);
+  if (general && f32) return 1.0;
   double worst = 0;
   for (int iv = 0; iv < PSI_NI; ++iv) {
     long double lo, hi;
@@ -104,8 +154,14 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
     rec[0] = (double)(1 / half);
     rec[1] = (double)(-mid / half);
     double cm[PSI_DEG + 1], cs[PSI_DEG + 1];
-    auto fmf = [&](long double az) { return stable ? psi_m_stable_ld(pm, az, f32) : psi_m_unstable_ld(pm, -az, f32); };
-    auto fsf = [&](long double az) { return stable ? psi_s_stable_ld(ps, az) : psi_s_unstable_ld(ps, -az, f32); };
+    auto fmf = [&](long double az) {
+      if (general) return psi_profile_ld(f.psi_momentum, stable ? az : -az);
+      return stable ? psi_m_stable_ld(pm, az, f32) : psi_m_unstable_ld(pm, -az, f32);
+    };
+    auto fsf = [&](long double az) {
+      if (general) return psi_profile_ld(f.psi_temperature, stable ? az : -az);
+      return stable ? psi_s_stable_ld(ps, az) : psi_s_unstable_ld(ps, -az, f32);
+    };
     cheb_fit_monomial(fmf, lo, hi, PSI_DEG, cm);
     cheb_fit_monomial(fsf, lo, hi, PSI_DEG, cs);
     for (int k = 0; k <= PSI_DEG; ++k) { rec[2 + 2 * k] = cm[k]; rec[2 + 2 * k + 1] = cs[k]; }
@@ -128,8 +184,14 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
     rec[0] = (double)(1 / half);
     rec[1] = (double)(-mid / half);
     double cm[TINY_DEG + 1], cs[TINY_DEG + 1];
-    auto fmf = [&](long double az) { return stable ? psi_m_stable_ld(pm, az, f32) : psi_m_unstable_ld(pm, -az, f32); };
-    auto fsf = [&](long double az) { return stable ? psi_s_stable_ld(ps, az) : psi_s_unstable_ld(ps, -az, f32); };
+    auto fmf = [&](long double az) {
+      if (general) return psi_profile_ld(f.psi_momentum, stable ? az : -az);
+      return stable ? psi_m_stable_ld(pm, az, f32) : psi_m_unstable_ld(pm, -az, f32);
+    };
+    auto fsf = [&](long double az) {
+      if (general) return psi_profile_ld(f.psi_temperature, stable ? az : -az);
+      return stable ? psi_s_stable_ld(ps, az) : psi_s_unstable_ld(ps, -az, f32);
+    };
     cheb_fit_monomial(fmf, lo, hi, TINY_DEG, cm);
     cheb_fit_monomial(fsf, lo, hi, TINY_DEG, cs);
     for (int k = 0; k <= TINY_DEG; ++k) { rec[2 + 2 * k] = cm[k]; rec[2 + 2 * k + 1] = cs[k]; }
@@ -146,7 +208,7 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
   const double ratio = g.minimum_gustiness / g.gustiness_parameter;
   T.cbrt_floor = ratio * ratio * ratio / 8;
   T.same_exp = (pm[0] == ps[0] && pm[1] == ps[1]);
-  T.pad_ = 0;
+  T.general_psi = general ? 1 : 0;
   T.log_hd = 0;
   return worst;
 }
@@ -179,30 +241,35 @@ __device__ __forceinline__ void psi_stable_pair(const FastParams& P, const TabPa
 
 // closed forms outside the table: stable side with the custom exp, far unstable side through libdevice.
 // Out of line and returning by value, so the common path keeps ψ in registers.
-__device__ __noinline__ double2 psi_outside(const FastParams& P, const TabParams& T, double z) {
+// ff != nullptr: tables of a non-Edson pair — the generic closed forms of ne_physics.cuh.
+__device__ __noinline__ double2 psi_outside(const FastParams& P, const TabParams& T, const NeFluxFormulation* ff, double z) {
   double pm, ps;
-  if (z > 0) psi_stable_pair(P, T, z, pm, ps);
+  if (ff) {
+    pm = stability_profile<double, double>(ff->psi_momentum, z);
+    ps = stability_profile<double, double>(ff->psi_temperature, z);
+  } else if (z > 0) psi_stable_pair(P, T, z, pm, ps);
   else psi_far_unstable(P, z, pm, ps);
   return make_double2(pm, ps);
 }
 
 // ψ_m(ζ), ψ_s(ζ) at the same ζ
-__device__ __forceinline__ void tab_psi_pair(const FastParams& P, const TabParams& T, const double* tab, double z,
-                                             double& pm, double& ps) {
+__device__ __forceinline__ void tab_psi_pair(const FastParams& P, const TabParams& T, const NeFluxFormulation* ff,
+                                             const double* tab, double z, double& pm, double& ps) {
   bool outside;
   const int iv = fm::psi_interval(z, outside);
   if (!outside) {
     fm::psi_pair(tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(z), pm, ps);
   } else {
-    const double2 r = psi_outside(P, T, z);
+    const double2 r = psi_outside(P, T, ff, z);
     pm = r.x; ps = r.y;
   }
 }
 
 // out-of-line general lookup for the rare case where ψ(ℓ/L★) leaves the tiny-|ζ| records
-__device__ __noinline__ double2 tab_psi_pair_rare(const FastParams& P, const TabParams& T, const double* tab, double z) {
+__device__ __noinline__ double2 tab_psi_pair_rare(const FastParams& P, const TabParams& T, const NeFluxFormulation* ff,
+                                                  const double* tab, double z) {
   double pm, ps;
-  tab_psi_pair(P, T, tab, z, pm, ps);
+  tab_psi_pair(P, T, ff, tab, z, pm, ps);
   return make_double2(pm, ps);
 }
 
@@ -211,7 +278,7 @@ __device__ __noinline__ double2 tab_psi_pair_rare(const FastParams& P, const Tab
 //   u★ (as a double), ru = 1/u★, ℓu (already clipped), 1/L★, Δh = z − d and log Δh  →  χ_u, χ_s
 __device__ __forceinline__ void tab_core(const FastParams& P, const TabParams& T, const double* tab, double ustar,
                                          double ru, double lu, double Linv, double hd, double log_hd,
-                                         double& chi_u, double& chi_s) {
+                                         double& chi_u, double& chi_s, const NeFluxFormulation* ff = nullptr) {
   using fm::dmax;
   (void)ru;
   const double log_lu = fm::log_pos(tab, T.mc, lu);
@@ -226,14 +293,14 @@ __device__ __forceinline__ void tab_core(const FastParams& P, const TabParams& T
   const double dh = lifted ? 2.0 * lu : hd;
   const double log_dh = lifted ? T.mc.ln2 + log_lu : log_hd;
   double pm_h, ps_h, pm_l, ps_l;
-  tab_psi_pair(P, T, tab, mul_(dh, Linv), pm_h, ps_h);
+  tab_psi_pair(P, T, ff, tab, mul_(dh, Linv), pm_h, ps_h);
   // ψ(ℓ/L★): |ℓ/L★| < 2^-12 except in the first trips from the 1e-4 initial guess
   const double zu = mul_(lu, Linv), zs = mul_(ls, Linv);
   if (fm::psi_is_tiny(zu) && fm::psi_is_tiny(zs)) {
     fm::psi_tiny_pair(tab + fm::TAB_TINY + (Linv < 0 ? 0 : fm::TINY_REC), fabs(zu), fabs(zs), pm_l, ps_l);
   } else {
-    pm_l = tab_psi_pair_rare(P, T, tab, zu).x;
-    ps_l = tab_psi_pair_rare(P, T, tab, zs).y;
+    pm_l = tab_psi_pair_rare(P, T, ff, tab, zu).x;
+    ps_l = tab_psi_pair_rare(P, T, ff, tab, zs).y;
   }
   const double Pi_u = (log_dh - log_lu) - pm_h + pm_l;
   const double Pi_s = (log_dh - log_ls) - ps_h + ps_l;
@@ -246,7 +313,8 @@ __device__ __forceinline__ void tab_core(const FastParams& P, const TabParams& T
   chi_s = fm::fma_(fm::fma_(-Pi_s, chi_s, P.kappa), rs_, chi_s);
 }
 
-__device__ __forceinline__ void tab_iteration(const FastParams& P, const TabParams& T, const double* tab, FastPoint& s) {
+__device__ __forceinline__ void tab_iteration(const FastParams& P, const TabParams& T, const double* tab, FastPoint& s,
+                                              const NeFluxFormulation* ff = nullptr) {
   using fm::dmax;
   using fm::dmin;
   using fm::fma_;
@@ -260,7 +328,7 @@ __device__ __forceinline__ void tab_iteration(const FastParams& P, const TabPara
   const double lu = dmin(fma_(mul_(P.a1, s.ustar), s.ustar, mul_(P.a2, ru)), P.lmax);
   const double Linv = mul_(mul_(mul_(P.kappa, bstar), ru), ru);   // 1/L★ (0 when b★ == 0, i.e. L★ = Inf)
   double chi_u, chi_s;
-  tab_core(P, T, tab, s.ustar, ru, lu, Linv, s.hd, s.log_hd, chi_u, chi_s);
+  tab_core(P, T, tab, s.ustar, ru, lu, Linv, s.hd, s.log_hd, chi_u, chi_s, ff);
   s.ustar = mul_(chi_u, U);
   s.theta_star = mul_(chi_s, s.dtheta);
   s.q_star = mul_(chi_s, s.dq);

@@ -40,3 +40,11 @@ def test_psi_tables_reproduce_the_closed_forms(report):
     assert report["psi_dense_err"] <= 1e-15
     assert report["psi_tiny_abs"] <= 1e-15
     assert report["interval_logic_ok"] == 1
+
+
+def test_general_psi_tables_sea_ice_and_large_yeager_pairs(report):
+    """The same piecewise polynomials fitted to Split(SHEBA, Paulson) (the atmosphere-sea-ice default,
+    similarity_theory_turbulent_fluxes.jl:779-789) and Split(LinearStable, Paulson) (:766-771)."""
+    assert report["psi_seaice_general"] == 1
+    assert report["psi_seaice_fit_err"] <= 1e-15 and report["psi_seaice_dense_err"] <= 1e-15
+    assert report["psi_ly_fit_err"] <= 1e-15 and report["psi_ly_dense_err"] <= 1e-15

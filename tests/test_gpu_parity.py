@@ -229,6 +229,39 @@ def test_ocean_sea_ice_model_step(oracle_lib, cuda_backend, cuda_lib, asi_temper
 
 
 @pytest.mark.parametrize("atm_FT", ["f64", "f32"])
+def test_sea_ice_work_queue_kernel_against_generic_kernel(cuda_backend, cuda_lib, monkeypatch, atm_FT):
+    """Default a-si tree at 1/4 degree: the work-queue kernel with the tabulated Split(SHEBA, Paulson) functions
+    against the generic kernel (libdevice closed forms).  Converged points to 1e-10, same trip counts."""
+    dev = synthetic.build_case("C2", cuda_backend, FT="f64", atm_FT=atm_FT, sea_ice=True, with_iterations=True)
+    dev.initialize()
+    dev.interpolate_state(T_STEP)
+    g = dev.grid
+    Ts0 = dev.sea_ice_state.top_temperature.clone()
+
+    def run():
+        dev.sea_ice_state.top_temperature.copy_(Ts0)   # READ-MODIFY-WRITE input
+        dev.compute_atmosphere_sea_ice_fluxes()
+        cuda_backend.synchronize()
+        out = {n: g.interior(cuda_backend.to_numpy(getattr(dev.asi_fluxes, n))).copy() for n in dev.asi_fluxes.names()}
+        out["Ts"] = g.interior(cuda_backend.to_numpy(dev.sea_ice_state.top_temperature)).copy()
+        return out, g.interior(cuda_backend.to_numpy(dev.asi_iterations)).copy()
+
+    fast, fit = run()
+    monkeypatch.setenv("NE_B200_FORCE_GENERIC", "1")
+    gen, git = run()
+    monkeypatch.delenv("NE_B200_FORCE_GENERIC")
+    assert (fit > 0).sum() > 10000 and ((fit > 0) == (git > 0)).all()
+    assert float((fit != git).mean()) <= 1e-3, float((fit != git).mean())
+    conv = (git < 100) & (fit < 100)
+    for n in fast:
+        a, b = fast[n], gen[n]
+        assert np.isfinite(a).all(), n
+        s = float(np.abs(b).max()) or 1.0
+        assert float(np.abs(a - b)[conv].max()) / s <= F64_TOL, f"{n}: {float(np.abs(a - b)[conv].max()) / s}"
+        assert float(np.abs(a - b).max()) / s <= 1e-3, f"{n} (limit-cycle points): {float(np.abs(a - b).max()) / s}"
+
+
+@pytest.mark.parametrize("atm_FT", ["f64", "f32"])
 @pytest.mark.parametrize("single_pass", [False, True])
 def test_fused_interface_step_matches_unfused(oracle_lib, cuda_backend, cuda_lib, atm_FT, single_pass, monkeypatch):
     """One C-ABI call (single-pass interpolation + solve kernel, then assembly and radiation) against the

@@ -13,10 +13,67 @@ static void default_formulation(NeFluxFormulation& f) {
   std::memset(&f, 0, sizeof(f));
   double m[11] = {50, 0.35, 0.7, 0.75, 5 / 0.35, 15, 2, 3.141592653589793 / 2, 10.15, 3, 3.141592653589793 / std::sqrt(3.0)};
   double s[12] = {50, 0.35, 2.0 / 3, 1.5, 14.28, 8.525, 15, 2, 0, 34.15, 3, 3.141592653589793 / std::sqrt(3.0)};
+  f.psi_momentum.a.kind = NE_PSI_EDSON_MOMENTUM;
+  f.psi_temperature.a.kind = f.psi_water_vapor.a.kind = NE_PSI_EDSON_SCALAR;
   for (int k = 0; k < 11; ++k) f.psi_momentum.a.p[k] = m[k];
   for (int k = 0; k < 12; ++k) { f.psi_temperature.a.p[k] = s[k]; f.psi_water_vapor.a.p[k] = s[k]; }
   f.subgrid_velocities.gustiness_parameter = 1.2;
   f.subgrid_velocities.minimum_gustiness = 0.01;
+}
+
+// atmosphere_sea_ice_stability_functions (similarity_theory_turbulent_fluxes.jl:779-789): Split(SHEBA, Paulson)
+static void sea_ice_formulation(NeFluxFormulation& f) {
+  default_formulation(f);
+  auto split = [](NeStabilityProfile& s, int stable_kind, const double* ps, int np, int unstable_kind, const double* pu, int nu) {
+    std::memset(&s, 0, sizeof(s));
+    s.split = 1;
+    s.a.kind = stable_kind;
+    for (int k = 0; k < np; ++k) s.a.p[k] = ps[k];
+    s.b.kind = unstable_kind;
+    for (int k = 0; k < nu; ++k) s.b.p[k] = pu[k];
+  };
+  const double sm[2] = {6.5, 1.3}, ss[3] = {5.0, 5.0, 3.0}, pm[2] = {16.0, 3.141592653589793 / 2}, pp[1] = {16.0};
+  split(f.psi_momentum, NE_PSI_SHEBA_MOMENTUM, sm, 2, NE_PSI_PAULSON_MOMENTUM, pm, 2);
+  split(f.psi_temperature, NE_PSI_SHEBA_SCALAR, ss, 3, NE_PSI_PAULSON_SCALAR, pp, 1);
+  f.psi_water_vapor = f.psi_temperature;
+}
+// large_yeager_stability_functions (:766-771): Split(LinearStable, Paulson)
+static void large_yeager_formulation(NeFluxFormulation& f) {
+  sea_ice_formulation(f);
+  const double ls[2] = {5.0, 10.0};
+  for (NeStabilityProfile* s : {&f.psi_momentum, &f.psi_temperature, &f.psi_water_vapor}) {
+    std::memset(&s->a, 0, sizeof(s->a));
+    s->a.kind = NE_PSI_LINEAR_STABLE;
+    s->a.p[0] = ls[0]; s->a.p[1] = ls[1];
+  }
+}
+
+// dense check of a general (non-Edson) table against psi_profile_ld, both sides, relative to max(1, |ψ|)
+static double dense_general(const NeFluxFormulation& f, const double* tab, std::mt19937_64& rng) {
+  std::uniform_real_distribution<double> u(0, 1);
+  double worst = 0;
+  for (int i = 0; i < 200000; ++i) {
+    const double az = std::exp(std::log(1e-9) + u(rng) * (std::log(127.99) - std::log(1e-9)));
+    for (int side = 0; side < 2; ++side) {
+      const double z = side ? az : -az;
+      bool outside;
+      const int iv = fm::psi_interval(z, outside);
+      if (outside) return 1e300;
+      double m, s;
+      fm::psi_pair(tab + fm::TAB_PSI + iv * fm::PSI_REC, az, m, s);
+      const long double tm = psi_profile_ld(f.psi_momentum, z), ts = psi_profile_ld(f.psi_temperature, z);
+      const double em = (double)(fabsl((long double)m - tm) / fmaxl(1, fabsl(tm)));
+      const double es = (double)(fabsl((long double)s - ts) / fmaxl(1, fabsl(ts)));
+      if (!(em <= worst)) worst = em;
+      if (!(es <= worst)) worst = es;
+      if (az < std::ldexp(1.0, fm::TINY_EXP)) {
+        fm::psi_tiny_pair(tab + fm::TAB_TINY + side * fm::TINY_REC, az, az, m, s);
+        const double e2 = (double)fmaxl(fabsl((long double)m - tm), fabsl((long double)s - ts));
+        if (!(e2 <= worst)) worst = e2;
+      }
+    }
+  }
+  return worst;
 }
 
 template <class F, class G>
@@ -112,7 +169,16 @@ int main() {
       if (!(es <= e_tiny)) e_tiny = es;
     }
   }
-  printf("{\"rcp_ulp\": %.3f, \"div_ulp\": %.3f, \"sqrt_ulp\": %.3f, \"cbrt_ulp\": %.3f, \"cbrt_wide_ulp\": %.3f, "
+  NeFluxFormulation fi, fl;
+  sea_ice_formulation(fi);
+  large_yeager_formulation(fl);
+  static double tab_i[fm::TAB_SIZE], tab_l[fm::TAB_SIZE];
+  TabParams Ti, Tl;
+  const double fit_i = build_solver_tables(fi, tab_i, Ti), fit_l = build_solver_tables(fl, tab_l, Tl);
+  const double dense_i = dense_general(fi, tab_i, rng), dense_l = dense_general(fl, tab_l, rng);
+  printf("{\"psi_seaice_fit_err\": %.3e, \"psi_seaice_dense_err\": %.3e, \"psi_seaice_general\": %d, "
+         "\"psi_ly_fit_err\": %.3e, \"psi_ly_dense_err\": %.3e, ", fit_i, dense_i, Ti.general_psi, fit_l, dense_l);
+  printf("\"rcp_ulp\": %.3f, \"div_ulp\": %.3f, \"sqrt_ulp\": %.3f, \"cbrt_ulp\": %.3f, \"cbrt_wide_ulp\": %.3f, "
          "\"log_ulp_small\": %.3f, \"log_ulp_large\": %.3f, \"log_abs_near1_ulp1\": %.3f, \"exp_ulp\": %.3f, \"exp_ulp_mid\": %.3f, "
          "\"psi_fit_err\": %.3e, \"psi_dense_err\": %.3e, \"psi_tiny_abs\": %.3e, \"interval_logic_ok\": %d, \"cbrt_floor\": %.6e, \"same_exp\": %d}\n",
          e_rcp, e_div, e_sqrt, e_cbrt, e_cbrt2, e_log, e_log_hi, e_log_abs, e_exp, e_exp2, fit, e_psi, e_tiny, iv_ok, T.cbrt_floor, T.same_exp);

@@ -45,6 +45,23 @@ def main():
         torch.cuda.synchronize()
         out[name] = e0.elapsed_time(e1) / 10
         print(cfg, FT, name, f"{out[name]:.3f} ms", flush=True)
+    # the same phases in update_state order, one event after each call (device time) + host wall time of the sequence
+    import time as _t
+    seq = ["interpolate_state", "atmosphere_ocean_fluxes", "atmosphere_sea_ice_fluxes", "sea_ice_ocean_fluxes",
+           "update_net_fluxes", "apply_air_sea_radiative_fluxes", "apply_air_sea_ice_radiative_fluxes"]
+    for rep in range(3):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(seq) + 1)]
+        torch.cuda.synchronize()
+        w0 = _t.perf_counter()
+        ev[0].record()
+        for k, name in enumerate(seq):
+            phases[name]()
+            ev[k + 1].record()
+        w1 = _t.perf_counter()
+        torch.cuda.synchronize()
+        w2 = _t.perf_counter()
+        print("sequence", rep, "host enqueue %.3f ms, until done %.3f ms;" % (1e3 * (w1 - w0), 1e3 * (w2 - w0)),
+              " ".join(f"{n.split('_')[0]}..={ev[k].elapsed_time(ev[k + 1]):.3f}" for k, n in enumerate(seq)), flush=True)
     it = backend.to_numpy(ci.asi_iterations) if getattr(ci, "asi_iterations", None) is not None else None
     if it is not None:
         act = it[it > 0]
