@@ -441,18 +441,6 @@ typedef struct NeElevationCorrectionDesc {
   double dry_air_gas_constant;   /* Parameters.R_d of the atmosphere's thermodynamics (:71) */
 } NeElevationCorrectionDesc;
 
-/* ---- fused interface step: interpolation -> a–o solve -> assembly -> radiation in ONE pass
- * (update_state! phases 1-4 for an OceanOnlyModel,
- *  src/EarthSystemModels/time_step_earth_system_model.jl:38-83).  Intermediate atmosphere
- * state arrays in `ao` may be NULL: they are then never materialised in HBM. */
-typedef struct NeFusedStepDesc {
-  NeInterpDesc atmosphere;   /* 7 fields: u v T q p rain snow */
-  NeInterpDesc radiation;    /* 2 fields: SW LW (n_fields = 0 => radiation off) */
-  NeAtmosOceanDesc ao;
-  NeAssembleOceanDesc assemble;
-  NeApplyRadiationDesc apply_radiation;
-} NeFusedStepDesc;
-
 /* ---- diagnostics reduction (src/Diagnostics/interface_fluxes.jl:90-195; conservation sums) */
 #define NE_DIAG_MAX_FIELDS 16
 typedef struct NeDiagDesc {
@@ -466,6 +454,39 @@ typedef struct NeDiagDesc {
   int64_t n_blocks;          /* fixed block count => deterministic summation order */
   double* result;            /* device, n_fields doubles                           */
 } NeDiagDesc;
+
+/* ---- fused interface step: interpolation -> a–o solve -> assembly -> radiation in ONE pass
+ * (update_state! phases 1-4 for an OceanOnlyModel,
+ *  src/EarthSystemModels/time_step_earth_system_model.jl:38-83).  Intermediate atmosphere
+ * state arrays in `ao` may be NULL: they are then never materialised in HBM.  Phases 3-4 (+ the optional
+ * diagnostics sums) run as ONE kernel when assemble / apply_radiation / diag share a launch range and
+ * apply_radiation.heat_flux is assemble.JT. */
+typedef struct NeFusedStepDesc {
+  NeInterpDesc atmosphere;   /* 7 fields: u v T q p rain snow */
+  NeInterpDesc radiation;    /* 2 fields: SW LW (n_fields = 0 => radiation off) */
+  NeAtmosOceanDesc ao;
+  NeAssembleOceanDesc assemble;
+  NeApplyRadiationDesc apply_radiation;
+  /* optional (n_fields = 0: off): area-weighted sums of `diag.fields` as ne_diag_reduce computes them, accumulated
+   * by the same kernel that assembles the net fluxes and applies the radiation (one pass over the exchange grid
+   * instead of three; same point -> block assignment, so the sums equal ne_diag_reduce's bit for bit).            */
+  NeDiagDesc diag;
+} NeFusedStepDesc;
+
+/* ---- host-buffer step (ne_pipeline.cu): the ocean surface state arrives in pinned host memory every
+ * coupled step; chunked H2D copies on the pipeline's own stream overlap the band-restricted kernels. */
+#define NE_HOST_MAX_FIELDS 8
+typedef struct NeHostField {
+  const void* host;          /* pinned host memory, exchange-layout parent */
+  void* device;              /* the device array the kernels read           */
+} NeHostField;
+typedef struct NeHostStepDesc {
+  NeFusedStepDesc step;      /* full launch ranges; the pipeline restricts them per band     */
+  int32_t n_fields;          /* ocean surface fields copied every step (T, S, u, v)           */
+  int32_t n_chunks;          /* latitude chunks (<= the handle's capacity)                    */
+  NeHostField fields[NE_HOST_MAX_FIELDS];
+  int64_t row_bytes;         /* (nx + 2 hx) * sizeof(exchange element)                        */
+} NeHostStepDesc;
 
 /* ---- entry points ---------------------------------------------------------------------- */
 int ne_version(void);
@@ -518,6 +539,14 @@ int ne_diag_reduce_f32(const NeDiagDesc*, void* stream);
 int ne_memcpy_h2d(void* dst_device, const void* src_host, uint64_t bytes, void* stream);
 int ne_memcpy_d2h(void* dst_host, const void* src_device, uint64_t bytes, void* stream);
 int ne_stream_synchronize(void* stream);
+
+/* Host-buffer interface step: create once per device (owns a non-blocking copy stream and max_chunks + 1
+ * events), then one call per coupled step on the caller's compute stream; everything is enqueued, nothing
+ * synchronises.  Results equal the unchunked ne_fused_interface_step bit for bit. */
+int ne_host_pipeline_create(void** handle, int32_t max_chunks);
+int ne_host_pipeline_destroy(void* handle);
+int ne_host_pipelined_step_f64(void* handle, const NeHostStepDesc*, void* stream);
+int ne_host_pipelined_step_f32(void* handle, const NeHostStepDesc*, void* stream);
 
 /* FP64 DFMA-issue microbenchmark used to measure the FP64 roofline denominator
  * (MEASURED_PEAKS.json has no FP64 figure).  Returns achieved TFLOP/s in *tflops. */

@@ -232,9 +232,14 @@ class NeApplyRadiationDesc(C.Structure):
                 ("upwelling_longwave", vp), ("downwelling_longwave", vp), ("downwelling_shortwave", vp)]
 
 
+class NeDiagDesc(C.Structure):
+    _fields_ = [("grid", NeExchangeGrid), ("n_fields", i32), ("pad_", i32), ("fields", vp * NE_DIAG_MAX_FIELDS),
+                ("area", vp), ("inactive", vp), ("partial", vp), ("n_blocks", i64), ("result", vp)]
+
+
 class NeFusedStepDesc(C.Structure):
     _fields_ = [("atmosphere", NeInterpDesc), ("radiation", NeInterpDesc), ("ao", NeAtmosOceanDesc),
-                ("assemble", NeAssembleOceanDesc), ("apply_radiation", NeApplyRadiationDesc)]
+                ("assemble", NeAssembleOceanDesc), ("apply_radiation", NeApplyRadiationDesc), ("diag", NeDiagDesc)]
 
 
 class NeElevationCorrectionDesc(C.Structure):
@@ -242,9 +247,16 @@ class NeElevationCorrectionDesc(C.Structure):
                 ("gravitational_acceleration", f64), ("dry_air_gas_constant", f64)]
 
 
-class NeDiagDesc(C.Structure):
-    _fields_ = [("grid", NeExchangeGrid), ("n_fields", i32), ("pad_", i32), ("fields", vp * NE_DIAG_MAX_FIELDS),
-                ("area", vp), ("inactive", vp), ("partial", vp), ("n_blocks", i64), ("result", vp)]
+NE_HOST_MAX_FIELDS = 8
+
+
+class NeHostField(C.Structure):
+    _fields_ = [("host", vp), ("device", vp)]
+
+
+class NeHostStepDesc(C.Structure):
+    _fields_ = [("step", NeFusedStepDesc), ("n_fields", i32), ("n_chunks", i32), ("fields", NeHostField * NE_HOST_MAX_FIELDS),
+                ("row_bytes", i64)]
 
 
 STRUCTS = {c.__name__: c for c in [
@@ -252,7 +264,7 @@ STRUCTS = {c.__name__: c for c in [
     NeStabilityProfile, NeRoughnessLength, NeSubgridVelocity, NeStopCriteria, NePolynomialDrag, NeTransferCoefficient,
     NeLargeYeager, NeFluxFormulation, NeInterfaceProperties, NeMediumProperties, NeSeaIceAlbedo, NeTabulatedAlbedo, NeSurfaceRadiation, NeAtmosOceanDesc,
     NeAtmosSeaIceDesc, NeSeaIceOceanDesc, NeSeaIceOceanStressDesc, NeAssembleOceanDesc, NeAssembleSeaIceDesc,
-    NeApplyRadiationDesc, NeElevationCorrectionDesc, NeFusedStepDesc, NeDiagDesc]}
+    NeApplyRadiationDesc, NeElevationCorrectionDesc, NeFusedStepDesc, NeDiagDesc, NeHostField, NeHostStepDesc]}
 
 # entry points declared in include/ne_b200.h: name -> descriptor struct (None: special signature)
 DESC_ENTRY_POINTS = {
@@ -271,7 +283,8 @@ DESC_ENTRY_POINTS = {
     "ne_diag_reduce": NeDiagDesc,
 }
 OTHER_ENTRY_POINTS = ["ne_version", "ne_last_error", "ne_device_count", "ne_memcpy_h2d", "ne_memcpy_d2h",
-                      "ne_stream_synchronize", "ne_measure_fp64_peak", "ne_struct_size"]
+                      "ne_stream_synchronize", "ne_measure_fp64_peak", "ne_struct_size", "ne_host_pipeline_create",
+                      "ne_host_pipeline_destroy", "ne_host_pipelined_step_f64", "ne_host_pipelined_step_f32"]
 
 
 def all_entry_points():

@@ -16,6 +16,8 @@
 //
 // All are one-thread-per-point, consecutive threads along x: every load/store of a warp is one
 // fully-used 128 B (f32) / 256 B (f64) segment; constants arrive through NeSlot without a load.
+#include <cstdlib>
+
 #include "ne_physics.cuh"
 
 namespace ne {
@@ -120,10 +122,9 @@ sea_ice_ocean_stress_kernel(const __grid_constant__ NeSeaIceOceanStressDesc d, c
   ((FT*)d.y_momentum)[idx] = rho * Cd * m_sqrt(sq(du4) + sq(dv)) * dv;
 }
 
+// one point of _assemble_net_ocean_fluxes! (Oceans/assemble_net_ocean_fluxes.jl:74-153)
 template <class FT>
-__global__ void __launch_bounds__(256)
-assemble_ocean_kernel(const __grid_constant__ NeAssembleOceanDesc d, const __grid_constant__ Layout L) {
-  NE_POINT_INDEX();
+__device__ __forceinline__ void assemble_ocean_point(const NeAssembleOceanDesc& d, const Layout& L, int64_t idx) {
   const FT rho_inv = 1 / (FT)d.ocean.reference_density;
   const FT c_inv = 1 / (FT)d.ocean.heat_capacity;
   const int64_t sx = L.sx;
@@ -159,6 +160,13 @@ assemble_ocean_kernel(const __grid_constant__ NeAssembleOceanDesc d, const __gri
 
 template <class FT>
 __global__ void __launch_bounds__(256)
+assemble_ocean_kernel(const __grid_constant__ NeAssembleOceanDesc d, const __grid_constant__ Layout L) {
+  NE_POINT_INDEX();
+  assemble_ocean_point<FT>(d, L, idx);
+}
+
+template <class FT>
+__global__ void __launch_bounds__(256)
 assemble_sea_ice_kernel(const __grid_constant__ NeAssembleSeaIceDesc d, const __grid_constant__ Layout L) {
   NE_POINT_INDEX();
   FT conc = slot_at<FT>(d.concentration, idx);
@@ -175,10 +183,10 @@ assemble_sea_ice_kernel(const __grid_constant__ NeAssembleSeaIceDesc d, const __
   ((FT*)d.bottom_heat)[idx] = inactive ? (FT)0 : Qf + Qi;
 }
 
+// one point of _apply_air_sea[_ice]_radiative_fluxes! (Radiations/apply_air_sea_radiative_fluxes.jl:62-111,
+// apply_air_sea_ice_radiative_fluxes.jl:55-90)
 template <class FT>
-__global__ void __launch_bounds__(256)
-apply_radiation_kernel(const __grid_constant__ NeApplyRadiationDesc d, const __grid_constant__ Layout L) {
-  NE_POINT_INDEX();
+__device__ __forceinline__ void apply_radiation_point(const NeApplyRadiationDesc& d, const Layout& L, int64_t idx, int32_t j) {
   FT conc = slot_at<FT>(d.concentration, idx);
   FT Ts = __ldg((const FT*)d.surface_temperature + idx);
   if (d.medium.temperature_units == NE_DEGREES_CELSIUS) Ts = Ts + (FT)273.15;
@@ -209,6 +217,13 @@ apply_radiation_kernel(const __grid_constant__ NeApplyRadiationDesc d, const __g
   ((FT*)d.downwelling_shortwave)[idx] = -tr;
 }
 
+template <class FT>
+__global__ void __launch_bounds__(256)
+apply_radiation_kernel(const __grid_constant__ NeApplyRadiationDesc d, const __grid_constant__ Layout L) {
+  NE_POINT_INDEX();
+  apply_radiation_point<FT>(d, L, idx, j);
+}
+
 // ---- ElevationCorrection: _correct_atmosphere_elevation! (atmosphere_state_correction.jl:133-146) -------
 template <class FT>
 __global__ void __launch_bounds__(256)
@@ -226,33 +241,9 @@ elevation_correction_kernel(const __grid_constant__ NeElevationCorrectionDesc d,
 }
 
 // ---- diagnostics: deterministic two-stage area-weighted sums (FP64 accumulation) ---------------------
-// NF: compile-time bound on the field count (4, 8 or 16) so the accumulators of unused slots cost no registers
-template <class FT, int NF>
-__global__ void __launch_bounds__(256)
-diag_partial_kernel(const __grid_constant__ NeDiagDesc d, const __grid_constant__ Layout L) {
-  __shared__ double sm[8][NF];
-  const int64_t n = (int64_t)L.ni * L.nj;
-  double acc[NF];
-#pragma unroll
-  for (int f = 0; f < NF; ++f) acc[f] = 0;
-  // fixed assignment of points to blocks/threads => run-to-run and rank-count independent order
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
-    const int32_t jj = (int32_t)(t / L.ni);
-    const int64_t idx = L.at(L.i_lo + (int32_t)(t - (int64_t)jj * L.ni), L.j_lo + jj);
-    const bool active = !(d.inactive && d.inactive[idx]);
-    // every load is issued unconditionally (predicated on the field count only), then masked: the loads of
-    // a point do not wait for its mask byte
-    const double w = d.area ? (double)__ldg((const FT*)d.area + idx) : 1.0;
-    double x[NF];
-#pragma unroll
-    for (int f = 0; f < NF; ++f) x[f] = f < d.n_fields ? (double)__ldg((const FT*)d.fields[f] + idx) : 0.0;
-    if (active) {
-#pragma unroll
-      for (int f = 0; f < NF; ++f)
-        if (f < d.n_fields) acc[f] += w * x[f];
-    }
-  }
+// block-level stage: warp shuffle tree, then thread f adds the 8 warp sums of field f in warp order
+template <int NF>
+__device__ __forceinline__ void diag_block_reduce(const NeDiagDesc& d, const double (&acc)[NF], double (&sm)[8][NF]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int f = 0; f < NF; ++f) {
@@ -269,6 +260,43 @@ diag_partial_kernel(const __grid_constant__ NeDiagDesc d, const __grid_constant_
   }
 }
 
+// the per-point part of the first stage (shared by diag_partial_kernel and post_solve_kernel: same arithmetic, same
+// point -> thread assignment, hence bit-identical sums)
+template <class FT, int NF>
+__device__ __forceinline__ void diag_accumulate(const NeDiagDesc& d, int64_t idx, double (&acc)[NF]) {
+  const bool active = !(d.inactive && d.inactive[idx]);
+  // every load is issued unconditionally (predicated on the field count only), then masked: the loads of
+  // a point do not wait for its mask byte
+  const double w = d.area ? (double)__ldg((const FT*)d.area + idx) : 1.0;
+  double x[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) x[f] = f < d.n_fields ? (double)__ldcg((const FT*)d.fields[f] + idx) : 0.0;
+  if (active) {
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+      if (f < d.n_fields) acc[f] += w * x[f];
+  }
+}
+
+// NF: compile-time bound on the field count (4, 8 or 16) so the accumulators of unused slots cost no registers
+template <class FT, int NF>
+__global__ void __launch_bounds__(256)
+diag_partial_kernel(const __grid_constant__ NeDiagDesc d, const __grid_constant__ Layout L) {
+  __shared__ double sm[8][NF];
+  const int64_t n = (int64_t)L.ni * L.nj;
+  double acc[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) acc[f] = 0;
+  // fixed assignment of points to blocks/threads => run-to-run and rank-count independent order
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    const int32_t jj = (int32_t)(t / L.ni);
+    const int64_t idx = L.at(L.i_lo + (int32_t)(t - (int64_t)jj * L.ni), L.j_lo + jj);
+    diag_accumulate<FT, NF>(d, idx, acc);
+  }
+  diag_block_reduce<NF>(d, acc, sm);
+}
+
 // one warp per field: lane l sums blocks l, l+32, … in order, then a fixed shuffle tree — the order depends
 // only on n_blocks, never on scheduling
 __global__ void __launch_bounds__(32 * NE_DIAG_MAX_FIELDS)
@@ -280,6 +308,32 @@ diag_final_kernel(const double* __restrict__ partial, int64_t n_blocks, int n_fi
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   if (lane == 0) result[f] = v;
+}
+
+// ---- phases 3-4 of update_state! in one pass: net ocean flux assembly, radiative flux application and (optionally)
+// the first stage of the diagnostics sums.  Grid-stride over the launch range with the diagnostics' fixed block
+// count, so a point is summed by the same thread, in the same order, as in diag_partial_kernel.  The fields the
+// diagnostics read were written (or read) by this very thread a few instructions earlier: they come from L1/L2,
+// not from HBM — the separate reduction pass over 7 fields x 58 MB (1/12 degree) disappears.
+template <class FT, int NF, bool RAD, bool DIAG, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+post_solve_kernel(const __grid_constant__ NeAssembleOceanDesc da, const __grid_constant__ NeApplyRadiationDesc dr,
+                  const __grid_constant__ NeDiagDesc dd, const __grid_constant__ Layout L) {
+  __shared__ double sm[8][NF];
+  const int64_t n = (int64_t)L.ni * L.nj;
+  double acc[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) acc[f] = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    const int32_t jj = (int32_t)(t / L.ni);
+    const int32_t j = L.j_lo + jj;
+    const int64_t idx = L.at(L.i_lo + (int32_t)(t - (int64_t)jj * L.ni), j);
+    assemble_ocean_point<FT>(da, L, idx);
+    if (RAD) apply_radiation_point<FT>(dr, L, idx, j);
+    if (DIAG) diag_accumulate<FT, NF>(dd, idx, acc);
+  }
+  if (DIAG) diag_block_reduce<NF>(dd, acc, sm);
 }
 
 template <class K, class D>
@@ -333,6 +387,64 @@ static int diag_entry(const NeDiagDesc* d, void* stream) {
   NE_CUDA_CHECK_LAUNCH("ne_diag_reduce(final)");
   return NE_OK;
 }
+
+static bool same_range(const NeExchangeGrid& a, const NeExchangeGrid& b) {
+  return a.nx == b.nx && a.ny == b.ny && a.hx == b.hx && a.hy == b.hy && a.i_lo == b.i_lo && a.i_hi == b.i_hi &&
+         a.j_lo == b.j_lo && a.j_hi == b.j_hi;
+}
+
+// Phases 3-4 (+ diagnostics) of the fused step as one kernel.  Returns NE_OK when enqueued, +1 when the descriptors
+// do not qualify (the caller then enqueues the component kernels), < 0 on error.
+template <class FT>
+static int post_solve(const NeFusedStepDesc* d, void* stream) {
+  const char* off = std::getenv("NE_B200_NO_POST_SOLVE_FUSION");
+  if (off && off[0] == '1') return 1;
+  const NeAssembleOceanDesc& a = d->assemble;
+  const NeApplyRadiationDesc& r = d->apply_radiation;
+  const NeDiagDesc& g = d->diag;
+  const bool rad = r.radiation.enabled != 0, diag = g.n_fields > 0;
+  if (!rad && !diag) return 1;
+  if (rad && (!same_range(a.grid, r.grid) || r.over_sea_ice || r.heat_flux != a.JT)) return 1;
+  if (diag && !same_range(a.grid, g.grid)) return 1;
+  NE_REQUIRE(a.tau_x && a.tau_y && a.JT && a.JS && a.Jw && a.JH, "assemble ocean: null output");
+  NE_REQUIRE(grid_ok(a.grid, 1, 0), "assemble ocean: launch range (+stencil) leaves the parent array");
+  if (rad) {
+    NE_REQUIRE(r.surface_temperature && r.heat_flux && r.upwelling_longwave && r.downwelling_longwave && r.downwelling_shortwave, "apply radiation: null array");
+    NE_REQUIRE(!r.two_color || r.two_color_surface_flux, "apply radiation: two_color without surface_flux array");
+  }
+  if (diag) {
+    NE_REQUIRE(g.n_fields <= NE_DIAG_MAX_FIELDS, "diag: n_fields out of range");
+    NE_REQUIRE(g.partial && g.result && g.n_blocks >= 1, "diag: null scratch/result");
+    for (int f = 0; f < g.n_fields; ++f) NE_REQUIRE(g.fields[f] != nullptr, "diag: null field");
+  }
+  Layout L = make_layout(a.grid);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = (int64_t)L.ni * L.nj;
+  const unsigned blocks = diag ? (unsigned)g.n_blocks : (unsigned)((n + 255) / 256);
+  const char* mb = std::getenv("NE_B200_POST_MINB");   // occupancy experiment knob
+  const int minb = mb ? std::atoi(mb) : 4;
+#define NE_POST(NF, RAD, DIAG)                                                                   \
+  do {                                                                                           \
+    if (minb == 2) post_solve_kernel<FT, NF, RAD, DIAG, 2><<<blocks, 256, 0, s>>>(a, r, g, L);      \
+    else if (minb == 3) post_solve_kernel<FT, NF, RAD, DIAG, 3><<<blocks, 256, 0, s>>>(a, r, g, L); \
+    else if (minb == 5) post_solve_kernel<FT, NF, RAD, DIAG, 5><<<blocks, 256, 0, s>>>(a, r, g, L); \
+    else post_solve_kernel<FT, NF, RAD, DIAG, 4><<<blocks, 256, 0, s>>>(a, r, g, L);                \
+  } while (0)
+  if (!diag) NE_POST(4, true, false);
+  else if (g.n_fields <= 4) { if (rad) NE_POST(4, true, true); else NE_POST(4, false, true); }
+  else if (g.n_fields <= 8) { if (rad) NE_POST(8, true, true); else NE_POST(8, false, true); }
+  else { if (rad) NE_POST(NE_DIAG_MAX_FIELDS, true, true); else NE_POST(NE_DIAG_MAX_FIELDS, false, true); }
+#undef NE_POST
+  NE_CUDA_CHECK_LAUNCH("ne_fused_interface_step(assembly+radiation+diagnostics)");
+  if (diag) {
+    diag_final_kernel<<<1, 32 * NE_DIAG_MAX_FIELDS, 0, s>>>(g.partial, g.n_blocks, g.n_fields, g.result);
+    NE_CUDA_CHECK_LAUNCH("ne_fused_interface_step(diagnostics final)");
+  }
+  return NE_OK;
+}
+
+int post_solve_f64(const NeFusedStepDesc* d, void* stream) { return post_solve<double>(d, stream); }
+int post_solve_f32(const NeFusedStepDesc* d, void* stream) { return post_solve<float>(d, stream); }
 
 }  // namespace ne
 

@@ -639,8 +639,13 @@ class ComponentInterfaces:
         self.apply_air_sea_radiative_fluxes()
         self.apply_air_sea_ice_radiative_fluxes()
 
-    def fused_step_desc(self, t) -> A.NeFusedStepDesc:
+    def fused_step_desc(self, t, diagnostics=None) -> A.NeFusedStepDesc:
+        """`diagnostics` (a sharding.FluxDiagnostics): its area-weighted sums are accumulated by the kernel that
+        assembles the net fluxes and applies the radiation; follow the call with diagnostics.all_reduce() when
+        world_size > 1."""
         d = A.NeFusedStepDesc()
+        if diagnostics is not None:
+            d.diag = diagnostics.desc
         d.atmosphere = self.atmosphere_interp_desc(t)
         if self.radiation is not None:
             d.radiation = self.radiation_interp_desc(t)
@@ -650,8 +655,9 @@ class ComponentInterfaces:
             d.apply_radiation = self.apply_radiation_desc(False)
         return d
 
-    def fused_interface_step(self, t):
-        """Interpolation -> a–o solve -> net ocean flux assembly -> radiation for an OceanOnlyModel, one C-ABI call."""
+    def fused_interface_step(self, t, diagnostics=None):
+        """Interpolation -> a–o solve -> net ocean flux assembly -> radiation (-> diagnostics sums) for an
+        OceanOnlyModel, one C-ABI call."""
         self.clock_time = t
         if self.atmosphere_correction is not None:   # phase 1.5 sits between the phases the fused call merges
             d, s, FT = self.fused_step_desc(t), self.backend.stream(), self.grid.FT
@@ -661,5 +667,9 @@ class ComponentInterfaces:
             self.lib.call("assemble_net_ocean_fluxes", FT, d.assemble, s)
             if self.radiation is not None:
                 self.lib.call("apply_radiative_fluxes", FT, d.apply_radiation, s)
+            if diagnostics is not None:
+                diagnostics.reduce()
             return
-        self.lib.call("fused_interface_step", self.grid.FT, self.fused_step_desc(t), self.backend.stream())
+        self.lib.call("fused_interface_step", self.grid.FT, self.fused_step_desc(t, diagnostics), self.backend.stream())
+        if diagnostics is not None:
+            diagnostics.all_reduce()

@@ -56,6 +56,12 @@ class Library:
             self.dll.ne_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
             self.dll.ne_stream_synchronize.argtypes = [C.c_void_p]
             self.dll.ne_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+            self.dll.ne_host_pipeline_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
+            self.dll.ne_host_pipeline_destroy.argtypes = [C.c_void_p]
+            for suffix in ("_f64", "_f32"):
+                fn = getattr(self.dll, "ne_host_pipelined_step" + suffix)
+                fn.restype = C.c_int
+                fn.argtypes = [C.c_void_p, C.POINTER(A.NeHostStepDesc), C.c_void_p]
 
     def last_error(self):
         if self.prefix != "ne_":

@@ -77,6 +77,11 @@ class FluxDiagnostics:
         """Enqueue the local reduction and (world_size > 1) the all-reduce; returns the device/host
         result array without synchronising."""
         self.ci.lib.call("diag_reduce", self.ci.grid.FT, self.desc, self.ci.backend.stream())
+        return self.all_reduce(group)
+
+    def all_reduce(self, group=None):
+        """The collective alone: for local sums already produced by the fused interface step
+        (NeFusedStepDesc.diag)."""
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

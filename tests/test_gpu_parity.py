@@ -347,7 +347,7 @@ def test_diagnostics_reduction_matches_numpy_and_is_deterministic(cuda_backend, 
         assert abs(r1[k] - ref) <= 1e-12 * scale, (k, r1[k], ref)
 
 
-@pytest.mark.parametrize("n_chunks", [1, 3, 8])
+@pytest.mark.parametrize("n_chunks", [1, 3, 8, 37])
 def test_host_pipelined_step_equals_update_state(cuda_backend, cuda_lib, n_chunks):
     """Ocean state in pinned host buffers, chunked H2D overlapped with the band-restricted kernels: every flux field is
     bit-identical to the plain device-resident update_state!."""
@@ -464,6 +464,33 @@ def test_float32_model_fast_path_against_generic_kernel_and_oracle(oracle_lib, c
     assert abs(float(fi[oi > 0].mean()) - float(oi[oi > 0].mean())) <= 0.5
     assert abs(float((fi == 100).mean()) - float((oi == 100).mean())) <= 0.005
     assert fi.max() <= 100
+
+
+@pytest.mark.parametrize("FT", ["f64", "f32"])
+def test_post_solve_kernel_equals_component_kernels_bitwise(cuda_backend, cuda_lib, monkeypatch, FT):
+    """Assembly + radiation + diagnostics partial sums in one kernel (NeFusedStepDesc.diag) against the three
+    component kernels: every output field and the diagnostics sums bit for bit."""
+    from numericalearth_jl_b200 import sharding
+    outs = []
+    for fused in (True, False):
+        if not fused:
+            monkeypatch.setenv("NE_B200_NO_POST_SOLVE_FUSION", "1")
+        dev = synthetic.build_case("C2", cuda_backend, FT=FT, atm_FT="f32")
+        dev.initialize()
+        f = dev.ao_fluxes
+        diag = sharding.FluxDiagnostics(dev, [f.latent_heat, f.sensible_heat, f.water_vapor, f.x_momentum, f.y_momentum,
+                                              dev.net_ocean.T, dev.net_ocean.eta])
+        dev.fused_interface_step(T_STEP, diagnostics=diag)
+        cuda_backend.synchronize()
+        o = {"diag": cuda_backend.to_numpy(diag.result).copy()}
+        for bag in ("net_ocean", "rad_fluxes_ocean"):
+            for n in getattr(dev, bag).names():
+                o[bag + "." + n] = cuda_backend.to_numpy(getattr(getattr(dev, bag), n)).copy()
+        outs.append(o)
+    monkeypatch.delenv("NE_B200_NO_POST_SOLVE_FUSION")
+    assert np.isfinite(outs[0]["diag"]).all() and (outs[0]["diag"] != 0).any()
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k], equal_nan=True), k
 
 
 def test_no_kernel_variant_raises(cuda_backend, cuda_lib):

@@ -31,7 +31,11 @@ def main():
     lib = ne_b200.get_library()
     ci = synthetic.build_case(cfg, backend, FT="f64", atm_FT="f32", with_iterations=False)
     ci.initialize()
-    d = ci.fused_step_desc(0.37 * 10800.0)
+    from numericalearth_jl_b200 import sharding
+    f = ci.ao_fluxes
+    diag = sharding.FluxDiagnostics(ci, [f.latent_heat, f.sensible_heat, f.water_vapor, f.x_momentum, f.y_momentum,
+                                         ci.net_ocean.T, ci.net_ocean.eta], n_blocks=int(os.environ.get("NE_DIAG_BLOCKS", "1184")))
+    d = ci.fused_step_desc(0.37 * 10800.0, diagnostics=diag)
     stream = backend.stream()
     out = []
     for env in settings:
@@ -45,6 +49,8 @@ def main():
         r["ao"] = timed(lambda: lib.call("atmosphere_ocean_fluxes", "f64", d.ao, stream))
         r["assemble"] = timed(lambda: lib.call("assemble_net_ocean_fluxes", "f64", d.assemble, stream))
         r["apply_rad"] = timed(lambda: lib.call("apply_radiative_fluxes", "f64", d.apply_radiation, stream))
+        r["diag"] = timed(lambda: lib.call("diag_reduce", "f64", diag.desc, stream))
+        r["post_solve(fused_step - interp_and_ao)"] = r["fused_step"] - r["interp_and_ao"]
         out.append(r)
         print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()}))
         for k in env:
