@@ -32,6 +32,17 @@ sys.path.insert(0, ROOT)
 if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NE_BENCH_KEEP_NCCL_DEBUG"):
     os.environ["NCCL_DEBUG"] = "WARN"
 
+# ... and whatever a library still writes to file descriptor 1 (NCCL prints its version banner there on some
+# boxes regardless) goes to stderr: the JSON line is written to a private duplicate of the original stdout
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(line + "\n")
+    _REAL_STDOUT.flush()
+
+
 import numpy as np  # noqa: E402
 
 import ne_b200  # noqa: E402,F401  (registers the package as numericalearth_jl_b200)
@@ -186,7 +197,7 @@ def reference_arm(args):
             "cpu_baseline": {"value": r["value"], "unit": "points/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "Julia is not installed: the reference arm is the C++/OpenMP oracle restating the reference algorithm"}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def workload_config(args, n):
@@ -375,7 +386,7 @@ def b200_arm(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
