@@ -107,6 +107,14 @@ typedef struct NeInterpDesc {
   void* potential;
   int32_t potential_from;
   double ocean_reference_density;
+  /* intrinsic_vector (interpolate_atmospheric_state.jl:123-126): on a rotated exchange grid (tripolar, cubed sphere)
+   * the interpolated vector (fields rotate_u, rotate_v) is turned into the grid's frame before it is stored:
+   * u' = u cos(theta) + v sin(theta), v' = -u sin(theta) + v cos(theta).  Exchange-layout arrays of the exchange
+   * element type holding the grid's rotation angle (Oceananigans rotation metrics, third party: the binding fills them
+   * once).  NULL => latitude-longitude exchange grid: the vector is stored as interpolated.                         */
+  const void* rotation_cos;
+  const void* rotation_sin;
+  int32_t rotate_u, rotate_v;
 } NeInterpDesc;
 
 /* Fractional indices of exchange nodes on a LatitudeLongitude source grid

@@ -60,7 +60,8 @@ class NeInterpDesc(C.Structure):
     _fields_ = [("grid", NeExchangeGrid), ("frac_i", vp), ("frac_j", vp), ("src_dtype", i32), ("n_fields", i32),
                 ("src_nx", i64), ("src_ny", i64), ("src_hx", i64), ("src_hy", i64), ("src_nt", i64),
                 ("time", NeTimeInterp), ("n_summands", i32 * 9), ("series", (NeTimeSeries * NE_MAX_SUMMANDS) * 9),
-                ("out", vp * 9), ("potential", vp), ("potential_from", i32), ("ocean_reference_density", f64)]
+                ("out", vp * 9), ("potential", vp), ("potential_from", i32), ("ocean_reference_density", f64),
+                ("rotation_cos", vp), ("rotation_sin", vp), ("rotate_u", i32), ("rotate_v", i32)]
 
 
 class NeFracIndexDesc(C.Structure):

@@ -682,6 +682,7 @@ int fused_interp_ao_f64(const NeInterpDesc* atm, const NeInterpDesc* rad, const 
   if (!atm || !d || !fast_path_eligible(d->flux, d->properties, d->thermo) || !tab_path_eligible(d->flux)) return 1;
   const bool has_rad = rad && rad->n_fields > 0;
   if (atm->n_fields < 5 || atm->n_fields > 7 || !same_launch(atm->grid, d->grid)) return 1;
+  if (atm->rotation_cos || atm->rotation_sin) return 1;   // rotated exchange grids: component kernels
   for (int f = 0; f < 5; ++f)
     if (atm->n_summands[f] != 1 || !atm->series[f][0].data) return 1;
   if (atm->potential && (atm->potential_from < 0 || atm->potential_from > 4)) return 1;

@@ -23,6 +23,20 @@
 
 namespace ne {
 
+// intrinsic_vector (interpolate_atmospheric_state.jl:123-126; Oceananigans rotation operators, third party): the
+// interpolated (u, v) turned into the frame of a rotated exchange grid, every operation separately rounded in the
+// promoted type of (interpolated value, exchange element type)
+template <class FT, class W>
+__device__ __forceinline__ void store_rotated(const NeInterpDesc& d, int64_t idx, W u, W v) {
+  using P = decltype(W() * FT());
+  const P c = (P)__ldg((const FT*)d.rotation_cos + idx), sn = (P)__ldg((const FT*)d.rotation_sin + idx);
+  const P ur = add_rn(mul_rn((P)u, c), mul_rn((P)v, sn));
+  const P vr = add_rn(mul_rn(-(P)u, sn), mul_rn((P)v, c));
+  ((FT*)d.out[d.rotate_u])[idx] = (FT)ur;
+  ((FT*)d.out[d.rotate_v])[idx] = (FT)vr;
+}
+static bool rotation_requested(const NeInterpDesc& d) { return d.rotation_cos != nullptr || d.rotation_sin != nullptr; }
+
 // One thread per exchange point, consecutive threads along x: a block writes one contiguous 2 KB run
 // per field (DRAM-friendly streams; measured 2.3x faster than 32x4 tiles on B200, profiles/r01_notes.md).
 // Fully unrolled over the (at most 9) fields so every pointer is a constant-bank operand;
@@ -39,6 +53,8 @@ interp_state_kernel(const __grid_constant__ NeInterpDesc d, const __grid_constan
   const TT nt = (TT)d.time.frac;
   const bool same = d.time.same != 0;
   using W = decltype(AT() * TT());
+  const bool rotate = d.rotation_cos != nullptr;   // validated on the host: both arrays, two distinct output fields
+  W vec_u = 0, vec_v = 0;
 #pragma unroll
   for (int f = 0; f < 9; ++f) {
     if (f >= d.n_fields) break;
@@ -51,9 +67,12 @@ interp_state_kernel(const __grid_constant__ NeInterpDesc d, const __grid_constan
     } else {
       total = interp_field<AT, TT>(d, f, p, S, nt, same);
     }
+    if (rotate && f == d.rotate_u) { vec_u = total; continue; }
+    if (rotate && f == d.rotate_v) { vec_v = total; continue; }
     out[idx] = (FT)total;
     if (d.potential && f == d.potential_from) ((FT*)d.potential)[idx] = div_rn((FT)total, (FT)d.ocean_reference_density);
   }
+  if (rotate) store_rotated<FT, W>(d, idx, vec_u, vec_v);
 }
 
 // ---- shared-memory staged variant --------------------------------------------------------------------
@@ -182,6 +201,7 @@ template <int NS>
 static bool make_staged_plan(const NeInterpDesc& d, const Layout& L, StagedPlan<NS>& P) {
   const char* off = std::getenv("NE_B200_INTERP_DIRECT");
   if (off && off[0] == '1') return false;
+  if (rotation_requested(d)) return false;   // rotated (curvilinear) exchange grids take the direct-gather kernel
   // staging pays when a 256-point block spans few source columns: exchange grid at least 4x finer than the source
   if (d.grid.nx < 4 * d.src_nx) return false;
   std::memset(&P, 0, sizeof(P));
@@ -295,6 +315,13 @@ static int interp_entry(const NeInterpDesc* d, void* stream) {
   for (int f = 0; f < d->n_fields; ++f)
     NE_REQUIRE(d->n_summands[f] >= 0 && d->n_summands[f] <= NE_MAX_SUMMANDS, "interp: too many summands");
   if (d->potential) NE_REQUIRE(d->potential_from >= 0 && d->potential_from < d->n_fields, "interp: potential_from out of range");
+  if (rotation_requested(*d)) {
+    NE_REQUIRE(d->rotation_cos && d->rotation_sin, "interp: rotation needs both the cos and the sin array");
+    NE_REQUIRE(d->rotate_u >= 0 && d->rotate_u < d->n_fields && d->rotate_v >= 0 && d->rotate_v < d->n_fields &&
+               d->rotate_u != d->rotate_v && d->out[d->rotate_u] && d->out[d->rotate_v] &&
+               !(d->potential && (d->potential_from == d->rotate_u || d->potential_from == d->rotate_v)),
+               "interp: rotate_u / rotate_v must name two distinct stored fields");
+  }
   cudaStream_t s = (cudaStream_t)stream;
   const bool a64 = d->src_dtype == NE_F64, t64 = d->time.frac_dtype == NE_F64;
   if (a64) return t64 ? launch_interp<FT, double, double>(*d, s) : launch_interp<FT, double, float>(*d, s);

@@ -45,6 +45,10 @@ class ExchangeGrid:
     hz: int = 0
     j_offset: int = 0          # latitude-band shards: global row index of local row 1, minus 1
     ny_global: Optional[int] = None
+    # rotated exchange grids (tripolar, cubed sphere): exchange-layout (cos θ, sin θ) of the angle between the grid's
+    # x direction and geographic east — what Oceananigans' intrinsic_vector uses (third party; the binding fills it once).
+    # None: latitude-longitude grid, interpolated vectors are stored as they are.
+    rotation: Any = None
 
     def __post_init__(self):
         npd = np.float64 if self.FT == "f64" else np.float32
@@ -169,6 +173,16 @@ class PrescribedRadiation:
     time_indexing: str = "cyclical"
 
 
+@dataclass
+class PrescribedLand:
+    """PrescribedLand freshwater fluxes (Lands/prescribed_land.jl; JRA55 river + iceberg runoff on its own 1440x720
+    daily grid, DataWrangling/JRA55/JRA55_metadata.jl:24-25): a tuple of series on one source grid, summed."""
+    grid: LatLonSourceGrid
+    times: Any
+    freshwater_flux: Any = ()      # tuple of series (rivers, icebergs, ...), each (nt, ny+2hy, nx+2hx)
+    time_indexing: str = "cyclical"
+
+
 class _Fields:
     """Bag of named exchange-layout arrays."""
 
@@ -203,8 +217,10 @@ class ComponentInterfaces:
                  atmosphere_sea_ice_interface_temperature=None, atmosphere_sea_ice_velocity_difference=None,
                  sea_ice_ocean_heat_flux=None,
                  ocean_properties=None, sea_ice_properties=None,
-                 gravitational_acceleration=9.80665, inactive=None, with_iterations=False, atmosphere_correction=None):
+                 gravitational_acceleration=9.80665, inactive=None, with_iterations=False, atmosphere_correction=None,
+                 land: Optional[PrescribedLand] = None):
         self.grid, self.backend = grid, backend
+        self.land = land
         self.lib = lib if lib is not None else get_library()
         if getattr(self.lib, "is_device", True) != backend.is_device:
             raise RuntimeError("array back-end and compute library disagree on where memory lives "
@@ -244,6 +260,12 @@ class ComponentInterfaces:
             self.phi_dev = backend.from_numpy(grid.phi)
             self.rad_fluxes_ocean = _Fields(upwelling_longwave=Z(), downwelling_longwave=Z(), downwelling_shortwave=Z())
             self.rad_fluxes_sea_ice = _Fields(upwelling_longwave=Z(), downwelling_longwave=Z(), downwelling_shortwave=Z()) if sea_ice else None
+        # PrescribedLand exchanger state (Lands/prescribed_land_regridder.jl): the summed runoff on the exchange grid
+        self.land_state = None
+        self.land_frac = None
+        if land is not None:
+            self.land_state = _Fields(freshwater_flux=Z())
+            self.land_frac = _Fields(i=backend.zeros(grid.shape, land.grid.FT), j=backend.zeros(grid.shape, land.grid.FT))
         # ocean surface state (pointers to the top-level plane of the 3-D parents)
         self.ocean_state = _Fields(u=Z(), v=Z(), T=Z(), S=Z())
         self.kappa = None
@@ -288,6 +310,10 @@ class ComponentInterfaces:
             self.lib.call("frac_indices", self.grid.FT, self._frac_desc(self.atmosphere.grid, self.frac), s)
         if self.radiation is not None:
             self.lib.call("frac_indices", self.grid.FT, self._frac_desc(self.radiation.grid, self.rad_frac), s)
+        if self.land is not None:
+            # the reference evaluates these fractional indices on the fly from the node (interpolate_land_state.jl:55-60);
+            # they are the same function of the same node, so they are computed once
+            self.lib.call("frac_indices", self.grid.FT, self._frac_desc(self.land.grid, self.land_frac), s)
 
     # ---- phase 1: interpolation ---------------------------------------------------------------------
     def _time_interp(self, times, t, time_indexing, frac_dtype="f64"):
@@ -315,6 +341,15 @@ class ComponentInterfaces:
             for k, s in enumerate(series):
                 d.series[f][k].data = _ptr(b, s)
             d.out[f] = b.ptr(out)
+        if g.rotation is not None:   # intrinsic_vector (interpolate_atmospheric_state.jl:123-126)
+            if not hasattr(self, "_rotation_dev"):
+                npd = np.float64 if g.FT == "f64" else np.float32
+                self._rotation_dev = tuple(b.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=npd))) for a in g.rotation)
+                for a in self._rotation_dev:
+                    if tuple(a.shape) != tuple(g.shape):
+                        raise ValueError("rotation arrays must have the exchange layout (ny + 2hy, nx + 2hx)")
+            d.rotation_cos, d.rotation_sin = b.ptr(self._rotation_dev[0]), b.ptr(self._rotation_dev[1])
+            d.rotate_u, d.rotate_v = 0, 1
         return d
 
     def radiation_interp_desc(self, t) -> A.NeInterpDesc:
@@ -331,6 +366,27 @@ class ComponentInterfaces:
             d.n_summands[f] = 1
             d.series[f][0].data = b.ptr(s)
             d.out[f] = b.ptr(out)
+        return d
+
+    def land_interp_desc(self, t) -> A.NeInterpDesc:
+        """interpolate_state!(exchanger, grid, ::PrescribedLand, model) (Lands/interpolate_land_state.jl:6-61): ONE output
+        field, the sum over the runoff series (interp_atmos_time_series of a tuple, interpolate_atmospheric_state.jl:152-182)."""
+        b, g, land = self.backend, self.grid, self.land
+        series = list(land.freshwater_flux)
+        if not 1 <= len(series) <= A.NE_MAX_SUMMANDS:
+            raise F.NoKernelVariantError("PrescribedLand needs 1 to 4 freshwater flux series")
+        d = A.NeInterpDesc()
+        d.grid = g.pod(True)
+        d.frac_i, d.frac_j = b.ptr(self.land_frac.i), b.ptr(self.land_frac.j)
+        d.src_dtype = NE_DT[land.grid.FT]
+        d.src_nx, d.src_ny, d.src_hx, d.src_hy = land.grid.nx, land.grid.ny, land.grid.hx, land.grid.hy
+        d.src_nt = len(land.times)
+        d.time = self._time_interp(land.times, t, land.time_indexing)
+        d.n_fields = 1
+        d.n_summands[0] = len(series)
+        for k, sr in enumerate(series):
+            d.series[0][k].data = b.ptr(sr)
+        d.out[0] = b.ptr(self.land_state.freshwater_flux)
         return d
 
     # ---- ElevationCorrection (atmosphere_state_correction.jl) -----------------------------------------------
@@ -385,6 +441,8 @@ class ComponentInterfaces:
             self.lib.call("interp_state", self.grid.FT, self.radiation_interp_desc(t), s)
         if self.atmosphere is not None:
             self.lib.call("interp_state", self.grid.FT, self.atmosphere_interp_desc(t), s)
+        if self.land is not None:
+            self.lib.call("interp_state", self.grid.FT, self.land_interp_desc(t), s)
 
     # ---- radiation POD ---------------------------------------------------------------------------------
     def _surface_radiation(self, surface, time_seconds=None) -> A.NeSurfaceRadiation:
@@ -564,7 +622,8 @@ class ComponentInterfaces:
                 setattr(d, n, _slot(b, 0.0))
         d.ocean_surface_temperature = _slot(b, self.ocean_state.T)
         d.rainfall, d.snowfall = _slot(b, self.atmos_state.Jrn), _slot(b, self.atmos_state.Jsn)
-        d.intercepted_snowfall, d.land_freshwater = _slot(b, 0.0), _slot(b, 0.0)
+        d.intercepted_snowfall = _slot(b, 0.0)
+        d.land_freshwater = _slot(b, self.land_state.freshwater_flux if self.land is not None else 0.0)
         d.inactive = _ptr(b, self.inactive)
         d.ocean = self.ocean_properties.pod()
         n = self.net_ocean
@@ -670,6 +729,8 @@ class ComponentInterfaces:
             if diagnostics is not None:
                 diagnostics.reduce()
             return
+        if self.land is not None:   # the runoff interpolation is independent of everything else in phase 1
+            self.lib.call("interp_state", self.grid.FT, self.land_interp_desc(t), self.backend.stream())
         self.lib.call("fused_interface_step", self.grid.FT, self.fused_step_desc(t, diagnostics), self.backend.stream())
         if diagnostics is not None:
             diagnostics.all_reduce()

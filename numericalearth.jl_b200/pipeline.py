@@ -70,6 +70,8 @@ class HostPipelinedStep:
             v = host_ocean[name]
             d.fields[k].host = v.data_ptr() if hasattr(v, "data_ptr") else v.ctypes.data
         self._set_time(t)
+        if self.ci.land is not None:   # PrescribedLand runoff: independent of the ocean state, ahead of the pipeline
+            self.lib.call("interp_state", self.FT, self.ci.land_interp_desc(t), self.ci.backend.stream())
         rc = self._fn(self.handle, C.byref(d), C.c_void_p(self.ci.backend.stream()))
         if rc != 0:
             if rc == A.NE_E_NO_VARIANT:

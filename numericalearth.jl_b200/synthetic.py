@@ -10,7 +10,7 @@ import numpy as np
 
 from . import formulations as F
 from .interface import (ComponentInterfaces, ExchangeGrid, LatLonSourceGrid, PrescribedAtmosphere,
-                        PrescribedRadiation)
+                        PrescribedLand, PrescribedRadiation)
 
 CONFIGS = {
     "C1": dict(nx=360, ny=150, latitude=(-75.0, 75.0)),
@@ -112,6 +112,35 @@ def row_cost_weights(config, FT="f64", active_cost=4.3):
     return g.nx + active_cost * (m == 0).sum(axis=1).astype(np.float64)
 
 
+def land_arrays(src: LatLonSourceGrid, nt, rng):
+    """JRA55-shaped runoff: two non-negative, sparse series (rivers, icebergs) on the land grid, (nt, ny+2hy, nx+2hx),
+    periodic x halos filled."""
+    npd = np.float64 if src.FT == "f64" else np.float32
+    ny, nx = src.ny, src.nx
+    out = []
+    for scale, frac in ((2e-4, 0.04), (5e-5, 0.01)):
+        base = scale * rng.uniform(0, 1, (ny, nx)) * (rng.uniform(size=(ny, nx)) < frac)
+        a = np.stack([base * (1 + 0.2 * np.sin(2 * np.pi * n / max(nt, 1))) for n in range(nt)])
+        full = np.zeros((nt, ny + 2 * src.hy, nx + 2 * src.hx), dtype=npd)
+        full[:, src.hy:src.hy + ny, src.hx:src.hx + nx] = a
+        full[:, :, :src.hx] = full[:, :, nx:nx + src.hx]
+        full[:, :, nx + src.hx:] = full[:, :, src.hx:2 * src.hx]
+        full[:, :src.hy, :] = full[:, src.hy:src.hy + 1, :]
+        full[:, src.hy + ny:, :] = full[:, src.hy + ny - 1:src.hy + ny, :]
+        out.append(full)
+    return out
+
+
+def rotation_arrays(grid: ExchangeGrid):
+    """A smooth synthetic rotation angle θ(λ, φ) ∈ (−π, π) in the exchange layout, as (cos θ, sin θ): stands in for the
+    rotation metrics of a tripolar grid (θ grows towards the northern fold)."""
+    phi = np.deg2rad(grid.phi.astype(np.float64))[:, None]
+    lam = np.deg2rad(grid.lam.astype(np.float64))[None, :]
+    theta = 2.5 * np.sin(lam) * np.clip((np.rad2deg(phi) - 20.0) / 60.0, 0.0, 1.0) ** 2 + 0.05 * np.cos(2 * lam) * np.cos(phi)
+    npd = np.float64 if grid.FT == "f64" else np.float32
+    return np.cos(theta).astype(npd), np.sin(theta).astype(npd)
+
+
 def ocean_arrays(grid: ExchangeGrid, rng, sea_ice=False):
     """Exchange-layout (ny+2hy, nx+2hx) ocean surface / sea-ice state + inactive mask."""
     npd = np.float64 if grid.FT == "f64" else np.float32
@@ -139,12 +168,15 @@ def ocean_arrays(grid: ExchangeGrid, rng, sea_ice=False):
 
 
 def build_case(config, backend, FT="f64", atm_FT="f64", nt=2, seed_offset=0, sea_ice=False, radiation=True,
-               stretched_latitude=False, lib=None, with_iterations=False, grid=None, **interface_kwargs):
+               stretched_latitude=False, lib=None, with_iterations=False, grid=None, land=False, rotated=False,
+               **interface_kwargs):
     """Construct a fully populated ComponentInterfaces for one BASELINE.json config on `backend`."""
     cfg = CONFIGS[config] if isinstance(config, str) else config
     if grid is None:
         grid = ExchangeGrid(nx=cfg["nx"], ny=cfg["ny"], hx=cfg.get("hx", 7), hy=cfg.get("hy", 7),
                             latitude=cfg["latitude"], FT=FT)
+    if rotated:
+        grid.rotation = rotation_arrays(grid)
     rng = np.random.default_rng(BASE_SEED + seed_offset)
     src = LatLonSourceGrid(nx=cfg.get("src_nx", 640), ny=cfg.get("src_ny", 320), FT=atm_FT,
                            phi_nodes=gaussian_like_latitudes(cfg.get("src_ny", 320)) if stretched_latitude else None,
@@ -162,8 +194,15 @@ def build_case(config, backend, FT="f64", atm_FT="f64", nt=2, seed_offset=0, sea
         o = {k: np.ascontiguousarray(v[grid.j_offset:grid.j_offset + grid.ny + 2 * grid.hy, :]) for k, v in og.items()}
     else:
         o = ocean_arrays(grid, rng, sea_ice=sea_ice)
+    land_component = None
+    if land:   # after every other draw, so the atmosphere / ocean inputs do not depend on it
+        lsrc = LatLonSourceGrid(nx=cfg.get("land_nx", 1440), ny=cfg.get("land_ny", 720), FT=atm_FT)
+        ltimes = np.arange(nt, dtype=np.float64) * 86400.0
+        lrng = np.random.default_rng(BASE_SEED + 5000 + seed_offset)
+        land_component = PrescribedLand(grid=lsrc, times=ltimes,
+                                        freshwater_flux=tuple(backend.from_numpy(x) for x in land_arrays(lsrc, nt, lrng)))
     ci = ComponentInterfaces(grid, backend, atm, rad, sea_ice=sea_ice, lib=lib, inactive=backend.from_numpy(o["inactive"]),
-                             with_iterations=with_iterations, **interface_kwargs)
+                             with_iterations=with_iterations, land=land_component, **interface_kwargs)
     ci.ocean_state.u, ci.ocean_state.v = backend.from_numpy(o["u"]), backend.from_numpy(o["v"])
     ci.ocean_state.T, ci.ocean_state.S = backend.from_numpy(o["T"]), backend.from_numpy(o["S"])
     if sea_ice:

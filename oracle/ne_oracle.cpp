@@ -762,6 +762,8 @@ void interp_state(const NeInterpDesc& d) {
   const TT nt = (TT)d.time.frac;
   const int64_t o1 = (int64_t)(d.time.m1 - 1) * plane, o2 = (int64_t)(d.time.m2 - 1) * plane;
   using W = decltype(AT() * TT());
+  const bool rotate = d.rotation_cos && d.rotation_sin && d.rotate_u >= 0 && d.rotate_v >= 0 && d.rotate_u < d.n_fields &&
+                      d.rotate_v < d.n_fields && d.rotate_u != d.rotate_v && d.out[d.rotate_u] && d.out[d.rotate_v];
 #pragma omp parallel for schedule(static)
   for (int64_t j = d.grid.j_lo; j <= d.grid.j_hi; ++j) {
     for (int64_t i = d.grid.i_lo; i <= d.grid.i_hi; ++i) {
@@ -776,6 +778,7 @@ void interp_state(const NeInterpDesc& d) {
       const int64_t a_mp = (ix.im + d.src_hx - 1) + (iy.ip + d.src_hy - 1) * ssx;
       const int64_t a_pm = (ix.ip + d.src_hx - 1) + (iy.im + d.src_hy - 1) * ssx;
       const int64_t a_pp = (ix.ip + d.src_hx - 1) + (iy.ip + d.src_hy - 1) * ssx;
+      W vec_u = 0, vec_v = 0;
       for (int f = 0; f < d.n_fields; ++f) {
         FT* out = (FT*)d.out[f];
         if (!out) continue;
@@ -796,7 +799,16 @@ void interp_state(const NeInterpDesc& d) {
           total = first ? val : total + val;
           first = false;
         }
+        if (rotate && (f == d.rotate_u || f == d.rotate_v)) { (f == d.rotate_u ? vec_u : vec_v) = total; continue; }
         out[idx] = (FT)total;
+      }
+      if (rotate) {   // intrinsic_vector (interpolate_atmospheric_state.jl:123-126; Oceananigans rotation, third party)
+        using P = decltype(W() * FT());
+        const P c = ((const FT*)d.rotation_cos)[idx], sn = ((const FT*)d.rotation_sin)[idx];
+        const P ur = (P)vec_u * c + (P)vec_v * sn;
+        const P vr = -(P)vec_u * sn + (P)vec_v * c;
+        ((FT*)d.out[d.rotate_u])[idx] = (FT)ur;
+        ((FT*)d.out[d.rotate_v])[idx] = (FT)vr;
       }
       if (d.potential) ((FT*)d.potential)[idx] = ((FT*)d.out[d.potential_from])[idx] / (FT)d.ocean_reference_density;
     }
