@@ -289,7 +289,8 @@ static int launch_interp(const NeInterpDesc& d, cudaStream_t stream) {
     int active = 0;
     for (int f = 0; f < d.n_fields; ++f) active += d.out[f] != nullptr;
     bool done = false;
-    if (active == 7) done = try_staged<FT, AT, TT, 7>(d, L, S, stream);
+    if (active == 9) done = try_staged<FT, AT, TT, 9>(d, L, S, stream);   // atmosphere + radiation merged (ne_fused.cu)
+    else if (active == 7) done = try_staged<FT, AT, TT, 7>(d, L, S, stream);
     else if (active == 5) done = try_staged<FT, AT, TT, 5>(d, L, S, stream);
     else if (active == 2) done = try_staged<FT, AT, TT, 2>(d, L, S, stream);
     if (done) {

@@ -18,6 +18,7 @@
 namespace ne {
 int post_solve_f64(const NeFusedStepDesc* d, void* stream);   // ne_surface_kernels.cu
 int post_solve_f32(const NeFusedStepDesc* d, void* stream);
+int interp_phase(const NeFusedStepDesc* d, void* stream, bool f64);   // ne_fused.cu
 
 struct HostPipeline {
   int device;
@@ -82,11 +83,7 @@ static int pipelined_step(HostPipeline* hp, const NeHostStepDesc* d, void* strea
     NE_CUDA_TRY(cudaEventRecord(hp->done, compute), "host pipeline (record done)");
     return NE_OK;
   }
-  if (d->step.radiation.n_fields > 0) {
-    rc = f64 ? ne_interp_state_f64(&d->step.radiation, stream) : ne_interp_state_f32(&d->step.radiation, stream);
-    if (rc) return rc;
-  }
-  rc = f64 ? ne_interp_state_f64(&d->step.atmosphere, stream) : ne_interp_state_f32(&d->step.atmosphere, stream);
+  rc = interp_phase(&d->step, stream, f64);
   if (rc) return rc;
 
   NeFusedStepDesc band = d->step;   // launch ranges rewritten per band

@@ -256,7 +256,15 @@ class ComponentInterfaces:
         self.rad_frac = None
         if radiation is not None:
             self.rad_state = _Fields(sw=Z(), lw=Z())
-            self.rad_frac = _Fields(i=backend.zeros(grid.shape, radiation.grid.FT), j=backend.zeros(grid.shape, radiation.grid.FT))
+            # same source grid as the atmosphere (JRA55 radiation is): one set of fractional indices serves both, and the
+            # fused step then interpolates the 9 series in one launch
+            sg, ag = radiation.grid, (atmosphere.grid if atmosphere is not None else None)
+            self.shared_frac = ag is not None and (sg is ag or (
+                sg.FT == ag.FT and (sg.nx, sg.ny, sg.hx, sg.hy, sg.x_regular, sg.y_regular) ==
+                (ag.nx, ag.ny, ag.hx, ag.hy, ag.x_regular, ag.y_regular) and
+                np.array_equal(sg.lam_nodes, ag.lam_nodes) and np.array_equal(sg.phi_nodes, ag.phi_nodes)))
+            self.rad_frac = self.frac if self.shared_frac else \
+                _Fields(i=backend.zeros(grid.shape, radiation.grid.FT), j=backend.zeros(grid.shape, radiation.grid.FT))
             self.phi_dev = backend.from_numpy(grid.phi)
             self.rad_fluxes_ocean = _Fields(upwelling_longwave=Z(), downwelling_longwave=Z(), downwelling_shortwave=Z())
             self.rad_fluxes_sea_ice = _Fields(upwelling_longwave=Z(), downwelling_longwave=Z(), downwelling_shortwave=Z()) if sea_ice else None
@@ -308,7 +316,7 @@ class ComponentInterfaces:
         s = self.backend.stream()
         if self.atmosphere is not None:
             self.lib.call("frac_indices", self.grid.FT, self._frac_desc(self.atmosphere.grid, self.frac), s)
-        if self.radiation is not None:
+        if self.radiation is not None and not self.shared_frac:
             self.lib.call("frac_indices", self.grid.FT, self._frac_desc(self.radiation.grid, self.rad_frac), s)
         if self.land is not None:
             # the reference evaluates these fractional indices on the fly from the node (interpolate_land_state.jl:55-60);

@@ -540,3 +540,20 @@ def test_full_size_properties_C4(cuda_backend, cuda_lib):
         os.environ.pop("NE_B200_INTERP_DIRECT", None)
     for n, a in staged.items():
         assert np.array_equal(a, to(getattr(dev.atmos_state, n)), equal_nan=True), f"staged vs direct interpolation: {n}"
+    # (vi) the fused step interpolates atmosphere + radiation in ONE 9-series staged launch (shared fractional indices):
+    # bit-identical to the two separate launches, and so is everything downstream
+    rad_sep = {n: to(getattr(dev.rad_state, n)).copy() for n in dev.rad_state.names()}
+    net_sep = {n: to(getattr(dev.net_ocean, n)).copy() for n in dev.net_ocean.names()}
+    assert dev.shared_frac
+    for bag in (dev.atmos_state, dev.rad_state, dev.net_ocean):
+        for n in bag.names():
+            getattr(bag, n).fill_(float("nan"))
+    dev.fused_interface_step(T_STEP)
+    cuda_backend.synchronize()
+    for n, a in staged.items():
+        assert np.array_equal(g.interior(a), g.interior(to(getattr(dev.atmos_state, n))), equal_nan=True), f"merged interpolation: {n}"
+    for n, a in rad_sep.items():
+        assert np.array_equal(g.interior(a), g.interior(to(getattr(dev.rad_state, n))), equal_nan=True), f"merged interpolation: {n}"
+    inner = (slice(g.hy, g.hy + g.ny), slice(g.hx, g.hx + g.nx))
+    for n, a in net_sep.items():
+        assert np.array_equal(a[inner], to(getattr(dev.net_ocean, n))[inner], equal_nan=True), f"fused step net flux: {n}"
