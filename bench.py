@@ -79,6 +79,7 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--e2e-chunks", type=int, default=8)
     p.add_argument("--equal-bands", action="store_true", help="equal row counts per band instead of cost-balanced bands")
+    p.add_argument("--no-rebalance", action="store_true", help="keep the mask-based bands (no re-balancing from measured trip counts)")
     return p.parse_args()
 
 
@@ -206,8 +207,8 @@ def workload_config(args, n):
     return {"workload": f"{args.config}: {c['nx']}x{c['ny']} exchange grid (lat {c['latitude']}), JRA55-shaped 640x320 "
                         f"{args.atm_dtype} atmosphere + radiation, SimilarityTheoryFluxes defaults, OceanOnlyModel interface step",
             "exchange_dtype": args.dtype, "atmosphere_dtype": args.atm_dtype,
-            "partition": f"{n} latitude band(s)" + ("" if n == 1 else (", equal row counts" if args.equal_bands else
-                         ", rows balanced by active-point count")) + ", one-ring overcompute, no data-path collective",
+            "partition": f"{n} latitude band(s)" + ("" if n == 1 else ", " + getattr(args, "partition_note", "rows balanced by active-point count")) +
+                         ", one-ring overcompute, no data-path collective",
             "l2": "inputs larger than L2 (≈35 fields x 58 MB at N=1); no explicit flush",
             "points_per_step": (c["nx"] + 2) * (c["ny"] + 2)}
 
@@ -231,10 +232,29 @@ def b200_arm(args):
     backend = ne_b200.TorchCudaBackend(f"cuda:{local_rank}")
     lib = ne_b200.get_library()
     cfg = synthetic.CONFIGS[args.config]
-    # latitude bands balanced by estimated row cost (active-point count from the land mask: static information)
+    # latitude bands balanced by row cost.  First guess: active-point count from the land mask (static information);
+    # then, as a coupled run would do every so often, re-balanced once from the trip counts the solve itself reports
+    # (`iterations` of a set-up step; setup is not timed).
     weights = synthetic.row_cost_weights(args.config, FT=args.dtype) if (world > 1 and not args.equal_bands) else None
     grid = sharding.band_grid(cfg["nx"], cfg["ny"], cfg["latitude"], rank, world, FT=args.dtype, weights=weights)
     ci = synthetic.build_case(args.config, backend, FT=args.dtype, atm_FT=args.atm_dtype, grid=grid, with_iterations=True)
+    partition_note = "equal row counts" if args.equal_bands else "rows balanced by active-point count"
+    if world > 1 and not args.equal_bands and not args.no_rebalance:
+        ci.initialize()
+        ci.update_state(0.37 * 10800.0)
+        torch.cuda.synchronize()
+        active_rows, trip_rows = sharding.gather_row_statistics(backend.to_numpy(grid.interior(ci.ao_iterations)), grid)
+        weights = sharding.measured_row_weights(cfg["nx"], active_rows, trip_rows)
+        new_grid = sharding.band_grid(cfg["nx"], cfg["ny"], cfg["latitude"], rank, world, FT=args.dtype, weights=weights)
+        moved = torch.tensor([int((new_grid.j_offset, new_grid.ny) != (grid.j_offset, grid.ny))], device=backend.device)
+        dist.all_reduce(moved)
+        if int(moved.item()) > 0:
+            del ci
+            torch.cuda.empty_cache()
+            grid = new_grid
+            ci = synthetic.build_case(args.config, backend, FT=args.dtype, atm_FT=args.atm_dtype, grid=grid, with_iterations=True)
+        partition_note = "rows balanced by measured trip counts of a set-up step"
+    args.partition_note = partition_note
     ci.initialize()
     f = ci.ao_fluxes
     diag = sharding.FluxDiagnostics(ci, [f.latent_heat, f.sensible_heat, f.water_vapor, f.x_momentum, f.y_momentum,

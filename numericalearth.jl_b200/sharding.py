@@ -38,6 +38,32 @@ def latitude_bands(ny, world_size, weights=None):
     return [(edges[r] + 1, edges[r + 1]) for r in range(world_size)]
 
 
+def measured_row_weights(nx, active_per_row, trips_per_row, per_active=3.0, per_point=2.5):
+    """Per-row cost from MEASURED trip counts (the `iterations` output of the previous coupled step: the trip count
+    of a point changes slowly from step to step, so last step's field predicts this step's cost): one unit per
+    lane-trip of the solve, `per_active` for the prologue + flux epilogue of an active point, `per_point` for the
+    HBM-bound kernels every point pays (ratios measured on B200, profiles/r01_notes.md)."""
+    a = np.asarray(active_per_row, dtype=np.float64)
+    t = np.asarray(trips_per_row, dtype=np.float64)
+    return t + per_active * a + per_point * float(nx)
+
+
+def gather_row_statistics(iterations_interior, grid, group=None):
+    """All ranks: per-row (active points, trips) of the GLOBAL grid from each band's iteration-count field
+    (rows 1..ny of the band's launch window; one small all_gather_object)."""
+    import torch.distributed as dist
+    it = np.asarray(iterations_interior)[1:-1, 1:-1]           # drop the overcomputed ring
+    mine = (int(grid.j_offset), (it > 0).sum(axis=1).astype(np.int64), it.sum(axis=1).astype(np.int64))
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, mine, group=group)
+    ny = grid.ny_global or grid.ny
+    active, trips = np.zeros(ny, dtype=np.int64), np.zeros(ny, dtype=np.int64)
+    for j0, a, t in parts:
+        active[j0:j0 + len(a)] = a
+        trips[j0:j0 + len(t)] = t
+    return active, trips
+
+
 def band_grid(nx, ny, latitude, rank, world_size, FT="f64", hx=7, hy=7, weights=None):
     j0, j1 = latitude_bands(ny, world_size, weights)[rank]
     return ExchangeGrid(nx=nx, ny=j1 - j0 + 1, hx=hx, hy=hy, latitude=latitude, FT=FT, j_offset=j0 - 1, ny_global=ny)

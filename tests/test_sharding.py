@@ -97,3 +97,49 @@ def test_diagnostics_all_reduce_two_ranks_gloo(oracle_lib, host_backend):
     f = glob.ao_fluxes
     ref = np.array([(x[rows, cols] * area[rows, cols])[act].sum() for x in (f.latent_heat, f.sensible_heat, f.x_momentum, glob.net_ocean.T)])
     assert np.allclose(res[0][1], ref, rtol=1e-12)
+
+
+def _rebalance_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    lib = oracle.load()
+    host = ne_b200.NumpyHostBackend()
+    cfg = synthetic.CONFIGS["tiny"]
+    grid = sharding.band_grid(cfg["nx"], cfg["ny"], cfg["latitude"], rank, world)
+    ci = synthetic.build_case("tiny", host, lib=lib, grid=grid, with_iterations=True)
+    ci.initialize(); ci.update_state(4000.0)
+    active, trips = sharding.gather_row_statistics(grid.interior(ci.ao_iterations), grid)
+    q.put((rank, active, trips))
+    dist.destroy_process_group()
+
+
+def test_rebalancing_from_measured_trip_counts_two_ranks_gloo(oracle_lib, host_backend):
+    """Every rank assembles the same global per-row (active, trips) table from the bands' iteration-count fields; the
+    table equals the single-rank one; bands dealt by it are contiguous, cover every row once and even out the cost."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rebalance_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+    glob = synthetic.build_case("tiny", host_backend, lib=oracle_lib, with_iterations=True)
+    glob.initialize(); glob.update_state(4000.0)
+    g = glob.grid
+    it = g.interior(glob.ao_iterations)[1:-1, 1:-1]
+    assert np.array_equal(res[0][1], (it > 0).sum(axis=1)) and np.array_equal(res[0][2], it.sum(axis=1))
+    w = sharding.measured_row_weights(g.nx, res[0][1], res[0][2])
+    assert (w > 0).all()
+    for world in (2, 3, 4):
+        bands = sharding.latitude_bands(g.ny, world, w)
+        assert bands[0][0] == 1 and bands[-1][1] == g.ny
+        assert all(bands[k][1] + 1 == bands[k + 1][0] for k in range(world - 1))
+        cost = np.array([w[j0 - 1:j1].sum() for j0, j1 in bands])
+        equal = np.array([w[j0 - 1:j1].sum() for j0, j1 in sharding.latitude_bands(g.ny, world)])
+        assert cost.max() <= equal.max() + w.max()      # never worse than equal rows by more than one row
