@@ -243,8 +243,8 @@ def b200_arm(args):
         ci.initialize()
         ci.update_state(0.37 * 10800.0)
         torch.cuda.synchronize()
-        active_rows, trip_rows = sharding.gather_row_statistics(backend.to_numpy(grid.interior(ci.ao_iterations)), grid)
-        weights = sharding.measured_row_weights(cfg["nx"], active_rows, trip_rows)
+        _, _, warp_trip_rows = sharding.gather_row_statistics(backend.to_numpy(grid.interior(ci.ao_iterations)), grid)
+        weights = sharding.measured_row_weights(cfg["nx"], warp_trip_rows)
         new_grid = sharding.band_grid(cfg["nx"], cfg["ny"], cfg["latitude"], rank, world, FT=args.dtype, weights=weights)
         moved = torch.tensor([int((new_grid.j_offset, new_grid.ny) != (grid.j_offset, grid.ny))], device=backend.device)
         dist.all_reduce(moved)

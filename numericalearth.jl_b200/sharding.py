@@ -38,30 +38,35 @@ def latitude_bands(ny, world_size, weights=None):
     return [(edges[r] + 1, edges[r + 1]) for r in range(world_size)]
 
 
-def measured_row_weights(nx, active_per_row, trips_per_row, per_active=3.0, per_point=2.5):
+def measured_row_weights(nx, warp_trips_per_row, per_point=2.6):
     """Per-row cost from MEASURED trip counts (the `iterations` output of the previous coupled step: the trip count
-    of a point changes slowly from step to step, so last step's field predicts this step's cost): one unit per
-    lane-trip of the solve, `per_active` for the prologue + flux epilogue of an active point, `per_point` for the
-    HBM-bound kernels every point pays (ratios measured on B200, profiles/r01_notes.md)."""
-    a = np.asarray(active_per_row, dtype=np.float64)
-    t = np.asarray(trips_per_row, dtype=np.float64)
-    return t + per_active * a + per_point * float(nx)
+    of a point changes slowly from step to step, so last step's field predicts this step's cost).  The solve costs
+    one unit per lane SLOT of a warp-trip — a warp runs until its slowest lane converges, so the row's cost is
+    32 x the sum over its 32-point groups of the group's maximum trip count (fits the measured per-band kernel times
+    to 4 %; the plain sum of trips to 8.5 %) — plus `per_point` units for the HBM-bound kernels every point pays
+    (ratio measured on B200, profiles/r01_notes.md)."""
+    return np.asarray(warp_trips_per_row, dtype=np.float64) + per_point * float(nx)
 
 
 def gather_row_statistics(iterations_interior, grid, group=None):
-    """All ranks: per-row (active points, trips) of the GLOBAL grid from each band's iteration-count field
-    (rows 1..ny of the band's launch window; one small all_gather_object)."""
+    """All ranks: per-row (active points, trips, warp-slot trips) of the GLOBAL grid from each band's
+    iteration-count field (rows 1..ny of the band's launch window; one small all_gather_object)."""
     import torch.distributed as dist
     it = np.asarray(iterations_interior)[1:-1, 1:-1]           # drop the overcomputed ring
-    mine = (int(grid.j_offset), (it > 0).sum(axis=1).astype(np.int64), it.sum(axis=1).astype(np.int64))
+    n32 = it.shape[1] // 32 * 32
+    groups = it[:, :n32].reshape(it.shape[0], -1, 32).max(axis=2).sum(axis=1) * 32
+    if n32 < it.shape[1]:
+        groups = groups + it[:, n32:].max(axis=1) * 32
+    mine = (int(grid.j_offset), (it > 0).sum(axis=1).astype(np.int64), it.sum(axis=1).astype(np.int64), groups.astype(np.int64))
     parts = [None] * dist.get_world_size(group)
     dist.all_gather_object(parts, mine, group=group)
     ny = grid.ny_global or grid.ny
-    active, trips = np.zeros(ny, dtype=np.int64), np.zeros(ny, dtype=np.int64)
-    for j0, a, t in parts:
+    active, trips, wtrips = (np.zeros(ny, dtype=np.int64) for _ in range(3))
+    for j0, a, t, w in parts:
         active[j0:j0 + len(a)] = a
         trips[j0:j0 + len(t)] = t
-    return active, trips
+        wtrips[j0:j0 + len(w)] = w
+    return active, trips, wtrips
 
 
 def band_grid(nx, ny, latitude, rank, world_size, FT="f64", hx=7, hy=7, weights=None):

@@ -110,8 +110,8 @@ def _rebalance_worker(rank, world, port, q):
     grid = sharding.band_grid(cfg["nx"], cfg["ny"], cfg["latitude"], rank, world)
     ci = synthetic.build_case("tiny", host, lib=lib, grid=grid, with_iterations=True)
     ci.initialize(); ci.update_state(4000.0)
-    active, trips = sharding.gather_row_statistics(grid.interior(ci.ao_iterations), grid)
-    q.put((rank, active, trips))
+    active, trips, wtrips = sharding.gather_row_statistics(grid.interior(ci.ao_iterations), grid)
+    q.put((rank, active, trips, wtrips))
     dist.destroy_process_group()
 
 
@@ -134,7 +134,8 @@ def test_rebalancing_from_measured_trip_counts_two_ranks_gloo(oracle_lib, host_b
     g = glob.grid
     it = g.interior(glob.ao_iterations)[1:-1, 1:-1]
     assert np.array_equal(res[0][1], (it > 0).sum(axis=1)) and np.array_equal(res[0][2], it.sum(axis=1))
-    w = sharding.measured_row_weights(g.nx, res[0][1], res[0][2])
+    assert np.array_equal(res[0][3], res[1][3]) and (res[0][3] >= res[0][2]).all()   # a warp waits for its slowest lane
+    w = sharding.measured_row_weights(g.nx, res[0][3])
     assert (w > 0).all()
     for world in (2, 3, 4):
         bands = sharding.latitude_bands(g.ny, world, w)
