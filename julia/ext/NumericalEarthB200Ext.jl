@@ -140,5 +140,12 @@ end
 # (cpu_interpolating_time_indices, src/Atmospheres/interpolate_atmospheric_state.jl:57-60) and passed in
 # NeTimeInterp, and fractional indices may be left to the reference's own initialize! so that they are
 # bit-exact by construction.
+#
+# Also behind ne_interp_state_*: interpolate_state!(exchanger, grid, ::PrescribedLand, model)
+# (src/Lands/interpolate_land_state.jl:6-61; one output field, n_summands = number of runoff series, fractional indices
+# of the land grid from ne_frac_indices_* once), and — on TripolarGrid / rotated exchange grids — the intrinsic_vector
+# rotation (interpolate_atmospheric_state.jl:123-126): `NeInterpDesc.rotation_cos/sin` are filled once in initialize!
+# from Oceananigans' rotation metrics of the exchange grid, `rotate_u/v = 0/1`.
+# Host-resident ocean state: ne_host_pipeline_create once, ne_host_pipelined_step_* per coupled step (INTEGRATION.md §5).
 
 end # module
