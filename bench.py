@@ -79,6 +79,7 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--e2e-chunks", type=int, default=8)
     p.add_argument("--equal-bands", action="store_true", help="equal row counts per band instead of cost-balanced bands")
+    p.add_argument("--no-extras", action="store_true", help="skip the one-number measurements of the other BASELINE configs")
     p.add_argument("--no-rebalance", action="store_true", help="keep the mask-based bands (no re-balancing from measured trip counts)")
     return p.parse_args()
 
@@ -372,6 +373,34 @@ def b200_arm(args):
         r = run_cpu(args, seconds_per_step=args.cpu_seconds / 6.0, steps=5, warmup=1)
         cpu = {"value": r["value"], "unit": "points/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
+    # ---- the other BASELINE configurations, one number each (N = 1 only; never allowed to break the headline line) ----
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = {}
+        try:
+            other = "f32" if args.dtype == "f64" else "f64"
+            c2 = synthetic.build_case(args.config, backend, FT=other, atm_FT=args.atm_dtype)
+            c2.initialize()
+            f2 = c2.ao_fluxes
+            dg2 = sharding.FluxDiagnostics(c2, [f2.latent_heat, f2.sensible_heat, f2.water_vapor, f2.x_momentum, f2.y_momentum,
+                                                c2.net_ocean.T, c2.net_ocean.eta])
+            fd2 = c2.fused_step_desc(0.37 * 10800.0, diagnostics=dg2)
+            for _ in range(3):   # the first call builds and uploads the solver table of this parameter set
+                lib.call("fused_interface_step", other, fd2, stream)
+            extras[f"{args.config}_{other}_model_ms_per_step"] = timed(lambda: lib.call("fused_interface_step", other, fd2, stream), reps) / reps
+            del c2, dg2, fd2
+            torch.cuda.empty_cache()
+            c3 = synthetic.build_case("C3", backend, FT=args.dtype, atm_FT=args.atm_dtype, sea_ice=True)
+            c3.initialize()
+            col = synthetic.ocean_column(c3.grid, backend, nz=10) + (600.0, 10)
+            c3.update_state(0.37 * 10800.0, ocean_column=col)
+            extras[f"C3_ocean_sea_ice_{args.dtype}_ms_per_step"] = timed(lambda: c3.update_state(0.37 * 10800.0, ocean_column=col), reps) / reps
+            extras["note"] = ("other BASELINE configs, device-resident: the same grid in the other exchange precision (fused step incl. "
+                              "diagnostics); config 3 = 1/4 degree OceanSeaIceModel update_state (a-o + a-si + si-o kernels, 10-level frazil "
+                              "column, net fluxes, both radiation kernels; Python call sequence, 9 launches)")
+        except Exception as e:   # noqa: BLE001
+            extras["error"] = repr(e)[:200]
+
     ncu_applies = args.config == "C4" and world == 1 and args.dtype == "f64" and args.atm_dtype == "f32"
     if rank == 0:
         n_active = int(active.sum())
@@ -405,6 +434,8 @@ def b200_arm(args):
                                   "component kernels are timed alone for reference"},
             "diagnostics": diag_values,
         }
+        if extras:
+            line["other_configs"] = extras
         if cpu is not None:
             line["cpu_baseline"] = cpu
         emit(json.dumps(line))
