@@ -557,3 +557,86 @@ def test_full_size_properties_C4(cuda_backend, cuda_lib):
     inner = (slice(g.hy, g.hy + g.ny), slice(g.hx, g.hx + g.nx))
     for n, a in net_sep.items():
         assert np.array_equal(a[inner], to(getattr(dev.net_ocean, n))[inner], equal_nan=True), f"fused step net flux: {n}"
+
+
+@pytest.mark.parametrize("case", ["fixed_iterations", "fixed_zero_iterations", "all_inactive", "no_mask", "odd_size", "array_heights"])
+def test_float32_work_queue_edge_cases(oracle_lib, cuda_backend, cuda_lib, case):
+    """The Float32 default tree runs on the persistent work-queue kernel: stop criteria, masks and grid sizes that
+    stress its ring logic (tiles that are all inactive, partial last tiles, FixedIterations solving masked points,
+    zero trips, per-point heights), each against the oracle."""
+    kw = {}
+    cfg = "C1"
+    if case == "fixed_iterations":
+        kw["atmosphere_ocean_fluxes"] = ne_b200.SimilarityTheoryFluxes(solver_stop_criteria=ne_b200.FixedIterations(7))
+    elif case == "fixed_zero_iterations":
+        kw["atmosphere_ocean_fluxes"] = ne_b200.SimilarityTheoryFluxes(solver_stop_criteria=ne_b200.FixedIterations(0))
+    elif case == "odd_size":
+        cfg = dict(nx=37, ny=11, latitude=(-60.0, 60.0))
+    ref, dev = build_pair(cfg, oracle_lib, cuda_backend, FT="f32", atm_FT="f32", **kw)
+    if case == "all_inactive":
+        ref.inactive[:] = 1
+        dev.inactive.fill_(1)
+    elif case == "no_mask":
+        ref.inactive = None
+        dev.inactive = None
+    elif case == "array_heights":   # surface-layer / boundary-layer heights as exchange-layout arrays (non-HS kernel variant)
+        rng = np.random.default_rng(5)
+        zs = rng.uniform(8.0, 12.0, ref.grid.shape).astype(np.float32)
+        hb = rng.uniform(400.0, 700.0, ref.grid.shape).astype(np.float32)
+        ref.atmosphere.surface_layer_height, ref.atmosphere.boundary_layer_height = zs, hb
+        dev.atmosphere.surface_layer_height, dev.atmosphere.boundary_layer_height = cuda_backend.from_numpy(zs), cuda_backend.from_numpy(hb)
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP); dev.update_state(T_STEP)
+    cuda_backend.synchronize()
+    res = compare_fields(ref.ao_fluxes, dev.ao_fluxes, ref.grid, cuda_backend)
+    for n, (r, fr, _) in res.items():
+        assert fr <= F32_TOL, f"{case}/{n}: {fr}"
+    g = ref.grid
+    ri, di = g.interior(ref.ao_iterations), g.interior(cuda_backend.to_numpy(dev.ao_iterations))
+    if case.startswith("fixed"):
+        assert np.array_equal(ri, di)
+    else:
+        assert ((ri > 0) == (di > 0)).all()
+    Tr, Td = g.interior(ref.ao_temperature), g.interior(cuda_backend.to_numpy(dev.ao_temperature))
+    assert np.abs(Tr.astype(np.float64) - Td).max() <= 1e-4
+    # net fluxes downstream
+    for n, (r, fr, _) in compare_fields(ref.net_ocean, dev.net_ocean, ref.grid, cuda_backend, with_halo_ring=False).items():
+        assert fr <= F32_TOL, f"{case}/net {n}: {fr}"
+
+
+@pytest.mark.parametrize("case", ["fixed_iterations", "no_ice", "all_ice_no_mask"])
+def test_sea_ice_work_queue_edge_cases(oracle_lib, cuda_backend, cuda_lib, case):
+    """The a-si default tree on the work-queue kernel: FixedIterations (masked points ARE solved, :141-142), an ice-free
+    ocean (every point takes the immediate path) and full ice cover without a mask (every tile is a full round)."""
+    kw = {}
+    if case == "fixed_iterations":
+        kw["atmosphere_sea_ice_fluxes"] = ne_b200.SimilarityTheoryFluxes(
+            stability_functions=ne_b200.atmosphere_sea_ice_stability_functions(), solver_stop_criteria=ne_b200.FixedIterations(6))
+    ref, dev = build_pair("C1", oracle_lib, cuda_backend, FT="f64", atm_FT="f64", sea_ice=True, **kw)
+    if case == "no_ice":
+        ref.sea_ice_state.concentration[:] = 0
+        dev.sea_ice_state.concentration.fill_(0)
+    elif case == "all_ice_no_mask":
+        for ci, one in ((ref, None), (dev, None)):
+            ci.inactive = None
+        ref.sea_ice_state.concentration[:] = 0.9
+        dev.sea_ice_state.concentration.fill_(0.9)
+        ref.sea_ice_state.hi[:] = 1.2; dev.sea_ice_state.hi.fill_(1.2)
+        ref.sea_ice_state.hs[:] = 0.1; dev.sea_ice_state.hs.fill_(0.1)
+    ref.initialize(); dev.initialize()
+    ref.interpolate_state(T_STEP); dev.interpolate_state(T_STEP)
+    ref.compute_atmosphere_sea_ice_fluxes(); dev.compute_atmosphere_sea_ice_fluxes()
+    cuda_backend.synchronize()
+    g = ref.grid
+    ri, di = g.interior(ref.asi_iterations), g.interior(cuda_backend.to_numpy(dev.asi_iterations))
+    if case == "fixed_iterations":
+        assert np.array_equal(ri, di) and ri.max() == 6
+    else:
+        assert float((ri != di).mean()) <= 2e-3
+    mask = (ri < 100) & (di < 100)
+    for n in ref.asi_fluxes.names():
+        a, b = g.interior(getattr(ref.asi_fluxes, n)), g.interior(cuda_backend.to_numpy(getattr(dev.asi_fluxes, n)))
+        s = float(np.abs(a).max()) or 1.0
+        assert float(np.abs(a - b)[mask].max()) / s <= (F64_TOL if case != "fixed_iterations" else 1e-9), f"{case}/{n}"
+    Tr, Td = g.interior(ref.sea_ice_state.top_temperature), g.interior(cuda_backend.to_numpy(dev.sea_ice_state.top_temperature))
+    assert np.abs(Tr - Td)[mask].max() <= 1e-8
