@@ -154,7 +154,7 @@ ao_flux_tab_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_cons
         s.dq = aq - qs;
         s.ustar = s.theta_star = s.q_star = 1e-4;
       }
-      iters = tab_solve(P, T, tab, s);
+      iters = tab_solve(P, T, tab, s, T.general_psi ? &d.flux : nullptr);
       ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
     }
     // epilogue (atmosphere_ocean_fluxes.jl:160-196): atmosphere state re-read
@@ -601,12 +601,19 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
   const bool v64 = std::is_same<FT, double>::value || viscosity_is_f64_literal(d->flux);
   if (std::is_same<FT, double>::value) {
     // NE_B200_FORCE_GENERIC=1 routes the default tree through the generic kernel (used by the parity tests)
-    if (fast_path_eligible(d->flux, d->properties, d->thermo) && !env_flag("NE_B200_FORCE_GENERIC")) {
+    // the default tree with the Edson functions, or with any other pair of the shipped stability functions whose
+    // tables verify (Large–Yeager: Split(LinearStable, Paulson); SHEBA; …) — the latter only on the table kernel
+    const bool edson = fast_path_eligible(d->flux, d->properties, d->thermo);
+    const bool other_psi = !edson && default_roughness_gustiness(d->flux) && tab_path_eligible(d->flux) &&
+                           d->properties.temperature_formulation == NE_TEMP_BULK && !env_flag("NE_B200_CLOSED_FORM_PSI");
+    const SolverTables* other_tabs = other_psi && !env_flag("NE_B200_FORCE_GENERIC") ? solver_tables(d->flux) : nullptr;
+    if ((edson || other_tabs) && !env_flag("NE_B200_FORCE_GENERIC")) {
       Layout L = make_layout(d->grid);
       FastParams P = make_fast_params(d->flux, d->gravitational_acceleration);
       const int64_t n = (int64_t)L.ni * L.nj;
       // NE_B200_CLOSED_FORM_PSI=1 keeps the libdevice closed-form iteration (parity-tested both ways)
-      const SolverTables* tabs = env_flag("NE_B200_CLOSED_FORM_PSI") || !tab_path_eligible(d->flux) ? nullptr : solver_tables(d->flux);
+      const SolverTables* tabs = other_tabs ? other_tabs
+          : (env_flag("NE_B200_CLOSED_FORM_PSI") || !tab_path_eligible(d->flux) ? nullptr : solver_tables(d->flux));
       // Float64: the work-queue kernel (opt-in, NE_B200_QUEUE=1) does not beat the one-thread-per-point kernel on
       // B200 (1.78 vs 1.73 ms on C4: the trip counts only spread 7–24 and the desynchronised warps cost more in
       // instruction-cache misses and exposed load latency than the denser rounds save, profiles/r01_notes.md)

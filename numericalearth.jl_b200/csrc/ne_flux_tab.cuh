@@ -376,7 +376,8 @@ __device__ __forceinline__ void tab_iteration(const FastParams& P, const FrontF3
 
 // compute_interface_state.jl:10-18: the first trip always runs; then until drift < tol or it ≥ maxiter
 // (FixedIterations: exactly maxiter trips)
-__device__ __forceinline__ int tab_solve(const FastParams& P, const TabParams& T, const double* tab, FastPoint& s) {
+__device__ __forceinline__ int tab_solve(const FastParams& P, const TabParams& T, const double* tab, FastPoint& s,
+                                         const NeFluxFormulation* ff = nullptr) {
   if (P.fixed && P.maxiter <= 0) return 0;
   const double tol = P.fixed ? -1.0 : P.tol;   // drift ≥ 0 > −1: never "converged" under FixedIterations
   const int maxiter = P.maxiter;
@@ -384,7 +385,7 @@ __device__ __forceinline__ int tab_solve(const FastParams& P, const TabParams& T
   double drift;
   do {
     const double pu = s.ustar, pt = s.theta_star, pq = s.q_star;
-    tab_iteration(P, T, tab, s);
+    tab_iteration(P, T, tab, s, ff);
     drift = fabs(s.ustar - pu) + fabs(s.theta_star - pt) + fabs(s.q_star - pq);
     ++it;
   } while (!(drift < tol) && it < maxiter);
