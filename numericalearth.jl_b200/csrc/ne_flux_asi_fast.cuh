@@ -163,7 +163,7 @@ struct AsiProblem {
     f.dtheta = s.theta_a - s.Ts;
     f.dq = s.aq - qs;
     f.ustar = s.ustar; f.theta_star = s.theta_star; f.q_star = s.q_star;
-    tab_iteration(p.P, p.T, tab, f, p.T.general_psi ? &p.d.flux : nullptr);
+    tab_iteration<true>(p.P, p.T, tab, f, p.T.general_psi ? &p.d.flux : nullptr);
     const FT drift = fabs(f.ustar - s.ustar) + fabs(f.theta_star - s.theta_star) + fabs(f.q_star - s.q_star);
     s.ustar = f.ustar; s.theta_star = f.theta_star; s.q_star = f.q_star;
     return drift;
@@ -176,18 +176,30 @@ struct AsiProblem {
 
 // the roughness / gustiness / profile part of the default tree (shared with the a–o eligibility test)
 inline bool default_roughness_gustiness(const NeFluxFormulation& f) {
-  if (f.kind != NE_FLUX_SIMILARITY_THEORY || f.similarity_form != NE_PROFILE_LOGARITHMIC) return false;
+  if (f.kind != NE_FLUX_SIMILARITY_THEORY) return false;
+  if (f.similarity_form != NE_PROFILE_LOGARITHMIC) return false;
   if (std::memcmp(&f.psi_temperature, &f.psi_water_vapor, sizeof(NeStabilityProfile)) != 0) return false;
   if (std::memcmp(&f.ell_temperature, &f.ell_water_vapor, sizeof(NeRoughnessLength)) != 0) return false;
   const NeRoughnessLength& m = f.ell_momentum;
   const NeRoughnessLength& s = f.ell_temperature;
-  if (m.kind != NE_ROUGH_MOMENTUM || m.wave_kind != NE_WAVE_CONSTANT || m.visc_kind != NE_VISC_CONSTANT) return false;
+  if (m.kind != NE_ROUGH_MOMENTUM || m.visc_kind != NE_VISC_CONSTANT) return false;
+  if (m.wave_kind != NE_WAVE_CONSTANT && m.wave_kind != NE_WAVE_WIND_DEPENDENT) return false;
   if (s.kind != NE_ROUGH_SCALAR || s.visc_kind != NE_VISC_CONSTANT || s.nu != m.nu) return false;
   if (!(m.nu > 0) || !(s.reynolds_A > 0) || !(s.maximum_roughness_length > 0) || !(m.maximum_roughness_length > 0)) return false;
-  if (!(m.smooth_wall_parameter > 0) && !(m.wave_constant > 0)) return false;
+  if (!(m.gravitational_acceleration > 0)) return false;
+  // ℓu must stay positive: a smooth-wall term, or a wave term that cannot vanish
+  if (!(m.smooth_wall_parameter > 0) && !(m.wave_kind == NE_WAVE_CONSTANT && m.wave_constant > 0)) return false;
   const NeSubgridVelocity& g = f.subgrid_velocities;
-  if (g.composite || g.convective_kind != NE_SGS_CONVECTIVE || !(g.minimum_gustiness > 0)) return false;
+  if (g.convective_kind != NE_SGS_CONVECTIVE || !(g.minimum_gustiness > 0)) return false;
+  if (g.composite && g.mesoscale_kind != NE_SGS_NONE && g.mesoscale_kind != NE_SGS_CONSTANT) return false;
   return true;
+}
+
+// strict default tree: logarithmic profile, constant wave parameter, no mesoscale term (the EXT = false kernels)
+inline bool strict_default_options(const NeFluxFormulation& f) {
+  const NeSubgridVelocity& g = f.subgrid_velocities;
+  return f.similarity_form == NE_PROFILE_LOGARITHMIC && f.ell_momentum.wave_kind == NE_WAVE_CONSTANT &&
+         !(g.composite && g.mesoscale_kind == NE_SGS_CONSTANT && g.mesoscale_constant != 0.0);
 }
 
 inline bool asi_fast_path_eligible(const NeFluxFormulation& f, const NeInterfaceProperties& ip) {

@@ -38,6 +38,11 @@ struct FastParams {
   double kappa, d_zero, g;
   double tol;
   int32_t maxiter, fixed;
+  // options of the table kernels beyond the strict default tree (all off for it)
+  int32_t wind_waves;       // WindDependentWaveFormulation: 𝒞g = max(0, C1 min(U, Umax) + C2) (roughness_lengths.jl:75)
+  double wave_C1, wave_C2, wave_Umax, inv_g_rough;
+  double sgs_const2;        // SubgridVelocityCorrection: constant mesoscale term, already squared (:88-98)
+  int32_t pad_opt_;
   // small-|ζ| unstable branch: ψ(ζ) ≈ Σ c_k (ζ/ζs)^k on [-ζs, 0], fitted on the host at Chebyshev nodes in
   // long double from the closed forms (max abs error ≲ 2e-16, checked at fit time; zsmall = 0 disables it)
   double zsmall, zsmall_inv;
@@ -168,6 +173,15 @@ inline FastParams make_fast_params(const NeFluxFormulation& f, double g, bool f3
   P.beta = R(f.subgrid_velocities.gustiness_parameter); P.gmin = R(f.subgrid_velocities.minimum_gustiness);
   P.kappa = R(f.von_karman_constant); P.d_zero = R(f.zero_plane_displacement); P.g = R(g);
   P.tol = R(f.stop.tolerance); P.maxiter = f.stop.maxiter; P.fixed = f.stop.kind == NE_STOP_FIXED_ITERATIONS;
+  P.pad_opt_ = 0;
+  P.wind_waves = m.wave_kind == NE_WAVE_WIND_DEPENDENT;
+  P.wave_C1 = R(m.wave_C1); P.wave_C2 = R(m.wave_C2); P.wave_Umax = R(m.wave_Umax);
+  P.inv_g_rough = 1.0 / R(m.gravitational_acceleration);
+  {
+    const NeSubgridVelocity& sg = f.subgrid_velocities;
+    const double c = (sg.composite && sg.mesoscale_kind == NE_SGS_CONSTANT) ? R(sg.mesoscale_constant) : 0.0;
+    P.sgs_const2 = c * c;
+  }
   // the small-|ζ| polynomial belongs to the closed-form kernel only: see add_small_zeta_poly
   P.zsmall = 0; P.zsmall_inv = 0;
   for (int k = 0; k <= NE_FAST_PSI_DEG; ++k) { P.pm[k] = 0; P.ps[k] = 0; }

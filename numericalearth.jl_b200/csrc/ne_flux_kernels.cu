@@ -107,7 +107,7 @@ ao_flux_fast_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
 // Register budget: only the 9 per-point invariants and the 3-component iterate live across the loop; the
 // atmosphere state needed by the flux epilogue is re-read from global memory (L2 hits) after the solve.
 // HS: surface-layer and boundary-layer heights are scalars (PrescribedAtmosphere default) → uniform.
-template <class CT, int MINB, bool HS>
+template <class CT, int MINB, bool HS, bool EXT>
 __global__ void __launch_bounds__(256, MINB)
 ao_flux_tab_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_constant__ Layout L,
                    const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P,
@@ -154,7 +154,7 @@ ao_flux_tab_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_cons
         s.dq = aq - qs;
         s.ustar = s.theta_star = s.q_star = 1e-4;
       }
-      iters = tab_solve(P, T, tab, s, T.general_psi ? &d.flux : nullptr);
+      iters = tab_solve<EXT>(P, T, tab, s, T.general_psi ? &d.flux : nullptr);
       ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
     }
     // epilogue (atmosphere_ocean_fluxes.jl:160-196): atmosphere state re-read
@@ -306,7 +306,7 @@ ao_fused_tab_kernel(const __grid_constant__ NeInterpDesc atm, const __grid_const
         s.dtheta = (aT + P.g * az / th.cp_m(aq)) - To;
         s.dq = aq - qs;
         s.ustar = s.theta_star = s.q_star = 1e-4;
-        iters = tab_solve(P, T, tab, s);
+        iters = tab_solve<false>(P, T, tab, s);
         ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
       }
     }
@@ -617,7 +617,8 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
       // Float64: the work-queue kernel (opt-in, NE_B200_QUEUE=1) does not beat the one-thread-per-point kernel on
       // B200 (1.78 vs 1.73 ms on C4: the trip counts only spread 7–24 and the desynchronised warps cost more in
       // instruction-cache misses and exposed load latency than the denser rounds save, profiles/r01_notes.md)
-      if (tabs && env_flag("NE_B200_QUEUE") && queue_path_ok(d->grid))
+      const bool ext = !strict_default_options(d->flux);
+      if (tabs && env_flag("NE_B200_QUEUE") && queue_path_ok(d->grid) && !ext)
         return ct64 ? launch_queue<double, double>(*d, tabs, s) : launch_queue<double, float>(*d, tabs, s);
       if (tabs) {
         const int tminb = tab_minb();
@@ -625,21 +626,28 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
         const bool hs = !d->surface_layer_height.ptr && !d->boundary_layer_height.ptr;
         TabParams TP = tabs->T;
         TP.log_hd = std::log(d->surface_layer_height.value - P.d_zero);
-#define NE_LAUNCH_TAB2(MB, HS)                                                                                          \
+#define NE_LAUNCH_TAB3(MB, HS, EXT)                                                                                          \
   do {                                                                                                                  \
-    if (ct64) ao_flux_tab_kernel<double, MB, HS><<<tb, 256, 0, s>>>(*d, L, Thermo<double>::make(d->thermo), P, TP, tabs->dptr); \
-    else ao_flux_tab_kernel<float, MB, HS><<<tb, 256, 0, s>>>(*d, L, Thermo<float>::make(d->thermo), P, TP, tabs->dptr);        \
+    if (ct64) ao_flux_tab_kernel<double, MB, HS, EXT><<<tb, 256, 0, s>>>(*d, L, Thermo<double>::make(d->thermo), P, TP, tabs->dptr); \
+    else ao_flux_tab_kernel<float, MB, HS, EXT><<<tb, 256, 0, s>>>(*d, L, Thermo<float>::make(d->thermo), P, TP, tabs->dptr);        \
+  } while (0)
+#define NE_LAUNCH_TAB2(MB, HS)          \
+  do {                                  \
+    if (ext) NE_LAUNCH_TAB3(MB, HS, true); \
+    else NE_LAUNCH_TAB3(MB, HS, false);    \
   } while (0)
 #define NE_LAUNCH_TAB(MB)          \
   do {                             \
     if (hs) NE_LAUNCH_TAB2(MB, true); \
     else NE_LAUNCH_TAB2(MB, false);   \
   } while (0)
-        if (tminb == 2) NE_LAUNCH_TAB(2);
+        if (ext) NE_LAUNCH_TAB(3);   // the option kernels are built at the default occupancy only
+        else if (tminb == 2) NE_LAUNCH_TAB(2);
         else if (tminb == 4) NE_LAUNCH_TAB(4);
         else NE_LAUNCH_TAB(3);
 #undef NE_LAUNCH_TAB
 #undef NE_LAUNCH_TAB2
+#undef NE_LAUNCH_TAB3
         NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(tab)");
         return NE_OK;
       }

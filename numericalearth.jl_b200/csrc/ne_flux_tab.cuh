@@ -276,6 +276,11 @@ __device__ __noinline__ double2 tab_psi_pair_rare(const FastParams& P, const Tab
 // The Float64 core shared by the Float64 and the mixed-precision Float32 iterations: roughness lengths, the
 // two logarithmic profiles with their ψ corrections and the transfer coefficients χ = ϰ/Π.
 //   u★ (as a double), ru = 1/u★, ℓu (already clipped), 1/L★, Δh = z − d and log Δh  →  χ_u, χ_s
+// EXT: the options beyond the strict default tree (wind-dependent waves, constant mesoscale term) and a domain guard —
+// compiled out of the default-tree kernels, whose iterates stay positive.  (The COARE profile stays on the generic
+// kernel: without the ψ(ℓ/L★) term Π changes sign on the way from the 1e-4 initial guess at ~1 % of the points, and
+// what the reference then does with negative roughness lengths and NaNs is not worth imitating in a fast path.)
+template <bool EXT = false>
 __device__ __forceinline__ void tab_core(const FastParams& P, const TabParams& T, const double* tab, double ustar,
                                          double ru, double lu, double Linv, double hd, double log_hd,
                                          double& chi_u, double& chi_s, const NeFluxFormulation* ff = nullptr) {
@@ -283,7 +288,8 @@ __device__ __forceinline__ void tab_core(const FastParams& P, const TabParams& T
   (void)ru;
   const double log_lu = fm::log_pos(tab, T.mc, lu);
   using fm::mul_;
-  const double log_Rs = fm::log_pos(tab, T.mc, mul_(mul_(lu, ustar), P.nu_inv));
+  const double Rs = mul_(mul_(lu, ustar), P.nu_inv);
+  const double log_Rs = fm::log_pos(tab, T.mc, Rs);
   const double log_ls_un = fm::fma_(-P.rb, log_Rs, P.log_rA);
   const bool clipped = log_ls_un > P.log_ls_max;
   const double log_ls = clipped ? P.log_ls_max : log_ls_un;
@@ -311,8 +317,14 @@ __device__ __forceinline__ void tab_core(const FastParams& P, const TabParams& T
   chi_u = mul_(P.kappa, ru_); chi_s = mul_(P.kappa, rs_);
   chi_u = fm::fma_(fm::fma_(-Pi_u, chi_u, P.kappa), ru_, chi_u);
   chi_s = fm::fma_(fm::fma_(-Pi_s, chi_s, P.kappa), rs_, chi_s);
+  if (EXT) {
+    // Outside the domain of the branch-free log (a non-positive ℓu or R★: an iterate that went through Π ≤ 0, which
+    // the non-default profiles allow) the reference's log / pow return NaN and the point stays NaN: do the same.
+    if (!((lu > 0.0) & (Rs > 0.0))) { chi_u = __longlong_as_double(0x7ff8000000000000LL); chi_s = chi_u; }
+  }
 }
 
+template <bool EXT = false>
 __device__ __forceinline__ void tab_iteration(const FastParams& P, const TabParams& T, const double* tab, FastPoint& s,
                                               const NeFluxFormulation* ff = nullptr) {
   using fm::dmax;
@@ -323,12 +335,14 @@ __device__ __forceinline__ void tab_iteration(const FastParams& P, const TabPara
   const double bstar = mul_(s.gTv, fma_(s.theta_star, s.c1, mul_(s.c2, s.q_star)));
   const double Jb = -mul_(s.ustar, bstar);
   const double UG = dmax(P.gmin, mul_(P.beta, fm::cbrt_pos(T.mc, dmax(mul_(dmax(0.0, Jb), s.h_bl), T.cbrt_floor))));
-  const double U = fm::sqrt_pos(fma_(UG, UG, s.dudv2));
+  const double U = fm::sqrt_pos(EXT ? fma_(UG, UG, s.dudv2) + P.sgs_const2 : fma_(UG, UG, s.dudv2));
   const double ru = fm::rcp(s.ustar);
-  const double lu = dmin(fma_(mul_(P.a1, s.ustar), s.ustar, mul_(P.a2, ru)), P.lmax);
+  // 𝒞g/g: constant, or WindDependentWaveFormulation (roughness_lengths.jl:75) with the gusty wind speed U
+  const double a1 = (EXT && P.wind_waves) ? mul_(dmax(0.0, fma_(P.wave_C1, dmin(U, P.wave_Umax), P.wave_C2)), P.inv_g_rough) : P.a1;
+  const double lu = dmin(fma_(mul_(a1, s.ustar), s.ustar, mul_(P.a2, ru)), P.lmax);
   const double Linv = mul_(mul_(mul_(P.kappa, bstar), ru), ru);   // 1/L★ (0 when b★ == 0, i.e. L★ = Inf)
   double chi_u, chi_s;
-  tab_core(P, T, tab, s.ustar, ru, lu, Linv, s.hd, s.log_hd, chi_u, chi_s, ff);
+  tab_core<EXT>(P, T, tab, s.ustar, ru, lu, Linv, s.hd, s.log_hd, chi_u, chi_s, ff);
   s.ustar = mul_(chi_u, U);
   s.theta_star = mul_(chi_s, s.dtheta);
   s.q_star = mul_(chi_s, s.dq);
@@ -368,7 +382,7 @@ __device__ __forceinline__ void tab_iteration(const FastParams& P, const FrontF3
   const float aL = fabsf(Lstar);
   const double Linv = (aL < 3.0e38f) ? ((aL > 1.0e-30f) ? fm::rcp((double)Lstar) : 1.0 / (double)Lstar) : 0.0;
   double chi_u, chi_s;
-  tab_core(P, T, tab, ud, ru, lu, Linv, (double)s.hd, s.log_hd, chi_u, chi_s);
+  tab_core<false>(P, T, tab, ud, ru, lu, Linv, (double)s.hd, s.log_hd, chi_u, chi_s);
   s.ustar = (float)fm::mul_(chi_u, (double)U);
   s.theta_star = (float)fm::mul_(chi_s, (double)s.dtheta);
   s.q_star = (float)fm::mul_(chi_s, (double)s.dq);
@@ -376,6 +390,7 @@ __device__ __forceinline__ void tab_iteration(const FastParams& P, const FrontF3
 
 // compute_interface_state.jl:10-18: the first trip always runs; then until drift < tol or it ≥ maxiter
 // (FixedIterations: exactly maxiter trips)
+template <bool EXT = false>
 __device__ __forceinline__ int tab_solve(const FastParams& P, const TabParams& T, const double* tab, FastPoint& s,
                                          const NeFluxFormulation* ff = nullptr) {
   if (P.fixed && P.maxiter <= 0) return 0;
@@ -385,7 +400,7 @@ __device__ __forceinline__ int tab_solve(const FastParams& P, const TabParams& T
   double drift;
   do {
     const double pu = s.ustar, pt = s.theta_star, pq = s.q_star;
-    tab_iteration(P, T, tab, s, ff);
+    tab_iteration<EXT>(P, T, tab, s, ff);
     drift = fabs(s.ustar - pu) + fabs(s.theta_star - pt) + fabs(s.q_star - pq);
     ++it;
   } while (!(drift < tol) && it < maxiter);

@@ -160,6 +160,12 @@ VARIANTS = {
                                                                   air_kinematic_viscosity=ne_b200.TemperatureDependentAirViscosity()),
         temperature_roughness_length=ne_b200.ScalarRoughnessLength(air_kinematic_viscosity=ne_b200.TemperatureDependentAirViscosity()),
         water_vapor_roughness_length=ne_b200.ScalarRoughnessLength(air_kinematic_viscosity=ne_b200.TemperatureDependentAirViscosity()))),
+    "wind_dependent_waves": dict(atmosphere_ocean_fluxes=lambda: ne_b200.SimilarityTheoryFluxes(
+        momentum_roughness_length=ne_b200.MomentumRoughnessLength(wave_formulation=ne_b200.WindDependentWaveFormulation()))),
+    "large_yeager_psi_mesoscale_wind_waves": dict(atmosphere_ocean_fluxes=lambda: ne_b200.SimilarityTheoryFluxes(
+        stability_functions=ne_b200.large_yeager_stability_functions(),
+        subgrid_velocities=ne_b200.SubgridVelocityCorrection(mesoscale=ne_b200.mahrt_sun_subgrid_velocity(100e3)),
+        momentum_roughness_length=ne_b200.MomentumRoughnessLength(wave_formulation=ne_b200.WindDependentWaveFormulation()))),
     "constant_roughness_no_gustiness_neutral": dict(atmosphere_ocean_fluxes=lambda: ne_b200.SimilarityTheoryFluxes(
         stability_functions=None, subgrid_velocities=None, momentum_roughness_length=1e-4,
         temperature_roughness_length=1e-4, water_vapor_roughness_length=1e-4)),
