@@ -154,7 +154,7 @@ ao_flux_tab_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_cons
         s.dq = aq - qs;
         s.ustar = s.theta_star = s.q_star = 1e-4;
       }
-      iters = tab_solve<EXT>(P, T, tab, s, T.general_psi ? &d.flux : nullptr);
+      iters = tab_solve<EXT>(P, T, tab, s, (EXT && T.general_psi) ? &d.flux : nullptr);   // non-Edson tables: EXT build only
       ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
     }
     // epilogue (atmosphere_ocean_fluxes.jl:160-196): atmosphere state re-read
@@ -617,7 +617,7 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
       // Float64: the work-queue kernel (opt-in, NE_B200_QUEUE=1) does not beat the one-thread-per-point kernel on
       // B200 (1.78 vs 1.73 ms on C4: the trip counts only spread 7–24 and the desynchronised warps cost more in
       // instruction-cache misses and exposed load latency than the denser rounds save, profiles/r01_notes.md)
-      const bool ext = !strict_default_options(d->flux);
+      const bool ext = !strict_default_options(d->flux) || (tabs && tabs->T.general_psi);
       if (tabs && env_flag("NE_B200_QUEUE") && queue_path_ok(d->grid) && !ext)
         return ct64 ? launch_queue<double, double>(*d, tabs, s) : launch_queue<double, float>(*d, tabs, s);
       if (tabs) {
