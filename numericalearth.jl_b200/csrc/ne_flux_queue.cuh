@@ -176,7 +176,7 @@ struct AoProblem {
   __device__ static __forceinline__ FT trip(const Params& p, const double* tab, Point& s, int) {
     const FT pu = s.ustar, pt = s.theta_star, pq = s.q_star;
     if constexpr (std::is_same<FT, float>::value) tab_iteration(p.P, p.Q, p.T, tab, s);
-    else tab_iteration<false>(p.P, p.T, tab, s, p.T.general_psi ? &p.d.flux : nullptr);
+    else tab_iteration<false>(p.P, p.T, tab, s, nullptr);   // strict default tree only (dispatch: ne_flux_kernels.cu)
     return m_abs(s.ustar - pu) + m_abs(s.theta_star - pt) + m_abs(s.q_star - pq);
   }
   __device__ static __forceinline__ void finish(const Params& p, int32_t idx, const Point& s, int it) {
