@@ -20,20 +20,21 @@
 
 namespace ne {
 
+template <class FT>
 struct AsiPoint {
   // invariants
-  double theta_a, dudv2, h_bl, hd, log_hd;
-  double ap, aq;
-  double rho_c, rho_L;        // ρₐ cₚₘ, ρₐ ℒˢ
-  double Qd, R, Tb, sig_eps;
+  FT theta_a, dudv2, h_bl, hd;
+  double log_hd;
+  FT ap, aq;
+  FT rho_c, rho_L;            // ρₐ cₚₘ, ρₐ ℒˢ
+  FT Qd, R, Tb, sig_eps;
   // iterate
-  double ustar, theta_star, q_star, Ts;
+  FT ustar, theta_star, q_star, Ts;
 };
 
-template <class CT>
+template <class FT, class CT>
 __device__ __noinline__ void asi_write_outputs(const NeAtmosSeaIceDesc& d, const Thermo<CT>& th, int64_t idx,
-                                               double ustar, double theta_star, double q_star, double Ts, int iters) {
-  using FT = double;
+                                               FT ustar, FT theta_star, FT q_star, FT Ts, int iters) {
   AtmosState<FT> a;
   a.u = __ldg((const FT*)d.ua + idx);
   a.v = __ldg((const FT*)d.va + idx);
@@ -47,29 +48,36 @@ __device__ __noinline__ void asi_write_outputs(const NeAtmosSeaIceDesc& d, const
   ((FT*)d.water_vapor)[idx] = e.Jv;
   ((FT*)d.x_momentum)[idx] = e.tx;
   ((FT*)d.y_momentum)[idx] = e.ty;
-  ((FT*)d.interface_temperature)[idx] = d.sea_ice.temperature_units == NE_DEGREES_CELSIUS ? Ts - 273.15 : Ts;
+  ((FT*)d.interface_temperature)[idx] = d.sea_ice.temperature_units == NE_DEGREES_CELSIUS ? Ts - (FT)273.15 : Ts;
   if (d.iterations) d.iterations[idx] = iters;
 }
 
-template <class CT, bool HS>
+// FT = double: Float64 model.  FT = float: Float32 model with Float32 thermodynamics and the Float64-literal viscosity —
+// skin temperature and q_sat in Float32, the similarity step mixed precision exactly as in the a–o Float32 kernel
+// (tab_iteration(…, FastPointF&), ne_flux_tab.cuh).
+template <class FT_, class CT, bool HS>
 struct AsiProblem {
-  using FT = double;
-  using Point = AsiPoint;
+  using FT = FT_;
+  using Point = AsiPoint<FT>;
   static constexpr int NSTATE = 4;
+  static constexpr bool F32 = std::is_same<FT, float>::value;
   struct Params {
     NeAtmosSeaIceDesc d;
     Layout L;
     Thermo<CT> th;
     FastParams P;
     TabParams T;
+    FrontF32 Q;
   };
   __device__ static __forceinline__ const Layout& layout(const Params& p) { return p.L; }
   __device__ static __forceinline__ const FastParams& fast(const Params& p) { return p.P; }
-  __device__ static __forceinline__ FT tolerance(const Params& p) { return p.P.tol; }
+  __device__ static __forceinline__ FT tolerance(const Params& p) { return F32 ? (FT)p.Q.tol : (FT)p.P.tol; }
+  __device__ static __forceinline__ FT gravity(const Params& p) { return F32 ? (FT)p.Q.g : (FT)p.P.g; }
+  __device__ static __forceinline__ FT zero_plane(const Params& p) { return F32 ? (FT)p.Q.d_zero : (FT)p.P.d_zero; }
 
   __device__ static __forceinline__ FT initial_Ts(const Params& p, int32_t idx) {
     FT Ts0 = ((const FT*)p.d.interface_temperature)[idx];
-    if (p.d.sea_ice.temperature_units == NE_DEGREES_CELSIUS) Ts0 = Ts0 + 273.15;
+    if (p.d.sea_ice.temperature_units == NE_DEGREES_CELSIUS) Ts0 = Ts0 + (FT)273.15;
     return Ts0;
   }
 
@@ -79,13 +87,13 @@ struct AsiProblem {
     const bool ice_free = slot_at<FT>(d.concentration, idx) == 0;
     if ((!p.P.fixed && not_water) || ice_free) {   // :141-142: zero scales, Tₛ = ocean surface temperature
       FT To = slot_at<FT>(d.To, idx);
-      if (d.ocean.temperature_units == NE_DEGREES_CELSIUS) To = To + 273.15;
-      asi_write_outputs<CT>(d, p.th, idx, 0.0, 0.0, 0.0, To, 0);
+      if (d.ocean.temperature_units == NE_DEGREES_CELSIUS) To = To + (FT)273.15;
+      asi_write_outputs<FT, CT>(d, p.th, idx, (FT)0, (FT)0, (FT)0, To, 0);
       return false;
     }
     if (p.P.fixed && p.P.maxiter <= 0) {           // no trip: the initial state (:127-131)
       const FT x0 = (FT)1e-4f;
-      asi_write_outputs<CT>(d, p.th, idx, x0, x0, x0, initial_Ts(p, idx), 0);
+      asi_write_outputs<FT, CT>(d, p.th, idx, x0, x0, x0, initial_Ts(p, idx), 0);
       return false;
     }
     return true;
@@ -97,11 +105,11 @@ struct AsiProblem {
     const FT au = __ldg((const FT*)d.ua + idx), av = __ldg((const FT*)d.va + idx);
     const FT aT = __ldg((const FT*)d.Ta + idx), ap = __ldg((const FT*)d.pa + idx), aq = __ldg((const FT*)d.qa + idx);
     const FT az = HS ? (FT)d.surface_layer_height.value : slot_at<FT>(d.surface_layer_height, idx);
-    s.theta_a = aT + p.P.g * az / th.cp_m(aq);        // surface_atmosphere_temperature interface_states.jl:308-317
+    s.theta_a = aT + gravity(p) * az / th.cp_m(aq);   // surface_atmosphere_temperature interface_states.jl:308-317
     s.dudv2 = au * au + av * av;                      // ice velocity forced to 0 (:97-98)
     s.h_bl = HS ? (FT)d.boundary_layer_height.value : slot_at<FT>(d.boundary_layer_height, idx);
-    s.hd = az - p.P.d_zero;
-    s.log_hd = HS ? p.T.log_hd : log(s.hd);
+    s.hd = az - zero_plane(p);
+    s.log_hd = HS ? p.T.log_hd : log((double)s.hd);
     s.ap = ap; s.aq = aq;
     const auto rho_a = th.air_density(aT, ap, aq);
     s.rho_c = rho_a * th.cp_m(aq);
@@ -115,9 +123,9 @@ struct AsiProblem {
     if (ip.temperature_formulation == NE_TEMP_SKIN_CONDUCTIVE) s.R = hi / (FT)ip.ice_conductivity;
     else s.R = slot_at<FT>(d.hs, idx) / (FT)ip.snow_conductivity + hi / (FT)ip.ice_conductivity;
     FT Tb = (FT)d.sea_ice.liquidus_freshwater_melting_temperature - (FT)d.sea_ice.liquidus_slope * slot_at<FT>(d.So, idx);
-    if (d.sea_ice.temperature_units == NE_DEGREES_CELSIUS) Tb = Tb + 273.15;
+    if (d.sea_ice.temperature_units == NE_DEGREES_CELSIUS) Tb = Tb + (FT)273.15;
     s.Tb = Tb;
-    if (!(hi >= hc)) s.R = -1.0;                      // thin ice: Tₛ = T_b whatever the balance says (:505-507)
+    if (!(hi >= hc)) s.R = (FT)-1;                    // thin ice: Tₛ = T_b whatever the balance says (:505-507)
     if (fresh) {
       s.ustar = s.theta_star = s.q_star = (FT)1e-4f;  // convert(FT, 1f-4) :127
       s.Ts = initial_Ts(p, idx);
@@ -131,14 +139,14 @@ struct AsiProblem {
     const NeInterfaceProperties& ip = p.d.properties;
     const FT Tsm = s.Ts;
     FT Tm = (FT)p.d.sea_ice.liquidus_freshwater_melting_temperature;
-    if (p.d.sea_ice.temperature_units == NE_DEGREES_CELSIUS) Tm = Tm + 273.15;
+    if (p.d.sea_ice.temperature_units == NE_DEGREES_CELSIUS) Tm = Tm + (FT)273.15;
     if (s.R < 0) return s.Tb;
     const FT lw_up = s.sig_eps * pow4(Tsm);
     const FT QT = -s.rho_c * s.ustar * s.theta_star;
     const FT Qv = -s.rho_L * s.ustar * s.q_star;
     const FT dT = s.theta_a - Tsm;
     const FT Qa = Qv + lw_up + s.Qd;
-    const FT Oc = (dT == 0) ? 0.0 : QT / dT;
+    const FT Oc = (dT == 0) ? (FT)0 : QT / dT;
     const FT beta = 4 * lw_up / Tsm;
     const FT R = s.R;
     const FT D = 1 + beta * R - Oc * R;
@@ -154,23 +162,25 @@ struct AsiProblem {
     const NeInterfaceProperties& ip = p.d.properties;
     if (ip.temperature_formulation != NE_TEMP_BULK) s.Ts = skin_temperature(p, s);
     const FT qs = surface_specific_humidity<FT, CT>(ip, p.th, s.ap, s.Ts, (FT)0);   // humidity scalar 0 over ice (:737)
-    FastPoint f;
     const FT Tv = p.th.virtual_temperature(s.Ts, qs);
-    f.gTv = p.P.g / Tv;
+    typename QPointOf<FT>::type f;
+    f.gTv = gravity(p) / Tv;
     f.c1 = 1 + p.th.delta * qs;
     f.c2 = p.th.delta * Tv;
     f.dudv2 = s.dudv2; f.h_bl = s.h_bl; f.hd = s.hd; f.log_hd = s.log_hd;
     f.dtheta = s.theta_a - s.Ts;
     f.dq = s.aq - qs;
     f.ustar = s.ustar; f.theta_star = s.theta_star; f.q_star = s.q_star;
-    tab_iteration<true>(p.P, p.T, tab, f, p.T.general_psi ? &p.d.flux : nullptr);
-    const FT drift = fabs(f.ustar - s.ustar) + fabs(f.theta_star - s.theta_star) + fabs(f.q_star - s.q_star);
+    const NeFluxFormulation* ff = p.T.general_psi ? &p.d.flux : nullptr;
+    if constexpr (F32) tab_iteration(p.P, p.Q, p.T, tab, f, ff);
+    else tab_iteration<true>(p.P, p.T, tab, f, ff);
+    const FT drift = m_abs(f.ustar - s.ustar) + m_abs(f.theta_star - s.theta_star) + m_abs(f.q_star - s.q_star);
     s.ustar = f.ustar; s.theta_star = f.theta_star; s.q_star = f.q_star;
     return drift;
   }
 
   __device__ static __forceinline__ void finish(const Params& p, int32_t idx, const Point& s, int it) {
-    asi_write_outputs<CT>(p.d, p.th, idx, s.ustar, s.theta_star, s.q_star, s.Ts, it);
+    asi_write_outputs<FT, CT>(p.d, p.th, idx, s.ustar, s.theta_star, s.q_star, s.Ts, it);
   }
 };
 

@@ -491,16 +491,16 @@ static bool queue_path_ok(const NeExchangeGrid& g) {
   return parent < ((int64_t)1 << 31);
 }
 
-static FrontF32 make_front_f32(const NeAtmosOceanDesc& d) {
+static FrontF32 make_front_f32(const NeFluxFormulation& flux, double gravitational_acceleration) {
   FrontF32 Q;
-  Q.gmin = (float)d.flux.subgrid_velocities.minimum_gustiness;
-  Q.beta = (float)d.flux.subgrid_velocities.gustiness_parameter;
-  Q.Cg = (float)d.flux.ell_momentum.wave_constant;
-  Q.g_rough = (float)d.flux.ell_momentum.gravitational_acceleration;
-  Q.kappa = (float)d.flux.von_karman_constant;
-  Q.tol = (float)d.flux.stop.tolerance;
-  Q.g = (float)d.gravitational_acceleration;
-  Q.d_zero = (float)d.flux.zero_plane_displacement;
+  Q.gmin = (float)flux.subgrid_velocities.minimum_gustiness;
+  Q.beta = (float)flux.subgrid_velocities.gustiness_parameter;
+  Q.Cg = (float)flux.ell_momentum.wave_constant;
+  Q.g_rough = (float)flux.ell_momentum.gravitational_acceleration;
+  Q.kappa = (float)flux.von_karman_constant;
+  Q.tol = (float)flux.stop.tolerance;
+  Q.g = (float)gravitational_acceleration;
+  Q.d_zero = (float)flux.zero_plane_displacement;
   return Q;
 }
 
@@ -551,7 +551,7 @@ static int launch_queue_hs(const NeAtmosOceanDesc& d, const SolverTables* tabs, 
   prm.L = make_layout(d.grid);
   prm.th = Thermo<CT>::make(d.thermo);
   prm.P = make_fast_params(d.flux, d.gravitational_acceleration, f32);
-  prm.Q = make_front_f32(d);
+  prm.Q = make_front_f32(d.flux, d.gravitational_acceleration);
   prm.T = tabs->T;
   prm.T.log_hd = f32 ? std::log((double)((float)d.surface_layer_height.value - prm.Q.d_zero))
                      : std::log(d.surface_layer_height.value - prm.P.d_zero);
@@ -569,16 +569,19 @@ static int launch_queue(const NeAtmosOceanDesc& d, const SolverTables* tabs, cud
 }
 
 // atmosphere–sea-ice default tree on the work-queue kernel (ne_flux_asi_fast.cuh)
-template <class CT, bool HS>
+template <class FT, class CT, bool HS>
 static int launch_asi_queue_hs(const NeAtmosSeaIceDesc& d, const SolverTables* tabs, cudaStream_t s) {
-  using Problem = AsiProblem<CT, HS>;
+  using Problem = AsiProblem<FT, CT, HS>;
+  const bool f32 = std::is_same<FT, float>::value;
   typename Problem::Params prm;
   prm.d = d;
   prm.L = make_layout(d.grid);
   prm.th = Thermo<CT>::make(d.thermo);
-  prm.P = make_fast_params(d.flux, d.gravitational_acceleration, false);
+  prm.P = make_fast_params(d.flux, d.gravitational_acceleration, f32);
+  prm.Q = make_front_f32(d.flux, d.gravitational_acceleration);
   prm.T = tabs->T;
-  prm.T.log_hd = std::log(d.surface_layer_height.value - prm.P.d_zero);
+  prm.T.log_hd = f32 ? std::log((double)((float)d.surface_layer_height.value - prm.Q.d_zero))
+                     : std::log(d.surface_layer_height.value - prm.P.d_zero);
   uint32_t* counters = queue_counters();
   NE_REQUIRE(counters != nullptr, "atmosphere-sea-ice: could not allocate the work-queue counters");
   const unsigned grid = queue_grid((int64_t)prm.L.ni * prm.L.nj, 4, 4);
@@ -586,10 +589,10 @@ static int launch_asi_queue_hs(const NeAtmosSeaIceDesc& d, const SolverTables* t
   NE_CUDA_CHECK_LAUNCH("ne_atmosphere_sea_ice_fluxes(queue)");
   return NE_OK;
 }
-template <class CT>
+template <class FT, class CT>
 static int launch_asi_queue(const NeAtmosSeaIceDesc& d, const SolverTables* tabs, cudaStream_t s) {
   const bool hs = !d.surface_layer_height.ptr && !d.boundary_layer_height.ptr;
-  return hs ? launch_asi_queue_hs<CT, true>(d, tabs, s) : launch_asi_queue_hs<CT, false>(d, tabs, s);
+  return hs ? launch_asi_queue_hs<FT, CT, true>(d, tabs, s) : launch_asi_queue_hs<FT, CT, false>(d, tabs, s);
 }
 
 template <class FT>
@@ -773,10 +776,18 @@ static int asi_entry(const NeAtmosSeaIceDesc* d, void* stream) {
     if (asi_fast_path_eligible(d->flux, d->properties) && queue_path_ok(d->grid) && !env_flag("NE_B200_FORCE_GENERIC") &&
         !env_flag("NE_B200_CLOSED_FORM_PSI")) {
       const SolverTables* tabs = solver_tables(d->flux, false);
-      if (tabs) return ct64 ? launch_asi_queue<double>(*d, tabs, s) : launch_asi_queue<float>(*d, tabs, s);
+      if (tabs) return ct64 ? launch_asi_queue<double, double>(*d, tabs, s) : launch_asi_queue<double, float>(*d, tabs, s);
     }
     return ct64 ? launch_asi<double, double, double>(*d, s) : launch_asi<double, float, double>(*d, s);
   } else {
+    // Float32 model: the same kernel with the mixed-precision similarity step (Float32 thermodynamics, Float64-literal
+    // viscosity, strict default options)
+    if (!ct64 && viscosity_is_f64_literal(d->flux) && asi_fast_path_eligible(d->flux, d->properties) &&
+        strict_default_options(d->flux) && queue_path_ok(d->grid) && !env_flag("NE_B200_FORCE_GENERIC") &&
+        !env_flag("NE_B200_CLOSED_FORM_PSI")) {
+      const SolverTables* tabs = solver_tables(d->flux, true);
+      if (tabs) return launch_asi_queue<float, float>(*d, tabs, s);
+    }
     if (ct64) return v64 ? launch_asi<float, double, double>(*d, s) : launch_asi<float, double, float>(*d, s);
     return v64 ? launch_asi<float, float, double>(*d, s) : launch_asi<float, float, float>(*d, s);
   }

@@ -20,6 +20,8 @@ struct TabParams {
   double log_hd;         // log(surface_layer_height − d) when the height is a scalar (set per launch)
   int32_t same_exp;      // ψ_m and ψ_s stable branches share exp(−min(ζmax, A⁺ζ))
   int32_t general_psi;   // tables fitted to non-Edson stability functions: outside the table → generic closed forms
+  int32_t f32_model;     // Float32 model: the generic closed forms take the Float32-rounded parameters
+  int32_t pad_;
 };
 
 // ---- host: Chebyshev interpolation → monomials in w ∈ [−1, 1] (long double) -------------------------
@@ -104,6 +106,13 @@ inline long double psi_profile_ld(const NeStabilityProfile& s, long double z) { 
   if (!s.split) return psi_fn_ld(s.a, z);
   return z > 0 ? psi_fn_ld(s.a, z) : psi_fn_ld(s.b, z);
 }
+// one side of a profile as a function of |ζ|, continued to |ζ| = 0 from its own side (a SplitStabilityFunction
+// evaluates ζ = 0 with its unstable member, :720-725: a one-point discontinuity of the size of the members' rounding
+// at 0 — 1e-16 in Float64, 4e-8 with Float32-rounded parameters — that a polynomial should not chase)
+inline long double psi_side_ld(const NeStabilityProfile& s, long double az, bool stable) {
+  if (!s.split) return psi_fn_ld(s.a, stable ? az : -az);
+  return stable ? psi_fn_ld(s.a, az) : psi_fn_ld(s.b, -az);
+}
 inline bool psi_is_plain_edson(const NeFluxFormulation& f) {
   return !f.psi_momentum.split && f.psi_momentum.a.kind == NE_PSI_EDSON_MOMENTUM &&
          !f.psi_temperature.split && f.psi_temperature.a.kind == NE_PSI_EDSON_SCALAR;
@@ -138,7 +147,13 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
   // any other combination of the shipped stability functions (SHEBA / Paulson / linear-stable / split / zero):
   // the same piecewise polynomials fitted to the general closed forms (Float64 models only)
   const bool general = !psi_is_plain_edson(f);
-  if (general && f32) return 1.0;
+  // Float32 model with non-Edson functions: the closed forms at the Float32-rounded parameters (the generic kernel also
+  // forms a few derived constants in Float32: a 1e-7 relative difference in ψ, far inside the Float32 bar of 1e-5)
+  NeStabilityProfile gm = f.psi_momentum, gs = f.psi_temperature;
+  if (general && f32)
+    for (NeStabilityProfile* pr : {&gm, &gs})
+      for (NeStabilityFn* fn : {&pr->a, &pr->b})
+        for (int k = 0; k < 12; ++k) fn->p[k] = (double)(float)fn->p[k];
   double worst = 0;
   for (int iv = 0; iv < PSI_NI; ++iv) {
     long double lo, hi;
@@ -155,11 +170,11 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
     rec[1] = (double)(-mid / half);
     double cm[PSI_DEG + 1], cs[PSI_DEG + 1];
     auto fmf = [&](long double az) {
-      if (general) return psi_profile_ld(f.psi_momentum, stable ? az : -az);
+      if (general) return psi_side_ld(gm, az, stable);
       return stable ? psi_m_stable_ld(pm, az, f32) : psi_m_unstable_ld(pm, -az, f32);
     };
     auto fsf = [&](long double az) {
-      if (general) return psi_profile_ld(f.psi_temperature, stable ? az : -az);
+      if (general) return psi_side_ld(gs, az, stable);
       return stable ? psi_s_stable_ld(ps, az) : psi_s_unstable_ld(ps, -az, f32);
     };
     cheb_fit_monomial(fmf, lo, hi, PSI_DEG, cm);
@@ -185,11 +200,11 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
     rec[1] = (double)(-mid / half);
     double cm[TINY_DEG + 1], cs[TINY_DEG + 1];
     auto fmf = [&](long double az) {
-      if (general) return psi_profile_ld(f.psi_momentum, stable ? az : -az);
+      if (general) return psi_side_ld(gm, az, stable);
       return stable ? psi_m_stable_ld(pm, az, f32) : psi_m_unstable_ld(pm, -az, f32);
     };
     auto fsf = [&](long double az) {
-      if (general) return psi_profile_ld(f.psi_temperature, stable ? az : -az);
+      if (general) return psi_side_ld(gs, az, stable);
       return stable ? psi_s_stable_ld(ps, az) : psi_s_unstable_ld(ps, -az, f32);
     };
     cheb_fit_monomial(fmf, lo, hi, TINY_DEG, cm);
@@ -209,6 +224,8 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
   T.cbrt_floor = ratio * ratio * ratio / 8;
   T.same_exp = (pm[0] == ps[0] && pm[1] == ps[1]);
   T.general_psi = general ? 1 : 0;
+  T.f32_model = f32 ? 1 : 0;
+  T.pad_ = 0;
   T.log_hd = 0;
   return worst;
 }
@@ -244,7 +261,10 @@ __device__ __forceinline__ void psi_stable_pair(const FastParams& P, const TabPa
 // ff != nullptr: tables of a non-Edson pair — the generic closed forms of ne_physics.cuh.
 __device__ __noinline__ double2 psi_outside(const FastParams& P, const TabParams& T, const NeFluxFormulation* ff, double z) {
   double pm, ps;
-  if (ff) {
+  if (ff && T.f32_model) {
+    pm = stability_profile<float, double>(ff->psi_momentum, z);
+    ps = stability_profile<float, double>(ff->psi_temperature, z);
+  } else if (ff) {
     pm = stability_profile<double, double>(ff->psi_momentum, z);
     ps = stability_profile<double, double>(ff->psi_temperature, z);
   } else if (z > 0) psi_stable_pair(P, T, z, pm, ps);
@@ -365,7 +385,7 @@ struct FastPointF {
 };
 
 __device__ __forceinline__ void tab_iteration(const FastParams& P, const FrontF32& Q, const TabParams& T,
-                                              const double* tab, FastPointF& s) {
+                                              const double* tab, FastPointF& s, const NeFluxFormulation* ff = nullptr) {
   const float bstar = __fmul_rn(s.gTv, __fadd_rn(__fmul_rn(s.theta_star, s.c1), __fmul_rn(s.c2, s.q_star)));
   const float Jb = -__fmul_rn(s.ustar, bstar);
   const float Jp = Jb > 0.0f ? Jb : 0.0f;
@@ -382,7 +402,7 @@ __device__ __forceinline__ void tab_iteration(const FastParams& P, const FrontF3
   const float aL = fabsf(Lstar);
   const double Linv = (aL < 3.0e38f) ? ((aL > 1.0e-30f) ? fm::rcp((double)Lstar) : 1.0 / (double)Lstar) : 0.0;
   double chi_u, chi_s;
-  tab_core<false>(P, T, tab, ud, ru, lu, Linv, (double)s.hd, s.log_hd, chi_u, chi_s);
+  tab_core<false>(P, T, tab, ud, ru, lu, Linv, (double)s.hd, s.log_hd, chi_u, chi_s, ff);
   s.ustar = (float)fm::mul_(chi_u, (double)U);
   s.theta_star = (float)fm::mul_(chi_s, (double)s.dtheta);
   s.q_star = (float)fm::mul_(chi_s, (double)s.dq);

@@ -256,6 +256,7 @@ def test_sea_ice_work_queue_kernel_against_generic_kernel(cuda_backend, cuda_lib
     monkeypatch.setenv("NE_B200_FORCE_GENERIC", "1")
     gen, git = run()
     monkeypatch.delenv("NE_B200_FORCE_GENERIC")
+    assert any((fast[n] != gen[n]).any() for n in fast), "the a-si fast path did not run (results identical to the generic kernel's)"
     assert (fit > 0).sum() > 10000 and ((fit > 0) == (git > 0)).all()
     assert float((fit != git).mean()) <= 1e-3, float((fit != git).mean())
     conv = (git < 100) & (fit < 100)
@@ -461,6 +462,7 @@ def test_float32_model_fast_path_against_generic_kernel_and_oracle(oracle_lib, c
         assert np.isfinite(a).all(), n
         assert np.abs(a - b).max() / s <= F32_TOL, f"{n}: fast vs generic {np.abs(a - b).max() / s}"
         assert np.abs(a - r).max() / s <= F32_TOL, f"{n}: fast vs oracle {np.abs(a - r).max() / s}"
+    assert any((fast[n] != generic[n]).any() for n in dev.ao_fluxes.names()), "the Float32 fast path did not run"
     fi, gi, oi = (g.interior(x).astype(int) for x in (fast["iterations"], generic["iterations"], ref.ao_iterations))
     assert ((fi > 0) == (oi > 0)).all()
     # trip counts: statistically those of the reference algorithm (a last-bit difference in a Float64 intermediate
@@ -646,3 +648,45 @@ def test_sea_ice_work_queue_edge_cases(oracle_lib, cuda_backend, cuda_lib, case)
         assert float(np.abs(a - b)[mask].max()) / s <= (F64_TOL if case != "fixed_iterations" else 1e-9), f"{case}/{n}"
     Tr, Td = g.interior(ref.sea_ice_state.top_temperature), g.interior(cuda_backend.to_numpy(dev.sea_ice_state.top_temperature))
     assert np.abs(Tr - Td)[mask].max() <= 1e-8
+
+
+def test_float32_sea_ice_fast_path_against_generic_kernel_and_oracle(oracle_lib, cuda_backend, cuda_lib, monkeypatch):
+    """Float32 OceanSeaIce model: the a-si default tree on the work-queue kernel (Float32 skin temperature and q_sat,
+    mixed-precision similarity step, tables fitted to the Float32-rounded SHEBA / Paulson parameters) against the generic
+    kernel and the oracle.  Bar: 1e-5 of the field scale on points that converge in all three."""
+    ref, dev = build_pair("C2", oracle_lib, cuda_backend, FT="f32", atm_FT="f32", sea_ice=True)
+    ref.initialize(); dev.initialize()
+    ref.interpolate_state(T_STEP); dev.interpolate_state(T_STEP)
+    g = dev.grid
+    Ts0 = dev.sea_ice_state.top_temperature.clone()
+    ref.compute_atmosphere_sea_ice_fluxes()
+
+    def run():
+        dev.sea_ice_state.top_temperature.copy_(Ts0)
+        dev.compute_atmosphere_sea_ice_fluxes()
+        cuda_backend.synchronize()
+        out = {n: g.interior(cuda_backend.to_numpy(getattr(dev.asi_fluxes, n))).astype(np.float64) for n in dev.asi_fluxes.names()}
+        out["Ts"] = g.interior(cuda_backend.to_numpy(dev.sea_ice_state.top_temperature)).astype(np.float64)
+        return out, g.interior(cuda_backend.to_numpy(dev.asi_iterations)).astype(int)
+
+    fast, fit = run()
+    monkeypatch.setenv("NE_B200_FORCE_GENERIC", "1")
+    gen, git = run()
+    monkeypatch.delenv("NE_B200_FORCE_GENERIC")
+    oit = g.interior(ref.asi_iterations).astype(int)
+    assert any((fast[n] != gen[n]).any() for n in fast), "the Float32 a-si fast path did not run (results identical to the generic kernel's)"
+    assert ((fit > 0) == (oit > 0)).all() and (fit > 0).sum() > 10000
+    conv = (fit < 100) & (git < 100) & (oit < 100) & (fit > 0)
+    assert conv.mean() > 0.02
+    for n in dev.asi_fluxes.names():
+        o = g.interior(getattr(ref.asi_fluxes, n)).astype(np.float64)
+        s = float(np.abs(o).max()) or 1.0
+        assert np.isfinite(fast[n]).all(), n
+        assert np.abs(fast[n] - gen[n])[conv].max() / s <= F32_TOL, f"{n}: fast vs generic {np.abs(fast[n] - gen[n])[conv].max() / s}"
+        assert np.abs(fast[n] - o)[conv].max() / s <= F32_TOL, f"{n}: fast vs oracle {np.abs(fast[n] - o)[conv].max() / s}"
+        assert np.abs(fast[n] - o).max() / s <= 2e-2, f"{n}: limit-cycle points {np.abs(fast[n] - o).max() / s}"
+    To = g.interior(ref.sea_ice_state.top_temperature).astype(np.float64)
+    assert np.abs(fast["Ts"] - To)[conv].max() <= 2e-3
+    ice = oit > 0
+    assert abs(float(fit[ice].mean()) - float(oit[ice].mean())) <= 3.0
+    assert abs(float((fit[ice] == 100).mean()) - float((oit[ice] == 100).mean())) <= 0.05
