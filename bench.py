@@ -54,15 +54,15 @@ BYTES_INTERP_ATM = 2 * 4 + 7 * 8      # 2 Float32 fractional indices in, 7 Float
 BYTES_INTERP_RAD = 2 * 4 + 2 * 8
 DT_STEP = 1200.0
 # One `ncu --set full` capture of this workload (C4, 1 GPU, f64 grid, f32 atmosphere), per launch:
-# profiles/r01_ncu_full_v3_summary.csv.  DRAM traffic = dram__bytes_read.sum + dram__bytes_write.sum; the executed view
+# profiles/r01_ncu_full_v8_summary.txt (the solve kernel is the one of r01_ncu_full_v3_summary.csv; re-captured).  DRAM traffic = dram__bytes_read.sum + dram__bytes_write.sum; the executed view
 # of the solve = thread-level DFMA/DMUL/DADD counts (DFMA = 2 flop) over the ncu duration, next to the algorithmic
 # (as-written census) figure of `roofline.achieved`, which the table-driven kernel under-executes by ~8x.
 NCU_C4 = {
-    "ao_traffic_bytes": 470.2e6 + 537.5e6,
-    "interp_traffic_bytes": 67.8e6 + 350.6e6,
+    "ao_traffic_bytes": 470.0e6 + 511.1e6,
+    "interp_traffic_bytes": 67.8e6 + 348.7e6,
     "ao_executed": {"tflops": 12.6, "frac_of_measured_dfma_peak": 0.37, "fp64_pipe_active": 0.558,
                     "issue_slots_active": 0.630, "lane_efficiency": 0.80,
-                    "source": "profiles/r01_ncu_full_v3_summary.csv + profiles/r01_notes.md"},
+                    "source": "profiles/r01_ncu_full_v8_summary.txt + profiles/r01_notes.md"},
 }
 
 

@@ -690,3 +690,49 @@ def test_float32_sea_ice_fast_path_against_generic_kernel_and_oracle(oracle_lib,
     ice = oit > 0
     assert abs(float(fit[ice].mean()) - float(oit[ice].mean())) <= 3.0
     assert abs(float((fit[ice] == 100).mean()) - float((oit[ice] == 100).mean())) <= 0.05
+
+
+@pytest.mark.parametrize("FT", ["f64", "f32"])
+def test_interface_step_replays_from_a_cuda_graph(cuda_backend, cuda_lib, FT):
+    """The whole step (merged interpolation, solve — the persistent work-queue kernel for Float32 —, post-solve kernel with
+    diagnostics, and the a-si work-queue kernel) is capturable: no allocation, memset or synchronisation after the first
+    call, the queue kernels re-arm their own tile counters.  Replaying the graph reproduces the eager results bit for bit."""
+    import torch
+    from numericalearth_jl_b200 import sharding
+    dev = synthetic.build_case("C1", cuda_backend, FT=FT, atm_FT="f32", sea_ice=True)
+    dev.initialize()
+    f = dev.ao_fluxes
+    diag = sharding.FluxDiagnostics(dev, [f.latent_heat, f.sensible_heat, f.x_momentum, dev.net_ocean.T])
+    Ts0 = dev.sea_ice_state.top_temperature.clone()
+
+    def step():
+        dev.sea_ice_state.top_temperature.copy_(Ts0)
+        dev.fused_interface_step(T_STEP, diagnostics=diag)
+        dev.compute_atmosphere_sea_ice_fluxes()
+
+    def snapshot():
+        out = {"diag": diag.result.clone()}
+        for bag in ("ao_fluxes", "net_ocean", "asi_fluxes"):
+            for n in getattr(dev, bag).names():
+                out[bag + "." + n] = getattr(getattr(dev, bag), n).clone()
+        out["Ts"] = dev.sea_ice_state.top_temperature.clone()
+        return out
+
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):       # warm-up on the capture stream: builds the solver tables, allocates the counter pool
+        step(); step()
+        torch.cuda.synchronize()
+        eager = snapshot()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            step()
+        for bag in ("ao_fluxes", "net_ocean", "asi_fluxes"):
+            for n in getattr(dev, bag).names():
+                getattr(getattr(dev, bag), n).fill_(float("nan"))
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        replayed = snapshot()
+    for k, v in eager.items():
+        assert torch.equal(v, replayed[k]) or (torch.isnan(v) == torch.isnan(replayed[k])).all() and \
+            torch.equal(torch.nan_to_num(v), torch.nan_to_num(replayed[k])), k
