@@ -363,6 +363,42 @@ typedef struct NeAtmosSeaIceDesc {
   int32_t* iterations;
 } NeAtmosSeaIceDesc;
 
+/* ---- atmosphere–land turbulent fluxes (atmosphere_land_fluxes.jl:48-251) -----------------------
+ * Same solver as the ocean / sea-ice kernels with a third interface state (AirLandInterfaceState,
+ * interface_states.jl:740-777): zero surface velocity, the bulk land temperature as interface temperature
+ * (BulkTemperature, the reference's default for land), and a land surface-humidity closure
+ * (interface_states.jl:92-229, 585-651).  No masking; launch range `:xy` = (1:nx) x (1:ny).  Temperatures in Kelvin.
+ * DryLayerHumidity (dry_layer_humidity.jl) has no kernel variant yet: NE_E_NO_VARIANT.                          */
+enum { NE_LANDQ_BULK = 0,                 /* BulkHumidity: q_sat(T_s) where saturation > 0, else 0                  */
+       NE_LANDQ_FRACTIONAL_CRITICAL = 1,  /* FractionalHumidity(CriticalSaturation): min(S / S_c, 1) q_sat(T_s)      */
+       NE_LANDQ_FRACTIONAL_CONSTANT = 2,  /* FractionalHumidity(beta::Number)                                        */
+       NE_LANDQ_SKIN = 3 };               /* SkinHumidity: soil vapor-flux balance, re-solved every trip (:600-651) */
+typedef struct NeLandHumidity {
+  int32_t kind;
+  int32_t phase;                 /* NE_PHASE_LIQUID / NE_PHASE_ICE */
+  double critical_saturation;    /* FRACTIONAL_CRITICAL */
+  double efficiency;             /* FRACTIONAL_CONSTANT */
+  double surface_thickness;      /* SKIN: saturation depth d         */
+  double vapor_diffusivity;      /* SKIN: soil vapor diffusivity     */
+} NeLandHumidity;
+typedef struct NeAtmosLandDesc {
+  NeExchangeGrid grid;
+  const void *ua, *va, *Ta, *pa, *qa;
+  NeSlot surface_layer_height, boundary_layer_height;
+  NeSlot land_temperature;       /* exchanger.land.state.T: bulk land temperature, Kelvin (:182-184)                  */
+  NeSlot saturation;             /* exchanger.land.state.saturation                                                  */
+  NeThermoParams thermo;
+  double gravitational_acceleration;
+  NeFluxFormulation flux;        /* default: Large-Yeager stability functions, constant roughness 0.1 / 0.01 / 0.01 m
+                                    (component_interfaces.jl:514-521)                                                 */
+  NeInterfaceProperties properties; /* temperature_formulation must be NE_TEMP_BULK; velocity formulation as usual     */
+  NeLandHumidity humidity;
+  void *latent_heat, *sensible_heat, *water_vapor, *x_momentum, *y_momentum;
+  void *interface_temperature;
+  void *friction_velocity, *temperature_scale, *water_vapor_scale;
+  int32_t* iterations;
+} NeAtmosLandDesc;
+
 /* ---- sea-ice–ocean fluxes (sea_ice_ocean_fluxes.jl:20-226, freezing_limited_ocean_temperature.jl:73-118) */
 enum { NE_SIO_ICE_BATH = 0, NE_SIO_THREE_EQUATION = 1, NE_SIO_FREEZE_ONLY = 2 };
 enum { NE_USTAR_CONSTANT = 0, NE_USTAR_MOMENTUM_BASED = 1 };   /* friction_velocity.jl:24-44 */
@@ -517,6 +553,9 @@ int ne_atmosphere_ocean_fluxes_f32(const NeAtmosOceanDesc*, void* stream);
 
 int ne_atmosphere_sea_ice_fluxes_f64(const NeAtmosSeaIceDesc*, void* stream);
 int ne_atmosphere_sea_ice_fluxes_f32(const NeAtmosSeaIceDesc*, void* stream);
+
+int ne_atmosphere_land_fluxes_f64(const NeAtmosLandDesc*, void* stream);
+int ne_atmosphere_land_fluxes_f32(const NeAtmosLandDesc*, void* stream);
 
 int ne_sea_ice_ocean_fluxes_f64(const NeSeaIceOceanDesc*, void* stream);
 int ne_sea_ice_ocean_fluxes_f32(const NeSeaIceOceanDesc*, void* stream);

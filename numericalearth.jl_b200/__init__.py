@@ -14,6 +14,6 @@ from . import abi  # noqa: F401
 from .formulations import *  # noqa: F401,F403
 from .formulations import NoKernelVariantError  # noqa: F401
 from .interface import (ComponentInterfaces, ExchangeGrid, LatLonSourceGrid, PrescribedAtmosphere,  # noqa: F401
-                        PrescribedLand, PrescribedRadiation, interpolating_time_indices)
+                        PrescribedLand, PrescribedRadiation, SlabLandState, interpolating_time_indices)
 from .pipeline import HostPipelinedStep  # noqa: F401
 from .lib import LIB_PATH, Library, NeError, NumpyHostBackend, TorchCudaBackend, get_library  # noqa: F401

@@ -188,6 +188,26 @@ class NeAtmosSeaIceDesc(C.Structure):
                 ("interface_temperature", vp), ("iterations", vp)]
 
 
+NE_LANDQ_BULK, NE_LANDQ_FRACTIONAL_CRITICAL, NE_LANDQ_FRACTIONAL_CONSTANT, NE_LANDQ_SKIN = 0, 1, 2, 3
+
+
+class NeLandHumidity(C.Structure):
+    _fields_ = [("kind", i32), ("phase", i32), ("critical_saturation", f64), ("efficiency", f64),
+                ("surface_thickness", f64), ("vapor_diffusivity", f64)]
+
+
+class NeAtmosLandDesc(C.Structure):
+    _fields_ = [("grid", NeExchangeGrid),
+                ("ua", vp), ("va", vp), ("Ta", vp), ("pa", vp), ("qa", vp),
+                ("surface_layer_height", NeSlot), ("boundary_layer_height", NeSlot),
+                ("land_temperature", NeSlot), ("saturation", NeSlot),
+                ("thermo", NeThermoParams), ("gravitational_acceleration", f64), ("flux", NeFluxFormulation),
+                ("properties", NeInterfaceProperties), ("humidity", NeLandHumidity),
+                ("latent_heat", vp), ("sensible_heat", vp), ("water_vapor", vp), ("x_momentum", vp), ("y_momentum", vp),
+                ("interface_temperature", vp),
+                ("friction_velocity", vp), ("temperature_scale", vp), ("water_vapor_scale", vp), ("iterations", vp)]
+
+
 class NeSeaIceOceanDesc(C.Structure):
     _fields_ = [("grid", NeExchangeGrid), ("nz", i64), ("hz", i64), ("T", vp), ("S", vp), ("dz", vp), ("dt", f64),
                 ("formulation", i32), ("friction_velocity_kind", i32),
@@ -264,7 +284,7 @@ STRUCTS = {c.__name__: c for c in [
     NeSlot, NeExchangeGrid, NeTimeSeries, NeTimeInterp, NeInterpDesc, NeFracIndexDesc, NeThermoParams, NeStabilityFn,
     NeStabilityProfile, NeRoughnessLength, NeSubgridVelocity, NeStopCriteria, NePolynomialDrag, NeTransferCoefficient,
     NeLargeYeager, NeFluxFormulation, NeInterfaceProperties, NeMediumProperties, NeSeaIceAlbedo, NeTabulatedAlbedo, NeSurfaceRadiation, NeAtmosOceanDesc,
-    NeAtmosSeaIceDesc, NeSeaIceOceanDesc, NeSeaIceOceanStressDesc, NeAssembleOceanDesc, NeAssembleSeaIceDesc,
+    NeAtmosSeaIceDesc, NeLandHumidity, NeAtmosLandDesc, NeSeaIceOceanDesc, NeSeaIceOceanStressDesc, NeAssembleOceanDesc, NeAssembleSeaIceDesc,
     NeApplyRadiationDesc, NeElevationCorrectionDesc, NeFusedStepDesc, NeDiagDesc, NeHostField, NeHostStepDesc]}
 
 # entry points declared in include/ne_b200.h: name -> descriptor struct (None: special signature)
@@ -274,6 +294,7 @@ DESC_ENTRY_POINTS = {
     "ne_correct_atmosphere_elevation": NeElevationCorrectionDesc,
     "ne_atmosphere_ocean_fluxes": NeAtmosOceanDesc,
     "ne_atmosphere_sea_ice_fluxes": NeAtmosSeaIceDesc,
+    "ne_atmosphere_land_fluxes": NeAtmosLandDesc,
     "ne_sea_ice_ocean_fluxes": NeSeaIceOceanDesc,
     "ne_sea_ice_ocean_stress": NeSeaIceOceanStressDesc,
     "ne_assemble_net_ocean_fluxes": NeAssembleOceanDesc,

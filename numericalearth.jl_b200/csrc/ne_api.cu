@@ -48,7 +48,7 @@ int64_t ne_struct_size(const char* name) {
   NE_SZ(NeFracIndexDesc) NE_SZ(NeThermoParams) NE_SZ(NeStabilityFn) NE_SZ(NeStabilityProfile)
   NE_SZ(NeRoughnessLength) NE_SZ(NeSubgridVelocity) NE_SZ(NeStopCriteria) NE_SZ(NePolynomialDrag)
   NE_SZ(NeTransferCoefficient) NE_SZ(NeLargeYeager) NE_SZ(NeFluxFormulation) NE_SZ(NeInterfaceProperties)
-  NE_SZ(NeMediumProperties) NE_SZ(NeSurfaceRadiation) NE_SZ(NeAtmosOceanDesc) NE_SZ(NeAtmosSeaIceDesc)
+  NE_SZ(NeMediumProperties) NE_SZ(NeSurfaceRadiation) NE_SZ(NeAtmosOceanDesc) NE_SZ(NeAtmosSeaIceDesc) NE_SZ(NeLandHumidity) NE_SZ(NeAtmosLandDesc)
   NE_SZ(NeSeaIceOceanDesc) NE_SZ(NeSeaIceOceanStressDesc) NE_SZ(NeAssembleOceanDesc) NE_SZ(NeAssembleSeaIceDesc)
   NE_SZ(NeApplyRadiationDesc) NE_SZ(NeHostField) NE_SZ(NeHostStepDesc) NE_SZ(NeFusedStepDesc) NE_SZ(NeDiagDesc) NE_SZ(NeElevationCorrectionDesc) NE_SZ(NeSeaIceAlbedo) NE_SZ(NeTabulatedAlbedo)
 #undef NE_SZ

@@ -39,7 +39,48 @@ struct InterfaceSolver {
   RadState<FT> rad;
   FT surf_u, surf_v, surf_S;
 
+  // land interface (AirLandInterfaceState, interface_states.jl:740-777): humidity closure + the land state it reads.
+  // Trailing members: aggregate initialisation of the ocean / sea-ice kernels leaves them null / zero.
+  const NeLandHumidity* landq;
+  FT land_saturation, land_T;
+
   using WT = decltype(FT() + CT());
+
+  // saturation_specific_humidity interface_states.jl:79-90 (pressure-based, thermodynamics' element type)
+  template <class T, class P>
+  __device__ __forceinline__ CT saturation_specific_humidity(T Tk, P p_at, int phase) const {
+    CT Tc = (CT)Tk, p = (CT)p_at;
+    CT pv = th.saturation_vapor_pressure(Tc, phase);
+    pv = mn(pv, (CT)0.999 * p);
+    return th.eps_inv * pv / (p - (1 - th.eps_inv) * pv);
+  }
+
+  // compute_interface_humidity for the land closures: BulkHumidity :120-126, FractionalHumidity :592-598 (+ :151-157),
+  // SkinHumidity :625-651 (previous iterate's u★, q★, qˢ)
+  __device__ __forceinline__ FT land_humidity() const {
+    const NeLandHumidity& h = *landq;
+    if (h.kind == NE_LANDQ_BULK) {
+      CT qv = saturation_specific_humidity(Ts, a.p, h.phase);
+      return (FT)((land_saturation > 0) ? qv : (CT)0);
+    }
+    if (h.kind == NE_LANDQ_FRACTIONAL_CRITICAL) {
+      FT beta = mn(land_saturation / (FT)h.critical_saturation, (FT)1);
+      CT qv = saturation_specific_humidity(Ts, a.p, h.phase);
+      return (FT)(beta * qv);
+    }
+    if (h.kind == NE_LANDQ_FRACTIONAL_CONSTANT) {
+      CT qv = saturation_specific_humidity(Ts, a.p, h.phase);
+      return (FT)(h.efficiency * qv);   // β::Number keeps its own (Float64) type
+    }
+    auto rho_a = th.air_density(a.T, a.p, a.q);
+    CT qv = saturation_specific_humidity(land_T, a.p, h.phase);
+    double gs = h.vapor_diffusivity / h.surface_thickness;
+    auto Ja = -rho_a * ustar * q_star;
+    FT dq = qs - a.q;
+    auto D = gs * dq + Ja;
+    auto q = (gs * qv * dq + Ja * a.q) / D;
+    return (FT)((D == 0) ? (decltype(q))qs : q);
+  }
 
   // compute_interface_temperature(::SkinTemperature) interface_states.jl:526-577
   __device__ __forceinline__ FT skin_temperature(WT theta_a) const {
@@ -186,8 +227,8 @@ struct InterfaceSolver {
       bool go = fixed ? (it < maxiter) : (!((drift < tol) | (it >= maxiter)) | (it == 0));
       if (!go) break;
       if (!bulk) Ts = skin_temperature(theta_a);
-      if (!bulk || it == 0) {
-        qs = surface_specific_humidity<FT, CT>(ip, th, a.p, Ts, ICE ? (FT)0 : surf_S);
+      if (!bulk || it == 0 || (landq && landq->kind == NE_LANDQ_SKIN)) {
+        qs = landq ? land_humidity() : surface_specific_humidity<FT, CT>(ip, th, a.p, Ts, ICE ? (FT)0 : surf_S);
         dq = a.q - qs;
         dtheta = theta_a - Ts;
       }
@@ -325,6 +366,52 @@ asi_flux_kernel(const __grid_constant__ NeAtmosSeaIceDesc d, const __grid_consta
   if (d.iterations) d.iterations[idx] = iters;
 }
 
+// ---- atmosphere–land kernel (_compute_atmosphere_land_interface_state!, atmosphere_land_fluxes.jl:147-251) -----------
+template <class FT, class CT, class VT>
+__global__ void __launch_bounds__(128)
+al_flux_kernel(const __grid_constant__ NeAtmosLandDesc d, const __grid_constant__ Layout L,
+               const __grid_constant__ Thermo<CT> th, const __grid_constant__ SolveFlags flags,
+               const __grid_constant__ NeMediumProperties medium) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)L.ni * L.nj) return;
+  const int32_t jj = (int32_t)(t / L.ni);
+  const int64_t idx = L.at(L.i_lo + (int32_t)(t - (int64_t)jj * L.ni), L.j_lo + jj);
+
+  InterfaceSolver<FT, CT, VT, false> s{d.flux, d.properties, medium, th, (FT)d.gravitational_acceleration, flags};
+  s.a.u = __ldg((const FT*)d.ua + idx);
+  s.a.v = __ldg((const FT*)d.va + idx);
+  s.a.T = __ldg((const FT*)d.Ta + idx);
+  s.a.p = __ldg((const FT*)d.pa + idx);
+  s.a.q = __ldg((const FT*)d.qa + idx);
+  s.a.z = slot_at<FT>(d.surface_layer_height, idx);
+  s.a.h_bl = slot_at<FT>(d.boundary_layer_height, idx);
+  const FT Tland = slot_at<FT>(d.land_temperature, idx);
+  s.in.u = 0; s.in.v = 0; s.in.T = Tland; s.in.S = 0;      // surface velocities are zero for land (:189-191)
+  s.in.kappa = 0; s.in.hi = 0; s.in.hs = 0; s.in.hc = 0;
+  s.rad = RadState<FT>{0, 0, 0, 0, 0};
+  s.surf_u = 0; s.surf_v = 0; s.surf_S = 0;
+  s.landq = &d.humidity;
+  s.land_saturation = slot_at<FT>(d.saturation, idx);
+  s.land_T = Tland;
+  s.ustar = s.theta_star = s.q_star = (FT)1e-4;              // convert(FT, 1e-4) :204
+  s.Ts = Tland;
+  s.qs = (FT)s.saturation_specific_humidity(Tland, s.a.p, d.humidity.phase);   // :205
+  const int iters = s.solve();
+  FT du, dv;
+  if (d.properties.velocity_formulation == NE_VEL_RELATIVE) { du = s.a.u - s.surf_u; dv = s.a.v - s.surf_v; } else { du = s.a.u; dv = s.a.v; }
+  FluxEpilogue<FT, CT> e(th, s.a, s.ustar, s.theta_star, s.q_star, du, dv, false);
+  ((FT*)d.latent_heat)[idx] = e.Qv;
+  ((FT*)d.sensible_heat)[idx] = e.Qc;
+  ((FT*)d.water_vapor)[idx] = e.Jv;
+  ((FT*)d.x_momentum)[idx] = e.tx;
+  ((FT*)d.y_momentum)[idx] = e.ty;
+  ((FT*)d.interface_temperature)[idx] = s.Ts;
+  ((FT*)d.friction_velocity)[idx] = s.ustar;
+  ((FT*)d.temperature_scale)[idx] = s.theta_star;
+  ((FT*)d.water_vapor_scale)[idx] = s.q_star;
+  if (d.iterations) d.iterations[idx] = iters;
+}
+
 inline SolveFlags make_flags(const NeFluxFormulation& f) {
   SolveFlags fl = {0, 0};
   if (f.kind == NE_FLUX_SIMILARITY_THEORY &&
@@ -358,6 +445,21 @@ int launch_asi(const NeAtmosSeaIceDesc& d, cudaStream_t stream) {
   const int64_t blocks = (n + threads - 1) / threads;
   asi_flux_kernel<FT, CT, VT><<<(unsigned)blocks, threads, 0, stream>>>(d, L, th, fl);
   NE_CUDA_CHECK_LAUNCH("ne_atmosphere_sea_ice_fluxes");
+  return NE_OK;
+}
+
+template <class FT, class CT, class VT>
+int launch_al(const NeAtmosLandDesc& d, cudaStream_t stream) {
+  Layout L = make_layout(d.grid);
+  Thermo<CT> th = Thermo<CT>::make(d.thermo);
+  SolveFlags fl = make_flags(d.flux);
+  NeMediumProperties medium;
+  std::memset(&medium, 0, sizeof(medium));   // only read by skin temperatures, which the land interface does not use
+  const int64_t n = (int64_t)L.ni * L.nj;
+  const int threads = 128;
+  const int64_t blocks = (n + threads - 1) / threads;
+  al_flux_kernel<FT, CT, VT><<<(unsigned)blocks, threads, 0, stream>>>(d, L, th, fl, medium);
+  NE_CUDA_CHECK_LAUNCH("ne_atmosphere_land_fluxes");
   return NE_OK;
 }
 

@@ -24,6 +24,7 @@
 #include "ne_flux_tab.cuh"
 #include "ne_flux_queue.cuh"
 #include "ne_flux_asi_fast.cuh"
+#include "ne_queue_host.cuh"
 #include "ne_interp_device.cuh"
 #include "ne_physics.cuh"
 
@@ -32,6 +33,7 @@ namespace ne {
 // generic kernels: defined in ne_flux_generic.cuh, instantiated in ne_flux_generic_*.cu
 template <class FT, class CT, class VT> int launch_ao(const NeAtmosOceanDesc& d, cudaStream_t stream);
 template <class FT, class CT, class VT> int launch_asi(const NeAtmosSeaIceDesc& d, cudaStream_t stream);
+template <class FT, class CT, class VT> int launch_al(const NeAtmosLandDesc& d, cudaStream_t stream);
 
 // ---- atmosphere–ocean kernel, default plugin tree (Float64), see ne_flux_fast.cuh --------------------
 template <class CT, int MINB>
@@ -458,11 +460,6 @@ static int validate_ao(const NeAtmosOceanDesc* d, bool need_atmosphere_arrays) {
   return NE_OK;
 }
 
-static bool env_flag(const char* name) {
-  const char* v = std::getenv(name);
-  return v && v[0] == '1';
-}
-
 // grid size of the table-driven kernels: enough 256-thread CTAs for `waves` rounds of full residency
 static unsigned tab_grid(int64_t n, int minb) {
   int sms = 148, dev = 0;
@@ -472,127 +469,6 @@ static unsigned tab_grid(int64_t n, int minb) {
   const int waves = tw ? std::atoi(tw) : 8;
   const int64_t tiles = (n + 255) / 256;
   return (unsigned)std::min<int64_t>(tiles, (int64_t)sms * minb * waves);
-}
-static int tab_minb() {
-  const char* tm = std::getenv("NE_B200_TAB_MINB");   // occupancy experiment knob (profiles/r01_notes.md)
-  const int m = tm ? std::atoi(tm) : 3;
-  return (m == 2 || m == 4) ? m : 3;
-}
-
-static int env_int(const char* name, int dflt) {
-  const char* v = std::getenv(name);
-  return v ? std::atoi(v) : dflt;
-}
-
-// the work-queue kernel indexes points with 32 bits
-static bool queue_path_ok(const NeExchangeGrid& g) {
-  if (env_flag("NE_B200_TAB_CLASSIC")) return false;
-  const int64_t parent = (int64_t)(g.nx + 2 * g.hx) * (int64_t)(g.ny + 2 * g.hy);
-  return parent < ((int64_t)1 << 31);
-}
-
-static FrontF32 make_front_f32(const NeFluxFormulation& flux, double gravitational_acceleration) {
-  FrontF32 Q;
-  Q.gmin = (float)flux.subgrid_velocities.minimum_gustiness;
-  Q.beta = (float)flux.subgrid_velocities.gustiness_parameter;
-  Q.Cg = (float)flux.ell_momentum.wave_constant;
-  Q.g_rough = (float)flux.ell_momentum.gravitational_acceleration;
-  Q.kappa = (float)flux.von_karman_constant;
-  Q.tol = (float)flux.stop.tolerance;
-  Q.g = (float)gravitational_acceleration;
-  Q.d_zero = (float)flux.zero_plane_displacement;
-  return Q;
-}
-
-// Tile/CTA counters of the work-queue kernel: a per-device pool of zero-initialised {tile, cta} pairs used round
-// robin.  A kernel leaves its pair zeroed (last CTA out), so no per-launch memset is needed and launches can be
-// captured in CUDA graphs; two launches share a pair only if QUEUE_SLOTS launches are in flight at once.
-constexpr int QUEUE_SLOTS = 1024;
-struct QueueCounters { int device; uint32_t* dptr; unsigned next; };
-static std::vector<QueueCounters> g_qcounters;
-
-static uint32_t* queue_counters() {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  std::lock_guard<std::mutex> lock(g_tab_mutex);
-  for (QueueCounters& q : g_qcounters)
-    if (q.device == dev) return q.dptr + 2 * (q.next++ % QUEUE_SLOTS);
-  QueueCounters q = {dev, nullptr, 1};
-  if (cudaMalloc(&q.dptr, sizeof(uint32_t) * 2 * QUEUE_SLOTS) != cudaSuccess ||
-      cudaMemset(q.dptr, 0, sizeof(uint32_t) * 2 * QUEUE_SLOTS) != cudaSuccess) {
-    cudaGetLastError();
-    return nullptr;
-  }
-  g_qcounters.push_back(q);
-  return q.dptr;
-}
-
-// grid of the persistent work-queue kernels: resident CTAs x NE_B200_QUEUE_WAVES, at most one CTA per 32*warps points
-static unsigned queue_grid(int64_t n, int warps, int ctas_per_sm) {
-  int sms = 148, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t ctas_needed = (n + 32 * warps - 1) / (32 * warps);
-  const int waves = std::max(1, env_int("NE_B200_QUEUE_WAVES", 1));
-  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)sms * ctas_per_sm * waves));
-}
-static int queue_theta() {
-  const int theta = env_int("NE_B200_QUEUE_THETA", 12);
-  return theta < 0 ? 0 : (theta > 24 ? 24 : theta);
-}
-
-// Work-queue solve (ne_flux_queue.cuh), atmosphere–ocean default tree
-template <class FT, class CT, bool HS>
-static int launch_queue_hs(const NeAtmosOceanDesc& d, const SolverTables* tabs, cudaStream_t s) {
-  using Problem = AoProblem<FT, CT, HS>;
-  const bool f32 = std::is_same<FT, float>::value;
-  typename Problem::Params prm;
-  prm.d = d;
-  prm.L = make_layout(d.grid);
-  prm.th = Thermo<CT>::make(d.thermo);
-  prm.P = make_fast_params(d.flux, d.gravitational_acceleration, f32);
-  prm.Q = make_front_f32(d.flux, d.gravitational_acceleration);
-  prm.T = tabs->T;
-  prm.T.log_hd = f32 ? std::log((double)((float)d.surface_layer_height.value - prm.Q.d_zero))
-                     : std::log(d.surface_layer_height.value - prm.P.d_zero);
-  uint32_t* counters = queue_counters();
-  NE_REQUIRE(counters != nullptr, "atmosphere-ocean: could not allocate the work-queue counters");
-  const unsigned grid = queue_grid((int64_t)prm.L.ni * prm.L.nj, 8, 3);
-  flux_queue_kernel<Problem, 8, 3><<<grid, 256, 0, s>>>(prm, tabs->dptr, queue_theta(), counters);
-  NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(queue)");
-  return NE_OK;
-}
-template <class FT, class CT>
-static int launch_queue(const NeAtmosOceanDesc& d, const SolverTables* tabs, cudaStream_t s) {
-  const bool hs = !d.surface_layer_height.ptr && !d.boundary_layer_height.ptr;
-  return hs ? launch_queue_hs<FT, CT, true>(d, tabs, s) : launch_queue_hs<FT, CT, false>(d, tabs, s);
-}
-
-// atmosphere–sea-ice default tree on the work-queue kernel (ne_flux_asi_fast.cuh)
-template <class FT, class CT, bool HS>
-static int launch_asi_queue_hs(const NeAtmosSeaIceDesc& d, const SolverTables* tabs, cudaStream_t s) {
-  using Problem = AsiProblem<FT, CT, HS>;
-  const bool f32 = std::is_same<FT, float>::value;
-  typename Problem::Params prm;
-  prm.d = d;
-  prm.L = make_layout(d.grid);
-  prm.th = Thermo<CT>::make(d.thermo);
-  prm.P = make_fast_params(d.flux, d.gravitational_acceleration, f32);
-  prm.Q = make_front_f32(d.flux, d.gravitational_acceleration);
-  prm.T = tabs->T;
-  prm.T.log_hd = f32 ? std::log((double)((float)d.surface_layer_height.value - prm.Q.d_zero))
-                     : std::log(d.surface_layer_height.value - prm.P.d_zero);
-  uint32_t* counters = queue_counters();
-  NE_REQUIRE(counters != nullptr, "atmosphere-sea-ice: could not allocate the work-queue counters");
-  const unsigned grid = queue_grid((int64_t)prm.L.ni * prm.L.nj, 4, 4);
-  flux_queue_kernel<Problem, 4, 4><<<grid, 128, 0, s>>>(prm, tabs->dptr, queue_theta(), counters);
-  NE_CUDA_CHECK_LAUNCH("ne_atmosphere_sea_ice_fluxes(queue)");
-  return NE_OK;
-}
-template <class FT, class CT>
-static int launch_asi_queue(const NeAtmosSeaIceDesc& d, const SolverTables* tabs, cudaStream_t s) {
-  const bool hs = !d.surface_layer_height.ptr && !d.boundary_layer_height.ptr;
-  return hs ? launch_asi_queue_hs<FT, CT, true>(d, tabs, s) : launch_asi_queue_hs<FT, CT, false>(d, tabs, s);
 }
 
 template <class FT>
@@ -622,10 +498,9 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
       // instruction-cache misses and exposed load latency than the denser rounds save, profiles/r01_notes.md)
       const bool ext = !strict_default_options(d->flux) || (tabs && tabs->T.general_psi);
       if (tabs && env_flag("NE_B200_QUEUE") && queue_path_ok(d->grid) && !ext)
-        return ct64 ? launch_queue<double, double>(*d, tabs, s) : launch_queue<double, float>(*d, tabs, s);
+        return ct64 ? launch_queue<double, double>(*d, tabs->T, tabs->dptr, s) : launch_queue<double, float>(*d, tabs->T, tabs->dptr, s);
       if (tabs) {
-        const int tminb = tab_minb();
-        const unsigned tb = tab_grid(n, tminb);
+        const unsigned tb = tab_grid(n, 3);
         const bool hs = !d->surface_layer_height.ptr && !d->boundary_layer_height.ptr;
         TabParams TP = tabs->T;
         TP.log_hd = std::log(d->surface_layer_height.value - P.d_zero);
@@ -644,10 +519,7 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
     if (hs) NE_LAUNCH_TAB2(MB, true); \
     else NE_LAUNCH_TAB2(MB, false);   \
   } while (0)
-        if (ext) NE_LAUNCH_TAB(3);   // the option kernels are built at the default occupancy only
-        else if (tminb == 2) NE_LAUNCH_TAB(2);
-        else if (tminb == 4) NE_LAUNCH_TAB(4);
-        else NE_LAUNCH_TAB(3);
+        NE_LAUNCH_TAB(3);   // 80 registers, 3 CTAs per SM: the measured optimum (profiles/r01_notes.md: 64 regs 1.89-1.99 ms, 128 regs 1.87 ms)
 #undef NE_LAUNCH_TAB
 #undef NE_LAUNCH_TAB2
 #undef NE_LAUNCH_TAB3
@@ -655,17 +527,13 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
         return NE_OK;
       }
       add_small_zeta_poly(P, d->flux);   // closed-form kernel only
-      const char* mb = std::getenv("NE_B200_FAST_MINB");   // occupancy experiment knob
-      const int minb = mb ? std::atoi(mb) : 8;   // 64 registers/thread measured fastest on B200 (profiles/r01_notes.md)
-      const unsigned nb = (unsigned)((n + 127) / 128);
+      const unsigned nb = (unsigned)((n + 127) / 128);   // 64 registers/thread measured fastest on B200 (profiles/r01_notes.md)
 #define NE_LAUNCH_FAST(MB)                                                                                   \
   do {                                                                                                       \
     if (ct64) ao_flux_fast_kernel<double, MB><<<nb, 128, 0, s>>>(*d, L, Thermo<double>::make(d->thermo), P); \
     else ao_flux_fast_kernel<float, MB><<<nb, 128, 0, s>>>(*d, L, Thermo<float>::make(d->thermo), P);        \
   } while (0)
-      if (minb == 4) NE_LAUNCH_FAST(4);
-      else if (minb == 6) NE_LAUNCH_FAST(6);
-      else NE_LAUNCH_FAST(8);
+      NE_LAUNCH_FAST(8);
 #undef NE_LAUNCH_FAST
       NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(fast)");
       return NE_OK;
@@ -678,7 +546,7 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
         tab_path_eligible(d->flux) && queue_path_ok(d->grid) && !env_flag("NE_B200_FORCE_GENERIC") &&
         !env_flag("NE_B200_CLOSED_FORM_PSI")) {
       const SolverTables* tabs = solver_tables(d->flux, true);
-      if (tabs) return launch_queue<float, float>(*d, tabs, s);
+      if (tabs) return launch_queue<float, float>(*d, tabs->T, tabs->dptr, s);
     }
     if (ct64) return v64 ? launch_ao<float, double, double>(*d, s) : launch_ao<float, double, float>(*d, s);
     return v64 ? launch_ao<float, float, double>(*d, s) : launch_ao<float, float, float>(*d, s);
@@ -722,8 +590,7 @@ int fused_interp_ao_f64(const NeInterpDesc* atm, const NeInterpDesc* rad, const 
   Layout L = make_layout(d->grid);
   FastParams P = make_fast_params(d->flux, d->gravitational_acceleration);
   const int64_t n = (int64_t)L.ni * L.nj;
-  const int tminb = tab_minb() == 4 ? 3 : tab_minb();
-  const unsigned tb = tab_grid(n, tminb);
+  const unsigned tb = tab_grid(n, 3);
   const bool hs = !d->surface_layer_height.ptr && !d->boundary_layer_height.ptr;
   TabParams TP = tabs->T;
   TP.log_hd = std::log(d->surface_layer_height.value - P.d_zero);
@@ -738,13 +605,8 @@ int fused_interp_ao_f64(const NeInterpDesc* atm, const NeInterpDesc* rad, const 
   ao_fused_tab_kernel<CT, AT, TT, MB, HS><<<tb, 256, 0, s>>>(*atm, r, *d, L, Sa, Sr, Thermo<CT>::make(d->thermo), P, TP, tabs->dptr)
 #define NE_FUSED3(CT, AT, TT)                     \
   do {                                            \
-    if (tminb == 2) {                             \
-      if (hs) NE_FUSED4(CT, AT, TT, 2, true);     \
-      else NE_FUSED4(CT, AT, TT, 2, false);       \
-    } else {                                      \
-      if (hs) NE_FUSED4(CT, AT, TT, 3, true);     \
-      else NE_FUSED4(CT, AT, TT, 3, false);       \
-    }                                             \
+    if (hs) NE_FUSED4(CT, AT, TT, 3, true);       \
+    else NE_FUSED4(CT, AT, TT, 3, false);         \
   } while (0)
   // thermodynamics default to the atmosphere's element type (prescribed_atmosphere.jl:224): the mixed
   // (CT ≠ AT) combinations and a time fraction narrower than the data are left to the component kernels
@@ -776,7 +638,7 @@ static int asi_entry(const NeAtmosSeaIceDesc* d, void* stream) {
     if (asi_fast_path_eligible(d->flux, d->properties) && queue_path_ok(d->grid) && !env_flag("NE_B200_FORCE_GENERIC") &&
         !env_flag("NE_B200_CLOSED_FORM_PSI")) {
       const SolverTables* tabs = solver_tables(d->flux, false);
-      if (tabs) return ct64 ? launch_asi_queue<double, double>(*d, tabs, s) : launch_asi_queue<double, float>(*d, tabs, s);
+      if (tabs) return ct64 ? launch_asi_queue<double, double>(*d, tabs->T, tabs->dptr, s) : launch_asi_queue<double, float>(*d, tabs->T, tabs->dptr, s);
     }
     return ct64 ? launch_asi<double, double, double>(*d, s) : launch_asi<double, float, double>(*d, s);
   } else {
@@ -786,16 +648,45 @@ static int asi_entry(const NeAtmosSeaIceDesc* d, void* stream) {
         strict_default_options(d->flux) && queue_path_ok(d->grid) && !env_flag("NE_B200_FORCE_GENERIC") &&
         !env_flag("NE_B200_CLOSED_FORM_PSI")) {
       const SolverTables* tabs = solver_tables(d->flux, true);
-      if (tabs) return launch_asi_queue<float, float>(*d, tabs, s);
+      if (tabs) return launch_asi_queue<float, float>(*d, tabs->T, tabs->dptr, s);
     }
     if (ct64) return v64 ? launch_asi<float, double, double>(*d, s) : launch_asi<float, double, float>(*d, s);
     return v64 ? launch_asi<float, float, double>(*d, s) : launch_asi<float, float, float>(*d, s);
   }
 }
 
+template <class FT>
+static int al_entry(const NeAtmosLandDesc* d, void* stream) {
+  NE_REQUIRE(d != nullptr, "null descriptor");
+  NE_REQUIRE(grid_ok(d->grid, 0, 0), "atmosphere-land: launch range leaves the parent array");
+  NE_REQUIRE(d->ua && d->va && d->Ta && d->pa && d->qa, "atmosphere-land: null atmosphere state array");
+  NE_REQUIRE(d->latent_heat && d->sensible_heat && d->water_vapor && d->x_momentum && d->y_momentum &&
+             d->interface_temperature && d->friction_velocity && d->temperature_scale && d->water_vapor_scale,
+             "atmosphere-land: null output array");
+  int rc = validate_formulation(d->flux, d->properties, false);
+  if (rc != NE_OK) return rc;
+  if (d->properties.temperature_formulation != NE_TEMP_BULK)
+    NE_NO_VARIANT("atmosphere-land: only BulkTemperature has a kernel variant (the reference's default for land)");
+  const NeLandHumidity& h = d->humidity;
+  if (h.kind < NE_LANDQ_BULK || h.kind > NE_LANDQ_SKIN)
+    NE_NO_VARIANT("land humidity formulation %d has no kernel variant (DryLayerHumidity is not built)", h.kind);
+  if (h.phase != NE_PHASE_LIQUID && h.phase != NE_PHASE_ICE) NE_NO_VARIANT("unknown thermodynamic phase");
+  if (h.kind == NE_LANDQ_FRACTIONAL_CRITICAL) NE_REQUIRE(h.critical_saturation > 0, "CriticalSaturation must be positive");
+  if (h.kind == NE_LANDQ_SKIN) NE_REQUIRE(h.surface_thickness > 0, "SkinHumidity: surface_thickness must be positive");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool ct64 = d->thermo.dtype == NE_F64;
+  const bool v64 = std::is_same<FT, double>::value || viscosity_is_f64_literal(d->flux);
+  if (std::is_same<FT, double>::value)
+    return ct64 ? launch_al<double, double, double>(*d, s) : launch_al<double, float, double>(*d, s);
+  if (ct64) return v64 ? launch_al<float, double, double>(*d, s) : launch_al<float, double, float>(*d, s);
+  return v64 ? launch_al<float, float, double>(*d, s) : launch_al<float, float, float>(*d, s);
+}
+
 }  // namespace ne
 
 extern "C" {
+int ne_atmosphere_land_fluxes_f64(const NeAtmosLandDesc* d, void* stream) { return ne::al_entry<double>(d, stream); }
+int ne_atmosphere_land_fluxes_f32(const NeAtmosLandDesc* d, void* stream) { return ne::al_entry<float>(d, stream); }
 int ne_atmosphere_ocean_fluxes_f64(const NeAtmosOceanDesc* d, void* stream) { return ne::ao_entry<double>(d, stream); }
 int ne_atmosphere_ocean_fluxes_f32(const NeAtmosOceanDesc* d, void* stream) { return ne::ao_entry<float>(d, stream); }
 int ne_atmosphere_sea_ice_fluxes_f64(const NeAtmosSeaIceDesc* d, void* stream) { return ne::asi_entry<double>(d, stream); }

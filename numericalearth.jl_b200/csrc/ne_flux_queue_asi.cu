@@ -1,0 +1,37 @@
+// ne_flux_queue_asi.cu — work-queue kernel, atmosphere–sea-ice default tree (Float64 and Float32 models): launchers.
+#include "ne_flux_asi_fast.cuh"
+#include "ne_queue_host.cuh"
+
+namespace ne {
+
+template <class FT, class CT, bool HS>
+static int launch_asi_queue_hs(const NeAtmosSeaIceDesc& d, const TabParams& T, const double* tab, cudaStream_t s) {
+  using Problem = AsiProblem<FT, CT, HS>;
+  const bool f32 = std::is_same<FT, float>::value;
+  typename Problem::Params prm;
+  prm.d = d;
+  prm.L = make_layout(d.grid);
+  prm.th = Thermo<CT>::make(d.thermo);
+  prm.P = make_fast_params(d.flux, d.gravitational_acceleration, f32);
+  prm.Q = make_front_f32(d.flux, d.gravitational_acceleration);
+  prm.T = T;
+  prm.T.log_hd = f32 ? std::log((double)((float)d.surface_layer_height.value - prm.Q.d_zero))
+                     : std::log(d.surface_layer_height.value - prm.P.d_zero);
+  uint32_t* counters = queue_counters();
+  NE_REQUIRE(counters != nullptr, "atmosphere-sea-ice: could not allocate the work-queue counters");
+  const unsigned grid = queue_grid((int64_t)prm.L.ni * prm.L.nj, 4, 4);
+  flux_queue_kernel<Problem, 4, 4><<<grid, 128, 0, s>>>(prm, tab, queue_theta(), counters);
+  NE_CUDA_CHECK_LAUNCH("ne_atmosphere_sea_ice_fluxes(queue)");
+  return NE_OK;
+}
+
+template <class FT, class CT>
+int launch_asi_queue(const NeAtmosSeaIceDesc& d, const TabParams& T, const double* tab, cudaStream_t s) {
+  const bool hs = !d.surface_layer_height.ptr && !d.boundary_layer_height.ptr;
+  return hs ? launch_asi_queue_hs<FT, CT, true>(d, T, tab, s) : launch_asi_queue_hs<FT, CT, false>(d, T, tab, s);
+}
+template int launch_asi_queue<double, double>(const NeAtmosSeaIceDesc&, const TabParams&, const double*, cudaStream_t);
+template int launch_asi_queue<double, float>(const NeAtmosSeaIceDesc&, const TabParams&, const double*, cudaStream_t);
+template int launch_asi_queue<float, float>(const NeAtmosSeaIceDesc&, const TabParams&, const double*, cudaStream_t);
+
+}  // namespace ne

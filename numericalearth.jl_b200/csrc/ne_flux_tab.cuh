@@ -244,7 +244,7 @@ __device__ __forceinline__ void psi_far_unstable(const FastParams& P, double z, 
   ps = fast_psi_s(P, z);
 }
 
-__device__ __noinline__ double pow_general(double x, double y) { return pow(x, y); }
+static __device__ __noinline__ double pow_general(double x, double y) { return pow(x, y); }
 
 // stable closed forms (ζ ≥ 2^-6) with the custom exp/sqrt
 __device__ __forceinline__ void psi_stable_pair(const FastParams& P, const TabParams& T, double z, double& pm, double& ps) {
@@ -259,7 +259,7 @@ __device__ __forceinline__ void psi_stable_pair(const FastParams& P, const TabPa
 // closed forms outside the table: stable side with the custom exp, far unstable side through libdevice.
 // Out of line and returning by value, so the common path keeps ψ in registers.
 // ff != nullptr: tables of a non-Edson pair — the generic closed forms of ne_physics.cuh.
-__device__ __noinline__ double2 psi_outside(const FastParams& P, const TabParams& T, const NeFluxFormulation* ff, double z) {
+static __device__ __noinline__ double2 psi_outside(const FastParams& P, const TabParams& T, const NeFluxFormulation* ff, double z) {
   double pm, ps;
   if (ff && T.f32_model) {
     pm = stability_profile<float, double>(ff->psi_momentum, z);
@@ -286,7 +286,7 @@ __device__ __forceinline__ void tab_psi_pair(const FastParams& P, const TabParam
 }
 
 // out-of-line general lookup for the rare case where ψ(ℓ/L★) leaves the tiny-|ζ| records
-__device__ __noinline__ double2 tab_psi_pair_rare(const FastParams& P, const TabParams& T, const NeFluxFormulation* ff,
+static __device__ __noinline__ double2 tab_psi_pair_rare(const FastParams& P, const TabParams& T, const NeFluxFormulation* ff,
                                                   const double* tab, double z) {
   double pm, ps;
   tab_psi_pair(P, T, ff, tab, z, pm, ps);

@@ -432,6 +432,16 @@ class SimilarityTheoryFluxes:  # :174-214
         return f
 
 
+def atmosphere_land_stability_functions():  # :776-777 (currently the Large-Yeager set)
+    return large_yeager_stability_functions()
+
+
+def default_atmosphere_land_fluxes(solver_stop_criteria=None):  # component_interfaces.jl:514-521
+    kw = {} if solver_stop_criteria is None else {"solver_stop_criteria": solver_stop_criteria}
+    return SimilarityTheoryFluxes(stability_functions=atmosphere_land_stability_functions(), momentum_roughness_length=0.1,
+                                  temperature_roughness_length=0.01, water_vapor_roughness_length=0.01, **kw)
+
+
 def atmosphere_sea_ice_similarity_theory():  # :791-794
     return SimilarityTheoryFluxes(stability_functions=atmosphere_sea_ice_stability_functions())
 
@@ -547,6 +557,61 @@ class WaterMoleFraction:  # :236-253
 class ImpureSaturationSpecificHumidity:  # :20-44
     phase: Any = field(default_factory=Liquid)
     water_mole_fraction: Any = None
+
+
+# ---- land surface humidity closures (interface_states.jl:92-229) --------------------------------------------
+@dataclass
+class BulkHumidity:  # :107-126
+    phase: Any = field(default_factory=Liquid)
+
+
+@dataclass
+class CriticalSaturation:  # :145-157 (Manabe 1969)
+    critical_saturation: float = 0.75
+
+
+@dataclass
+class FractionalHumidity:  # :174-181
+    efficiency: Any = None      # CriticalSaturation or a constant number
+    phase: Any = field(default_factory=Liquid)
+
+
+@dataclass
+class SkinHumidity:  # :208-219, solved inside the iteration :625-651
+    surface_thickness: float = 0.1
+    vapor_diffusivity: float = 2e-2
+    phase: Any = field(default_factory=Liquid)
+
+
+class DryLayerHumidity:  # dry_layer_humidity.jl — no kernel variant yet
+    pass
+
+
+def land_humidity_pod(q) -> A.NeLandHumidity:
+    h = A.NeLandHumidity()
+    if isinstance(q, BulkHumidity):
+        h.kind = A.NE_LANDQ_BULK
+    elif isinstance(q, FractionalHumidity):
+        if isinstance(q.efficiency, CriticalSaturation):
+            h.kind, h.critical_saturation = A.NE_LANDQ_FRACTIONAL_CRITICAL, float(q.efficiency.critical_saturation)
+        elif isinstance(q.efficiency, (int, float)):
+            h.kind, h.efficiency = A.NE_LANDQ_FRACTIONAL_CONSTANT, float(q.efficiency)
+        else:
+            raise NoKernelVariantError(f"evaporation efficiency {q.efficiency!r} has no kernel variant")
+    elif isinstance(q, SkinHumidity):
+        if not isinstance(q.surface_thickness, (int, float)):
+            raise NoKernelVariantError("SkinHumidity with a wetness-dependent surface thickness has no kernel variant")
+        h.kind = A.NE_LANDQ_SKIN
+        h.surface_thickness, h.vapor_diffusivity = float(q.surface_thickness), float(q.vapor_diffusivity)
+    else:
+        raise NoKernelVariantError(f"land humidity formulation {q!r} has no kernel variant (DryLayerHumidity is not built)")
+    if isinstance(q.phase, Liquid):
+        h.phase = A.NE_PHASE_LIQUID
+    elif isinstance(q.phase, Ice):
+        h.phase = A.NE_PHASE_ICE
+    else:
+        raise NoKernelVariantError(f"phase {q.phase!r} has no kernel variant")
+    return h
 
 
 class BulkTemperature:  # :330

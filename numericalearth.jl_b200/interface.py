@@ -183,6 +183,14 @@ class PrescribedLand:
     time_indexing: str = "cyclical"
 
 
+@dataclass
+class SlabLandState:
+    """The land exchanger state the atmosphere-land flux kernel reads (atmosphere_land_fluxes.jl:78-84): bulk land
+    temperature (Kelvin) and surface saturation, exchange-layout arrays or numbers."""
+    T: Any = 288.0
+    saturation: Any = 1.0
+
+
 class _Fields:
     """Bag of named exchange-layout arrays."""
 
@@ -218,9 +226,15 @@ class ComponentInterfaces:
                  sea_ice_ocean_heat_flux=None,
                  ocean_properties=None, sea_ice_properties=None,
                  gravitational_acceleration=9.80665, inactive=None, with_iterations=False, atmosphere_correction=None,
-                 land: Optional[PrescribedLand] = None):
+                 land: Optional[PrescribedLand] = None, slab_land: Optional[SlabLandState] = None,
+                 atmosphere_land_fluxes=None, atmosphere_land_interface_specific_humidity=None,
+                 atmosphere_land_velocity_difference=None):
         self.grid, self.backend = grid, backend
         self.land = land
+        self.slab_land = slab_land
+        self.al_flux_formulation = atmosphere_land_fluxes or F.default_atmosphere_land_fluxes()
+        self.al_humidity = atmosphere_land_interface_specific_humidity or F.BulkHumidity()   # component_interfaces.jl:501-503
+        self.al_velocity = atmosphere_land_velocity_difference or F.RelativeVelocity()
         self.lib = lib if lib is not None else get_library()
         if getattr(self.lib, "is_device", True) != backend.is_device:
             raise RuntimeError("array back-end and compute library disagree on where memory lives "
@@ -274,6 +288,11 @@ class ComponentInterfaces:
         if land is not None:
             self.land_state = _Fields(freshwater_flux=Z())
             self.land_frac = _Fields(i=backend.zeros(grid.shape, land.grid.FT), j=backend.zeros(grid.shape, land.grid.FT))
+        if slab_land is not None:   # AtmosphereSurfaceFluxes of the atmosphere-land interface (atmosphere_land_fluxes.jl:33-37)
+            self.al_fluxes = _Fields(latent_heat=Z(), sensible_heat=Z(), water_vapor=Z(), x_momentum=Z(), y_momentum=Z(),
+                                     friction_velocity=Z(), temperature_scale=Z(), water_vapor_scale=Z())
+            self.al_temperature = Z()
+            self.al_iterations = backend.zeros(grid.shape, "i32") if with_iterations else None
         # ocean surface state (pointers to the top-level plane of the 3-D parents)
         self.ocean_state = _Fields(u=Z(), v=Z(), T=Z(), S=Z())
         self.kappa = None
@@ -570,6 +589,35 @@ class ComponentInterfaces:
         if self.has_sea_ice:
             self.lib.call("atmosphere_sea_ice_fluxes", self.grid.FT, self.atmosphere_sea_ice_desc(), self.backend.stream())
 
+    def atmosphere_land_desc(self) -> A.NeAtmosLandDesc:
+        """compute_atmosphere_land_fluxes!(model) (atmosphere_land_fluxes.jl:48-122): launch range `:xy`."""
+        b, g, atm = self.backend, self.grid, self.atmosphere
+        d = A.NeAtmosLandDesc()
+        d.grid = g.pod(False)
+        a = self.atmos_state
+        d.ua, d.va, d.Ta, d.pa, d.qa = b.ptr(a.u), b.ptr(a.v), b.ptr(a.T), b.ptr(a.p), b.ptr(a.q)
+        d.surface_layer_height = _slot(b, atm.surface_layer_height if atm else 10.0)
+        d.boundary_layer_height = _slot(b, atm.boundary_layer_height if atm else 512.0)
+        d.land_temperature, d.saturation = _slot(b, self.slab_land.T), _slot(b, self.slab_land.saturation)
+        d.thermo = (atm.thermodynamics_parameters if atm else F.AtmosphereThermodynamicsParameters(FT=g.FT)).pod()
+        d.gravitational_acceleration = self.g
+        d.flux = F.flux_formulation_pod(self.al_flux_formulation)
+        d.properties = F.InterfaceProperties(F.ImpureSaturationSpecificHumidity(F.Liquid(), None), F.BulkTemperature(),
+                                             self.al_velocity).pod()
+        d.humidity = F.land_humidity_pod(self.al_humidity)
+        f = self.al_fluxes
+        d.latent_heat, d.sensible_heat, d.water_vapor = b.ptr(f.latent_heat), b.ptr(f.sensible_heat), b.ptr(f.water_vapor)
+        d.x_momentum, d.y_momentum = b.ptr(f.x_momentum), b.ptr(f.y_momentum)
+        d.interface_temperature = b.ptr(self.al_temperature)
+        d.friction_velocity, d.temperature_scale, d.water_vapor_scale = \
+            b.ptr(f.friction_velocity), b.ptr(f.temperature_scale), b.ptr(f.water_vapor_scale)
+        d.iterations = _ptr(b, self.al_iterations)
+        return d
+
+    def compute_atmosphere_land_fluxes(self):
+        if self.slab_land is not None:
+            self.lib.call("atmosphere_land_fluxes", self.grid.FT, self.atmosphere_land_desc(), self.backend.stream())
+
     def sea_ice_ocean_desc(self, T3, S3, dz, dt, nz, hz=0) -> A.NeSeaIceOceanDesc:
         b, g = self.backend, self.grid
         d = A.NeSeaIceOceanDesc()
@@ -700,6 +748,7 @@ class ComponentInterfaces:
         self.correct_state()
         self.compute_atmosphere_ocean_fluxes()
         self.compute_atmosphere_sea_ice_fluxes()
+        self.compute_atmosphere_land_fluxes()
         if ocean_column is not None and self.has_sea_ice:
             self.lib.call("sea_ice_ocean_fluxes", self.grid.FT, self.sea_ice_ocean_desc(*ocean_column), self.backend.stream())
         self.update_net_fluxes()

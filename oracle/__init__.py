@@ -39,6 +39,10 @@ def load():
         path = build()
         _lib = ne_b200.Library(path, prefix="neo_", takes_stream=False, is_device=False)
         d = _lib.dll
+        d.neo_land_interface_humidity.restype = C.c_double
+        d.neo_land_interface_humidity.argtypes = [C.c_void_p, C.c_void_p] + [C.c_double] * 9
+        d.neo_saturation_specific_humidity.restype = C.c_double
+        d.neo_saturation_specific_humidity.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int]
         d.neo_stability_f64.restype = C.c_double
         d.neo_stability_f64.argtypes = [C.c_void_p, C.c_double]
         d.neo_vsgs2_f64.restype = C.c_double

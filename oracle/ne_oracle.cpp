@@ -472,14 +472,63 @@ void iterate_coefficient(const NeFluxFormulation& ff, const NeInterfacePropertie
   qs_out = (Cd == 0) ? (FT)0 : (FT)(Cq / m_sqrt(Cd) * dq);
 }
 
+// ---- land surface humidity closures (interface_states.jl:76-229, 585-651) ------------------------------
+// saturation_specific_humidity (:79-90): pressure-based, in the thermodynamics' element type
+template <class CT, class T, class P>
+inline CT saturation_specific_humidity(const Thermo<CT>& th, T Ts, P p_at, int phase) {
+  CT Tc = (CT)Ts, p = (CT)p_at;
+  CT pv = th.saturation_vapor_pressure(Tc, phase);
+  pv = m_min<CT>(pv, (CT)0.999 * p);
+  const CT eps_inv = 1 / th.eps;
+  return eps_inv * pv / (p - (1 - eps_inv) * pv);
+}
+
+template <class FT> struct LandSurface {
+  const NeLandHumidity* h;   // nullptr: not a land interface
+  FT saturation;             // Ψ.hydrology.saturation
+  FT T_bulk;                 // Ψ.energy.temperature (the SkinHumidity reservoir)
+};
+
+// compute_interface_humidity for AirLandInterfaceState: BulkHumidity :120-126 (via :587-588), FractionalHumidity
+// :592-598 with evaporation_efficiency :151-157, SkinHumidity :625-651 (previous iterate's u★, q★, qˢ)
+template <class FT, class CT>
+inline FT land_interface_humidity(const LandSurface<FT>& land, const Thermo<CT>& th, const State<FT>& s,
+                                  const AtmosState<FT>& a, FT Ts) {
+  const NeLandHumidity& h = *land.h;
+  if (h.kind == NE_LANDQ_BULK) {
+    CT qv = saturation_specific_humidity<CT>(th, Ts, a.p, h.phase);
+    return (FT)((land.saturation > 0) ? qv : (CT)0);
+  }
+  if (h.kind == NE_LANDQ_FRACTIONAL_CRITICAL) {
+    FT beta = m_min<FT>(land.saturation / (FT)h.critical_saturation, (FT)1);
+    CT qv = saturation_specific_humidity<CT>(th, Ts, a.p, h.phase);
+    return (FT)(beta * qv);
+  }
+  if (h.kind == NE_LANDQ_FRACTIONAL_CONSTANT) {
+    CT qv = saturation_specific_humidity<CT>(th, Ts, a.p, h.phase);
+    return (FT)(h.efficiency * qv);   // β::Number keeps its own (Float64) type
+  }
+  // SkinHumidity
+  auto rho_a = th.air_density(a.T, a.p, a.q);
+  CT qv = saturation_specific_humidity<CT>(th, land.T_bulk, a.p, h.phase);
+  double gs = h.vapor_diffusivity / h.surface_thickness;   // κ / d, the user's numbers
+  auto Ja = -rho_a * s.ustar * s.q_star;
+  FT dq = s.q - a.q;
+  auto D = gs * dq + Ja;
+  auto qs = (gs * qv * dq + Ja * a.q) / D;
+  return (FT)((D == 0) ? (decltype(qs))s.q : qs);
+}
+
 // ---- iterate_interface_state: compute_interface_state.jl:69-122 ---------------------------------
 template <class FT, class CT, class VT>
 State<FT> iterate_interface_state(const NeFluxFormulation& ff, const NeInterfaceProperties& ip, const Thermo<CT>& th,
                                   FT g, const State<FT>& s, const AtmosState<FT>& a, const Interior<FT>& in,
-                                  const RadState<FT>& rad, const NeMediumProperties& medium, bool ice_state) {
+                                  const RadState<FT>& rad, const NeMediumProperties& medium, bool ice_state,
+                                  const LandSurface<FT>* land = nullptr) {
   FT Ts = interface_temperature<FT, CT>(ip, s, a, in, rad, th, g, medium);
-  // humidity_surface_scalar: salinity for AirSea, 0 for AirIce (interface_states.jl:717,737)
-  FT qs = surface_specific_humidity<FT, CT>(ip, th, a.p, Ts, ice_state ? (FT)0 : s.S);
+  // humidity_surface_scalar: salinity for AirSea, 0 for AirIce (interface_states.jl:717,737); land closures for AirLand
+  FT qs = land ? land_interface_humidity<FT, CT>(*land, th, s, a, Ts)
+               : surface_specific_humidity<FT, CT>(ip, th, a.p, Ts, ice_state ? (FT)0 : s.S);
   FT dq = a.q - qs;
   auto theta_a = surface_atmosphere_temperature(a, th, g);
   auto dtheta = theta_a - Ts;
@@ -499,7 +548,7 @@ template <class FT, class CT, class VT>
 State<FT> compute_interface_state(const NeFluxFormulation& ff, const NeInterfaceProperties& ip, const Thermo<CT>& th,
                                   FT g, const State<FT>& init, const AtmosState<FT>& a, const Interior<FT>& in,
                                   const RadState<FT>& rad, const NeMediumProperties& medium, bool ice_state,
-                                  int& iterations) {
+                                  int& iterations, const LandSurface<FT>* land = nullptr) {
   State<FT> cur = init, prev = init;
   int it = 0;
   for (;;) {
@@ -516,7 +565,7 @@ State<FT> compute_interface_state(const NeFluxFormulation& ff, const NeInterface
     }
     if (!go) break;
     prev = cur;
-    cur = iterate_interface_state<FT, CT, VT>(ff, ip, th, g, prev, a, in, rad, medium, ice_state);
+    cur = iterate_interface_state<FT, CT, VT>(ff, ip, th, g, prev, a, in, rad, medium, ice_state, land);
     ++it;
   }
   iterations = it;
@@ -735,6 +784,56 @@ void atmosphere_sea_ice(const NeAtmosSeaIceDesc& d) {
 
 // ---- interpolation: Atmospheres/interpolate_atmospheric_state.jl:91-182 + [3rd-party Oceananigans
 // interpolator/_interpolate/time interpolation] ----------------------------------------------------
+// ---- _compute_atmosphere_land_interface_state!: atmosphere_land_fluxes.jl:147-251 ------------------------
+template <class FT, class CT, class VT>
+void atmosphere_land(const NeAtmosLandDesc& d) {
+  const Layout L(d.grid);
+  const Thermo<CT> th(d.thermo);
+  const FT g = (FT)d.gravitational_acceleration;
+  const FT* ua = (const FT*)d.ua; const FT* va = (const FT*)d.va; const FT* Ta = (const FT*)d.Ta;
+  const FT* pa = (const FT*)d.pa; const FT* qa = (const FT*)d.qa;
+  NeMediumProperties medium = {};   // only read by skin temperatures, which the land interface does not use
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int64_t j = d.grid.j_lo; j <= d.grid.j_hi; ++j) {
+    for (int64_t i = d.grid.i_lo; i <= d.grid.i_hi; ++i) {
+      const int64_t idx = L.at(i, j);
+      AtmosState<FT> a;
+      a.u = ua[idx]; a.v = va[idx]; a.T = Ta[idx]; a.p = pa[idx]; a.q = qa[idx];
+      a.z = slot_at<FT>(d.surface_layer_height, idx);
+      a.h_bl = slot_at<FT>(d.boundary_layer_height, idx);
+      const FT Ts = slot_at<FT>(d.land_temperature, idx);   // bulk land temperature = initial (and Bulk) interface temperature
+      Interior<FT> in = {};
+      in.u = 0; in.v = 0; in.T = Ts;                         // surface velocities are zero for land (:189-191)
+      RadState<FT> rad = {};
+      LandSurface<FT> land = {&d.humidity, slot_at<FT>(d.saturation, idx), Ts};
+      const FT us0 = (FT)1e-4;                                // convert(FT, 1e-4) :204
+      const FT qs0 = (FT)saturation_specific_humidity<CT>(th, Ts, a.p, d.humidity.phase);   // :205
+      State<FT> init = {us0, us0, us0, (FT)0, (FT)0, Ts, qs0, land.saturation};
+      int iters = 0;
+      State<FT> st = compute_interface_state<FT, CT, VT>(d.flux, d.properties, th, g, init, a, in, rad, medium, false, iters, &land);
+      FT ustar = st.ustar, theta_star = st.theta_star, q_star = st.q_star;
+      FT du, dv;
+      if (d.properties.velocity_formulation == NE_VEL_RELATIVE) { du = a.u - st.u; dv = a.v - st.v; } else { du = a.u; dv = a.v; }
+      FT dU = m_sqrt(sq(du) + sq(dv));
+      FT taux = (dU == 0) ? (FT)0 : -sq(ustar) * du / dU;
+      FT tauy = (dU == 0) ? (FT)0 : -sq(ustar) * dv / dU;
+      auto rho_a = th.air_density(a.T, a.p, a.q);
+      auto cpm = th.cp_m(a.q);
+      auto Ll = th.latent_heat_vapor(a.T);
+      ((FT*)d.latent_heat)[idx] = (FT)(-rho_a * Ll * ustar * q_star);
+      ((FT*)d.sensible_heat)[idx] = (FT)(-rho_a * cpm * ustar * theta_star);
+      ((FT*)d.water_vapor)[idx] = (FT)(-rho_a * ustar * q_star);
+      ((FT*)d.x_momentum)[idx] = (FT)(rho_a * taux);
+      ((FT*)d.y_momentum)[idx] = (FT)(rho_a * tauy);
+      ((FT*)d.interface_temperature)[idx] = st.T;
+      ((FT*)d.friction_velocity)[idx] = ustar;
+      ((FT*)d.temperature_scale)[idx] = theta_star;
+      ((FT*)d.water_vapor_scale)[idx] = q_star;
+      if (d.iterations) d.iterations[idx] = iters;
+    }
+  }
+}
+
 template <class AT> struct Interpolator { int64_t im, ip; AT xi; };
 
 template <class AT> inline AT julia_mod1(AT x) {   // Base.mod(x, one(x)) for floats
@@ -1132,6 +1231,23 @@ int neo_atmosphere_ocean_fluxes_f64(const NeAtmosOceanDesc* d) { NEO_DISPATCH_FL
 int neo_atmosphere_ocean_fluxes_f32(const NeAtmosOceanDesc* d) { NEO_DISPATCH_FLUX(atmosphere_ocean, float, d); return 0; }
 int neo_atmosphere_sea_ice_fluxes_f64(const NeAtmosSeaIceDesc* d) { NEO_DISPATCH_FLUX(atmosphere_sea_ice, double, d); return 0; }
 int neo_atmosphere_sea_ice_fluxes_f32(const NeAtmosSeaIceDesc* d) { NEO_DISPATCH_FLUX(atmosphere_sea_ice, float, d); return 0; }
+int neo_atmosphere_land_fluxes_f64(const NeAtmosLandDesc* d) { NEO_DISPATCH_FLUX(atmosphere_land, double, d); return 0; }
+int neo_atmosphere_land_fluxes_f32(const NeAtmosLandDesc* d) { NEO_DISPATCH_FLUX(atmosphere_land, float, d); return 0; }
+
+/* compute_interface_humidity of one AirLandInterfaceState (Float64): for the reference's own known-answer tests
+ * (test/test_surface_fluxes.jl:340-423) */
+double neo_land_interface_humidity(const NeLandHumidity* h, const NeThermoParams* thermo, double p_at, double q_at, double T_at,
+                                   double T_skin, double T_bulk, double saturation, double ustar, double q_star, double q_prev) {
+  const Thermo<double> th(*thermo);
+  LandSurface<double> land = {h, saturation, T_bulk};
+  State<double> s = {ustar, 0.0, q_star, 0.0, 0.0, T_skin, q_prev, saturation};
+  AtmosState<double> a = {10.0, 0.0, 0.0, T_at, p_at, q_at, 512.0};
+  return land_interface_humidity<double, double>(land, th, s, a, T_skin);
+}
+double neo_saturation_specific_humidity(const NeThermoParams* thermo, double T, double p, int phase) {
+  const Thermo<double> th(*thermo);
+  return saturation_specific_humidity<double>(th, T, p, phase);
+}
 
 static int interp_dispatch(const NeInterpDesc* d, bool out64) {
   const bool a64 = d->src_dtype == NE_F64, t64 = d->time.frac_dtype == NE_F64;

@@ -1,0 +1,159 @@
+"""the atmosphere-land flux kernel (atmosphere_land_fluxes.jl:48-251) with the land
+humidity closures BulkHumidity / FractionalHumidity / SkinHumidity (interface_states.jl:92-229, 585-651).
+CPU: the reference's own known answers (test/test_surface_fluxes.jl:340-423) against the oracle, and properties of the
+oracle kernel.  GPU: CUDA kernel against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import ne_b200
+from numericalearth_jl_b200 import abi as A
+from numericalearth_jl_b200 import formulations as F
+from numericalearth_jl_b200 import synthetic
+
+T_STEP = 0.37 * 10800.0
+CFG = dict(nx=96, ny=40, latitude=(-70.0, 70.0))
+
+
+def _thermo():
+    return F.AtmosphereThermodynamicsParameters(FT="f64").pod()
+
+
+def _q(oracle_lib, humidity, Ts, Td, S, ustar, qstar, qprev, p=101325.0, qa=0.005, Ta=290.0):
+    h, th = F.land_humidity_pod(humidity), _thermo()
+    return oracle_lib.dll.neo_land_interface_humidity(C.byref(h), C.byref(th), p, qa, Ta, Ts, Td, S, ustar, qstar, qprev)
+
+
+def _qsat(oracle_lib, T, p=101325.0):
+    th = _thermo()
+    return oracle_lib.dll.neo_saturation_specific_humidity(C.byref(th), T, p, A.NE_PHASE_LIQUID)
+
+
+def test_skin_humidity_vapor_flux_balance_reference_kat(oracle_lib):
+    """test/test_surface_fluxes.jl:340-391."""
+    qa, Td, Ts = 0.005, 295.0, 310.0
+    qv = _qsat(oracle_lib, Td)
+    assert qv > qa
+
+    def converge(d):
+        sh = F.SkinHumidity(surface_thickness=d, vapor_diffusivity=2e-2)
+        q = qv
+        for _ in range(100):
+            q = _q(oracle_lib, sh, Ts, Td, 1.0, 0.3, -1e-4, q)
+        return q
+
+    thin, mid, thick = converge(1e-3), converge(1e-1), converge(1e2)
+    for q in (thin, mid, thick):
+        assert qa <= q <= qv
+    assert abs(thin - qv) <= 1e-2 * qv and abs(thick - qa) <= 1e-2 * qa
+    assert thin > mid > thick
+    # zero turbulent flux (first iterate): saturated surface; and independent of the skin temperature
+    sh = F.SkinHumidity(surface_thickness=0.1, vapor_diffusivity=2e-2)
+    assert abs(_q(oracle_lib, sh, Ts, Td, 1.0, 0.0, 0.0, 0.0) - qv) <= 1e-12 * qv
+    assert _q(oracle_lib, sh, 280.0, Td, 1.0, 0.3, -1e-4, 0.01) == _q(oracle_lib, sh, 310.0, Td, 1.0, 0.3, -1e-4, 0.01)
+
+
+def test_fractional_and_bulk_humidity_reference_kat(oracle_lib):
+    """test/test_surface_fluxes.jl:393-423 (Manabe critical wetness) + BulkHumidity (interface_states.jl:120-126)."""
+    Ts = 295.0
+    qv = _qsat(oracle_lib, Ts)
+    fh = F.FractionalHumidity(efficiency=F.CriticalSaturation(0.75))
+    assert _q(oracle_lib, fh, Ts, Ts, 0.0, 0.3, 0.0, 0.0) == 0.0
+    assert abs(_q(oracle_lib, fh, Ts, Ts, 0.375, 0.3, 0.0, 0.0) - 0.5 * qv) <= 1e-15
+    assert abs(_q(oracle_lib, fh, Ts, Ts, 0.75, 0.3, 0.0, 0.0) - qv) <= 1e-15
+    assert abs(_q(oracle_lib, fh, Ts, Ts, 1.0, 0.3, 0.0, 0.0) - qv) <= 1e-15
+    fc = F.FractionalHumidity(efficiency=0.4)
+    assert abs(_q(oracle_lib, fc, Ts, Ts, 0.1, 0.3, 0.0, 0.0) - 0.4 * qv) <= 1e-15
+    bh = F.BulkHumidity()
+    assert _q(oracle_lib, bh, Ts, Ts, 0.0, 0.3, 0.0, 0.0) == 0.0
+    assert _q(oracle_lib, bh, Ts, Ts, 1e-6, 0.3, 0.0, 0.0) == qv
+    with pytest.raises(ne_b200.NoKernelVariantError):
+        F.land_humidity_pod(F.DryLayerHumidity())
+
+
+HUMIDITIES = {
+    "bulk": lambda: F.BulkHumidity(),
+    "fractional_critical": lambda: F.FractionalHumidity(efficiency=F.CriticalSaturation(0.75)),
+    "fractional_constant": lambda: F.FractionalHumidity(efficiency=0.4),
+    "skin": lambda: F.SkinHumidity(surface_thickness=0.05, vapor_diffusivity=2e-2),
+}
+
+
+def _land_state(grid, backend, FT):
+    rng = np.random.default_rng(77)
+    npd = np.float64 if FT == "f64" else np.float32
+    phi = np.deg2rad(grid.phi.astype(np.float64))[:, None] * np.ones((1, grid.shape[1]))
+    T = (300.0 - 35.0 * np.sin(phi) ** 2 + rng.normal(0, 3.0, grid.shape)).astype(npd)
+    S = np.clip(rng.uniform(-0.2, 1.1, grid.shape), 0.0, 1.0).astype(npd)      # some cells completely dry, some saturated
+    return ne_b200.SlabLandState(T=backend.from_numpy(T), saturation=backend.from_numpy(S))
+
+
+def _case(backend, lib, FT, atm_FT, humidity, **kw):
+    ci = synthetic.build_case(CFG, backend, FT=FT, atm_FT=atm_FT, lib=lib, with_iterations=True,
+                              atmosphere_land_interface_specific_humidity=humidity, **kw)
+    ci.slab_land = _land_state(ci.grid, backend, FT)
+    # the land exchanger state is attached after construction: allocate the land flux fields the same way the constructor does
+    Z = lambda: backend.zeros(ci.grid.shape, FT)  # noqa: E731
+    from numericalearth_jl_b200.interface import _Fields
+    ci.al_fluxes = _Fields(latent_heat=Z(), sensible_heat=Z(), water_vapor=Z(), x_momentum=Z(), y_momentum=Z(),
+                           friction_velocity=Z(), temperature_scale=Z(), water_vapor_scale=Z())
+    ci.al_temperature = Z()
+    ci.al_iterations = backend.zeros(ci.grid.shape, "i32")
+    ci.initialize()
+    ci.interpolate_state(T_STEP)
+    ci.compute_atmosphere_land_fluxes()
+    return ci
+
+
+@pytest.mark.parametrize("name", sorted(HUMIDITIES))
+def test_land_flux_kernel_oracle_properties(oracle_lib, name):
+    ci = _case(ne_b200.NumpyHostBackend(), oracle_lib, "f64", "f64", HUMIDITIES[name]())
+    g = ci.grid
+    inner = (slice(g.hy, g.hy + g.ny), slice(g.hx, g.hx + g.nx))
+    f = ci.al_fluxes
+    it = ci.al_iterations[inner]
+    assert it.min() >= 1 and it.max() <= 100
+    us = f.friction_velocity[inner]
+    conv = it < 100
+    assert np.isfinite(us[conv]).all() and (us[conv] > 0).all()
+    assert np.array_equal(ci.al_temperature[inner], np.asarray(ci.slab_land.T)[inner])       # BulkTemperature: T_s is the land temperature
+    # momentum flux opposes the wind (surface at rest), Q_c = -rho c_p u* theta*, Q_v = L J_v with L > 0
+    ua, va = ci.atmos_state.u[inner], ci.atmos_state.v[inner]
+    assert (np.sign(f.x_momentum[inner][conv]) == -np.sign(ua[conv])).all() and (np.sign(f.y_momentum[inner][conv]) == -np.sign(va[conv])).all()
+    Jv, Qv = f.water_vapor[inner][conv], f.latent_heat[inner][conv]
+    assert (np.sign(Jv) == np.sign(Qv)).all()
+    if name == "bulk":   # completely dry cells (S = 0) have q_s = 0: vapour can only flow downward (dew), J_v <= 0
+        dry = (np.asarray(ci.slab_land.saturation)[inner] == 0) & conv
+        assert dry.sum() > 50 and (f.water_vapor[inner][dry] <= 0).all()
+    # the halo / ring outside `:xy` is not written
+    assert (f.latent_heat[: g.hy, :] == 0).all() and (f.latent_heat[g.hy - 1, :] == 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("FT,atm_FT", [("f64", "f64"), ("f64", "f32"), ("f32", "f32")])
+@pytest.mark.parametrize("name", sorted(HUMIDITIES))
+def test_cuda_land_flux_kernel_parity(oracle_lib, cuda_backend, cuda_lib, name, FT, atm_FT):
+    ref = _case(ne_b200.NumpyHostBackend(), oracle_lib, FT, atm_FT, HUMIDITIES[name]())
+    dev = _case(cuda_backend, None, FT, atm_FT, HUMIDITIES[name]())
+    cuda_backend.synchronize()
+    g = ref.grid
+    inner = (slice(g.hy, g.hy + g.ny), slice(g.hx, g.hx + g.nx))
+    ri, di = ref.al_iterations[inner], cuda_backend.to_numpy(dev.al_iterations)[inner]
+    tol = 1e-10 if (FT, atm_FT) == ("f64", "f64") else (2e-6 if FT == "f64" else 1e-5)
+    if FT == "f64":
+        assert float((ri != di).mean()) <= 2e-3
+    conv = (ri < 100) & (di < 100)
+    assert conv.mean() > 0.5
+    for n in ref.al_fluxes.names():
+        a = np.asarray(getattr(ref.al_fluxes, n))[inner].astype(np.float64)
+        b = cuda_backend.to_numpy(getattr(dev.al_fluxes, n))[inner].astype(np.float64)
+        assert np.array_equal(np.isnan(a), np.isnan(b)), n
+        s = float(np.nanmax(np.abs(a))) or 1.0
+        assert np.nanmax(np.abs(a - b)[conv]) / s <= tol, f"{name}/{n}: {np.nanmax(np.abs(a - b)[conv]) / s}"
+    assert np.array_equal(ref.al_temperature[inner], cuda_backend.to_numpy(dev.al_temperature)[inner])
+    # an unknown closure is refused by the library itself
+    d = dev.atmosphere_land_desc()
+    d.humidity.kind = 9
+    with pytest.raises(ne_b200.NoKernelVariantError):
+        cuda_lib.call("atmosphere_land_fluxes", FT, d, cuda_backend.stream())
