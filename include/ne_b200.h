@@ -463,7 +463,9 @@ typedef struct NeApplyRadiationDesc {
   const void* surface_temperature;  /* a–o interface temperature / sea-ice top temperature */
   NeMediumProperties medium;        /* ocean_properties or sea_ice_properties               */
   const uint8_t* inactive;
-  int32_t over_sea_ice;             /* 0: ocean variant (JT += ...), 1: sea-ice variant      */
+  int32_t over_sea_ice;             /* surface: 0 ocean (JT += ...), 1 sea ice (top heat += ... * concentration),
+                                       2 land (surface_energy_flux += ...; apply_air_land_radiative_fluxes.jl:64-97,
+                                       surface_temperature = the atmosphere-land interface temperature, medium units Kelvin) */
   int32_t two_color;                /* ocean: route SW to TwoColorRadiation.surface_flux (src/Oceans/radiative_forcing.jl:84-91) */
   void* heat_flux;                  /* READ-MODIFY-WRITE: net_ocean_fluxes.T or top_heat_flux */
   void* two_color_surface_flux;

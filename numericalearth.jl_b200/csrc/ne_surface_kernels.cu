@@ -208,6 +208,9 @@ __device__ __forceinline__ void apply_radiation_point(const NeApplyRadiationDesc
     FT SQ = up_o + ab + Qss;
     FT JT = SQ * (1 / (FT)d.medium.reference_density) * (1 / (FT)d.medium.heat_capacity);
     H[idx] += inactive ? (FT)0 : JT;
+  } else if (d.over_sea_ice == 2) {   // land: apply_air_land_radiative_fluxes.jl:79-93 (surface_energy_flux is positive upward)
+    FT SQrad = -up - (ab + tr);
+    H[idx] += inactive ? (FT)0 : -SQrad;
   } else {
     FT SQ = (up + ab + tr) * conc;
     H[idx] += inactive ? (FT)0 : SQ;

@@ -293,6 +293,8 @@ class ComponentInterfaces:
                                      friction_velocity=Z(), temperature_scale=Z(), water_vapor_scale=Z())
             self.al_temperature = Z()
             self.al_iterations = backend.zeros(grid.shape, "i32") if with_iterations else None
+            self.land_surface_energy_flux = Z()     # land.fluxes.surface_energy_flux (positive upward), READ-MODIFY-WRITE
+            self.rad_fluxes_land = _Fields(upwelling_longwave=Z(), downwelling_longwave=Z(), downwelling_shortwave=Z())
         # ocean surface state (pointers to the top-level plane of the 3-D parents)
         self.ocean_state = _Fields(u=Z(), v=Z(), T=Z(), S=Z())
         self.kappa = None
@@ -731,6 +733,26 @@ class ComponentInterfaces:
             b.ptr(r.upwelling_longwave), b.ptr(r.downwelling_longwave), b.ptr(r.downwelling_shortwave)
         return d
 
+    def apply_air_land_radiative_fluxes(self):
+        """apply_air_land_radiative_fluxes!(model) (Radiations/apply_air_land_radiative_fluxes.jl:17-97): needs a `land`
+        entry in the radiation's surface properties."""
+        if self.radiation is None or self.slab_land is None or "land" not in self.radiation.surface_properties:
+            return
+        b, g = self.backend, self.grid
+        d = A.NeApplyRadiationDesc()
+        d.grid = g.pod(False)
+        d.radiation = self._surface_radiation("land")
+        d.concentration = _slot(b, 0.0)
+        d.inactive = _ptr(b, self.inactive)
+        d.over_sea_ice = 2
+        d.surface_temperature = b.ptr(self.al_temperature)
+        d.medium = F.MediumProperties(temperature_units=F.DegreesKelvin()).pod()
+        d.heat_flux = b.ptr(self.land_surface_energy_flux)
+        r = self.rad_fluxes_land
+        d.upwelling_longwave, d.downwelling_longwave, d.downwelling_shortwave = \
+            b.ptr(r.upwelling_longwave), b.ptr(r.downwelling_longwave), b.ptr(r.downwelling_shortwave)
+        self.lib.call("apply_radiative_fluxes", g.FT, d, b.stream())
+
     def apply_air_sea_radiative_fluxes(self):
         if self.radiation is not None:
             self.lib.call("apply_radiative_fluxes", self.grid.FT, self.apply_radiation_desc(False), self.backend.stream())
@@ -754,6 +776,7 @@ class ComponentInterfaces:
         self.update_net_fluxes()
         self.apply_air_sea_radiative_fluxes()
         self.apply_air_sea_ice_radiative_fluxes()
+        self.apply_air_land_radiative_fluxes()
 
     def fused_step_desc(self, t, diagnostics=None) -> A.NeFusedStepDesc:
         """`diagnostics` (a sharding.FluxDiagnostics): its area-weighted sums are accumulated by the kernel that

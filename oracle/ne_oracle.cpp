@@ -1160,6 +1160,9 @@ void apply_radiation(const NeApplyRadiationDesc& d) {
         FT rho_inv = 1 / (FT)d.medium.reference_density, c_inv = 1 / (FT)d.medium.heat_capacity;
         FT JT = SQ * rho_inv * c_inv;
         H[idx] += inactive ? (FT)0 : JT;
+      } else if (d.over_sea_ice == 2) {   // land: apply_air_land_radiative_fluxes.jl:79-93 (surface_energy_flux is positive upward)
+        FT SQrad = -up - (ab + tr);
+        H[idx] += inactive ? (FT)0 : -SQrad;
       } else {
         FT SQ = (up + ab + tr) * conc;
         H[idx] += inactive ? (FT)0 : SQ;

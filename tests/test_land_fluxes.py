@@ -100,9 +100,14 @@ def _case(backend, lib, FT, atm_FT, humidity, **kw):
                            friction_velocity=Z(), temperature_scale=Z(), water_vapor_scale=Z())
     ci.al_temperature = Z()
     ci.al_iterations = backend.zeros(ci.grid.shape, "i32")
+    ci.land_surface_energy_flux = Z()
+    ci.rad_fluxes_land = _Fields(upwelling_longwave=Z(), downwelling_longwave=Z(), downwelling_shortwave=Z())
+    ci.radiation.surface_properties["land"] = F.SurfaceRadiationProperties(0.23, 0.95)
     ci.initialize()
     ci.interpolate_state(T_STEP)
     ci.compute_atmosphere_land_fluxes()
+    ci.land_surface_energy_flux[...] = 3.5          # READ-MODIFY-WRITE: the kernel adds to what is there
+    ci.apply_air_land_radiative_fluxes()
     return ci
 
 
@@ -128,6 +133,19 @@ def test_land_flux_kernel_oracle_properties(oracle_lib, name):
         assert dry.sum() > 50 and (f.water_vapor[inner][dry] <= 0).all()
     # the halo / ring outside `:xy` is not written
     assert (f.latent_heat[: g.hy, :] == 0).all() and (f.latent_heat[g.hy - 1, :] == 0).all()
+    # apply_air_land_radiative_fluxes! (apply_air_land_radiative_fluxes.jl:64-97): Q += σ ε Tₛ⁴ − ε ℐ↓ˡʷ − (1 − α) ℐ↓ˢʷ at active
+    # cells (positive upward), the three diagnostic fluxes everywhere
+    sig, alpha, eps = ci.radiation.stefan_boltzmann_constant, 0.23, 0.95
+    Ts = ci.al_temperature[inner]
+    sw, lw = ci.rad_state.sw[inner], ci.rad_state.lw[inner]
+    up = sig * eps * Ts ** 4
+    act = np.asarray(ci.inactive)[inner] == 0
+    expect = 3.5 + np.where(act, up - eps * lw - (1 - alpha) * sw, 0.0)
+    assert np.abs(ci.land_surface_energy_flux[inner] - expect).max() <= 1e-12 * np.abs(expect).max()
+    r = ci.rad_fluxes_land
+    assert np.abs(r.upwelling_longwave[inner] - up).max() <= 1e-12 * up.max()
+    assert np.abs(r.downwelling_longwave[inner] - eps * lw).max() <= 1e-12 * lw.max()
+    assert np.abs(r.downwelling_shortwave[inner] - (1 - alpha) * sw).max() <= 1e-12 * max(sw.max(), 1.0)
 
 
 @pytest.mark.gpu
@@ -152,6 +170,10 @@ def test_cuda_land_flux_kernel_parity(oracle_lib, cuda_backend, cuda_lib, name, 
         s = float(np.nanmax(np.abs(a))) or 1.0
         assert np.nanmax(np.abs(a - b)[conv]) / s <= tol, f"{name}/{n}: {np.nanmax(np.abs(a - b)[conv]) / s}"
     assert np.array_equal(ref.al_temperature[inner], cuda_backend.to_numpy(dev.al_temperature)[inner])
+    # land radiation kernel: same arithmetic (-fmad=false translation unit): bit-exact
+    assert np.array_equal(ref.land_surface_energy_flux[inner], cuda_backend.to_numpy(dev.land_surface_energy_flux)[inner])
+    for n in ref.rad_fluxes_land.names():
+        assert np.array_equal(getattr(ref.rad_fluxes_land, n)[inner], cuda_backend.to_numpy(getattr(dev.rad_fluxes_land, n))[inner]), n
     # an unknown closure is refused by the library itself
     d = dev.atmosphere_land_desc()
     d.humidity.kind = 9
