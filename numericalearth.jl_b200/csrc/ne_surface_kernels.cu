@@ -424,15 +424,8 @@ static int post_solve(const NeFusedStepDesc* d, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n = (int64_t)L.ni * L.nj;
   const unsigned blocks = diag ? (unsigned)g.n_blocks : (unsigned)((n + 255) / 256);
-  const char* mb = std::getenv("NE_B200_POST_MINB");   // occupancy experiment knob
-  const int minb = mb ? std::atoi(mb) : 4;
-#define NE_POST(NF, RAD, DIAG)                                                                   \
-  do {                                                                                           \
-    if (minb == 2) post_solve_kernel<FT, NF, RAD, DIAG, 2><<<blocks, 256, 0, s>>>(a, r, g, L);      \
-    else if (minb == 3) post_solve_kernel<FT, NF, RAD, DIAG, 3><<<blocks, 256, 0, s>>>(a, r, g, L); \
-    else if (minb == 5) post_solve_kernel<FT, NF, RAD, DIAG, 5><<<blocks, 256, 0, s>>>(a, r, g, L); \
-    else post_solve_kernel<FT, NF, RAD, DIAG, 4><<<blocks, 256, 0, s>>>(a, r, g, L);                \
-  } while (0)
+  // 64 registers (4 CTAs per SM): 0.29 ms; 80 regs 0.35, 122 regs 0.39, 48 regs (spills) 0.33 ms (profiles/r01_notes.md)
+#define NE_POST(NF, RAD, DIAG) post_solve_kernel<FT, NF, RAD, DIAG, 4><<<blocks, 256, 0, s>>>(a, r, g, L)
   if (!diag) NE_POST(4, true, false);
   else if (g.n_fields <= 4) { if (rad) NE_POST(4, true, true); else NE_POST(4, false, true); }
   else if (g.n_fields <= 8) { if (rad) NE_POST(8, true, true); else NE_POST(8, false, true); }
