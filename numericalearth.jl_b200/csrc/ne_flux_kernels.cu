@@ -503,6 +503,7 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
         const unsigned tb = tab_grid(n, 3);
         const bool hs = !d->surface_layer_height.ptr && !d->boundary_layer_height.ptr;
         TabParams TP = tabs->T;
+        TP.far_fm = !TP.general_psi && far_unstable_fm_ok(P);
         TP.log_hd = std::log(d->surface_layer_height.value - P.d_zero);
 #define NE_LAUNCH_TAB3(MB, HS, EXT)                                                                                          \
   do {                                                                                                                  \
@@ -593,6 +594,7 @@ int fused_interp_ao_f64(const NeInterpDesc* atm, const NeInterpDesc* rad, const 
   const unsigned tb = tab_grid(n, 3);
   const bool hs = !d->surface_layer_height.ptr && !d->boundary_layer_height.ptr;
   TabParams TP = tabs->T;
+  TP.far_fm = !TP.general_psi && far_unstable_fm_ok(P);
   TP.log_hd = std::log(d->surface_layer_height.value - P.d_zero);
   NeInterpDesc norad;
   std::memset(&norad, 0, sizeof(norad));

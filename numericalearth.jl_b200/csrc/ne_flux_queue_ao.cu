@@ -36,6 +36,7 @@ static int launch_queue_hs(const NeAtmosOceanDesc& d, const TabParams& T, const 
   prm.P = make_fast_params(d.flux, d.gravitational_acceleration, f32);
   prm.Q = make_front_f32(d.flux, d.gravitational_acceleration);
   prm.T = T;
+  prm.T.far_fm = !T.general_psi && far_unstable_fm_ok(prm.P);
   prm.T.log_hd = f32 ? std::log((double)((float)d.surface_layer_height.value - prm.Q.d_zero))
                      : std::log(d.surface_layer_height.value - prm.P.d_zero);
   uint32_t* counters = queue_counters();

@@ -21,7 +21,7 @@ struct TabParams {
   int32_t same_exp;      // ψ_m and ψ_s stable branches share exp(−min(ζmax, A⁺ζ))
   int32_t general_psi;   // tables fitted to non-Edson stability functions: outside the table → generic closed forms
   int32_t f32_model;     // Float32 model: the generic closed forms take the Float32-rounded parameters
-  int32_t pad_;
+  int32_t far_fm;        // Edson far-unstable closed forms through the branch-free functions (set per launch)
 };
 
 // ---- host: Chebyshev interpolation → monomials in w ∈ [−1, 1] (long double) -------------------------
@@ -225,7 +225,7 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
   T.same_exp = (pm[0] == ps[0] && pm[1] == ps[1]);
   T.general_psi = general ? 1 : 0;
   T.f32_model = f32 ? 1 : 0;
-  T.pad_ = 0;
+  T.far_fm = 0;
   T.log_hd = 0;
   return worst;
 }
@@ -237,8 +237,62 @@ inline bool tab_path_eligible(const NeFluxFormulation& f) {
   return true;
 }
 
+// ---- Edson unstable closed forms for ζ ≤ −2^7 with the branch-free elementary functions -------------------------------
+// The second trip of an unstable point starts from a tiny u★ and lands at ζ ~ −10^3…−10^5, outside the tables: more than
+// half of the active warps pass here once (ncu source counters: 88 076 of 163 178 warp-tiles on C4), and the libdevice
+// closed forms cost 805 SASS instructions per pass (5.9 % of the kernel).  Same formulas
+// (similarity_theory_turbulent_fluxes.jl:501-532, 586-618) with log_pos / sqrt_pos / cbrt_pos and an arctangent that only
+// has to handle large arguments: atan(x) = π/2 − atan(1/x), 1/x ≤ 0.16 here, odd Taylor series to x⁻¹⁹.
+// Requires B⁻ = 2 for ψ_m (P.m_B2; the only value the reference ships) — the caller falls back to libdevice otherwise.
+namespace fm {
+NE_HD double atan_large(double x) {   // x ≥ 6: |error| ≲ 1 ulp of π/2
+  const double y = rcp(x), y2 = y * y;
+  double p = -1.0 / 19.0;
+  p = fma_(p, y2, 1.0 / 17.0);
+  p = fma_(p, y2, -1.0 / 15.0);
+  p = fma_(p, y2, 1.0 / 13.0);
+  p = fma_(p, y2, -1.0 / 11.0);
+  p = fma_(p, y2, 1.0 / 9.0);
+  p = fma_(p, y2, -1.0 / 7.0);
+  p = fma_(p, y2, 1.0 / 5.0);
+  p = fma_(p, y2, -1.0 / 3.0);
+  p = fma_(p, y2, 1.0);
+  return 1.5707963267948966 - y * p;
+}
+}  // namespace fm
+
+NE_HD void psi_far_unstable_fm(const FastParams& P, const TabParams& T, const double* tab, double z, double& pm, double& ps) {
+  const double z2 = z * z;
+  const double fw = 1.0 - fm::rcp(1.0 + z2);                      // ζ²/(1 + ζ²)
+  {  // momentum
+    const double f1 = fm::sqrt_pos(fm::sqrt_pos(1.0 - P.m_Am * z));
+    const double f1s = f1 * f1;
+    const double psi1 = fm::log_pos(tab, T.mc, (1.0 + f1) * (1.0 + f1) * (1.0 + f1s) * 0.125) - 2.0 * fm::atan_large(f1) + P.m_Cm;
+    const double f2 = fm::cbrt_pos(T.mc, 1.0 - P.m_Dm * z);
+    const double psi2 = P.m_halfEm * fm::log_pos(tab, T.mc, (1.0 + f2 + f2 * f2) * P.m_iEm) -
+                        P.m_rEm * fm::atan_large((1.0 + 2.0 * f2) * P.m_irEm) + P.m_Fm;
+    pm = psi1 + fw * (psi2 - psi1);
+  }
+  {  // scalar
+    const double f1 = fm::sqrt_pos(1.0 - P.s_Am * z);
+    const double psi1 = P.s_Bm * fm::log_pos(tab, T.mc, (1.0 + f1) * P.s_iBm) + P.s_Cm;
+    const double f2 = fm::cbrt_pos(T.mc, 1.0 - P.s_Dm * z);
+    const double psi2 = P.s_halfEm * fm::log_pos(tab, T.mc, (1.0 + f2 + f2 * f2) * P.s_iEm) -
+                        P.s_rEm * fm::atan_large((1.0 + 2.0 * f2) * P.s_irEm) + P.s_Fm;
+    ps = psi1 + fw * (psi2 - psi1);
+  }
+}
+// the arguments of atan_large above must stay ≥ 6 for ζ ≤ −2^7: checked on the host for the user's parameters
+inline bool far_unstable_fm_ok(const FastParams& P) {
+  if (!P.m_B2 || !(P.m_Am > 0) || !(P.m_Dm > 0) || !(P.s_Am > 0) || !(P.s_Dm > 0)) return false;
+  const double z = -128.0;
+  const double f1 = std::sqrt(std::sqrt(1.0 - P.m_Am * z));
+  const double a_m = (1.0 + 2.0 * std::cbrt(1.0 - P.m_Dm * z)) * P.m_irEm, a_s = (1.0 + 2.0 * std::cbrt(1.0 - P.s_Dm * z)) * P.s_irEm;
+  return f1 >= 6.0 && a_m >= 6.0 && a_s >= 6.0 && P.m_iEm > 0 && P.s_iEm > 0 && P.s_iBm > 0;
+}
+
 #if defined(__CUDACC__)
-// unstable closed forms through libdevice for |ζ| ≥ 2^7 (free-convection limit; rare)
+// unstable closed forms through libdevice for |ζ| ≥ 2^7 (parameter sets the branch-free version does not cover)
 __device__ __forceinline__ void psi_far_unstable(const FastParams& P, double z, double& pm, double& ps) {
   pm = fast_psi_m(P, z);   // |z| ≥ 2^7 > P.zsmall: the closed-form branch
   ps = fast_psi_s(P, z);
@@ -259,7 +313,8 @@ __device__ __forceinline__ void psi_stable_pair(const FastParams& P, const TabPa
 // closed forms outside the table: stable side with the custom exp, far unstable side through libdevice.
 // Out of line and returning by value, so the common path keeps ψ in registers.
 // ff != nullptr: tables of a non-Edson pair — the generic closed forms of ne_physics.cuh.
-static __device__ __noinline__ double2 psi_outside(const FastParams& P, const TabParams& T, const NeFluxFormulation* ff, double z) {
+static __device__ __noinline__ double2 psi_outside(const FastParams& P, const TabParams& T, const NeFluxFormulation* ff,
+                                                   const double* tab, double z) {
   double pm, ps;
   if (ff && T.f32_model) {
     pm = stability_profile<float, double>(ff->psi_momentum, z);
@@ -268,6 +323,7 @@ static __device__ __noinline__ double2 psi_outside(const FastParams& P, const Ta
     pm = stability_profile<double, double>(ff->psi_momentum, z);
     ps = stability_profile<double, double>(ff->psi_temperature, z);
   } else if (z > 0) psi_stable_pair(P, T, z, pm, ps);
+  else if (T.far_fm) psi_far_unstable_fm(P, T, tab, z, pm, ps);
   else psi_far_unstable(P, z, pm, ps);
   return make_double2(pm, ps);
 }
@@ -280,7 +336,7 @@ __device__ __forceinline__ void tab_psi_pair(const FastParams& P, const TabParam
   if (!outside) {
     fm::psi_pair(tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(z), pm, ps);
   } else {
-    const double2 r = psi_outside(P, T, ff, z);
+    const double2 r = psi_outside(P, T, ff, tab, z);
     pm = r.x; ps = r.y;
   }
 }

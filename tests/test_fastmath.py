@@ -42,6 +42,12 @@ def test_psi_tables_reproduce_the_closed_forms(report):
     assert report["interval_logic_ok"] == 1
 
 
+def test_far_unstable_closed_forms_with_branch_free_functions(report):
+    """ζ ≤ −2^7 (the second trip of an unstable point): log_pos / sqrt_pos / cbrt_pos / atan_large against long double."""
+    assert report["psi_far_err"] <= 2e-15
+    assert report["atan_large_abs"] <= 4e-16
+
+
 def test_general_psi_tables_sea_ice_and_large_yeager_pairs(report):
     """The same piecewise polynomials fitted to Split(SHEBA, Paulson) (the atmosphere-sea-ice default,
     similarity_theory_turbulent_fluxes.jl:779-789) and Split(LinearStable, Paulson) (:766-771)."""

@@ -169,6 +169,25 @@ int main() {
       if (!(es <= e_tiny)) e_tiny = es;
     }
   }
+  // far-unstable closed forms with the branch-free functions (ζ ≤ −2^7) against long double
+  double e_far = 0, e_atan = 0;
+  {
+    const FastParams P = make_fast_params(f, 9.80665);
+    std::uniform_real_distribution<double> u(0, 1);
+    for (int i = 0; i < 200000; ++i) {
+      const double az = std::exp(std::log(128.0) + u(rng) * (std::log(1e9) - std::log(128.0)));
+      double m, s2;
+      psi_far_unstable_fm(P, T, tab, -az, m, s2);
+      const long double tm = psi_m_unstable_ld(pm, -(long double)az), ts = psi_s_unstable_ld(ps, -(long double)az);
+      const double em = (double)(fabsl((long double)m - tm) / fmaxl(1, fabsl(tm))), es = (double)(fabsl((long double)s2 - ts) / fmaxl(1, fabsl(ts)));
+      if (!(em <= e_far)) e_far = em;
+      if (!(es <= e_far)) e_far = es;
+      const double x = 6.0 + az * 1e-3;
+      const double ea = (double)fabsl((long double)fm::atan_large(x) - atanl((long double)x));
+      if (!(ea <= e_atan)) e_atan = ea;
+    }
+    if (!far_unstable_fm_ok(P)) e_far = 1e300;
+  }
   NeFluxFormulation fi, fl;
   sea_ice_formulation(fi);
   large_yeager_formulation(fl);
@@ -176,7 +195,8 @@ int main() {
   TabParams Ti, Tl;
   const double fit_i = build_solver_tables(fi, tab_i, Ti), fit_l = build_solver_tables(fl, tab_l, Tl);
   const double dense_i = dense_general(fi, tab_i, rng), dense_l = dense_general(fl, tab_l, rng);
-  printf("{\"psi_seaice_fit_err\": %.3e, \"psi_seaice_dense_err\": %.3e, \"psi_seaice_general\": %d, "
+  printf("{\"psi_far_err\": %.3e, \"atan_large_abs\": %.3e, ", e_far, e_atan);
+  printf("\"psi_seaice_fit_err\": %.3e, \"psi_seaice_dense_err\": %.3e, \"psi_seaice_general\": %d, "
          "\"psi_ly_fit_err\": %.3e, \"psi_ly_dense_err\": %.3e, ", fit_i, dense_i, Ti.general_psi, fit_l, dense_l);
   printf("\"rcp_ulp\": %.3f, \"div_ulp\": %.3f, \"sqrt_ulp\": %.3f, \"cbrt_ulp\": %.3f, \"cbrt_wide_ulp\": %.3f, "
          "\"log_ulp_small\": %.3f, \"log_ulp_large\": %.3f, \"log_abs_near1_ulp1\": %.3f, \"exp_ulp\": %.3f, \"exp_ulp_mid\": %.3f, "
