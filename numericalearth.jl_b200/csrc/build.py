@@ -28,6 +28,7 @@ SOURCES = {
     "ne_flux_generic_al_f32.cu": [],
     "ne_flux_queue_ao.cu": [],
     "ne_flux_queue_asi.cu": [],
+    "ne_flux_queue_land.cu": [],
     "ne_interp_kernels.cu": ["-fmad=false"],
     "ne_surface_kernels.cu": ["-fmad=false"],
     "ne_fused.cu": [],
@@ -37,7 +38,7 @@ COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-st
           "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 DEPS = ["ne_common.cuh", "ne_physics.cuh", os.path.join("..", "..", "include", "ne_b200.h")]
 EXTRA_DEPS = {
-    "ne_flux_kernels.cu": ["ne_flux_fast.cuh", "ne_flux_tab.cuh", "ne_flux_queue.cuh", "ne_flux_asi_fast.cuh", "ne_queue_host.cuh", "ne_fastmath.cuh", "ne_interp_device.cuh"],
+    "ne_flux_kernels.cu": ["ne_flux_fast.cuh", "ne_flux_tab.cuh", "ne_flux_queue.cuh", "ne_flux_asi_fast.cuh", "ne_flux_land_fast.cuh", "ne_queue_host.cuh", "ne_fastmath.cuh", "ne_interp_device.cuh"],
     "ne_interp_kernels.cu": ["ne_interp_device.cuh"],
     "ne_flux_generic_ao_f64.cu": ["ne_flux_generic.cuh"],
     "ne_flux_generic_ao_f32.cu": ["ne_flux_generic.cuh"],
@@ -46,6 +47,7 @@ EXTRA_DEPS = {
     "ne_flux_generic_al.cu": ["ne_flux_generic.cuh"],
     "ne_flux_generic_al_f32.cu": ["ne_flux_generic.cuh"],
     "ne_flux_queue_ao.cu": ["ne_flux_fast.cuh", "ne_flux_tab.cuh", "ne_fastmath.cuh", "ne_flux_queue.cuh", "ne_queue_host.cuh"],
+    "ne_flux_queue_land.cu": ["ne_flux_fast.cuh", "ne_flux_tab.cuh", "ne_fastmath.cuh", "ne_flux_queue.cuh", "ne_flux_land_fast.cuh", "ne_queue_host.cuh"],
     "ne_flux_queue_asi.cu": ["ne_flux_fast.cuh", "ne_flux_tab.cuh", "ne_fastmath.cuh", "ne_flux_queue.cuh", "ne_flux_asi_fast.cuh", "ne_queue_host.cuh"],
     "ne_fused.cu": ["ne_flux_fast.cuh"],
 }

@@ -42,7 +42,8 @@ struct FastParams {
   int32_t wind_waves;       // WindDependentWaveFormulation: 𝒞g = max(0, C1 min(U, Umax) + C2) (roughness_lengths.jl:75)
   double wave_C1, wave_C2, wave_Umax, inv_g_rough;
   double sgs_const2;        // SubgridVelocityCorrection: constant mesoscale term, already squared (:88-98)
-  int32_t pad_opt_;
+  int32_t const_rough;      // constant roughness lengths (the land default, component_interfaces.jl:514-521): ℓu, ℓθ = ℓq fixed
+  double lu_c, ls_c, log_lu_c, log_ls_c;
   // small-|ζ| unstable branch: ψ(ζ) ≈ Σ c_k (ζ/ζs)^k on [-ζs, 0], fitted on the host at Chebyshev nodes in
   // long double from the closed forms (max abs error ≲ 2e-16, checked at fit time; zsmall = 0 disables it)
   double zsmall, zsmall_inv;
@@ -173,7 +174,14 @@ inline FastParams make_fast_params(const NeFluxFormulation& f, double g, bool f3
   P.beta = R(f.subgrid_velocities.gustiness_parameter); P.gmin = R(f.subgrid_velocities.minimum_gustiness);
   P.kappa = R(f.von_karman_constant); P.d_zero = R(f.zero_plane_displacement); P.g = R(g);
   P.tol = R(f.stop.tolerance); P.maxiter = f.stop.maxiter; P.fixed = f.stop.kind == NE_STOP_FIXED_ITERATIONS;
-  P.pad_opt_ = 0;
+  P.const_rough = m.kind == NE_ROUGH_CONSTANT && s.kind == NE_ROUGH_CONSTANT;
+  P.lu_c = R(m.constant); P.ls_c = R(s.constant);
+  P.log_lu_c = P.const_rough ? std::log(P.lu_c) : 0.0;
+  P.log_ls_c = P.const_rough ? std::log(P.ls_c) : 0.0;
+  if (P.const_rough) {   // the roughness-model constants are not used: keep them finite
+    // … and such that tab_core's Reynolds-scaling branch always resolves to the clipped value ℓs = ls_c
+    P.a1 = 0; P.a2 = 0; P.lmax = P.lu_c; P.nu_inv = 1; P.rA = 1; P.log_rA = 700.0; P.rb = 0; P.ls_max = P.ls_c; P.log_ls_max = P.log_ls_c;
+  }
   P.wind_waves = m.wave_kind == NE_WAVE_WIND_DEPENDENT;
   P.wave_C1 = R(m.wave_C1); P.wave_C2 = R(m.wave_C2); P.wave_Umax = R(m.wave_Umax);
   P.inv_g_rough = 1.0 / R(m.gravitational_acceleration);

@@ -24,6 +24,7 @@
 #include "ne_flux_tab.cuh"
 #include "ne_flux_queue.cuh"
 #include "ne_flux_asi_fast.cuh"
+#include "ne_flux_land_fast.cuh"
 #include "ne_queue_host.cuh"
 #include "ne_interp_device.cuh"
 #include "ne_physics.cuh"
@@ -678,8 +679,15 @@ static int al_entry(const NeAtmosLandDesc* d, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const bool ct64 = d->thermo.dtype == NE_F64;
   const bool v64 = std::is_same<FT, double>::value || viscosity_is_f64_literal(d->flux);
-  if (std::is_same<FT, double>::value)
+  if (std::is_same<FT, double>::value) {
+    // the land defaults (constant roughness, tabulatable stability functions, BulkTemperature): work-queue kernel
+    if (land_fast_path_eligible(d->flux, d->properties) && queue_path_ok(d->grid) && !env_flag("NE_B200_FORCE_GENERIC") &&
+        !env_flag("NE_B200_CLOSED_FORM_PSI")) {
+      const SolverTables* tabs = solver_tables(d->flux, false);
+      if (tabs) return ct64 ? launch_land_queue<double>(*d, tabs->T, tabs->dptr, s) : launch_land_queue<float>(*d, tabs->T, tabs->dptr, s);
+    }
     return ct64 ? launch_al<double, double, double>(*d, s) : launch_al<double, float, double>(*d, s);
+  }
   if (ct64) return v64 ? launch_al<float, double, double>(*d, s) : launch_al<float, double, float>(*d, s);
   return v64 ? launch_al<float, float, double>(*d, s) : launch_al<float, float, float>(*d, s);
 }

@@ -415,7 +415,7 @@ __device__ __forceinline__ void tab_iteration(const FastParams& P, const TabPara
   const double ru = fm::rcp(s.ustar);
   // 𝒞g/g: constant, or WindDependentWaveFormulation (roughness_lengths.jl:75) with the gusty wind speed U
   const double a1 = (EXT && P.wind_waves) ? mul_(dmax(0.0, fma_(P.wave_C1, dmin(U, P.wave_Umax), P.wave_C2)), P.inv_g_rough) : P.a1;
-  const double lu = dmin(fma_(mul_(a1, s.ustar), s.ustar, mul_(P.a2, ru)), P.lmax);
+  const double lu = (EXT && P.const_rough) ? P.lu_c : dmin(fma_(mul_(a1, s.ustar), s.ustar, mul_(P.a2, ru)), P.lmax);
   const double Linv = mul_(mul_(mul_(P.kappa, bstar), ru), ru);   // 1/L★ (0 when b★ == 0, i.e. L★ = Inf)
   double chi_u, chi_s;
   tab_core<EXT>(P, T, tab, s.ustar, ru, lu, Linv, s.hd, s.log_hd, chi_u, chi_s, ff);

@@ -60,6 +60,7 @@ inline int queue_theta() {
 
 // launchers (explicitly instantiated in ne_flux_queue_ao.cu / ne_flux_queue_asi.cu); `tab` = device solver table
 template <class FT, class CT> int launch_queue(const NeAtmosOceanDesc& d, const TabParams& T, const double* tab, cudaStream_t s);
+template <class CT> int launch_land_queue(const NeAtmosLandDesc& d, const TabParams& T, const double* tab, cudaStream_t s);
 template <class FT, class CT> int launch_asi_queue(const NeAtmosSeaIceDesc& d, const TabParams& T, const double* tab, cudaStream_t s);
 
 }  // namespace ne

@@ -151,10 +151,27 @@ def test_land_flux_kernel_oracle_properties(oracle_lib, name):
 @pytest.mark.gpu
 @pytest.mark.parametrize("FT,atm_FT", [("f64", "f64"), ("f64", "f32"), ("f32", "f32")])
 @pytest.mark.parametrize("name", sorted(HUMIDITIES))
-def test_cuda_land_flux_kernel_parity(oracle_lib, cuda_backend, cuda_lib, name, FT, atm_FT):
+def test_cuda_land_flux_kernel_parity(oracle_lib, cuda_backend, cuda_lib, monkeypatch, name, FT, atm_FT):
+    """Float64 models take the work-queue kernel with the tabulated Large-Yeager functions (ne_flux_land_fast.cuh), Float32
+    models the generic kernel; both against the oracle, and the Float64 fast path against the generic kernel."""
     ref = _case(ne_b200.NumpyHostBackend(), oracle_lib, FT, atm_FT, HUMIDITIES[name]())
     dev = _case(cuda_backend, None, FT, atm_FT, HUMIDITIES[name]())
     cuda_backend.synchronize()
+    if FT == "f64":
+        monkeypatch.setenv("NE_B200_FORCE_GENERIC", "1")
+        gen = _case(cuda_backend, None, FT, atm_FT, HUMIDITIES[name]())
+        cuda_backend.synchronize()
+        monkeypatch.delenv("NE_B200_FORCE_GENERIC")
+        gi = ref.grid
+        win = (slice(gi.hy, gi.hy + gi.ny), slice(gi.hx, gi.hx + gi.nx))
+        both = (cuda_backend.to_numpy(dev.al_iterations)[win] < 100) & (cuda_backend.to_numpy(gen.al_iterations)[win] < 100)
+        differs = False
+        for n in dev.al_fluxes.names():
+            a, b = cuda_backend.to_numpy(getattr(dev.al_fluxes, n))[win], cuda_backend.to_numpy(getattr(gen.al_fluxes, n))[win]
+            differs |= bool((a != b).any())
+            sc = float(np.nanmax(np.abs(b))) or 1.0
+            assert np.nanmax(np.abs(a - b)[both]) / sc <= 1e-10, f"fast vs generic {name}/{n}: {np.nanmax(np.abs(a - b)[both]) / sc}"
+        assert differs, "the land fast path did not run (results identical to the generic kernel's)"
     g = ref.grid
     inner = (slice(g.hy, g.hy + g.ny), slice(g.hx, g.hx + g.nx))
     ri, di = ref.al_iterations[inner], cuda_backend.to_numpy(dev.al_iterations)[inner]
