@@ -166,6 +166,11 @@ def run_cpu(args, seconds_per_step=1.5, steps=None, warmup=1):
     import oracle
     from numericalearth_jl_b200 import synthetic
     lib = oracle.load()
+    # all the host cores this process may use — torchrun exports OMP_NUM_THREADS=1, which would leave the oracle on one
+    try:
+        lib.dll.neo_set_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        lib.dll.neo_set_threads(os.cpu_count() or 1)
     threads = lib.dll.neo_max_threads()
     full_ny = synthetic.CONFIGS[args.config]["ny"]
     ci, step, _ = cpu_step_factory(args, 8)
