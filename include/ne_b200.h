@@ -368,11 +368,14 @@ typedef struct NeAtmosSeaIceDesc {
  * interface_states.jl:740-777): zero surface velocity, the bulk land temperature as interface temperature
  * (BulkTemperature, the reference's default for land), and a land surface-humidity closure
  * (interface_states.jl:92-229, 585-651).  No masking; launch range `:xy` = (1:nx) x (1:ny).  Temperatures in Kelvin.
- * DryLayerHumidity (dry_layer_humidity.jl) has no kernel variant yet: NE_E_NO_VARIANT.                          */
+ * A depth diagnostic other than StorageBasedDryLayerDepth has no kernel variant: NE_E_NO_VARIANT.                */
 enum { NE_LANDQ_BULK = 0,                 /* BulkHumidity: q_sat(T_s) where saturation > 0, else 0                  */
        NE_LANDQ_FRACTIONAL_CRITICAL = 1,  /* FractionalHumidity(CriticalSaturation): min(S / S_c, 1) q_sat(T_s)      */
        NE_LANDQ_FRACTIONAL_CONSTANT = 2,  /* FractionalHumidity(beta::Number)                                        */
-       NE_LANDQ_SKIN = 3 };               /* SkinHumidity: soil vapor-flux balance, re-solved every trip (:600-651) */
+       NE_LANDQ_SKIN = 3,                 /* SkinHumidity: soil vapor-flux balance, re-solved every trip (:600-651) */
+       NE_LANDQ_DRY_LAYER = 4 };          /* DryLayerHumidity (dry_layer_humidity.jl:81-366): Fick flux through a dry surface
+                                             layer of depth dv(S), blended into the saturated skin with a logistic weight      */
+enum { NE_TORTUOSITY_CONSTANT = 0, NE_TORTUOSITY_POWER_LAW = 1 };   /* dry_layer_humidity.jl: Constant / Millington-Quirk */
 typedef struct NeLandHumidity {
   int32_t kind;
   int32_t phase;                 /* NE_PHASE_LIQUID / NE_PHASE_ICE */
@@ -380,6 +383,12 @@ typedef struct NeLandHumidity {
   double efficiency;             /* FRACTIONAL_CONSTANT */
   double surface_thickness;      /* SKIN: saturation depth d         */
   double vapor_diffusivity;      /* SKIN: soil vapor diffusivity     */
+  /* DRY_LAYER: StorageBasedDryLayerDepth, DryLayerVaporPistonVelocity, thermal exchange depth, porosity */
+  double maximum_dry_layer_depth, dry_layer_onset_saturation, dry_layer_exponent;
+  double minimum_dry_layer_depth, molecular_diffusivity, wet_transition_width;
+  double thermal_exchange_depth, porosity;
+  int32_t tortuosity;
+  int32_t pad_;
 } NeLandHumidity;
 typedef struct NeAtmosLandDesc {
   NeExchangeGrid grid;

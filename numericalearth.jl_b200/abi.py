@@ -188,12 +188,16 @@ class NeAtmosSeaIceDesc(C.Structure):
                 ("interface_temperature", vp), ("iterations", vp)]
 
 
-NE_LANDQ_BULK, NE_LANDQ_FRACTIONAL_CRITICAL, NE_LANDQ_FRACTIONAL_CONSTANT, NE_LANDQ_SKIN = 0, 1, 2, 3
+NE_LANDQ_BULK, NE_LANDQ_FRACTIONAL_CRITICAL, NE_LANDQ_FRACTIONAL_CONSTANT, NE_LANDQ_SKIN, NE_LANDQ_DRY_LAYER = 0, 1, 2, 3, 4
+NE_TORTUOSITY_CONSTANT, NE_TORTUOSITY_POWER_LAW = 0, 1
 
 
 class NeLandHumidity(C.Structure):
     _fields_ = [("kind", i32), ("phase", i32), ("critical_saturation", f64), ("efficiency", f64),
-                ("surface_thickness", f64), ("vapor_diffusivity", f64)]
+                ("surface_thickness", f64), ("vapor_diffusivity", f64),
+                ("maximum_dry_layer_depth", f64), ("dry_layer_onset_saturation", f64), ("dry_layer_exponent", f64),
+                ("minimum_dry_layer_depth", f64), ("molecular_diffusivity", f64), ("wet_transition_width", f64),
+                ("thermal_exchange_depth", f64), ("porosity", f64), ("tortuosity", i32), ("pad_", i32)]
 
 
 class NeAtmosLandDesc(C.Structure):

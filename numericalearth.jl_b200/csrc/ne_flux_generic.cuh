@@ -72,6 +72,35 @@ struct InterfaceSolver {
       CT qv = saturation_specific_humidity(Ts, a.p, h.phase);
       return (FT)(h.efficiency * qv);   // β::Number keeps its own (Float64) type
     }
+    if (h.kind == NE_LANDQ_DRY_LAYER) {   // compute_interface_humidity(::DryLayerHumidity) dry_layer_humidity.jl
+      auto rho_d = th.air_density(a.T, a.p, a.q);
+      const FT S = land_saturation, Tin = Ts, Tla = land_T;
+      const FT sc = mn(S / (FT)h.dry_layer_onset_saturation, (FT)1);
+      const FT dv = (FT)h.maximum_dry_layer_depth * m_pow(mx((FT)1 - sc, (FT)0), (FT)h.dry_layer_exponent);
+      const FT dvmin = (FT)h.minimum_dry_layer_depth, lT = (FT)h.thermal_exchange_depth;
+      const FT chi = clampv<FT>(dv / lT, (FT)0, (FT)1);
+      const FT Te = Tin + chi * (Tla - Tin);
+      CT qe = saturation_specific_humidity(Te, a.p, h.phase);
+      const FT theta_l = S * (FT)h.porosity;
+      FT Dv;
+      if (h.tortuosity == NE_TORTUOSITY_CONSTANT) Dv = (FT)h.molecular_diffusivity;
+      else {
+        const FT nu = (FT)h.porosity, tg = mx(nu - theta_l, (FT)0);
+        Dv = (FT)h.molecular_diffusivity * m_pow(tg, (FT)10 / (FT)3) / (nu * nu);
+      }
+      auto Ge = rho_d * Dv / mx(dv, dvmin);
+      auto Jd = -rho_d * ustar * q_star;
+      FT dqd = qs - a.q;
+      auto Dd = Ge * dqd + Jd;
+      auto qbal = (Ge * qe * dqd + Jd * a.q) / Dd;
+      qbal = (Dd == 0) ? (decltype(qbal))qs : qbal;
+      CT qinp = saturation_specific_humidity(Tin, a.p, h.phase);
+      const FT dvw = (FT)h.wet_transition_width;
+      const FT eps_ft = std::is_same<FT, double>::value ? (FT)2.220446049250313e-16 : (FT)1.1920929e-07f;
+      const FT z = 10 * (dv - dvmin - dvw / 2) / mx(dvw, eps_ft);
+      const FT sigma = 1 / (1 + m_exp(-z));
+      return (FT)(qinp + sigma * (qbal - qinp));
+    }
     auto rho_a = th.air_density(a.T, a.p, a.q);
     CT qv = saturation_specific_humidity(land_T, a.p, h.phase);
     double gs = h.vapor_diffusivity / h.surface_thickness;
@@ -227,7 +256,7 @@ struct InterfaceSolver {
       bool go = fixed ? (it < maxiter) : (!((drift < tol) | (it >= maxiter)) | (it == 0));
       if (!go) break;
       if (!bulk) Ts = skin_temperature(theta_a);
-      if (!bulk || it == 0 || (landq && landq->kind == NE_LANDQ_SKIN)) {
+      if (!bulk || it == 0 || (landq && (landq->kind == NE_LANDQ_SKIN || landq->kind == NE_LANDQ_DRY_LAYER))) {
         qs = landq ? land_humidity() : surface_specific_humidity<FT, CT>(ip, th, a.p, Ts, ICE ? (FT)0 : surf_S);
         dq = a.q - qs;
         dtheta = theta_a - Ts;

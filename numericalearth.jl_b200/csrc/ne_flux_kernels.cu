@@ -671,8 +671,13 @@ static int al_entry(const NeAtmosLandDesc* d, void* stream) {
   if (d->properties.temperature_formulation != NE_TEMP_BULK)
     NE_NO_VARIANT("atmosphere-land: only BulkTemperature has a kernel variant (the reference's default for land)");
   const NeLandHumidity& h = d->humidity;
-  if (h.kind < NE_LANDQ_BULK || h.kind > NE_LANDQ_SKIN)
-    NE_NO_VARIANT("land humidity formulation %d has no kernel variant (DryLayerHumidity is not built)", h.kind);
+  if (h.kind < NE_LANDQ_BULK || h.kind > NE_LANDQ_DRY_LAYER)
+    NE_NO_VARIANT("land humidity formulation %d has no kernel variant", h.kind);
+  if (h.kind == NE_LANDQ_DRY_LAYER) {
+    if (h.tortuosity != NE_TORTUOSITY_CONSTANT && h.tortuosity != NE_TORTUOSITY_POWER_LAW) NE_NO_VARIANT("tortuosity model with no kernel variant");
+    NE_REQUIRE(h.dry_layer_onset_saturation > 0 && h.thermal_exchange_depth > 0 && h.minimum_dry_layer_depth > 0 && h.porosity > 0,
+               "DryLayerHumidity: onset saturation, thermal exchange depth, minimum dry-layer depth and porosity must be positive");
+  }
   if (h.phase != NE_PHASE_LIQUID && h.phase != NE_PHASE_ICE) NE_NO_VARIANT("unknown thermodynamic phase");
   if (h.kind == NE_LANDQ_FRACTIONAL_CRITICAL) NE_REQUIRE(h.critical_saturation > 0, "CriticalSaturation must be positive");
   if (h.kind == NE_LANDQ_SKIN) NE_REQUIRE(h.surface_thickness > 0, "SkinHumidity: surface_thickness must be positive");

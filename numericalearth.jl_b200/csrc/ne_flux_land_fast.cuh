@@ -15,8 +15,11 @@ namespace ne {
 struct LandPoint {
   FastPoint f;                 // invariants of the similarity step + the iterate (u★, θ★, q★)
   double Ts, ap, aq;           // interface (= bulk land) temperature, atmosphere pressure and humidity
-  double rho_a, qv_res;        // SkinHumidity: air density, reservoir saturation q⁺(T_bulk)
-  double qs;                   // surface specific humidity (carried by SkinHumidity)
+  // SkinHumidity / DryLayerHumidity (vapor-flux balances re-solved every trip): air density, conductance G (κ/d, or
+  // ρₐ Dᵛ / max(δᵛ, δᵛmin)), source humidity (reservoir / evaporation front), saturated-skin value and logistic weight
+  // (SkinHumidity: q⁺ unused, σ = 1)
+  double rho_a, G, q_src, q_sat_skin, sigma;
+  double qs;                   // surface specific humidity (carried from trip to trip by the balances)
 };
 
 template <class CT>
@@ -96,9 +99,32 @@ struct LandProblem {
     s.f.log_hd = HS ? p.T.log_hd : log(s.f.hd);
     s.f.dtheta = (aT + p.P.g * az / p.th.cp_m(aq)) - s.Ts;
     const NeLandHumidity& h = d.humidity;
-    if (h.kind == NE_LANDQ_SKIN) {
+    if (h.kind == NE_LANDQ_SKIN || h.kind == NE_LANDQ_DRY_LAYER) {
       s.rho_a = p.th.air_density(aT, ap, aq);
-      s.qv_res = qsat(p, s.Ts, ap);                     // the reservoir sits at the bulk land temperature (= T_s under BulkTemperature)
+      if (h.kind == NE_LANDQ_SKIN) {
+        s.G = h.vapor_diffusivity / h.surface_thickness;
+        s.q_src = qsat(p, s.Ts, ap);                    // the reservoir sits at the bulk land temperature (= T_s under BulkTemperature)
+        s.q_sat_skin = 0; s.sigma = 1;
+      } else {   // dry_layer_humidity.jl: under BulkTemperature T_in = T_la, so everything but the balance itself is invariant
+        const FT S = slot_at<FT>(d.saturation, idx), Tin = s.Ts, Tla = s.Ts;
+        const FT sc = mn(S / (FT)h.dry_layer_onset_saturation, (FT)1);
+        const FT dv = (FT)h.maximum_dry_layer_depth * pow(mx((FT)1 - sc, (FT)0), (FT)h.dry_layer_exponent);
+        const FT dvmin = (FT)h.minimum_dry_layer_depth;
+        const FT chi = clampv<FT>(dv / (FT)h.thermal_exchange_depth, (FT)0, (FT)1);
+        const FT Te = Tin + chi * (Tla - Tin);
+        s.q_src = qsat(p, Te, ap);
+        const FT theta_l = S * (FT)h.porosity;
+        FT Dv = (FT)h.molecular_diffusivity;
+        if (h.tortuosity != NE_TORTUOSITY_CONSTANT) {
+          const FT nu = (FT)h.porosity, tg = mx(nu - theta_l, (FT)0);
+          Dv = (FT)h.molecular_diffusivity * pow(tg, (FT)10 / (FT)3) / (nu * nu);
+        }
+        s.G = s.rho_a * Dv / mx(dv, dvmin);
+        s.q_sat_skin = qsat(p, Tin, ap);
+        const FT dvw = (FT)h.wet_transition_width;
+        const FT z = 10 * (dv - dvmin - dvw / 2) / mx(dvw, (FT)2.220446049250313e-16);
+        s.sigma = 1 / (1 + exp(-z));
+      }
       if (fresh) set_humidity(p, s, (FT)qsat(p, s.Ts, ap));   // initial qₛ (:205); replaced before the first similarity step
     } else {
       const FT S = slot_at<FT>(d.saturation, idx);
@@ -108,7 +134,7 @@ struct LandProblem {
       else if (h.kind == NE_LANDQ_FRACTIONAL_CRITICAL) qs = (FT)(mn(S / (FT)h.critical_saturation, (FT)1) * qv);
       else qs = (FT)(h.efficiency * qv);
       set_humidity(p, s, qs);
-      s.rho_a = 0; s.qv_res = 0;
+      s.rho_a = 0; s.G = 0; s.q_src = 0; s.q_sat_skin = 0; s.sigma = 0;
     }
     if (fresh) s.f.ustar = s.f.theta_star = s.f.q_star = 1e-4;   // convert(FT, 1e-4) :204
   }
@@ -117,13 +143,13 @@ struct LandProblem {
 
   __device__ static __forceinline__ FT trip(const Params& p, const double* tab, Point& s, int) {
     const NeLandHumidity& h = p.d.humidity;
-    if (h.kind == NE_LANDQ_SKIN) {   // compute_interface_humidity(::SkinHumidity) :625-651 with the previous iterate
-      const double gs = h.vapor_diffusivity / h.surface_thickness;
+    if (h.kind == NE_LANDQ_SKIN || h.kind == NE_LANDQ_DRY_LAYER) {
+      // compute_interface_humidity(::SkinHumidity) :625-651 / (::DryLayerHumidity) with the previous iterate
       const FT Ja = -s.rho_a * s.f.ustar * s.f.q_star;
       const FT dq = s.qs - s.aq;
-      const FT D = gs * dq + Ja;
-      const FT q = (gs * s.qv_res * dq + Ja * s.aq) / D;
-      set_humidity(p, s, (D == 0) ? s.qs : q);
+      const FT D = s.G * dq + Ja;
+      const FT qbal = (D == 0) ? s.qs : (s.G * s.q_src * dq + Ja * s.aq) / D;
+      set_humidity(p, s, h.kind == NE_LANDQ_SKIN ? qbal : s.q_sat_skin + s.sigma * (qbal - s.q_sat_skin));
     }
     const FT pu = s.f.ustar, pt = s.f.theta_star, pq = s.f.q_star;
     tab_iteration<true>(p.P, p.T, tab, s.f, p.T.general_psi ? &p.d.flux : nullptr);

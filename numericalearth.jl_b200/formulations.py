@@ -583,8 +583,40 @@ class SkinHumidity:  # :208-219, solved inside the iteration :625-651
     phase: Any = field(default_factory=Liquid)
 
 
-class DryLayerHumidity:  # dry_layer_humidity.jl — no kernel variant yet
+@dataclass
+class StorageBasedDryLayerDepth:  # dry_layer_humidity.jl: δᵛ(𝒮) = δᵛmax [1 − min(𝒮/𝒮ᶜ, 1)]^η
+    maximum_dry_layer_depth: float = 0.05
+    dry_layer_onset_saturation: float = 0.5
+    dry_layer_exponent: float = 2.0
+
+
+class ConstantTortuosity:
     pass
+
+
+class PowerLawTortuosity:  # Millington–Quirk
+    pass
+
+
+@dataclass
+class DryLayerVaporPistonVelocity:
+    minimum_dry_layer_depth: float = 1e-4
+    molecular_diffusivity: float = 2.5e-5
+    wet_transition_width: Any = None            # default 5 δᵛmin
+    tortuosity: Any = field(default_factory=ConstantTortuosity)
+
+    def __post_init__(self):
+        if self.wet_transition_width is None:
+            self.wet_transition_width = 5 * self.minimum_dry_layer_depth
+
+
+@dataclass
+class DryLayerHumidity:  # dry_layer_humidity.jl
+    dry_layer_depth: Any = field(default_factory=StorageBasedDryLayerDepth)
+    vapor_exchange: Any = field(default_factory=DryLayerVaporPistonVelocity)
+    thermal_exchange_depth: float = 0.10
+    porosity: float = 0.4
+    phase: Any = field(default_factory=Liquid)
 
 
 def land_humidity_pod(q) -> A.NeLandHumidity:
@@ -603,8 +635,24 @@ def land_humidity_pod(q) -> A.NeLandHumidity:
             raise NoKernelVariantError("SkinHumidity with a wetness-dependent surface thickness has no kernel variant")
         h.kind = A.NE_LANDQ_SKIN
         h.surface_thickness, h.vapor_diffusivity = float(q.surface_thickness), float(q.vapor_diffusivity)
+    elif isinstance(q, DryLayerHumidity):
+        dd, vx = q.dry_layer_depth, q.vapor_exchange
+        if not isinstance(dd, StorageBasedDryLayerDepth) or not isinstance(vx, DryLayerVaporPistonVelocity):
+            raise NoKernelVariantError("DryLayerHumidity: only StorageBasedDryLayerDepth + DryLayerVaporPistonVelocity have a kernel variant")
+        h.kind = A.NE_LANDQ_DRY_LAYER
+        h.maximum_dry_layer_depth, h.dry_layer_onset_saturation = float(dd.maximum_dry_layer_depth), float(dd.dry_layer_onset_saturation)
+        h.dry_layer_exponent = float(dd.dry_layer_exponent)
+        h.minimum_dry_layer_depth, h.molecular_diffusivity = float(vx.minimum_dry_layer_depth), float(vx.molecular_diffusivity)
+        h.wet_transition_width = float(vx.wet_transition_width)
+        if isinstance(vx.tortuosity, ConstantTortuosity):
+            h.tortuosity = A.NE_TORTUOSITY_CONSTANT
+        elif isinstance(vx.tortuosity, PowerLawTortuosity):
+            h.tortuosity = A.NE_TORTUOSITY_POWER_LAW
+        else:
+            raise NoKernelVariantError(f"tortuosity {vx.tortuosity!r} has no kernel variant")
+        h.thermal_exchange_depth, h.porosity = float(q.thermal_exchange_depth), float(q.porosity)
     else:
-        raise NoKernelVariantError(f"land humidity formulation {q!r} has no kernel variant (DryLayerHumidity is not built)")
+        raise NoKernelVariantError(f"land humidity formulation {q!r} has no kernel variant")
     if isinstance(q.phase, Liquid):
         h.phase = A.NE_PHASE_LIQUID
     elif isinstance(q.phase, Ice):

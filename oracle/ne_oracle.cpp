@@ -508,6 +508,33 @@ inline FT land_interface_humidity(const LandSurface<FT>& land, const Thermo<CT>&
     CT qv = saturation_specific_humidity<CT>(th, Ts, a.p, h.phase);
     return (FT)(h.efficiency * qv);   // β::Number keeps its own (Float64) type
   }
+  if (h.kind == NE_LANDQ_DRY_LAYER) {   // compute_interface_humidity(::DryLayerHumidity) dry_layer_humidity.jl
+    auto rho_a = th.air_density(a.T, a.p, a.q);
+    const FT S = land.saturation, Tin = Ts, Tla = land.T_bulk;
+    const FT sc = m_min<FT>(S / (FT)h.dry_layer_onset_saturation, (FT)1);
+    const FT dv = (FT)h.maximum_dry_layer_depth * m_pow(m_max<FT>((FT)1 - sc, (FT)0), (FT)h.dry_layer_exponent);
+    const FT dvmin = (FT)h.minimum_dry_layer_depth, lT = (FT)h.thermal_exchange_depth;
+    const FT chi = m_clamp<FT>(dv / lT, (FT)0, (FT)1);
+    const FT Te = Tin + chi * (Tla - Tin);
+    CT qe = saturation_specific_humidity<CT>(th, Te, a.p, h.phase);
+    const FT theta_l = S * (FT)h.porosity;
+    FT Dv;
+    if (h.tortuosity == NE_TORTUOSITY_CONSTANT) Dv = (FT)h.molecular_diffusivity;
+    else {
+      const FT nu = (FT)h.porosity, tg = m_max<FT>(nu - theta_l, (FT)0);
+      Dv = (FT)h.molecular_diffusivity * m_pow(tg, (FT)10 / (FT)3) / (nu * nu);
+    }
+    auto Ge = rho_a * Dv / m_max<FT>(dv, dvmin);
+    auto Ja = -rho_a * s.ustar * s.q_star;
+    FT dq = s.q - a.q;
+    auto D = Ge * dq + Ja;
+    auto qbal = (D == 0) ? (decltype((Ge * qe * dq + Ja * a.q) / D))s.q : (Ge * qe * dq + Ja * a.q) / D;
+    CT qinp = saturation_specific_humidity<CT>(th, Tin, a.p, h.phase);
+    const FT dvw = (FT)h.wet_transition_width;
+    const FT z = 10 * (dv - dvmin - dvw / 2) / m_max<FT>(dvw, std::numeric_limits<FT>::epsilon());
+    const FT sigma = 1 / (1 + m_exp(-z));
+    return (FT)(qinp + sigma * (qbal - qinp));
+  }
   // SkinHumidity
   auto rho_a = th.air_density(a.T, a.p, a.q);
   CT qv = saturation_specific_humidity<CT>(th, land.T_bulk, a.p, h.phase);

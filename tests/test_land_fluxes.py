@@ -69,7 +69,52 @@ def test_fractional_and_bulk_humidity_reference_kat(oracle_lib):
     assert _q(oracle_lib, bh, Ts, Ts, 0.0, 0.3, 0.0, 0.0) == 0.0
     assert _q(oracle_lib, bh, Ts, Ts, 1e-6, 0.3, 0.0, 0.0) == qv
     with pytest.raises(ne_b200.NoKernelVariantError):
-        F.land_humidity_pod(F.DryLayerHumidity())
+        F.land_humidity_pod(F.DryLayerHumidity(dry_layer_depth=lambda S: 0.01))   # a user closure: no kernel variant
+
+
+def _dry(eta=1.0, D0=2.5e-5, width=None, tort=None):
+    return F.DryLayerHumidity(
+        dry_layer_depth=F.StorageBasedDryLayerDepth(maximum_dry_layer_depth=0.05, dry_layer_onset_saturation=0.5, dry_layer_exponent=eta),
+        vapor_exchange=F.DryLayerVaporPistonVelocity(minimum_dry_layer_depth=1e-4, molecular_diffusivity=D0, wet_transition_width=width,
+                                                     tortuosity=tort or F.ConstantTortuosity()),
+        thermal_exchange_depth=0.10, porosity=0.4)
+
+
+def test_dry_layer_humidity_reference_kats(oracle_lib):
+    """test/test_dry_layer_humidity.jl:30-140: wet branch, vapor divider, T_e interpolation, G_e -> 0, wet-transition blend."""
+    p, qa, Ta, us, qst, qprev = 1.0e5, 1.0e-2, 295.0, 0.3, -2.0e-4, 0.005
+    kw = dict(p=p, qa=qa, Ta=Ta)
+    # wet branch: S = S_c -> dv = 0 -> q_in = q_sat(T_in) (sharp switch)
+    q = _q(oracle_lib, _dry(eta=2.0, width=0.0), 300.0, 290.0, 0.5, us, qst, qprev, **kw)
+    assert abs(q - _qsat(oracle_lib, 300.0, p)) <= 1e-15
+    # vapor divider, fully dry: dv = dv_max = 0.05, chi = 0.5, T_e = (T_in + T_la) / 2
+    q = _q(oracle_lib, _dry(), 300.0, 290.0, 0.0, us, qst, qprev, **kw)
+    th = _thermo()
+    Rd, Rv = th.gas_constant / th.dry_air_molar_mass, th.gas_constant / th.water_molar_mass
+    rho = p / ((Rd * (1 - qa) + Rv * qa) * Ta)
+    qe = _qsat(oracle_lib, 295.0, p)
+    Ge, Ja, dq = rho * 2.5e-5 / 0.05, -rho * us * qst, qprev - qa
+    expected = (Ge * qe + Ja / dq * qa) / (Ge + Ja / dq)
+    # the logistic weight at dv = 0.05, dv_min = 1e-4, width 5e-4 is 1 to machine precision
+    assert abs(q - expected) <= 1e-15
+    # T_e interpolation: dry source is colder than the skin -> q_dry < q_wet = q_sat(T_in)
+    qd = _q(oracle_lib, _dry(width=0.0), 310.0, 290.0, 0.0, us, qst, qprev, **kw)
+    qw = _q(oracle_lib, _dry(width=0.0), 310.0, 290.0, 0.5, us, qst, qprev, **kw)
+    assert abs(qw - _qsat(oracle_lib, 310.0, p)) <= 1e-15 and qd < qw
+    # G_e -> 0: the atmospheric flux drives q_in to q_at
+    q = _q(oracle_lib, _dry(D0=1e-14), 300.0, 290.0, 0.0, us, qst, qprev, **kw)
+    assert abs(q - qa) <= 1e-6
+    # wet-transition blend: monotone in dv between the saturated skin and the series solution, sigma = 1/2 at the centre
+    w = 5e-3
+    centre_S = 0.5 * (1 - (1e-4 + w / 2) / 0.05)          # eta = 1: dv = dv_max (1 - S / S_c)
+    q_mid = _q(oracle_lib, _dry(width=w), 300.0, 290.0, centre_S, us, qst, qprev, **kw)
+    q_sat = _qsat(oracle_lib, 300.0, p)
+    q_ser = _q(oracle_lib, _dry(width=0.0), 300.0, 290.0, centre_S, us, qst, qprev, **kw)
+    assert abs(q_mid - 0.5 * (q_sat + q_ser)) <= 1e-9
+    # Millington-Quirk tortuosity lowers the diffusivity of a moist soil: closer to q_at than with constant tortuosity
+    qc = _q(oracle_lib, _dry(), 300.0, 290.0, 0.2, us, qst, qprev, **kw)
+    qp = _q(oracle_lib, _dry(tort=F.PowerLawTortuosity()), 300.0, 290.0, 0.2, us, qst, qprev, **kw)
+    assert abs(qp - qa) < abs(qc - qa)
 
 
 HUMIDITIES = {
@@ -77,6 +122,11 @@ HUMIDITIES = {
     "fractional_critical": lambda: F.FractionalHumidity(efficiency=F.CriticalSaturation(0.75)),
     "fractional_constant": lambda: F.FractionalHumidity(efficiency=0.4),
     "skin": lambda: F.SkinHumidity(surface_thickness=0.05, vapor_diffusivity=2e-2),
+    "dry_layer": lambda: F.DryLayerHumidity(
+        dry_layer_depth=F.StorageBasedDryLayerDepth(maximum_dry_layer_depth=0.05, dry_layer_onset_saturation=0.6, dry_layer_exponent=2.0),
+        vapor_exchange=F.DryLayerVaporPistonVelocity(minimum_dry_layer_depth=1e-4, molecular_diffusivity=2.5e-5,
+                                                     tortuosity=F.PowerLawTortuosity()),
+        thermal_exchange_depth=0.10, porosity=0.4),
 }
 
 
