@@ -246,3 +246,21 @@ def test_cuda_land_flux_kernel_parity(oracle_lib, cuda_backend, cuda_lib, monkey
     d.humidity.kind = 9
     with pytest.raises(ne_b200.NoKernelVariantError):
         cuda_lib.call("atmosphere_land_fluxes", FT, d, cuda_backend.stream())
+
+
+@pytest.mark.gpu
+def test_cuda_land_example_configuration(oracle_lib, cuda_backend, cuda_lib):
+    """The configuration of the reference's own land example (examples/era5_forced_slab_land.jl:164-193): DryLayerHumidity,
+    default land fluxes with FixedIterations(8), BulkTemperature — work-queue kernel against the oracle, exactly 8 trips."""
+    kw = dict(atmosphere_land_fluxes=F.default_atmosphere_land_fluxes(solver_stop_criteria=F.FixedIterations(8)))
+    ref = _case(ne_b200.NumpyHostBackend(), oracle_lib, "f64", "f32", HUMIDITIES["dry_layer"](), **kw)
+    dev = _case(cuda_backend, None, "f64", "f32", HUMIDITIES["dry_layer"](), **kw)
+    cuda_backend.synchronize()
+    g = ref.grid
+    inner = (slice(g.hy, g.hy + g.ny), slice(g.hx, g.hx + g.nx))
+    assert (ref.al_iterations[inner] == 8).all() and (cuda_backend.to_numpy(dev.al_iterations)[inner] == 8).all()
+    for n in ref.al_fluxes.names():
+        a = np.asarray(getattr(ref.al_fluxes, n))[inner]
+        b = cuda_backend.to_numpy(getattr(dev.al_fluxes, n))[inner]
+        s = float(np.abs(a).max()) or 1.0
+        assert np.isfinite(b).all() and np.abs(a - b).max() / s <= 2e-6, f"{n}: {np.abs(a - b).max() / s}"   # Float32 q_sat
