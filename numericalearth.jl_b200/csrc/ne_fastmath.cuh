@@ -242,6 +242,11 @@ NE_HD void psi_pair(const double* __restrict__ rec, double az, double& pm, doubl
   pm = poly_eo<PSI_DEG>(rec + 2, 2, w, w2);
   ps = poly_eo<PSI_DEG>(rec + 3, 2, w, w2);
 }
+// one of the two (which = 0: ψ_m, 1: ψ_s): same operations as psi_pair, so the same bits
+NE_HD double psi_single(const double* __restrict__ rec, double az, int which) {
+  const double w = fma_(az, rec[0], rec[1]);
+  return poly_eo<PSI_DEG>(rec + 2 + which, 2, w, w * w);
+}
 // ψ_m(|ζ_u|) and ψ_s(|ζ_s|) for |ζ| < 2^TINY_EXP, both on the side (record) `rec`
 NE_HD void psi_tiny_pair(const double* __restrict__ rec, double azu, double azs, double& pm, double& ps) {
   const double wu = fma_(azu, rec[0], rec[1]), ws = fma_(azs, rec[0], rec[1]);
