@@ -45,10 +45,14 @@ constexpr int PSI_REC = 2 + 2 * (PSI_DEG + 1);         // (a, b) of w = a|ζ| + 
 constexpr int TINY_DEG = 9;                            // |ζ| < 2^TINY_EXP (the ψ(ℓ/L★) terms): low-degree records
 constexpr int TINY_EXP = -7;
 constexpr int TINY_REC = 2 + 2 * (TINY_DEG + 1);       // record 0: unstable side, record 1: stable side
+constexpr int MICRO_DEG = 5;                           // |ζ| < 2^MICRO_EXP: where ψ(ℓ/L★) sits once u★ has left its initial guess
+constexpr int MICRO_EXP = -12;
+constexpr int MICRO_REC = 2 + 2 * (MICRO_DEG + 1);
 constexpr int TAB_LOG = 0;
 constexpr int TAB_PSI = 2 * LOG_N;
 constexpr int TAB_TINY = TAB_PSI + PSI_NI * PSI_REC;
-constexpr int TAB_SIZE = TAB_TINY + 2 * TINY_REC;      // doubles (3344 = 26 752 B)
+constexpr int TAB_MICRO = TAB_TINY + 2 * TINY_REC;
+constexpr int TAB_SIZE = TAB_MICRO + 2 * MICRO_REC;    // doubles (3372 = 26 976 B)
 
 struct MathConsts {
   double logp[LOG_DEG];      // P(r) = Σ logp[k] r^k
@@ -219,6 +223,9 @@ NE_HD int psi_interval(double zeta, bool& outside) {
   i = i > PSI_NQ ? PSI_NQ : i;
   return zeta < 0 ? i : i + PSI_NS;
 }
+NE_HD bool psi_is_micro(double zeta) {
+  return ((hi32(zeta) & 0x7fffffff) >> 20) < 1023 + MICRO_EXP;
+}
 NE_HD bool psi_is_tiny(double zeta) {
   return ((hi32(zeta) & 0x7fffffff) >> 20) < 1023 + TINY_EXP;
 }
@@ -252,6 +259,13 @@ NE_HD void psi_tiny_pair(const double* __restrict__ rec, double azu, double azs,
   const double wu = fma_(azu, rec[0], rec[1]), ws = fma_(azs, rec[0], rec[1]);
   pm = poly_eo<TINY_DEG>(rec + 2, 2, wu, wu * wu);
   ps = poly_eo<TINY_DEG>(rec + 3, 2, ws, ws * ws);
+}
+
+// the same for |ζ| < 2^MICRO_EXP with the degree-MICRO_DEG records
+NE_HD void psi_micro_pair(const double* __restrict__ rec, double azu, double azs, double& pm, double& ps) {
+  const double wu = fma_(azu, rec[0], rec[1]), ws = fma_(azs, rec[0], rec[1]);
+  pm = poly_eo<MICRO_DEG>(rec + 2, 2, wu, wu * wu);
+  ps = poly_eo<MICRO_DEG>(rec + 3, 2, ws, ws * ws);
 }
 
 }  // namespace fm

@@ -219,6 +219,34 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
       if (!(es <= worst)) worst = es;
     }
   }
+  for (int side = 0; side < 2; ++side) {   // |ζ| < 2^MICRO_EXP records
+    const bool stable = side == 1;
+    const long double lo = 0, hi = ldexpl(1, MICRO_EXP);
+    double* rec = tab + TAB_MICRO + side * MICRO_REC;
+    const long double half = (hi - lo) / 2, mid = (hi + lo) / 2;
+    rec[0] = (double)(1 / half);
+    rec[1] = (double)(-mid / half);
+    double cm[MICRO_DEG + 1], cs[MICRO_DEG + 1];
+    auto fmf = [&](long double az) {
+      if (general) return psi_side_ld(gm, az, stable);
+      return stable ? psi_m_stable_ld(pm, az, f32) : psi_m_unstable_ld(pm, -az, f32);
+    };
+    auto fsf = [&](long double az) {
+      if (general) return psi_side_ld(gs, az, stable);
+      return stable ? psi_s_stable_ld(ps, az) : psi_s_unstable_ld(ps, -az, f32);
+    };
+    cheb_fit_monomial(fmf, lo, hi, MICRO_DEG, cm);
+    cheb_fit_monomial(fsf, lo, hi, MICRO_DEG, cs);
+    for (int k = 0; k <= MICRO_DEG; ++k) { rec[2 + 2 * k] = cm[k]; rec[2 + 2 * k + 1] = cs[k]; }
+    for (int n = 0; n <= 48; ++n) {
+      const double az = (double)(lo + (hi - lo) * n / 48.0L);
+      double m, s2;
+      psi_micro_pair(rec, az, az, m, s2);
+      const double em = (double)fabsl((long double)m - fmf(az)), es = (double)fabsl((long double)s2 - fsf(az));
+      if (!(em <= worst)) worst = em;
+      if (!(es <= worst)) worst = es;
+    }
+  }
   const NeSubgridVelocity& g = f.subgrid_velocities;
   const double ratio = g.minimum_gustiness / g.gustiness_parameter;
   T.cbrt_floor = ratio * ratio * ratio / 8;
@@ -385,7 +413,9 @@ __device__ __forceinline__ void tab_core(const FastParams& P, const TabParams& T
   tab_psi_pair(P, T, ff, tab, mul_(dh, Linv), pm_h, ps_h);
   // ψ(ℓ/L★): |ℓ/L★| < 2^-12 except in the first trips from the 1e-4 initial guess
   const double zu = mul_(lu, Linv), zs = mul_(ls, Linv);
-  if (fm::psi_is_tiny(zu) && fm::psi_is_tiny(zs)) {
+  if (fm::psi_is_micro(zu) && fm::psi_is_micro(zs)) {
+    fm::psi_micro_pair(tab + fm::TAB_MICRO + (Linv < 0 ? 0 : fm::MICRO_REC), fabs(zu), fabs(zs), pm_l, ps_l);
+  } else if (fm::psi_is_tiny(zu) && fm::psi_is_tiny(zs)) {
     fm::psi_tiny_pair(tab + fm::TAB_TINY + (Linv < 0 ? 0 : fm::TINY_REC), fabs(zu), fabs(zs), pm_l, ps_l);
   } else {
     const double2 r2 = tab_psi_rare2(P, T, ff, tab, zu, zs);

@@ -39,6 +39,7 @@ def test_psi_tables_reproduce_the_closed_forms(report):
     assert report["psi_fit_err"] <= 1e-15
     assert report["psi_dense_err"] <= 1e-15
     assert report["psi_tiny_abs"] <= 1e-15
+    assert report["psi_micro_abs"] <= 1e-15
     assert report["interval_logic_ok"] == 1
 
 

@@ -169,6 +169,25 @@ int main() {
       if (!(es <= e_tiny)) e_tiny = es;
     }
   }
+  double e_micro = 0;
+  {
+    std::uniform_real_distribution<double> u(0, 1);
+    for (int i = 0; i < 200000; ++i) {
+      double az = std::exp(std::log(1e-14) + u(rng) * (std::log(std::ldexp(0.9999, fm::MICRO_EXP)) - std::log(1e-14)));
+      double m, s2;
+      fm::psi_micro_pair(tab + fm::TAB_MICRO, az, az * 0.7, m, s2);
+      double em = (double)fabsl((long double)m - psi_m_unstable_ld(pm, -(long double)az));
+      double es = (double)fabsl((long double)s2 - psi_s_unstable_ld(ps, -(long double)(az * 0.7)));
+      if (!(em <= e_micro)) e_micro = em;
+      if (!(es <= e_micro)) e_micro = es;
+      fm::psi_micro_pair(tab + fm::TAB_MICRO + fm::MICRO_REC, az, az * 0.7, m, s2);
+      em = (double)fabsl((long double)m - psi_m_stable_ld(pm, (long double)az));
+      es = (double)fabsl((long double)s2 - psi_s_stable_ld(ps, (long double)(az * 0.7)));
+      if (!(em <= e_micro)) e_micro = em;
+      if (!(es <= e_micro)) e_micro = es;
+    }
+    if (!(fm::psi_is_micro(std::ldexp(0.99, fm::MICRO_EXP)) && !fm::psi_is_micro(std::ldexp(1.0, fm::MICRO_EXP)) && fm::psi_is_micro(-1e-9))) e_micro = 1e300;
+  }
   // far-unstable closed forms with the branch-free functions (ζ ≤ −2^7) against long double
   double e_far = 0, e_atan = 0;
   {
@@ -195,7 +214,7 @@ int main() {
   TabParams Ti, Tl;
   const double fit_i = build_solver_tables(fi, tab_i, Ti), fit_l = build_solver_tables(fl, tab_l, Tl);
   const double dense_i = dense_general(fi, tab_i, rng), dense_l = dense_general(fl, tab_l, rng);
-  printf("{\"psi_far_err\": %.3e, \"atan_large_abs\": %.3e, ", e_far, e_atan);
+  printf("{\"psi_far_err\": %.3e, \"atan_large_abs\": %.3e, \"psi_micro_abs\": %.3e, ", e_far, e_atan, e_micro);
   printf("\"psi_seaice_fit_err\": %.3e, \"psi_seaice_dense_err\": %.3e, \"psi_seaice_general\": %d, "
          "\"psi_ly_fit_err\": %.3e, \"psi_ly_dense_err\": %.3e, ", fit_i, dense_i, Ti.general_psi, fit_l, dense_l);
   printf("\"rcp_ulp\": %.3f, \"div_ulp\": %.3f, \"sqrt_ulp\": %.3f, \"cbrt_ulp\": %.3f, \"cbrt_wide_ulp\": %.3f, "
