@@ -58,11 +58,11 @@ DT_STEP = 1200.0
 # of the solve = thread-level DFMA/DMUL/DADD counts (DFMA = 2 flop) over the ncu duration, next to the algorithmic
 # (as-written census) figure of `roofline.achieved`, which the table-driven kernel under-executes by ~8x.
 NCU_C4 = {
-    "ao_traffic_bytes": 470.0e6 + 511.1e6,
+    "ao_traffic_bytes": 467.7e6 + 510.1e6,
     "interp_traffic_bytes": 67.8e6 + 348.7e6,
-    "ao_executed": {"tflops": 12.6, "frac_of_measured_dfma_peak": 0.37, "fp64_pipe_active": 0.558,
-                    "issue_slots_active": 0.630, "lane_efficiency": 0.80,
-                    "source": "profiles/r01_ncu_full_v8_summary.txt + profiles/r01_notes.md"},
+    "ao_executed": {"tflops": 11.8, "frac_of_measured_dfma_peak": 0.35, "fp64_pipe_active": 0.553,
+                    "issue_slots_active": 0.624, "lane_efficiency": 0.80, "flop_per_launch": 1.984e10,
+                    "source": "profiles/r01_ncu_full_v10_summary.txt + profiles/r01_notes.md"},
 }
 
 
