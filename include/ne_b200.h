@@ -543,6 +543,35 @@ typedef struct NeHostStepDesc {
   int64_t row_bytes;         /* (nx + 2 hx) * sizeof(exchange element)                        */
 } NeHostStepDesc;
 
+/* ---- FieldTimeSeries window on the device (ne_series_ring.cu).
+ * The reference keeps Nt_mem slices of each series in memory and, when the two interpolating time indices leave
+ * that window, reloads the WHOLE window synchronously (update_state!(::PrescribedAtmosphere),
+ * src/Atmospheres/prescribed_atmosphere.jl:154-162 -> Oceananigans update_field_time_series! -> set!(fts),
+ * src/DataWrangling/JRA55/JRA55_field_time_series.jl:60-76 and :78-124).  Here the device array of a series is a
+ * RING of n_slots slices: one slice at a time is replaced, on the ring's own copy stream, while the step's kernels
+ * run; `NeTimeInterp.m1/m2` name ring slots.  Loading one slot does what set!(fts) does to one slice:
+ *   raw file slice (nx x ny, x fastest, no halos) in pinned HOST memory
+ *     -> missing value -> NaN, unit conversion (_set_region_kernel!, src/DataWrangling/set_region_data.jl:200-205,
+ *        whole-globe region, no mangling; convert_units, src/DataWrangling/metadata_field.jl:486-525)
+ *     -> interior of the slot, then fill_halo_regions!(fts): periodic in x (test/test_jra55.jl:40-47: fts[Nx+1,..] ==
+ *        fts[1,..]) or mirrored when the source grid is bounded in x, mirrored (zero-flux) in y.
+ * Which time index lives in which slot, and what to prefetch, is host policy (the binding's; series_window.py here). */
+#define NE_RING_MAX_SERIES 16
+enum { NE_CONV_NONE = 0, NE_CONV_NEGATE = 1, NE_CONV_ADD = 2, NE_CONV_SUB = 3, NE_CONV_MUL = 4, NE_CONV_DIV = 5,
+       NE_CONV_MUL_DIV = 6 };   /* d, -d, d + a, d - a, d * a, d / a, d * a / b: each one rounding in the series eltype */
+typedef struct NeSeriesRingDesc {
+  int32_t n_series;            /* series that share the time axis (<= NE_RING_MAX_SERIES)          */
+  int32_t n_slots;             /* Nt_mem: slices each ring holds                                    */
+  int32_t dtype;               /* NE_F32 / NE_F64: element type of the raw slices and of the rings  */
+  int32_t periodic_x;          /* 1: x halos wrap (full-longitude source grid); 0: mirrored         */
+  int64_t nx, ny, hx, hy;      /* source grid; a ring slice is (ny + 2 hy) rows of (nx + 2 hx)      */
+  void* ring[NE_RING_MAX_SERIES];          /* device, n_slots slices each                           */
+  int32_t conv_kind[NE_RING_MAX_SERIES];   /* NE_CONV_*                                             */
+  double conv_a[NE_RING_MAX_SERIES], conv_b[NE_RING_MAX_SERIES];   /* rounded to `dtype` before use */
+  int32_t has_missing[NE_RING_MAX_SERIES]; /* 1: raw values equal to missing_value become NaN       */
+  double missing_value[NE_RING_MAX_SERIES];
+} NeSeriesRingDesc;
+
 /* ---- entry points ---------------------------------------------------------------------- */
 int ne_version(void);
 const char* ne_last_error(void);
@@ -605,6 +634,18 @@ int ne_host_pipeline_create(void** handle, int32_t max_chunks);
 int ne_host_pipeline_destroy(void* handle);
 int ne_host_pipelined_step_f64(void* handle, const NeHostStepDesc*, void* stream);
 int ne_host_pipelined_step_f32(void* handle, const NeHostStepDesc*, void* stream);
+
+/* FieldTimeSeries ring (see NeSeriesRingDesc).  create: owns a non-blocking copy stream, one device staging slice per
+ * series and n_slots + 1 events.  load: enqueue, on the copy stream, the H2D copy of one raw slice of every series
+ * (host_raw[k], pinned, valid until the copy has run) and the kernel that writes slot `slot` (0-based) of every ring;
+ * the copy waits for the kernels enqueued on the compute stream before the last release.  acquire: the compute stream
+ * waits until `slot` has been written.  release: the kernels enqueued so far on the compute stream are the readers a
+ * later load has to wait for.  Nothing synchronises the host. */
+int ne_series_ring_create(void** handle, const NeSeriesRingDesc*);
+int ne_series_ring_destroy(void* handle);
+int ne_series_ring_load(void* handle, int32_t slot, const void* const* host_raw);
+int ne_series_ring_acquire(void* handle, int32_t slot, void* compute_stream);
+int ne_series_ring_release(void* handle, void* compute_stream);
 
 /* FP64 DFMA-issue microbenchmark used to measure the FP64 roofline denominator
  * (MEASURED_PEAKS.json has no FP64 figure).  Returns achieved TFLOP/s in *tflops. */

@@ -16,4 +16,5 @@ from .formulations import NoKernelVariantError  # noqa: F401
 from .interface import (ComponentInterfaces, ExchangeGrid, LatLonSourceGrid, PrescribedAtmosphere,  # noqa: F401
                         PrescribedLand, PrescribedRadiation, SlabLandState, interpolating_time_indices)
 from .pipeline import HostPipelinedStep  # noqa: F401
+from .series_window import SeriesWindow, WindowPolicy  # noqa: F401
 from .lib import LIB_PATH, Library, NeError, NumpyHostBackend, TorchCudaBackend, get_library  # noqa: F401

@@ -284,12 +284,24 @@ class NeHostStepDesc(C.Structure):
                 ("row_bytes", i64)]
 
 
+NE_RING_MAX_SERIES = 16
+NE_CONV_NONE, NE_CONV_NEGATE, NE_CONV_ADD, NE_CONV_SUB, NE_CONV_MUL, NE_CONV_DIV, NE_CONV_MUL_DIV = range(7)
+
+
+class NeSeriesRingDesc(C.Structure):
+    _fields_ = [("n_series", i32), ("n_slots", i32), ("dtype", i32), ("periodic_x", i32),
+                ("nx", i64), ("ny", i64), ("hx", i64), ("hy", i64),
+                ("ring", vp * NE_RING_MAX_SERIES), ("conv_kind", i32 * NE_RING_MAX_SERIES),
+                ("conv_a", C.c_double * NE_RING_MAX_SERIES), ("conv_b", C.c_double * NE_RING_MAX_SERIES),
+                ("has_missing", i32 * NE_RING_MAX_SERIES), ("missing_value", C.c_double * NE_RING_MAX_SERIES)]
+
+
 STRUCTS = {c.__name__: c for c in [
     NeSlot, NeExchangeGrid, NeTimeSeries, NeTimeInterp, NeInterpDesc, NeFracIndexDesc, NeThermoParams, NeStabilityFn,
     NeStabilityProfile, NeRoughnessLength, NeSubgridVelocity, NeStopCriteria, NePolynomialDrag, NeTransferCoefficient,
     NeLargeYeager, NeFluxFormulation, NeInterfaceProperties, NeMediumProperties, NeSeaIceAlbedo, NeTabulatedAlbedo, NeSurfaceRadiation, NeAtmosOceanDesc,
     NeAtmosSeaIceDesc, NeLandHumidity, NeAtmosLandDesc, NeSeaIceOceanDesc, NeSeaIceOceanStressDesc, NeAssembleOceanDesc, NeAssembleSeaIceDesc,
-    NeApplyRadiationDesc, NeElevationCorrectionDesc, NeFusedStepDesc, NeDiagDesc, NeHostField, NeHostStepDesc]}
+    NeApplyRadiationDesc, NeElevationCorrectionDesc, NeFusedStepDesc, NeDiagDesc, NeHostField, NeHostStepDesc, NeSeriesRingDesc]}
 
 # entry points declared in include/ne_b200.h: name -> descriptor struct (None: special signature)
 DESC_ENTRY_POINTS = {
@@ -310,7 +322,9 @@ DESC_ENTRY_POINTS = {
 }
 OTHER_ENTRY_POINTS = ["ne_version", "ne_last_error", "ne_device_count", "ne_memcpy_h2d", "ne_memcpy_d2h",
                       "ne_stream_synchronize", "ne_measure_fp64_peak", "ne_struct_size", "ne_host_pipeline_create",
-                      "ne_host_pipeline_destroy", "ne_host_pipelined_step_f64", "ne_host_pipelined_step_f32"]
+                      "ne_host_pipeline_destroy", "ne_host_pipelined_step_f64", "ne_host_pipelined_step_f32",
+                      "ne_series_ring_create", "ne_series_ring_destroy", "ne_series_ring_load", "ne_series_ring_acquire",
+                      "ne_series_ring_release"]
 
 
 def all_entry_points():

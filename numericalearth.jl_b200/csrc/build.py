@@ -33,6 +33,7 @@ SOURCES = {
     "ne_surface_kernels.cu": ["-fmad=false"],
     "ne_fused.cu": [],
     "ne_pipeline.cu": [],
+    "ne_series_ring.cu": [],
 }
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
           "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -50,7 +50,7 @@ int64_t ne_struct_size(const char* name) {
   NE_SZ(NeTransferCoefficient) NE_SZ(NeLargeYeager) NE_SZ(NeFluxFormulation) NE_SZ(NeInterfaceProperties)
   NE_SZ(NeMediumProperties) NE_SZ(NeSurfaceRadiation) NE_SZ(NeAtmosOceanDesc) NE_SZ(NeAtmosSeaIceDesc) NE_SZ(NeLandHumidity) NE_SZ(NeAtmosLandDesc)
   NE_SZ(NeSeaIceOceanDesc) NE_SZ(NeSeaIceOceanStressDesc) NE_SZ(NeAssembleOceanDesc) NE_SZ(NeAssembleSeaIceDesc)
-  NE_SZ(NeApplyRadiationDesc) NE_SZ(NeHostField) NE_SZ(NeHostStepDesc) NE_SZ(NeFusedStepDesc) NE_SZ(NeDiagDesc) NE_SZ(NeElevationCorrectionDesc) NE_SZ(NeSeaIceAlbedo) NE_SZ(NeTabulatedAlbedo)
+  NE_SZ(NeApplyRadiationDesc) NE_SZ(NeHostField) NE_SZ(NeHostStepDesc) NE_SZ(NeSeriesRingDesc) NE_SZ(NeFusedStepDesc) NE_SZ(NeDiagDesc) NE_SZ(NeElevationCorrectionDesc) NE_SZ(NeSeaIceAlbedo) NE_SZ(NeTabulatedAlbedo)
 #undef NE_SZ
   return -1;
 }

@@ -154,6 +154,7 @@ class PrescribedAtmosphere:
     boundary_layer_height: float = 512.0    # :223
     thermodynamics_parameters: Any = None
     time_indexing: str = "cyclical"
+    window: Any = None        # a series_window.SeriesWindow when the series are device rings (partly in memory)
 
     def __post_init__(self):
         if self.thermodynamics_parameters is None:
@@ -171,6 +172,7 @@ class PrescribedRadiation:
         "ocean": F.SurfaceRadiationProperties(0.05, 0.97),
         "sea_ice": F.SurfaceRadiationProperties(0.7, 1.0)})
     time_indexing: str = "cyclical"
+    window: Any = None
 
 
 @dataclass
@@ -181,6 +183,7 @@ class PrescribedLand:
     times: Any
     freshwater_flux: Any = ()      # tuple of series (rivers, icebergs, ...), each (nt, ny+2hy, nx+2hx)
     time_indexing: str = "cyclical"
+    window: Any = None
 
 
 @dataclass
@@ -345,9 +348,29 @@ class ComponentInterfaces:
             self.lib.call("frac_indices", self.grid.FT, self._frac_desc(self.land.grid, self.land_frac), s)
 
     # ---- phase 1: interpolation ---------------------------------------------------------------------
-    def _time_interp(self, times, t, time_indexing, frac_dtype="f64"):
-        nt, n1, n2 = interpolating_time_indices(times, t, time_indexing)
+    def _time_interp(self, src, t, frac_dtype="f64"):
+        """Time weight and the two in-memory slices of a prescribed component at time t.  Fully in-memory series: the
+        slices are the time indices; a windowed component (`src.window`) answers with ring slots and makes the
+        compute stream wait for them (update_field_time_series!, prescribed_atmosphere.jl:154-162)."""
+        if src.window is not None:
+            nt, m1, m2, same = src.window.time_interp(t, self.backend.stream())
+            return A.NeTimeInterp(frac=nt, frac_dtype=NE_DT[frac_dtype], m1=m1, m2=m2, same=same)
+        nt, n1, n2 = interpolating_time_indices(src.times, t, src.time_indexing)
         return A.NeTimeInterp(frac=nt, frac_dtype=NE_DT[frac_dtype], m1=n1, m2=n2, same=int(n1 == n2))
+
+    @staticmethod
+    def _n_memory(src):
+        return src.window.n_slots if src.window is not None else len(src.times)
+
+    def release_windows(self):
+        """After the interpolation kernels of a step have been enqueued: let every windowed component start loading
+        the slices of the coming intervals behind them."""
+        seen = []
+        for src in (self.atmosphere, self.radiation, self.land):
+            w = getattr(src, "window", None) if src is not None else None
+            if w is not None and not any(w is x for x in seen):
+                seen.append(w)
+                w.after_launch(self.backend.stream())
 
     def atmosphere_interp_desc(self, t) -> A.NeInterpDesc:
         b, g, atm = self.backend, self.grid, self.atmosphere
@@ -356,8 +379,8 @@ class ComponentInterfaces:
         d.frac_i, d.frac_j = b.ptr(self.frac.i), b.ptr(self.frac.j)
         d.src_dtype = NE_DT[atm.grid.FT]
         d.src_nx, d.src_ny, d.src_hx, d.src_hy = atm.grid.nx, atm.grid.ny, atm.grid.hx, atm.grid.hy
-        d.src_nt = len(atm.times)
-        d.time = self._time_interp(atm.times, t, atm.time_indexing)
+        d.src_nt = self._n_memory(atm)
+        d.time = self._time_interp(atm, t)
         fields = [(atm.u,), (atm.v,), (atm.T,), (atm.q,), (atm.p,), tuple(atm.rain), tuple(atm.snow)]
         outs = [self.atmos_state.u, self.atmos_state.v, self.atmos_state.T, self.atmos_state.q, self.atmos_state.p,
                 self.atmos_state.Jrn, self.atmos_state.Jsn]
@@ -388,8 +411,8 @@ class ComponentInterfaces:
         d.frac_i, d.frac_j = b.ptr(self.rad_frac.i), b.ptr(self.rad_frac.j)
         d.src_dtype = NE_DT[rad.grid.FT]
         d.src_nx, d.src_ny, d.src_hx, d.src_hy = rad.grid.nx, rad.grid.ny, rad.grid.hx, rad.grid.hy
-        d.src_nt = len(rad.times)
-        d.time = self._time_interp(rad.times, t, rad.time_indexing)
+        d.src_nt = self._n_memory(rad)
+        d.time = self._time_interp(rad, t)
         d.n_fields = 2
         for f, (s, out) in enumerate([(rad.downwelling_shortwave, self.rad_state.sw), (rad.downwelling_longwave, self.rad_state.lw)]):
             d.n_summands[f] = 1
@@ -409,8 +432,8 @@ class ComponentInterfaces:
         d.frac_i, d.frac_j = b.ptr(self.land_frac.i), b.ptr(self.land_frac.j)
         d.src_dtype = NE_DT[land.grid.FT]
         d.src_nx, d.src_ny, d.src_hx, d.src_hy = land.grid.nx, land.grid.ny, land.grid.hx, land.grid.hy
-        d.src_nt = len(land.times)
-        d.time = self._time_interp(land.times, t, land.time_indexing)
+        d.src_nt = self._n_memory(land)
+        d.time = self._time_interp(land, t)
         d.n_fields = 1
         d.n_summands[0] = len(series)
         for k, sr in enumerate(series):
@@ -472,6 +495,7 @@ class ComponentInterfaces:
             self.lib.call("interp_state", self.grid.FT, self.atmosphere_interp_desc(t), s)
         if self.land is not None:
             self.lib.call("interp_state", self.grid.FT, self.land_interp_desc(t), s)
+        self.release_windows()
 
     # ---- radiation POD ---------------------------------------------------------------------------------
     def _surface_radiation(self, surface, time_seconds=None) -> A.NeSurfaceRadiation:
@@ -812,5 +836,6 @@ class ComponentInterfaces:
         if self.land is not None:   # the runoff interpolation is independent of everything else in phase 1
             self.lib.call("interp_state", self.grid.FT, self.land_interp_desc(t), self.backend.stream())
         self.lib.call("fused_interface_step", self.grid.FT, self.fused_step_desc(t, diagnostics), self.backend.stream())
+        self.release_windows()
         if diagnostics is not None:
             diagnostics.all_reduce()

@@ -58,6 +58,11 @@ class Library:
             self.dll.ne_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
             self.dll.ne_host_pipeline_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
             self.dll.ne_host_pipeline_destroy.argtypes = [C.c_void_p]
+            self.dll.ne_series_ring_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(A.NeSeriesRingDesc)]
+            self.dll.ne_series_ring_destroy.argtypes = [C.c_void_p]
+            self.dll.ne_series_ring_load.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+            self.dll.ne_series_ring_acquire.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+            self.dll.ne_series_ring_release.argtypes = [C.c_void_p, C.c_void_p]
             for suffix in ("_f64", "_f32"):
                 fn = getattr(self.dll, "ne_host_pipelined_step" + suffix)
                 fn.restype = C.c_int

@@ -17,7 +17,6 @@ into rows an earlier band computed).
 import ctypes as C
 
 from . import abi as A
-from .interface import interpolating_time_indices
 
 
 class HostPipelinedStep:
@@ -58,8 +57,8 @@ class HostPipelinedStep:
         for d, src in ((self.desc.step.atmosphere, ci.atmosphere), (self.desc.step.radiation, ci.radiation)):
             if src is None:
                 continue
-            nt, n1, n2 = interpolating_time_indices(src.times, t, src.time_indexing)
-            d.time.frac, d.time.m1, d.time.m2, d.time.same = nt, n1, n2, int(n1 == n2)
+            ti = ci._time_interp(src, t)
+            d.time.frac, d.time.m1, d.time.m2, d.time.same = ti.frac, ti.m1, ti.m2, ti.same
 
     def step(self, t, host_ocean):
         """host_ocean: dict of pinned host arrays (torch CPU tensors or numpy) named T, S, u, v with the exchange
@@ -78,6 +77,7 @@ class HostPipelinedStep:
                 from .formulations import NoKernelVariantError
                 raise NoKernelVariantError(self.lib.last_error())
             raise RuntimeError(self.lib.last_error())
+        self.ci.release_windows()
         if self.diagnostics is not None:
             self.diagnostics.all_reduce()
 

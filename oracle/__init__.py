@@ -60,6 +60,7 @@ def load():
         d.neo_interpolator_f64.argtypes = [C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         d.neo_interpolator_f32.argtypes = [C.c_float, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_float)]
         d.neo_set_threads.argtypes = [C.c_int]
+        d.neo_series_slot_fill.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         d.neo_max_threads.restype = C.c_int
         d.neo_get_op_counts.argtypes = [C.POINTER(C.c_uint64)]
     return _lib

@@ -1238,6 +1238,42 @@ inline bool viscosity_is_f64_literal(const NeFluxFormulation& f) {
     else      { if (v64) FUNC<FT, float, double>(*(desc));  else FUNC<FT, float, FT>(*(desc)); }  \
   } while (0)
 
+// set!(fts) for ONE slice of ONE series (JRA55_field_time_series.jl:60-76): _set_region_kernel! over the interior
+// (set_region_data.jl:200-205; whole-globe region, no mangling: missing -> NaN, then convert_units,
+// metadata_field.jl:486-525), then fill_halo_regions!: periodic in x (test_jra55.jl:40-47) or zero-flux mirror,
+// zero-flux mirror in y.  raw: nx*ny, x fastest; dst: (ny+2hy) rows of (nx+2hx).
+template <typename T>
+static void series_slot_fill(const NeSeriesRingDesc& d, int k, const T* raw, T* dst) {
+  const int64_t W = d.nx + 2 * d.hx;
+  const T a = (T)d.conv_a[k], b = (T)d.conv_b[k], mv = (T)d.missing_value[k];
+  auto at = [&](int64_t i, int64_t j) -> T& { return dst[(j + d.hy) * W + (i + d.hx)]; };
+  for (int64_t j = 0; j < d.ny; ++j)
+    for (int64_t i = 0; i < d.nx; ++i) {
+      T v = raw[j * d.nx + i];
+      if (d.has_missing[k] && v == mv) v = std::numeric_limits<T>::quiet_NaN();
+      switch (d.conv_kind[k]) {
+        case NE_CONV_NEGATE: v = -v; break;
+        case NE_CONV_ADD: v = v + a; break;
+        case NE_CONV_SUB: v = v - a; break;
+        case NE_CONV_MUL: v = v * a; break;
+        case NE_CONV_DIV: v = v / a; break;
+        case NE_CONV_MUL_DIV: { volatile T m = v * a; v = m / b; break; }
+        default: break;
+      }
+      at(i, j) = v;
+    }
+  for (int64_t j = 0; j < d.ny; ++j)          // west / east halos of the interior rows
+    for (int64_t h = 1; h <= d.hx; ++h) {
+      at(-h, j) = d.periodic_x ? at(d.nx - h, j) : at(h - 1, j);
+      at(d.nx - 1 + h, j) = d.periodic_x ? at(h - 1, j) : at(d.nx - h, j);
+    }
+  for (int64_t h = 1; h <= d.hy; ++h)         // south / north halos over the whole row, corners included
+    for (int64_t i = -d.hx; i < d.nx + d.hx; ++i) {
+      at(i, -h) = at(i, h - 1);
+      at(i, d.ny - 1 + h) = at(i, d.ny - h);
+    }
+}
+
 extern "C" {
 
 int neo_version(void) { return NE_ABI_VERSION; }
@@ -1277,6 +1313,13 @@ double neo_land_interface_humidity(const NeLandHumidity* h, const NeThermoParams
 double neo_saturation_specific_humidity(const NeThermoParams* thermo, double T, double p, int phase) {
   const Thermo<double> th(*thermo);
   return saturation_specific_humidity<double>(th, T, p, phase);
+}
+
+int neo_series_slot_fill(const NeSeriesRingDesc* d, int32_t series, const void* raw, void* dst) {
+  if (!d || !raw || !dst || series < 0 || series >= d->n_series) return -1;
+  if (d->dtype == NE_F64) series_slot_fill<double>(*d, series, (const double*)raw, (double*)dst);
+  else series_slot_fill<float>(*d, series, (const float*)raw, (float*)dst);
+  return 0;
 }
 
 static int interp_dispatch(const NeInterpDesc* d, bool out64) {

@@ -1,0 +1,279 @@
+"""the FieldTimeSeries window on the device.
+
+Reference behaviour restated: update_state!(::PrescribedAtmosphere) (src/Atmospheres/prescribed_atmosphere.jl:154-162) ->
+update_field_time_series! -> set!(fts) (src/DataWrangling/JRA55/JRA55_field_time_series.jl:60-76): raw file slices go
+through _set_region_kernel! (src/DataWrangling/set_region_data.jl:200-205) into the interior and fill_halo_regions!
+fills the halos (test/test_jra55.jl:40-47 checks fts[Nx+1, ...] == fts[1, ...]).
+
+CPU: the slot bookkeeping (WindowPolicy) and the oracle's slot fill against numpy.  GPU: the ring's slot-fill kernel against
+the oracle bit for bit, and a windowed PrescribedAtmosphere + PrescribedRadiation stepped across many intervals (and the
+cyclical wrap) against the same series fully in memory, bit for bit.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import ne_b200
+from ne_b200 import abi as A
+from numericalearth_jl_b200 import synthetic
+from numericalearth_jl_b200.series_window import CONVERSIONS, SeriesWindow, WindowPolicy
+
+NPD = {"f64": np.float64, "f32": np.float32}
+
+
+# ------------------------------------------------------------------------------------------------- policy (CPU)
+def _walk(policy, times, ts, indexing):
+    """Drive the policy the way SeriesWindow does; returns (demand loads per step, prefetch loads per step)."""
+    dem, pre = [], []
+    for t in ts:
+        _, n1, n2 = ne_b200.interpolating_time_indices(times, t, indexing)
+        before = dict(policy.where)
+        d = policy.demand(n1, n2)
+        assert policy.resident[policy.where[n1]] == n1 and policy.resident[policy.where[n2]] == n2
+        assert n1 == n2 or policy.where[n1] != policy.where[n2]
+        for n, _slot in d:
+            assert n not in before
+        p = policy.prefetch(n1, n2)
+        # a prefetch never replaces the two slices the kernel that was just enqueued reads
+        assert policy.resident[policy.where[n1]] == n1 and policy.resident[policy.where[n2]] == n2
+        for n, slot in p:
+            assert slot not in (before.get(n1, -1), before.get(n2, -1)) or before.get(n1) is None
+        # the map and the slot table stay each other's inverse
+        assert {n: s for s, n in enumerate(policy.resident) if n is not None} == policy.where
+        dem.append(len(d))
+        pre.append(len(p))
+    return dem, pre
+
+
+@pytest.mark.parametrize("nt,n_slots", [(8, 4), (8, 3), (5, 5), (24, 6), (3, 3)])
+def test_cyclical_clock_never_waits_after_the_first_step(nt, n_slots):
+    times = np.arange(nt) * 10800.0
+    policy = WindowPolicy(nt, n_slots, "cyclical")
+    ts = np.arange(0, 3.2 * nt * 10800.0, 1800.0)   # 6 steps per interval, three times around the year
+    dem, pre = _walk(policy, times, ts, "cyclical")
+    assert dem[0] == 2 and sum(dem[1:]) == 0          # only the very first step loads on demand
+    n_intervals = int(ts[-1] // 10800.0)
+    if nt > n_slots:
+        assert sum(pre) >= n_intervals - 1            # one new slice per interval, each ahead of its interval
+    else:
+        assert sum(pre) == nt - 2                     # the whole series fits: every slice is loaded exactly once
+
+
+def test_two_slots_degrade_to_one_demand_load_per_interval():
+    """n_slots = 2 leaves nowhere to prefetch into: every new interval waits for ONE slice — still not for a whole
+    window like the reference's reload."""
+    nt = 6
+    times = np.arange(nt) * 10800.0
+    policy = WindowPolicy(nt, 2, "cyclical")
+    ts = np.arange(0, 2 * nt * 10800.0, 5400.0)
+    dem, pre = _walk(policy, times, ts, "cyclical")
+    assert sum(pre) == 0 and dem[0] == 2
+    assert all(d == (1 if k % 2 == 0 else 0) for k, d in enumerate(dem[1:], start=1))
+
+
+def test_linear_and_clamped_series_stop_prefetching_at_the_end():
+    nt = 6
+    times = np.arange(nt) * 10800.0
+    for indexing in ("linear", "clamp"):
+        policy = WindowPolicy(nt, 3, indexing)
+        ts = np.arange(600.0, (nt - 1) * 10800.0, 3600.0)
+        dem, pre = _walk(policy, times, ts, indexing)
+        assert dem[0] == 2 and sum(dem[1:]) == 0
+        assert sum(pre) == nt - 2                      # every later slice exactly once, nothing past the last
+    policy = WindowPolicy(nt, 3, "clamp")
+    _walk(policy, times, [1e9], "clamp")               # clamped past the end: n1 == n2 == nt, one slot
+    assert policy.where == {nt: policy.where[nt]}
+
+
+def test_clock_jumps_reload_on_demand_and_recover():
+    nt = 12
+    times = np.arange(nt) * 10800.0
+    rng = np.random.default_rng(3)
+    policy = WindowPolicy(nt, 4, "cyclical")
+    ts = list(rng.uniform(0, 5 * nt * 10800.0, 40))    # random access: every step may need both slices
+    dem, _ = _walk(policy, times, ts, "cyclical")
+    assert max(dem) <= 2
+    t0 = ts[-1]
+    dem, _ = _walk(policy, times, t0 + np.arange(1, 60) * 1800.0, "cyclical")   # marching again from wherever it landed
+    assert sum(dem) == 0
+
+
+def test_upcoming_wraps_only_for_cyclical_series():
+    assert WindowPolicy(5, 4, "cyclical").upcoming(4, 3) == [5, 1, 2]
+    assert WindowPolicy(5, 4, "linear").upcoming(4, 3) == [5]
+    assert WindowPolicy(2, 2, "cyclical").upcoming(2, 3) == [1]
+
+
+# ------------------------------------------------------------------------------------------------- slot fill (oracle, CPU)
+def _ring_desc(FT, nx, ny, hx, hy, n_series=1, periodic=True, conv=None, missing=None):
+    d = A.NeSeriesRingDesc()
+    d.n_series, d.n_slots, d.dtype, d.periodic_x = n_series, 2, A.NE_F64 if FT == "f64" else A.NE_F32, int(periodic)
+    d.nx, d.ny, d.hx, d.hy = nx, ny, hx, hy
+    for k in range(n_series):
+        kind, a, b = CONVERSIONS[conv]
+        d.conv_kind[k], d.conv_a[k], d.conv_b[k] = kind, a, b
+        if missing is not None:
+            d.has_missing[k], d.missing_value[k] = 1, missing
+    return d
+
+
+def _oracle_fill(oracle_lib, d, raw, FT):
+    out = np.full((d.ny + 2 * d.hy, d.nx + 2 * d.hx), -777.0, dtype=NPD[FT])
+    raw = np.ascontiguousarray(raw, dtype=NPD[FT])
+    assert oracle_lib.dll.neo_series_slot_fill(C.addressof(d), 0, raw.ctypes.data, out.ctypes.data) == 0
+    return out
+
+
+def _numpy_fill(raw, hx, hy, periodic, FT, conv=None, missing=None):
+    v = np.array(raw, dtype=NPD[FT])
+    if missing is not None:
+        v[v == NPD[FT](missing)] = np.nan
+    kind, a, b = CONVERSIONS[conv]
+    a, b = NPD[FT](a), NPD[FT](b)
+    v = {A.NE_CONV_NONE: lambda: v, A.NE_CONV_NEGATE: lambda: -v, A.NE_CONV_ADD: lambda: v + a, A.NE_CONV_SUB: lambda: v - a,
+         A.NE_CONV_MUL: lambda: v * a, A.NE_CONV_DIV: lambda: v / a, A.NE_CONV_MUL_DIV: lambda: (v * a) / b}[kind]()
+    v = np.pad(v, ((0, 0), (hx, hx)), mode="wrap" if periodic else "symmetric")
+    return np.pad(v, ((hy, hy), (0, 0)), mode="symmetric")
+
+
+@pytest.mark.parametrize("FT", ["f32", "f64"])
+@pytest.mark.parametrize("periodic", [True, False])
+@pytest.mark.parametrize("conv", [None, "Celsius", "Kelvin", "Millibar", "MillimetersPerHour", "MetersPerHour", "InverseSign"])
+def test_oracle_slot_fill_is_set_region_plus_halo_fill(oracle_lib, FT, periodic, conv):
+    rng = np.random.default_rng(11)
+    nx, ny, hx, hy = 37, 19, 3, 2
+    raw = rng.normal(280.0, 30.0, (ny, nx)).astype(NPD[FT])
+    raw[rng.random((ny, nx)) < 0.05] = NPD[FT](-9999.0)
+    d = _ring_desc(FT, nx, ny, hx, hy, periodic=periodic, conv=conv, missing=-9999.0)
+    got = _oracle_fill(oracle_lib, d, raw, FT)
+    want = _numpy_fill(raw, hx, hy, periodic, FT, conv, -9999.0)
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.isnan(got).any()
+    if periodic:   # test/test_jra55.jl:40-47: fts[Nx+1, j] == fts[1, j], data[1, :] == data[Nx+1, :]
+        assert np.array_equal(got[:, hx], got[:, hx + nx], equal_nan=True)
+        assert np.array_equal(got[:, hx - 1], got[:, hx + nx - 1], equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------- device
+def _window_case(backend, lib, FT, atm_FT, nt, n_slots, seed_offset=0):
+    """Two identically seeded interfaces: `full` reads the series fully in memory (halos filled the reference's way),
+    `win` reads device rings fed from the raw slices."""
+    cfg = dict(nx=96, ny=40, latitude=(-70.0, 70.0), src_nx=64, src_ny=32)
+    full = synthetic.build_case(cfg, backend, FT=FT, atm_FT=atm_FT, nt=nt, seed_offset=seed_offset)
+    win = synthetic.build_case(cfg, backend, FT=FT, atm_FT=atm_FT, nt=nt, seed_offset=seed_offset)
+    src = full.atmosphere.grid
+    a = full._host_inputs["atmosphere"]
+    raw = {k: np.ascontiguousarray(v[:, src.hy:src.hy + src.ny, src.hx:src.hx + src.nx]) for k, v in a.items()}
+    padded = {k: np.stack([_numpy_fill(v[n], src.hx, src.hy, True, atm_FT) for n in range(nt)]) for k, v in raw.items()}
+    dev = {k: backend.from_numpy(v) for k, v in padded.items()}
+    w = SeriesWindow(backend, lib, src, full.atmosphere.times, raw, n_slots=n_slots)
+    for ci, s in ((full, dev), (win, w.series)):
+        atm, rad = ci.atmosphere, ci.radiation
+        atm.u, atm.v, atm.T, atm.q, atm.p = s["u"], s["v"], s["T"], s["q"], s["p"]
+        atm.rain, atm.snow = (s["rain"],), (s["snow"],)
+        rad.downwelling_shortwave, rad.downwelling_longwave = s["sw"], s["lw"]
+    win.atmosphere.window = win.radiation.window = w
+    full.initialize()
+    win.initialize()
+    return full, win, w, padded
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("FT", ["f32", "f64"])
+@pytest.mark.parametrize("periodic", [True, False])
+def test_ring_slot_fill_kernel_matches_the_oracle(cuda_backend, cuda_lib, oracle_lib, FT, periodic):
+    import torch
+    rng = np.random.default_rng(5)
+    src = ne_b200.LatLonSourceGrid(nx=640, ny=320, FT=FT)
+    names = ["T", "p", "rain"]
+    convs = {"T": "Celsius", "p": "Millibar", "rain": "MillimetersPerHour"}
+    nt = 3
+    raw = {k: rng.normal(20.0, 9.0, (nt, src.ny, src.nx)).astype(NPD[FT]) for k in names}
+    raw["rain"][raw["rain"] < 8.0] = NPD[FT](1e20)
+    w = SeriesWindow(cuda_backend, cuda_lib, src, np.arange(nt) * 10800.0, raw, n_slots=3, conversions=convs,
+                     missing_values={"rain": 1e20}, periodic_x=periodic)
+    s = cuda_backend.stream()
+    w.time_interp(0.5 * 10800.0, s)      # demand-loads slices 1 and 2
+    w.after_launch(s)                    # prefetches slice 3
+    torch.cuda.synchronize()
+    assert w.demand_loads == 2 and w.prefetched == 1
+    for k in names:
+        d = _ring_desc(FT, src.nx, src.ny, src.hx, src.hy, periodic=periodic, conv=convs[k], missing=1e20 if k == "rain" else None)
+        ring = cuda_backend.to_numpy(w[k])
+        for n in range(1, nt + 1):
+            want = _oracle_fill(oracle_lib, d, raw[k][n - 1], FT)
+            assert np.array_equal(ring[w.policy.where[n]], want, equal_nan=True), (k, n)
+    assert np.isnan(cuda_backend.to_numpy(w["rain"])).any()
+    w.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("FT,atm_FT,n_slots", [("f64", "f32", 4), ("f64", "f64", 3), ("f32", "f32", 5), ("f64", "f32", 2)])
+def test_windowed_series_interpolate_like_the_series_fully_in_memory(cuda_backend, cuda_lib, FT, atm_FT, n_slots):
+    import torch
+    nt = 8
+    full, win, w, _ = _window_case(cuda_backend, cuda_lib, FT, atm_FT, nt, n_slots)
+    dt = 10800.0 / 5
+    steps = int(2.3 * nt * 5)            # more than twice around the cyclical series
+    for k in range(steps):
+        t = 400.0 + k * dt
+        full.interpolate_state(t)
+        win.interpolate_state(t)
+        if k % 7 == 0 or k == steps - 1:
+            torch.cuda.synchronize()
+            for name in ("u", "v", "T", "q", "p", "Jrn", "Jsn"):
+                x, y = cuda_backend.to_numpy(getattr(full.atmos_state, name)), cuda_backend.to_numpy(getattr(win.atmos_state, name))
+                assert np.array_equal(x, y, equal_nan=True), (name, k)
+            for name in ("sw", "lw"):
+                x, y = cuda_backend.to_numpy(getattr(full.rad_state, name)), cuda_backend.to_numpy(getattr(win.rad_state, name))
+                assert np.array_equal(x, y, equal_nan=True), (name, k)
+    torch.cuda.synchronize()
+    n_intervals = int((400.0 + (steps - 1) * dt) // 10800.0)
+    if n_slots >= 3:   # after the first step nothing was ever waited for; each later slice arrived ahead of its interval
+        assert w.demand_loads == 2
+        assert w.prefetched >= n_intervals
+    else:
+        assert w.prefetched == 0 and w.demand_loads == 2 + n_intervals
+    w.close()
+
+
+@pytest.mark.gpu
+def test_windowed_fused_step_and_host_pipeline_match_the_in_memory_step(cuda_backend, cuda_lib):
+    """The one-call interface step and the host-buffer pipeline read the rings too (ring slots in NeTimeInterp.m1/m2,
+    src_nt = n_slots), including the merged 9-series interpolation launch."""
+    import torch
+    nt = 6
+    full, win, w, _ = _window_case(cuda_backend, cuda_lib, "f64", "f32", nt, 4, seed_offset=2)
+    assert win.shared_frac
+    pipe = ne_b200.HostPipelinedStep(win, n_chunks=3)
+    host = {k: torch.from_numpy(cuda_backend.to_numpy(getattr(win.ocean_state, k))).pin_memory() for k in ("T", "S", "u", "v")}
+    for k in range(3 * nt):
+        t = 100.0 + k * 10800.0 * 0.75
+        full.fused_interface_step(t)
+        if k % 2:
+            pipe.step(t, host)
+        else:
+            win.fused_interface_step(t)
+        torch.cuda.synchronize()
+        for name in ("Qc", "Qv", "Fv", "tau_x", "tau_y"):
+            x, y = cuda_backend.to_numpy(getattr(full.ao_fluxes, name)), cuda_backend.to_numpy(getattr(win.ao_fluxes, name))
+            assert np.array_equal(x, y, equal_nan=True), (name, k)
+        x, y = cuda_backend.to_numpy(full.net_ocean.Q), cuda_backend.to_numpy(win.net_ocean.Q)
+        assert np.array_equal(x, y, equal_nan=True), k
+    assert w.demand_loads == 2
+    w.close()
+
+
+@pytest.mark.gpu
+def test_ring_rejects_bad_descriptors(cuda_backend, cuda_lib):
+    d = _ring_desc("f32", 8, 8, 3, 3)
+    h = C.c_void_p()
+    assert cuda_lib.dll.ne_series_ring_create(C.byref(h), C.byref(d)) == A.NE_E_INVALID   # null ring pointer
+    assert "ring" in cuda_lib.last_error()
+    d.n_slots = 1
+    assert cuda_lib.dll.ne_series_ring_create(C.byref(h), C.byref(d)) == A.NE_E_INVALID
+    with pytest.raises(RuntimeError):   # acquire of a slot nothing was ever loaded into
+        src = ne_b200.LatLonSourceGrid(nx=16, ny=8, FT="f32")
+        w = SeriesWindow(cuda_backend, cuda_lib, src, np.arange(3) * 1.0, {"a": np.zeros((3, 8, 16), np.float32)}, n_slots=3)
+        w._check(cuda_lib.dll.ne_series_ring_acquire(w.handle, C.c_int32(1), C.c_void_p(cuda_backend.stream())))
