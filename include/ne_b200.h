@@ -551,14 +551,17 @@ typedef struct NeHostStepDesc {
  * RING of n_slots slices: one slice at a time is replaced, on the ring's own copy stream, while the step's kernels
  * run; `NeTimeInterp.m1/m2` name ring slots.  Loading one slot does what set!(fts) does to one slice:
  *   raw file slice (nx x ny, x fastest, no halos) in pinned HOST memory
- *     -> missing value -> NaN, unit conversion (_set_region_kernel!, src/DataWrangling/set_region_data.jl:200-205,
- *        whole-globe region, no mangling; convert_units, src/DataWrangling/metadata_field.jl:486-525)
+ *     -> read_data (src/DataWrangling/set_region_data.jl:162-163): file index = grid index + BoundingBoxOffset (di, dj),
+ *        lat-axis mangling (mangle, :50-53: ShiftSouth reads j - 1, AverageNorthSouth averages j and j + 1; indices
+ *        clamped to the file extent), missing value -> NaN, then convert_units (_set_region_kernel!, :200-205;
+ *        src/DataWrangling/metadata_field.jl:486-525).  Column regions (a blend of four file cells into one) stay with the host.
  *     -> interior of the slot, then fill_halo_regions!(fts): periodic in x (test/test_jra55.jl:40-47: fts[Nx+1,..] ==
  *        fts[1,..]) or mirrored when the source grid is bounded in x, mirrored (zero-flux) in y.
  * Which time index lives in which slot, and what to prefetch, is host policy (the binding's; series_window.py here). */
 #define NE_RING_MAX_SERIES 16
 enum { NE_CONV_NONE = 0, NE_CONV_NEGATE = 1, NE_CONV_ADD = 2, NE_CONV_SUB = 3, NE_CONV_MUL = 4, NE_CONV_DIV = 5,
        NE_CONV_MUL_DIV = 6 };   /* d, -d, d + a, d - a, d * a, d / a, d * a / b: each one rounding in the series eltype */
+enum { NE_MANGLE_NONE = 0, NE_MANGLE_SHIFT_SOUTH = 1, NE_MANGLE_AVERAGE_NORTH_SOUTH = 2 };
 typedef struct NeSeriesRingDesc {
   int32_t n_series;            /* series that share the time axis (<= NE_RING_MAX_SERIES)          */
   int32_t n_slots;             /* Nt_mem: slices each ring holds                                    */
@@ -570,6 +573,11 @@ typedef struct NeSeriesRingDesc {
   double conv_a[NE_RING_MAX_SERIES], conv_b[NE_RING_MAX_SERIES];   /* rounded to `dtype` before use */
   int32_t has_missing[NE_RING_MAX_SERIES]; /* 1: raw values equal to missing_value become NaN       */
   double missing_value[NE_RING_MAX_SERIES];
+  /* the raw (file) slice when it is not nx x ny: its extent (0 => nx / ny), where the grid's first cell sits in it
+   * (region_info(::BoundingBox), set_region_data.jl:88-111) and the lat-axis mangling (mangling_for, :153-158:
+   * raw_ny == ny - 1 => ShiftSouth, raw_ny == ny + 1 => AverageNorthSouth).                                      */
+  int64_t raw_nx, raw_ny, di, dj;
+  int32_t mangling[NE_RING_MAX_SERIES];    /* NE_MANGLE_*                                           */
 } NeSeriesRingDesc;
 
 /* ---- entry points ---------------------------------------------------------------------- */

@@ -285,6 +285,7 @@ class NeHostStepDesc(C.Structure):
 
 
 NE_RING_MAX_SERIES = 16
+NE_MANGLE_NONE, NE_MANGLE_SHIFT_SOUTH, NE_MANGLE_AVERAGE_NORTH_SOUTH = range(3)
 NE_CONV_NONE, NE_CONV_NEGATE, NE_CONV_ADD, NE_CONV_SUB, NE_CONV_MUL, NE_CONV_DIV, NE_CONV_MUL_DIV = range(7)
 
 
@@ -293,7 +294,8 @@ class NeSeriesRingDesc(C.Structure):
                 ("nx", i64), ("ny", i64), ("hx", i64), ("hy", i64),
                 ("ring", vp * NE_RING_MAX_SERIES), ("conv_kind", i32 * NE_RING_MAX_SERIES),
                 ("conv_a", C.c_double * NE_RING_MAX_SERIES), ("conv_b", C.c_double * NE_RING_MAX_SERIES),
-                ("has_missing", i32 * NE_RING_MAX_SERIES), ("missing_value", C.c_double * NE_RING_MAX_SERIES)]
+                ("has_missing", i32 * NE_RING_MAX_SERIES), ("missing_value", C.c_double * NE_RING_MAX_SERIES),
+                ("raw_nx", i64), ("raw_ny", i64), ("di", i64), ("dj", i64), ("mangling", i32 * NE_RING_MAX_SERIES)]
 
 
 STRUCTS = {c.__name__: c for c in [

@@ -37,7 +37,9 @@ struct SlotFillArgs {
   double conv_a[NE_RING_MAX_SERIES], conv_b[NE_RING_MAX_SERIES];
   int has_missing[NE_RING_MAX_SERIES];
   double missing_value[NE_RING_MAX_SERIES];
+  int mangling[NE_RING_MAX_SERIES];
   long long nx, ny, hx, hy;
+  long long raw_nx, raw_ny, di, dj;
   int periodic_x;
 };
 
@@ -51,6 +53,7 @@ __device__ __forceinline__ long long mirror_index(long long i, long long n) {
 // One thread per ring-slice element (interior and halos), blockIdx.y = series.  Each element is ONE read of the raw
 // slice (L2-resident: the staging copy has just landed) and one coalesced write: HBM/L2-bound, 2 x sizeof(T) bytes
 // per element.  The arithmetic is the reference's, one rounding per operation in the series element type.
+// A halo element is first mapped to the interior cell whose value fill_halo_regions! copies, then read like it.
 template <typename T>
 __global__ void __launch_bounds__(256) slot_fill_kernel(const SlotFillArgs a) {
   const int s = blockIdx.y;
@@ -70,7 +73,17 @@ __global__ void __launch_bounds__(256) slot_fill_kernel(const SlotFillArgs a) {
       i = mirror_index(i, a.nx);
     }
     j = mirror_index(j, a.ny);
-    T v = raw[j * a.nx + i];
+    // read_data: region offset, lat-axis mangling with indices clamped to the file extent, missing -> NaN
+    const long long ii = min(max(i + a.di, 0LL), a.raw_nx - 1);
+    long long jj = j + a.dj;
+    const int mg = a.mangling[s];
+    if (mg == NE_MANGLE_SHIFT_SOUTH) jj -= 1;
+    const long long j0 = min(max(jj, 0LL), a.raw_ny - 1);
+    T v = raw[j0 * a.raw_nx + ii];
+    if (mg == NE_MANGLE_AVERAGE_NORTH_SOUTH) {
+      const long long j1 = min(max(jj + 1, 0LL), a.raw_ny - 1);
+      v = (v + raw[j1 * a.raw_nx + ii]) / (T)2;
+    }
     if (hm && v == mv) v = (T)NAN;
     switch (kind) {
       case NE_CONV_NEGATE: v = -v; break;
@@ -101,7 +114,9 @@ int ne_series_ring_create(void** handle, const NeSeriesRingDesc* d) {
   for (int k = 0; k < d->n_series; ++k) {
     NE_REQUIRE(d->ring[k] != nullptr, "series ring: null ring pointer");
     NE_REQUIRE(d->conv_kind[k] >= NE_CONV_NONE && d->conv_kind[k] <= NE_CONV_MUL_DIV, "series ring: unknown unit conversion");
+    NE_REQUIRE(d->mangling[k] >= NE_MANGLE_NONE && d->mangling[k] <= NE_MANGLE_AVERAGE_NORTH_SOUTH, "series ring: unknown mangling");
   }
+  NE_REQUIRE(d->raw_nx >= 0 && d->raw_ny >= 0 && d->di >= 0 && d->dj >= 0, "series ring: negative raw extent or region offset");
   ne::SeriesRing* r = new ne::SeriesRing();
   r->d = *d;
   r->copy = nullptr;
@@ -109,7 +124,9 @@ int ne_series_ring_create(void** handle, const NeSeriesRingDesc* d) {
   r->released = nullptr;
   r->have_release = false;
   r->ever_loaded.assign(d->n_slots, 0);
-  const size_t raw_bytes = (size_t)d->nx * d->ny * ne::elem_bytes(*d);
+  if (r->d.raw_nx == 0) r->d.raw_nx = d->nx;
+  if (r->d.raw_ny == 0) r->d.raw_ny = d->ny;
+  const size_t raw_bytes = (size_t)r->d.raw_nx * r->d.raw_ny * ne::elem_bytes(*d);
   cudaError_t e = cudaGetDevice(&r->device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->copy, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMalloc(&r->staging, raw_bytes * d->n_series);
@@ -146,7 +163,7 @@ int ne_series_ring_load(void* handle, int32_t slot, const void* const* host_raw)
   NE_REQUIRE(r != nullptr && host_raw != nullptr, "series ring load: null argument");
   const NeSeriesRingDesc& d = r->d;
   NE_REQUIRE(slot >= 0 && slot < d.n_slots, "series ring load: slot out of range");
-  const size_t eb = ne::elem_bytes(d), raw_bytes = (size_t)d.nx * d.ny * eb;
+  const size_t eb = ne::elem_bytes(d), raw_bytes = (size_t)d.raw_nx * d.raw_ny * eb;
   const size_t slice_bytes = (size_t)(d.nx + 2 * d.hx) * (d.ny + 2 * d.hy) * eb;
   // the slot may still be read by kernels enqueued before the last release
   if (r->have_release) NE_CUDA_TRY(cudaStreamWaitEvent(r->copy, r->released, 0), "series ring load (wait readers)");
@@ -162,7 +179,9 @@ int ne_series_ring_load(void* handle, int32_t slot, const void* const* host_raw)
     a.conv_b[k] = d.conv_b[k];
     a.has_missing[k] = d.has_missing[k];
     a.missing_value[k] = d.missing_value[k];
+    a.mangling[k] = d.mangling[k];
   }
+  a.raw_nx = d.raw_nx; a.raw_ny = d.raw_ny; a.di = d.di; a.dj = d.dj;
   a.nx = d.nx; a.ny = d.ny; a.hx = d.hx; a.hy = d.hy; a.periodic_x = d.periodic_x;
   const long long elems = (long long)(d.nx + 2 * d.hx) * (d.ny + 2 * d.hy);
   const unsigned bx = (unsigned)std::min<long long>((elems + 255) / 256, 148LL * 8);

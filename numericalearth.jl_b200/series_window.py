@@ -19,7 +19,6 @@ those interpolated from the fully in-memory series bit for bit (same slices, sam
 host store and the native handle.
 """
 import ctypes as C
-from collections import deque
 
 import numpy as np
 
@@ -118,14 +117,16 @@ class WindowPolicy:
 class SeriesWindow:
     """Device rings of the series of one prescribed component (all on one source grid and one time axis).
 
-    raw: dict name -> host array (nt, ny, nx) of the source element type, the decoded file variable (no halos, x
-    fastest; what `ds[name][:, :, nn]` returns in JRA55_field_time_series.jl:67, transposed to row-major); kept in
-    pinned memory.  `series[name]` is the device ring (n_slots, ny + 2hy, nx + 2hx) a PrescribedAtmosphere /
-    PrescribedRadiation / PrescribedLand field points to.
+    raw: dict name -> host array (nt, ny_file, nx_file) of the source element type, the decoded file variable (no halos,
+    x fastest; what `ds[name][:, :, nn]` returns in JRA55_field_time_series.jl:67, transposed to row-major); kept in
+    pinned memory.  `region_offset` = (di, dj) of a BoundingBox region inside the file (region_info, set_region_data.jl:88-111);
+    a whole-globe file with one latitude less / more than the grid is read with ShiftSouth / AverageNorthSouth mangling.
+    `series[name]` is the device ring (n_slots, ny + 2hy, nx + 2hx) a PrescribedAtmosphere / PrescribedRadiation /
+    PrescribedLand field points to.
     """
 
     def __init__(self, backend, lib, grid, times, raw, n_slots=4, time_indexing="cyclical", conversions=None,
-                 missing_values=None, periodic_x=True, lookahead=None):
+                 missing_values=None, periodic_x=True, lookahead=None, region_offset=(0, 0)):
         if not backend.is_device:
             raise RuntimeError("SeriesWindow needs the CUDA library and device arrays (there is no CPU fallback)")
         self.backend, self.lib, self.grid = backend, lib, grid
@@ -139,24 +140,34 @@ class SeriesWindow:
         npd = np.float64 if grid.FT == "f64" else np.float32
         torch = backend.torch
         self.host = {}
+        raw_shape = None
         for k in self.names:
             a = np.ascontiguousarray(np.asarray(raw[k], dtype=npd))
-            if a.shape != (nt, grid.ny, grid.nx):
-                raise ValueError(f"raw series {k}: expected shape {(nt, grid.ny, grid.nx)}, got {a.shape}")
+            if a.ndim != 3 or a.shape[0] != nt or (raw_shape is not None and a.shape != raw_shape):
+                raise ValueError(f"raw series {k}: expected {nt} slices of one common (ny_file, nx_file) shape, got {a.shape}")
+            raw_shape = a.shape
             self.host[k] = torch.from_numpy(a).pin_memory()
+        raw_ny, raw_nx = raw_shape[1:]
+        # mangling_for (src/DataWrangling/set_region_data.jl:153-158): a file with one latitude less / more than the grid
+        whole = tuple(region_offset) == (0, 0)
+        mangling = A.NE_MANGLE_SHIFT_SOUTH if whole and raw_ny == grid.ny - 1 else \
+            A.NE_MANGLE_AVERAGE_NORTH_SOUTH if whole and raw_ny == grid.ny + 1 else A.NE_MANGLE_NONE
+        self.mangling = mangling
         self.series = {k: backend.zeros((self.n_slots,) + tuple(grid.shape), grid.FT) for k in self.names}
         d = self.desc = A.NeSeriesRingDesc()
         d.n_series, d.n_slots, d.dtype, d.periodic_x = len(self.names), self.n_slots, A.NE_F64 if grid.FT == "f64" else A.NE_F32, int(periodic_x)
         d.nx, d.ny, d.hx, d.hy = grid.nx, grid.ny, grid.hx, grid.hy
+        d.raw_nx, d.raw_ny, d.di, d.dj = raw_nx, raw_ny, int(region_offset[0]), int(region_offset[1])
         for i, k in enumerate(self.names):
             d.ring[i] = backend.ptr(self.series[k])
+            d.mangling[i] = mangling
             kind, a, b = CONVERSIONS[(conversions or {}).get(k)]
             d.conv_kind[i], d.conv_a[i], d.conv_b[i] = kind, a, b
             if missing_values and k in missing_values:
                 d.has_missing[i], d.missing_value[i] = 1, float(missing_values[k])
         self.handle = C.c_void_p()
         self._check(lib.dll.ne_series_ring_create(C.byref(self.handle), C.byref(d)))
-        self._slice_bytes = grid.ny * grid.nx * (8 if grid.FT == "f64" else 4)
+        self._slice_bytes = raw_ny * raw_nx * (8 if grid.FT == "f64" else 4)
         self.demand_loads = 0      # slices a step had to wait for (the reference's stall, per slice)
         self.prefetched = 0        # slices loaded behind a step's kernels
         self._current = None

@@ -1245,11 +1245,24 @@ inline bool viscosity_is_f64_literal(const NeFluxFormulation& f) {
 template <typename T>
 static void series_slot_fill(const NeSeriesRingDesc& d, int k, const T* raw, T* dst) {
   const int64_t W = d.nx + 2 * d.hx;
+  const int64_t rnx = d.raw_nx ? d.raw_nx : d.nx, rny = d.raw_ny ? d.raw_ny : d.ny;
   const T a = (T)d.conv_a[k], b = (T)d.conv_b[k], mv = (T)d.missing_value[k];
   auto at = [&](int64_t i, int64_t j) -> T& { return dst[(j + d.hy) * W + (i + d.hx)]; };
+  // mangle (set_region_data.jl:48-53): 1-based file indices clamped to the file extent; here 0-based
+  auto file = [&](int64_t i, int64_t j) -> T {
+    i = std::min(std::max<int64_t>(i, 0), rnx - 1);
+    j = std::min(std::max<int64_t>(j, 0), rny - 1);
+    return raw[j * rnx + i];
+  };
   for (int64_t j = 0; j < d.ny; ++j)
     for (int64_t i = 0; i < d.nx; ++i) {
-      T v = raw[j * d.nx + i];
+      const int64_t fi = i + d.di, fj = j + d.dj;     // read_data(…, ::BoundingBoxOffset, …) (:163)
+      T v;
+      switch (d.mangling[k]) {
+        case NE_MANGLE_SHIFT_SOUTH: v = file(fi, fj - 1); break;
+        case NE_MANGLE_AVERAGE_NORTH_SOUTH: { volatile T sum = file(fi, fj) + file(fi, fj + 1); v = sum / (T)2; break; }
+        default: v = file(fi, fj); break;
+      }
       if (d.has_missing[k] && v == mv) v = std::numeric_limits<T>::quiet_NaN();
       switch (d.conv_kind[k]) {
         case NE_CONV_NEGATE: v = -v; break;

@@ -155,6 +155,42 @@ def test_oracle_slot_fill_is_set_region_plus_halo_fill(oracle_lib, FT, periodic,
         assert np.array_equal(got[:, hx - 1], got[:, hx + nx - 1], equal_nan=True)
 
 
+def test_mangle_known_answers_of_the_reference(oracle_lib):
+    """test/test_mangling.jl:8-41: data = reshape(Float32[1 2 3; 4 5 6; 7 8 9], 3, 3, 1), data[i, j]; our raw[j, i]."""
+    data = np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9]], dtype=np.float32)    # data[i-1, j-1]
+    raw = np.ascontiguousarray(data.T)
+
+    def mangle(i, j, mangling):   # 1-based grid index (i, j) on a grid large enough to hold it; returns the interior value
+        nx, ny = max(i, 3), max(j, 3)
+        d = _ring_desc("f32", nx, ny, 0, 0)
+        d.raw_nx, d.raw_ny = 3, 3
+        d.mangling[0] = mangling
+        out = np.zeros((ny, nx), dtype=np.float32)
+        assert oracle_lib.dll.neo_series_slot_fill(C.addressof(d), 0, raw.ctypes.data, out.ctypes.data) == 0
+        return out[j - 1, i - 1]
+
+    N, S, AV = A.NE_MANGLE_NONE, A.NE_MANGLE_SHIFT_SOUTH, A.NE_MANGLE_AVERAGE_NORTH_SOUTH
+    assert mangle(2, 2, N) == 5
+    assert mangle(2, 2, S) == 4 and mangle(2, 1, S) == 4            # j - 1, clamped at the southern edge
+    assert mangle(2, 1, AV) == np.float32(4.5) and mangle(2, 2, AV) == np.float32(5.5)
+    assert mangle(4, 2, N) == data[2, 1] and mangle(2, 4, N) == data[1, 2]   # past the east / north edge: nearest cell
+    assert mangle(2, 5, S) == data[1, 2]                             # j - 1 past north
+    assert mangle(2, 3, AV) == data[1, 2]                            # j + 1 past north: (6 + 6) / 2
+
+
+@pytest.mark.parametrize("FT", ["f32", "f64"])
+def test_oracle_slot_fill_reads_a_bounding_box_region(oracle_lib, FT):
+    """read_data(data, i, j, k, b::BoundingBoxOffset, …) = mangle(i + di, j + dj, …) (set_region_data.jl:163)."""
+    rng = np.random.default_rng(2)
+    file = rng.normal(0, 1, (50, 90)).astype(NPD[FT])
+    nx, ny, di, dj = 20, 12, 31, 7
+    d = _ring_desc(FT, nx, ny, 2, 2, periodic=False)
+    d.raw_nx, d.raw_ny, d.di, d.dj = 90, 50, di, dj
+    got = _oracle_fill(oracle_lib, d, file, FT)
+    want = _numpy_fill(file[dj:dj + ny, di:di + nx], 2, 2, False, FT)
+    assert np.array_equal(got, want)
+
+
 # ------------------------------------------------------------------------------------------------- device
 def _window_case(backend, lib, FT, atm_FT, nt, n_slots, seed_offset=0):
     """Two identically seeded interfaces: `full` reads the series fully in memory (halos filled the reference's way),
@@ -263,6 +299,32 @@ def test_windowed_fused_step_and_host_pipeline_match_the_in_memory_step(cuda_bac
             x, y = cuda_backend.to_numpy(getattr(full.net_ocean, name)), cuda_backend.to_numpy(getattr(win.net_ocean, name))
             assert np.array_equal(x, y, equal_nan=True), (name, k)
     assert w.demand_loads == 2
+    w.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("FT", ["f32", "f64"])
+@pytest.mark.parametrize("case", ["shift_south", "average_north_south", "bounding_box"])
+def test_ring_slot_fill_with_mangling_and_regions_matches_the_oracle(cuda_backend, cuda_lib, oracle_lib, FT, case):
+    import torch
+    rng = np.random.default_rng(8)
+    src = ne_b200.LatLonSourceGrid(nx=72, ny=36, FT=FT)
+    raw_ny = {"shift_south": 35, "average_north_south": 37, "bounding_box": 60}[case]
+    raw_nx = 120 if case == "bounding_box" else 72
+    off = (17, 9) if case == "bounding_box" else (0, 0)
+    raw = {"v": rng.normal(0, 3, (2, raw_ny, raw_nx)).astype(NPD[FT])}
+    raw["v"][rng.random(raw["v"].shape) < 0.03] = NPD[FT](-9999.0)
+    w = SeriesWindow(cuda_backend, cuda_lib, src, np.arange(2) * 3600.0, raw, n_slots=2, conversions={"v": "CentimetersPerSecond"},
+                     missing_values={"v": -9999.0}, periodic_x=case != "bounding_box", region_offset=off)
+    assert w.mangling == {"shift_south": A.NE_MANGLE_SHIFT_SOUTH, "average_north_south": A.NE_MANGLE_AVERAGE_NORTH_SOUTH,
+                          "bounding_box": A.NE_MANGLE_NONE}[case]
+    w.time_interp(1800.0, cuda_backend.stream())
+    torch.cuda.synchronize()
+    ring = cuda_backend.to_numpy(w["v"])
+    for n in (1, 2):
+        want = _oracle_fill(oracle_lib, w.desc, raw["v"][n - 1], FT)
+        assert np.array_equal(ring[w.policy.where[n]], want, equal_nan=True), n
+        assert np.isnan(want).any() and np.isfinite(want).any()
     w.close()
 
 
