@@ -329,6 +329,36 @@ def test_ring_slot_fill_with_mangling_and_regions_matches_the_oracle(cuda_backen
 
 
 @pytest.mark.gpu
+def test_windowed_land_runoff_matches_the_in_memory_series(cuda_backend, cuda_lib):
+    """PrescribedLand (daily JRA55 river + iceberg runoff, Lands/interpolate_land_state.jl:6-61) behind its own ring."""
+    import torch
+    cfg = dict(nx=96, ny=40, latitude=(-70.0, 70.0), src_nx=64, src_ny=32, land_nx=120, land_ny=60)
+    nt = 7
+    full = synthetic.build_case(cfg, cuda_backend, FT="f64", atm_FT="f32", nt=nt, land=True)
+    win = synthetic.build_case(cfg, cuda_backend, FT="f64", atm_FT="f32", nt=nt, land=True)
+    lsrc = full.land.grid
+    series = [cuda_backend.to_numpy(x) for x in full.land.freshwater_flux]
+    raw = {f"runoff{k}": np.ascontiguousarray(v[:, lsrc.hy:lsrc.hy + lsrc.ny, lsrc.hx:lsrc.hx + lsrc.nx]) for k, v in enumerate(series)}
+    padded = [np.stack([_numpy_fill(v[n], lsrc.hx, lsrc.hy, True, "f32") for n in range(nt)]) for v in raw.values()]
+    full.land.freshwater_flux = tuple(cuda_backend.from_numpy(v) for v in padded)
+    w = SeriesWindow(cuda_backend, cuda_lib, lsrc, full.land.times, raw, n_slots=3)
+    win.land.freshwater_flux = tuple(w[k] for k in raw)
+    win.land.window = w
+    full.initialize()
+    win.initialize()
+    for k in range(40):
+        t = 1000.0 + k * 86400.0 * 0.45
+        full.interpolate_state(t)
+        win.interpolate_state(t)
+        torch.cuda.synchronize()
+        x, y = cuda_backend.to_numpy(full.land_state.freshwater_flux), cuda_backend.to_numpy(win.land_state.freshwater_flux)
+        assert np.array_equal(x, y, equal_nan=True), k
+        assert (x > 0).any()
+    assert w.demand_loads == 2 and w.prefetched >= 15
+    w.close()
+
+
+@pytest.mark.gpu
 def test_ring_rejects_bad_descriptors(cuda_backend, cuda_lib):
     d = _ring_desc("f32", 8, 8, 3, 3)
     h = C.c_void_p()
