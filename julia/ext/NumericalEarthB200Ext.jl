@@ -147,5 +147,12 @@ end
 # rotation (interpolate_atmospheric_state.jl:123-126): `NeInterpDesc.rotation_cos/sin` are filled once in initialize!
 # from Oceananigans' rotation metrics of the exchange grid, `rotate_u/v = 0/1`.
 # Host-resident ocean state: ne_host_pipeline_create once, ne_host_pipelined_step_* per coupled step (INTEGRATION.md §5).
+#
+# Partly-in-memory series: Oceananigans.TimeSteppers.update_state!(atmos::PrescribedAtmosphere) for a B200 model does not
+# call update_field_time_series! (whole-window set!(fts), src/Atmospheres/prescribed_atmosphere.jl:154-162); the parent of
+# every series is a ring of Nt_mem slices owned by ne_series_ring_create, and the interpolate_state! override does
+# load (first step / clock jump) -> acquire -> launch -> release -> prefetch loads, as INTEGRATION.md §6 spells out;
+# the raw slices come from the same NCDatasets reads set!(fts) performs (JRA55_field_time_series.jl:60-76), one time
+# index at a time, into pinned host buffers.
 
 end # module
