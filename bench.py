@@ -80,6 +80,7 @@ def parse():
     p.add_argument("--e2e-chunks", type=int, default=8)
     p.add_argument("--equal-bands", action="store_true", help="equal row counts per band instead of cost-balanced bands")
     p.add_argument("--no-extras", action="store_true", help="skip the one-number measurements of the other BASELINE configs")
+    p.add_argument("--sync-allreduce", action="store_true", help="diagnostics all-reduce on the compute stream (not overlapped)")
     p.add_argument("--no-rebalance", action="store_true", help="keep the mask-based bands (no re-balancing from measured trip counts)")
     return p.parse_args()
 
@@ -282,8 +283,9 @@ def b200_arm(args):
 
     def step():
         set_time(state["t"])
+        diag.flip(fused)                 # the previous step's all-reduce may still be in flight on the other result vector
         lib.call("fused_interface_step", args.dtype, fused, stream)
-        diag.all_reduce()
+        diag.all_reduce(async_op=not args.sync_allreduce)   # on the communicator's stream, overlapped by the next step's kernels
         state["t"] += DT_STEP
 
     def barrier():
@@ -297,6 +299,7 @@ def b200_arm(args):
         e0.record()
         for _ in range(n):
             fn()
+        diag.wait()                      # the timed region ends after the last step's all-reduce
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)

@@ -93,7 +93,10 @@ class FluxDiagnostics:
         area = (np.cos(phi)[:, None] * np.ones((1, g.shape[1]))).astype(np.float64 if g.FT == "f64" else np.float32)
         self.area = b.from_numpy(area)
         self.partial = b.zeros((n_blocks * len(fields),), "f64")
-        self.result = b.zeros((len(fields),), "f64")
+        # two result vectors: with an asynchronous all-reduce the next step's local sums go to the other one
+        self.results = [b.zeros((len(fields),), "f64"), b.zeros((len(fields),), "f64")]
+        self._cur = 0
+        self._work = [None, None]
         d = A.NeDiagDesc()
         d.grid = g.pod(False)
         d.n_fields = len(fields)
@@ -101,8 +104,39 @@ class FluxDiagnostics:
             d.fields[k] = b.ptr(f)
         d.area = b.ptr(self.area)
         d.inactive = b.ptr(interfaces.inactive) if interfaces.inactive is not None else None
-        d.partial, d.n_blocks, d.result = b.ptr(self.partial), n_blocks, b.ptr(self.result)
+        d.partial, d.n_blocks, d.result = b.ptr(self.partial), n_blocks, b.ptr(self.results[0])
         self.desc = d
+
+    @property
+    def result(self):
+        """The result vector of the current step (global sums once its all-reduce has been waited for)."""
+        return self.results[self._cur]
+
+    def flip(self, *descs):
+        """Switch to the other result vector before enqueuing the next step, so that an all-reduce still in flight
+        (all_reduce(async_op=True)) is not overwritten.  `descs`: cached NeFusedStepDesc / NeHostStepDesc / NeDiagDesc
+        copies of this object's descriptor whose `result` pointer has to follow."""
+        self._cur ^= 1
+        w = self._work[self._cur]
+        if w is not None:          # the all-reduce issued two steps ago into this vector: long done, orders the streams
+            w.wait()
+            self._work[self._cur] = None
+        ptr = self.ci.backend.ptr(self.results[self._cur])
+        self.desc.result = ptr
+        for d in descs:
+            if hasattr(d, "step"):
+                d.step.diag.result = ptr
+            elif hasattr(d, "diag"):
+                d.diag.result = ptr
+            else:
+                d.result = ptr
+
+    def wait(self):
+        """Make the current stream (or the host, gloo) wait for every all-reduce still in flight."""
+        for k, w in enumerate(self._work):
+            if w is not None:
+                w.wait()
+                self._work[k] = None
 
     def reduce(self, group=None):
         """Enqueue the local reduction and (world_size > 1) the all-reduce; returns the device/host
@@ -110,19 +144,29 @@ class FluxDiagnostics:
         self.ci.lib.call("diag_reduce", self.ci.grid.FT, self.desc, self.ci.backend.stream())
         return self.all_reduce(group)
 
-    def all_reduce(self, group=None):
+    def all_reduce(self, group=None, async_op=False):
         """The collective alone: for local sums already produced by the fused interface step
-        (NeFusedStepDesc.diag)."""
+        (NeFusedStepDesc.diag).  async_op: the collective runs on the communicator's own stream behind the kernels
+        enqueued so far and the current stream does NOT wait for it — the next step's kernels overlap it; call
+        flip() before enqueuing that step and wait() before reading `result`."""
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
                 r = self.result
                 if isinstance(r, np.ndarray):
                     import torch
-                    t = torch.from_numpy(r)
-                    dist.all_reduce(t, group=group)
+                    r = torch.from_numpy(r)
+                if async_op:
+                    self.wait_current()
+                    self._work[self._cur] = dist.all_reduce(r, group=group, async_op=True)
                 else:
                     dist.all_reduce(r, group=group)
         except ImportError:
             pass
         return self.result
+
+    def wait_current(self):
+        w = self._work[self._cur]
+        if w is not None:
+            w.wait()
+            self._work[self._cur] = None

@@ -69,7 +69,23 @@ def _worker(rank, world, port, q):
     local = np.array([(np.asarray(x)[rows, cols] * diag.area[rows, cols])[act].sum() for x in diag.fields])
     t = torch.from_numpy(local.copy())
     dist.all_reduce(t)
-    q.put((rank, t.numpy().copy(), local))
+    # the product's collective, asynchronous and double-buffered the way bench.py steps: three "steps" whose local sums
+    # are k * local; each result is read only after wait(), while the next step's sums already sit in the other vector
+    seen = []
+    for k in (1, 2, 3):
+        diag.flip()
+        assert diag.desc.result == ci.backend.ptr(diag.result)
+        diag.result[:] = k * local
+        diag.all_reduce(async_op=True)
+        if k > 1:
+            prev = diag.results[diag._cur ^ 1]
+            w = diag._work[diag._cur ^ 1]
+            if w is not None:
+                w.wait()
+            seen.append(prev.copy())
+    diag.wait()
+    seen.append(diag.result.copy())
+    q.put((rank, t.numpy().copy(), local, seen))
     dist.destroy_process_group()
 
 
@@ -87,6 +103,10 @@ def test_diagnostics_all_reduce_two_ranks_gloo(oracle_lib, host_backend):
     res.sort(key=lambda x: x[0])
     assert np.array_equal(res[0][1], res[1][1])                       # every rank holds the same global sums
     assert np.allclose(res[0][1], res[0][2] + res[1][2], rtol=1e-15)
+    for r in res:                                                     # the asynchronous, double-buffered path: step k sums to k x global
+        assert len(r[3]) == 3
+        for k, got in enumerate(r[3], start=1):
+            assert np.allclose(got, k * (res[0][2] + res[1][2]), rtol=1e-15), k
     # and they equal the single-rank (global grid) integrals
     glob = synthetic.build_case("tiny", host_backend, lib=oracle_lib)
     glob.initialize(); glob.update_state(4000.0)
