@@ -105,6 +105,110 @@ def test_upcoming_wraps_only_for_cyclical_series():
     assert WindowPolicy(2, 2, "cyclical").upcoming(2, 3) == [1]
 
 
+# ------------------------------------------------------------------------------------------------- call order (CPU, fakes)
+class _FakeDll:
+    """Records the ring entry points SeriesWindow calls, in order."""
+
+    def __init__(self):
+        self.calls = []
+
+    def ne_series_ring_create(self, handle_ref, desc_ref):
+        self.calls.append(("create",))
+        handle_ref._obj.value = 0xB200    # a non-null handle
+        return 0
+
+    def ne_series_ring_destroy(self, handle):
+        self.calls.append(("destroy",))
+        return 0
+
+    def ne_series_ring_load(self, handle, slot, ptrs):
+        self.calls.append(("load", slot.value, tuple(int(p) for p in ptrs)))
+        return 0
+
+    def ne_series_ring_acquire(self, handle, slot, stream):
+        self.calls.append(("acquire", slot.value))
+        return 0
+
+    def ne_series_ring_release(self, handle, stream):
+        self.calls.append(("release",))
+        return 0
+
+
+class _FakePinned:
+    def __init__(self, a):
+        self.a = a
+
+    def pin_memory(self):
+        return self
+
+    def data_ptr(self):
+        return self.a.ctypes.data
+
+
+class _FakeTorch:
+    @staticmethod
+    def from_numpy(a):
+        return _FakePinned(a)
+
+
+class _FakeDeviceBackend(ne_b200.NumpyHostBackend):
+    is_device = True
+    torch = _FakeTorch()
+
+
+class _FakeLib:
+    def __init__(self):
+        self.dll = _FakeDll()
+
+    def last_error(self):
+        return ""
+
+
+def test_series_window_call_order_and_host_slices():
+    """What SeriesWindow asks of the native ring, step by step: demand loads before acquire, acquire of both slots before the
+    launch, release after it, then the prefetch loads — each load handing over the host pointers of THAT time index."""
+    src = ne_b200.LatLonSourceGrid(nx=16, ny=8, FT="f32")
+    nt = 6
+    raw = {"a": np.arange(nt * 8 * 16, dtype=np.float32).reshape(nt, 8, 16), "b": np.ones((nt, 8, 16), np.float32)}
+    lib = _FakeLib()
+    w = SeriesWindow(_FakeDeviceBackend(), lib, src, np.arange(nt) * 100.0, raw, n_slots=4)
+    calls = lib.dll.calls
+    assert calls == [("create",)]
+    assert w.series["a"].shape == (4, 8 + 2 * src.hy, 16 + 2 * src.hx)
+    assert (w.desc.n_series, w.desc.n_slots, w.desc.raw_nx, w.desc.raw_ny) == (2, 4, 16, 8)
+    slice_bytes = 8 * 16 * 4
+
+    def host_ptrs(n):
+        return tuple(w.host[k].data_ptr() + (n - 1) * slice_bytes for k in ("a", "b"))
+
+    del calls[:]
+    frac, m1, m2, same = w.time_interp(150.0, 0)           # n1 = 2, n2 = 3
+    assert (frac, same) == (0.5, 0) and m1 != m2
+    assert calls == [("load", m1 - 1, host_ptrs(2)), ("load", m2 - 1, host_ptrs(3)), ("acquire", m1 - 1), ("acquire", m2 - 1)] or \
+        calls == [("load", m1 - 1, host_ptrs(2)), ("load", m2 - 1, host_ptrs(3)), ("acquire", m2 - 1), ("acquire", m1 - 1)]
+    del calls[:]
+    w.after_launch(0)
+    assert calls[0] == ("release",)
+    loads = calls[1:]
+    assert [c[0] for c in loads] == ["load", "load"]         # lookahead = n_slots - 2: time indices 4 and 5
+    assert [c[2] for c in loads] == [host_ptrs(4), host_ptrs(5)]
+    assert {c[1] for c in loads}.isdisjoint({m1 - 1, m2 - 1})
+    del calls[:]
+    # same interval again: nothing to load, only the two waits and the release
+    w.time_interp(180.0, 0)
+    w.after_launch(0)
+    assert sorted(c[0] for c in calls) == ["acquire", "acquire", "release"]
+    del calls[:]
+    # next interval (n1 = 3, n2 = 4): both resident; the prefetch replaces the slot of time index 2 with index 6
+    slot_of_2 = w.policy.where[2]
+    w.time_interp(250.0, 0)
+    w.after_launch(0)
+    assert [c for c in calls if c[0] == "load"] == [("load", slot_of_2, host_ptrs(6))]
+    assert (w.demand_loads, w.prefetched) == (2, 3)
+    w.close()
+    assert calls[-1] == ("destroy",)
+
+
 # ------------------------------------------------------------------------------------------------- slot fill (oracle, CPU)
 def _ring_desc(FT, nx, ny, hx, hy, n_series=1, periodic=True, conv=None, missing=None):
     d = A.NeSeriesRingDesc()
