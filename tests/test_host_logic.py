@@ -134,3 +134,24 @@ def test_cuda_library_refuses_host_arrays(host_backend):
     g = ne_b200.ExchangeGrid(nx=4, ny=4, hx=2, hy=2)
     with pytest.raises(RuntimeError):
         ne_b200.ComponentInterfaces(g, host_backend, None, None, lib=ne_b200.Library())
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the CUDA arm) needs no GPU: one JSON line on
+    stdout carrying the contract keys, the oracle as `cpu_baseline` and an e2e block with zero copies."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "air-sea flux points/s" and d["unit"] == "points/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("C4")
