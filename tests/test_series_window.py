@@ -99,6 +99,25 @@ def test_clock_jumps_reload_on_demand_and_recover():
     assert sum(dem) == 0
 
 
+def test_policy_invariants_under_arbitrary_clocks():
+    """Any sequence of clock values, any window size, any indexing: the two interpolating slices are resident together
+    after `demand`, a prefetch never displaces them, and the slot table stays consistent (checked inside _walk)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(nt=st.integers(2, 20), n_slots=st.integers(2, 8), indexing=st.sampled_from(["cyclical", "linear", "clamp"]),
+           ts=st.lists(st.floats(-5e4, 4e5, allow_nan=False), min_size=1, max_size=40), lookahead=st.one_of(st.none(), st.integers(0, 9)))
+    def run(nt, n_slots, indexing, ts, lookahead):
+        times = np.arange(nt) * 10800.0
+        policy = WindowPolicy(nt, min(n_slots, nt), indexing, lookahead)
+        dem, pre = _walk(policy, times, ts, indexing)
+        assert max(dem) <= 2
+        assert all(p <= policy.lookahead for p in pre)
+        assert len(policy.where) <= policy.n_slots
+
+    run()
+
+
 def test_upcoming_wraps_only_for_cyclical_series():
     assert WindowPolicy(5, 4, "cyclical").upcoming(4, 3) == [5, 1, 2]
     assert WindowPolicy(5, 4, "linear").upcoming(4, 3) == [5]
