@@ -228,6 +228,69 @@ def test_series_window_call_order_and_host_slices():
     assert calls[-1] == ("destroy",)
 
 
+class _HostRing:
+    """A window whose rings live in host memory and whose slot loads are the oracle's slot fill: the interface wiring
+    (ring slots in NeTimeInterp, src_nt = n_slots, release after the launches) checked on the CPU against the oracle."""
+
+    def __init__(self, oracle_lib, grid, times, raw, n_slots, indexing="cyclical"):
+        self.lib, self.grid, self.times, self.raw, self.n_slots, self.time_indexing = oracle_lib, grid, times, raw, n_slots, indexing
+        self.policy = WindowPolicy(len(times), n_slots, indexing)
+        self.series = {k: np.full((n_slots,) + tuple(grid.shape), np.nan, dtype=NPD[grid.FT]) for k in raw}
+        self.desc = _ring_desc(grid.FT, grid.nx, grid.ny, grid.hx, grid.hy)
+        self.loads, self.releases, self._current = 0, 0, None
+
+    def _load(self, n, slot):
+        for k, v in self.raw.items():
+            self.series[k][slot] = _oracle_fill(self.lib, self.desc, v[n - 1], self.grid.FT)
+        self.loads += 1
+
+    def time_interp(self, t, stream):
+        frac, n1, n2 = ne_b200.interpolating_time_indices(self.times, t, self.time_indexing)
+        for n, slot in self.policy.demand(n1, n2):
+            self._load(n, slot)
+        self._current = (n1, n2)
+        return frac, self.policy.where[n1] + 1, self.policy.where[n2] + 1, int(n1 == n2)
+
+    def after_launch(self, stream):
+        self.releases += 1
+        for n, slot in self.policy.prefetch(*self._current):
+            self._load(n, slot)
+
+
+@pytest.mark.parametrize("FT,atm_FT", [("f64", "f32"), ("f32", "f32")])
+def test_interface_reads_ring_slots_like_the_in_memory_series_on_the_oracle(oracle_lib, host_backend, FT, atm_FT):
+    cfg = dict(nx=48, ny=20, latitude=(-60.0, 60.0), src_nx=32, src_ny=16)
+    nt = 6
+    full = synthetic.build_case(cfg, host_backend, FT=FT, atm_FT=atm_FT, nt=nt, lib=oracle_lib)
+    win = synthetic.build_case(cfg, host_backend, FT=FT, atm_FT=atm_FT, nt=nt, lib=oracle_lib)
+    src = full.atmosphere.grid
+    a = full._host_inputs["atmosphere"]
+    raw = {k: np.ascontiguousarray(v[:, src.hy:src.hy + src.ny, src.hx:src.hx + src.nx]) for k, v in a.items()}
+    padded = {k: np.stack([_numpy_fill(v[n], src.hx, src.hy, True, atm_FT) for n in range(nt)]) for k, v in raw.items()}
+    ring = _HostRing(oracle_lib, src, full.atmosphere.times, raw, n_slots=3)
+    for ci, s in ((full, padded), (win, ring.series)):
+        atm, rad = ci.atmosphere, ci.radiation
+        atm.u, atm.v, atm.T, atm.q, atm.p = s["u"], s["v"], s["T"], s["q"], s["p"]
+        atm.rain, atm.snow = (s["rain"],), (s["snow"],)
+        rad.downwelling_shortwave, rad.downwelling_longwave = s["sw"], s["lw"]
+    win.atmosphere.window = win.radiation.window = ring      # one ring shared by both components
+    full.initialize()
+    win.initialize()
+    steps = 0
+    for k in range(2 * nt * 2 + 3):
+        t = 50.0 + k * 10800.0 / 2
+        full.update_state(t)
+        win.update_state(t)
+        steps += 1
+        for bag_f, bag_w in ((full.atmos_state, win.atmos_state), (full.rad_state, win.rad_state), (full.ao_fluxes, win.ao_fluxes),
+                             (full.net_ocean, win.net_ocean)):
+            for name in bag_f.names():
+                assert np.array_equal(getattr(bag_f, name), getattr(bag_w, name), equal_nan=True), (name, k)
+    assert ring.releases == steps                            # once per step although two components share the ring
+    crossed = int((50.0 + (steps - 1) * 10800.0 / 2) // 10800.0)
+    assert ring.loads == 2 + 1 + crossed                     # two on demand, one look-ahead, then one prefetch per interval entered
+
+
 # ------------------------------------------------------------------------------------------------- slot fill (oracle, CPU)
 def _ring_desc(FT, nx, ny, hx, hy, n_series=1, periodic=True, conv=None, missing=None):
     d = A.NeSeriesRingDesc()
