@@ -155,3 +155,18 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("C4")
+
+
+def test_prescribed_radiation_defaults_match_reference():
+    """test/test_radiations.jl:20-24: ocean albedo 0.05 / emissivity 0.97, sea ice 0.7 / 1.0, σ ≈ 5.67e-8 (atol 1e-10);
+    :63-79: a land surface given as numbers is read back unchanged."""
+    src = ne_b200.LatLonSourceGrid(nx=8, ny=4)
+    rad = ne_b200.PrescribedRadiation(grid=src, times=[0.0, 1.0])
+    assert rad.surface_properties["ocean"].albedo == 0.05 and rad.surface_properties["ocean"].emissivity == 0.97
+    assert rad.surface_properties["sea_ice"].albedo == 0.7 and rad.surface_properties["sea_ice"].emissivity == 1.0
+    assert abs(rad.stefan_boltzmann_constant - 5.67e-8) < 1e-10
+    assert set(rad.surface_properties) == {"ocean", "sea_ice"}
+    land = ne_b200.SurfaceRadiationProperties(0.15, 0.93)
+    rad2 = ne_b200.PrescribedRadiation(grid=src, times=[0.0, 1.0], surface_properties={"land": land})
+    assert rad2.surface_properties["land"].albedo == 0.15 and rad2.surface_properties["land"].emissivity == 0.93
+    assert rad.window is None and rad.time_indexing == "cyclical"
