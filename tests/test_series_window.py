@@ -377,6 +377,38 @@ def test_oracle_slot_fill_reads_a_bounding_box_region(oracle_lib, FT):
     assert np.array_equal(got, want)
 
 
+def test_oracle_slot_fill_against_numpy_for_random_shapes_regions_and_manglings(oracle_lib):
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=120, deadline=None)
+    @given(nx=st.integers(1, 24), ny=st.integers(1, 16), hx=st.integers(0, 3), hy=st.integers(0, 3), periodic=st.booleans(),
+           mangling=st.sampled_from([A.NE_MANGLE_NONE, A.NE_MANGLE_SHIFT_SOUTH, A.NE_MANGLE_AVERAGE_NORTH_SOUTH]),
+           di=st.integers(0, 5), dj=st.integers(0, 5), ex=st.integers(-1, 6), ey=st.integers(-1, 6), FT=st.sampled_from(["f32", "f64"]),
+           seed=st.integers(0, 2**16))
+    def run(nx, ny, hx, hy, periodic, mangling, di, dj, ex, ey, FT, seed):
+        hx, hy = min(hx, nx), min(hy, ny)
+        rnx, rny = max(1, nx + di + ex), max(1, ny + dj + ey)      # the file may be larger OR smaller than region + grid
+        rng = np.random.default_rng(seed)
+        file = rng.normal(0, 1, (rny, rnx)).astype(NPD[FT])
+        d = _ring_desc(FT, nx, ny, hx, hy, periodic=periodic)
+        d.raw_nx, d.raw_ny, d.di, d.dj = rnx, rny, di, dj
+        d.mangling[0] = mangling
+        got = _oracle_fill(oracle_lib, d, file, FT)
+        # numpy restatement of read_data + mangle (set_region_data.jl:48-53, :163): clamped file indices
+        ii = np.clip(np.arange(nx) + di, 0, rnx - 1)
+        jj = np.arange(ny) + dj
+        if mangling == A.NE_MANGLE_SHIFT_SOUTH:
+            interior = file[np.clip(jj - 1, 0, rny - 1)][:, ii]
+        elif mangling == A.NE_MANGLE_AVERAGE_NORTH_SOUTH:
+            interior = (file[np.clip(jj, 0, rny - 1)][:, ii] + file[np.clip(jj + 1, 0, rny - 1)][:, ii]) / NPD[FT](2)
+        else:
+            interior = file[np.clip(jj, 0, rny - 1)][:, ii]
+        want = _numpy_fill(interior, hx, hy, periodic, FT)
+        assert np.array_equal(got, want)
+
+    run()
+
+
 # ------------------------------------------------------------------------------------------------- device
 def _window_case(backend, lib, FT, atm_FT, nt, n_slots, seed_offset=0):
     """Two identically seeded interfaces: `full` reads the series fully in memory (halos filled the reference's way),
