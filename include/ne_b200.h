@@ -659,6 +659,14 @@ int ne_series_ring_release(void* handle, void* compute_stream);
  * (MEASURED_PEAKS.json has no FP64 figure).  Returns achieved TFLOP/s in *tflops. */
 int ne_measure_fp64_peak(double* tflops, double* sm_clock_mhz_estimate);
 
+/* FP64 instructions ONE launch of ne_atmosphere_ocean_fluxes_f64 executes on this descriptor (default plugin tree):
+ * runs the counting instantiation of the shipped solve kernel (same source, every FP64 operation goes through a
+ * counting policy) and synchronises.  out[0..5] = thread-level {fused multiply-adds, multiplies, adds/subtracts,
+ * estimated instructions of library code the policy cannot see (IEEE division / libdevice on rare paths),
+ * thread trips (iterate_interface_state calls), warp trips (32-lane loop passes)}; out[6..7] reserved.
+ * Executed flop = 2 out[0] + out[1] + out[2].  The roofline numerator of bench.py; no profiler involved. */
+int ne_count_solve_ops_f64(const NeAtmosOceanDesc*, uint64_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@ OBJ = os.path.join(HERE, "_obj")
 SOURCES = {
     "ne_api.cu": [],
     "ne_flux_kernels.cu": [],
+    "ne_flux_tab2.cu": [],
     "ne_flux_generic_ao_f64.cu": [],
     "ne_flux_generic_ao_f32.cu": [],
     "ne_flux_generic_asi_f64.cu": [],
@@ -41,6 +42,7 @@ DEPS = ["ne_common.cuh", "ne_physics.cuh", os.path.join("..", "..", "include", "
 EXTRA_DEPS = {
     "ne_flux_kernels.cu": ["ne_flux_fast.cuh", "ne_flux_tab.cuh", "ne_flux_queue.cuh", "ne_flux_asi_fast.cuh", "ne_flux_land_fast.cuh", "ne_queue_host.cuh", "ne_fastmath.cuh", "ne_interp_device.cuh"],
     "ne_interp_kernels.cu": ["ne_interp_device.cuh"],
+    "ne_flux_tab2.cu": ["ne_flux_fast.cuh", "ne_flux_tab.cuh", "ne_flux_tab2.cuh", "ne_fastmath.cuh", "ne_queue_host.cuh"],
     "ne_flux_generic_ao_f64.cu": ["ne_flux_generic.cuh"],
     "ne_flux_generic_ao_f32.cu": ["ne_flux_generic.cuh"],
     "ne_flux_generic_asi_f64.cu": ["ne_flux_generic.cuh"],

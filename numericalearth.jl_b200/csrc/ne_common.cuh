@@ -77,17 +77,21 @@ __device__ __forceinline__ FT slot_at(const NeSlot& s, int64_t idx) {
 }
 
 // ---- typed math: float and double overloads, never fast-math ------------------------------------
-__device__ __forceinline__ float  m_exp(float x)   { return expf(x); }
+// Float32 transcendentals are evaluated in Float64 and rounded once: the correctly rounded Float32 function (up to
+// double rounding, probability ~2^-29 per call).  That is what Julia's Float32 `^` does (Base.Math.pow_body widens to
+// Float64) and within half an ulp of its other Float32 functions; CUDA's powf / expf (2-4 ulp) would put a Float32
+// q_sat (interface_states.jl:56-59) 1e-7 away from the oracle's.
+__device__ __forceinline__ float  m_exp(float x)   { return (float)exp((double)x); }
 __device__ __forceinline__ double m_exp(double x)  { return exp(x); }
-__device__ __forceinline__ float  m_log(float x)   { return logf(x); }
+__device__ __forceinline__ float  m_log(float x)   { return (float)log((double)x); }
 __device__ __forceinline__ double m_log(double x)  { return log(x); }
-__device__ __forceinline__ float  m_atan(float x)  { return atanf(x); }
+__device__ __forceinline__ float  m_atan(float x)  { return (float)atan((double)x); }
 __device__ __forceinline__ double m_atan(double x) { return atan(x); }
-__device__ __forceinline__ float  m_cbrt(float x)  { return cbrtf(x); }
+__device__ __forceinline__ float  m_cbrt(float x)  { return (float)cbrt((double)x); }
 __device__ __forceinline__ double m_cbrt(double x) { return cbrt(x); }
 __device__ __forceinline__ float  m_sqrt(float x)  { return sqrtf(x); }
 __device__ __forceinline__ double m_sqrt(double x) { return sqrt(x); }
-__device__ __forceinline__ float  m_pow(float x, float y)   { return powf(x, y); }
+__device__ __forceinline__ float  m_pow(float x, float y)   { return (float)pow((double)x, (double)y); }
 __device__ __forceinline__ double m_pow(double x, double y) { return pow(x, y); }
 __device__ __forceinline__ double m_pow(float x, double y)  { return pow((double)x, y); }
 __device__ __forceinline__ double m_pow(double x, float y)  { return pow(x, (double)y); }

@@ -112,6 +112,50 @@ NE_HD double mul_(double a, double b) {
 #endif
 }
 
+// ---- operation policies ---------------------------------------------------------------------------
+// Every FP64 operation of the hot path goes through a policy object: OpsPlain issues the separately rounded
+// instruction and nothing else; OpsCount additionally counts it per thread, so an instrumented instantiation of
+// the SAME kernel source reports the FP64 instructions a launch executes (bench.py's roofline numerator) without
+// a profiler.  add/sub/mul are never contracted (explicit __d*_rn), fma is an explicit fused operation.
+struct OpsPlain {
+  NE_HD double fma(double a, double b, double c) { return fma_(a, b, c); }
+  NE_HD double mul(double a, double b) { return mul_(a, b); }
+  NE_HD double add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b; return r;
+#endif
+  }
+  NE_HD double sub(double a, double b) { return add(a, -b); }
+  NE_HD void other(int) {}
+  NE_HD void trip() {}
+  NE_HD void flush(unsigned long long*) {}
+};
+struct OpsCount {
+  unsigned long long n_fma = 0, n_mul = 0, n_add = 0;
+  OpsPlain base;
+  NE_HD double fma(double a, double b, double c) { ++n_fma; return base.fma(a, b, c); }
+  NE_HD double mul(double a, double b) { ++n_mul; return base.mul(a, b); }
+  NE_HD double add(double a, double b) { ++n_add; return base.add(a, b); }
+  NE_HD double sub(double a, double b) { ++n_add; return base.sub(a, b); }
+  unsigned long long n_other = 0, n_trips = 0;
+  NE_HD void other(int n) { n_other += (unsigned)n; }   // library code the policy cannot see (IEEE division, libdevice): a declared estimate, reported apart
+  NE_HD void trip() { ++n_trips; }
+  // counts[0..4] += {fma, mul, add, other, thread trips}
+  NE_HD void flush(unsigned long long* counts) {
+#if defined(__CUDA_ARCH__)
+    if (counts) {
+      atomicAdd(counts + 0, n_fma); atomicAdd(counts + 1, n_mul); atomicAdd(counts + 2, n_add);
+      atomicAdd(counts + 3, n_other); atomicAdd(counts + 4, n_trips);
+    }
+#else
+    if (counts) { counts[0] += n_fma; counts[1] += n_mul; counts[2] += n_add; counts[3] += n_other; counts[4] += n_trips; }
+#endif
+    n_fma = n_mul = n_add = n_other = n_trips = 0;
+  }
+};
+
 // ---- seeds (≈ 20 bits on the device; the host emulation rounds to Float32) ------------------------
 NE_HD double rcp_seed(double x) {
 #if defined(__CUDA_ARCH__)
@@ -129,32 +173,32 @@ NE_HD double rsqrt_seed(double x) {
 }
 
 // 1/x, x finite, normal, non-zero (either sign): seed + two Newton steps
-NE_HD double rcp(double x) {
+template <class O> NE_HD double rcp(O& o, double x) {
   double r = rcp_seed(x);
-  double e = fma_(-x, r, 1.0);
-  r = fma_(r, e, r);
-  e = fma_(-x, r, 1.0);
-  return fma_(r, e, r);
+  double e = o.fma(-x, r, 1.0);
+  r = o.fma(r, e, r);
+  e = o.fma(-x, r, 1.0);
+  return o.fma(r, e, r);
 }
 // a/b with one residual correction (≲ 1 ulp)
-NE_HD double div(double a, double b) {
-  const double r = rcp(b);
-  const double q = a * r;
-  return fma_(fma_(-b, q, a), r, q);
+template <class O> NE_HD double div(O& o, double a, double b) {
+  const double r = rcp(o, b);
+  const double q = o.mul(a, r);
+  return o.fma(o.fma(-b, q, a), r, q);
 }
 // sqrt(x), x > 0 normal: coupled Goldschmidt iteration + residual correction
-NE_HD double sqrt_pos(double x) {
+template <class O> NE_HD double sqrt_pos(O& o, double x) {
   const double r = rsqrt_seed(x);
-  double g = x * r, h = 0.5 * r;
-  double e = fma_(-h, g, 0.5);
-  g = fma_(g, e, g); h = fma_(h, e, h);
-  e = fma_(-h, g, 0.5);
-  g = fma_(g, e, g); h = fma_(h, e, h);
-  return fma_(fma_(-g, g, x), h, g);
+  double g = o.mul(x, r), h = o.mul(0.5, r);
+  double e = o.fma(-h, g, 0.5);
+  g = o.fma(g, e, g); h = o.fma(h, e, h);
+  e = o.fma(-h, g, 0.5);
+  g = o.fma(g, e, g); h = o.fma(h, e, h);
+  return o.fma(o.fma(-g, g, x), h, g);
 }
 // cbrt(x), x > 0 normal.  x = 2^(3q)·m with m ∈ [1, 8): seed m^(-1/3) in Float32 (MUFU lg2/ex2 on the
 // device), two Newton steps on r ↦ r + r(1 − m r³)/3, result m·r²·2^q.
-NE_HD double cbrt_pos(const MathConsts& C, double x) {
+template <class O> NE_HD double cbrt_pos(O& o, const MathConsts& C, double x) {
   const int32_t hi = hi32(x);
   const int32_t e = (hi >> 20) - 1023;                 // unbiased exponent
   const int32_t q = (e + 3072) * 21846 >> 16;          // floor((e + 3072)/3), exact for |e| ≤ 1100
@@ -169,49 +213,57 @@ NE_HD double cbrt_pos(const MathConsts& C, double x) {
   double r = (double)(float)std::exp2(-std::log2((float)m) / 3.0f) * (1.0 + 4e-7);
 #endif
   const double third = C.third;
-  double r2 = r * r;
-  double e1 = fma_(-m * r, r2, 1.0);
-  r = fma_(r * third, e1, r);
-  r2 = r * r;
-  e1 = fma_(-m * r, r2, 1.0);
-  r = fma_(r * third, e1, r);
-  double y = (m * r) * r;                              // m^(1/3) ∈ [1, 2)
+  double r2 = o.mul(r, r);
+  double e1 = o.fma(o.mul(-m, r), r2, 1.0);
+  r = o.fma(o.mul(r, third), e1, r);
+  r2 = o.mul(r, r);
+  e1 = o.fma(o.mul(-m, r), r2, 1.0);
+  r = o.fma(o.mul(r, third), e1, r);
+  double y = o.mul(o.mul(m, r), r);                    // m^(1/3) ∈ [1, 2)
   // one residual step on y: y ← y − (y³ − m)/(3y²) = y + (m − y³)·r²/3  (r ≈ 1/y)
-  const double y2 = y * y;
-  y = fma_(fma_(-y2, y, m), (r * r) * third, y);
+  const double y2 = o.mul(y, y);
+  y = o.fma(o.fma(-y2, y, m), o.mul(o.mul(r, r), third), y);
   return mk64(hi32(y) + (q3 << 20), lo32(y));
 }
 
 // log(x), x > 0 normal.  x = 2^k z, z ∈ [√½, √2); z = c_i(1 + r), |r| ≤ 2^-7; table holds 1/c_i and log c_i.
-NE_HD double log_pos(const double* __restrict__ tab, const MathConsts& C, double x) {
+template <class O> NE_HD double log_pos(O& o, const double* __restrict__ tab, const MathConsts& C, double x) {
   const int32_t hi = hi32(x);
   const int32_t tmp = hi - 0x3fe6a09e;
   const int32_t k = tmp >> 20;
   const int32_t i = (tmp >> 14) & (LOG_N - 1);
   const double z = mk64(hi - (k << 20), lo32(x));
   const double invc = tab[TAB_LOG + 2 * i], logc = tab[TAB_LOG + 2 * i + 1];
-  const double r = fma_(z, invc, -1.0);
+  const double r = o.fma(z, invc, -1.0);
   double p = C.logp[LOG_DEG - 1];
 #pragma unroll
-  for (int n = LOG_DEG - 2; n >= 0; --n) p = fma_(p, r, C.logp[n]);
-  const double r2 = r * r;
-  const double base = fma_((double)k, C.ln2, logc);
-  return base + fma_(r2, p, r);
+  for (int n = LOG_DEG - 2; n >= 0; --n) p = o.fma(p, r, C.logp[n]);
+  const double r2 = o.mul(r, r);
+  const double base = o.fma((double)k, C.ln2, logc);
+  return o.add(base, o.fma(r2, p, r));
 }
 
 // exp(x), |x| ≤ 700.  x = k ln2 + r; 2^k applied by exponent arithmetic (result stays normal).
-NE_HD double exp_mid(const MathConsts& C, double x) {
+template <class O> NE_HD double exp_mid(O& o, const MathConsts& C, double x) {
   const double magic = 6755399441055744.0;  // 1.5·2^52
-  const double t = fma_(x, C.log2e, magic);
+  const double t = o.fma(x, C.log2e, magic);
   const int32_t k = lo32(t);
-  const double kf = t - magic;
-  double r = fma_(-kf, C.ln2_hi, x);
-  r = fma_(-kf, C.ln2_lo, r);
+  const double kf = o.sub(t, magic);
+  double r = o.fma(-kf, C.ln2_hi, x);
+  r = o.fma(-kf, C.ln2_lo, r);
   double p = C.expp[EXP_DEG];
 #pragma unroll
-  for (int n = EXP_DEG - 1; n >= 0; --n) p = fma_(p, r, C.expp[n]);
+  for (int n = EXP_DEG - 1; n >= 0; --n) p = o.fma(p, r, C.expp[n]);
   return mk64(hi32(p) + (k << 20), lo32(p));
 }
+
+// the policy-free names used by the kernels of round 1 (same operations, same bits)
+NE_HD double rcp(double x) { OpsPlain o; return rcp(o, x); }
+NE_HD double div(double a, double b) { OpsPlain o; return div(o, a, b); }
+NE_HD double sqrt_pos(double x) { OpsPlain o; return sqrt_pos(o, x); }
+NE_HD double cbrt_pos(const MathConsts& C, double x) { OpsPlain o; return cbrt_pos(o, C, x); }
+NE_HD double log_pos(const double* __restrict__ tab, const MathConsts& C, double x) { OpsPlain o; return log_pos(o, tab, C, x); }
+NE_HD double exp_mid(const MathConsts& C, double x) { OpsPlain o; return exp_mid(o, C, x); }
 
 // ---- ψ table lookup --------------------------------------------------------------------------------
 // record index of ζ (branch-free); `outside` is set when |ζ| ≥ 2^7 or ζ is NaN (closed forms then)
@@ -231,41 +283,53 @@ NE_HD bool psi_is_tiny(double zeta) {
 }
 
 // Horner split into even and odd parts (two half-length dependency chains per polynomial)
+template <int DEG, class O>
+NE_HD double poly_eo(O& o, const double* __restrict__ c, int stride, double w, double w2) {
+  constexpr int TE = DEG & ~1, TO = (DEG & 1) ? DEG : DEG - 1;   // top even / odd degree
+  double e = c[TE * stride], od = c[TO * stride];
+#pragma unroll
+  for (int k = TE - 2; k >= 0; k -= 2) e = o.fma(e, w2, c[k * stride]);
+#pragma unroll
+  for (int k = TO - 2; k >= 1; k -= 2) od = o.fma(od, w2, c[k * stride]);
+  return o.fma(od, w, e);
+}
 template <int DEG>
 NE_HD double poly_eo(const double* __restrict__ c, int stride, double w, double w2) {
-  constexpr int TE = DEG & ~1, TO = (DEG & 1) ? DEG : DEG - 1;   // top even / odd degree
-  double e = c[TE * stride], o = c[TO * stride];
-#pragma unroll
-  for (int k = TE - 2; k >= 0; k -= 2) e = fma_(e, w2, c[k * stride]);
-#pragma unroll
-  for (int k = TO - 2; k >= 1; k -= 2) o = fma_(o, w2, c[k * stride]);
-  return fma_(o, w, e);
+  OpsPlain o; return poly_eo<DEG>(o, c, stride, w, w2);
 }
 
 // both ψ_m and ψ_s at the same |ζ| from interval record `rec`
-NE_HD void psi_pair(const double* __restrict__ rec, double az, double& pm, double& ps) {
-  const double w = fma_(az, rec[0], rec[1]);
-  const double w2 = w * w;
-  pm = poly_eo<PSI_DEG>(rec + 2, 2, w, w2);
-  ps = poly_eo<PSI_DEG>(rec + 3, 2, w, w2);
+template <class O> NE_HD void psi_pair(O& o, const double* __restrict__ rec, double az, double& pm, double& ps) {
+  const double w = o.fma(az, rec[0], rec[1]);
+  const double w2 = o.mul(w, w);
+  pm = poly_eo<PSI_DEG>(o, rec + 2, 2, w, w2);
+  ps = poly_eo<PSI_DEG>(o, rec + 3, 2, w, w2);
 }
+NE_HD void psi_pair(const double* __restrict__ rec, double az, double& pm, double& ps) { OpsPlain o; psi_pair(o, rec, az, pm, ps); }
 // one of the two (which = 0: ψ_m, 1: ψ_s): same operations as psi_pair, so the same bits
-NE_HD double psi_single(const double* __restrict__ rec, double az, int which) {
-  const double w = fma_(az, rec[0], rec[1]);
-  return poly_eo<PSI_DEG>(rec + 2 + which, 2, w, w * w);
+template <class O> NE_HD double psi_single(O& o, const double* __restrict__ rec, double az, int which) {
+  const double w = o.fma(az, rec[0], rec[1]);
+  return poly_eo<PSI_DEG>(o, rec + 2 + which, 2, w, o.mul(w, w));
 }
+NE_HD double psi_single(const double* __restrict__ rec, double az, int which) { OpsPlain o; return psi_single(o, rec, az, which); }
 // ψ_m(|ζ_u|) and ψ_s(|ζ_s|) for |ζ| < 2^TINY_EXP, both on the side (record) `rec`
+template <class O> NE_HD void psi_tiny_pair(O& o, const double* __restrict__ rec, double azu, double azs, double& pm, double& ps) {
+  const double wu = o.fma(azu, rec[0], rec[1]), ws = o.fma(azs, rec[0], rec[1]);
+  pm = poly_eo<TINY_DEG>(o, rec + 2, 2, wu, o.mul(wu, wu));
+  ps = poly_eo<TINY_DEG>(o, rec + 3, 2, ws, o.mul(ws, ws));
+}
 NE_HD void psi_tiny_pair(const double* __restrict__ rec, double azu, double azs, double& pm, double& ps) {
-  const double wu = fma_(azu, rec[0], rec[1]), ws = fma_(azs, rec[0], rec[1]);
-  pm = poly_eo<TINY_DEG>(rec + 2, 2, wu, wu * wu);
-  ps = poly_eo<TINY_DEG>(rec + 3, 2, ws, ws * ws);
+  OpsPlain o; psi_tiny_pair(o, rec, azu, azs, pm, ps);
 }
 
 // the same for |ζ| < 2^MICRO_EXP with the degree-MICRO_DEG records
+template <class O> NE_HD void psi_micro_pair(O& o, const double* __restrict__ rec, double azu, double azs, double& pm, double& ps) {
+  const double wu = o.fma(azu, rec[0], rec[1]), ws = o.fma(azs, rec[0], rec[1]);
+  pm = poly_eo<MICRO_DEG>(o, rec + 2, 2, wu, o.mul(wu, wu));
+  ps = poly_eo<MICRO_DEG>(o, rec + 3, 2, ws, o.mul(ws, ws));
+}
 NE_HD void psi_micro_pair(const double* __restrict__ rec, double azu, double azs, double& pm, double& ps) {
-  const double wu = fma_(azu, rec[0], rec[1]), ws = fma_(azs, rec[0], rec[1]);
-  pm = poly_eo<MICRO_DEG>(rec + 2, 2, wu, wu * wu);
-  ps = poly_eo<MICRO_DEG>(rec + 3, 2, ws, ws * ws);
+  OpsPlain o; psi_micro_pair(o, rec, azu, azs, pm, ps);
 }
 
 }  // namespace fm

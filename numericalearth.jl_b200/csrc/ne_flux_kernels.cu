@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <deque>
 #include <mutex>
 #include <vector>
 
@@ -35,6 +36,10 @@ namespace ne {
 template <class FT, class CT, class VT> int launch_ao(const NeAtmosOceanDesc& d, cudaStream_t stream);
 template <class FT, class CT, class VT> int launch_asi(const NeAtmosSeaIceDesc& d, cudaStream_t stream);
 template <class FT, class CT, class VT> int launch_al(const NeAtmosLandDesc& d, cudaStream_t stream);
+// round-2 a–o solve of the default tree (ne_flux_tab2.cu)
+bool tab2_eligible(const NeAtmosOceanDesc& d, const TabParams& TP);
+int launch_tab2(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P, const TabParams& TP, const double* tab,
+                cudaStream_t s, unsigned long long* counts);
 
 // ---- atmosphere–ocean kernel, default plugin tree (Float64), see ne_flux_fast.cuh --------------------
 template <class CT, int MINB>
@@ -342,8 +347,8 @@ ao_fused_tab_kernel(const __grid_constant__ NeInterpDesc atm, const __grid_const
 // Device-resident solver tables, built once per (device, ψ parameter set) and kept for the life of the
 // process (14 KB each).  The first call for a parameter set allocates and copies synchronously, so it
 // must happen outside CUDA-graph capture; later calls only enqueue the kernel.
-struct SolverTableKey {
-  NeStabilityProfile psi_momentum, psi_temperature;
+struct SolverTableKey {   // everything build_solver_tables reads
+  NeStabilityProfile psi_momentum, psi_temperature, psi_water_vapor;
   double gustiness_parameter, minimum_gustiness;
   int64_t f32;
 };
@@ -355,7 +360,7 @@ struct SolverTables {
   double fit_error;
 };
 static std::mutex g_tab_mutex;
-static std::vector<SolverTables> g_tabs;
+static std::deque<SolverTables> g_tabs;   // a deque never moves its elements: the returned pointers stay valid
 
 static const SolverTables* solver_tables(const NeFluxFormulation& f, bool f32 = false) {
   int dev = 0;
@@ -364,6 +369,7 @@ static const SolverTables* solver_tables(const NeFluxFormulation& f, bool f32 = 
   std::memset(&key, 0, sizeof(key));
   std::memcpy(&key.psi_momentum, &f.psi_momentum, sizeof(NeStabilityProfile));
   std::memcpy(&key.psi_temperature, &f.psi_temperature, sizeof(NeStabilityProfile));
+  std::memcpy(&key.psi_water_vapor, &f.psi_water_vapor, sizeof(NeStabilityProfile));
   key.gustiness_parameter = f.subgrid_velocities.gustiness_parameter;
   key.minimum_gustiness = f.subgrid_velocities.minimum_gustiness;
   key.f32 = f32 ? 1 : 0;
@@ -506,6 +512,8 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
         TabParams TP = tabs->T;
         TP.far_fm = !TP.general_psi && far_unstable_fm_ok(P);
         TP.log_hd = std::log(d->surface_layer_height.value - P.d_zero);
+        // the strict default tree with scalar heights: the round-2 kernel (NE_B200_TAB_V1=1 keeps the round-1 one)
+        if (!ext && tab2_eligible(*d, TP)) return launch_tab2(*d, L, P, TP, tabs->dptr, s, nullptr);
 #define NE_LAUNCH_TAB3(MB, HS, EXT)                                                                                          \
   do {                                                                                                                  \
     if (ct64) ao_flux_tab_kernel<double, MB, HS, EXT><<<tb, 256, 0, s>>>(*d, L, Thermo<double>::make(d->thermo), P, TP, tabs->dptr); \
@@ -697,9 +705,43 @@ static int al_entry(const NeAtmosLandDesc* d, void* stream) {
   return v64 ? launch_al<float, float, double>(*d, s) : launch_al<float, float, float>(*d, s);
 }
 
+// FP64 instructions one launch of the shipped a–o solve executes on this descriptor (the OpsCount instantiation of
+// the same kernel source: thread-level fma / mul / add counts, library-code estimate, thread trips, warp trips).
+static int count_solve_ops(const NeAtmosOceanDesc* d, uint64_t* out, void* stream) {
+  int rc = validate_ao(d, true);
+  if (rc != NE_OK) return rc;
+  NE_REQUIRE(out != nullptr, "null output");
+  if (!fast_path_eligible(d->flux, d->properties, d->thermo) || !tab_path_eligible(d->flux) || !strict_default_options(d->flux))
+    NE_NO_VARIANT("operation counting covers the default plugin tree only");
+  const SolverTables* tabs = solver_tables(d->flux);
+  NE_REQUIRE(tabs != nullptr, "solver tables unavailable");
+  Layout L = make_layout(d->grid);
+  FastParams P = make_fast_params(d->flux, d->gravitational_acceleration);
+  TabParams TP = tabs->T;
+  TP.far_fm = !TP.general_psi && far_unstable_fm_ok(P);
+  TP.log_hd = std::log(d->surface_layer_height.value - P.d_zero);
+  if (!tab2_eligible(*d, TP)) NE_NO_VARIANT("operation counting needs the round-2 solve kernel (scalar heights, < 2^31 points)");
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long* dev = nullptr;
+  cudaError_t e = cudaMalloc(&dev, 8 * sizeof(unsigned long long));
+  if (e != cudaSuccess) return cuda_error(e, "ne_count_solve_ops: cudaMalloc");
+  cudaMemsetAsync(dev, 0, 8 * sizeof(unsigned long long), s);
+  rc = launch_tab2(*d, L, P, TP, tabs->dptr, s, dev);
+  if (rc == NE_OK) {
+    unsigned long long host[8];
+    e = cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = cuda_error(e, "ne_count_solve_ops");
+    else for (int k = 0; k < 8; ++k) out[k] = host[k];
+  }
+  cudaFree(dev);
+  return rc;
+}
+
 }  // namespace ne
 
 extern "C" {
+int ne_count_solve_ops_f64(const NeAtmosOceanDesc* d, uint64_t* out, void* stream) { return ne::count_solve_ops(d, out, stream); }
 int ne_atmosphere_land_fluxes_f64(const NeAtmosLandDesc* d, void* stream) { return ne::al_entry<double>(d, stream); }
 int ne_atmosphere_land_fluxes_f32(const NeAtmosLandDesc* d, void* stream) { return ne::al_entry<float>(d, stream); }
 int ne_atmosphere_ocean_fluxes_f64(const NeAtmosOceanDesc* d, void* stream) { return ne::ao_entry<double>(d, stream); }

@@ -482,7 +482,8 @@ __device__ __forceinline__ void tab_iteration(const FastParams& P, const FrontF3
   const float bstar = __fmul_rn(s.gTv, __fadd_rn(__fmul_rn(s.theta_star, s.c1), __fmul_rn(s.c2, s.q_star)));
   const float Jb = -__fmul_rn(s.ustar, bstar);
   const float Jp = Jb > 0.0f ? Jb : 0.0f;
-  const float ug = __fmul_rn(Q.beta, cbrtf(__fmul_rn(Jp, s.h_bl)));
+  const float Jh = __fmul_rn(Jp, s.h_bl);   // cbrt: correctly rounded Float32 (evaluated in Float64, rounded once; see ne_common.cuh)
+  const float ug = __fmul_rn(Q.beta, Jh > 0.0f ? (float)fm::cbrt_pos(T.mc, (double)Jh) : 0.0f);
   const float UG = Q.gmin < ug ? ug : Q.gmin;
   const float U = sqrtf(__fadd_rn(s.dudv2, __fmul_rn(UG, UG)));
   const float u2 = __fmul_rn(s.ustar, s.ustar);

@@ -1,0 +1,353 @@
+// ne_flux_tab2.cuh — round-2 form of the table-driven a–o solve (default plugin tree, Float64 model).
+//
+// Same fixed point, stopping rule and trip counts as ne_flux_tab.cuh (compute_interface_state.jl:5-58,
+// similarity_theory_turbulent_fluxes.jl:315-385); what changes is the SHAPE of the code the hardware sees
+// (profiles/r01_ncu_full_v10_summary.txt: FP64 pipe 55 %, issue 62 %, shared-memory wavefronts 61 %, lane
+// efficiency 25.6/32, `wait` the largest stall):
+//
+//   * one straight-line basic block per trip: the ψ(Δh/L★) pair and the |ζ| < 2^-12 ψ(ℓ/L★) pair are ALWAYS
+//     evaluated from (clamped) table records and the rare cases (|ζ| ≥ 2^7, ℓ/L★ outside the micro records)
+//     overwrite the result afterwards — the scheduler can interleave the cbrt → sqrt chain of the gustiness,
+//     the two logs, the exp and the four Horner chains instead of running them block after block;
+//   * every FP64 operation goes through an ops policy (ne_fastmath.cuh): the OpsCount instantiation of the same
+//     source counts the FP64 instructions a launch executes (bench.py's roofline numerator, no profiler);
+//   * prologue and epilogue (once per point) use the branch-free reciprocal / log / exp instead of IEEE division
+//     and libdevice powf / expf (~650 → ~350 instructions per point); a Float32 q_sat (Float32 thermodynamics:
+//     interface_states.jl:56-59) is evaluated as Float32(pow_Float64) · Float32(exp_Float64), i.e. correctly
+//     rounded Float32 functions, which is what Julia's Float32 `^` is (Base.Math.pow_body widens to Float64)
+//     and what every other kernel and the oracle do (ne_common.cuh m_pow / m_exp);
+//   * points are dealt to warps in the order of the PREVIOUS step's trip counts (ne_flux_tab2.cu:
+//     trip_order_kernel), so the 32 lanes of a warp leave the loop together.
+#pragma once
+
+#include "ne_flux_tab.cuh"
+
+namespace ne {
+
+#if defined(__CUDACC__)
+
+namespace fm {
+template <class O> __device__ __forceinline__ double atan_large(O& o, double x) {   // x ≥ 6: |error| ≲ 1 ulp of π/2
+  const double y = rcp(o, x), y2 = o.mul(y, y);
+  double p = -1.0 / 19.0;
+  p = o.fma(p, y2, 1.0 / 17.0);
+  p = o.fma(p, y2, -1.0 / 15.0);
+  p = o.fma(p, y2, 1.0 / 13.0);
+  p = o.fma(p, y2, -1.0 / 11.0);
+  p = o.fma(p, y2, 1.0 / 9.0);
+  p = o.fma(p, y2, -1.0 / 7.0);
+  p = o.fma(p, y2, 1.0 / 5.0);
+  p = o.fma(p, y2, -1.0 / 3.0);
+  p = o.fma(p, y2, 1.0);
+  return o.fma(-y, p, 1.5707963267948966);
+}
+}  // namespace fm
+
+// ---- rare ψ paths -----------------------------------------------------------------------------------------
+// Edson unstable closed forms for ζ ≤ −2^7 (similarity_theory_turbulent_fluxes.jl:501-532, 586-618), B⁻ = 2
+template <class O>
+__device__ __forceinline__ void tab2_psi_far_unstable(O& o, const FastParams& P, const TabParams& T, const double* tab,
+                                                      double z, double& pm, double& ps) {
+  const double z2 = o.mul(z, z);
+  const double fw = o.sub(1.0, fm::rcp(o, o.add(1.0, z2)));                      // ζ²/(1 + ζ²)
+  {  // momentum
+    const double f1 = fm::sqrt_pos(o, fm::sqrt_pos(o, o.fma(-P.m_Am, z, 1.0)));
+    const double f1s = o.mul(f1, f1), f1p = o.add(1.0, f1);
+    const double arg = o.mul(o.mul(o.mul(f1p, f1p), o.add(1.0, f1s)), 0.125);
+    const double psi1 = o.add(o.fma(-2.0, fm::atan_large(o, f1), fm::log_pos(o, tab, T.mc, arg)), P.m_Cm);
+    const double f2 = fm::cbrt_pos(o, T.mc, o.fma(-P.m_Dm, z, 1.0));
+    const double l2 = fm::log_pos(o, tab, T.mc, o.mul(o.fma(f2, f2, o.add(1.0, f2)), P.m_iEm));
+    const double a2 = fm::atan_large(o, o.mul(o.fma(2.0, f2, 1.0), P.m_irEm));
+    const double psi2 = o.add(o.fma(-P.m_rEm, a2, o.mul(P.m_halfEm, l2)), P.m_Fm);
+    pm = o.fma(fw, o.sub(psi2, psi1), psi1);
+  }
+  {  // scalar
+    const double f1 = fm::sqrt_pos(o, o.fma(-P.s_Am, z, 1.0));
+    const double psi1 = o.fma(P.s_Bm, fm::log_pos(o, tab, T.mc, o.mul(o.add(1.0, f1), P.s_iBm)), P.s_Cm);
+    const double f2 = fm::cbrt_pos(o, T.mc, o.fma(-P.s_Dm, z, 1.0));
+    const double l2 = fm::log_pos(o, tab, T.mc, o.mul(o.fma(f2, f2, o.add(1.0, f2)), P.s_iEm));
+    const double a2 = fm::atan_large(o, o.mul(o.fma(2.0, f2, 1.0), P.s_irEm));
+    const double psi2 = o.add(o.fma(-P.s_rEm, a2, o.mul(P.s_halfEm, l2)), P.s_Fm);
+    ps = o.fma(fw, o.sub(psi2, psi1), psi1);
+  }
+}
+
+// stable closed forms (ζ ≥ 2^7: the tables cover the rest) with the branch-free exp / sqrt (:519-531, 605-617)
+template <class O>
+__device__ __forceinline__ void tab2_psi_stable(O& o, const FastParams& P, const TabParams& T, double z, double& pm, double& ps) {
+  const double em = fm::exp_mid(o, T.mc, -fm::dmin(P.m_zmax, o.mul(P.m_Ap, z)));
+  const double es = T.same_exp ? em : fm::exp_mid(o, T.mc, -fm::dmin(P.s_zmax, o.mul(P.s_Ap, z)));
+  pm = o.sub(o.fma(-o.mul(P.m_Cp, o.sub(z, P.m_Dp)), em, -o.mul(P.m_Bp, z)), P.m_CpDp);
+  const double x = o.fma(P.s_Bp, z, 1.0);
+  double xp;
+  if (P.s_C15) xp = o.mul(x, fm::sqrt_pos(o, x));
+  else { xp = pow_general(x, P.s_Cp); o.other(60); }
+  ps = o.sub(o.fma(-o.mul(P.s_Bp, o.sub(z, P.s_Dp)), es, -xp), P.s_Ep);
+}
+
+// Out of line, own policy object (an ops reference would force the caller's counters into local memory); the
+// counting instantiation adds its operations to the launch's global counters itself.
+template <class O>
+static __device__ __noinline__ double2 tab2_psi_outside(const FastParams& P, const TabParams& T, const double* tab, double z,
+                                                        unsigned long long* counts) {
+  O o;
+  double pm, ps;
+  if (z > 0) tab2_psi_stable(o, P, T, z, pm, ps);
+  else if (T.far_fm) tab2_psi_far_unstable(o, P, T, tab, z, pm, ps);
+  else { psi_far_unstable(P, z, pm, ps); o.other(700); }
+  o.flush(counts);
+  return make_double2(pm, ps);
+}
+
+// ψ_m(ζ_u), ψ_s(ζ_s) when ℓ/L★ leaves the micro records (the first trips, while u★ is still near its 1e-4 guess)
+template <class O>
+static __device__ __noinline__ double2 tab2_psi_small(const FastParams& P, const TabParams& T, const double* tab, double zu,
+                                                      double zs, double Linv, unsigned long long* counts) {
+  O o;
+  double pm, ps;
+  if (fm::psi_is_tiny(zu) && fm::psi_is_tiny(zs)) {
+    fm::psi_tiny_pair(o, tab + fm::TAB_TINY + (Linv < 0 ? 0 : fm::TINY_REC), fabs(zu), fabs(zs), pm, ps);
+  } else {
+    bool outside;
+    int iv = fm::psi_interval(zu, outside);
+    if (!outside) pm = fm::psi_single(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(zu), 0);
+    else pm = tab2_psi_outside<O>(P, T, tab, zu, counts).x;
+    iv = fm::psi_interval(zs, outside);
+    if (!outside) ps = fm::psi_single(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(zs), 1);
+    else ps = tab2_psi_outside<O>(P, T, tab, zs, counts).y;
+  }
+  o.flush(counts);
+  return make_double2(pm, ps);
+}
+
+// ---- one trip of iterate_interface_state (compute_interface_state.jl:69-122 + similarity_theory…:315-385) ---
+template <class O>
+__device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const TabParams& T, const double* tab, FastPoint& s,
+                                               unsigned long long* counts) {
+  using fm::dmax;
+  using fm::dmin;
+  // b★, gustiness, U (similarity_theory…:354-358, 417-425)
+  const double bstar = o.mul(s.gTv, o.fma(s.theta_star, s.c1, o.mul(s.c2, s.q_star)));
+  const double Jb = -o.mul(s.ustar, bstar);
+  const double UG = dmax(P.gmin, o.mul(P.beta, fm::cbrt_pos(o, T.mc, dmax(o.mul(dmax(0.0, Jb), s.h_bl), T.cbrt_floor))));
+  const double U = fm::sqrt_pos(o, o.fma(UG, UG, s.dudv2));
+  // roughness lengths (roughness_lengths.jl:197-246) and 1/L★
+  const double ru = fm::rcp(o, s.ustar);
+  const double lu = dmin(o.fma(o.mul(P.a1, s.ustar), s.ustar, o.mul(P.a2, ru)), P.lmax);
+  const double Linv = o.mul(o.mul(o.mul(P.kappa, bstar), ru), ru);   // 0 when b★ == 0, i.e. L★ = Inf (:372)
+  const double log_lu = fm::log_pos(o, tab, T.mc, lu);
+  const double Rs = o.mul(o.mul(lu, s.ustar), P.nu_inv);
+  const double log_Rs = fm::log_pos(o, tab, T.mc, Rs);
+  const double log_ls_un = o.fma(-P.rb, log_Rs, P.log_rA);
+  const bool clipped = log_ls_un > P.log_ls_max;
+  const double log_ls = clipped ? P.log_ls_max : log_ls_un;
+  const double ls_un = fm::exp_mid(o, T.mc, dmax(log_ls_un, -700.0));
+  const double ls = clipped ? P.ls_max : ls_un;
+  const double lu2 = o.add(lu, lu);
+  const bool lifted = lu2 > s.hd;                                    // Δh = max(Δh − d, 2ℓu) (:313)
+  const double dh = lifted ? lu2 : s.hd;
+  const double log_dh = lifted ? o.add(T.mc.ln2, log_lu) : s.log_hd;
+  // ψ(Δh/L★): always from the (clamped) record; |ζ| ≥ 2^7 overwrites below
+  const double zh = o.mul(dh, Linv);
+  bool outside;
+  const int iv = fm::psi_interval(zh, outside);
+  double pm_h, ps_h;
+  fm::psi_pair(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(zh), pm_h, ps_h);
+  // ψ(ℓ/L★): always from the |ζ| < 2^-12 record of the side of L★
+  const double zu = o.mul(lu, Linv), zs = o.mul(ls, Linv);
+  double pm_l, ps_l;
+  fm::psi_micro_pair(o, tab + fm::TAB_MICRO + (Linv < 0 ? 0 : fm::MICRO_REC), fabs(zu), fabs(zs), pm_l, ps_l);
+  if (outside) {
+    const double2 r = tab2_psi_outside<O>(P, T, tab, zh, counts);
+    pm_h = r.x; ps_h = r.y;
+  }
+  if (!(fm::psi_is_micro(zu) && fm::psi_is_micro(zs))) {
+    const double2 r = tab2_psi_small<O>(P, T, tab, zu, zs, Linv, counts);
+    pm_l = r.x; ps_l = r.y;
+  }
+  // Π = log(Δh/ℓ) − ψ(Δh/L★) + ψ(ℓ/L★), χ = ϰ/Π (:242-247, 375-377)
+  const double Pi_u = o.add(o.sub(o.sub(log_dh, log_lu), pm_h), pm_l);
+  const double Pi_s = o.add(o.sub(o.sub(log_dh, log_ls), ps_h), ps_l);
+  const double r = fm::rcp(o, o.mul(Pi_u, Pi_s));
+  const double ru_ = o.mul(Pi_s, r), rs_ = o.mul(Pi_u, r);           // 1/Π_u, 1/Π_s
+  double chi_u = o.mul(P.kappa, ru_), chi_s = o.mul(P.kappa, rs_);
+  chi_u = o.fma(o.fma(-Pi_u, chi_u, P.kappa), ru_, chi_u);
+  chi_s = o.fma(o.fma(-Pi_s, chi_s, P.kappa), rs_, chi_s);
+  s.ustar = o.mul(chi_u, U);
+  s.theta_star = o.mul(chi_s, s.dtheta);
+  s.q_star = o.mul(chi_s, s.dq);
+}
+
+// compute_interface_state.jl:10-18: the first trip always runs; then until drift < tol or it ≥ maxiter
+template <class O>
+__device__ __forceinline__ int tab2_solve(O& o, const FastParams& P, const TabParams& T, const double* tab, FastPoint& s,
+                                          unsigned long long* counts) {
+  if (P.fixed && P.maxiter <= 0) return 0;
+  const double tol = P.fixed ? -1.0 : P.tol;
+  const int maxiter = P.maxiter;
+  int it = 0;
+  double drift;
+  do {
+    const double pu = s.ustar, pt = s.theta_star, pq = s.q_star;
+    tab2_iteration(o, P, T, tab, s, counts);
+    drift = o.add(o.add(fabs(o.sub(s.ustar, pu)), fabs(o.sub(s.theta_star, pt))), fabs(o.sub(s.q_star, pq)));
+    ++it;
+    o.trip();
+  } while (!(drift < tol) && it < maxiter);
+  return it;
+}
+
+// ---- once per point: q_sat and the iteration invariants ---------------------------------------------------
+// Float32 functions of a Float32 thermodynamics, correctly rounded through Float64 (see the header comment)
+template <class O>
+__device__ __forceinline__ float tab2_powf(O& o, const TabParams& T, const double* tab, float x, float y) {
+  return (float)fm::exp_mid(o, T.mc, o.mul((double)y, fm::log_pos(o, tab, T.mc, (double)x)));
+}
+
+template <class O>
+__device__ __forceinline__ double tab2_psat(O& o, const Thermo<float>& th, const TabParams& T, const double* tab, int phase, double Ts) {
+  const float Tf = (float)Ts;
+  const int ph = phase == NE_PHASE_LIQUID ? 0 : 1;
+  const float x = __fdiv_rn(Tf, th.T_triple);
+  const float a = __fmul_rn(th.psat_exp[ph], __fsub_rn(th.inv_T_triple, __fdiv_rn(1.0f, Tf)));
+  const float pw = tab2_powf(o, T, tab, x, th.psat_pow[ph]);
+  const float ex = (float)fm::exp_mid(o, T.mc, (double)a);
+  return (double)__fmul_rn(__fmul_rn(th.press_triple, pw), ex);
+}
+template <class O>
+__device__ __forceinline__ double tab2_psat(O& o, const Thermo<double>& th, const TabParams& T, const double* tab, int phase, double Ts) {
+  const int ph = phase == NE_PHASE_LIQUID ? 0 : 1;
+  const double x = o.mul(Ts, th.inv_T_triple);
+  const double a = o.mul(th.psat_exp[ph], o.sub(th.inv_T_triple, fm::rcp(o, Ts)));
+  const double pw = fm::exp_mid(o, T.mc, o.mul(th.psat_pow[ph], fm::log_pos(o, tab, T.mc, x)));
+  return o.mul(o.mul(th.press_triple, pw), fm::exp_mid(o, T.mc, a));
+}
+
+// surface_specific_humidity (interface_states.jl:55-74) for Float64 exchange fields
+template <class O, class CT>
+__device__ __forceinline__ double tab2_surface_humidity(O& o, const NeInterfaceProperties& ip, const Thermo<CT>& th,
+                                                        const TabParams& T, const double* tab, double p_at, double Ts, double Ss) {
+  const CT p = (CT)p_at;
+  // the branch-free log/exp want a positive, finite argument; anything else (it would be a NaN in the reference
+  // as well) goes through the library functions
+  if (!(Ts > 150.0 && Ts < 400.0 && p > (CT)0)) { o.other(400); return surface_specific_humidity<double, CT>(ip, th, p_at, Ts, Ss); }
+  const double psat = tab2_psat(o, th, T, tab, ip.phase, Ts);
+  double pv;
+  if (ip.x_h2o_kind == NE_XH2O_ONE) pv = psat;
+  else if (ip.x_h2o_kind == NE_XH2O_CONSTANT) pv = o.mul(ip.x_h2o, psat);
+  else { pv = water_mole_fraction<double>(ip, Ss) * psat; o.other(40); }
+  const double lim = (double)((CT)0.999 * p);
+  pv = lim < pv ? lim : pv;
+  const double num = o.mul((double)th.eps_inv, pv);
+  const double den = o.fma(-(double)((CT)1 - th.eps_inv), pv, (double)p);
+  return fm::div(o, num, den);
+}
+
+template <class O, class CT, bool HS, bool FMPRO>
+__device__ __forceinline__ void tab2_prologue(O& o, const NeAtmosOceanDesc& d, const Layout& L, const Thermo<CT>& th,
+                                              const FastParams& P, const TabParams& T, const double* tab, int64_t idx,
+                                              bool celsius, bool relative, FastPoint& s) {
+  const double au = __ldg((const double*)d.ua + idx), av = __ldg((const double*)d.va + idx);
+  const double aT = __ldg((const double*)d.Ta + idx), ap = __ldg((const double*)d.pa + idx), aq = __ldg((const double*)d.qa + idx);
+  const double az = HS ? d.surface_layer_height.value : slot_at<double>(d.surface_layer_height, idx);
+  double du = au, dv = av;
+  if (relative) {
+    du -= d.uo.ptr ? (slot_at<double>(d.uo, idx) + slot_at<double>(d.uo, idx + 1)) / 2 : d.uo.value;
+    dv -= d.vo.ptr ? (slot_at<double>(d.vo, idx) + slot_at<double>(d.vo, idx + L.sx)) / 2 : d.vo.value;
+  }
+  double To = slot_at<double>(d.To, idx);
+  if (celsius) To = To + 273.15;
+  s.h_bl = HS ? d.boundary_layer_height.value : slot_at<double>(d.boundary_layer_height, idx);
+  s.hd = az - P.d_zero;
+  if (FMPRO) {
+    const double qs = tab2_surface_humidity(o, d.properties, th, T, tab, ap, To, slot_at<double>(d.So, idx));
+    const double Rm = o.fma((double)th.R_v, qs, o.mul((double)th.R_d, o.sub(1.0, qs)));     // R_d(1 − q) + R_v q
+    const double Tv = fm::div(o, o.mul(To, Rm), (double)th.R_d);                          // virtual_temperature
+    s.gTv = fm::div(o, P.g, Tv);
+    s.c1 = o.fma((double)th.delta, qs, 1.0);
+    s.c2 = o.mul((double)th.delta, Tv);
+    s.dudv2 = o.fma(du, du, o.mul(dv, dv));
+    s.log_hd = HS ? T.log_hd : fm::log_pos(o, tab, T.mc, s.hd);
+    const double cpm = o.fma((double)th.cp_v, aq, o.mul((double)th.cp_d, o.sub(1.0, aq)));
+    s.dtheta = o.sub(o.add(aT, fm::div(o, o.mul(P.g, az), cpm)), To);                      // θₐ − Tₛ (interface_states.jl:308-317)
+    s.dq = o.sub(aq, qs);
+  } else {
+    const double qs = surface_specific_humidity<double, CT>(d.properties, th, ap, To, slot_at<double>(d.So, idx));
+    const double Tv = th.virtual_temperature(To, qs);
+    s.gTv = P.g / Tv;
+    s.c1 = 1 + th.delta * qs;
+    s.c2 = th.delta * Tv;
+    s.dudv2 = du * du + dv * dv;
+    s.log_hd = HS ? T.log_hd : log(s.hd);
+    s.dtheta = (aT + P.g * az / th.cp_m(aq)) - To;
+    s.dq = aq - qs;
+    o.other(300);
+  }
+  s.ustar = s.theta_star = s.q_star = 1e-4;   // atmosphere_ocean_fluxes.jl:131-137
+}
+
+// flux epilogue + stores (atmosphere_ocean_fluxes.jl:160-196); the atmosphere state is re-read (L2 hits) instead
+// of being kept live across the solve
+template <class O, class CT, bool FMPRO>
+__device__ __forceinline__ void tab2_epilogue(O& o, const NeAtmosOceanDesc& d, const Layout& L, const Thermo<CT>& th,
+                                              int64_t idx, bool celsius, bool relative, bool not_water, double ustar,
+                                              double theta_star, double q_star, int iters) {
+  AtmosState<double> a;
+  a.u = __ldg((const double*)d.ua + idx);
+  a.v = __ldg((const double*)d.va + idx);
+  a.T = __ldg((const double*)d.Ta + idx);
+  a.p = __ldg((const double*)d.pa + idx);
+  a.q = __ldg((const double*)d.qa + idx);
+  a.z = 0; a.h_bl = 0;
+  double du = a.u, dv = a.v, Ts;
+  if (not_water) {  // zero_interface_state (interface_states.jl:800-803): Δu = uₐ − 0
+    ustar = 0; theta_star = 0; q_star = 0; Ts = 273.15;
+  } else {
+    if (relative) {
+      du -= d.uo.ptr ? (slot_at<double>(d.uo, idx) + slot_at<double>(d.uo, idx + 1)) / 2 : d.uo.value;
+      dv -= d.vo.ptr ? (slot_at<double>(d.vo, idx) + slot_at<double>(d.vo, idx + L.sx)) / 2 : d.vo.value;
+    }
+    Ts = slot_at<double>(d.To, idx);
+    if (celsius) Ts = Ts + 273.15;
+  }
+  double Qv, Qc, Jv, tx, ty;
+  if (FMPRO && a.T > 150.0 && a.p > 0.0) {
+    const double dU2 = o.fma(du, du, o.mul(dv, dv));
+    double taux = 0, tauy = 0;
+    if (dU2 > 1e-290) {                                               // τ = −u★² Δu/ΔU with the RESOLVED ΔU (:166-170)
+      const double m = -o.mul(o.mul(ustar, ustar), fm::rcp(o, fm::sqrt_pos(o, dU2)));
+      taux = o.mul(m, du); tauy = o.mul(m, dv);
+    } else if (dU2 != 0.0) {
+      const double dU = sqrt(dU2);
+      taux = -(ustar * ustar) * du / dU; tauy = -(ustar * ustar) * dv / dU;
+    }
+    const double Rm = o.fma((double)th.R_v, a.q, o.mul((double)th.R_d, o.sub(1.0, a.q)));
+    const double rho = fm::div(o, a.p, o.mul(Rm, a.T));                // air_density
+    const double cpm = o.fma((double)th.cp_v, a.q, o.mul((double)th.cp_d, o.sub(1.0, a.q)));
+    const double Lv = o.fma((double)(th.cp_v - th.cp_l), o.sub(a.T, (double)th.T_0), (double)th.LH_v0);
+    const double ru = o.mul(-rho, ustar);
+    Qv = o.mul(o.mul(ru, Lv), q_star);
+    Qc = o.mul(o.mul(ru, cpm), theta_star);
+    Jv = o.mul(ru, q_star);
+    tx = o.mul(rho, taux);
+    ty = o.mul(rho, tauy);
+  } else {
+    FluxEpilogue<double, CT> e(th, a, ustar, theta_star, q_star, du, dv, false);
+    Qv = e.Qv; Qc = e.Qc; Jv = e.Jv; tx = e.tx; ty = e.ty;
+    o.other(150);
+  }
+  ((double*)d.latent_heat)[idx] = Qv;
+  ((double*)d.sensible_heat)[idx] = Qc;
+  ((double*)d.water_vapor)[idx] = Jv;
+  ((double*)d.x_momentum)[idx] = tx;
+  ((double*)d.y_momentum)[idx] = ty;
+  ((double*)d.interface_temperature)[idx] = celsius ? Ts - 273.15 : Ts;
+  ((double*)d.friction_velocity)[idx] = ustar;
+  ((double*)d.temperature_scale)[idx] = theta_star;
+  ((double*)d.water_vapor_scale)[idx] = q_star;
+  if (d.iterations) d.iterations[idx] = iters;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace ne

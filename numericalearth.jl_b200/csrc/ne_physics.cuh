@@ -24,6 +24,9 @@ namespace ne {
 template <class CT>
 struct Thermo {
   CT R_d, R_v, eps, eps_inv, delta, cp_d, cp_v, cp_l, cp_i, LH_v0, LH_s0, T_0, T_triple, press_triple;
+  // constants of saturation_vapor_pressure per phase (0 liquid, 1 ice), formed once on the host in CT arithmetic in the
+  // order the formula applies them: Δcp/R_v, (ℒ₀ − Δcp T₀)/R_v, 1/T_triple
+  CT psat_pow[2], psat_exp[2], inv_T_triple;
 
   static Thermo make(const NeThermoParams& p) {  // host: derived constants in CT arithmetic (:73-78, 256)
     Thermo t;
@@ -37,6 +40,14 @@ struct Thermo {
     t.cp_v = (CT)p.cp_v; t.cp_l = (CT)p.cp_l; t.cp_i = (CT)p.cp_i;
     t.LH_v0 = (CT)p.LH_v0; t.LH_s0 = (CT)p.LH_s0; t.T_0 = (CT)p.T_0;
     t.T_triple = (CT)p.T_triple; t.press_triple = (CT)p.press_triple;
+    const CT dcp[2] = {(CT)(t.cp_v - t.cp_l), (CT)(t.cp_v - t.cp_i)}, LH[2] = {t.LH_v0, t.LH_s0};
+    for (int ph = 0; ph < 2; ++ph) {
+      volatile CT prod = dcp[ph] * t.T_0;       // volatile: separately rounded whatever the host compiler's contraction mode
+      volatile CT diff = LH[ph] - prod;
+      t.psat_pow[ph] = dcp[ph] / t.R_v;
+      t.psat_exp[ph] = diff / t.R_v;
+    }
+    t.inv_T_triple = 1 / t.T_triple;
     return t;
   }
 

@@ -231,7 +231,7 @@ class ComponentInterfaces:
                  gravitational_acceleration=9.80665, inactive=None, with_iterations=False, atmosphere_correction=None,
                  land: Optional[PrescribedLand] = None, slab_land: Optional[SlabLandState] = None,
                  atmosphere_land_fluxes=None, atmosphere_land_interface_specific_humidity=None,
-                 atmosphere_land_velocity_difference=None):
+                 atmosphere_land_velocity_difference=None, barotropic_potential=False, two_color_radiation=False):
         self.grid, self.backend = grid, backend
         self.land = land
         self.slab_land = slab_land
@@ -316,6 +316,13 @@ class ComponentInterfaces:
             self.sio_fluxes = _Fields(frazil_heat=Z(), interface_heat=Z(), salt=Z(), freshwater=Z(), x_momentum=Z(), y_momentum=Z())
             self.sio_temperature, self.sio_salinity = Z(), Z()
             self.net_sea_ice = _Fields(top_heat=Z(), top_snowfall=Z(), top_u=Z(), top_v=Z(), bottom_heat=Z())
+        # barotropic forcing of the ocean free surface (interpolate_atmospheric_state.jl:80-85): potential .= p / rho_ocean
+        self.barotropic_potential = Z() if barotropic_potential else None
+        # TwoColorRadiation.surface_flux (Oceans/radiative_forcing.jl:84-91): the penetrating shortwave leaves JT
+        self.two_color_surface_flux = Z() if two_color_radiation else None
+        # FreezingLimitedOceanTemperature.frazil_heat (SeaIces/freezing_limited_ocean_temperature.jl:73-118): the
+        # OceanOnlyModel default "sea ice"; allocated by the first step that passes an ocean column
+        self.frazil_heat = None
         self._keep = []   # device copies of node arrays etc.
 
     # ---- one-time: fractional indices (prescribed_atmosphere_regridder.jl:41-71) ---------------------
@@ -393,6 +400,9 @@ class ComponentInterfaces:
             for k, s in enumerate(series):
                 d.series[f][k].data = _ptr(b, s)
             d.out[f] = b.ptr(out)
+        if self.barotropic_potential is not None:   # :80-85, from the interpolated pressure (field 4)
+            d.potential, d.potential_from = b.ptr(self.barotropic_potential), 4
+            d.ocean_reference_density = float(self.ocean_properties.reference_density)
         if g.rotation is not None:   # intrinsic_vector (interpolate_atmospheric_state.jl:123-126)
             if not hasattr(self, "_rotation_dev"):
                 npd = np.float64 if g.FT == "f64" else np.float32
@@ -650,9 +660,13 @@ class ComponentInterfaces:
         d.grid = g.pod(False)
         d.nz, d.hz = nz, hz
         d.T, d.S, d.dz, d.dt = b.ptr(T3), b.ptr(S3), b.ptr(dz), dt
-        ff = self.sio_formulation
-        if ff is None:
+        ff = self.sio_formulation if self.has_sea_ice else None
+        if ff is None:   # FreezingLimitedOceanTemperature: the frazil clamp only (freezing_limited_ocean_temperature.jl:73-118)
             d.formulation = A.NE_SIO_FREEZE_ONLY
+            if not self.has_sea_ice:
+                if self.frazil_heat is None:
+                    self.frazil_heat = b.zeros(g.shape, g.FT)
+                d.frazil_heat = b.ptr(self.frazil_heat)
         else:
             if isinstance(ff, F.IceBathHeatFlux):
                 d.formulation = A.NE_SIO_ICE_BATH
@@ -685,6 +699,14 @@ class ComponentInterfaces:
                 b.ptr(f.frazil_heat), b.ptr(f.interface_heat), b.ptr(f.salt), b.ptr(f.freshwater)
             d.interface_temperature, d.interface_salinity = b.ptr(self.sio_temperature), b.ptr(self.sio_salinity)
         return d
+
+    def compute_sea_ice_ocean_fluxes(self, ocean_column):
+        """compute_sea_ice_ocean_fluxes!(model) (sea_ice_ocean_fluxes.jl:20-77) with a sea-ice model; without one the
+        OceanOnlyModel default FreezingLimitedOceanTemperature (freezing_limited_ocean_temperature.jl:73-93): clamp the
+        T column to the liquidus and store the frazil heat.  ocean_column = (T3, S3, dz, dt, nz, hz); None: no 3-D ocean
+        state was handed over (surface-only callers), nothing to do."""
+        if ocean_column is not None:
+            self.lib.call("sea_ice_ocean_fluxes", self.grid.FT, self.sea_ice_ocean_desc(*ocean_column), self.backend.stream())
 
     # ---- phase 3: net fluxes ----------------------------------------------------------------------------
     def assemble_ocean_desc(self) -> A.NeAssembleOceanDesc:
@@ -753,6 +775,8 @@ class ComponentInterfaces:
             d.medium = self.ocean_properties.pod()
             d.heat_flux = b.ptr(self.net_ocean.T)
             r = self.rad_fluxes_ocean
+            if self.two_color_surface_flux is not None:
+                d.two_color, d.two_color_surface_flux = 1, b.ptr(self.two_color_surface_flux)
         d.upwelling_longwave, d.downwelling_longwave, d.downwelling_shortwave = \
             b.ptr(r.upwelling_longwave), b.ptr(r.downwelling_longwave), b.ptr(r.downwelling_shortwave)
         return d
@@ -795,8 +819,7 @@ class ComponentInterfaces:
         self.compute_atmosphere_ocean_fluxes()
         self.compute_atmosphere_sea_ice_fluxes()
         self.compute_atmosphere_land_fluxes()
-        if ocean_column is not None and self.has_sea_ice:
-            self.lib.call("sea_ice_ocean_fluxes", self.grid.FT, self.sea_ice_ocean_desc(*ocean_column), self.backend.stream())
+        self.compute_sea_ice_ocean_fluxes(ocean_column)
         self.update_net_fluxes()
         self.apply_air_sea_radiative_fluxes()
         self.apply_air_sea_ice_radiative_fluxes()
@@ -818,9 +841,11 @@ class ComponentInterfaces:
             d.apply_radiation = self.apply_radiation_desc(False)
         return d
 
-    def fused_interface_step(self, t, diagnostics=None):
+    def fused_interface_step(self, t, diagnostics=None, ocean_column=None):
         """Interpolation -> a–o solve -> net ocean flux assembly -> radiation (-> diagnostics sums) for an
-        OceanOnlyModel, one C-ABI call."""
+        OceanOnlyModel, one C-ABI call.  `ocean_column` (T3, S3, dz, dt, nz, hz): the FreezingLimitedOceanTemperature clamp
+        of the 3-D ocean temperature runs behind it (it only touches the column and frazil_heat, which nothing else in the
+        step reads: its place in phase 2 or after phase 4 makes no difference)."""
         self.clock_time = t
         if self.atmosphere_correction is not None:   # phase 1.5 sits between the phases the fused call merges
             d, s, FT = self.fused_step_desc(t), self.backend.stream(), self.grid.FT
@@ -832,10 +857,12 @@ class ComponentInterfaces:
                 self.lib.call("apply_radiative_fluxes", FT, d.apply_radiation, s)
             if diagnostics is not None:
                 diagnostics.reduce()
+            self.compute_sea_ice_ocean_fluxes(ocean_column)
             return
         if self.land is not None:   # the runoff interpolation is independent of everything else in phase 1
             self.lib.call("interp_state", self.grid.FT, self.land_interp_desc(t), self.backend.stream())
         self.lib.call("fused_interface_step", self.grid.FT, self.fused_step_desc(t, diagnostics), self.backend.stream())
         self.release_windows()
+        self.compute_sea_ice_ocean_fluxes(ocean_column)
         if diagnostics is not None:
             diagnostics.all_reduce()

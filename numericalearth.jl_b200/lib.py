@@ -56,6 +56,7 @@ class Library:
             self.dll.ne_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
             self.dll.ne_stream_synchronize.argtypes = [C.c_void_p]
             self.dll.ne_measure_fp64_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+            self.dll.ne_count_solve_ops_f64.argtypes = [C.POINTER(A.NeAtmosOceanDesc), C.POINTER(C.c_uint64), C.c_void_p]
             self.dll.ne_host_pipeline_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
             self.dll.ne_host_pipeline_destroy.argtypes = [C.c_void_p]
             self.dll.ne_series_ring_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(A.NeSeriesRingDesc)]
@@ -86,6 +87,20 @@ class Library:
 
     def device_count(self):
         return self.dll.ne_device_count()
+
+    def count_solve_ops(self, desc, stream=0):
+        """FP64 instructions one launch of the a–o solve executes on `desc` (ne_count_solve_ops_f64): dict of thread-level
+        counts.  Synchronises."""
+        out = (C.c_uint64 * 8)()
+        rc = self.dll.ne_count_solve_ops_f64(C.byref(desc), out, C.c_void_p(stream))
+        if rc != 0:
+            if rc == A.NE_E_NO_VARIANT:
+                from .formulations import NoKernelVariantError
+                raise NoKernelVariantError(self.last_error())
+            raise NeError(rc, self.last_error())
+        fma, mul, add, other, trips, wtrips = (int(out[k]) for k in range(6))
+        return {"dfma": fma, "dmul": mul, "dadd": add, "library_code_estimate": other, "thread_trips": trips,
+                "warp_trips": wtrips, "flop": 2 * fma + mul + add}
 
     def measure_fp64_peak(self):
         tf, mhz = C.c_double(0), C.c_double(0)

@@ -54,13 +54,19 @@ class HostPipelinedStep:
 
     def _set_time(self, t):
         ci = self.ci
+        # clock-dependent surface properties (TabulatedAlbedo: seconds in the day, solar declination) are host scalars
+        # inside the radiation PODs: refresh them every step, as fused_interface_step does by rebuilding its descriptor
+        ci.clock_time = t
+        if ci.radiation is not None:
+            self.desc.step.ao.radiation = ci._surface_radiation("ocean")
+            self.desc.step.apply_radiation.radiation = ci._surface_radiation("ocean")
         for d, src in ((self.desc.step.atmosphere, ci.atmosphere), (self.desc.step.radiation, ci.radiation)):
             if src is None:
                 continue
             ti = ci._time_interp(src, t)
             d.time.frac, d.time.m1, d.time.m2, d.time.same = ti.frac, ti.m1, ti.m2, ti.same
 
-    def step(self, t, host_ocean):
+    def step(self, t, host_ocean, ocean_column=None):
         """host_ocean: dict of pinned host arrays (torch CPU tensors or numpy) named T, S, u, v with the exchange
         layout.  Enqueues everything on the current stream (+ the pipeline's copy stream) and returns without
         synchronising."""
@@ -78,6 +84,7 @@ class HostPipelinedStep:
                 raise NoKernelVariantError(self.lib.last_error())
             raise RuntimeError(self.lib.last_error())
         self.ci.release_windows()
+        self.ci.compute_sea_ice_ocean_fluxes(ocean_column)   # FreezingLimitedOceanTemperature clamp (device-resident column)
         if self.diagnostics is not None:
             self.diagnostics.all_reduce()
 

