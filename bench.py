@@ -28,12 +28,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0 prints exactly ONE line on stdout: keep NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NE_BENCH_KEEP_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = "WARN"
-
-# ... and whatever a library still writes to file descriptor 1 (NCCL prints its version banner there on some
-# boxes regardless) goes to stderr: the JSON line is written to a private duplicate of the original stdout
+# rank 0 prints exactly ONE line on stdout.  NCCL_DEBUG is left as the caller set it (INFO shows the communicator's
+# nranks / NVLS lines): whatever a library writes to file descriptor 1 (NCCL's log and version banner) is sent to
+# stderr, and the JSON line is written to a private duplicate of the original stdout
 _REAL_STDOUT = os.fdopen(os.dup(1), "w")
 os.dup2(2, 1)
 
@@ -53,17 +50,17 @@ F_EPI = 150.0
 BYTES_INTERP_ATM = 2 * 4 + 7 * 8      # 2 Float32 fractional indices in, 7 Float64 fields out
 BYTES_INTERP_RAD = 2 * 4 + 2 * 8
 DT_STEP = 1200.0
-# One `ncu --set full` capture of this workload (C4, 1 GPU, f64 grid, f32 atmosphere), per launch:
-# profiles/r01_ncu_full_v8_summary.txt (the solve kernel is the one of r01_ncu_full_v3_summary.csv; re-captured).  DRAM traffic = dram__bytes_read.sum + dram__bytes_write.sum; the executed view
-# of the solve = thread-level DFMA/DMUL/DADD counts (DFMA = 2 flop) over the ncu duration, next to the algorithmic
-# (as-written census) figure of `roofline.achieved`, which the table-driven kernel under-executes by ~8x.
-NCU_C4 = {
-    "ao_traffic_bytes": 467.7e6 + 510.1e6,
-    "interp_traffic_bytes": 67.8e6 + 348.7e6,
-    "ao_executed": {"tflops": 11.8, "frac_of_measured_dfma_peak": 0.35, "fp64_pipe_active": 0.553,
-                    "issue_slots_active": 0.624, "lane_efficiency": 0.80, "flop_per_launch": 1.984e10,
-                    "source": "profiles/r01_ncu_full_v10_summary.txt + profiles/r01_notes.md"},
-}
+
+
+def ncu_traffic(key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of one committed `ncu --set full` capture of
+    this workload, or None when no capture of this configuration is on file (profiles/ncu_traffic.json names its source)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(key)
+    except (OSError, ValueError):
+        return None
 
 
 def parse():
@@ -84,6 +81,8 @@ def parse():
     p.add_argument("--no-extras", action="store_true", help="skip the one-number measurements of the other BASELINE configs")
     p.add_argument("--sync-allreduce", action="store_true", help="diagnostics all-reduce on the compute stream (not overlapped)")
     p.add_argument("--no-rebalance", action="store_true", help="keep the mask-based bands (no re-balancing from measured trip counts)")
+    p.add_argument("--sustained-seconds", type=float, default=1.0, help="second timed region of at least this length (0: skip)")
+    p.add_argument("--no-parity", action="store_true", help="skip the oracle parity check on the cpu_baseline sample")
     return p.parse_args()
 
 
@@ -193,6 +192,57 @@ def run_cpu(args, seconds_per_step=1.5, steps=None, warmup=1):
     return {"value": pts * n / total, "unit": "points/s", "cores": int(threads), "kind": "port",
             "sample": f"{args.config} subsampled in latitude to {nx}x{ny} ({pts} launch points/step), {n} steps, "
                       f"OpenMP oracle, {threads} threads", "ms_per_step": 1e3 * total / n, "points_per_step": pts}
+
+
+def parity_on_sample(args, backend, sample_ny):
+    """The oracle as the checker: the cpu_baseline sample (the workload subsampled in latitude) through the CUDA path and
+    through the oracle, compared point by point.  |a - b| <= tol * max(|b|, 1e-6 max|b|), tol = 1e-10 (Float64) / 1e-5
+    (Float32); fields: the nine a-o outputs, the six net ocean fluxes, the three radiative fluxes."""
+    import ne_b200
+    import oracle
+    from numericalearth_jl_b200 import synthetic
+    cfg = dict(synthetic.CONFIGS[args.config])
+    cfg["ny"] = int(sample_ny)
+    t = 0.37 * 10800.0
+    ref = synthetic.build_case(cfg, ne_b200.NumpyHostBackend(), FT=args.dtype, atm_FT=args.atm_dtype, lib=oracle.load(), with_iterations=True)
+    dev = synthetic.build_case(cfg, backend, FT=args.dtype, atm_FT=args.atm_dtype, with_iterations=True)
+    ref.initialize(); dev.initialize()
+    ref.update_state(t)
+    dev.fused_interface_step(t)
+    dev.fused_interface_step(t)          # the second step runs in trip-count order
+    backend.synchronize()
+    g = ref.grid
+    tol = 1e-10 if args.dtype == "f64" else 1e-5
+    it_r = g.interior(ref.ao_iterations).astype(np.int64)
+    it_d = g.interior(backend.to_numpy(dev.ao_iterations)).astype(np.int64)
+    maxiter = 100
+    ok = (it_r < maxiter) & (it_d < maxiter)
+    worst, exceed, fields = 0.0, 0, {}
+    bags = [("ao_fluxes", True), ("net_ocean", False), ("rad_fluxes_ocean", False)]
+    for bag, ring in bags:
+        for n in getattr(ref, bag).names():
+            a, b = backend.to_numpy(getattr(getattr(dev, bag), n)), getattr(getattr(ref, bag), n)
+            if ring:
+                a, b, m = g.interior(a), g.interior(b), ok
+            else:
+                sl = (slice(g.hy, g.hy + g.ny), slice(g.hx, g.hx + g.nx))
+                a, b, m = a[sl], b[sl], ok[1:-1, 1:-1]
+            a, b = a.astype(np.float64)[m], b.astype(np.float64)[m]
+            scale = float(np.max(np.abs(b))) or 1.0
+            r = np.abs(a - b) / np.maximum(np.abs(b), 1e-6 * scale)
+            fields[f"{bag}.{n}"] = float(r.max())
+            worst = max(worst, float(r.max()))
+            exceed += int((r > tol).sum())
+    interp_exact = all(np.array_equal(g.interior(backend.to_numpy(getattr(dev.atmos_state, n))), g.interior(getattr(ref.atmos_state, n)))
+                       for n in ref.atmos_state.names())
+    solved = it_r > 0
+    return {"checker": "oracle (C++ restatement of the reference; Julia absent)", "sample": f"{args.config} subsampled in latitude to {g.nx}x{g.ny}",
+            "criterion": "|a-b| <= tol*max(|b|, 1e-6*max|b|)", "tol": tol, "max_pointwise_rel": worst, "points_above_tol": exceed,
+            "per_field_max_pointwise_rel": fields, "interpolation_bit_exact": bool(interp_exact),
+            "trip_count_mismatch_rate": float((it_r != it_d)[solved].mean()) if solved.any() else 0.0,
+            "trip_count_max_abs_diff": int(np.abs(it_r - it_d).max()),
+            "maxiter_points": {"oracle": int((it_r >= maxiter).sum()), "device": int((it_d >= maxiter).sum())},
+            "solved_points": int(solved.sum())}
 
 
 def reference_arm(args):
@@ -321,10 +371,20 @@ def b200_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = global_points / (ms_per_step * 1e-3)
+    # a second, long timed region: the K-step figure above is a ~40 ms burst at boost clock, this one is >= 1 s
+    sustained = None
+    if args.sustained_seconds > 0:
+        n_long = int(max(args.steps, min(5000, np.ceil(args.sustained_seconds * 1e3 / max(ms_per_step, 1e-3)))))
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        ms_long = timed(step, n_long)
+        c2 = sampler2.stop() if rank == 0 else None
+        sustained = {"steps": n_long, "ms_per_step": ms_long / n_long, "value": global_points / (ms_long / n_long * 1e-3),
+                     "seconds": ms_long * 1e-3, "clocks": c2}
 
     # ---- per-kernel timings for the rooflines (same inputs, kernel timed alone on the launch stream) ---
-    ao_desc = ci.atmosphere_ocean_desc()
-    ao_desc.iterations = None
+    ao_desc = ci.atmosphere_ocean_desc()     # as the step calls it (iterations array included: trip-count ordered launch)
     atm_desc, rad_desc = fused.atmosphere, fused.radiation
     reps = max(5, min(args.steps, 20))
     ms_ao = timed(lambda: lib.call("atmosphere_ocean_fluxes", args.dtype, ao_desc, stream), reps) / reps
@@ -350,7 +410,17 @@ def b200_arm(args):
     flops_local = iters_sum * F_ITER + float(active.sum()) * F_EPI
     fp64_peak, _ = lib.measure_fp64_peak()
     peaks, peak_src = load_peaks()
-    achieved_tf = flops_local / (ms_ao * 1e-3) / 1e12
+    algorithmic_tf = flops_local / (ms_ao * 1e-3) / 1e12
+    # executed FP64 work of ONE launch of the solve on this rank's band, counted by the counting instantiation of the
+    # same kernel source (ne_count_solve_ops_f64; no profiler): thread-level DFMA (2 flop), DMUL, DADD
+    counts = None
+    if args.dtype == "f64":
+        try:
+            cd = ci.atmosphere_ocean_desc()     # with the iterations array: the launch runs in trip-count order, as in the step
+            counts = lib.count_solve_ops(cd, stream)
+        except Exception as e:   # noqa: BLE001
+            counts = {"error": repr(e)[:200]}
+    executed_tf = counts["flop"] / (ms_ao * 1e-3) / 1e12 if counts and "flop" in counts else None
     wbytes = 8 if args.dtype == "f64" else 4
     ibytes = 4 if args.atm_dtype == "f32" else 8
     interp_bytes = local_points * (2 * ibytes + 7 * wbytes)
@@ -379,16 +449,86 @@ def b200_arm(args):
     e2e_value = global_points / (ms_e2e * 1e-3)
     torch.cuda.synchronize()
     diag_values = [float(x) for x in result_host.tolist()]
+    # round trip: the same step, and the six net ocean fluxes come back to pinned host memory band by band behind the
+    # kernels (the result an ocean model on the host needs), next to the 7 diagnostics sums
+    net = ci.net_ocean
+    back = {n: (getattr(net, n), torch.empty(getattr(net, n).shape, dtype=getattr(net, n).dtype).pin_memory()) for n in net.names()}
+    pipe_rt = ne_b200.HostPipelinedStep(ci, n_chunks=args.e2e_chunks, diagnostics=diag, return_fields=back)
+    d2h_rt = pipe_rt.d2h_bytes_per_step() + d2h
+
+    def e2e_rt_step():
+        pipe_rt.step(state["t"], pinned)
+        result_host.copy_(diag.result, non_blocking=True)
+        state["t"] += DT_STEP
+
+    for _ in range(2):
+        e2e_rt_step()
+    ms_e2e_rt = timed(e2e_rt_step, args.steps) / args.steps
+    torch.cuda.synchronize()
+    rt_ok = bool(torch.equal(back["T"][1], net.T.cpu()))
 
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = run_cpu(args, seconds_per_step=args.cpu_seconds / 6.0, steps=5, warmup=1)
         cpu = {"value": r["value"], "unit": "points/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        if not args.no_parity:
+            try:
+                parity = parity_on_sample(args, backend, r["sample_ny"])
+            except Exception as e:   # noqa: BLE001
+                parity = {"error": repr(e)[:300]}
 
     # ---- the other BASELINE configurations, one number each (N = 1 only; never allowed to break the headline line) ----
     extras = None
+    if not args.no_extras and args.config != "C5":
+        # BASELINE config 5 (1/48 degree) in both precisions at THIS GPU count: each rank builds its own latitude band
+        # (band-local random surface state: only the throughput matters here), fused step incl. diagnostics + all-reduce
+        c5 = {}
+        for ft in ("f64", "f32"):
+            try:
+                c5cfg = synthetic.CONFIGS["C5"]
+                # equal rows: the band-local mask below is ~30 % inactive in every band, so the bands cost the same
+                g5 = sharding.band_grid(c5cfg["nx"], c5cfg["ny"], c5cfg["latitude"], rank, world, FT=ft)
+                ci5 = synthetic.build_case("C5", backend, FT=ft, atm_FT=args.atm_dtype, grid=g5, with_iterations=True, local_surface=True)
+                ci5.initialize()
+                f5 = ci5.ao_fluxes
+                dg5 = sharding.FluxDiagnostics(ci5, [f5.latent_heat, f5.sensible_heat, f5.water_vapor, f5.x_momentum, f5.y_momentum,
+                                                     ci5.net_ocean.T, ci5.net_ocean.eta])
+                fd5 = ci5.fused_step_desc(0.37 * 10800.0, diagnostics=dg5)
+
+                def step5():
+                    dg5.flip(fd5)
+                    lib.call("fused_interface_step", ft, fd5, stream)
+                    dg5.all_reduce(async_op=not args.sync_allreduce)
+
+                for _ in range(3):
+                    step5()
+                dg5.wait()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                e0.record()
+                for _ in range(8):
+                    step5()
+                dg5.wait()
+                e1.record()
+                barrier()
+                ms5 = e0.elapsed_time(e1) / 8
+                if world > 1:
+                    t5 = torch.tensor([ms5], device=backend.device, dtype=torch.float64)
+                    dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+                    ms5 = float(t5.item())
+                pts5 = (c5cfg["nx"] + 2) * (c5cfg["ny"] + 2)
+                c5[f"C5_{ft}"] = {"ms_per_step": ms5, "points_per_s": pts5 / (ms5 * 1e-3), "n_gpus": world, "steps": 8,
+                                  "points_per_step": pts5}
+                del ci5, dg5, fd5, f5
+                torch.cuda.empty_cache()
+            except Exception as e:   # noqa: BLE001
+                c5[f"C5_{ft}"] = {"error": repr(e)[:200]}
+        extras = dict(c5)
+        extras["C5_note"] = ("BASELINE config 5, 17280x6720, device-resident fused step incl. diagnostics, latitude bands balanced by "
+                             "active-point count, max over ranks; band-local random surface state")
     if rank == 0 and world == 1 and not args.no_extras:
-        extras = {}
+        extras = extras or {}
         try:
             other = "f32" if args.dtype == "f64" else "f64"
             c2 = synthetic.build_case(args.config, backend, FT=other, atm_FT=args.atm_dtype)
@@ -413,39 +553,56 @@ def b200_arm(args):
         except Exception as e:   # noqa: BLE001
             extras["error"] = repr(e)[:200]
 
-    ncu_applies = args.config == "C4" and world == 1 and args.dtype == "f64" and args.atm_dtype == "f32"
+    cfg_key = f"{args.config}_{args.dtype}_atm{args.atm_dtype}" if world == 1 else None
+    traffic = ncu_traffic(cfg_key) if cfg_key else None
     if rank == 0:
         n_active = int(active.sum())
+        have_counts = bool(counts) and "flop" in counts
         line = {
             "metric": "air-sea flux points/s", "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e, "api": "ne_b200.HostPipelinedStep", "chunks": int(args.e2e_chunks),
-                    "gpu_launches_per_step": int(pipe.launches_per_step())},
-            "gpu_launches": int((4 if ci.shared_frac else 5) * args.steps),
+                    "gpu_launches_per_step": int(pipe.launches_per_step()),
+                    "round_trip": {"value": global_points / (ms_e2e_rt * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e_rt,
+                                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_rt),
+                                   "returns": "the six net ocean flux fields (band by band, behind the kernels) + 7 diagnostics sums",
+                                   "host_copy_equals_device": rt_ok}},
+            "gpu_launches": int((5 if ci.shared_frac else 6) * args.steps),
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "ao_flux_tab_kernel", "achieved": achieved_tf, "peak": fp64_peak,
-                         "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak if fp64_peak else None,
-                         "traffic": NCU_C4["ao_traffic_bytes"] if ncu_applies else None,
-                         "executed": dict(NCU_C4["ao_executed"], applies_to_this_run=ncu_applies),
+            "sustained": sustained,
+            "roofline": {"bound": "fp64", "kernel": "ao_flux_tab2_kernel (+ trip_order_kernel)",
+                         "achieved": executed_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": (executed_tf / fp64_peak) if (executed_tf and fp64_peak) else None,
+                         "what": "EXECUTED thread-level FP64 flop of one launch (DFMA = 2, DMUL = DADD = 1; counted in this run by "
+                                 "the counting instantiation of the same kernel source, ne_count_solve_ops_f64) / CUDA-event time of the launch",
+                         "executed_counts": counts,
+                         "lane_efficiency": (counts["thread_trips"] / (32.0 * counts["warp_trips"])) if have_counts and counts["warp_trips"] else None,
+                         "traffic": (traffic or {}).get("ao_flux_bytes"), "traffic_source": (traffic or {}).get("source"),
                          "peak_source": "measured in this run by ne_measure_fp64_peak (DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
-                         "ms_per_launch": ms_ao, "algorithmic_flop_per_iteration": F_ITER, "algorithmic_flop_epilogue": F_EPI,
+                         "ms_per_launch": ms_ao,
+                         "algorithmic": {"achieved": algorithmic_tf, "frac_of_peak": algorithmic_tf / fp64_peak if fp64_peak else None,
+                                         "flop_per_iteration": F_ITER, "flop_epilogue": F_EPI,
+                                         "note": "as-written census of the reference's iteration (SURVEY 8(d) weights): the table-driven "
+                                                 "kernel executes ~8x fewer flops, so this is NOT a fraction of peak; side note only"},
                          "mean_iterations_active": iters_sum / max(n_active, 1), "max_iterations": int(it.max()),
                          "active_points": n_active, "points_per_launch": int(local_points)},
             "roofline_hbm": {"bound": "hbm", "kernel": "interp_staged_kernel(atmosphere)", "achieved": hbm_achieved,
                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / peaks["hbm_gbs"],
                              "peak_source": peak_src, "ms_per_launch": ms_ia,
-                             "traffic": NCU_C4["interp_traffic_bytes"] if ncu_applies else None},
+                             "traffic": (traffic or {}).get("interp_bytes")},
             "kernel_ms": {"interp_radiation": ms_ir, "interp_atmosphere": ms_ia, "atmosphere_ocean_fluxes": ms_ao,
                           "assemble_net_ocean_fluxes": ms_as, "apply_radiative_fluxes": ms_ap, "diag_reduce": ms_dg,
                           "step_with_unfused_post_solve_kernels": ms_unfused_step,
                           "note": "the step runs ONE interpolation launch (atmosphere + radiation: 9 series, shared fractional "
-                                  "indices; the two launches above are timed alone for reference), the solve, ONE post-solve kernel (assembly + radiation + "
+                                  "indices; the two launches above are timed alone for reference), the trip-order pass + the solve, ONE post-solve kernel (assembly + radiation + "
                                   "diagnostics partial sums) and the diagnostics final stage; the three post-solve "
                                   "component kernels are timed alone for reference"},
             "diagnostics": diag_values,
         }
+        if parity is not None:
+            line["parity"] = parity
         if extras:
             line["other_configs"] = extras
         if cpu is not None:

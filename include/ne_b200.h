@@ -541,6 +541,12 @@ typedef struct NeHostStepDesc {
   int32_t n_chunks;          /* latitude chunks (<= the handle's capacity)                    */
   NeHostField fields[NE_HOST_MAX_FIELDS];
   int64_t row_bytes;         /* (nx + 2 hx) * sizeof(exchange element)                        */
+  /* results back to the host (optional): the parent rows of each out_field leave device -> pinned host on a second
+   * copy stream as soon as the band that writes them is done (net ocean fluxes, radiative fluxes, ...); the compute
+   * stream is made to wait for the last of these copies, so synchronising it also means "results are on the host". */
+  int32_t n_out_fields;
+  int32_t pad_;
+  NeHostField out_fields[NE_HOST_MAX_FIELDS];
 } NeHostStepDesc;
 
 /* ---- FieldTimeSeries window on the device (ne_series_ring.cu).

@@ -281,7 +281,7 @@ class NeHostField(C.Structure):
 
 class NeHostStepDesc(C.Structure):
     _fields_ = [("step", NeFusedStepDesc), ("n_fields", i32), ("n_chunks", i32), ("fields", NeHostField * NE_HOST_MAX_FIELDS),
-                ("row_bytes", i64)]
+                ("row_bytes", i64), ("n_out_fields", i32), ("pad_", i32), ("out_fields", NeHostField * NE_HOST_MAX_FIELDS)]
 
 
 NE_RING_MAX_SERIES = 16

@@ -26,6 +26,11 @@ struct HostPipeline {
   std::vector<cudaEvent_t> landed;   // chunk c is on the device
   cudaEvent_t done;                  // the kernels of the previous step have read the device arrays
   bool first;
+  // results back to the host (NeHostStepDesc.out_fields): band c's rows leave on their own stream as soon as the
+  // post-solve kernel of band c has written them, behind the kernels of band c + 1 and the H2D copies (PCIe is full duplex)
+  cudaStream_t back;
+  std::vector<cudaEvent_t> computed;
+  cudaEvent_t drained;
 };
 
 #define NE_CUDA_TRY(expr, where)                             \
@@ -39,6 +44,9 @@ static int pipelined_step(HostPipeline* hp, const NeHostStepDesc* d, void* strea
   NE_REQUIRE(d->n_fields >= 0 && d->n_fields <= NE_HOST_MAX_FIELDS, "host pipeline: n_fields out of range");
   NE_REQUIRE(d->n_chunks >= 1 && d->n_chunks <= (int)hp->landed.size(), "host pipeline: n_chunks exceeds the handle's capacity");
   NE_REQUIRE(d->row_bytes > 0, "host pipeline: row_bytes must be positive");
+  NE_REQUIRE(d->n_out_fields >= 0 && d->n_out_fields <= NE_HOST_MAX_FIELDS, "host pipeline: n_out_fields out of range");
+  for (int f = 0; f < d->n_out_fields; ++f)
+    NE_REQUIRE(d->out_fields[f].host && d->out_fields[f].device, "host pipeline: null output field pointer");
   const NeExchangeGrid& g = d->step.ao.grid;
   NE_REQUIRE(g.ny >= 1 && g.hy >= 1, "host pipeline: needs a one-row halo");
   cudaStream_t compute = (cudaStream_t)stream;
@@ -112,12 +120,25 @@ static int pipelined_step(HostPipeline* hp, const NeHostStepDesc* d, void* strea
           if (rc) return rc;
         }
       }
+      if (d->n_out_fields > 0) {   // parent rows of the launch rows a0..a1 (the first / last band also carries the halo rows)
+        NE_CUDA_TRY(cudaEventRecord(hp->computed[c], compute), "host pipeline (record computed)");
+        NE_CUDA_TRY(cudaStreamWaitEvent(hp->back, hp->computed[c], 0), "host pipeline (wait computed)");
+        const int64_t r0 = (a0 == d->step.assemble.grid.j_lo) ? 0 : a0 + g.hy - 1;
+        const int64_t r1 = (a1 == d->step.assemble.grid.j_hi) ? rows_total : a1 + g.hy;
+        for (int f = 0; f < d->n_out_fields; ++f)
+          NE_CUDA_TRY(cudaMemcpyAsync((char*)d->out_fields[f].host + r0 * d->row_bytes, (const char*)d->out_fields[f].device + r0 * d->row_bytes,
+                                      (size_t)((r1 - r0) * d->row_bytes), cudaMemcpyDeviceToHost, hp->back), "host pipeline (D2H)");
+      }
     }
     j_next = b + 1;
   }
   if (d->step.diag.n_fields > 0) {
     rc = f64 ? ne_diag_reduce_f64(&d->step.diag, stream) : ne_diag_reduce_f32(&d->step.diag, stream);
     if (rc) return rc;
+  }
+  if (d->n_out_fields > 0) {   // whoever synchronises the compute stream also waits for the results to be on the host
+    NE_CUDA_TRY(cudaEventRecord(hp->drained, hp->back), "host pipeline (record drained)");
+    NE_CUDA_TRY(cudaStreamWaitEvent(compute, hp->drained, 0), "host pipeline (wait drained)");
   }
   NE_CUDA_TRY(cudaEventRecord(hp->done, compute), "host pipeline (record done)");
   return NE_OK;
@@ -132,19 +153,28 @@ int ne_host_pipeline_create(void** handle, int32_t max_chunks) {
   ne::HostPipeline* hp = new ne::HostPipeline();
   hp->first = true;
   hp->copy = nullptr;
+  hp->back = nullptr;
   hp->done = nullptr;
+  hp->drained = nullptr;
   cudaError_t e = cudaGetDevice(&hp->device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->copy, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp->back, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&hp->done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&hp->drained, cudaEventDisableTiming);
   for (int c = 0; c < max_chunks && e == cudaSuccess; ++c) {
     cudaEvent_t ev;
     e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e == cudaSuccess) hp->landed.push_back(ev);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) hp->computed.push_back(ev);
   }
   if (e != cudaSuccess) {
     const int rc = ne::cuda_error(e, "ne_host_pipeline_create");
     for (cudaEvent_t ev : hp->landed) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : hp->computed) cudaEventDestroy(ev);
     if (hp->done) cudaEventDestroy(hp->done);
+    if (hp->drained) cudaEventDestroy(hp->drained);
+    if (hp->back) cudaStreamDestroy(hp->back);
     if (hp->copy) cudaStreamDestroy(hp->copy);
     delete hp;
     cudaGetLastError();
@@ -158,7 +188,10 @@ int ne_host_pipeline_destroy(void* handle) {
   ne::HostPipeline* hp = (ne::HostPipeline*)handle;
   if (!hp) return NE_OK;
   for (cudaEvent_t ev : hp->landed) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : hp->computed) cudaEventDestroy(ev);
   cudaEventDestroy(hp->done);
+  cudaEventDestroy(hp->drained);
+  cudaStreamDestroy(hp->back);
   cudaStreamDestroy(hp->copy);
   delete hp;
   return NE_OK;

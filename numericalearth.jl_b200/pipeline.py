@@ -22,7 +22,10 @@ from . import abi as A
 class HostPipelinedStep:
     FIELDS = ("T", "S", "u", "v")
 
-    def __init__(self, interfaces, n_chunks=8, diagnostics=None):
+    def __init__(self, interfaces, n_chunks=8, diagnostics=None, return_fields=None):
+        """return_fields: dict name -> (device array, pinned host array) of exchange-layout results (e.g. the six net
+        ocean fluxes) copied back to the host band by band behind the kernels; synchronising the compute stream then
+        also means the results are on the host."""
         ci = self.ci = interfaces
         if not ci.backend.is_device:
             raise RuntimeError("HostPipelinedStep needs the CUDA library and device arrays (there is no CPU fallback)")
@@ -42,6 +45,13 @@ class HostPipelinedStep:
         d.n_fields, d.n_chunks, d.row_bytes = len(self.FIELDS), self.n_chunks, self.row_bytes
         for k, name in enumerate(self.FIELDS):
             d.fields[k].device = ci.backend.ptr(self.dev[name])
+        self.return_fields = dict(return_fields or {})
+        if len(self.return_fields) > A.NE_HOST_MAX_FIELDS:
+            raise ValueError(f"at most {A.NE_HOST_MAX_FIELDS} fields can be returned to the host")
+        d.n_out_fields = len(self.return_fields)
+        for k, (dev, host) in enumerate(self.return_fields.values()):
+            d.out_fields[k].device = ci.backend.ptr(dev)
+            d.out_fields[k].host = host.data_ptr() if hasattr(host, "data_ptr") else host.ctypes.data
         self._fn = getattr(self.lib.dll, "ne_host_pipelined_step_" + self.FT)
 
     def __del__(self):
@@ -91,6 +101,10 @@ class HostPipelinedStep:
     def h2d_bytes_per_step(self):
         g = self.ci.grid
         return len(self.FIELDS) * (g.ny + 2 * g.hy) * self.row_bytes
+
+    def d2h_bytes_per_step(self):
+        g = self.ci.grid
+        return len(self.return_fields) * (g.ny + 2 * g.hy) * self.row_bytes
 
     def launches_per_step(self):
         """Kernel launches of one step: 2 interpolations, (solve + post-solve) per band, 2 diagnostics stages."""

@@ -169,8 +169,10 @@ def ocean_arrays(grid: ExchangeGrid, rng, sea_ice=False):
 
 def build_case(config, backend, FT="f64", atm_FT="f64", nt=2, seed_offset=0, sea_ice=False, radiation=True,
                stretched_latitude=False, lib=None, with_iterations=False, grid=None, land=False, rotated=False,
-               **interface_kwargs):
-    """Construct a fully populated ComponentInterfaces for one BASELINE.json config on `backend`."""
+               local_surface=False, **interface_kwargs):
+    """Construct a fully populated ComponentInterfaces for one BASELINE.json config on `backend`.
+    local_surface: a latitude band draws its own surface state (seeded by its row offset) instead of slicing the global
+    one — for throughput measurements of grids whose global state would not be worth generating on every rank."""
     cfg = CONFIGS[config] if isinstance(config, str) else config
     if grid is None:
         grid = ExchangeGrid(nx=cfg["nx"], ny=cfg["ny"], hx=cfg.get("hx", 7), hy=cfg.get("hy", 7),
@@ -188,7 +190,9 @@ def build_case(config, backend, FT="f64", atm_FT="f64", nt=2, seed_offset=0, sea
                                rain=(dev["rain"],), snow=(dev["snow"],))
     rad = PrescribedRadiation(grid=src, times=times, downwelling_shortwave=dev["sw"], downwelling_longwave=dev["lw"]) \
         if radiation else None
-    if grid.ny_global is not None:   # latitude band: generate the GLOBAL surface state, keep this band's rows
+    if grid.ny_global is not None and local_surface:
+        o = ocean_arrays(grid, np.random.default_rng(BASE_SEED + seed_offset + 7919 * (1 + grid.j_offset)), sea_ice=sea_ice)
+    elif grid.ny_global is not None:   # latitude band: generate the GLOBAL surface state, keep this band's rows
         gg = ExchangeGrid(nx=grid.nx, ny=grid.ny_global, hx=grid.hx, hy=grid.hy, latitude=grid.latitude, FT=grid.FT)
         og = ocean_arrays(gg, rng, sea_ice=sea_ice)
         o = {k: np.ascontiguousarray(v[grid.j_offset:grid.j_offset + grid.ny + 2 * grid.hy, :]) for k, v in og.items()}

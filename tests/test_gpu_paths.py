@@ -219,3 +219,26 @@ def test_host_pipeline_refreshes_clock_dependent_albedo(cuda_backend, cuda_lib):
     a.fused_interface_step(0.0)
     cuda_backend.synchronize()
     assert not np.array_equal(sw0, cuda_backend.to_numpy(a.rad_fluxes_ocean.downwelling_shortwave)), "the albedo should depend on the clock"
+
+
+def test_host_pipeline_returns_results_to_host(cuda_backend, cuda_lib):
+    """NeHostStepDesc.out_fields: the net ocean fluxes leave for pinned host memory band by band behind the kernels;
+    after synchronising the compute stream the host copies equal the device arrays, and the step itself is unchanged."""
+    import torch
+    a = synthetic.build_case("C1", cuda_backend, FT="f64", atm_FT="f32")
+    b = synthetic.build_case("C1", cuda_backend, FT="f64", atm_FT="f32")
+    a.initialize(); b.initialize()
+    a.fused_interface_step(T_STEP)
+    pinned = {k: torch.from_numpy(np.ascontiguousarray(b._host_inputs["ocean"][k])).pin_memory() for k in ("T", "S", "u", "v")}
+    back = {n: (getattr(b.net_ocean, n), torch.full(getattr(b.net_ocean, n).shape, float("nan"), dtype=torch.float64).pin_memory())
+            for n in b.net_ocean.names()}
+    for n_chunks in (1, 5):
+        pipe = ne_b200.HostPipelinedStep(b, n_chunks=n_chunks, return_fields=back)
+        assert pipe.d2h_bytes_per_step() == 6 * b.ocean_state.T.numel() * 8
+        for _ in range(2):
+            pipe.step(T_STEP, pinned)
+        torch.cuda.current_stream().synchronize()       # the compute stream waits for the last D2H copy
+        for n, (dev, host) in back.items():
+            assert torch.equal(host, dev.cpu()), f"{n}: host copy differs (n_chunks={n_chunks})"
+            assert np.array_equal(cuda_backend.to_numpy(getattr(a.net_ocean, n)), host.numpy(), equal_nan=True), n
+            host.fill_(float("nan"))

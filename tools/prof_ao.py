@@ -12,7 +12,7 @@ backend = ne_b200.TorchCudaBackend("cuda:0")
 lib = ne_b200.get_library()
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C4"
 FT = sys.argv[2] if len(sys.argv) > 2 else "f64"
-ci = synthetic.build_case(cfg, backend, FT=FT, atm_FT="f32", with_iterations=False)
+ci = synthetic.build_case(cfg, backend, FT=FT, atm_FT="f32", with_iterations=True)
 ci.initialize()
 ci.interpolate_state(0.37 * 10800.0)
 d = ci.atmosphere_ocean_desc()

@@ -22,7 +22,7 @@ def main():
     backend = ne_b200.TorchCudaBackend("cuda:0")
     lib = ne_b200.get_library()
     FT = opts["--dtype"]
-    ci = synthetic.build_case(opts["--config"], backend, FT=FT, atm_FT="f32", with_iterations=False)
+    ci = synthetic.build_case(opts["--config"], backend, FT=FT, atm_FT="f32", with_iterations=True)   # iterations: the trip-count ordered launch
     ci.initialize()
     ci.interpolate_state(0.37 * 10800.0)
     d = ci.atmosphere_ocean_desc()
@@ -41,8 +41,15 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        out.append({"env": env, "ms": ms, "config": opts["--config"], "dtype": FT})
-        print(opts["--config"], FT, env, f"{ms:.3f} ms", flush=True)
+        rec = {"env": env, "ms": ms, "config": opts["--config"], "dtype": FT}
+        if FT == "f64" and "NE_B200_TAB_V1" not in env and "NE_B200_TAB2_LIBM_PROLOGUE" not in env:
+            try:
+                rec["counts"] = lib.count_solve_ops(d, stream)
+                rec["executed_tflops"] = rec["counts"]["flop"] / (ms * 1e-3) / 1e12
+            except Exception as e:   # noqa: BLE001
+                rec["counts_error"] = repr(e)[:200]
+        out.append(rec)
+        print(opts["--config"], FT, env, f"{ms:.3f} ms", rec.get("executed_tflops"), flush=True)
         for k in env:
             os.environ.pop(k, None)
     json.dump(out, open(f"gpurun_out/{opts['--out']}.json", "w"))
