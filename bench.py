@@ -191,7 +191,7 @@ def run_cpu(args, seconds_per_step=1.5, steps=None, warmup=1):
     total = float(np.sum(times))
     return {"value": pts * n / total, "unit": "points/s", "cores": int(threads), "kind": "port",
             "sample": f"{args.config} subsampled in latitude to {nx}x{ny} ({pts} launch points/step), {n} steps, "
-                      f"OpenMP oracle, {threads} threads", "ms_per_step": 1e3 * total / n, "points_per_step": pts}
+                      f"OpenMP oracle, {threads} threads", "ms_per_step": 1e3 * total / n, "points_per_step": pts, "sample_ny": ny}
 
 
 def parity_on_sample(args, backend, sample_ny):

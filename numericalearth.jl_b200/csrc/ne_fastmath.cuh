@@ -35,10 +35,26 @@ namespace fm {
 constexpr int LOG_N = 64;       // log table entries (invc, logc)
 constexpr int LOG_DEG = 6;      // log1p(r) = r + r²·P(r), P has LOG_DEG coefficients (|r| ≤ 2^-7)
 constexpr int EXP_DEG = 11;     // e^r on |r| ≤ ln2/2
-constexpr int PSI_DEG = 13;
-constexpr int PSI_OCT_LO = -6;  // table covers 2^-6 ≤ |ζ| < 2^7 on the unstable side
+// Resolution of the ψ tables.  Round 1 shipped quarter octaves with degree 13 (30 doubles per record: 15 LDS.128 per
+// lookup).  ncu (profiles/r02_ncu_tab2_v1_summary.txt) shows the L1TEX data pipe at 80-88 % of its peak — shared-memory
+// wavefronts of exactly these lookups — while FP64 and issue sit near 55 %: eighth octaves from 2^-8 with degree 9 need
+// 11 LDS.128 and 8 fewer DFMA per lookup for the same verified accuracy (3e-16; tools/fastmath_check.cu), at 44 KB
+// instead of 27 KB of shared memory per CTA.  (Quarter octaves need degree 11 from 2^-7, degree 8 misses 2e-15.)
+#ifndef NE_PSI_SUB_BITS
+#define NE_PSI_SUB_BITS 3
+#endif
+#ifndef NE_PSI_DEG
+#define NE_PSI_DEG 9
+#endif
+constexpr int PSI_DEG = NE_PSI_DEG;
+constexpr int PSI_SUB_BITS = NE_PSI_SUB_BITS;   // 2^PSI_SUB_BITS intervals per octave
+constexpr int PSI_SUB = 1 << PSI_SUB_BITS;
+#ifndef NE_PSI_OCT_LO
+#define NE_PSI_OCT_LO -8
+#endif
+constexpr int PSI_OCT_LO = NE_PSI_OCT_LO;  // table covers 2^PSI_OCT_LO ≤ |ζ| < 2^7 on each side (+ one record for [0, 2^PSI_OCT_LO))
 constexpr int PSI_OCT_HI = 7;
-constexpr int PSI_NQ = 4 * (PSI_OCT_HI - PSI_OCT_LO);  // quarter-octave intervals
+constexpr int PSI_NQ = PSI_SUB * (PSI_OCT_HI - PSI_OCT_LO);  // intervals per side above 2^PSI_OCT_LO
 constexpr int PSI_NS = PSI_NQ + 1;                     // records per side: [0, 2^-6) then the quarter octaves
 constexpr int PSI_NI = 2 * PSI_NS;                     // unstable side (ζ < 0) first, then the stable side
 constexpr int PSI_REC = 2 + 2 * (PSI_DEG + 1);         // (a, b) of w = a|ζ| + b, then (c_m, c_s) pairs
@@ -268,7 +284,7 @@ NE_HD double exp_mid(const MathConsts& C, double x) { OpsPlain o; return exp_mid
 // ---- ψ table lookup --------------------------------------------------------------------------------
 // record index of ζ (branch-free); `outside` is set when |ζ| ≥ 2^7 or ζ is NaN (closed forms then)
 NE_HD int psi_interval(double zeta, bool& outside) {
-  const int32_t q = ((hi32(zeta) & 0x7fffffff) >> 18) - ((1023 + PSI_OCT_LO) << 2);
+  const int32_t q = ((hi32(zeta) & 0x7fffffff) >> (20 - PSI_SUB_BITS)) - ((1023 + PSI_OCT_LO) << PSI_SUB_BITS);
   outside = q >= PSI_NQ;
   int32_t i = q + 1;
   i = i < 0 ? 0 : i;

@@ -39,7 +39,7 @@ template <class FT, class CT, class VT> int launch_al(const NeAtmosLandDesc& d, 
 // round-2 a–o solve of the default tree (ne_flux_tab2.cu)
 bool tab2_eligible(const NeAtmosOceanDesc& d, const TabParams& TP);
 int launch_tab2(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P, const TabParams& TP, const double* tab,
-                cudaStream_t s, unsigned long long* counts);
+                const double* host_tab, cudaStream_t s, unsigned long long* counts);
 
 // ---- atmosphere–ocean kernel, default plugin tree (Float64), see ne_flux_fast.cuh --------------------
 template <class CT, int MINB>
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256, MINB)
 ao_flux_tab_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_constant__ Layout L,
                    const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P,
                    const __grid_constant__ TabParams T, const double* __restrict__ gtab) {
-  __shared__ __align__(16) double tab[fm::TAB_SIZE];
+  extern __shared__ __align__(16) double tab[];   // fm::TAB_SIZE doubles (dynamic: see allow_table_smem)
   for (int k = threadIdx.x; k < fm::TAB_SIZE / 2; k += 256)
     reinterpret_cast<double2*>(tab)[k] = __ldg(reinterpret_cast<const double2*>(gtab) + k);
   __syncthreads();
@@ -211,7 +211,7 @@ ao_fused_tab_kernel(const __grid_constant__ NeInterpDesc atm, const __grid_const
                     const __grid_constant__ InterpSource Sa, const __grid_constant__ InterpSource Sr,
                     const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P,
                     const __grid_constant__ TabParams T, const double* __restrict__ gtab) {
-  __shared__ __align__(16) double tab[fm::TAB_SIZE];
+  extern __shared__ __align__(16) double tab[];   // fm::TAB_SIZE doubles (dynamic: see allow_table_smem)
   __shared__ double park[5][256];
   for (int k = threadIdx.x; k < fm::TAB_SIZE / 2; k += 256)
     reinterpret_cast<double2*>(tab)[k] = __ldg(reinterpret_cast<const double2*>(gtab) + k);
@@ -355,6 +355,7 @@ struct SolverTableKey {   // everything build_solver_tables reads
 struct SolverTables {
   int device;
   SolverTableKey key;
+  std::vector<double> host;   // host copy (the |ζ| < 2^-12 records also travel as kernel parameters)
   double* dptr;
   TabParams T;
   double fit_error;
@@ -380,7 +381,8 @@ static const SolverTables* solver_tables(const NeFluxFormulation& f, bool f32 = 
   t.device = dev;
   std::memcpy(&t.key, &key, sizeof(key));
   t.dptr = nullptr;
-  std::vector<double> host(fm::TAB_SIZE);
+  std::vector<double>& host = t.host;
+  host.assign(fm::TAB_SIZE, 0.0);
   t.fit_error = build_solver_tables(f, host.data(), t.T, f32);
   if (t.fit_error <= 2e-15) {   // else: ψ parameters the polynomials cannot represent → closed-form / generic kernel
     if (cudaMalloc(&t.dptr, sizeof(double) * fm::TAB_SIZE) != cudaSuccess ||
@@ -513,11 +515,11 @@ static int ao_entry(const NeAtmosOceanDesc* d, void* stream) {
         TP.far_fm = !TP.general_psi && far_unstable_fm_ok(P);
         TP.log_hd = std::log(d->surface_layer_height.value - P.d_zero);
         // the strict default tree with scalar heights: the round-2 kernel (NE_B200_TAB_V1=1 keeps the round-1 one)
-        if (!ext && tab2_eligible(*d, TP)) return launch_tab2(*d, L, P, TP, tabs->dptr, s, nullptr);
+        if (!ext && tab2_eligible(*d, TP)) return launch_tab2(*d, L, P, TP, tabs->dptr, tabs->host.data(), s, nullptr);
 #define NE_LAUNCH_TAB3(MB, HS, EXT)                                                                                          \
   do {                                                                                                                  \
-    if (ct64) ao_flux_tab_kernel<double, MB, HS, EXT><<<tb, 256, 0, s>>>(*d, L, Thermo<double>::make(d->thermo), P, TP, tabs->dptr); \
-    else ao_flux_tab_kernel<float, MB, HS, EXT><<<tb, 256, 0, s>>>(*d, L, Thermo<float>::make(d->thermo), P, TP, tabs->dptr);        \
+    if (ct64) { allow_table_smem<ao_flux_tab_kernel<double, MB, HS, EXT>>(); ao_flux_tab_kernel<double, MB, HS, EXT><<<tb, 256, TAB_SMEM_BYTES, s>>>(*d, L, Thermo<double>::make(d->thermo), P, TP, tabs->dptr); } \
+    else { allow_table_smem<ao_flux_tab_kernel<float, MB, HS, EXT>>(); ao_flux_tab_kernel<float, MB, HS, EXT><<<tb, 256, TAB_SMEM_BYTES, s>>>(*d, L, Thermo<float>::make(d->thermo), P, TP, tabs->dptr); }        \
   } while (0)
 #define NE_LAUNCH_TAB2(MB, HS)          \
   do {                                  \
@@ -612,8 +614,11 @@ int fused_interp_ao_f64(const NeInterpDesc* atm, const NeInterpDesc* rad, const 
   InterpSource Sr = Sa;
   if (has_rad) Sr = make_interp_source(*rad);
   const bool ct64 = d->thermo.dtype == NE_F64, a64 = atm->src_dtype == NE_F64, t64 = atm->time.frac_dtype == NE_F64;
-#define NE_FUSED4(CT, AT, TT, MB, HS) \
-  ao_fused_tab_kernel<CT, AT, TT, MB, HS><<<tb, 256, 0, s>>>(*atm, r, *d, L, Sa, Sr, Thermo<CT>::make(d->thermo), P, TP, tabs->dptr)
+#define NE_FUSED4(CT, AT, TT, MB, HS)                                  \
+  do {                                                                 \
+    allow_table_smem<ao_fused_tab_kernel<CT, AT, TT, MB, HS>>();        \
+    ao_fused_tab_kernel<CT, AT, TT, MB, HS><<<tb, 256, TAB_SMEM_BYTES, s>>>(*atm, r, *d, L, Sa, Sr, Thermo<CT>::make(d->thermo), P, TP, tabs->dptr); \
+  } while (0)
 #define NE_FUSED3(CT, AT, TT)                     \
   do {                                            \
     if (hs) NE_FUSED4(CT, AT, TT, 3, true);       \
@@ -726,7 +731,7 @@ static int count_solve_ops(const NeAtmosOceanDesc* d, uint64_t* out, void* strea
   cudaError_t e = cudaMalloc(&dev, 8 * sizeof(unsigned long long));
   if (e != cudaSuccess) return cuda_error(e, "ne_count_solve_ops: cudaMalloc");
   cudaMemsetAsync(dev, 0, 8 * sizeof(unsigned long long), s);
-  rc = launch_tab2(*d, L, P, TP, tabs->dptr, s, dev);
+  rc = launch_tab2(*d, L, P, TP, tabs->dptr, tabs->host.data(), s, dev);
   if (rc == NE_OK) {
     unsigned long long host[8];
     e = cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, s);

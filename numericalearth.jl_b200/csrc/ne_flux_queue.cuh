@@ -192,7 +192,7 @@ flux_queue_kernel(const __grid_constant__ typename Problem::Params p, const doub
   using FT = typename Problem::FT;
   using Point = typename Problem::Point;
   constexpr int NS = Problem::NSTATE;
-  __shared__ __align__(16) double tab[fm::TAB_SIZE];
+  extern __shared__ __align__(16) double tab[];       // fm::TAB_SIZE doubles (dynamic: see allow_table_smem)
   __shared__ int32_t f_idx[NWARPS][QRING];          // fresh points: only the point index
   __shared__ int32_t d_idx[NWARPS][QRING];          // deferred points: index, trips so far, iterate
   __shared__ int32_t d_it[NWARPS][QRING];

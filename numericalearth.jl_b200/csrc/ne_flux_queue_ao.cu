@@ -42,7 +42,8 @@ static int launch_queue_hs(const NeAtmosOceanDesc& d, const TabParams& T, const 
   uint32_t* counters = queue_counters();
   NE_REQUIRE(counters != nullptr, "atmosphere-ocean: could not allocate the work-queue counters");
   const unsigned grid = queue_grid((int64_t)prm.L.ni * prm.L.nj, 8, 3);
-  flux_queue_kernel<Problem, 8, 3><<<grid, 256, 0, s>>>(prm, tab, queue_theta(), counters);
+  if (cudaError_t e = allow_table_smem<flux_queue_kernel<Problem, 8, 3>>(); e != cudaSuccess) return cuda_error(e, "work-queue kernel (shared memory opt-in)");
+  flux_queue_kernel<Problem, 8, 3><<<grid, 256, TAB_SMEM_BYTES, s>>>(prm, tab, queue_theta(), counters);
   NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(queue)");
   return NE_OK;
 }

@@ -21,7 +21,8 @@ static int launch_asi_queue_hs(const NeAtmosSeaIceDesc& d, const TabParams& T, c
   uint32_t* counters = queue_counters();
   NE_REQUIRE(counters != nullptr, "atmosphere-sea-ice: could not allocate the work-queue counters");
   const unsigned grid = queue_grid((int64_t)prm.L.ni * prm.L.nj, 4, 4);
-  flux_queue_kernel<Problem, 4, 4><<<grid, 128, 0, s>>>(prm, tab, queue_theta(), counters);
+  if (cudaError_t e = allow_table_smem<flux_queue_kernel<Problem, 4, 4>>(); e != cudaSuccess) return cuda_error(e, "work-queue kernel (shared memory opt-in)");
+  flux_queue_kernel<Problem, 4, 4><<<grid, 128, TAB_SMEM_BYTES, s>>>(prm, tab, queue_theta(), counters);
   NE_CUDA_CHECK_LAUNCH("ne_atmosphere_sea_ice_fluxes(queue)");
   return NE_OK;
 }

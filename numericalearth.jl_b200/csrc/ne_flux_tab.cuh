@@ -161,8 +161,8 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
     const int r = stable ? iv - PSI_NS : iv;
     if (r == 0) { lo = 0; hi = ldexpl(1, PSI_OCT_LO); }
     else {
-      const int q = r - 1, e = PSI_OCT_LO + (q >> 2), s = q & 3;
-      lo = ldexpl(1 + s / 4.0L, e); hi = ldexpl(1 + (s + 1) / 4.0L, e);
+      const int q = r - 1, e = PSI_OCT_LO + (q >> PSI_SUB_BITS), s = q & (PSI_SUB - 1);
+      lo = ldexpl(1 + s / (long double)PSI_SUB, e); hi = ldexpl(1 + (s + 1) / (long double)PSI_SUB, e);
     }
     double* rec = tab + TAB_PSI + iv * PSI_REC;
     const long double half = (hi - lo) / 2, mid = (hi + lo) / 2;

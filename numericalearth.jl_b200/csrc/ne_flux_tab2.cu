@@ -25,21 +25,24 @@
 
 namespace ne {
 
-constexpr int TAB2_WINDOW = 1024;
 constexpr int TAB2_KEYS = 64;
 
+// Counting sort of every W-point window of the launch range by the previous step's trip count: perm[window * W + k] =
+// offset (within the window) of the point with the k-th smallest count.  One 256-thread block per window.
+template <int W>
 __global__ void __launch_bounds__(256)
 trip_order_kernel(const int32_t* __restrict__ iterations, const __grid_constant__ Layout L, const uint32_t n,
                   uint16_t* __restrict__ perm) {
+  constexpr int PER = W / 256;
   __shared__ int hist[TAB2_KEYS];
   __shared__ int base[TAB2_KEYS];
   const int tid = threadIdx.x;
   if (tid < TAB2_KEYS) hist[tid] = 0;
   __syncthreads();
-  const uint32_t t0 = blockIdx.x * (uint32_t)TAB2_WINDOW;
-  int key[4], rank[4];
+  const uint32_t t0 = blockIdx.x * (uint32_t)W;
+  int key[PER], rank[PER];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < PER; ++k) {
     const uint32_t t = t0 + tid + 256 * k;
     int kk = TAB2_KEYS - 1;                    // beyond the launch range: last
     if (t < n) {
@@ -64,51 +67,70 @@ trip_order_kernel(const int32_t* __restrict__ iterations, const __grid_constant_
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < 4; ++k) perm[t0 + base[key[k]] + rank[k]] = (uint16_t)(tid + 256 * k);
+  for (int k = 0; k < PER; ++k) perm[t0 + base[key[k]] + rank[k]] = (uint16_t)(tid + 256 * k);
 }
 
-template <class CT, bool SORT, bool FMPRO, class O>
-__global__ void __launch_bounds__(256, 3)
+// NW warps per CTA (8: 80 registers at 3 CTAs per SM; 7: 96 registers, no spills), W points per window.
+template <class CT, bool SORT, int NW, int W, class O>
+__global__ void __maxnreg__(NW == 8 ? 80 : 96)
 ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_constant__ Layout L,
                     const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P,
-                    const __grid_constant__ TabParams T, const double* __restrict__ gtab,
+                    const __grid_constant__ TabParams T, const __grid_constant__ Micro Mi, const double* __restrict__ gtab,
                     const uint16_t* __restrict__ perm, unsigned long long* __restrict__ counts) {
-  __shared__ __align__(16) double tab[fm::TAB_SIZE];
-  for (int k = threadIdx.x; k < fm::TAB_SIZE / 2; k += 256)
+  constexpr int NT = NW * 32, GROUPS = W / 32;
+  extern __shared__ __align__(16) double tab[];   // fm::TAB_SIZE doubles (dynamic: see allow_table_smem)
+  __shared__ double park[6][NT];
+  for (int k = threadIdx.x; k < fm::TAB_SIZE / 2; k += NT)
     reinterpret_cast<double2*>(tab)[k] = __ldg(reinterpret_cast<const double2*>(gtab) + k);
   __syncthreads();
   O o;
   const uint32_t n = (uint32_t)L.ni * (uint32_t)L.nj;
-  const uint32_t n_windows = (n + TAB2_WINDOW - 1) / TAB2_WINDOW;
+  const uint32_t n_windows = (n + W - 1) / W;
   const bool celsius = d.ocean.temperature_units == NE_DEGREES_CELSIUS;
   const bool relative = d.properties.velocity_formulation == NE_VEL_RELATIVE;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
   unsigned long long warp_trips = 0;
   for (uint32_t w = blockIdx.x; w < n_windows; w += gridDim.x) {
+    // the (sorted) window's groups are dealt to the warps in a snake (…, NW−1, NW−1, …, 0): every warp gets cheap and
+    // expensive groups; the starting warp rotates with the window so that no warp is always the one with a group more
+    const int r0 = (warp + (int)(w % NW)) % NW;
 #pragma unroll 1
-    for (int r = 0; r < 4; ++r) {
-      // snake: every warp gets one group of each quarter of the (sorted) window
-      const int g = (r == 0) ? warp : (r == 1) ? 15 - warp : (r == 2) ? 16 + warp : 31 - warp;
-      const uint32_t slot = w * (uint32_t)TAB2_WINDOW + (uint32_t)(g * 32 + lane);
-      const uint32_t t = SORT ? w * (uint32_t)TAB2_WINDOW + perm[slot] : slot;
-      if (t >= n) continue;
-      const uint32_t jj = t / (uint32_t)L.ni;
-      const int64_t idx = L.at(L.i_lo + (int32_t)(t - jj * (uint32_t)L.ni), L.j_lo + (int32_t)jj);
-      const bool not_water = d.inactive ? (d.inactive[idx] != 0) : false;
-      const bool skip = not_water && !P.fixed;   // needs_to_converge && not_water (atmosphere_ocean_fluxes.jl:144)
+    for (int pass = 0; pass * NW < GROUPS; ++pass) {
+      const int g = pass * NW + ((pass & 1) ? NW - 1 - r0 : r0);
+      if (g >= GROUPS) continue;
+      const uint32_t slot = w * (uint32_t)W + (uint32_t)(g * 32 + lane);
+      const uint32_t t = SORT ? w * (uint32_t)W + perm[slot] : slot;
+      const bool valid = t < n;
+      int64_t idx = 0;
+      bool not_water = true;
+      if (valid) {
+        const uint32_t jj = t / (uint32_t)L.ni;
+        idx = L.at(L.i_lo + (int32_t)(t - jj * (uint32_t)L.ni), L.j_lo + (int32_t)jj);
+        not_water = d.inactive ? (d.inactive[idx] != 0) : false;
+      }
+      const bool solve = valid && !(not_water && !P.fixed);   // needs_to_converge && not_water: no solve (atmosphere_ocean_fluxes.jl:144)
+      const unsigned solving = __ballot_sync(0xffffffffu, solve);   // all 32 lanes are converged here (loop head)
       double ustar = 0, theta_star = 0, q_star = 0;
       int iters = 0;
-      if (!skip) {
-        FastPoint s;
-        tab2_prologue<O, CT, true, FMPRO>(o, d, L, th, P, T, tab, idx, celsius, relative, s);
-        iters = tab2_solve(o, P, T, tab, s, counts);
-        ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
-        if (!std::is_same<O, fm::OpsPlain>::value) {
-          const int mx = __reduce_max_sync(__activemask(), iters);
-          if (lane == __ffs(__activemask()) - 1) warp_trips += mx;
+      if (valid) {
+        Parked k;
+        double So;
+        tab2_load<true>(d, L, idx, celsius, relative, not_water, k, So);
+        if (solve) {
+          FastPoint s;
+          tab2_invariants(o, d, th, P, T, tab, k, k.du, k.dv, So, s);
+          park[0][tid] = k.du; park[1][tid] = k.dv; park[2][tid] = k.Ta; park[3][tid] = k.pa; park[4][tid] = k.qa; park[5][tid] = k.Ts;
+          iters = tab2_solve(o, P, T, Mi, tab, s, counts);
+          ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
+          k.du = park[0][tid]; k.dv = park[1][tid]; k.Ta = park[2][tid]; k.pa = park[3][tid]; k.qa = park[4][tid]; k.Ts = park[5][tid];
+          if (!std::is_same<O, fm::OpsPlain>::value) {   // warp trips = the slowest lane's, once per group
+            __syncwarp(solving);
+            const int mx = __reduce_max_sync(solving, iters);
+            if (lane == __ffs(solving) - 1) warp_trips += mx;
+          }
         }
+        tab2_epilogue<O, CT>(o, d, th, idx, celsius, not_water, k, ustar, theta_star, q_star, iters);
       }
-      tab2_epilogue<O, CT, FMPRO>(o, d, L, th, idx, celsius, relative, not_water, ustar, theta_star, q_star, iters);
     }
   }
   if (!std::is_same<O, fm::OpsPlain>::value) {
@@ -135,65 +157,78 @@ static uint16_t* order_buffer(const void* key, uint32_t n) {
     g_order.clear();
   }
   OrderBuf b{dev, key, n, nullptr};
-  const size_t windows = ((size_t)n + TAB2_WINDOW - 1) / TAB2_WINDOW;
-  if (cudaMalloc(&b.perm, windows * TAB2_WINDOW * sizeof(uint16_t)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  const size_t windows = ((size_t)n + 1023) / 1024;
+  if (cudaMalloc(&b.perm, windows * 1024 * sizeof(uint16_t)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   g_order.push_back(b);
   return b.perm;
 }
 
-static unsigned tab2_grid(uint32_t n_windows) {
+static unsigned tab2_grid(uint32_t n_windows, int window) {
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int waves = std::max(1, env_int("NE_B200_TAB_WAVES", 4));
+  // resident CTAs x waves; a wave of 256-point windows is a quarter of the work of a wave of 1024-point ones
+  const int waves = std::max(1, env_int("NE_B200_TAB_WAVES", 8 * 1024 / window / 4));
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(n_windows, (int64_t)sms * 3 * waves));
 }
+
+constexpr int TAB2_MAX_WINDOW = 1024;
 
 bool tab2_eligible(const NeAtmosOceanDesc& d, const TabParams& TP) {
   if (env_flag("NE_B200_TAB_V1")) return false;
   if (TP.general_psi || d.surface_layer_height.ptr || d.boundary_layer_height.ptr) return false;
   const int64_t n = (int64_t)(d.grid.i_hi - d.grid.i_lo + 1) * (int64_t)(d.grid.j_hi - d.grid.j_lo + 1);
-  return n > 0 && n < ((int64_t)1 << 31) - TAB2_WINDOW;
+  return n > 0 && n < ((int64_t)1 << 31) - TAB2_MAX_WINDOW;
 }
 
-// counts != nullptr: the counting instantiation (6 device counters: fma, mul, add, other, thread trips, warp trips)
-int launch_tab2(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P, const TabParams& TP, const double* tab,
-                cudaStream_t s, unsigned long long* counts) {
-  const uint32_t n = (uint32_t)L.ni * (uint32_t)L.nj;
-  const uint32_t n_windows = (n + TAB2_WINDOW - 1) / TAB2_WINDOW;
-  const bool ct64 = d.thermo.dtype == NE_F64;
-  const bool fmpro = !env_flag("NE_B200_TAB2_LIBM_PROLOGUE");
-  uint16_t* perm = nullptr;
-  if (d.iterations && !env_flag("NE_B200_TAB2_NO_ORDER")) perm = order_buffer(d.iterations, n);
+template <class CT, int NW, int W>
+static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P, const TabParams& TP, const Micro& Mi,
+                         const double* tab, cudaStream_t s, unsigned long long* counts, uint16_t* perm, uint32_t n) {
+  const uint32_t n_windows = (n + W - 1) / W;
   if (perm) {
-    trip_order_kernel<<<n_windows, 256, 0, s>>>(d.iterations, L, n, perm);
+    trip_order_kernel<W><<<n_windows, 256, 0, s>>>(d.iterations, L, n, perm);
     NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(trip order)");
   }
-  const unsigned grid = tab2_grid(n_windows);
-#define NE_TAB2(CT, SORT, FMPRO, O) \
-  ao_flux_tab2_kernel<CT, SORT, FMPRO, O><<<grid, 256, 0, s>>>(d, L, Thermo<CT>::make(d.thermo), P, TP, tab, perm, counts)
-#define NE_TAB2_O(CT, SORT, FMPRO)                      \
-  do {                                                  \
-    if (counts) NE_TAB2(CT, SORT, FMPRO, fm::OpsCount); \
-    else NE_TAB2(CT, SORT, FMPRO, fm::OpsPlain);        \
+  const unsigned grid = tab2_grid(n_windows, W);
+  const Thermo<CT> th = Thermo<CT>::make(d.thermo);
+#define NE_TAB2_GO(SORT, O)                                                                                                    \
+  do {                                                                                                                         \
+    if (cudaError_t e = allow_table_smem<ao_flux_tab2_kernel<CT, SORT, NW, W, O>>(); e != cudaSuccess)                         \
+      return cuda_error(e, "ne_atmosphere_ocean_fluxes(tab2: shared memory opt-in)");                                          \
+    ao_flux_tab2_kernel<CT, SORT, NW, W, O><<<grid, NW * 32, TAB_SMEM_BYTES, s>>>(d, L, th, P, TP, Mi, tab, perm, counts);     \
   } while (0)
-#define NE_TAB2_S(CT, FMPRO)                   \
-  do {                                         \
-    if (perm) NE_TAB2_O(CT, true, FMPRO);      \
-    else NE_TAB2_O(CT, false, FMPRO);          \
-  } while (0)
-  if (fmpro) {
-    if (ct64) NE_TAB2_S(double, true); else NE_TAB2_S(float, true);
+  if (counts) {
+    if (perm) NE_TAB2_GO(true, fm::OpsCount); else NE_TAB2_GO(false, fm::OpsCount);
   } else {
-    if (counts) { set_error("the counting build covers the shipped prologue only"); return NE_E_INVALID; }
-    if (ct64) { if (perm) NE_TAB2(double, true, false, fm::OpsPlain); else NE_TAB2(double, false, false, fm::OpsPlain); }
-    else { if (perm) NE_TAB2(float, true, false, fm::OpsPlain); else NE_TAB2(float, false, false, fm::OpsPlain); }
+    if (perm) NE_TAB2_GO(true, fm::OpsPlain); else NE_TAB2_GO(false, fm::OpsPlain);
   }
-#undef NE_TAB2_S
-#undef NE_TAB2_O
-#undef NE_TAB2
+#undef NE_TAB2_GO
   NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(tab2)");
   return NE_OK;
+}
+
+// counts != nullptr: the counting instantiation (6 device counters: fma, mul, add, other, thread trips, warp trips);
+// host_tab: the host copy of the solver table (the micro records travel as a kernel parameter)
+int launch_tab2(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P, const TabParams& TP, const double* tab,
+                const double* host_tab, cudaStream_t s, unsigned long long* counts) {
+  const uint32_t n = (uint32_t)L.ni * (uint32_t)L.nj;
+  const bool ct64 = d.thermo.dtype == NE_F64;
+  Micro Mi;
+  for (int side = 0; side < 2; ++side)
+    for (int k = 0; k < fm::MICRO_REC; ++k) Mi.rec[side][k] = host_tab[fm::TAB_MICRO + side * fm::MICRO_REC + k];
+  uint16_t* perm = nullptr;
+  if (d.iterations && !env_flag("NE_B200_TAB2_NO_ORDER")) perm = order_buffer(d.iterations, n);
+  // development knobs (profiles/r02_notes.md): warps per CTA and window size of the shipped configuration
+  const int nw = env_int("NE_B200_TAB2_WARPS", 8), win = env_int("NE_B200_TAB2_WINDOW", 1024);
+#define NE_TAB2_W(CT, NW)                                                                          \
+  do {                                                                                             \
+    if (win == 256) return launch_tab2_t<CT, NW, 256>(d, L, P, TP, Mi, tab, s, counts, perm, n);   \
+    if (win == 512) return launch_tab2_t<CT, NW, 512>(d, L, P, TP, Mi, tab, s, counts, perm, n);   \
+    return launch_tab2_t<CT, NW, 1024>(d, L, P, TP, Mi, tab, s, counts, perm, n);                  \
+  } while (0)
+  if (ct64) { if (nw == 7) NE_TAB2_W(double, 7); else NE_TAB2_W(double, 8); }
+  else { if (nw == 7) NE_TAB2_W(float, 7); else NE_TAB2_W(float, 8); }
+#undef NE_TAB2_W
 }
 
 }  // namespace ne

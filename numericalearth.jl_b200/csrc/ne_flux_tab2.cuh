@@ -121,9 +121,12 @@ static __device__ __noinline__ double2 tab2_psi_small(const FastParams& P, const
 }
 
 // ---- one trip of iterate_interface_state (compute_interface_state.jl:69-122 + similarity_theory…:315-385) ---
+// the two |ζ| < 2^-12 records (unstable, stable) as a kernel parameter: constant-bank operands
+struct Micro { double rec[2][fm::MICRO_REC]; };
+
 template <class O>
-__device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const TabParams& T, const double* tab, FastPoint& s,
-                                               unsigned long long* counts) {
+__device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const TabParams& T, const Micro& Mi, const double* tab,
+                                               FastPoint& s, unsigned long long* counts) {
   using fm::dmax;
   using fm::dmin;
   // b★, gustiness, U (similarity_theory…:354-358, 417-425)
@@ -153,10 +156,20 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
   const int iv = fm::psi_interval(zh, outside);
   double pm_h, ps_h;
   fm::psi_pair(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(zh), pm_h, ps_h);
-  // ψ(ℓ/L★): always from the |ζ| < 2^-12 record of the side of L★
+  // ψ(ℓ/L★): always from the |ζ| < 2^-12 record of the side of L★.  The two records also sit in the kernel-parameter
+  // constant bank (Micro): a warp whose lanes are all on one side — nearly every warp, L★ varies smoothly in space —
+  // takes its coefficients from there and issues no shared-memory load for this lookup (7 LDS.128 = 28 wavefronts of
+  // the ~100 a trip puts on the L1TEX data pipe, the unit that bounds this kernel)
   const double zu = o.mul(lu, Linv), zs = o.mul(ls, Linv);
   double pm_l, ps_l;
-  fm::psi_micro_pair(o, tab + fm::TAB_MICRO + (Linv < 0 ? 0 : fm::MICRO_REC), fabs(zu), fabs(zs), pm_l, ps_l);
+  {
+    const bool unstable = Linv < 0;
+    const unsigned act = __activemask();
+    const unsigned neg = __ballot_sync(act, unstable);
+    if (neg == act) fm::psi_micro_pair(o, Mi.rec[0], fabs(zu), fabs(zs), pm_l, ps_l);
+    else if (neg == 0u) fm::psi_micro_pair(o, Mi.rec[1], fabs(zu), fabs(zs), pm_l, ps_l);
+    else fm::psi_micro_pair(o, tab + fm::TAB_MICRO + (unstable ? 0 : fm::MICRO_REC), fabs(zu), fabs(zs), pm_l, ps_l);
+  }
   if (outside) {
     const double2 r = tab2_psi_outside<O>(P, T, tab, zh, counts);
     pm_h = r.x; ps_h = r.y;
@@ -180,8 +193,8 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
 
 // compute_interface_state.jl:10-18: the first trip always runs; then until drift < tol or it ≥ maxiter
 template <class O>
-__device__ __forceinline__ int tab2_solve(O& o, const FastParams& P, const TabParams& T, const double* tab, FastPoint& s,
-                                          unsigned long long* counts) {
+__device__ __forceinline__ int tab2_solve(O& o, const FastParams& P, const TabParams& T, const Micro& Mi, const double* tab,
+                                          FastPoint& s, unsigned long long* counts) {
   if (P.fixed && P.maxiter <= 0) return 0;
   const double tol = P.fixed ? -1.0 : P.tol;
   const int maxiter = P.maxiter;
@@ -189,7 +202,7 @@ __device__ __forceinline__ int tab2_solve(O& o, const FastParams& P, const TabPa
   double drift;
   do {
     const double pu = s.ustar, pt = s.theta_star, pq = s.q_star;
-    tab2_iteration(o, P, T, tab, s, counts);
+    tab2_iteration(o, P, T, Mi, tab, s, counts);
     drift = o.add(o.add(fabs(o.sub(s.ustar, pu)), fabs(o.sub(s.theta_star, pt))), fabs(o.sub(s.q_star, pq)));
     ++it;
     o.trip();
@@ -204,6 +217,11 @@ __device__ __forceinline__ float tab2_powf(O& o, const TabParams& T, const doubl
   return (float)fm::exp_mid(o, T.mc, o.mul((double)y, fm::log_pos(o, tab, T.mc, (double)x)));
 }
 
+// p_sat = p_tr (T/T_tr)^(Δcp/R_v) exp[(ℒ₀ − Δcp T₀)/R_v (1/T_tr − 1/T)].  The ARGUMENTS of the power and of the exponential are
+// formed with the reference's own operations in its order (IEEE divisions; the constant factors on the host, Thermo::make):
+// a one-ulp difference there is multiplied by |argument| ≈ 20 in the result, and q_sat feeds Δq = qₐ − qₛ, whose
+// cancellation the pointwise parity criterion sees.  Only the two transcendental evaluations differ from the oracle's
+// library calls (≲ 3 ulp).
 template <class O>
 __device__ __forceinline__ double tab2_psat(O& o, const Thermo<float>& th, const TabParams& T, const double* tab, int phase, double Ts) {
   const float Tf = (float)Ts;
@@ -217,8 +235,9 @@ __device__ __forceinline__ double tab2_psat(O& o, const Thermo<float>& th, const
 template <class O>
 __device__ __forceinline__ double tab2_psat(O& o, const Thermo<double>& th, const TabParams& T, const double* tab, int phase, double Ts) {
   const int ph = phase == NE_PHASE_LIQUID ? 0 : 1;
-  const double x = o.mul(Ts, th.inv_T_triple);
-  const double a = o.mul(th.psat_exp[ph], o.sub(th.inv_T_triple, fm::rcp(o, Ts)));
+  const double x = __ddiv_rn(Ts, th.T_triple);
+  const double a = o.mul(th.psat_exp[ph], o.sub(th.inv_T_triple, __ddiv_rn(1.0, Ts)));
+  o.other(2);
   const double pw = fm::exp_mid(o, T.mc, o.mul(th.psat_pow[ph], fm::log_pos(o, tab, T.mc, x)));
   return o.mul(o.mul(th.press_triple, pw), fm::exp_mid(o, T.mc, a));
 }
@@ -239,79 +258,66 @@ __device__ __forceinline__ double tab2_surface_humidity(O& o, const NeInterfaceP
   const double lim = (double)((CT)0.999 * p);
   pv = lim < pv ? lim : pv;
   const double num = o.mul((double)th.eps_inv, pv);
-  const double den = o.fma(-(double)((CT)1 - th.eps_inv), pv, (double)p);
+  const double den = o.sub((double)p, o.mul((double)((CT)1 - th.eps_inv), pv));
   return fm::div(o, num, den);
 }
 
-template <class O, class CT, bool HS, bool FMPRO>
-__device__ __forceinline__ void tab2_prologue(O& o, const NeAtmosOceanDesc& d, const Layout& L, const Thermo<CT>& th,
-                                              const FastParams& P, const TabParams& T, const double* tab, int64_t idx,
-                                              bool celsius, bool relative, FastPoint& s) {
+// what the flux epilogue needs of a point, parked in shared memory across the solve (one slot per thread: conflict-free
+// 64-bit accesses, 2 wavefronts each) instead of being re-read from global memory (trip-ordered lanes touch up to 32
+// cache lines per load) or kept in registers (the loop already spills at 80)
+struct Parked { double du, dv, Ta, pa, qa, Ts; };
+
+// loads of one point: atmosphere state, velocity difference, surface temperature in Kelvin
+template <bool HS>
+__device__ __forceinline__ void tab2_load(const NeAtmosOceanDesc& d, const Layout& L, int64_t idx, bool celsius, bool relative,
+                                          bool not_water, Parked& k, double& So) {
   const double au = __ldg((const double*)d.ua + idx), av = __ldg((const double*)d.va + idx);
-  const double aT = __ldg((const double*)d.Ta + idx), ap = __ldg((const double*)d.pa + idx), aq = __ldg((const double*)d.qa + idx);
-  const double az = HS ? d.surface_layer_height.value : slot_at<double>(d.surface_layer_height, idx);
-  double du = au, dv = av;
-  if (relative) {
-    du -= d.uo.ptr ? (slot_at<double>(d.uo, idx) + slot_at<double>(d.uo, idx + 1)) / 2 : d.uo.value;
-    dv -= d.vo.ptr ? (slot_at<double>(d.vo, idx) + slot_at<double>(d.vo, idx + L.sx)) / 2 : d.vo.value;
+  k.Ta = __ldg((const double*)d.Ta + idx); k.pa = __ldg((const double*)d.pa + idx); k.qa = __ldg((const double*)d.qa + idx);
+  k.du = au; k.dv = av;
+  if (relative && !not_water) {
+    k.du -= d.uo.ptr ? (slot_at<double>(d.uo, idx) + slot_at<double>(d.uo, idx + 1)) / 2 : d.uo.value;
+    k.dv -= d.vo.ptr ? (slot_at<double>(d.vo, idx) + slot_at<double>(d.vo, idx + L.sx)) / 2 : d.vo.value;
   }
   double To = slot_at<double>(d.To, idx);
   if (celsius) To = To + 273.15;
-  s.h_bl = HS ? d.boundary_layer_height.value : slot_at<double>(d.boundary_layer_height, idx);
+  k.Ts = To;
+  So = slot_at<double>(d.So, idx);
+}
+
+// iteration invariants of a solved point (BulkTemperature: everything but the iterate is fixed)
+template <class O, class CT>
+__device__ __forceinline__ void tab2_invariants(O& o, const NeAtmosOceanDesc& d, const Thermo<CT>& th, const FastParams& P,
+                                                const TabParams& T, const double* tab, const Parked& k, double du, double dv,
+                                                double So, FastPoint& s) {
+  const double az = d.surface_layer_height.value;
+  const double To = k.Ts;
+  s.h_bl = d.boundary_layer_height.value;
   s.hd = az - P.d_zero;
-  if (FMPRO) {
-    const double qs = tab2_surface_humidity(o, d.properties, th, T, tab, ap, To, slot_at<double>(d.So, idx));
-    const double Rm = o.fma((double)th.R_v, qs, o.mul((double)th.R_d, o.sub(1.0, qs)));     // R_d(1 − q) + R_v q
-    const double Tv = fm::div(o, o.mul(To, Rm), (double)th.R_d);                          // virtual_temperature
-    s.gTv = fm::div(o, P.g, Tv);
-    s.c1 = o.fma((double)th.delta, qs, 1.0);
-    s.c2 = o.mul((double)th.delta, Tv);
-    s.dudv2 = o.fma(du, du, o.mul(dv, dv));
-    s.log_hd = HS ? T.log_hd : fm::log_pos(o, tab, T.mc, s.hd);
-    const double cpm = o.fma((double)th.cp_v, aq, o.mul((double)th.cp_d, o.sub(1.0, aq)));
-    s.dtheta = o.sub(o.add(aT, fm::div(o, o.mul(P.g, az), cpm)), To);                      // θₐ − Tₛ (interface_states.jl:308-317)
-    s.dq = o.sub(aq, qs);
-  } else {
-    const double qs = surface_specific_humidity<double, CT>(d.properties, th, ap, To, slot_at<double>(d.So, idx));
-    const double Tv = th.virtual_temperature(To, qs);
-    s.gTv = P.g / Tv;
-    s.c1 = 1 + th.delta * qs;
-    s.c2 = th.delta * Tv;
-    s.dudv2 = du * du + dv * dv;
-    s.log_hd = HS ? T.log_hd : log(s.hd);
-    s.dtheta = (aT + P.g * az / th.cp_m(aq)) - To;
-    s.dq = aq - qs;
-    o.other(300);
-  }
+  s.log_hd = T.log_hd;
+  const double qs = tab2_surface_humidity(o, d.properties, th, T, tab, k.pa, To, So);
+  const double Rm = o.add(o.mul((double)th.R_d, o.sub(1.0, qs)), o.mul((double)th.R_v, qs));   // R_d(1 − q) + R_v q
+  const double Tv = fm::div(o, o.mul(To, Rm), (double)th.R_d);                                  // virtual_temperature
+  s.gTv = fm::div(o, P.g, Tv);
+  s.c1 = o.fma((double)th.delta, qs, 1.0);
+  s.c2 = o.mul((double)th.delta, Tv);
+  s.dudv2 = o.fma(du, du, o.mul(dv, dv));
+  const double cpm = o.add(o.mul((double)th.cp_d, o.sub(1.0, k.qa)), o.mul((double)th.cp_v, k.qa));
+  s.dtheta = o.sub(o.add(k.Ta, fm::div(o, o.mul(P.g, az), cpm)), To);                           // θₐ − Tₛ (interface_states.jl:308-317)
+  s.dq = o.sub(k.qa, qs);
   s.ustar = s.theta_star = s.q_star = 1e-4;   // atmosphere_ocean_fluxes.jl:131-137
 }
 
-// flux epilogue + stores (atmosphere_ocean_fluxes.jl:160-196); the atmosphere state is re-read (L2 hits) instead
-// of being kept live across the solve
-template <class O, class CT, bool FMPRO>
-__device__ __forceinline__ void tab2_epilogue(O& o, const NeAtmosOceanDesc& d, const Layout& L, const Thermo<CT>& th,
-                                              int64_t idx, bool celsius, bool relative, bool not_water, double ustar,
-                                              double theta_star, double q_star, int iters) {
-  AtmosState<double> a;
-  a.u = __ldg((const double*)d.ua + idx);
-  a.v = __ldg((const double*)d.va + idx);
-  a.T = __ldg((const double*)d.Ta + idx);
-  a.p = __ldg((const double*)d.pa + idx);
-  a.q = __ldg((const double*)d.qa + idx);
-  a.z = 0; a.h_bl = 0;
-  double du = a.u, dv = a.v, Ts;
-  if (not_water) {  // zero_interface_state (interface_states.jl:800-803): Δu = uₐ − 0
+// flux epilogue + stores (atmosphere_ocean_fluxes.jl:160-196)
+template <class O, class CT>
+__device__ __forceinline__ void tab2_epilogue(O& o, const NeAtmosOceanDesc& d, const Thermo<CT>& th, int64_t idx, bool celsius,
+                                              bool not_water, const Parked& k, double ustar, double theta_star, double q_star, int iters) {
+  const double du = k.du, dv = k.dv;
+  double Ts = k.Ts;
+  if (not_water) {  // zero_interface_state (interface_states.jl:800-803): Δu = uₐ − 0 (parked as such)
     ustar = 0; theta_star = 0; q_star = 0; Ts = 273.15;
-  } else {
-    if (relative) {
-      du -= d.uo.ptr ? (slot_at<double>(d.uo, idx) + slot_at<double>(d.uo, idx + 1)) / 2 : d.uo.value;
-      dv -= d.vo.ptr ? (slot_at<double>(d.vo, idx) + slot_at<double>(d.vo, idx + L.sx)) / 2 : d.vo.value;
-    }
-    Ts = slot_at<double>(d.To, idx);
-    if (celsius) Ts = Ts + 273.15;
   }
   double Qv, Qc, Jv, tx, ty;
-  if (FMPRO && a.T > 150.0 && a.p > 0.0) {
+  if (k.Ta > 150.0 && k.pa > 0.0) {
     const double dU2 = o.fma(du, du, o.mul(dv, dv));
     double taux = 0, tauy = 0;
     if (dU2 > 1e-290) {                                               // τ = −u★² Δu/ΔU with the RESOLVED ΔU (:166-170)
@@ -321,17 +327,19 @@ __device__ __forceinline__ void tab2_epilogue(O& o, const NeAtmosOceanDesc& d, c
       const double dU = sqrt(dU2);
       taux = -(ustar * ustar) * du / dU; tauy = -(ustar * ustar) * dv / dU;
     }
-    const double Rm = o.fma((double)th.R_v, a.q, o.mul((double)th.R_d, o.sub(1.0, a.q)));
-    const double rho = fm::div(o, a.p, o.mul(Rm, a.T));                // air_density
-    const double cpm = o.fma((double)th.cp_v, a.q, o.mul((double)th.cp_d, o.sub(1.0, a.q)));
-    const double Lv = o.fma((double)(th.cp_v - th.cp_l), o.sub(a.T, (double)th.T_0), (double)th.LH_v0);
+    const double Rm = o.add(o.mul((double)th.R_d, o.sub(1.0, k.qa)), o.mul((double)th.R_v, k.qa));
+    const double rho = fm::div(o, k.pa, o.mul(Rm, k.Ta));              // air_density
+    const double cpm = o.add(o.mul((double)th.cp_d, o.sub(1.0, k.qa)), o.mul((double)th.cp_v, k.qa));
+    const double Lv = o.fma((double)(th.cp_v - th.cp_l), o.sub(k.Ta, (double)th.T_0), (double)th.LH_v0);
     const double ru = o.mul(-rho, ustar);
-    Qv = o.mul(o.mul(ru, Lv), q_star);
-    Qc = o.mul(o.mul(ru, cpm), theta_star);
+    Qv = o.mul(o.mul(o.mul(-rho, Lv), ustar), q_star);
+    Qc = o.mul(o.mul(o.mul(-rho, cpm), ustar), theta_star);
     Jv = o.mul(ru, q_star);
     tx = o.mul(rho, taux);
     ty = o.mul(rho, tauy);
   } else {
+    AtmosState<double> a;
+    a.u = 0; a.v = 0; a.z = 0; a.h_bl = 0; a.T = k.Ta; a.p = k.pa; a.q = k.qa;
     FluxEpilogue<double, CT> e(th, a, ustar, theta_star, q_star, du, dv, false);
     Qv = e.Qv; Qc = e.Qc; Jv = e.Jv; tx = e.tx; ty = e.ty;
     o.other(150);

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -17,6 +18,21 @@ inline bool env_flag(const char* name) {
 inline int env_int(const char* name, int dflt) {
   const char* v = std::getenv(name);
   return v ? std::atoi(v) : dflt;
+}
+
+// The solver table (fm::TAB_SIZE doubles, 44 KB) is DYNAMIC shared memory in every kernel that stages it: together with
+// a kernel's static shared memory it exceeds the 48 KB a kernel may use without opting in.  Once per kernel and device.
+constexpr size_t TAB_SMEM_BYTES = sizeof(double) * fm::TAB_SIZE;
+template <auto Kernel>
+inline cudaError_t allow_table_smem(size_t bytes = TAB_SMEM_BYTES) {
+  static std::atomic<unsigned long long> done{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_relaxed) & bit) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_relaxed);
+  return e;
 }
 
 // the work-queue kernel indexes points with 32 bits

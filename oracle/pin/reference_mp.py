@@ -1,0 +1,304 @@
+"""INDEPENDENT PIN of the oracle — TEST INFRASTRUCTURE ONLY (like everything under oracle/).
+
+A second restatement of the reference's similarity-theory flux path, written from the reference's own documentation
+and docstring mathematics — not from oracle/ne_oracle.cpp and not from the CUDA headers — in arbitrary precision
+(mpmath, 50 significant digits), with a different program structure (closures over a parameter record, one generic
+fixed-point driver).  It exists so that the C++ oracle is checked against something its author could not have
+mis-copied the same way twice: tests/test_oracle_independent_pin.py differential-tests every function below against
+the oracle on random arguments and whole fixed points.
+
+Sources (all relative to /root/reference):
+  saturation vapour pressure     docs/src/interface_fluxes.md:84-96  (Clausius–Clapeyron with constant Δc_p)
+  surface specific humidity      src/EarthSystemModels/InterfaceComputations/interface_states.jl:44-74
+                                 (q = ε p⁺ / (p − (1 − ε) p⁺), ε = R_d/R_v, p⁺ = min(x p_sat, 0.999 p))
+  mixture gas constant, b★       docs/src/interface_fluxes.md:500-545 ; similarity_theory_turbulent_fluxes.jl:389-425
+  roughness lengths              docs/src/interface_fluxes.md:236-262 ; roughness_lengths.jl:197-246 (Edson 2013 eq. 28)
+  gustiness                      similarity_theory_turbulent_fluxes.jl:36-48, 88-98  (U_G = max(floor, β (J_b h_bl)^{1/3}))
+  Edson et al. (2013) ψ_u, ψ_θ   docstring mathematics at similarity_theory_turbulent_fluxes.jl:450-486, 534-570
+                                 (= COARE 3.5 psiu_26 / psit_26) with the constants of :487-499, 571-584
+  similarity profile, χ          docs/src/interface_fluxes.md:620-690 ; similarity_theory_turbulent_fluxes.jl:239-253, 375-384
+  fixed point + stopping rule    compute_interface_state.jl:5-58
+  flux epilogue                  atmosphere_ocean_fluxes.jl:160-196
+  interpolator / bilinear / time docs of Oceananigans (third party): i⁻ = trunc(f) + 1, ξ = f mod 1; ψ₂ ñ + ψ₁ (1 − ñ)
+
+Every input is taken as the exact value of the double it was given as; every result is exact to ~1e-45, so a
+difference from the oracle IS the oracle's rounding error (or its mistake).
+"""
+from dataclasses import dataclass, field
+
+import mpmath as mp
+
+mp.mp.dps = 50
+M = mp.mpf
+
+
+def _m(x):
+    return M(float(x)) if not isinstance(x, mp.mpf) else x
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parameters (Appendix A of SURVEY.md = the reference's keyword defaults; cited where each record is used)
+# ----------------------------------------------------------------------------------------------------------------
+@dataclass
+class Thermo:   # src/Atmospheres/thermodynamic_parameters.jl:30-258
+    R: float = 8.3144598
+    M_d: float = 0.02897
+    M_v: float = 0.018015
+    kappa_d: float = 2.0 / 7.0
+    cp_v: float = 1859.0
+    cp_l: float = 4181.0
+    cp_i: float = 2100.0
+    LH_v0: float = 2500800.0
+    LH_s0: float = 2834400.0
+    T_0: float = 273.16
+    T_tr: float = 273.16
+    p_tr: float = 611.657
+
+    # the reference forms these in Float64 from the Float64 fields: keep the SAME doubles as inputs, exact afterwards
+    @property
+    def R_d(self):
+        return _m(self.R / self.M_d)
+
+    @property
+    def R_v(self):
+        return _m(self.R / self.M_v)
+
+    @property
+    def cp_d(self):
+        return _m((self.R / self.M_d) / self.kappa_d)
+
+    @property
+    def eps_vd(self):       # R_v / R_d = M_d / M_v
+        return _m(self.M_d / self.M_v)
+
+
+@dataclass
+class EdsonConstants:   # similarity_theory_turbulent_fluxes.jl:487-499 (momentum), 571-584 (scalar)
+    zmax: float = 50.0
+    Ap: float = 0.35
+    Bp_m: float = 0.7
+    Cp_m: float = 0.75
+    Dp_m: float = 5 / 0.35
+    Am: float = 15.0
+    Bm: float = 2.0
+    Cm_m: float = float(mp.pi / 2)
+    Dm_m: float = 10.15
+    Em: float = 3.0
+    Fm: float = float(mp.pi / mp.sqrt(3))
+    Bp_s: float = 2 / 3
+    Cp_s: float = 3 / 2
+    Dp_s: float = 14.28
+    Ep_s: float = 8.525
+    Cm_s: float = 0.0
+    Dm_s: float = 34.15
+
+
+@dataclass
+class SolverParams:   # SimilarityTheoryFluxes defaults, similarity_theory_turbulent_fluxes.jl:174-214 ; roughness_lengths.jl:93-139
+    kappa: float = 0.4
+    g: float = 9.80665
+    charnock: float = 0.02
+    smooth_wall: float = 0.11
+    nu: float = 1.5e-5
+    ell_max: float = 1.0
+    reynolds_A: float = 5.85e-5
+    reynolds_b: float = 0.72
+    scalar_ell_max: float = 1.6e-4
+    gust_beta: float = 1.2
+    gust_floor: float = 0.01
+    tol: float = 1e-8
+    maxiter: int = 100
+    x_h2o: float = 0.98          # component_interfaces.jl:353-358
+    thermo: Thermo = field(default_factory=Thermo)
+    edson: EdsonConstants = field(default_factory=EdsonConstants)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# thermodynamics
+# ----------------------------------------------------------------------------------------------------------------
+def p_sat(T, th: Thermo = Thermo(), ice=False):
+    """p_tr (T/T_tr)^(Δc_p/R_v) exp[(ℒ₀ − Δc_p T₀)/R_v (1/T_tr − 1/T)],  Δc_p = c_pv − c_pl (liquid) or c_pv − c_pi with ℒ_s0 (ice)."""
+    T = _m(T)
+    dcp = _m(th.cp_v) - _m(th.cp_i if ice else th.cp_l)
+    L0 = _m(th.LH_s0 if ice else th.LH_v0)
+    return _m(th.p_tr) * (T / _m(th.T_tr)) ** (dcp / th.R_v) * mp.e ** ((L0 - dcp * _m(th.T_0)) / th.R_v * (1 / _m(th.T_tr) - 1 / T))
+
+
+def q_surface(p, T, x_h2o=0.98, th: Thermo = Thermo(), ice=False):
+    p = _m(p)
+    pv = _m(x_h2o) * p_sat(T, th, ice)
+    pv = min(pv, _m(0.999) * p)
+    e = 1 / th.eps_vd                      # R_d / R_v
+    return e * pv / (p - (1 - e) * pv)
+
+
+def R_mix(q, th):
+    return th.R_d * (1 - q) + th.R_v * q
+
+
+def cp_mix(q, th):
+    return th.cp_d * (1 - q) + _m(th.cp_v) * q
+
+
+def buoyancy_scale(theta_star, q_star, Ts, qs, g, th):
+    """b★ = g/𝒯ₛ [θ★ (1 + δ qₛ) + δ 𝒯ₛ q★], 𝒯ₛ = Tₛ R_m(qₛ)/R_d, δ = R_v/R_d − 1."""
+    Tv = Ts * R_mix(qs, th) / th.R_d
+    delta = th.eps_vd - 1
+    return g / Tv * (theta_star * (1 + delta * qs) + delta * Tv * q_star)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Edson et al. (2013) stability functions
+# ----------------------------------------------------------------------------------------------------------------
+def _convective_branch(z, D, E, F):
+    y = mp.cbrt(1 - D * z)
+    rE = mp.sqrt(E)
+    return E / 2 * mp.log((1 + y + y * y) / E) - rE * mp.atan((1 + 2 * y) / rE) + F
+
+
+def psi_momentum(zeta, c: EdsonConstants = EdsonConstants()):
+    z = _m(zeta)
+    if z < 0:
+        x = (1 - _m(c.Am) * z) ** M("0.25")
+        B = _m(c.Bm)
+        kansas = B * mp.log((1 + x) / B) + mp.log((1 + x * x) / B) - B * mp.atan(x) + _m(c.Cm_m)
+        conv = _convective_branch(z, _m(c.Dm_m), _m(c.Em), _m(c.Fm))
+        f = z * z / (1 + z * z)
+        return (1 - f) * kansas + f * conv
+    dz = min(_m(c.zmax), _m(c.Ap) * z)
+    return -_m(c.Bp_m) * z - _m(c.Cp_m) * (z - _m(c.Dp_m)) * mp.exp(-dz) - _m(c.Cp_m) * _m(c.Dp_m)
+
+
+def psi_scalar(zeta, c: EdsonConstants = EdsonConstants()):
+    z = _m(zeta)
+    if z < 0:
+        x = mp.sqrt(1 - _m(c.Am) * z)
+        B = _m(c.Bm)
+        kansas = B * mp.log((1 + x) / B) + _m(c.Cm_s)
+        conv = _convective_branch(z, _m(c.Dm_s), _m(c.Em), _m(c.Fm))
+        f = z * z / (1 + z * z)
+        return (1 - f) * kansas + f * conv
+    dz = min(_m(c.zmax), _m(c.Ap) * z)
+    return -(1 + _m(c.Bp_s) * z) ** _m(c.Cp_s) - _m(c.Bp_s) * (z - _m(c.Dp_s)) * mp.exp(-dz) - _m(c.Ep_s)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# roughness, gustiness
+# ----------------------------------------------------------------------------------------------------------------
+def ell_momentum(ustar, P: SolverParams):
+    u = _m(ustar)
+    wave = _m(P.charnock) * u * u / _m(P.g)
+    visc = _m(P.smooth_wall) * _m(P.nu) / u if P.smooth_wall != 0 else M(0)
+    return min(wave + visc, _m(P.ell_max))
+
+
+def ell_scalar(ell_u, ustar, P: SolverParams):
+    Re = _m(ell_u) * _m(ustar) / _m(P.nu)
+    val = M(0) if Re == 0 else _m(P.reynolds_A) / Re ** _m(P.reynolds_b)
+    return min(val, _m(P.scalar_ell_max))
+
+
+def gustiness_squared(ustar, bstar, h_bl, P: SolverParams):
+    Jb = max(M(0), -_m(ustar) * _m(bstar))
+    ug = max(_m(P.gust_floor), _m(P.gust_beta) * mp.cbrt(Jb * _m(h_bl)))
+    return ug * ug
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# one trip and the fixed point
+# ----------------------------------------------------------------------------------------------------------------
+def most_map(state, inv, P: SolverParams):
+    """(u★, θ★, q★) ↦ (u★, θ★, q★): one iterate_interface_state of the default a–o tree with BulkTemperature.
+    inv = dict(Ts, qs, dtheta, dq, du, dv, h, h_bl)."""
+    us, ts, qs_ = state
+    th = P.thermo
+    b = buoyancy_scale(ts, qs_, inv["Ts"], inv["qs"], _m(P.g), th)
+    U = mp.sqrt(inv["du"] ** 2 + inv["dv"] ** 2 + gustiness_squared(us, b, inv["h_bl"], P))
+    lu = ell_momentum(us, P)
+    ls = ell_scalar(lu, us, P)
+    h = max(inv["h"], 2 * lu)                                  # zero-plane displacement 0
+    kap = _m(P.kappa)
+
+    def profile(psi, ell):
+        if b == 0:                                            # L★ = Inf: ψ(0) terms
+            return mp.log(h / ell) - psi(0) + psi(0)
+        L = us * us / (kap * b)
+        return mp.log(h / ell) - psi(h / L) + psi(ell / L)
+
+    cu = kap / profile(lambda z: psi_momentum(z, P.edson), lu)
+    cs = kap / profile(lambda z: psi_scalar(z, P.edson), ls)
+    return cu * U, cs * inv["dtheta"], cs * inv["dq"]
+
+
+def invariants(atm, ocean, P: SolverParams):
+    """atm = (u, v, T, p, q), ocean = (u, v, T_kelvin, S) as doubles; h = 10 m, h_bl = 512 m defaults passed in P?"""
+    ua, va, Ta, pa, qa = (_m(x) for x in atm)
+    uo, vo, To, So = (_m(x) for x in ocean)
+    th = P.thermo
+    qs = q_surface(pa, To, P.x_h2o, th)
+    h = _m(P_h(P))
+    theta_a = Ta + _m(P.g) * h / cp_mix(qa, th)
+    return dict(Ts=To, qs=qs, dtheta=theta_a - To, dq=qa - qs, du=ua - uo, dv=va - vo, h=h, h_bl=_m(P_hbl(P)))
+
+
+def P_h(P):
+    return getattr(P, "surface_layer_height", 10.0)
+
+
+def P_hbl(P):
+    return getattr(P, "boundary_layer_height", 512.0)
+
+
+def solve_point(atm, ocean, P: SolverParams = SolverParams(), round_iterate=True):
+    """compute_interface_state: do-while until |Δu★| + |Δθ★| + |Δq★| < tol or maxiter trips.  With round_iterate the iterate
+    is rounded to Float64 after every trip, as the reference stores it (compute_interface_state.jl:116-121) — otherwise the
+    exact orbit.  Returns (u★, θ★, q★, trips, fluxes dict)."""
+    inv = invariants(atm, ocean, P)
+    s = (M("1e-4"),) * 3 if not round_iterate else (_m(1e-4),) * 3
+    trips = 0
+    while True:
+        new = most_map(s, inv, P)
+        if round_iterate:
+            new = tuple(_m(float(x)) for x in new)
+        trips += 1
+        drift = abs(new[0] - s[0]) + abs(new[1] - s[1]) + abs(new[2] - s[2])
+        s = new
+        if drift < _m(P.tol) or trips >= P.maxiter:
+            break
+    us, ts, qs_ = s
+    ua, va, Ta, pa, qa = (_m(x) for x in atm)
+    th = P.thermo
+    dU = mp.sqrt(inv["du"] ** 2 + inv["dv"] ** 2)
+    taux = M(0) if dU == 0 else -us * us * inv["du"] / dU
+    tauy = M(0) if dU == 0 else -us * us * inv["dv"] / dU
+    rho = pa / (R_mix(qa, th) * Ta)
+    Lv = _m(th.LH_v0) + (_m(th.cp_v) - _m(th.cp_l)) * (Ta - _m(th.T_0))
+    fluxes = dict(latent_heat=-rho * Lv * us * qs_, sensible_heat=-rho * cp_mix(qa, th) * us * ts, water_vapor=-rho * us * qs_,
+                  x_momentum=rho * taux, y_momentum=rho * tauy)
+    return us, ts, qs_, trips, fluxes
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# interpolation (Oceananigans, third party: restated from its documented behaviour)
+# ----------------------------------------------------------------------------------------------------------------
+def interpolator(f):
+    """fractional index (0-based) → (i⁻, i⁺, ξ), 1-based indices: i⁻ = trunc(f) + 1, i⁺ = i⁻ + sign(f), ξ = f mod 1."""
+    f = _m(f)
+    t = int(mp.floor(f)) if f >= 0 else -int(mp.floor(-f))
+    sgn = 0 if f == 0 else (1 if f > 0 else -1)
+    xi = f - mp.floor(f)
+    return t + 1, t + 1 + sgn, xi
+
+
+def bilinear_time(corners1, corners2, xi, eta, nt, same):
+    """corners = (d(i⁻,j⁻), d(i⁻,j⁺), d(i⁺,j⁻), d(i⁺,j⁺)) at the two time levels; weights (1−ξ)(1−η) …; ψ₂ ñ + ψ₁ (1 − ñ)."""
+    xi, eta, nt = _m(xi), _m(eta), _m(nt)
+
+    def space(c):
+        a, b, c_, d = (_m(x) for x in c)
+        return (1 - xi) * (1 - eta) * a + (1 - xi) * eta * b + xi * (1 - eta) * c_ + xi * eta * d
+
+    p1 = space(corners1)
+    if same:
+        return p1
+    return space(corners2) * nt + p1 * (1 - nt)

@@ -47,14 +47,18 @@ def pointwise_rel(a, b, floor=1e-6):
     return float(np.nanmax(r))
 
 
-def pointwise_exceed(a, b, tol, floor=1e-6):
-    """Number of points that miss `tol` under the pointwise criterion."""
+def pointwise_exceed(a, b, tol, floor=1e-6, near_zero=1e-4):
+    """(number of points that miss `tol` under the pointwise criterion, how many of those lie where the field is smaller
+    than `near_zero` times its scale, i.e. next to a sign change)."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0, 0
     scale = float(np.nanmax(np.abs(b))) or 1.0
     den = np.maximum(np.abs(b), floor * scale)
     with np.errstate(invalid="ignore"):
-        return int((np.abs(a - b) > tol * den).sum())
+        bad = np.abs(a - b) > tol * den
+    return int(bad.sum()), int((bad & (np.abs(b) < near_zero * scale)).sum())
 
 
 class ParityLog:
@@ -123,7 +127,8 @@ def compare_pointwise(ref_bag, dev_bag, grid, backend, names=None, with_halo_rin
         assert np.array_equal(np.isnan(d), np.isnan(r)), f"{n}: NaN pattern differs"
         if mask is not None:
             r, d = r[mask], d[mask]
-        out[n] = dict(pw=pointwise_rel(d, r, floor), exceed=pointwise_exceed(d, r, tol, floor), n=int(np.asarray(r).size), exact=exact)
+        ex, ex_near_zero = pointwise_exceed(d, r, tol, floor)
+        out[n] = dict(pw=pointwise_rel(d, r, floor), exceed=ex, exceed_near_zero=ex_near_zero, n=int(np.asarray(r).size), exact=exact)
     return out
 
 

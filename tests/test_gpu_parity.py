@@ -413,10 +413,12 @@ def test_work_queue_kernel_equals_one_thread_per_point_kernel_bitwise(cuda_backe
     dev.initialize()
     dev.interpolate_state(T_STEP)
     monkeypatch.setenv("NE_B200_TAB_CLASSIC", "1")
+    monkeypatch.setenv("NE_B200_TAB_V1", "1")      # the round-1 one-thread-per-point kernel (the queue kernel embeds ITS iteration)
     dev.compute_atmosphere_ocean_fluxes()
     cuda_backend.synchronize()
     classic = _ao_outputs(dev, cuda_backend)
     monkeypatch.delenv("NE_B200_TAB_CLASSIC")
+    monkeypatch.delenv("NE_B200_TAB_V1")
     monkeypatch.setenv("NE_B200_QUEUE", "1")
     monkeypatch.setenv("NE_B200_QUEUE_THETA", theta)
     for n in dev.ao_fluxes.names():

@@ -24,6 +24,18 @@ pytestmark = pytest.mark.gpu
 T_STEP = 0.37 * 10800.0
 F64_TOL = 1e-10
 F32_TOL = 1e-5
+# Float32 fields: the floor of the criterion's denominator has to stay above the rounding of the field itself.  A net flux
+# that is the average of two neighbouring stresses of opposite sign carries an absolute error of eps(Float32) = 6e-8 of
+# the field's scale; with the Float64 floor (1e-6 of the scale) that alone would be a relative error of 6e-2.
+F32_FLOOR = 1e-2
+# Conditioning of the criterion in Float64.  The latent heat and vapour fluxes are proportional to Δq = qₐ − qₛ and q_sat
+# comes out of pow/exp: two correct Float64 evaluations of it differ by a few ulp (the reference's own q_sat has that
+# uncertainty: oracle vs the 50-digit restatement, 40 ulp; tests/test_oracle_independent_pin.py).  Where |Δq| is 1e-6 of
+# its scale, 3 ulp of qₛ ≈ 0.02 are 7e-18 / 1e-8 = 7e-10 of the flux: the criterion's floor sits BELOW what Float64 can
+# resolve for these two fields.  At most this many points per field may therefore miss 1e-10, every one of them must lie
+# where the field is below 1e-4 of its scale (next to a sign change of Δq or Δθ), and none may miss 1e-8.
+NEAR_ZERO_STRAGGLERS = 40
+NEAR_ZERO_STRAGGLER_TOL = 1e-8
 # Float32 q_sat (Float32 thermodynamics): both sides evaluate the Float32 pow / exp in Float64 and round once, through
 # different Float64 libraries.  The two Float32 results differ when the Float64 values straddle a rounding boundary
 # (probability ~1e-8 per call); such a point then carries one Float32 ulp (6e-8) of q_sat into its fluxes.
@@ -31,16 +43,24 @@ MIXED_STRAGGLERS = 8
 MIXED_STRAGGLER_TOL = 2e-6
 
 
-def _check_bags(tag, ref, dev, backend, bags, tol, mask_ring=None, mask_inner=None, stragglers=0, straggler_tol=0.0):
+def _check_bags(tag, ref, dev, backend, bags, tol, mask_ring=None, mask_inner=None, stragglers=0, straggler_tol=0.0, floor=1e-6):
+    """Every field of every bag under the pointwise criterion.  Points that miss `tol`: (i) at most NEAR_ZERO_STRAGGLERS per
+    field where the field is within 1e-4 of a sign change, bounded by 1e-8 (Float64 conditioning, see above); (ii)
+    `stragglers` more anywhere, bounded by `straggler_tol` (Float32 q_sat double-rounding events, mixed precision only)."""
     worst = 0.0
     for name, ring in bags:
         res = compare_pointwise(getattr(ref, name), getattr(dev, name), ref.grid, backend, with_halo_ring=ring, tol=tol,
-                                mask=(mask_ring if ring else mask_inner))
+                                mask=(mask_ring if ring else mask_inner), floor=floor)
         for n, r in res.items():
-            ParityLog.add(tag, bag=name, field=n, max_pointwise_rel=r["pw"], points=r["n"], exceed_tol=r["exceed"], tol=tol)
+            ParityLog.add(tag, bag=name, field=n, max_pointwise_rel=r["pw"], points=r["n"], exceed_tol=r["exceed"],
+                          exceed_tol_near_sign_change=r["exceed_near_zero"], tol=tol, floor=floor)
             worst = max(worst, r["pw"])
-            if r["exceed"] > stragglers or (r["exceed"] and r["pw"] > straggler_tol):
-                raise AssertionError(f"{tag}: {name}.{n}: max pointwise relative error {r['pw']:.3e}, {r['exceed']} points above {tol}")
+            elsewhere = r["exceed"] - r["exceed_near_zero"]
+            ok = (r["exceed_near_zero"] <= NEAR_ZERO_STRAGGLERS and elsewhere <= stragglers and
+                  (r["exceed"] == 0 or r["pw"] <= max(straggler_tol if elsewhere else 0.0, NEAR_ZERO_STRAGGLER_TOL * (tol / F64_TOL))))
+            if not ok:
+                raise AssertionError(f"{tag}: {name}.{n}: max pointwise relative error {r['pw']:.3e}, {r['exceed']} points above {tol} "
+                                     f"({r['exceed_near_zero']} of them next to a sign change of the field)")
     return worst
 
 
@@ -187,7 +207,7 @@ def test_C2_float32_model_pointwise(oracle_lib, cuda_backend, cuda_lib):
     both = np.maximum(ref.ao_iterations, cuda_backend.to_numpy(dev.ao_iterations))
     m_ring, m_inner = converged_mask(both, g, 100, True), converged_mask(both, g, 100, False)
     worst = _check_bags(tag, ref, dev, cuda_backend, [("ao_fluxes", True), ("net_ocean", False), ("rad_fluxes_ocean", False)],
-                        F32_TOL, mask_ring=m_ring, mask_inner=m_inner, stragglers=40, straggler_tol=1e-3)
+                        F32_TOL, mask_ring=m_ring, mask_inner=m_inner, floor=F32_FLOOR)
     st = trip_statistics(it_r, it_d, 100)
     ParityLog.add(tag, summary=True, worst_pointwise_rel_converged=worst, excluded_limit_cycle_points=int((~m_ring).sum()), **st)
     assert abs(st["maxiter_points_ref"] - st["maxiter_points_dev"]) <= 0.005 * st["solved_points"]

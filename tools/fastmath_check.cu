@@ -147,8 +147,13 @@ int main() {
     }
   }
   auto iv = [](double z) { bool o; int i = fm::psi_interval(z, o); return o ? -1 : i; };
-  int iv_ok = iv(-128.0) == -1 && iv(128.0) == -1 && iv(0.5) == fm::PSI_NS + 21 && iv(0.0) == fm::PSI_NS && iv(-1e-300) == 0 &&
-              iv(-0.015625) == 1 && iv(-127.9) == fm::PSI_NQ && iv(NAN) == -1 && iv(-1e300) == -1 && iv(0.015) == fm::PSI_NS &&
+  // geometry-independent statements of the interval logic: 2^PSI_OCT_LO opens record 1, 0.5 = 2^-1 opens the first record
+  // of its octave, everything below 2^PSI_OCT_LO shares record 0, |ζ| ≥ 2^7 and NaN are outside
+  const double lo = std::ldexp(1.0, fm::PSI_OCT_LO);
+  int iv_ok = iv(-128.0) == -1 && iv(128.0) == -1 && iv(0.5) == fm::PSI_NS + 1 + fm::PSI_SUB * (-1 - fm::PSI_OCT_LO) &&
+              iv(0.0) == fm::PSI_NS && iv(-1e-300) == 0 &&
+              iv(-lo) == 1 && iv(-127.9) == fm::PSI_NQ && iv(NAN) == -1 && iv(-1e300) == -1 && iv(0.96 * lo) == fm::PSI_NS &&
+              iv(lo * (1.0 + 1.0 / fm::PSI_SUB)) == fm::PSI_NS + 2 &&
               iv(127.9) == fm::PSI_NS + fm::PSI_NQ &&
               fm::psi_is_tiny(std::ldexp(0.99, fm::TINY_EXP)) && !fm::psi_is_tiny(std::ldexp(1.0, fm::TINY_EXP)) && fm::psi_is_tiny(-1e-9) && !fm::psi_is_tiny(NAN);
   double e_tiny = 0;
