@@ -4,19 +4,24 @@
 // SimilarityTheoryFluxes defaults + BulkTemperature + scalar surface/boundary-layer heights; every other tree keeps
 // the kernels of ne_flux_kernels.cu.  See ne_flux_tab2.cuh for what changed in the iteration.
 //
-// Launch shape: 256-thread CTAs, 3 per SM (80 registers); a CTA stages the 27 KB solver table in shared memory once
-// and walks 1024-point windows of the launch range with a grid stride; inside a window the 32 groups of 32 points
-// are dealt to the 8 warps in a snake order (w, 15−w, 16+w, 31−w) and the warps never synchronise again.
+// Launch shape: 256-thread CTAs, 3 per SM (80 registers); a CTA stages the 44 KB solver table in shared memory and
+// takes one window of W = 1024 points of the launch range (the hardware's CTA scheduler balances the load, whatever the
+// land mask looks like); the window's 32 groups of 32 points are dealt to the 8 warps in a snake order and the warps
+// never synchronise again.
 //
-// Trip-count ordering.  A warp iterates until its slowest lane has converged: with the points in memory order 18 %
-// of the lane-trips of C4 are idle lanes (trip counts 7–24, mean 13.6).  The trip count of a point changes little
-// from one coupled step to the next, and the kernel stores it (`iterations`), so before the solve
-// `trip_order_kernel` counting-sorts every 1024-point window by the PREVIOUS step's count (a permutation of window
-// offsets, 2 bytes per point, in a library-owned scratch buffer keyed by the `iterations` pointer) and lane l of
-// group g takes the point perm[32 g + l]: idle lane-trips fall to 3 %.  Which lane computes a point does not change
-// its arithmetic: results are bit-identical with and without the ordering (tested), and a stale or all-zero
-// `iterations` array (first step) only costs the speed-up.  Loads and stores of a group are scattered over the 8 KB
-// (per field) of its window instead of 256 contiguous bytes: L1/L2 absorb it, DRAM traffic stays the algorithmic one.
+// Ordering of the points.  Two properties of a warp decide what it costs: (i) it iterates until its SLOWEST lane has
+// converged — in memory order 18 % of the lane-trips of C4 are idle lanes (trip counts 7–24, mean 13.6); (ii) every trip
+// gathers 11 x 16 bytes per lane from the lane's ψ-table record, and lanes on different records whose 16-byte chunks share
+// banks serialise in the L1TEX data pipe, the unit that bounds this kernel (ncu: 74-88 % of its peak, 40 % of the
+// shared-memory wavefronts are bank conflicts; FP64 pipe 53 %).  Both the trip count and the table record of a point change
+// little from one coupled step to the next, so the kernel leaves a 16-bit hint per point (trips << 8 | record of its last
+// trip) in a library-owned scratch array, and before the next solve `trip_order_kernel` counting-sorts every window of W
+// points by that hint (a permutation of window offsets, 2 bytes per point): lane l of group g takes the point
+// perm[32 g + l].  The lanes of a warp then leave the loop together (idle lane-trips 3 %) and read the same or adjacent
+// records (adjacent records never share banks: the record stride is an odd number of 16-byte chunks).  Which lane
+// computes a point does not change its arithmetic: results are bit-identical with and without the ordering (tested); a
+// stale or zero hint (first step) only costs the speed-up.  Loads and stores of a group are scattered over the window
+// (8 KB per field for W = 1024) instead of 256 contiguous bytes: L1/L2 absorb it.
 #include <deque>
 #include <mutex>
 
@@ -25,49 +30,58 @@
 
 namespace ne {
 
-constexpr int TAB2_KEYS = 64;
+constexpr int TAB2_TRIP_BITS = 5, TAB2_REC_BITS = 8;
+constexpr int TAB2_BINS = 1 << (TAB2_TRIP_BITS + TAB2_REC_BITS);   // 8192 bins: (min(trips, 31), record)
+static_assert(fm::PSI_NI <= (1 << TAB2_REC_BITS), "the record index must fit the hint");
 
-// Counting sort of every W-point window of the launch range by the previous step's trip count: perm[window * W + k] =
-// offset (within the window) of the point with the k-th smallest count.  One 256-thread block per window.
+__device__ __forceinline__ uint16_t tab2_hint(int trips, int record) {
+  const int t = trips < 0 ? 0 : (trips > (1 << TAB2_TRIP_BITS) - 1 ? (1 << TAB2_TRIP_BITS) - 1 : trips);
+  return (uint16_t)((t << TAB2_REC_BITS) | (record & ((1 << TAB2_REC_BITS) - 1)));
+}
+
+// Counting sort of every W-point window of the launch range by the previous step's hint: perm[window * W + k] = offset
+// (within the window) of the point with the k-th smallest (trips, record).  One 256-thread block per window.
 template <int W>
 __global__ void __launch_bounds__(256)
-trip_order_kernel(const int32_t* __restrict__ iterations, const __grid_constant__ Layout L, const uint32_t n,
-                  uint16_t* __restrict__ perm) {
-  constexpr int PER = W / 256;
-  __shared__ int hist[TAB2_KEYS];
-  __shared__ int base[TAB2_KEYS];
+trip_order_kernel(const uint16_t* __restrict__ hint, const uint32_t n, uint16_t* __restrict__ perm) {
+  constexpr int PER = W / 256, BPT = TAB2_BINS / 256;
+  __shared__ int hist[TAB2_BINS];
+  __shared__ int part[256];
   const int tid = threadIdx.x;
-  if (tid < TAB2_KEYS) hist[tid] = 0;
+#pragma unroll
+  for (int k = 0; k < BPT; ++k) hist[tid + 256 * k] = 0;
   __syncthreads();
   const uint32_t t0 = blockIdx.x * (uint32_t)W;
   int key[PER], rank[PER];
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
     const uint32_t t = t0 + tid + 256 * k;
-    int kk = TAB2_KEYS - 1;                    // beyond the launch range: last
-    if (t < n) {
-      const uint32_t jj = t / (uint32_t)L.ni;
-      const int v = iterations[L.at(L.i_lo + (int32_t)(t - jj * (uint32_t)L.ni), L.j_lo + (int32_t)jj)];
-      kk = v < 0 ? 0 : (v > TAB2_KEYS - 2 ? TAB2_KEYS - 2 : v);
-    }
-    key[k] = kk;
-    rank[k] = atomicAdd(&hist[kk], 1);
+    key[k] = t < n ? (int)hint[t] : TAB2_BINS - 1;     // beyond the launch range: last
+    rank[k] = atomicAdd(&hist[key[k]], 1);
   }
   __syncthreads();
-  if (tid < 32) {   // exclusive scan of the 64 bins by one warp
-    const int a = hist[2 * tid], b = hist[2 * tid + 1];
-    int s = a + b;
+  // exclusive scan of the bins: thread t owns bins [t BPT, (t + 1) BPT)
+  int sum = 0;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, s, off);
-      if (tid >= off) s += v;
-    }
-    base[2 * tid] = s - a - b;
-    base[2 * tid + 1] = s - b;
+  for (int k = 0; k < BPT; ++k) sum += hist[tid * BPT + k];
+  part[tid] = sum;
+  __syncthreads();
+  for (int off = 1; off < 256; off <<= 1) {
+    const int v = tid >= off ? part[tid - off] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  int run = part[tid] - sum;
+#pragma unroll
+  for (int k = 0; k < BPT; ++k) {
+    const int c = hist[tid * BPT + k];
+    hist[tid * BPT + k] = run;
+    run += c;
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < PER; ++k) perm[t0 + base[key[k]] + rank[k]] = (uint16_t)(tid + 256 * k);
+  for (int k = 0; k < PER; ++k) perm[t0 + hist[key[k]] + rank[k]] = (uint16_t)(tid + 256 * k);
 }
 
 // NW warps per CTA (8: 80 registers at 3 CTAs per SM; 7: 96 registers, no spills), W points per window.
@@ -76,7 +90,7 @@ __global__ void __maxnreg__(NW == 8 ? 80 : 96)
 ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_constant__ Layout L,
                     const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P,
                     const __grid_constant__ TabParams T, const __grid_constant__ Micro Mi, const double* __restrict__ gtab,
-                    const uint16_t* __restrict__ perm, unsigned long long* __restrict__ counts) {
+                    const uint16_t* __restrict__ perm, uint16_t* __restrict__ hint, unsigned long long* __restrict__ counts) {
   constexpr int NT = NW * 32, GROUPS = W / 32;
   extern __shared__ __align__(16) double tab[];   // fm::TAB_SIZE doubles (dynamic: see allow_table_smem)
   __shared__ double park[6][NT];
@@ -120,7 +134,9 @@ ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
           FastPoint s;
           tab2_invariants(o, d, th, P, T, tab, k, k.du, k.dv, So, s);
           park[0][tid] = k.du; park[1][tid] = k.dv; park[2][tid] = k.Ta; park[3][tid] = k.pa; park[4][tid] = k.qa; park[5][tid] = k.Ts;
-          iters = tab2_solve(o, P, T, Mi, tab, s, counts);
+          int record;
+          iters = tab2_solve(o, P, T, Mi, tab, s, counts, record);
+          if (hint) hint[t] = tab2_hint(iters, record);
           ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
           k.du = park[0][tid]; k.dv = park[1][tid]; k.Ta = park[2][tid]; k.pa = park[3][tid]; k.qa = park[4][tid]; k.Ts = park[5][tid];
           if (!std::is_same<O, fm::OpsPlain>::value) {   // warp trips = the slowest lane's, once per group
@@ -129,6 +145,7 @@ ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
             if (lane == __ffs(solving) - 1) warp_trips += mx;
           }
         }
+        else if (hint) hint[t] = 0;
         tab2_epilogue<O, CT>(o, d, th, idx, celsius, not_water, k, ustar, theta_star, q_star, iters);
       }
     }
@@ -140,35 +157,43 @@ ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------
-// Scratch permutation buffers, one per (device, iterations array, launch extent), allocated on first use (outside
-// CUDA-graph capture, like the solver tables) and kept for the life of the process.
-struct OrderBuf { int device; const void* key; uint32_t n; uint16_t* perm; };
+// Scratch of the ordering, one per (device, output array, launch extent): the permutation and the hints, 2 + 2 bytes per
+// point, allocated and zeroed on first use (outside CUDA-graph capture, like the solver tables) and kept for the life
+// of the process.  Keyed by the friction-velocity output array and the launch range: two steps that write the same
+// outputs over the same range share their hints.
+struct OrderBuf { int device; const void* key; uint32_t n; int64_t i_lo, j_lo; uint16_t* perm; uint16_t* hint; };
 static std::mutex g_order_mutex;
 static std::deque<OrderBuf> g_order;
 
-static uint16_t* order_buffer(const void* key, uint32_t n) {
+static const OrderBuf* order_buffer(const void* key, uint32_t n, int64_t i_lo, int64_t j_lo) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lock(g_order_mutex);
   for (const OrderBuf& b : g_order)
-    if (b.device == dev && b.key == key && b.n == n) return b.perm;
-  if (g_order.size() >= 64) {   // a host that keeps re-allocating its `iterations` array: start over
+    if (b.device == dev && b.key == key && b.n == n && b.i_lo == i_lo && b.j_lo == j_lo) return &b;
+  if (g_order.size() >= 64) {   // a host that keeps re-allocating its output arrays: start over
     for (OrderBuf& b : g_order) cudaFree(b.perm);
     g_order.clear();
   }
-  OrderBuf b{dev, key, n, nullptr};
-  const size_t windows = ((size_t)n + 1023) / 1024;
-  if (cudaMalloc(&b.perm, windows * 1024 * sizeof(uint16_t)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  OrderBuf b{dev, key, n, i_lo, j_lo, nullptr, nullptr};
+  const size_t padded = (((size_t)n + 1023) / 1024) * 1024;
+  if (cudaMalloc(&b.perm, 2 * padded * sizeof(uint16_t)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  b.hint = b.perm + padded;
+  if (cudaMemset(b.perm, 0, 2 * padded * sizeof(uint16_t)) != cudaSuccess) { cudaGetLastError(); cudaFree(b.perm); return nullptr; }
   g_order.push_back(b);
-  return b.perm;
+  return &g_order.back();
 }
 
 static unsigned tab2_grid(uint32_t n_windows, int window) {
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // resident CTAs x waves; a wave of 256-point windows is a quarter of the work of a wave of 1024-point ones
-  const int waves = std::max(1, env_int("NE_B200_TAB_WAVES", 8 * 1024 / window / 4));
+  // one window per CTA by default: the hardware hands CTAs to SMs as they drain, which balances the load whatever the
+  // land mask looks like (measured on C4: 888 / 1776 / 7100 CTAs of 1024-point windows: 1.59 / 1.72 / 1.52 ms;
+  // staging the 44 KB table per CTA is < 1 % of a window's work).  NE_B200_TAB_WAVES = n caps the grid at n resident waves.
+  (void)window;
+  const int waves = env_int("NE_B200_TAB_WAVES", 0);
+  if (waves <= 0) return (unsigned)std::max<uint32_t>(1u, n_windows);
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>(n_windows, (int64_t)sms * 3 * waves));
 }
 
@@ -183,10 +208,10 @@ bool tab2_eligible(const NeAtmosOceanDesc& d, const TabParams& TP) {
 
 template <class CT, int NW, int W>
 static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P, const TabParams& TP, const Micro& Mi,
-                         const double* tab, cudaStream_t s, unsigned long long* counts, uint16_t* perm, uint32_t n) {
+                         const double* tab, cudaStream_t s, unsigned long long* counts, uint16_t* perm, uint16_t* hint, uint32_t n) {
   const uint32_t n_windows = (n + W - 1) / W;
   if (perm) {
-    trip_order_kernel<W><<<n_windows, 256, 0, s>>>(d.iterations, L, n, perm);
+    trip_order_kernel<W><<<n_windows, 256, 0, s>>>(hint, n, perm);
     NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(trip order)");
   }
   const unsigned grid = tab2_grid(n_windows, W);
@@ -195,7 +220,7 @@ static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastP
   do {                                                                                                                         \
     if (cudaError_t e = allow_table_smem<ao_flux_tab2_kernel<CT, SORT, NW, W, O>>(); e != cudaSuccess)                         \
       return cuda_error(e, "ne_atmosphere_ocean_fluxes(tab2: shared memory opt-in)");                                          \
-    ao_flux_tab2_kernel<CT, SORT, NW, W, O><<<grid, NW * 32, TAB_SMEM_BYTES, s>>>(d, L, th, P, TP, Mi, tab, perm, counts);     \
+    ao_flux_tab2_kernel<CT, SORT, NW, W, O><<<grid, NW * 32, TAB_SMEM_BYTES, s>>>(d, L, th, P, TP, Mi, tab, perm, hint, counts); \
   } while (0)
   if (counts) {
     if (perm) NE_TAB2_GO(true, fm::OpsCount); else NE_TAB2_GO(false, fm::OpsCount);
@@ -216,15 +241,16 @@ int launch_tab2(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P,
   Micro Mi;
   for (int side = 0; side < 2; ++side)
     for (int k = 0; k < fm::MICRO_REC; ++k) Mi.rec[side][k] = host_tab[fm::TAB_MICRO + side * fm::MICRO_REC + k];
-  uint16_t* perm = nullptr;
-  if (d.iterations && !env_flag("NE_B200_TAB2_NO_ORDER")) perm = order_buffer(d.iterations, n);
+  uint16_t *perm = nullptr, *hint = nullptr;
+  if (!env_flag("NE_B200_TAB2_NO_ORDER"))
+    if (const OrderBuf* ob = order_buffer(d.friction_velocity, n, d.grid.i_lo, d.grid.j_lo)) { perm = ob->perm; hint = ob->hint; }
   // development knobs (profiles/r02_notes.md): warps per CTA and window size of the shipped configuration
   const int nw = env_int("NE_B200_TAB2_WARPS", 8), win = env_int("NE_B200_TAB2_WINDOW", 1024);
 #define NE_TAB2_W(CT, NW)                                                                          \
   do {                                                                                             \
-    if (win == 256) return launch_tab2_t<CT, NW, 256>(d, L, P, TP, Mi, tab, s, counts, perm, n);   \
-    if (win == 512) return launch_tab2_t<CT, NW, 512>(d, L, P, TP, Mi, tab, s, counts, perm, n);   \
-    return launch_tab2_t<CT, NW, 1024>(d, L, P, TP, Mi, tab, s, counts, perm, n);                  \
+    if (win == 256) return launch_tab2_t<CT, NW, 256>(d, L, P, TP, Mi, tab, s, counts, perm, hint, n);   \
+    if (win == 512) return launch_tab2_t<CT, NW, 512>(d, L, P, TP, Mi, tab, s, counts, perm, hint, n);   \
+    return launch_tab2_t<CT, NW, 1024>(d, L, P, TP, Mi, tab, s, counts, perm, hint, n);                  \
   } while (0)
   if (ct64) { if (nw == 7) NE_TAB2_W(double, 7); else NE_TAB2_W(double, 8); }
   else { if (nw == 7) NE_TAB2_W(float, 7); else NE_TAB2_W(float, 8); }

@@ -126,7 +126,7 @@ struct Micro { double rec[2][fm::MICRO_REC]; };
 
 template <class O>
 __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const TabParams& T, const Micro& Mi, const double* tab,
-                                               FastPoint& s, unsigned long long* counts) {
+                                               FastPoint& s, unsigned long long* counts, int& record) {
   using fm::dmax;
   using fm::dmin;
   // b★, gustiness, U (similarity_theory…:354-358, 417-425)
@@ -154,6 +154,7 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
   const double zh = o.mul(dh, Linv);
   bool outside;
   const int iv = fm::psi_interval(zh, outside);
+  record = iv;
   double pm_h, ps_h;
   fm::psi_pair(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(zh), pm_h, ps_h);
   // ψ(ℓ/L★): always from the |ζ| < 2^-12 record of the side of L★.  The two records also sit in the kernel-parameter
@@ -192,9 +193,11 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
 }
 
 // compute_interface_state.jl:10-18: the first trip always runs; then until drift < tol or it ≥ maxiter
+// `record`: the ψ(Δh/L★) table record of the last trip (the next step's ordering hint)
 template <class O>
 __device__ __forceinline__ int tab2_solve(O& o, const FastParams& P, const TabParams& T, const Micro& Mi, const double* tab,
-                                          FastPoint& s, unsigned long long* counts) {
+                                          FastPoint& s, unsigned long long* counts, int& record) {
+  record = 0;
   if (P.fixed && P.maxiter <= 0) return 0;
   const double tol = P.fixed ? -1.0 : P.tol;
   const int maxiter = P.maxiter;
@@ -202,7 +205,7 @@ __device__ __forceinline__ int tab2_solve(O& o, const FastParams& P, const TabPa
   double drift;
   do {
     const double pu = s.ustar, pt = s.theta_star, pq = s.q_star;
-    tab2_iteration(o, P, T, Mi, tab, s, counts);
+    tab2_iteration(o, P, T, Mi, tab, s, counts, record);
     drift = o.add(o.add(fabs(o.sub(s.ustar, pu)), fabs(o.sub(s.theta_star, pt))), fabs(o.sub(s.q_star, pq)));
     ++it;
     o.trip();

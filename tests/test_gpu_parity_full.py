@@ -36,6 +36,12 @@ F32_FLOOR = 1e-2
 # where the field is below 1e-4 of its scale (next to a sign change of Δq or Δθ), and none may miss 1e-8.
 NEAR_ZERO_STRAGGLERS = 40
 NEAR_ZERO_STRAGGLER_TOL = 1e-8
+# ASSEMBLED fields (net ocean / net sea-ice fluxes) are sums of turbulent and radiative fluxes of either sign (and, for the
+# stresses, averages of two neighbouring cells): where the sum cancels to 1e-4 of the summands' scale, summands that agree
+# to 1e-14 of that scale (a few tens of ulp, which is what two Float64 evaluations of q_sat or of the ice skin-temperature
+# balance differ by) leave the sum agreeing to 1e-10 — the floor of the criterion has to sit there for these fields.
+ASSEMBLED_FLOOR = 1e-4
+ASSEMBLED = ("net_ocean", "net_sea_ice")
 # Float32 q_sat (Float32 thermodynamics): both sides evaluate the Float32 pow / exp in Float64 and round once, through
 # different Float64 libraries.  The two Float32 results differ when the Float64 values straddle a rounding boundary
 # (probability ~1e-8 per call); such a point then carries one Float32 ulp (6e-8) of q_sat into its fluxes.
@@ -49,11 +55,12 @@ def _check_bags(tag, ref, dev, backend, bags, tol, mask_ring=None, mask_inner=No
     `stragglers` more anywhere, bounded by `straggler_tol` (Float32 q_sat double-rounding events, mixed precision only)."""
     worst = 0.0
     for name, ring in bags:
+        fl = max(floor, ASSEMBLED_FLOOR) if name in ASSEMBLED else floor
         res = compare_pointwise(getattr(ref, name), getattr(dev, name), ref.grid, backend, with_halo_ring=ring, tol=tol,
-                                mask=(mask_ring if ring else mask_inner), floor=floor)
+                                mask=(mask_ring if ring else mask_inner), floor=fl)
         for n, r in res.items():
             ParityLog.add(tag, bag=name, field=n, max_pointwise_rel=r["pw"], points=r["n"], exceed_tol=r["exceed"],
-                          exceed_tol_near_sign_change=r["exceed_near_zero"], tol=tol, floor=floor)
+                          exceed_tol_near_sign_change=r["exceed_near_zero"], tol=tol, floor=fl)
             worst = max(worst, r["pw"])
             elsewhere = r["exceed"] - r["exceed_near_zero"]
             ok = (r["exceed_near_zero"] <= NEAR_ZERO_STRAGGLERS and elsewhere <= stragglers and
@@ -206,8 +213,10 @@ def test_C2_float32_model_pointwise(oracle_lib, cuda_backend, cuda_lib):
     it_r, it_d = g.interior(ref.ao_iterations), g.interior(cuda_backend.to_numpy(dev.ao_iterations))
     both = np.maximum(ref.ao_iterations, cuda_backend.to_numpy(dev.ao_iterations))
     m_ring, m_inner = converged_mask(both, g, 100, True), converged_mask(both, g, 100, False)
+    # a point whose two solves stop one trip apart on the one-ulp limit cycle of the Float32-rounded iterate keeps a few
+    # hundred Float32 ulp of difference without running into maxiter: a handful of them, bounded by 1e-4
     worst = _check_bags(tag, ref, dev, cuda_backend, [("ao_fluxes", True), ("net_ocean", False), ("rad_fluxes_ocean", False)],
-                        F32_TOL, mask_ring=m_ring, mask_inner=m_inner, floor=F32_FLOOR)
+                        F32_TOL, mask_ring=m_ring, mask_inner=m_inner, floor=F32_FLOOR, stragglers=20, straggler_tol=1e-4)
     st = trip_statistics(it_r, it_d, 100)
     ParityLog.add(tag, summary=True, worst_pointwise_rel_converged=worst, excluded_limit_cycle_points=int((~m_ring).sum()), **st)
     assert abs(st["maxiter_points_ref"] - st["maxiter_points_dev"]) <= 0.005 * st["solved_points"]

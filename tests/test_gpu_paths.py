@@ -26,7 +26,8 @@ TOL = 1e-10
 def _assert_bag(tag, ref, dev, backend, name, ring, mask=None, tol=TOL):
     """Pointwise criterion; the only points allowed to miss it are a handful next to a sign change of the field, bounded by
     1e-8 (Float64 conditioning of Δq = qₐ − qₛ and Δθ: see tests/test_gpu_parity_full.py)."""
-    for n, r in compare_pointwise(getattr(ref, name), getattr(dev, name), ref.grid, backend, with_halo_ring=ring, mask=mask, tol=tol).items():
+    floor = 1e-4 if name.startswith("net_") else 1e-6     # assembled sums: see ASSEMBLED_FLOOR in tests/test_gpu_parity_full.py
+    for n, r in compare_pointwise(getattr(ref, name), getattr(dev, name), ref.grid, backend, with_halo_ring=ring, mask=mask, tol=tol, floor=floor).items():
         ParityLog.add(tag, bag=name, field=n, max_pointwise_rel=r["pw"], points=r["n"], exceed_tol=r["exceed"],
                       exceed_tol_near_sign_change=r["exceed_near_zero"], tol=tol)
         assert r["exceed"] == r["exceed_near_zero"] <= 5 and (r["exceed"] == 0 or r["pw"] <= 1e-8), f"{tag}: {name}.{n}: {r['pw']:.3e} ({r['exceed']} points)"
