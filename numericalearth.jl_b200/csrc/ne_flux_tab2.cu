@@ -30,8 +30,7 @@
 
 namespace ne {
 
-constexpr int TAB2_TRIP_BITS = 5, TAB2_REC_BITS = 8;
-constexpr int TAB2_BINS = 1 << (TAB2_TRIP_BITS + TAB2_REC_BITS);   // 8192 bins: (min(trips, 31), record)
+constexpr int TAB2_TRIP_BITS = 5, TAB2_REC_BITS = 8;                // hint = (min(trips, 31), record): 13 bits
 static_assert(fm::PSI_NI <= (1 << TAB2_REC_BITS), "the record index must fit the hint");
 
 __device__ __forceinline__ uint16_t tab2_hint(int trips, int record) {
@@ -39,49 +38,43 @@ __device__ __forceinline__ uint16_t tab2_hint(int trips, int record) {
   return (uint16_t)((t << TAB2_REC_BITS) | (record & ((1 << TAB2_REC_BITS) - 1)));
 }
 
-// Counting sort of every W-point window of the launch range by the previous step's hint: perm[window * W + k] = offset
-// (within the window) of the point with the k-th smallest (trips, record).  One 256-thread block per window.
+// Sort of every W-point window of the launch range by the previous step's hint: perm[window * W + k] = offset (within the
+// window) of the point with the k-th smallest (trips, record).  One block of W/4 threads per window, bitonic network in
+// shared memory on (hint << 10 | offset): stable, deterministic, no atomics; ~10 us for the 7100 windows of C4.
 template <int W>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(W / 4)
 trip_order_kernel(const uint16_t* __restrict__ hint, const uint32_t n, uint16_t* __restrict__ perm) {
-  constexpr int PER = W / 256, BPT = TAB2_BINS / 256;
-  __shared__ int hist[TAB2_BINS];
-  __shared__ int part[256];
+  constexpr int NT = W / 4;
+  __shared__ uint32_t a[W];
   const int tid = threadIdx.x;
-#pragma unroll
-  for (int k = 0; k < BPT; ++k) hist[tid + 256 * k] = 0;
-  __syncthreads();
   const uint32_t t0 = blockIdx.x * (uint32_t)W;
-  int key[PER], rank[PER];
 #pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    const uint32_t t = t0 + tid + 256 * k;
-    key[k] = t < n ? (int)hint[t] : TAB2_BINS - 1;     // beyond the launch range: last
-    rank[k] = atomicAdd(&hist[key[k]], 1);
+  for (int k = 0; k < 4; ++k) {
+    const int i = tid + NT * k;
+    const uint32_t t = t0 + i;
+    const uint32_t h = t < n ? (uint32_t)hint[t] : 0xffffu;     // beyond the launch range: last
+    a[i] = (h << 10) | (uint32_t)i;
   }
   __syncthreads();
-  // exclusive scan of the bins: thread t owns bins [t BPT, (t + 1) BPT)
-  int sum = 0;
+  for (int size = 2; size <= W; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
 #pragma unroll
-  for (int k = 0; k < BPT; ++k) sum += hist[tid * BPT + k];
-  part[tid] = sum;
-  __syncthreads();
-  for (int off = 1; off < 256; off <<= 1) {
-    const int v = tid >= off ? part[tid - off] : 0;
-    __syncthreads();
-    part[tid] += v;
-    __syncthreads();
+      for (int k = 0; k < 2; ++k) {
+        const int c = tid + NT * k;                                   // comparator index, W/2 per stage
+        const int i = 2 * c - (c & (stride - 1));                     // lower element of the pair
+        const int j = i + stride;
+        const bool up = (i & size) == 0;
+        const uint32_t x = a[i], y = a[j];
+        if ((x > y) == up) { a[i] = y; a[j] = x; }
+      }
+      __syncthreads();
+    }
   }
-  int run = part[tid] - sum;
 #pragma unroll
-  for (int k = 0; k < BPT; ++k) {
-    const int c = hist[tid * BPT + k];
-    hist[tid * BPT + k] = run;
-    run += c;
+  for (int k = 0; k < 4; ++k) {
+    const int i = tid + NT * k;
+    perm[t0 + i] = (uint16_t)(a[i] & 1023u);
   }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < PER; ++k) perm[t0 + hist[key[k]] + rank[k]] = (uint16_t)(tid + 256 * k);
 }
 
 // NW warps per CTA (8: 80 registers at 3 CTAs per SM; 7: 96 registers, no spills), W points per window.
@@ -93,7 +86,7 @@ ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
                     const uint16_t* __restrict__ perm, uint16_t* __restrict__ hint, unsigned long long* __restrict__ counts) {
   constexpr int NT = NW * 32, GROUPS = W / 32;
   extern __shared__ __align__(16) double tab[];   // fm::TAB_SIZE doubles (dynamic: see allow_table_smem)
-  __shared__ double park[6][NT];
+  __shared__ double park[8][NT];
   for (int k = threadIdx.x; k < fm::TAB_SIZE / 2; k += NT)
     reinterpret_cast<double2*>(tab)[k] = __ldg(reinterpret_cast<const double2*>(gtab) + k);
   __syncthreads();
@@ -103,6 +96,7 @@ ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
   const bool celsius = d.ocean.temperature_units == NE_DEGREES_CELSIUS;
   const bool relative = d.properties.velocity_formulation == NE_VEL_RELATIVE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const Tab2Heights H = {d.boundary_layer_height.value, d.surface_layer_height.value - P.d_zero, T.log_hd};
   unsigned long long warp_trips = 0;
   for (uint32_t w = blockIdx.x; w < n_windows; w += gridDim.x) {
     // the (sorted) window's groups are dealt to the warps in a snake (…, NW−1, NW−1, …, 0): every warp gets cheap and
@@ -131,11 +125,11 @@ ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
         double So;
         tab2_load<true>(d, L, idx, celsius, relative, not_water, k, So);
         if (solve) {
-          FastPoint s;
-          tab2_invariants(o, d, th, P, T, tab, k, k.du, k.dv, So, s);
+          Tab2Point s;
+          tab2_invariants(o, d, th, P, T, tab, k, So, s, &park[6][tid], &park[7][tid]);
           park[0][tid] = k.du; park[1][tid] = k.dv; park[2][tid] = k.Ta; park[3][tid] = k.pa; park[4][tid] = k.qa; park[5][tid] = k.Ts;
           int record;
-          iters = tab2_solve(o, P, T, Mi, tab, s, counts, record);
+          iters = tab2_solve(o, P, T, Mi, tab, H, s, &park[6][tid], &park[7][tid], counts, record);
           if (hint) hint[t] = tab2_hint(iters, record);
           ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
           k.du = park[0][tid]; k.dv = park[1][tid]; k.Ta = park[2][tid]; k.pa = park[3][tid]; k.qa = park[4][tid]; k.Ts = park[5][tid];
@@ -211,7 +205,7 @@ static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastP
                          const double* tab, cudaStream_t s, unsigned long long* counts, uint16_t* perm, uint16_t* hint, uint32_t n) {
   const uint32_t n_windows = (n + W - 1) / W;
   if (perm) {
-    trip_order_kernel<W><<<n_windows, 256, 0, s>>>(hint, n, perm);
+    trip_order_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm);
     NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(trip order)");
   }
   const unsigned grid = tab2_grid(n_windows, W);

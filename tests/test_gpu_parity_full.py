@@ -145,6 +145,11 @@ def test_C3_ocean_sea_ice_step_full_size(oracle_lib, cuda_backend, cuda_lib, atm
     # points whose sea-ice solve sits on a limit cycle of the fixed-point map (they stop at maxiter = 100 on either side)
     # amplify last-ulp differences: compared apart, loosely; their number is on record
     both = np.maximum(it, it_dev)
+    # the bar is "1e-10 at the same iteration count": a point whose two solves stop one trip apart (rate below 1e-3, recorded
+    # below) differs by what one more trip changes, ~1e-9 with tol = 1e-8 — such points join the loosely bounded set
+    apart = (np.asarray(ref.asi_iterations) != cuda_backend.to_numpy(dev.asi_iterations)) | \
+            (np.asarray(ref.ao_iterations) != cuda_backend.to_numpy(dev.ao_iterations))
+    both = np.where(apart, 100, both)
     m_ring, m_inner = converged_mask(both, g, 100, True), converged_mask(both, g, 100, False)
     mixed = atm_FT == "f32"
     ref.ao_T = _temperature_bag(ref); dev.ao_T = _temperature_bag(dev)
@@ -168,7 +173,7 @@ def test_C3_ocean_sea_ice_step_full_size(oracle_lib, cuda_backend, cuda_lib, atm
     st_ao = trip_statistics(g.interior(ref.ao_iterations), g.interior(cuda_backend.to_numpy(dev.ao_iterations)), 100)
     ParityLog.add(tag, summary=True, worst_pointwise_rel_converged=worst, skin_temperature_max_abs_diff_K=dT,
                   worst_field_rel_including_limit_cycle_points=loose, sea_ice=st_ice, ocean=st_ao,
-                  excluded_limit_cycle_points=int((~m_ring).sum()))
+                  excluded_limit_cycle_or_trip_mismatch_points=int((~m_ring).sum()), trip_mismatch_points=int(g.interior(apart).sum()))
     assert dT <= 1e-8
     assert loose <= 1e-3
     assert st_ice["trip_mismatch_rate"] <= 1e-3 and st_ao["trip_mismatch_rate"] <= 2e-4, (st_ice, st_ao)

@@ -101,6 +101,7 @@ def test_extension_uses_only_existing_structs_fields_and_constants():
     structs, consts = _parse_julia_structs()
     text = _ext_text()
     code = "\n".join(line.split("#")[0] for line in text.splitlines())   # (no '#' inside strings in this file)
+    code = re.sub(r'"(?:\\.|[^"\\])*"', '""', code)                       # names inside string literals (ENV keys) are not code
     for name in set(re.findall(r"\b(Ne[A-Z]\w+)\b", code)):
         assert name in structs, f"extension mentions unknown struct {name}"
     for c in set(re.findall(r"\b(NE_[A-Z0-9_]+)\b", code)):
@@ -157,7 +158,8 @@ def test_extension_delimiters_balance():
     code = re.sub(r'"(?:\\.|[^"\\])*"', '""', code)
     for o, c in ("()", "[]", "{}"):
         assert code.count(o) == code.count(c), f"unbalanced {o}{c}: {code.count(o)} vs {code.count(c)}"
-    opens = len(re.findall(r"^\s*(?:function|if|for|while|let|module|struct|mutable struct|begin|try|do|quote|macro)\b|\bdo\s*$|\bbegin\s*$", code, flags=re.M))
+    opens = len(re.findall(r"^\s*(?:function|if|for|while|let|module|struct|mutable struct|begin|try|quote|macro)\b", code, flags=re.M))
+    opens += len(re.findall(r"\bdo\b", code))                               # `f(args) do x … end`
     opens += len(re.findall(r"=\s*(?:if|begin|let|try)\b", code))
     ends = len(re.findall(r"\bend\b", code))
     assert opens == ends, f"block openers {opens} vs `end` {ends}"
