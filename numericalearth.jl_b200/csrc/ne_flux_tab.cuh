@@ -22,6 +22,8 @@ struct TabParams {
   int32_t general_psi;   // tables fitted to non-Edson stability functions: outside the table → generic closed forms
   int32_t f32_model;     // Float32 model: the generic closed forms take the Float32-rounded parameters
   int32_t far_fm;        // Edson far-unstable closed forms through the branch-free functions (set per launch)
+  // Edson stable closed forms above ζ_sat = max(ζmax/A⁺)(1 + 1e-12): both exponentials equal exp(−ζmax) (ne_flux_tab2.cuh)
+  double z_sat, em_sat, es_sat;
 };
 
 // ---- host: Chebyshev interpolation → monomials in w ∈ [−1, 1] (long double) -------------------------
@@ -130,6 +132,7 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
     tab[TAB_LOG + 2 * i] = invc;
     tab[TAB_LOG + 2 * i + 1] = (double)(-logl((long double)invc));
   }
+  for (int j = 0; j < EXP2_N; ++j) tab[TAB_EXP2 + j] = (double)exp2l((long double)j / EXP2_N);
   fill_literals(T.mc);
   for (int k = 0; k < LOG_DEG; ++k) T.mc.logp[k] = ((k & 1) ? 1.0 : -1.0) / (double)(k + 2);   // −1/2, +1/3, −1/4 …
   {  // e^r on |r| ≤ 0.35, monomials in r
@@ -255,6 +258,12 @@ inline double build_solver_tables(const NeFluxFormulation& f, double* tab, TabPa
   T.f32_model = f32 ? 1 : 0;
   T.far_fm = 0;
   T.log_hd = 0;
+  T.z_sat = INFINITY; T.em_sat = T.es_sat = 0;
+  if (!general && pm[1] > 0 && ps[1] > 0) {
+    T.z_sat = std::fmax(pm[0] / pm[1], ps[0] / ps[1]) * (1 + 1e-12);
+    T.em_sat = fm::exp_mid(T.mc, -pm[0]);   // the same operations as on the device: the same bits
+    T.es_sat = fm::exp_mid(T.mc, -ps[0]);
+  }
   return worst;
 }
 

@@ -4,24 +4,22 @@
 // SimilarityTheoryFluxes defaults + BulkTemperature + scalar surface/boundary-layer heights; every other tree keeps
 // the kernels of ne_flux_kernels.cu.  See ne_flux_tab2.cuh for what changed in the iteration.
 //
-// Launch shape: 256-thread CTAs, 3 per SM (80 registers); a CTA stages the 44 KB solver table in shared memory and
-// takes one window of W = 1024 points of the launch range (the hardware's CTA scheduler balances the load, whatever the
-// land mask looks like); the window's 32 groups of 32 points are dealt to the 8 warps in a snake order and the warps
-// never synchronise again.
+// Launch shape: persistent 256-thread CTAs, 3 per SM (80 registers); a CTA stages the 44 KB solver table in shared memory
+// once, then each of its warps draws groups of 32 points from a global counter (so the load balances itself whatever the
+// land mask and the trip counts look like) and the warps never synchronise again.
 //
 // Ordering of the points.  Two properties of a warp decide what it costs: (i) it iterates until its SLOWEST lane has
 // converged — in memory order 18 % of the lane-trips of C4 are idle lanes (trip counts 7–24, mean 13.6); (ii) every trip
 // gathers 11 x 16 bytes per lane from the lane's ψ-table record, and lanes on different records whose 16-byte chunks share
-// banks serialise in the L1TEX data pipe, the unit that bounds this kernel (ncu: 74-88 % of its peak, 40 % of the
-// shared-memory wavefronts are bank conflicts; FP64 pipe 53 %).  Both the trip count and the table record of a point change
-// little from one coupled step to the next, so the kernel leaves a 16-bit hint per point (trips << 8 | record of its last
-// trip) in a library-owned scratch array, and before the next solve `trip_order_kernel` counting-sorts every window of W
-// points by that hint (a permutation of window offsets, 2 bytes per point): lane l of group g takes the point
-// perm[32 g + l].  The lanes of a warp then leave the loop together (idle lane-trips 3 %) and read the same or adjacent
-// records (adjacent records never share banks: the record stride is an odd number of 16-byte chunks).  Which lane
-// computes a point does not change its arithmetic: results are bit-identical with and without the ordering (tested); a
-// stale or zero hint (first step) only costs the speed-up.  Loads and stores of a group are scattered over the window
-// (8 KB per field for W = 1024) instead of 256 contiguous bytes: L1/L2 absorb it.
+// banks serialise in the L1TEX data pipe.  Both the trip count and the table record of a point change little from one
+// coupled step to the next, so the kernel leaves a 16-bit hint per point (trips << 8 | record of its last trip) in a
+// library-owned scratch array, and before the next solve `trip_order_kernel` sorts every window of W = 1024 points by that
+// hint (a permutation of window offsets, 2 bytes per point): lane l of group g takes the point perm[32 g + l].  The lanes
+// of a warp then leave the loop together (idle lane-trips 3 %) and read the same or adjacent records (adjacent records
+// never share banks: the record stride is an odd number of 16-byte chunks).  Which lane computes a point does not change
+// its arithmetic: results are bit-identical with and without the ordering (tested); a stale or zero hint (first step) only
+// costs the speed-up.  Loads and stores of a group are scattered over the window (8 KB per field) instead of 256
+// contiguous bytes: L1/L2 absorb it.
 #include <deque>
 #include <mutex>
 
@@ -30,6 +28,7 @@
 
 namespace ne {
 
+constexpr int TAB2_WINDOW = 1024;
 constexpr int TAB2_TRIP_BITS = 5, TAB2_REC_BITS = 8;                // hint = (min(trips, 31), record): 13 bits
 static_assert(fm::PSI_NI <= (1 << TAB2_REC_BITS), "the record index must fit the hint");
 
@@ -77,71 +76,79 @@ trip_order_kernel(const uint16_t* __restrict__ hint, const uint32_t n, uint16_t*
   }
 }
 
-// NW warps per CTA (8: 80 registers at 3 CTAs per SM; 7: 96 registers, no spills), W points per window.
-template <class CT, bool SORT, int NW, int W, class O>
-__global__ void __maxnreg__(NW == 8 ? 80 : 96)
+// 8 warps per CTA, 3 CTAs per SM (80 registers), persistent: a CTA stages the table once; its warps then draw groups of 32
+// sorted points from a global counter until the launch range is exhausted and never synchronise.  (Round 2 first shipped
+// one 1024-point window per CTA: the table was staged 7100 times per C4 launch and a CTA's fast warps idled until its
+// slowest one had finished — 15 % of the warp slots, ncu `sm__warps_active` 32 % of a possible 37.5 %.)
+template <class CT, bool SORT, class O>
+__global__ void __launch_bounds__(256, 3)
 ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_constant__ Layout L,
                     const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P,
                     const __grid_constant__ TabParams T, const __grid_constant__ Micro Mi, const double* __restrict__ gtab,
-                    const uint16_t* __restrict__ perm, uint16_t* __restrict__ hint, unsigned long long* __restrict__ counts) {
-  constexpr int NT = NW * 32, GROUPS = W / 32;
+                    const uint16_t* __restrict__ perm, uint16_t* __restrict__ hint, unsigned long long* __restrict__ counts,
+                    uint32_t* __restrict__ next_group) {
+  constexpr int NT = 256, W = TAB2_WINDOW;
   extern __shared__ __align__(16) double tab[];   // fm::TAB_SIZE doubles (dynamic: see allow_table_smem)
-  __shared__ double park[8][NT];
+  __shared__ double park[SL_COUNT][NT];
   for (int k = threadIdx.x; k < fm::TAB_SIZE / 2; k += NT)
     reinterpret_cast<double2*>(tab)[k] = __ldg(reinterpret_cast<const double2*>(gtab) + k);
   __syncthreads();
   O o;
   const uint32_t n = (uint32_t)L.ni * (uint32_t)L.nj;
-  const uint32_t n_windows = (n + W - 1) / W;
+  const uint32_t n_groups = ((n + W - 1) / W) * (W / 32);
   const bool celsius = d.ocean.temperature_units == NE_DEGREES_CELSIUS;
   const bool relative = d.properties.velocity_formulation == NE_VEL_RELATIVE;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int lane = threadIdx.x & 31, tid = threadIdx.x;
+  double* const col = &park[0][tid];
   const Tab2Heights H = {d.boundary_layer_height.value, d.surface_layer_height.value - P.d_zero, T.log_hd};
   unsigned long long warp_trips = 0;
-  for (uint32_t w = blockIdx.x; w < n_windows; w += gridDim.x) {
-    // the (sorted) window's groups are dealt to the warps in a snake (…, NW−1, NW−1, …, 0): every warp gets cheap and
-    // expensive groups; the starting warp rotates with the window so that no warp is always the one with a group more
-    const int r0 = (warp + (int)(w % NW)) % NW;
+  auto grab = [&]() {
+    uint32_t v = 0;
+    if (lane == 0) v = atomicAdd(next_group, 1u);
+    return __shfl_sync(0xffffffffu, v, 0);
+  };
+  // the next group index is requested one group ahead: its latency hides behind the solve in between
+  uint32_t g = grab();
+  uint32_t g_next = g < n_groups ? grab() : g;
 #pragma unroll 1
-    for (int pass = 0; pass * NW < GROUPS; ++pass) {
-      const int g = pass * NW + ((pass & 1) ? NW - 1 - r0 : r0);
-      if (g >= GROUPS) continue;
-      const uint32_t slot = w * (uint32_t)W + (uint32_t)(g * 32 + lane);
-      const uint32_t t = SORT ? w * (uint32_t)W + perm[slot] : slot;
-      const bool valid = t < n;
-      int64_t idx = 0;
-      bool not_water = true;
-      if (valid) {
-        const uint32_t jj = t / (uint32_t)L.ni;
-        idx = L.at(L.i_lo + (int32_t)(t - jj * (uint32_t)L.ni), L.j_lo + (int32_t)jj);
-        not_water = d.inactive ? (d.inactive[idx] != 0) : false;
-      }
-      const bool solve = valid && !(not_water && !P.fixed);   // needs_to_converge && not_water: no solve (atmosphere_ocean_fluxes.jl:144)
-      const unsigned solving = __ballot_sync(0xffffffffu, solve);   // all 32 lanes are converged here (loop head)
-      double ustar = 0, theta_star = 0, q_star = 0;
-      int iters = 0;
-      if (valid) {
-        Parked k;
-        double So;
-        tab2_load<true>(d, L, idx, celsius, relative, not_water, k, So);
-        if (solve) {
-          Tab2Point s;
-          tab2_invariants(o, d, th, P, T, tab, k, So, s, &park[6][tid], &park[7][tid]);
-          park[0][tid] = k.du; park[1][tid] = k.dv; park[2][tid] = k.Ta; park[3][tid] = k.pa; park[4][tid] = k.qa; park[5][tid] = k.Ts;
-          int record;
-          iters = tab2_solve(o, P, T, Mi, tab, H, s, &park[6][tid], &park[7][tid], counts, record);
-          if (hint) hint[t] = tab2_hint(iters, record);
-          ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
-          k.du = park[0][tid]; k.dv = park[1][tid]; k.Ta = park[2][tid]; k.pa = park[3][tid]; k.qa = park[4][tid]; k.Ts = park[5][tid];
-          if (!std::is_same<O, fm::OpsPlain>::value) {   // warp trips = the slowest lane's, once per group
-            __syncwarp(solving);
-            const int mx = __reduce_max_sync(solving, iters);
-            if (lane == __ffs(solving) - 1) warp_trips += mx;
-          }
+  while (g < n_groups) {
+    const uint32_t slot = g * 32u + (uint32_t)lane;                       // position in the (sorted) launch range
+    const uint32_t t = SORT ? (slot & ~(uint32_t)(W - 1)) + perm[slot] : slot;
+    g = g_next;
+    if (g < n_groups) g_next = grab();
+    const bool valid = t < n;
+    int64_t idx = 0;
+    bool not_water = true;
+    if (valid) {
+      const uint32_t jj = t / (uint32_t)L.ni;
+      idx = L.at(L.i_lo + (int32_t)(t - jj * (uint32_t)L.ni), L.j_lo + (int32_t)jj);
+      not_water = d.inactive ? (d.inactive[idx] != 0) : false;
+    }
+    const bool solve = valid && !(not_water && !P.fixed);   // needs_to_converge && not_water: no solve (atmosphere_ocean_fluxes.jl:144)
+    const unsigned solving = __ballot_sync(0xffffffffu, solve);   // all 32 lanes are converged here (loop head)
+    double ustar = 0, theta_star = 0, q_star = 0;
+    int iters = 0;
+    if (valid) {
+      Parked k;
+      double So;
+      tab2_load<true>(d, L, idx, celsius, relative, not_water, k, So);
+      if (solve) {
+        Tab2Point s;
+        tab2_invariants<NT>(o, d, th, P, T, tab, k, So, s, col);
+        col[SL_DU * NT] = k.du; col[SL_DV * NT] = k.dv; col[SL_TA * NT] = k.Ta; col[SL_PA * NT] = k.pa; col[SL_QA * NT] = k.qa; col[SL_TS * NT] = k.Ts;
+        int record;
+        iters = tab2_solve<NT>(o, P, T, Mi, tab, H, s, col, counts, record);
+        if (hint) hint[t] = tab2_hint(iters, record);
+        ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
+        k.du = col[SL_DU * NT]; k.dv = col[SL_DV * NT]; k.Ta = col[SL_TA * NT]; k.pa = col[SL_PA * NT]; k.qa = col[SL_QA * NT]; k.Ts = col[SL_TS * NT];
+        if (!std::is_same<O, fm::OpsPlain>::value) {   // warp trips = the slowest lane's, once per group
+          __syncwarp(solving);
+          const int mx = __reduce_max_sync(solving, iters);
+          if (lane == __ffs(solving) - 1) warp_trips += mx;
         }
-        else if (hint) hint[t] = 0;
-        tab2_epilogue<O, CT>(o, d, th, idx, celsius, not_water, k, ustar, theta_star, q_star, iters);
       }
+      else if (hint) hint[t] = 0;
+      tab2_epilogue<O, CT>(o, d, th, idx, celsius, not_water, k, ustar, theta_star, q_star, iters);
     }
   }
   if (!std::is_same<O, fm::OpsPlain>::value) {
@@ -178,43 +185,60 @@ static const OrderBuf* order_buffer(const void* key, uint32_t n, int64_t i_lo, i
   return &g_order.back();
 }
 
-static unsigned tab2_grid(uint32_t n_windows, int window) {
+
+// Group counters: a per-device pool used round robin; the launch zeroes its counter on its own stream right before the
+// kernel (a memset node under CUDA-graph capture), so an aborted launch cannot poison a later one.
+constexpr int TAB2_COUNTER_SLOTS = 1024;
+static uint32_t* tab2_counter() {
+  struct Pool { int device; uint32_t* dptr; unsigned next; };
+  static std::mutex mutex;
+  static std::deque<Pool> pools;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mutex);
+  for (Pool& q : pools)
+    if (q.device == dev) return q.dptr + (q.next++ % TAB2_COUNTER_SLOTS);
+  Pool q = {dev, nullptr, 1};
+  if (cudaMalloc(&q.dptr, sizeof(uint32_t) * TAB2_COUNTER_SLOTS) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  pools.push_back(q);
+  return q.dptr;
+}
+
+static unsigned tab2_grid(uint32_t n_groups) {
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // one window per CTA by default: the hardware hands CTAs to SMs as they drain, which balances the load whatever the
-  // land mask looks like (measured on C4: 888 / 1776 / 7100 CTAs of 1024-point windows: 1.59 / 1.72 / 1.52 ms;
-  // staging the 44 KB table per CTA is < 1 % of a window's work).  NE_B200_TAB_WAVES = n caps the grid at n resident waves.
-  (void)window;
-  const int waves = env_int("NE_B200_TAB_WAVES", 0);
-  if (waves <= 0) return (unsigned)std::max<uint32_t>(1u, n_windows);
-  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(n_windows, (int64_t)sms * 3 * waves));
+  const uint32_t ctas_needed = (n_groups + 7) / 8;
+  return std::max(1u, std::min<uint32_t>(ctas_needed, (uint32_t)sms * 3u));
 }
-
-constexpr int TAB2_MAX_WINDOW = 1024;
 
 bool tab2_eligible(const NeAtmosOceanDesc& d, const TabParams& TP) {
   if (env_flag("NE_B200_TAB_V1")) return false;
   if (TP.general_psi || d.surface_layer_height.ptr || d.boundary_layer_height.ptr) return false;
   const int64_t n = (int64_t)(d.grid.i_hi - d.grid.i_lo + 1) * (int64_t)(d.grid.j_hi - d.grid.j_lo + 1);
-  return n > 0 && n < ((int64_t)1 << 31) - TAB2_MAX_WINDOW;
+  return n > 0 && n < ((int64_t)1 << 31) - TAB2_WINDOW;
 }
 
-template <class CT, int NW, int W>
+template <class CT>
 static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P, const TabParams& TP, const Micro& Mi,
                          const double* tab, cudaStream_t s, unsigned long long* counts, uint16_t* perm, uint16_t* hint, uint32_t n) {
+  constexpr int W = TAB2_WINDOW;
   const uint32_t n_windows = (n + W - 1) / W;
+  uint32_t* counter = tab2_counter();
+  NE_REQUIRE(counter != nullptr, "atmosphere-ocean: could not allocate the group counter");
+  if (cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s); e != cudaSuccess)
+    return cuda_error(e, "ne_atmosphere_ocean_fluxes(tab2: counter reset)");
   if (perm) {
     trip_order_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm);
     NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(trip order)");
   }
-  const unsigned grid = tab2_grid(n_windows, W);
+  const unsigned grid = tab2_grid(n_windows * (W / 32));
   const Thermo<CT> th = Thermo<CT>::make(d.thermo);
-#define NE_TAB2_GO(SORT, O)                                                                                                    \
-  do {                                                                                                                         \
-    if (cudaError_t e = allow_table_smem<ao_flux_tab2_kernel<CT, SORT, NW, W, O>>(); e != cudaSuccess)                         \
-      return cuda_error(e, "ne_atmosphere_ocean_fluxes(tab2: shared memory opt-in)");                                          \
-    ao_flux_tab2_kernel<CT, SORT, NW, W, O><<<grid, NW * 32, TAB_SMEM_BYTES, s>>>(d, L, th, P, TP, Mi, tab, perm, hint, counts); \
+#define NE_TAB2_GO(SORT, O)                                                                                              \
+  do {                                                                                                                   \
+    if (cudaError_t e = allow_table_smem<ao_flux_tab2_kernel<CT, SORT, O>>(); e != cudaSuccess)                          \
+      return cuda_error(e, "ne_atmosphere_ocean_fluxes(tab2: shared memory opt-in)");                                    \
+    ao_flux_tab2_kernel<CT, SORT, O><<<grid, 256, TAB_SMEM_BYTES, s>>>(d, L, th, P, TP, Mi, tab, perm, hint, counts, counter); \
   } while (0)
   if (counts) {
     if (perm) NE_TAB2_GO(true, fm::OpsCount); else NE_TAB2_GO(false, fm::OpsCount);
@@ -231,24 +255,14 @@ static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastP
 int launch_tab2(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P, const TabParams& TP, const double* tab,
                 const double* host_tab, cudaStream_t s, unsigned long long* counts) {
   const uint32_t n = (uint32_t)L.ni * (uint32_t)L.nj;
-  const bool ct64 = d.thermo.dtype == NE_F64;
   Micro Mi;
   for (int side = 0; side < 2; ++side)
     for (int k = 0; k < fm::MICRO_REC; ++k) Mi.rec[side][k] = host_tab[fm::TAB_MICRO + side * fm::MICRO_REC + k];
   uint16_t *perm = nullptr, *hint = nullptr;
   if (!env_flag("NE_B200_TAB2_NO_ORDER"))
     if (const OrderBuf* ob = order_buffer(d.friction_velocity, n, d.grid.i_lo, d.grid.j_lo)) { perm = ob->perm; hint = ob->hint; }
-  // development knobs (profiles/r02_notes.md): warps per CTA and window size of the shipped configuration
-  const int nw = env_int("NE_B200_TAB2_WARPS", 8), win = env_int("NE_B200_TAB2_WINDOW", 1024);
-#define NE_TAB2_W(CT, NW)                                                                          \
-  do {                                                                                             \
-    if (win == 256) return launch_tab2_t<CT, NW, 256>(d, L, P, TP, Mi, tab, s, counts, perm, hint, n);   \
-    if (win == 512) return launch_tab2_t<CT, NW, 512>(d, L, P, TP, Mi, tab, s, counts, perm, hint, n);   \
-    return launch_tab2_t<CT, NW, 1024>(d, L, P, TP, Mi, tab, s, counts, perm, hint, n);                  \
-  } while (0)
-  if (ct64) { if (nw == 7) NE_TAB2_W(double, 7); else NE_TAB2_W(double, 8); }
-  else { if (nw == 7) NE_TAB2_W(float, 7); else NE_TAB2_W(float, 8); }
-#undef NE_TAB2_W
+  if (d.thermo.dtype == NE_F64) return launch_tab2_t<double>(d, L, P, TP, Mi, tab, s, counts, perm, hint, n);
+  return launch_tab2_t<float>(d, L, P, TP, Mi, tab, s, counts, perm, hint, n);
 }
 
 }  // namespace ne

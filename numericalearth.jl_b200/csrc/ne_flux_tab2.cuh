@@ -44,13 +44,14 @@ template <class O> __device__ __forceinline__ double atan_large(O& o, double x) 
 }  // namespace fm
 
 // ---- rare ψ paths -----------------------------------------------------------------------------------------
+// `which`: 0 = ψ_m only, 1 = ψ_s only, 2 = both (the half that is not asked for is not evaluated)
 // Edson unstable closed forms for ζ ≤ −2^7 (similarity_theory_turbulent_fluxes.jl:501-532, 586-618), B⁻ = 2
 template <class O>
 __device__ __forceinline__ void tab2_psi_far_unstable(O& o, const FastParams& P, const TabParams& T, const double* tab,
-                                                      double z, double& pm, double& ps) {
+                                                      double z, int which, double& pm, double& ps) {
   const double z2 = o.mul(z, z);
   const double fw = o.sub(1.0, fm::rcp(o, o.add(1.0, z2)));                      // ζ²/(1 + ζ²)
-  {  // momentum
+  if (which != 1) {  // momentum
     const double f1 = fm::sqrt_pos(o, fm::sqrt_pos(o, o.fma(-P.m_Am, z, 1.0)));
     const double f1s = o.mul(f1, f1), f1p = o.add(1.0, f1);
     const double arg = o.mul(o.mul(o.mul(f1p, f1p), o.add(1.0, f1s)), 0.125);
@@ -61,7 +62,7 @@ __device__ __forceinline__ void tab2_psi_far_unstable(O& o, const FastParams& P,
     const double psi2 = o.add(o.fma(-P.m_rEm, a2, o.mul(P.m_halfEm, l2)), P.m_Fm);
     pm = o.fma(fw, o.sub(psi2, psi1), psi1);
   }
-  {  // scalar
+  if (which != 0) {  // scalar
     const double f1 = fm::sqrt_pos(o, o.fma(-P.s_Am, z, 1.0));
     const double psi1 = o.fma(P.s_Bm, fm::log_pos(o, tab, T.mc, o.mul(o.add(1.0, f1), P.s_iBm)), P.s_Cm);
     const double f2 = fm::cbrt_pos(o, T.mc, o.fma(-P.s_Dm, z, 1.0));
@@ -72,28 +73,37 @@ __device__ __forceinline__ void tab2_psi_far_unstable(O& o, const FastParams& P,
   }
 }
 
-// stable closed forms (ζ ≥ 2^7: the tables cover the rest) with the branch-free exp / sqrt (:519-531, 605-617)
+// stable closed forms (ζ ≥ 2^7: the tables cover the rest) with the branch-free exp / sqrt (:519-531, 605-617).  Every
+// solve starts from u★ = θ★ = q★ = 1e-4 (atmosphere_ocean_fluxes.jl:131-137), i.e. from b★ > 0 and ζ ~ 1e5: its first
+// trips evaluate ψ(Δh/L★), ψ(ℓu/L★) and ψ(ℓs/L★) HERE, where both exponentials have long saturated at
+// exp(−ζmax) — above ζ_sat = max(ζmax/A⁺) they are the two constants T.em_sat, T.es_sat (the same bits exp_mid returns)
 template <class O>
-__device__ __forceinline__ void tab2_psi_stable(O& o, const FastParams& P, const TabParams& T, double z, double& pm, double& ps) {
-  const double em = fm::exp_mid(o, T.mc, -fm::dmin(P.m_zmax, o.mul(P.m_Ap, z)));
-  const double es = T.same_exp ? em : fm::exp_mid(o, T.mc, -fm::dmin(P.s_zmax, o.mul(P.s_Ap, z)));
-  pm = o.sub(o.fma(-o.mul(P.m_Cp, o.sub(z, P.m_Dp)), em, -o.mul(P.m_Bp, z)), P.m_CpDp);
-  const double x = o.fma(P.s_Bp, z, 1.0);
-  double xp;
-  if (P.s_C15) xp = o.mul(x, fm::sqrt_pos(o, x));
-  else { xp = pow_general(x, P.s_Cp); o.other(60); }
-  ps = o.sub(o.fma(-o.mul(P.s_Bp, o.sub(z, P.s_Dp)), es, -xp), P.s_Ep);
+__device__ __forceinline__ void tab2_psi_stable(O& o, const FastParams& P, const TabParams& T, double z, int which, double& pm, double& ps) {
+  double em, es;
+  if (z >= T.z_sat) { em = T.em_sat; es = T.es_sat; }
+  else {
+    em = fm::exp_mid(o, T.mc, -fm::dmin(P.m_zmax, o.mul(P.m_Ap, z)));
+    es = T.same_exp ? em : fm::exp_mid(o, T.mc, -fm::dmin(P.s_zmax, o.mul(P.s_Ap, z)));
+  }
+  if (which != 1) pm = o.sub(o.fma(-o.mul(P.m_Cp, o.sub(z, P.m_Dp)), em, -o.mul(P.m_Bp, z)), P.m_CpDp);
+  if (which != 0) {
+    const double x = o.fma(P.s_Bp, z, 1.0);
+    double xp;
+    if (P.s_C15) xp = o.mul(x, fm::sqrt_pos(o, x));
+    else { xp = pow_general(x, P.s_Cp); o.other(60); }
+    ps = o.sub(o.fma(-o.mul(P.s_Bp, o.sub(z, P.s_Dp)), es, -xp), P.s_Ep);
+  }
 }
 
 // Out of line, own policy object (an ops reference would force the caller's counters into local memory); the
 // counting instantiation adds its operations to the launch's global counters itself.
 template <class O>
 static __device__ __noinline__ double2 tab2_psi_outside(const FastParams& P, const TabParams& T, const double* tab, double z,
-                                                        unsigned long long* counts) {
+                                                        int which, unsigned long long* counts) {
   O o;
-  double pm, ps;
-  if (z > 0) tab2_psi_stable(o, P, T, z, pm, ps);
-  else if (T.far_fm) tab2_psi_far_unstable(o, P, T, tab, z, pm, ps);
+  double pm = 0, ps = 0;
+  if (z > 0) tab2_psi_stable(o, P, T, z, which, pm, ps);
+  else if (T.far_fm) tab2_psi_far_unstable(o, P, T, tab, z, which, pm, ps);
   else { psi_far_unstable(P, z, pm, ps); o.other(700); }
   o.flush(counts);
   return make_double2(pm, ps);
@@ -111,10 +121,10 @@ static __device__ __noinline__ double2 tab2_psi_small(const FastParams& P, const
     bool outside;
     int iv = fm::psi_interval(zu, outside);
     if (!outside) pm = fm::psi_single(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(zu), 0);
-    else pm = tab2_psi_outside<O>(P, T, tab, zu, counts).x;
+    else pm = tab2_psi_outside<O>(P, T, tab, zu, 0, counts).x;
     iv = fm::psi_interval(zs, outside);
     if (!outside) ps = fm::psi_single(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(zs), 1);
-    else ps = tab2_psi_outside<O>(P, T, tab, zs, counts).y;
+    else ps = tab2_psi_outside<O>(P, T, tab, zs, 1, counts).y;
   }
   o.flush(counts);
   return make_double2(pm, ps);
@@ -124,29 +134,34 @@ static __device__ __noinline__ double2 tab2_psi_small(const FastParams& P, const
 // the two |ζ| < 2^-12 records (unstable, stable) as a kernel parameter: constant-bank operands
 struct Micro { double rec[2][fm::MICRO_REC]; };
 
-// What a thread keeps in registers across the loop: the iterate and three invariants.  b★ = g/𝒯ₛ (θ★ (1 + δqₛ) + δ𝒯ₛ q★)
-// is evaluated as A θ★ + B q★ with A = g/𝒯ₛ (1 + δqₛ), B = g/𝒯ₛ δ𝒯ₛ formed once; Δθ and Δq, needed only by the last two
-// multiplications of a trip, wait in shared memory (`dth`, `dqq`: the thread's own slots).  With the surface-layer and
-// boundary-layer heights uniform (kernel parameters) that is 12 registers of loop-carried state instead of 24: the
-// 80-register build no longer spills inside the loop (the spill reloads were a third of its long-scoreboard stalls).
-struct Tab2Point { double A, B, dudv2, ustar, theta_star, q_star; };
+// What a thread keeps in registers across the loop: the iterate and b★ = g/𝒯ₛ (θ★ (1 + δqₛ) + δ𝒯ₛ q★), evaluated at the END
+// of a trip as A θ★ + B q★ with A = g/𝒯ₛ (1 + δqₛ), B = g/𝒯ₛ δ𝒯ₛ formed once.  The per-point invariants wait in the
+// thread's own column of shared memory (conflict-free 64-bit accesses) and are read where a trip needs them — A, B, Δθ, Δq
+// in its last four multiplications, Δu² + Δv² under the cube root: 8 registers of loop-carried state instead of 24 (the
+// 80-register build of round 1 reloaded three spilled doubles at the head of every trip: a third of its long-scoreboard
+// stalls).  Slots of the column (stride NT doubles):
+enum { SL_DU, SL_DV, SL_TA, SL_PA, SL_QA, SL_TS, SL_DTH, SL_DQ, SL_A, SL_B, SL_DUDV2, SL_COUNT };
+struct Tab2Point { double ustar, theta_star, q_star, bstar; };
 struct Tab2Heights { double h_bl, hd, log_hd; };
 
-template <class O>
+// a shared-memory read the compiler may not hoist out of the loop (hoisting is what spills)
+__device__ __forceinline__ double slot_ld(const double* p) { return *(const volatile double*)p; }
+
+template <int NT, class O>
 __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const TabParams& T, const Micro& Mi, const double* tab,
-                                               const Tab2Heights& H, Tab2Point& s, const double* dth, const double* dqq,
+                                               const Tab2Heights& H, Tab2Point& s, const double* col,
                                                unsigned long long* counts, int& record) {
   using fm::dmax;
   using fm::dmin;
   // b★, gustiness, U (similarity_theory…:354-358, 417-425)
-  const double bstar = o.fma(s.A, s.theta_star, o.mul(s.B, s.q_star));
+  const double bstar = s.bstar;
   const double Jb = -o.mul(s.ustar, bstar);
   // U_G = max(floor, β ∛(max(0, J_b) h_bl)) is its floor wherever the buoyancy flux is not destabilising: a warp whose lanes
   // are all stable (trip-ordered lanes share the stability regime) skips the cube root — same bits, 25 instructions fewer
   double UG = P.gmin;
   if (__any_sync(__activemask(), Jb > 0.0))
     UG = dmax(P.gmin, o.mul(P.beta, fm::cbrt_pos(o, T.mc, dmax(o.mul(dmax(0.0, Jb), H.h_bl), T.cbrt_floor))));
-  const double U = fm::sqrt_pos(o, o.fma(UG, UG, s.dudv2));
+  const double U = fm::sqrt_pos(o, o.fma(UG, UG, slot_ld(col + SL_DUDV2 * NT)));
   // roughness lengths (roughness_lengths.jl:197-246) and 1/L★
   const double ru = fm::rcp(o, s.ustar);
   const double lu = dmin(o.fma(o.mul(P.a1, s.ustar), s.ustar, o.mul(P.a2, ru)), P.lmax);
@@ -157,7 +172,8 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
   const double log_ls_un = o.fma(-P.rb, log_Rs, P.log_rA);
   const bool clipped = log_ls_un > P.log_ls_max;
   const double log_ls = clipped ? P.log_ls_max : log_ls_un;
-  const double ls_un = fm::exp_mid(o, T.mc, dmax(log_ls_un, -700.0));
+  // ℓs itself only scales the argument of ψ_s(ℓs/L★), |ψ| < 1e-3 against Π_s ~ 10: the short exponential (2e-12) is ample
+  const double ls_un = fm::exp_lo(o, tab, T.mc, dmax(log_ls_un, -700.0));
   const double ls = clipped ? P.ls_max : ls_un;
   const double lu2 = o.add(lu, lu);
   const bool lifted = lu2 > H.hd;                                    // Δh = max(Δh − d, 2ℓu) (:313)
@@ -172,8 +188,7 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
   fm::psi_pair(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(zh), pm_h, ps_h);
   // ψ(ℓ/L★): always from the |ζ| < 2^-12 record of the side of L★.  The two records also sit in the kernel-parameter
   // constant bank (Micro): a warp whose lanes are all on one side — nearly every warp, L★ varies smoothly in space —
-  // takes its coefficients from there and issues no shared-memory load for this lookup (7 LDS.128 = 28 wavefronts of
-  // the ~100 a trip puts on the L1TEX data pipe, the unit that bounds this kernel)
+  // takes its coefficients from there and issues no shared-memory load for this lookup
   const double zu = o.mul(lu, Linv), zs = o.mul(ls, Linv);
   double pm_l, ps_l;
   {
@@ -185,7 +200,7 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
     else fm::psi_micro_pair(o, tab + fm::TAB_MICRO + (unstable ? 0 : fm::MICRO_REC), fabs(zu), fabs(zs), pm_l, ps_l);
   }
   if (outside) {
-    const double2 r = tab2_psi_outside<O>(P, T, tab, zh, counts);
+    const double2 r = tab2_psi_outside<O>(P, T, tab, zh, 2, counts);
     pm_h = r.x; ps_h = r.y;
   }
   if (!(fm::psi_is_micro(zu) && fm::psi_is_micro(zs))) {
@@ -201,15 +216,16 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
   chi_u = o.fma(o.fma(-Pi_u, chi_u, P.kappa), ru_, chi_u);
   chi_s = o.fma(o.fma(-Pi_s, chi_s, P.kappa), rs_, chi_s);
   s.ustar = o.mul(chi_u, U);
-  s.theta_star = o.mul(chi_s, *dth);
-  s.q_star = o.mul(chi_s, *dqq);
+  s.theta_star = o.mul(chi_s, slot_ld(col + SL_DTH * NT));
+  s.q_star = o.mul(chi_s, slot_ld(col + SL_DQ * NT));
+  s.bstar = o.fma(slot_ld(col + SL_A * NT), s.theta_star, o.mul(slot_ld(col + SL_B * NT), s.q_star));
 }
 
 // compute_interface_state.jl:10-18: the first trip always runs; then until drift < tol or it ≥ maxiter
 // `record`: the ψ(Δh/L★) table record of the last trip (the next step's ordering hint)
-template <class O>
+template <int NT, class O>
 __device__ __forceinline__ int tab2_solve(O& o, const FastParams& P, const TabParams& T, const Micro& Mi, const double* tab,
-                                          const Tab2Heights& H, Tab2Point& s, const double* dth, const double* dqq,
+                                          const Tab2Heights& H, Tab2Point& s, const double* col,
                                           unsigned long long* counts, int& record) {
   record = 0;
   if (P.fixed && P.maxiter <= 0) return 0;
@@ -219,7 +235,7 @@ __device__ __forceinline__ int tab2_solve(O& o, const FastParams& P, const TabPa
   double drift;
   do {
     const double pu = s.ustar, pt = s.theta_star, pq = s.q_star;
-    tab2_iteration(o, P, T, Mi, tab, H, s, dth, dqq, counts, record);
+    tab2_iteration<NT>(o, P, T, Mi, tab, H, s, col, counts, record);
     drift = o.add(o.add(fabs(o.sub(s.ustar, pu)), fabs(o.sub(s.theta_star, pt))), fabs(o.sub(s.q_star, pq)));
     ++it;
     o.trip();
@@ -301,24 +317,27 @@ __device__ __forceinline__ void tab2_load(const NeAtmosOceanDesc& d, const Layou
   So = slot_at<double>(d.So, idx);
 }
 
-// iteration invariants of a solved point (BulkTemperature: everything but the iterate is fixed); Δθ, Δq go to `dth`, `dqq`
-template <class O, class CT>
+// iteration invariants of a solved point (BulkTemperature: everything but the iterate is fixed) into the thread's column
+template <int NT, class O, class CT>
 __device__ __forceinline__ void tab2_invariants(O& o, const NeAtmosOceanDesc& d, const Thermo<CT>& th, const FastParams& P,
                                                 const TabParams& T, const double* tab, const Parked& k, double So,
-                                                Tab2Point& s, double* dth, double* dqq) {
+                                                Tab2Point& s, double* col) {
   const double az = d.surface_layer_height.value;
   const double To = k.Ts;
   const double qs = tab2_surface_humidity(o, d.properties, th, T, tab, k.pa, To, So);
   const double Rm = o.add(o.mul((double)th.R_d, o.sub(1.0, qs)), o.mul((double)th.R_v, qs));   // R_d(1 − q) + R_v q
   const double Tv = fm::div(o, o.mul(To, Rm), (double)th.R_d);                                  // virtual_temperature
   const double gTv = fm::div(o, P.g, Tv);
-  s.A = o.mul(gTv, o.fma((double)th.delta, qs, 1.0));                                           // g/𝒯ₛ (1 + δ qₛ)
-  s.B = o.mul(gTv, o.mul((double)th.delta, Tv));                                                // g/𝒯ₛ δ𝒯ₛ
-  s.dudv2 = o.fma(k.du, k.du, o.mul(k.dv, k.dv));
+  const double A = o.mul(gTv, o.fma((double)th.delta, qs, 1.0));                                // g/𝒯ₛ (1 + δ qₛ)
+  const double B = o.mul(gTv, o.mul((double)th.delta, Tv));                                     // g/𝒯ₛ δ𝒯ₛ
+  col[SL_A * NT] = A;
+  col[SL_B * NT] = B;
+  col[SL_DUDV2 * NT] = o.fma(k.du, k.du, o.mul(k.dv, k.dv));
   const double cpm = o.add(o.mul((double)th.cp_d, o.sub(1.0, k.qa)), o.mul((double)th.cp_v, k.qa));
-  *dth = o.sub(o.add(k.Ta, fm::div(o, o.mul(P.g, az), cpm)), To);                               // θₐ − Tₛ (interface_states.jl:308-317)
-  *dqq = o.sub(k.qa, qs);
+  col[SL_DTH * NT] = o.sub(o.add(k.Ta, fm::div(o, o.mul(P.g, az), cpm)), To);                   // θₐ − Tₛ (interface_states.jl:308-317)
+  col[SL_DQ * NT] = o.sub(k.qa, qs);
   s.ustar = s.theta_star = s.q_star = 1e-4;   // atmosphere_ocean_fluxes.jl:131-137
+  s.bstar = o.fma(A, s.theta_star, o.mul(B, s.q_star));
 }
 
 // flux epilogue + stores (atmosphere_ocean_fluxes.jl:160-196)

@@ -34,6 +34,13 @@ def test_elementary_functions_within_a_few_ulp(report):
     assert report["exp_ulp"] <= 3.0 and report["exp_ulp_mid"] <= 3.0
 
 
+def test_short_exponential_and_saturated_constants(report):
+    """exp_lo (32-entry 2^(j/32) table, degree 4) serves the roughness length ℓs that only scales ψ(ℓs/L★): 2e-12 relative is
+    ample and is what it must deliver; the saturated exp(−ζmax) constants of the stable closed forms equal exp_mid's value."""
+    assert report["exp_lo_rel"] <= 3e-12
+    assert report["exp_sat_rel"] <= 1e-15 and report["z_sat_ok"] == 1
+
+
 def test_psi_tables_reproduce_the_closed_forms(report):
     # error relative to max(1, |ψ|); the library refuses tables worse than 2e-15 and falls back to the closed forms
     assert report["psi_fit_err"] <= 1e-15

@@ -117,6 +117,22 @@ int main() {
   }
   double e_exp = max_ulp([&](double x) { return fm::exp_mid(T.mc, x); }, [](long double x) { return expl(x); }, -700, 700, false, 400000, rng);
   double e_exp2 = max_ulp([&](double x) { return fm::exp_mid(T.mc, x); }, [](long double x) { return expl(x); }, -30, 1, false, 400000, rng);
+  // the short exponential (relative error, not ulp) and the saturated-exponential constants of the stable closed forms
+  double e_exp_lo = 0;
+  {
+    std::uniform_real_distribution<double> u(-700, 40);
+    fm::OpsPlain o;
+    for (int i = 0; i < 400000; ++i) {
+      const double x = u(rng);
+      const long double t = expl((long double)x);
+      const double e = (double)(fabsl((long double)fm::exp_lo(o, tab, T.mc, x) - t) / t);
+      if (!(e <= e_exp_lo)) e_exp_lo = e;
+    }
+  }
+  const double e_sat = std::fmax(std::fabs(T.em_sat - std::exp(-f.psi_momentum.a.p[0])) / std::exp(-f.psi_momentum.a.p[0]),
+                                 std::fabs(T.es_sat - std::exp(-f.psi_temperature.a.p[0])) / std::exp(-f.psi_temperature.a.p[0]));
+  const int sat_ok = T.z_sat * f.psi_momentum.a.p[1] >= f.psi_momentum.a.p[0] && T.z_sat * f.psi_temperature.a.p[1] >= f.psi_temperature.a.p[0] &&
+                     T.z_sat < 1e3;
   // ψ tables: dense independent check
   const double* pm = f.psi_momentum.a.p;
   const double* ps = f.psi_temperature.a.p;
@@ -220,6 +236,7 @@ int main() {
   const double fit_i = build_solver_tables(fi, tab_i, Ti), fit_l = build_solver_tables(fl, tab_l, Tl);
   const double dense_i = dense_general(fi, tab_i, rng), dense_l = dense_general(fl, tab_l, rng);
   printf("{\"psi_far_err\": %.3e, \"atan_large_abs\": %.3e, \"psi_micro_abs\": %.3e, ", e_far, e_atan, e_micro);
+  printf("\"exp_lo_rel\": %.3e, \"exp_sat_rel\": %.3e, \"z_sat_ok\": %d, ", e_exp_lo, e_sat, sat_ok);
   printf("\"psi_seaice_fit_err\": %.3e, \"psi_seaice_dense_err\": %.3e, \"psi_seaice_general\": %d, "
          "\"psi_ly_fit_err\": %.3e, \"psi_ly_dense_err\": %.3e, ", fit_i, dense_i, Ti.general_psi, fit_l, dense_l);
   printf("\"rcp_ulp\": %.3f, \"div_ulp\": %.3f, \"sqrt_ulp\": %.3f, \"cbrt_ulp\": %.3f, \"cbrt_wide_ulp\": %.3f, "
