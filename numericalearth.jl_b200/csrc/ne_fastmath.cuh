@@ -266,6 +266,28 @@ template <class O> NE_HD double log_pos(O& o, const double* __restrict__ tab, co
   return o.add(base, o.fma(r2, p, r));
 }
 
+// The same with a table replicated per lane class (tab2 kernel).  A lookup with 32 unrelated indices into the 64 x 16-byte
+// table costs 8 shared-memory wavefronts instead of the 4 its 512 bytes need: entries i and i + 8 share banks (ncu:
+// 7.9 wavefronts per LDS.128, ideal 3.7).  In `rep`, entry i of lane class c = lane mod 8 sits at 16-byte chunk 8 i + c, i.e.
+// in bank group c: the four lanes of a class can collide only with each other — at most 4 wavefronts, the ideal.
+constexpr int LOG_REP = 8;
+template <class O> NE_HD double log_pos_rep(O& o, const double* __restrict__ rep, int lane_class, const MathConsts& C, double x) {
+  const int32_t hi = hi32(x);
+  const int32_t tmp = hi - 0x3fe6a09e;
+  const int32_t k = tmp >> 20;
+  const int32_t i = (tmp >> 14) & (LOG_N - 1);
+  const double z = mk64(hi - (k << 20), lo32(x));
+  const double* e = rep + 2 * (LOG_REP * i + lane_class);
+  const double invc = e[0], logc = e[1];
+  const double r = o.fma(z, invc, -1.0);
+  double p = C.logp[LOG_DEG - 1];
+#pragma unroll
+  for (int n = LOG_DEG - 2; n >= 0; --n) p = o.fma(p, r, C.logp[n]);
+  const double r2 = o.mul(r, r);
+  const double base = o.fma((double)k, C.ln2, logc);
+  return o.add(base, o.fma(r2, p, r));
+}
+
 // exp(x), |x| ≤ 700.  x = k ln2 + r; 2^k applied by exponent arithmetic (result stays normal).
 template <class O> NE_HD double exp_mid(O& o, const MathConsts& C, double x) {
   const double magic = 6755399441055744.0;  // 1.5·2^52
@@ -348,6 +370,25 @@ template <class O> NE_HD void psi_pair(O& o, const double* __restrict__ rec, dou
   ps = poly_eo<PSI_DEG>(o, rec + 3, 2, w, w2);
 }
 NE_HD void psi_pair(const double* __restrict__ rec, double az, double& pm, double& ps) { OpsPlain o; psi_pair(o, rec, az, pm, ps); }
+// The record's (a, b) never has to be loaded: on [2^e (1 + k/S), 2^e (1 + (k+1)/S)) (S = PSI_SUB sub-intervals per octave)
+// w = a|ζ| + b = 2 f − 1 with f the fraction of the mantissa below its top PSI_SUB_BITS bits — shifting those bits out of
+// |ζ|'s mantissa gives u = 1 + f exactly and w = 2u − 3 in one fused operation: the same real number rounded once, i.e.
+// the same bits as fma(|ζ|, a, b) with the stored power-of-two a and integer b (checked in tools/fastmath_check.cu).
+// Below 2^PSI_OCT_LO (record 0 of a side) w = 2^(1 − PSI_OCT_LO) |ζ| − 1.  One LDS.128 (4.3 wavefronts) less per lookup.
+template <class O> NE_HD double psi_w_from_bits(O& o, double az) {
+  const int32_t hi = hi32(az), lo = lo32(az);
+  const uint32_t mh = (((uint32_t)hi << PSI_SUB_BITS) & 0x000fffffu) | ((uint32_t)lo >> (32 - PSI_SUB_BITS));
+  const double u = mk64((int32_t)(0x3ff00000u | mh), (int32_t)((uint32_t)lo << PSI_SUB_BITS));
+  const double w_hi = o.fma(u, 2.0, -3.0);
+  const double w_lo = o.fma(az, (double)(1ll << (1 - PSI_OCT_LO)), -1.0);
+  return (hi >> 20) < 1023 + PSI_OCT_LO ? w_lo : w_hi;
+}
+template <class O> NE_HD void psi_pair_bits(O& o, const double* __restrict__ rec, double az, double& pm, double& ps) {
+  const double w = psi_w_from_bits(o, az);
+  const double w2 = o.mul(w, w);
+  pm = poly_eo<PSI_DEG>(o, rec + 2, 2, w, w2);
+  ps = poly_eo<PSI_DEG>(o, rec + 3, 2, w, w2);
+}
 // one of the two (which = 0: ψ_m, 1: ψ_s): same operations as psi_pair, so the same bits
 template <class O> NE_HD double psi_single(O& o, const double* __restrict__ rec, double az, int which) {
   const double w = o.fma(az, rec[0], rec[1]);

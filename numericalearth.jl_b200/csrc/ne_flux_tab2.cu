@@ -84,14 +84,20 @@ template <class CT, bool SORT, class O>
 __global__ void __launch_bounds__(256, 3)
 ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_constant__ Layout L,
                     const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P,
-                    const __grid_constant__ TabParams T, const __grid_constant__ Micro Mi, const double* __restrict__ gtab,
+                    const __grid_constant__ TabParams T, const __grid_constant__ Micro Mi,
+                    const __grid_constant__ Tab2First F, const double* __restrict__ gtab,
                     const uint16_t* __restrict__ perm, uint16_t* __restrict__ hint, unsigned long long* __restrict__ counts,
                     uint32_t* __restrict__ next_group) {
   constexpr int NT = 256, W = TAB2_WINDOW;
   extern __shared__ __align__(16) double tab[];   // fm::TAB_SIZE doubles (dynamic: see allow_table_smem)
   __shared__ double park[SL_COUNT][NT];
+  __shared__ __align__(16) double lrep[2 * fm::LOG_N * fm::LOG_REP];   // the log table once per lane class (fm::log_pos_rep)
+  __shared__ Tab2Rare rare;
+  if (threadIdx.x == 0) { rare.P = P; rare.T = T; }
   for (int k = threadIdx.x; k < fm::TAB_SIZE / 2; k += NT)
     reinterpret_cast<double2*>(tab)[k] = __ldg(reinterpret_cast<const double2*>(gtab) + k);
+  for (int k = threadIdx.x; k < fm::LOG_N * fm::LOG_REP; k += NT)
+    reinterpret_cast<double2*>(lrep)[k] = __ldg(reinterpret_cast<const double2*>(gtab + fm::TAB_LOG) + k / fm::LOG_REP);
   __syncthreads();
   O o;
   const uint32_t n = (uint32_t)L.ni * (uint32_t)L.nj;
@@ -119,27 +125,32 @@ ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
     const bool valid = t < n;
     int64_t idx = 0;
     bool not_water = true;
-    if (valid) {
+    Parked k;
+    double So = 0;
+    if (valid) {   // the mask and the fields are requested together: one memory latency per group, not two
       const uint32_t jj = t / (uint32_t)L.ni;
       idx = L.at(L.i_lo + (int32_t)(t - jj * (uint32_t)L.ni), L.j_lo + (int32_t)jj);
-      not_water = d.inactive ? (d.inactive[idx] != 0) : false;
+      const uint8_t mask = d.inactive ? d.inactive[idx] : (uint8_t)0;
+      double uo, vo;
+      tab2_load<true>(d, L, idx, celsius, relative, k, uo, vo, So);
+      not_water = mask != 0;
+      if (!not_water) { k.du -= uo; k.dv -= vo; }   // land: zero_interface_state, Δu = uₐ − 0 (interface_states.jl:800-803)
     }
     const bool solve = valid && !(not_water && !P.fixed);   // needs_to_converge && not_water: no solve (atmosphere_ocean_fluxes.jl:144)
     const unsigned solving = __ballot_sync(0xffffffffu, solve);   // all 32 lanes are converged here (loop head)
     double ustar = 0, theta_star = 0, q_star = 0;
     int iters = 0;
     if (valid) {
-      Parked k;
-      double So;
-      tab2_load<true>(d, L, idx, celsius, relative, not_water, k, So);
       if (solve) {
         Tab2Point s;
         tab2_invariants<NT>(o, d, th, P, T, tab, k, So, s, col);
         col[SL_DU * NT] = k.du; col[SL_DV * NT] = k.dv; col[SL_TA * NT] = k.Ta; col[SL_PA * NT] = k.pa; col[SL_QA * NT] = k.qa; col[SL_TS * NT] = k.Ts;
         int record;
-        iters = tab2_solve<NT>(o, P, T, Mi, tab, H, s, col, counts, record);
+        iters = tab2_solve<NT>(o, P, T, rare, Mi, tab, lrep, lane & (fm::LOG_REP - 1), H, F, s, col, counts, record);
         if (hint) hint[t] = tab2_hint(iters, record);
-        ustar = s.ustar; theta_star = s.theta_star; q_star = s.q_star;
+        ustar = s.ustar;
+        if (iters > 0) { theta_star = o.mul(s.chi_s, col[SL_DTH * NT]); q_star = o.mul(s.chi_s, col[SL_DQ * NT]); }
+        else theta_star = q_star = 1e-4;
         k.du = col[SL_DU * NT]; k.dv = col[SL_DV * NT]; k.Ta = col[SL_TA * NT]; k.pa = col[SL_PA * NT]; k.qa = col[SL_QA * NT]; k.Ts = col[SL_TS * NT];
         if (!std::is_same<O, fm::OpsPlain>::value) {   // warp trips = the slowest lane's, once per group
           __syncwarp(solving);
@@ -221,7 +232,7 @@ bool tab2_eligible(const NeAtmosOceanDesc& d, const TabParams& TP) {
 
 template <class CT>
 static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P, const TabParams& TP, const Micro& Mi,
-                         const double* tab, cudaStream_t s, unsigned long long* counts, uint16_t* perm, uint16_t* hint, uint32_t n) {
+                         const Tab2First& F, const double* tab, cudaStream_t s, unsigned long long* counts, uint16_t* perm, uint16_t* hint, uint32_t n) {
   constexpr int W = TAB2_WINDOW;
   const uint32_t n_windows = (n + W - 1) / W;
   uint32_t* counter = tab2_counter();
@@ -238,7 +249,7 @@ static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastP
   do {                                                                                                                   \
     if (cudaError_t e = allow_table_smem<ao_flux_tab2_kernel<CT, SORT, O>>(); e != cudaSuccess)                          \
       return cuda_error(e, "ne_atmosphere_ocean_fluxes(tab2: shared memory opt-in)");                                    \
-    ao_flux_tab2_kernel<CT, SORT, O><<<grid, 256, TAB_SMEM_BYTES, s>>>(d, L, th, P, TP, Mi, tab, perm, hint, counts, counter); \
+    ao_flux_tab2_kernel<CT, SORT, O><<<grid, 256, TAB_SMEM_BYTES, s>>>(d, L, th, P, TP, Mi, F, tab, perm, hint, counts, counter); \
   } while (0)
   if (counts) {
     if (perm) NE_TAB2_GO(true, fm::OpsCount); else NE_TAB2_GO(false, fm::OpsCount);
@@ -261,8 +272,9 @@ int launch_tab2(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P,
   uint16_t *perm = nullptr, *hint = nullptr;
   if (!env_flag("NE_B200_TAB2_NO_ORDER"))
     if (const OrderBuf* ob = order_buffer(d.friction_velocity, n, d.grid.i_lo, d.grid.j_lo)) { perm = ob->perm; hint = ob->hint; }
-  if (d.thermo.dtype == NE_F64) return launch_tab2_t<double>(d, L, P, TP, Mi, tab, s, counts, perm, hint, n);
-  return launch_tab2_t<float>(d, L, P, TP, Mi, tab, s, counts, perm, hint, n);
+  const Tab2First F = make_tab2_first(P, TP, host_tab, d.surface_layer_height.value - P.d_zero, TP.log_hd);
+  if (d.thermo.dtype == NE_F64) return launch_tab2_t<double>(d, L, P, TP, Mi, F, tab, s, counts, perm, hint, n);
+  return launch_tab2_t<float>(d, L, P, TP, Mi, F, tab, s, counts, perm, hint, n);
 }
 
 }  // namespace ne

@@ -134,22 +134,32 @@ static __device__ __noinline__ double2 tab2_psi_small(const FastParams& P, const
 // the two |ζ| < 2^-12 records (unstable, stable) as a kernel parameter: constant-bank operands
 struct Micro { double rec[2][fm::MICRO_REC]; };
 
-// What a thread keeps in registers across the loop: the iterate and b★ = g/𝒯ₛ (θ★ (1 + δqₛ) + δ𝒯ₛ q★), evaluated at the END
-// of a trip as A θ★ + B q★ with A = g/𝒯ₛ (1 + δqₛ), B = g/𝒯ₛ δ𝒯ₛ formed once.  The per-point invariants wait in the
-// thread's own column of shared memory (conflict-free 64-bit accesses) and are read where a trip needs them — A, B, Δθ, Δq
-// in its last four multiplications, Δu² + Δv² under the cube root: 8 registers of loop-carried state instead of 24 (the
-// 80-register build of round 1 reloaded three spilled doubles at the head of every trip: a third of its long-scoreboard
-// stalls).  Slots of the column (stride NT doubles):
-enum { SL_DU, SL_DV, SL_TA, SL_PA, SL_QA, SL_TS, SL_DTH, SL_DQ, SL_A, SL_B, SL_DUDV2, SL_COUNT };
-struct Tab2Point { double ustar, theta_star, q_star, bstar; };
+// What a thread keeps in registers across the loop: u★, χ_s = ϰ/Π_s and b★.  With BulkTemperature θ★ = χ_s Δθ and
+// q★ = χ_s Δq are one number times two per-point invariants, so
+//     b★ = g/𝒯ₛ (θ★ (1 + δqₛ) + δ𝒯ₛ q★) = χ_s C,          C = A Δθ + B Δq,  A = g/𝒯ₛ (1 + δqₛ), B = g/𝒯ₛ δ𝒯ₛ
+//     |θ★ − θ★'| + |q★ − q★'| = |χ_s − χ_s'| D,            D = |Δθ| + |Δq|
+// (identities in real arithmetic; in Float64 they move b★ and the drift by a few ulp — the drift is compared with 1e-8,
+// the iterate itself is unchanged: θ★ and q★ are formed from the final χ_s with the reference's own multiplication).
+// C, D and Δu² + Δv² wait in the thread's own column of shared memory (conflict-free 64-bit accesses) and are read where
+// a trip needs them: 6 registers of loop-carried state instead of 24 (the 80-register build of round 1 reloaded three
+// spilled doubles at the head of every trip), 3 shared-memory loads per trip instead of 5.  The first trip starts from
+// θ★ = q★ = 1e-4 (atmosphere_ocean_fluxes.jl:131-137), which is not of that form: its b★ and its drift are formed as written.
+// Slots of the column (stride NT doubles):
+enum { SL_DU, SL_DV, SL_TA, SL_PA, SL_QA, SL_TS, SL_DTH, SL_DQ, SL_C, SL_D, SL_DUDV2, SL_COUNT };
+struct Tab2Point { double ustar, chi_s, bstar; };
 struct Tab2Heights { double h_bl, hd, log_hd; };
 
 // a shared-memory read the compiler may not hoist out of the loop (hoisting is what spills)
 __device__ __forceinline__ double slot_ld(const double* p) { return *(const volatile double*)p; }
 
+// `lrep`: the log table replicated per lane class (fm::log_pos_rep), `lc` = lane mod 8
+// `rare`: copies of P and T in shared memory for the out-of-line closed forms (a reference to a kernel parameter handed to a
+// non-inlined function turns every use into a generic load from the parameter window: long-scoreboard stalls, ncu)
+struct Tab2Rare { FastParams P; TabParams T; };
+
 template <int NT, class O>
-__device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const TabParams& T, const Micro& Mi, const double* tab,
-                                               const Tab2Heights& H, Tab2Point& s, const double* col,
+__device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const TabParams& T, const Tab2Rare& rare, const Micro& Mi, const double* tab,
+                                               const double* lrep, int lc, const Tab2Heights& H, Tab2Point& s, const double* col,
                                                unsigned long long* counts, int& record) {
   using fm::dmax;
   using fm::dmin;
@@ -166,9 +176,9 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
   const double ru = fm::rcp(o, s.ustar);
   const double lu = dmin(o.fma(o.mul(P.a1, s.ustar), s.ustar, o.mul(P.a2, ru)), P.lmax);
   const double Linv = o.mul(o.mul(o.mul(P.kappa, bstar), ru), ru);   // 0 when b★ == 0, i.e. L★ = Inf (:372)
-  const double log_lu = fm::log_pos(o, tab, T.mc, lu);
+  const double log_lu = fm::log_pos_rep(o, lrep, lc, T.mc, lu);
   const double Rs = o.mul(o.mul(lu, s.ustar), P.nu_inv);
-  const double log_Rs = fm::log_pos(o, tab, T.mc, Rs);
+  const double log_Rs = fm::log_pos_rep(o, lrep, lc, T.mc, Rs);
   const double log_ls_un = o.fma(-P.rb, log_Rs, P.log_rA);
   const bool clipped = log_ls_un > P.log_ls_max;
   const double log_ls = clipped ? P.log_ls_max : log_ls_un;
@@ -185,7 +195,7 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
   const int iv = fm::psi_interval(zh, outside);
   record = iv;
   double pm_h, ps_h;
-  fm::psi_pair(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(zh), pm_h, ps_h);
+  fm::psi_pair_bits(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, fabs(zh), pm_h, ps_h);
   // ψ(ℓ/L★): always from the |ζ| < 2^-12 record of the side of L★.  The two records also sit in the kernel-parameter
   // constant bank (Micro): a warp whose lanes are all on one side — nearly every warp, L★ varies smoothly in space —
   // takes its coefficients from there and issues no shared-memory load for this lookup
@@ -200,11 +210,11 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
     else fm::psi_micro_pair(o, tab + fm::TAB_MICRO + (unstable ? 0 : fm::MICRO_REC), fabs(zu), fabs(zs), pm_l, ps_l);
   }
   if (outside) {
-    const double2 r = tab2_psi_outside<O>(P, T, tab, zh, 2, counts);
+    const double2 r = tab2_psi_outside<O>(rare.P, rare.T, tab, zh, 2, counts);
     pm_h = r.x; ps_h = r.y;
   }
   if (!(fm::psi_is_micro(zu) && fm::psi_is_micro(zs))) {
-    const double2 r = tab2_psi_small<O>(P, T, tab, zu, zs, Linv, counts);
+    const double2 r = tab2_psi_small<O>(rare.P, rare.T, tab, zu, zs, Linv, counts);
     pm_l = r.x; ps_l = r.y;
   }
   // Π = log(Δh/ℓ) − ψ(Δh/L★) + ψ(ℓ/L★), χ = ϰ/Π (:242-247, 375-377)
@@ -216,27 +226,100 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
   chi_u = o.fma(o.fma(-Pi_u, chi_u, P.kappa), ru_, chi_u);
   chi_s = o.fma(o.fma(-Pi_s, chi_s, P.kappa), rs_, chi_s);
   s.ustar = o.mul(chi_u, U);
-  s.theta_star = o.mul(chi_s, slot_ld(col + SL_DTH * NT));
-  s.q_star = o.mul(chi_s, slot_ld(col + SL_DQ * NT));
-  s.bstar = o.fma(slot_ld(col + SL_A * NT), s.theta_star, o.mul(slot_ld(col + SL_B * NT), s.q_star));
+  s.chi_s = chi_s;
+  s.bstar = o.mul(chi_s, slot_ld(col + SL_C * NT));
+}
+
+// ---- the first trip ---------------------------------------------------------------------------------------
+// Every solve starts from u★ = θ★ = q★ = 1e-4 (atmosphere_ocean_fluxes.jl:131-137).  With that iterate the roughness
+// lengths, their logarithms and Δh are the same numbers at every point (formed once per launch on the host with the
+// functions of ne_fastmath.cuh), b★ > 0 (stable: U_G is its floor), and L★ is so small (ζ ~ 1e5) that ψ(Δh/L★) and
+// ψ(ℓu/L★) sit on the saturated stable branch, where the Edson functions are a line and a 3/2 power.  The generic trip
+// spends ~800 instructions there (three out-of-line closed-form calls); this one does the same arithmetic in ~150.
+// Taken only when every lane of the warp qualifies; otherwise the generic trip runs (same result either way to the
+// last ulp of the host-formed constants).
+struct Tab2First { double ru0, lu0, log_lu0, ls0, log_ls0, dh0, log_dh0; int32_t ok; };
+
+inline Tab2First make_tab2_first(const FastParams& P, const TabParams& T, const double* host_tab, double hd, double log_hd) {
+  using fm::dmax; using fm::dmin;
+  fm::OpsPlain o;
+  Tab2First F;
+  const double u0 = 1e-4;
+  F.ru0 = fm::rcp(o, u0);
+  F.lu0 = dmin(o.fma(o.mul(P.a1, u0), u0, o.mul(P.a2, F.ru0)), P.lmax);
+  F.log_lu0 = fm::log_pos(o, host_tab, T.mc, F.lu0);
+  const double Rs = o.mul(o.mul(F.lu0, u0), P.nu_inv);
+  const double log_ls_un = o.fma(-P.rb, fm::log_pos(o, host_tab, T.mc, Rs), P.log_rA);
+  const bool clipped = log_ls_un > P.log_ls_max;
+  F.log_ls0 = clipped ? P.log_ls_max : log_ls_un;
+  F.ls0 = clipped ? P.ls_max : fm::exp_lo(o, host_tab, T.mc, dmax(log_ls_un, -700.0));
+  const double lu2 = o.add(F.lu0, F.lu0);
+  const bool lifted = lu2 > hd;
+  F.dh0 = lifted ? lu2 : hd;
+  F.log_dh0 = lifted ? o.add(T.mc.ln2, F.log_lu0) : log_hd;
+  F.ok = (T.z_sat < 1e300 && P.s_C15 && F.lu0 > 0 && F.ls0 > 0 && Rs > 0 && !(P.fixed && P.maxiter <= 0)) ? 1 : 0;
+  return F;
+}
+
+template <int NT, class O>
+__device__ __forceinline__ bool tab2_first_trip(O& o, const FastParams& P, const TabParams& T, const Tab2First& F, const double* tab,
+                                                Tab2Point& s, const double* col, double& drift, int& record) {
+  const double Linv = o.mul(o.mul(o.mul(P.kappa, s.bstar), F.ru0), F.ru0);
+  const double zh = o.mul(F.dh0, Linv), zu = o.mul(F.lu0, Linv), zs = o.mul(F.ls0, Linv);
+  bool out_s, out_h;
+  const int ivs = fm::psi_interval(zs, out_s);
+  const bool mine = F.ok && s.bstar > 0.0 && zh >= T.z_sat && zu >= T.z_sat && !out_s && !fm::psi_is_tiny(zs);
+  if (!__all_sync(__activemask(), mine)) return false;
+  record = fm::psi_interval(zh, out_h);
+  const double U = fm::sqrt_pos(o, o.fma(P.gmin, P.gmin, slot_ld(col + SL_DUDV2 * NT)));
+  // ψ_m, ψ_s on the saturated stable branch (tab2_psi_stable with ζ ≥ ζ_sat: the same operations)
+  const double pm_h = o.sub(o.fma(-o.mul(P.m_Cp, o.sub(zh, P.m_Dp)), T.em_sat, -o.mul(P.m_Bp, zh)), P.m_CpDp);
+  const double pm_l = o.sub(o.fma(-o.mul(P.m_Cp, o.sub(zu, P.m_Dp)), T.em_sat, -o.mul(P.m_Bp, zu)), P.m_CpDp);
+  const double x = o.fma(P.s_Bp, zh, 1.0);
+  const double ps_h = o.sub(o.fma(-o.mul(P.s_Bp, o.sub(zh, P.s_Dp)), T.es_sat, -o.mul(x, fm::sqrt_pos(o, x))), P.s_Ep);
+  const double ps_l = fm::psi_single(o, tab + fm::TAB_PSI + ivs * fm::PSI_REC, zs, 1);
+  const double Pi_u = o.add(o.sub(o.sub(F.log_dh0, F.log_lu0), pm_h), pm_l);
+  const double Pi_s = o.add(o.sub(o.sub(F.log_dh0, F.log_ls0), ps_h), ps_l);
+  const double r = fm::rcp(o, o.mul(Pi_u, Pi_s));
+  const double ru_ = o.mul(Pi_s, r), rs_ = o.mul(Pi_u, r);
+  double chi_u = o.mul(P.kappa, ru_), chi_s = o.mul(P.kappa, rs_);
+  chi_u = o.fma(o.fma(-Pi_u, chi_u, P.kappa), ru_, chi_u);
+  chi_s = o.fma(o.fma(-Pi_s, chi_s, P.kappa), rs_, chi_s);
+  const double pu = s.ustar;
+  s.ustar = o.mul(chi_u, U);
+  s.chi_s = chi_s;
+  s.bstar = o.mul(chi_s, slot_ld(col + SL_C * NT));
+  const double th = o.mul(chi_s, slot_ld(col + SL_DTH * NT)), q = o.mul(chi_s, slot_ld(col + SL_DQ * NT));
+  drift = o.add(o.add(fabs(o.sub(s.ustar, pu)), fabs(o.sub(th, 1e-4))), fabs(o.sub(q, 1e-4)));
+  return true;
 }
 
 // compute_interface_state.jl:10-18: the first trip always runs; then until drift < tol or it ≥ maxiter
 // `record`: the ψ(Δh/L★) table record of the last trip (the next step's ordering hint)
 template <int NT, class O>
-__device__ __forceinline__ int tab2_solve(O& o, const FastParams& P, const TabParams& T, const Micro& Mi, const double* tab,
-                                          const Tab2Heights& H, Tab2Point& s, const double* col,
-                                          unsigned long long* counts, int& record) {
+__device__ __forceinline__ int tab2_solve(O& o, const FastParams& P, const TabParams& T, const Tab2Rare& rare, const Micro& Mi, const double* tab,
+                                          const double* lrep, int lc, const Tab2Heights& H, const Tab2First& F, Tab2Point& s,
+                                          const double* col, unsigned long long* counts, int& record) {
   record = 0;
   if (P.fixed && P.maxiter <= 0) return 0;
   const double tol = P.fixed ? -1.0 : P.tol;
   const int maxiter = P.maxiter;
   int it = 0;
   double drift;
+  if (tab2_first_trip<NT>(o, P, T, F, tab, s, col, drift, record)) {
+    it = 1;
+    o.trip();
+    if (!(!(drift < tol) && it < maxiter)) return it;
+  }
   do {
-    const double pu = s.ustar, pt = s.theta_star, pq = s.q_star;
-    tab2_iteration<NT>(o, P, T, Mi, tab, H, s, col, counts, record);
-    drift = o.add(o.add(fabs(o.sub(s.ustar, pu)), fabs(o.sub(s.theta_star, pt))), fabs(o.sub(s.q_star, pq)));
+    const double pu = s.ustar, pc = s.chi_s;
+    tab2_iteration<NT>(o, P, T, rare, Mi, tab, lrep, lc, H, s, col, counts, record);
+    if (it == 0) {   // against the initial guess u★ = θ★ = q★ = 1e-4, as written
+      const double th = o.mul(s.chi_s, slot_ld(col + SL_DTH * NT)), q = o.mul(s.chi_s, slot_ld(col + SL_DQ * NT));
+      drift = o.add(o.add(fabs(o.sub(s.ustar, pu)), fabs(o.sub(th, 1e-4))), fabs(o.sub(q, 1e-4)));
+    } else {
+      drift = o.fma(fabs(o.sub(s.chi_s, pc)), slot_ld(col + SL_D * NT), fabs(o.sub(s.ustar, pu)));
+    }
     ++it;
     o.trip();
   } while (!(drift < tol) && it < maxiter);
@@ -300,16 +383,17 @@ __device__ __forceinline__ double tab2_surface_humidity(O& o, const NeInterfaceP
 // cache lines per load) or kept in registers (the loop already spills at 80)
 struct Parked { double du, dv, Ta, pa, qa, Ts; };
 
-// loads of one point: atmosphere state, velocity difference, surface temperature in Kelvin
+// loads of one point: atmosphere state, ocean velocity at the cell centre, surface temperature in Kelvin.  Nothing here
+// depends on the land mask, so the kernel requests the mask and the fields together (one memory latency per group)
 template <bool HS>
 __device__ __forceinline__ void tab2_load(const NeAtmosOceanDesc& d, const Layout& L, int64_t idx, bool celsius, bool relative,
-                                          bool not_water, Parked& k, double& So) {
-  const double au = __ldg((const double*)d.ua + idx), av = __ldg((const double*)d.va + idx);
+                                          Parked& k, double& uo, double& vo, double& So) {
+  k.du = __ldg((const double*)d.ua + idx); k.dv = __ldg((const double*)d.va + idx);
   k.Ta = __ldg((const double*)d.Ta + idx); k.pa = __ldg((const double*)d.pa + idx); k.qa = __ldg((const double*)d.qa + idx);
-  k.du = au; k.dv = av;
-  if (relative && !not_water) {
-    k.du -= d.uo.ptr ? (slot_at<double>(d.uo, idx) + slot_at<double>(d.uo, idx + 1)) / 2 : d.uo.value;
-    k.dv -= d.vo.ptr ? (slot_at<double>(d.vo, idx) + slot_at<double>(d.vo, idx + L.sx)) / 2 : d.vo.value;
+  uo = vo = 0;
+  if (relative) {
+    uo = d.uo.ptr ? (slot_at<double>(d.uo, idx) + slot_at<double>(d.uo, idx + 1)) / 2 : d.uo.value;
+    vo = d.vo.ptr ? (slot_at<double>(d.vo, idx) + slot_at<double>(d.vo, idx + L.sx)) / 2 : d.vo.value;
   }
   double To = slot_at<double>(d.To, idx);
   if (celsius) To = To + 273.15;
@@ -330,14 +414,17 @@ __device__ __forceinline__ void tab2_invariants(O& o, const NeAtmosOceanDesc& d,
   const double gTv = fm::div(o, P.g, Tv);
   const double A = o.mul(gTv, o.fma((double)th.delta, qs, 1.0));                                // g/𝒯ₛ (1 + δ qₛ)
   const double B = o.mul(gTv, o.mul((double)th.delta, Tv));                                     // g/𝒯ₛ δ𝒯ₛ
-  col[SL_A * NT] = A;
-  col[SL_B * NT] = B;
   col[SL_DUDV2 * NT] = o.fma(k.du, k.du, o.mul(k.dv, k.dv));
   const double cpm = o.add(o.mul((double)th.cp_d, o.sub(1.0, k.qa)), o.mul((double)th.cp_v, k.qa));
-  col[SL_DTH * NT] = o.sub(o.add(k.Ta, fm::div(o, o.mul(P.g, az), cpm)), To);                   // θₐ − Tₛ (interface_states.jl:308-317)
-  col[SL_DQ * NT] = o.sub(k.qa, qs);
-  s.ustar = s.theta_star = s.q_star = 1e-4;   // atmosphere_ocean_fluxes.jl:131-137
-  s.bstar = o.fma(A, s.theta_star, o.mul(B, s.q_star));
+  const double dth = o.sub(o.add(k.Ta, fm::div(o, o.mul(P.g, az), cpm)), To);                   // θₐ − Tₛ (interface_states.jl:308-317)
+  const double dq = o.sub(k.qa, qs);
+  col[SL_DTH * NT] = dth;
+  col[SL_DQ * NT] = dq;
+  col[SL_C * NT] = o.fma(A, dth, o.mul(B, dq));
+  col[SL_D * NT] = o.add(fabs(dth), fabs(dq));
+  s.ustar = 1e-4;                             // u★ = θ★ = q★ = 1e-4 (atmosphere_ocean_fluxes.jl:131-137)
+  s.chi_s = 0;                                // not used by the first trip
+  s.bstar = o.fma(A, 1e-4, o.mul(B, 1e-4));
 }
 
 // flux epilogue + stores (atmosphere_ocean_fluxes.jl:160-196)

@@ -39,6 +39,8 @@ def test_short_exponential_and_saturated_constants(report):
     ample and is what it must deliver; the saturated exp(−ζmax) constants of the stable closed forms equal exp_mid's value."""
     assert report["exp_lo_rel"] <= 3e-12
     assert report["exp_sat_rel"] <= 1e-15 and report["z_sat_ok"] == 1
+    # w = a|ζ| + b from the mantissa bits of |ζ| and the per-lane-class copy of the log table change no bit
+    assert report["bit_w_and_replicated_log_same_bits"] == 1
 
 
 def test_psi_tables_reproduce_the_closed_forms(report):

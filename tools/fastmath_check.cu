@@ -133,6 +133,41 @@ int main() {
                                  std::fabs(T.es_sat - std::exp(-f.psi_temperature.a.p[0])) / std::exp(-f.psi_temperature.a.p[0]));
   const int sat_ok = T.z_sat * f.psi_momentum.a.p[1] >= f.psi_momentum.a.p[0] && T.z_sat * f.psi_temperature.a.p[1] >= f.psi_temperature.a.p[0] &&
                      T.z_sat < 1e3;
+  // bit-derived w and the replicated log table: the same bits as the stored (a, b) / the plain table
+  int bits_ok = 1;
+  {
+    static double lrep[2 * fm::LOG_N * fm::LOG_REP];
+    for (int k = 0; k < fm::LOG_N * fm::LOG_REP; ++k) { lrep[2 * k] = tab[fm::TAB_LOG + 2 * (k / fm::LOG_REP)]; lrep[2 * k + 1] = tab[fm::TAB_LOG + 2 * (k / fm::LOG_REP) + 1]; }
+    std::uniform_real_distribution<double> u(0, 1);
+    fm::OpsPlain o;
+    for (int i = 0; i < 400000; ++i) {
+      const double az = std::exp(std::log(1e-12) + u(rng) * (std::log(127.99) - std::log(1e-12)));
+      for (int side = 0; side < 2; ++side) {
+        bool outside;
+        const int iv = fm::psi_interval(side ? az : -az, outside);
+        double m1, s1, m2, s2;
+        fm::psi_pair(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, az, m1, s1);
+        fm::psi_pair_bits(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, az, m2, s2);
+        if (outside || std::memcmp(&m1, &m2, 8) || std::memcmp(&s1, &s2, 8)) bits_ok = 0;
+      }
+      const double x = std::exp(-30 + 60 * u(rng));
+      const double l1 = fm::log_pos(o, tab, T.mc, x), l2 = fm::log_pos_rep(o, lrep, i & (fm::LOG_REP - 1), T.mc, x);
+      if (std::memcmp(&l1, &l2, 8)) bits_ok = 0;
+    }
+    // interval edges: exact powers of two and sub-interval boundaries
+    for (int e = fm::PSI_OCT_LO - 2; e < fm::PSI_OCT_HI; ++e)
+      for (int k = 0; k < fm::PSI_SUB; ++k)
+        for (int d = -1; d <= 1; ++d) {
+          double az = std::ldexp(1.0 + (double)k / fm::PSI_SUB, e);
+          if (d) az = std::nextafter(az, d > 0 ? 1e300 : 0.0);
+          bool outside;
+          const int iv = fm::psi_interval(az, outside);
+          double m1, s1, m2, s2;
+          fm::psi_pair(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, az, m1, s1);
+          fm::psi_pair_bits(o, tab + fm::TAB_PSI + iv * fm::PSI_REC, az, m2, s2);
+          if (std::memcmp(&m1, &m2, 8) || std::memcmp(&s1, &s2, 8)) bits_ok = 0;
+        }
+  }
   // ψ tables: dense independent check
   const double* pm = f.psi_momentum.a.p;
   const double* ps = f.psi_temperature.a.p;
@@ -236,6 +271,7 @@ int main() {
   const double fit_i = build_solver_tables(fi, tab_i, Ti), fit_l = build_solver_tables(fl, tab_l, Tl);
   const double dense_i = dense_general(fi, tab_i, rng), dense_l = dense_general(fl, tab_l, rng);
   printf("{\"psi_far_err\": %.3e, \"atan_large_abs\": %.3e, \"psi_micro_abs\": %.3e, ", e_far, e_atan, e_micro);
+  printf("\"bit_w_and_replicated_log_same_bits\": %d, ", bits_ok);
   printf("\"exp_lo_rel\": %.3e, \"exp_sat_rel\": %.3e, \"z_sat_ok\": %d, ", e_exp_lo, e_sat, sat_ok);
   printf("\"psi_seaice_fit_err\": %.3e, \"psi_seaice_dense_err\": %.3e, \"psi_seaice_general\": %d, "
          "\"psi_ly_fit_err\": %.3e, \"psi_ly_dense_err\": %.3e, ", fit_i, dense_i, Ti.general_psi, fit_l, dense_l);
