@@ -249,6 +249,48 @@ template <class O> NE_HD double cbrt_pos(O& o, const MathConsts& C, double x) {
   return mk64(hi32(y) + (q3 << 20), lo32(y));
 }
 
+// ---- one third-order step instead of two Newton steps (tab2 kernel) ---------------------------------------------
+// The seeds carry ≥ 20 bits (relative error e ≤ 2^-20).  A second-order (Newton) step squares e and has to be applied twice;
+// one step built from the series of the function around the seed, truncated after e², leaves c·e³ ≤ 2^-60 — below half an
+// ulp — with half the operations and half the dependent chain:
+//   1/x      = r (1 + e + e²) (1 + O(e³)),                 e = 1 − x r
+//   √x       = t (1 + e/2 + 3e²/8) (1 + O(e³)),            t = x r,  e = 1 − t r        (r ≈ 1/√x)
+//   m^(-1/3) = r (1 + e/3 + 2e²/9) (1 + O(e³)),            e = 1 − m r³
+// Results within 1.5 ulp (checked against long double in tools/fastmath_check.cu and on the device in
+// tools/fastmath_gpu_check.cu); e itself is exact to its last bit because it comes out of one fused operation.
+template <class O> NE_HD double rcp3(O& o, double x) {
+  const double r = rcp_seed(x);
+  const double e = o.fma(-x, r, 1.0);
+  return o.fma(r, o.fma(e, e, e), r);
+}
+template <class O> NE_HD double sqrt3(O& o, double x) {
+  const double r = rsqrt_seed(x);
+  const double t = o.mul(x, r);
+  const double e = o.fma(-t, r, 1.0);
+  return o.fma(o.mul(t, e), o.fma(e, 0.375, 0.5), t);
+}
+template <class O> NE_HD double cbrt3(O& o, const MathConsts& C, double x) {
+  const int32_t hi = hi32(x);
+  const int32_t e = (hi >> 20) - 1023;                 // unbiased exponent
+  const int32_t q = (e + 3072) * 21846 >> 16;          // floor((e + 3072)/3), exact for |e| ≤ 1100
+  const int32_t q3 = q - 1024;                         // floor(e/3)
+  const double m = mk64(hi - ((3 * q3) << 20), lo32(x));  // [1, 8)
+#if defined(__CUDA_ARCH__)
+  float lg, ex;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float)m));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-0.333333333f * lg));
+  const double r = (double)ex;
+#else
+  const double r = (double)(float)std::exp2(-std::log2((float)m) / 3.0f) * (1.0 + 4e-7);
+#endif
+  const double r2 = o.mul(r, r);
+  const double mr = o.mul(m, r);
+  const double e1 = o.fma(-mr, r2, 1.0);                              // 1 − m r³
+  const double r1 = o.fma(o.mul(r, e1), o.fma(e1, 2.0 / 9.0, C.third), r);   // m^(-1/3)
+  const double y = o.mul(o.mul(m, r1), r1);                           // m^(1/3) ∈ [1, 2)
+  return mk64(hi32(y) + (q3 << 20), lo32(y));
+}
+
 // log(x), x > 0 normal.  x = 2^k z, z ∈ [√½, √2); z = c_i(1 + r), |r| ≤ 2^-7; table holds 1/c_i and log c_i.
 template <class O> NE_HD double log_pos(O& o, const double* __restrict__ tab, const MathConsts& C, double x) {
   const int32_t hi = hi32(x);

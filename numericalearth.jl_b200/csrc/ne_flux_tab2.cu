@@ -113,15 +113,21 @@ ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
     if (lane == 0) v = atomicAdd(next_group, 1u);
     return __shfl_sync(0xffffffffu, v, 0);
   };
-  // the next group index is requested one group ahead: its latency hides behind the solve in between
+  // the next group index is requested one group ahead, and so is the next group's row of the permutation: their latencies
+  // hide behind the solve in between
   uint32_t g = grab();
   uint32_t g_next = g < n_groups ? grab() : g;
+  uint32_t p_cur = (SORT && g < n_groups) ? perm[g * 32u + (uint32_t)lane] : 0u;
 #pragma unroll 1
   while (g < n_groups) {
     const uint32_t slot = g * 32u + (uint32_t)lane;                       // position in the (sorted) launch range
-    const uint32_t t = SORT ? (slot & ~(uint32_t)(W - 1)) + perm[slot] : slot;
+    const uint32_t t = SORT ? (slot & ~(uint32_t)(W - 1)) + p_cur : slot;
     g = g_next;
     if (g < n_groups) g_next = grab();
+    const uint32_t slot_next = g * 32u + (uint32_t)lane;
+    if (SORT && g < n_groups) p_cur = perm[slot_next];                    // consumed by the next pass
+    // (an L2 prefetch of the next group's ten input lines from here was measured: 1.360 vs 1.351 ms on C4 — the other five
+    // warps of the scheduler already cover a group's load latency; profiles/r02_notes.md)
     const bool valid = t < n;
     int64_t idx = 0;
     bool not_water = true;

@@ -170,10 +170,10 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
   // are all stable (trip-ordered lanes share the stability regime) skips the cube root — same bits, 25 instructions fewer
   double UG = P.gmin;
   if (__any_sync(__activemask(), Jb > 0.0))
-    UG = dmax(P.gmin, o.mul(P.beta, fm::cbrt_pos(o, T.mc, dmax(o.mul(dmax(0.0, Jb), H.h_bl), T.cbrt_floor))));
-  const double U = fm::sqrt_pos(o, o.fma(UG, UG, slot_ld(col + SL_DUDV2 * NT)));
+    UG = dmax(P.gmin, o.mul(P.beta, fm::cbrt3(o, T.mc, dmax(o.mul(dmax(0.0, Jb), H.h_bl), T.cbrt_floor))));
+  const double U = fm::sqrt3(o, o.fma(UG, UG, slot_ld(col + SL_DUDV2 * NT)));
   // roughness lengths (roughness_lengths.jl:197-246) and 1/L★
-  const double ru = fm::rcp(o, s.ustar);
+  const double ru = fm::rcp3(o, s.ustar);
   const double lu = dmin(o.fma(o.mul(P.a1, s.ustar), s.ustar, o.mul(P.a2, ru)), P.lmax);
   const double Linv = o.mul(o.mul(o.mul(P.kappa, bstar), ru), ru);   // 0 when b★ == 0, i.e. L★ = Inf (:372)
   const double log_lu = fm::log_pos_rep(o, lrep, lc, T.mc, lu);
@@ -220,7 +220,7 @@ __device__ __forceinline__ void tab2_iteration(O& o, const FastParams& P, const 
   // Π = log(Δh/ℓ) − ψ(Δh/L★) + ψ(ℓ/L★), χ = ϰ/Π (:242-247, 375-377)
   const double Pi_u = o.add(o.sub(o.sub(log_dh, log_lu), pm_h), pm_l);
   const double Pi_s = o.add(o.sub(o.sub(log_dh, log_ls), ps_h), ps_l);
-  const double r = fm::rcp(o, o.mul(Pi_u, Pi_s));
+  const double r = fm::rcp3(o, o.mul(Pi_u, Pi_s));
   const double ru_ = o.mul(Pi_s, r), rs_ = o.mul(Pi_u, r);           // 1/Π_u, 1/Π_s
   double chi_u = o.mul(P.kappa, ru_), chi_s = o.mul(P.kappa, rs_);
   chi_u = o.fma(o.fma(-Pi_u, chi_u, P.kappa), ru_, chi_u);
@@ -271,16 +271,16 @@ __device__ __forceinline__ bool tab2_first_trip(O& o, const FastParams& P, const
   const bool mine = F.ok && s.bstar > 0.0 && zh >= T.z_sat && zu >= T.z_sat && !out_s && !fm::psi_is_tiny(zs);
   if (!__all_sync(__activemask(), mine)) return false;
   record = fm::psi_interval(zh, out_h);
-  const double U = fm::sqrt_pos(o, o.fma(P.gmin, P.gmin, slot_ld(col + SL_DUDV2 * NT)));
+  const double U = fm::sqrt3(o, o.fma(P.gmin, P.gmin, slot_ld(col + SL_DUDV2 * NT)));
   // ψ_m, ψ_s on the saturated stable branch (tab2_psi_stable with ζ ≥ ζ_sat: the same operations)
   const double pm_h = o.sub(o.fma(-o.mul(P.m_Cp, o.sub(zh, P.m_Dp)), T.em_sat, -o.mul(P.m_Bp, zh)), P.m_CpDp);
   const double pm_l = o.sub(o.fma(-o.mul(P.m_Cp, o.sub(zu, P.m_Dp)), T.em_sat, -o.mul(P.m_Bp, zu)), P.m_CpDp);
   const double x = o.fma(P.s_Bp, zh, 1.0);
-  const double ps_h = o.sub(o.fma(-o.mul(P.s_Bp, o.sub(zh, P.s_Dp)), T.es_sat, -o.mul(x, fm::sqrt_pos(o, x))), P.s_Ep);
+  const double ps_h = o.sub(o.fma(-o.mul(P.s_Bp, o.sub(zh, P.s_Dp)), T.es_sat, -o.mul(x, fm::sqrt3(o, x))), P.s_Ep);
   const double ps_l = fm::psi_single(o, tab + fm::TAB_PSI + ivs * fm::PSI_REC, zs, 1);
   const double Pi_u = o.add(o.sub(o.sub(F.log_dh0, F.log_lu0), pm_h), pm_l);
   const double Pi_s = o.add(o.sub(o.sub(F.log_dh0, F.log_ls0), ps_h), ps_l);
-  const double r = fm::rcp(o, o.mul(Pi_u, Pi_s));
+  const double r = fm::rcp3(o, o.mul(Pi_u, Pi_s));
   const double ru_ = o.mul(Pi_s, r), rs_ = o.mul(Pi_u, r);
   double chi_u = o.mul(P.kappa, ru_), chi_s = o.mul(P.kappa, rs_);
   chi_u = o.fma(o.fma(-Pi_u, chi_u, P.kappa), ru_, chi_u);

@@ -41,6 +41,8 @@ def test_short_exponential_and_saturated_constants(report):
     assert report["exp_sat_rel"] <= 1e-15 and report["z_sat_ok"] == 1
     # w = a|ζ| + b from the mantissa bits of |ζ| and the per-lane-class copy of the log table change no bit
     assert report["bit_w_and_replicated_log_same_bits"] == 1
+    # one third-order step from the seed instead of two Newton steps (units 2^-53)
+    assert report["rcp3_ulp"] <= 2.0 and report["sqrt3_ulp"] <= 2.5 and report["cbrt3_ulp"] <= 5.0
 
 
 def test_psi_tables_reproduce_the_closed_forms(report):
@@ -64,3 +66,27 @@ def test_general_psi_tables_sea_ice_and_large_yeager_pairs(report):
     assert report["psi_seaice_general"] == 1
     assert report["psi_seaice_fit_err"] <= 1e-15 and report["psi_seaice_dense_err"] <= 1e-15
     assert report["psi_ly_fit_err"] <= 1e-15 and report["psi_ly_dense_err"] <= 1e-15
+
+
+@pytest.mark.gpu
+def test_device_functions_against_long_double(tmp_path):
+    """The same functions as the kernels run them, with the MUFU seeds of the real hardware (tools/fastmath_gpu_check.cu):
+    units 2^-53 relative.  The one-step third-order forms (rcp3 / sqrt3 / cbrt3) need seeds of ≥ 20 bits — this is where
+    that assumption is checked."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "fastmath_gpu_check")
+    r = subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe,
+                        os.path.join(ROOT, "tools", "fastmath_gpu_check.cu")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    rep = json.loads(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)
+    print("DEVICE_FASTMATH", json.dumps(rep))
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "fastmath_gpu_check.json"), "w") as f:
+            json.dump(rep, f)
+    assert rep["rcp_ulp"] <= 2.0 and rep["sqrt_ulp"] <= 2.0 and rep["cbrt_ulp"] <= 3.0
+    assert rep["rcp3_ulp"] <= 2.0 and rep["sqrt3_ulp"] <= 2.5 and rep["cbrt3_ulp"] <= 5.0
+    assert rep["log_ulp"] <= 4.0 and rep["log_rep_ulp"] <= 4.0 and rep["exp_ulp"] <= 3.0
+    assert rep["exp_lo_rel"] <= 3e-12

@@ -103,6 +103,10 @@ int main() {
   double e_sqrt = max_ulp([](double x) { return fm::sqrt_pos(x); }, [](long double x) { return sqrtl(x); }, 1e-8, 1e8, true, 400000, rng);
   double e_cbrt = max_ulp([&](double x) { return fm::cbrt_pos(T.mc, x); }, [](long double x) { return cbrtl(x); }, 1e-12, 1e12, true, 400000, rng);
   double e_cbrt2 = max_ulp([&](double x) { return fm::cbrt_pos(T.mc, x); }, [](long double x) { return cbrtl(x); }, 1e-300, 1e300, true, 400000, rng);
+  fm::OpsPlain ops;
+  double e_rcp3 = max_ulp([&](double x) { return fm::rcp3(ops, x); }, [](long double x) { return 1 / x; }, 1e-6, 1e6, true, 400000, rng);
+  double e_sqrt3 = max_ulp([&](double x) { return fm::sqrt3(ops, x); }, [](long double x) { return sqrtl(x); }, 1e-8, 1e8, true, 400000, rng);
+  double e_cbrt3 = max_ulp([&](double x) { return fm::cbrt3(ops, T.mc, x); }, [](long double x) { return cbrtl(x); }, 1e-300, 1e300, true, 400000, rng);
   // log: relative error away from 1, absolute error (in units of 2^-53) near 1
   double e_log = max_ulp([&](double x) { return fm::log_pos(tab, T.mc, x); }, [](long double x) { return logl(x); }, 1e-12, 0.5, true, 400000, rng);
   double e_log_hi = max_ulp([&](double x) { return fm::log_pos(tab, T.mc, x); }, [](long double x) { return logl(x); }, 2.0, 1e12, true, 400000, rng);
@@ -272,6 +276,7 @@ int main() {
   const double dense_i = dense_general(fi, tab_i, rng), dense_l = dense_general(fl, tab_l, rng);
   printf("{\"psi_far_err\": %.3e, \"atan_large_abs\": %.3e, \"psi_micro_abs\": %.3e, ", e_far, e_atan, e_micro);
   printf("\"bit_w_and_replicated_log_same_bits\": %d, ", bits_ok);
+  printf("\"rcp3_ulp\": %.3f, \"sqrt3_ulp\": %.3f, \"cbrt3_ulp\": %.3f, ", e_rcp3, e_sqrt3, e_cbrt3);
   printf("\"exp_lo_rel\": %.3e, \"exp_sat_rel\": %.3e, \"z_sat_ok\": %d, ", e_exp_lo, e_sat, sat_ok);
   printf("\"psi_seaice_fit_err\": %.3e, \"psi_seaice_dense_err\": %.3e, \"psi_seaice_general\": %d, "
          "\"psi_ly_fit_err\": %.3e, \"psi_ly_dense_err\": %.3e, ", fit_i, dense_i, Ti.general_psi, fit_l, dense_l);
