@@ -4,7 +4,7 @@
 // SimilarityTheoryFluxes defaults + BulkTemperature + scalar surface/boundary-layer heights; every other tree keeps
 // the kernels of ne_flux_kernels.cu.  See ne_flux_tab2.cuh for what changed in the iteration.
 //
-// Launch shape: persistent 256-thread CTAs, 3 per SM (80 registers); a CTA stages the 44 KB solver table in shared memory
+// Launch shape: one persistent 768-thread CTA per SM (24 warps, 80 registers); the CTA stages the 44 KB solver table in shared memory
 // once, then each of its warps draws groups of 32 points from a global counter (so the load balances itself whatever the
 // land mask and the trip counts look like) and the warps never synchronise again.
 //
@@ -80,19 +80,25 @@ trip_order_kernel(const uint16_t* __restrict__ hint, const uint32_t n, uint16_t*
 // sorted points from a global counter until the launch range is exhausted and never synchronise.  (Round 2 first shipped
 // one 1024-point window per CTA: the table was staged 7100 times per C4 launch and a CTA's fast warps idled until its
 // slowest one had finished — 15 % of the warp slots, ncu `sm__warps_active` 32 % of a possible 37.5 %.)
-template <class CT, bool SORT, class O>
-__global__ void __launch_bounds__(256, 3)
+// Shape of a CTA: NW warps, REGS registers per thread; everything in dynamic shared memory:
+//   [ solver table | log table per lane class | SL_COUNT columns of NW*32 doubles | parameters of the rare paths ]
+template <int NW> constexpr size_t tab2_smem_bytes() {
+  return sizeof(double) * (fm::TAB_SIZE + 2 * fm::LOG_N * fm::LOG_REP + SL_COUNT * NW * 32) + sizeof(Tab2Rare);
+}
+
+template <class CT, bool SORT, class O, int NW, int REGS>
+__global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS)
 ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_constant__ Layout L,
                     const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P,
                     const __grid_constant__ TabParams T, const __grid_constant__ Micro Mi,
                     const __grid_constant__ Tab2First F, const double* __restrict__ gtab,
                     const uint16_t* __restrict__ perm, uint16_t* __restrict__ hint, unsigned long long* __restrict__ counts,
                     uint32_t* __restrict__ next_group) {
-  constexpr int NT = 256, W = TAB2_WINDOW;
-  extern __shared__ __align__(16) double tab[];   // fm::TAB_SIZE doubles (dynamic: see allow_table_smem)
-  __shared__ double park[SL_COUNT][NT];
-  __shared__ __align__(16) double lrep[2 * fm::LOG_N * fm::LOG_REP];   // the log table once per lane class (fm::log_pos_rep)
-  __shared__ Tab2Rare rare;
+  constexpr int NT = NW * 32, W = TAB2_WINDOW;
+  extern __shared__ __align__(16) double tab[];   // fm::TAB_SIZE doubles, then:
+  double* const lrep = tab + fm::TAB_SIZE;         // the log table once per lane class (fm::log_pos_rep)
+  double* const park = lrep + 2 * fm::LOG_N * fm::LOG_REP;
+  Tab2Rare& rare = *reinterpret_cast<Tab2Rare*>(park + SL_COUNT * NT);
   if (threadIdx.x == 0) { rare.P = P; rare.T = T; }
   for (int k = threadIdx.x; k < fm::TAB_SIZE / 2; k += NT)
     reinterpret_cast<double2*>(tab)[k] = __ldg(reinterpret_cast<const double2*>(gtab) + k);
@@ -105,7 +111,7 @@ ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
   const bool celsius = d.ocean.temperature_units == NE_DEGREES_CELSIUS;
   const bool relative = d.properties.velocity_formulation == NE_VEL_RELATIVE;
   const int lane = threadIdx.x & 31, tid = threadIdx.x;
-  double* const col = &park[0][tid];
+  double* const col = park + tid;
   const Tab2Heights H = {d.boundary_layer_height.value, d.surface_layer_height.value - P.d_zero, T.log_hd};
   unsigned long long warp_trips = 0;
   auto grab = [&]() {
@@ -221,12 +227,12 @@ static uint32_t* tab2_counter() {
   return q.dptr;
 }
 
-static unsigned tab2_grid(uint32_t n_groups) {
+static unsigned tab2_grid(uint32_t n_groups, int warps, int ctas_per_sm) {
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const uint32_t ctas_needed = (n_groups + 7) / 8;
-  return std::max(1u, std::min<uint32_t>(ctas_needed, (uint32_t)sms * 3u));
+  const uint32_t ctas_needed = (n_groups + warps - 1) / warps;
+  return std::max(1u, std::min<uint32_t>(ctas_needed, (uint32_t)(sms * ctas_per_sm)));
 }
 
 bool tab2_eligible(const NeAtmosOceanDesc& d, const TabParams& TP) {
@@ -236,7 +242,7 @@ bool tab2_eligible(const NeAtmosOceanDesc& d, const TabParams& TP) {
   return n > 0 && n < ((int64_t)1 << 31) - TAB2_WINDOW;
 }
 
-template <class CT>
+template <class CT, int NW, int REGS, int CTAS>
 static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P, const TabParams& TP, const Micro& Mi,
                          const Tab2First& F, const double* tab, cudaStream_t s, unsigned long long* counts, uint16_t* perm, uint16_t* hint, uint32_t n) {
   constexpr int W = TAB2_WINDOW;
@@ -249,13 +255,14 @@ static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastP
     trip_order_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm);
     NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(trip order)");
   }
-  const unsigned grid = tab2_grid(n_windows * (W / 32));
+  const unsigned grid = tab2_grid(n_windows * (W / 32), NW, CTAS);
   const Thermo<CT> th = Thermo<CT>::make(d.thermo);
+  constexpr size_t smem = tab2_smem_bytes<NW>();
 #define NE_TAB2_GO(SORT, O)                                                                                              \
   do {                                                                                                                   \
-    if (cudaError_t e = allow_table_smem<ao_flux_tab2_kernel<CT, SORT, O>>(); e != cudaSuccess)                          \
+    if (cudaError_t e = allow_table_smem<ao_flux_tab2_kernel<CT, SORT, O, NW, REGS>>(smem); e != cudaSuccess)            \
       return cuda_error(e, "ne_atmosphere_ocean_fluxes(tab2: shared memory opt-in)");                                    \
-    ao_flux_tab2_kernel<CT, SORT, O><<<grid, 256, TAB_SMEM_BYTES, s>>>(d, L, th, P, TP, Mi, F, tab, perm, hint, counts, counter); \
+    ao_flux_tab2_kernel<CT, SORT, O, NW, REGS><<<grid, NW * 32, smem, s>>>(d, L, th, P, TP, Mi, F, tab, perm, hint, counts, counter); \
   } while (0)
   if (counts) {
     if (perm) NE_TAB2_GO(true, fm::OpsCount); else NE_TAB2_GO(false, fm::OpsCount);
@@ -279,8 +286,18 @@ int launch_tab2(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P,
   if (!env_flag("NE_B200_TAB2_NO_ORDER"))
     if (const OrderBuf* ob = order_buffer(d.friction_velocity, n, d.grid.i_lo, d.grid.j_lo)) { perm = ob->perm; hint = ob->hint; }
   const Tab2First F = make_tab2_first(P, TP, host_tab, d.surface_layer_height.value - P.d_zero, TP.log_hd);
-  if (d.thermo.dtype == NE_F64) return launch_tab2_t<double>(d, L, P, TP, Mi, F, tab, s, counts, perm, hint, n);
-  return launch_tab2_t<float>(d, L, P, TP, Mi, F, tab, s, counts, perm, hint, n);
+  // CTA shape (NE_B200_TAB2_SHAPE; C4: 1.322 / 1.355 / 1.278 ms): 0 = 8 warps x 3 CTAs per SM at 80 registers, 1 = 32 warps x 1 CTA at 64
+  // registers (a third more resident warps, but the spills push the L1TEX data pipe to 81 %), 2 = 24 warps x 1 CTA at 80 registers (shipped:
+  // one table per SM instead of three)
+  const int shape = counts ? 0 : env_int("NE_B200_TAB2_SHAPE", 2);
+  const bool f64 = d.thermo.dtype == NE_F64;
+#define NE_TAB2_SHAPE(NW, REGS, CTAS)                                                                            \
+  return f64 ? launch_tab2_t<double, NW, REGS, CTAS>(d, L, P, TP, Mi, F, tab, s, counts, perm, hint, n)          \
+             : launch_tab2_t<float, NW, REGS, CTAS>(d, L, P, TP, Mi, F, tab, s, counts, perm, hint, n)
+  if (shape == 1) { NE_TAB2_SHAPE(32, 64, 1); }
+  if (shape == 2) { NE_TAB2_SHAPE(24, 80, 1); }
+  NE_TAB2_SHAPE(8, 80, 3);
+#undef NE_TAB2_SHAPE
 }
 
 }  // namespace ne
