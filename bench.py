@@ -302,8 +302,11 @@ def b200_arm(args):
         ci.initialize()
         ci.update_state(0.37 * 10800.0)
         torch.cuda.synchronize()
-        _, _, warp_trip_rows = sharding.gather_row_statistics(backend.to_numpy(grid.interior(ci.ao_iterations)), grid)
-        weights = sharding.measured_row_weights(cfg["nx"], warp_trip_rows)
+        active_rows, trip_rows, warp_trip_rows = sharding.gather_row_statistics(backend.to_numpy(grid.interior(ci.ao_iterations)), grid)
+        if args.dtype == "f64":   # trip-ordered solve: a warp's lanes leave the loop together, the cost is the plain trip sum
+            weights = sharding.ordered_row_weights(cfg["nx"], active_rows, trip_rows)
+        else:
+            weights = sharding.measured_row_weights(cfg["nx"], warp_trip_rows)
         new_grid = sharding.band_grid(cfg["nx"], cfg["ny"], cfg["latitude"], rank, world, FT=args.dtype, weights=weights)
         moved = torch.tensor([int((new_grid.j_offset, new_grid.ny) != (grid.j_offset, grid.ny))], device=backend.device)
         dist.all_reduce(moved)
@@ -388,6 +391,20 @@ def b200_arm(args):
     atm_desc, rad_desc = fused.atmosphere, fused.radiation
     reps = max(5, min(args.steps, 20))
     ms_ao = timed(lambda: lib.call("atmosphere_ocean_fluxes", args.dtype, ao_desc, stream), reps) / reps
+    # this rank's own solve time (`timed` returns the max over ranks): how well the bands are balanced
+    per_rank_ao = None
+    if world > 1:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            lib.call("atmosphere_ocean_fluxes", args.dtype, ao_desc, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([e0.elapsed_time(e1) / reps], device=backend.device, dtype=torch.float64)
+        allt = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allt, mine)
+        per_rank_ao = [round(float(x.item()), 4) for x in allt]
     ms_ia = timed(lambda: lib.call("interp_state", args.dtype, atm_desc, stream), reps) / reps
     ms_ir = timed(lambda: lib.call("interp_state", args.dtype, rad_desc, stream), reps) / reps
     ms_as = timed(lambda: lib.call("assemble_net_ocean_fluxes", args.dtype, fused.assemble, stream), reps) / reps
@@ -592,6 +609,7 @@ def b200_arm(args):
                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / peaks["hbm_gbs"],
                              "peak_source": peak_src, "ms_per_launch": ms_ia,
                              "traffic": (traffic or {}).get("interp_bytes")},
+            "per_rank_solve_ms": per_rank_ao,
             "kernel_ms": {"interp_radiation": ms_ir, "interp_atmosphere": ms_ia, "atmosphere_ocean_fluxes": ms_ao,
                           "assemble_net_ocean_fluxes": ms_as, "apply_radiative_fluxes": ms_ap, "diag_reduce": ms_dg,
                           "step_with_unfused_post_solve_kernels": ms_unfused_step,

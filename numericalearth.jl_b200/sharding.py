@@ -48,6 +48,16 @@ def measured_row_weights(nx, warp_trips_per_row, per_point=2.6):
     return np.asarray(warp_trips_per_row, dtype=np.float64) + per_point * float(nx)
 
 
+def ordered_row_weights(nx, active_per_row, trips_per_row, per_active=1.5, per_point=3.4):
+    """Per-row cost for the TRIP-ORDERED solve (ne_flux_tab2.cu): the lanes of a warp leave the loop together (lane
+    efficiency 97 %), so a row costs the plain sum of its trips, plus `per_active` trip-equivalents per solved point for
+    the prologue / epilogue (~600 of ~400 instructions per trip) and `per_point` for the HBM-bound kernels every launch
+    point pays (C4 on B200: solve 1.28 ms for 69.1 M thread-trips = 18.5 ps per trip, interpolation + post-solve 0.46 ms
+    for 7.27 M points = 63 ps per point)."""
+    return (np.asarray(trips_per_row, dtype=np.float64) + per_active * np.asarray(active_per_row, dtype=np.float64) +
+            per_point * float(nx))
+
+
 def gather_row_statistics(iterations_interior, grid, group=None):
     """All ranks: per-row (active points, trips, warp-slot trips) of the GLOBAL grid from each band's
     iteration-count field (rows 1..ny of the band's launch window; one small all_gather_object)."""
