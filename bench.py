@@ -595,6 +595,12 @@ def b200_arm(args):
                          "what": "EXECUTED thread-level FP64 flop of one launch (DFMA = 2, DMUL = DADD = 1; counted in this run by "
                                  "the counting instantiation of the same kernel source, ne_count_solve_ops_f64) / CUDA-event time of the launch",
                          "executed_counts": counts,
+                         # the attainable flop rate of THIS instruction mix: every FP64 instruction occupies the pipe like a DFMA
+                         # but DMUL / DADD carry one flop
+                         "frac_of_mix_peak": ((counts["dfma"] + counts["dmul"] + counts["dadd"]) * 2.0 / (ms_ao * 1e-3) / 1e12 / fp64_peak)
+                         if have_counts and fp64_peak else None,
+                         "frac_of_mix_peak_note": "FP64 instructions x 2 / time / DFMA peak = share of the FP64 pipe's issue rate the solve uses "
+                                                  "(ncu sm__pipe_fp64_cycles_active of the same kernel: profiles/r02_notes.md)",
                          "lane_efficiency": (counts["thread_trips"] / (32.0 * counts["warp_trips"])) if have_counts and counts["warp_trips"] else None,
                          "traffic": (traffic or {}).get("ao_flux_bytes"), "traffic_source": (traffic or {}).get("source"),
                          "peak_source": "measured in this run by ne_measure_fp64_peak (DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
@@ -602,7 +608,7 @@ def b200_arm(args):
                          "algorithmic": {"achieved": algorithmic_tf, "frac_of_peak": algorithmic_tf / fp64_peak if fp64_peak else None,
                                          "flop_per_iteration": F_ITER, "flop_epilogue": F_EPI,
                                          "note": "as-written census of the reference's iteration (SURVEY 8(d) weights): the table-driven "
-                                                 "kernel executes ~8x fewer flops, so this is NOT a fraction of peak; side note only"},
+                                                 "kernel executes ~20x fewer flops, so this is NOT a fraction of peak; side note only"},
                          "mean_iterations_active": iters_sum / max(n_active, 1), "max_iterations": int(it.max()),
                          "active_points": n_active, "points_per_launch": int(local_points)},
             "roofline_hbm": {"bound": "hbm", "kernel": "interp_staged_kernel(atmosphere)", "achieved": hbm_achieved,

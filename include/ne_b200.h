@@ -635,6 +635,15 @@ int ne_interp_and_ao_fluxes_f32(const NeFusedStepDesc*, void* stream);
 int ne_diag_reduce_f64(const NeDiagDesc*, void* stream);
 int ne_diag_reduce_f32(const NeDiagDesc*, void* stream);
 
+/* The one collective of the path (north_star: "NCCL over NVLink only for the global flux and conservation
+ * diagnostics reduction"; the reference sums the lazy global integrals of src/Diagnostics/interface_fluxes.jl:90-195 over its
+ * MPI ranks).  In-place sum of `n` doubles (`sums`: device memory, normally NeDiagDesc.result) over the ranks of an NCCL
+ * communicator, enqueued on `stream` behind the kernels that produce the sums.  `nccl_comm` is the host's own ncclComm_t
+ * (NCCL.jl: `comm.handle`; one process per GPU): the library does not create communicators.  NCCL is bound at run time
+ * (dlopen of libnccl.so.2, NE_B200_NCCL_LIB overrides the name), so single-GPU hosts need no NCCL; returns NE_E_NO_VARIANT
+ * when the library cannot be loaded and NE_E_CUDA with the NCCL error string when the call fails. */
+int ne_diag_allreduce_f64(void* nccl_comm, double* sums, int32_t n, void* stream);
+
 /* Host-buffer convenience used by the end-to-end benchmark and by hosts without device
  * arrays: copies a contiguous host block to/from the device on `stream`. */
 int ne_memcpy_h2d(void* dst_device, const void* src_host, uint64_t bytes, void* stream);

@@ -823,9 +823,9 @@ end
 ##### conservation checks of a run sharded in latitude bands — the ONE place this path has a collective.
 #####
 # `ne_diag_reduce_*` leaves n_fields doubles in `result` (device) in a fixed summation order; a run on N GPUs (one rank per
-# GPU: MPI.jl / Oceananigans' Distributed) sums the N result vectors with NCCL.jl (`NCCL.Allreduce!(result, +, comm)` on the
-# same stream: 56 bytes, latency-bound, NVLS when available) or, CUDA-aware, `MPI.Allreduce!`.  The library itself stays
-# free of a communicator: the collective is the caller's, as every other MPI call of an Oceananigans run is.
+# GPU: MPI.jl / Oceananigans' Distributed) sums the N result vectors with `ne_diag_allreduce_f64(comm, result, n, stream)`:
+# NCCL bound at run time by the library, the communicator is the host's own (NCCL.jl: `comm.handle`, created once from the
+# MPI communicator of the run); 56 bytes, latency-bound, on the same stream behind the reduction kernels.
 
 struct FluxDiagnostics{R, P, A}
     result :: R      # CuVector{Float64}(n_fields)
@@ -838,6 +838,13 @@ FluxDiagnostics(n_fields::Int; area = nothing, n_blocks = 1184) =
     FluxDiagnostics(CUDA.zeros(Float64, n_fields), CUDA.zeros(Float64, n_blocks * n_fields), area, n_blocks)
 
 "sum_i area_i field_i over active cells for every field of `fields` (Fields on the exchange grid); returns diag.result (device)"
+"in-place sum of a device vector of Float64 over the ranks of an NCCL communicator (`comm.handle` of NCCL.jl)"
+function allreduce_fluxes!(result, nccl_comm::Ptr{Cvoid})
+    check(ccall((:ne_diag_allreduce_f64, libne[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}),
+                nccl_comm, devptr(result), Int32(length(result)), stream()))
+    return result
+end
+
 function reduce_fluxes!(diag::FluxDiagnostics, grid, fields; allreduce! = identity)
     enabled() || error("reduce_fluxes! needs libne_b200 (NE_B200_LIB)")
     length(fields) <= NE_DIAG_MAX_FIELDS || error("at most $NE_DIAG_MAX_FIELDS fields per reduction")
@@ -846,7 +853,7 @@ function reduce_fluxes!(diag::FluxDiagnostics, grid, fields; allreduce! = identi
                    area = devptr(diag.area), inactive = maskptr(grid), partial = devptr(diag.partial), n_blocks = diag.n_blocks,
                    result = devptr(diag.result))
     GC.@preserve diag fields check(ccall((entry("ne_diag_reduce", grid), libne[]), Cint, (Ref{NeDiagDesc}, Ptr{Cvoid}), d, stream()))
-    allreduce!(diag.result)        # e.g. r -> NCCL.Allreduce!(r, r, +, comm; stream = CUDA.stream())
+    allreduce!(diag.result)        # e.g. r -> allreduce_fluxes!(r, comm.handle)
     return diag.result
 end
 

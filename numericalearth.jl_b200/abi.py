@@ -326,7 +326,7 @@ OTHER_ENTRY_POINTS = ["ne_version", "ne_last_error", "ne_device_count", "ne_memc
                       "ne_stream_synchronize", "ne_measure_fp64_peak", "ne_struct_size", "ne_host_pipeline_create",
                       "ne_host_pipeline_destroy", "ne_host_pipelined_step_f64", "ne_host_pipelined_step_f32",
                       "ne_series_ring_create", "ne_series_ring_destroy", "ne_series_ring_load", "ne_series_ring_acquire",
-                      "ne_series_ring_release", "ne_count_solve_ops_f64"]
+                      "ne_series_ring_release", "ne_count_solve_ops_f64", "ne_diag_allreduce_f64"]
 
 
 def all_entry_points():

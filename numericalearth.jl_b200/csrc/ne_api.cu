@@ -1,4 +1,7 @@
 // ne_api.cu — library plumbing: version, thread-local error, copies, FP64 peak microbenchmark.
+#include <dlfcn.h>
+#include <mutex>
+#include <cstdlib>
 #include <cstdarg>
 
 #include "ne_common.cuh"
@@ -74,6 +77,51 @@ int ne_memcpy_h2d(void* dst, const void* src, uint64_t bytes, void* stream) {
 int ne_memcpy_d2h(void* dst, const void* src, uint64_t bytes, void* stream) {
   cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
   return e == cudaSuccess ? NE_OK : ne::cuda_error(e, "ne_memcpy_d2h");
+}
+
+// ---- the diagnostics all-reduce: NCCL bound at run time -----------------------------------------------------------
+namespace {
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*nccl_errstr_fn)(int);
+struct NcclBinding { void* handle = nullptr; nccl_allreduce_fn all_reduce = nullptr; nccl_errstr_fn err = nullptr; bool tried = false; };
+NcclBinding& nccl_binding() {
+  static NcclBinding b;
+  static std::mutex m;
+  std::lock_guard<std::mutex> lock(m);
+  if (!b.tried) {
+    b.tried = true;
+    const char* name = std::getenv("NE_B200_NCCL_LIB");
+    const char* names[] = {name, "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n || !n[0]) continue;
+      // a host that already carries NCCL (NCCL.jl, torch) has it mapped: RTLD_NOLOAD finds that copy first
+      b.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD);
+      if (!b.handle) b.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (b.handle) break;
+    }
+    if (b.handle) {
+      b.all_reduce = (nccl_allreduce_fn)dlsym(b.handle, "ncclAllReduce");
+      b.err = (nccl_errstr_fn)dlsym(b.handle, "ncclGetErrorString");
+    }
+  }
+  return b;
+}
+}  // namespace
+
+int ne_diag_allreduce_f64(void* nccl_comm, double* sums, int32_t n, void* stream) {
+  NE_REQUIRE(nccl_comm != nullptr && sums != nullptr && n > 0, "diag_allreduce: null communicator / buffer or n <= 0");
+  NcclBinding& b = nccl_binding();
+  if (!b.all_reduce) {
+    ne::set_error("diag_allreduce: NCCL is not available in this process (dlopen libnccl.so.2 failed; set NE_B200_NCCL_LIB)");
+    return NE_E_NO_VARIANT;
+  }
+  // ncclFloat64 = 8, ncclSum = 0 (nccl.h; stable since NCCL 2.0)
+  const int rc = b.all_reduce(sums, sums, (size_t)n, 8, 0, nccl_comm, (cudaStream_t)stream);
+  if (rc != 0) {
+    ne::set_error("diag_allreduce: ncclAllReduce failed: %s", b.err ? b.err(rc) : "unknown NCCL error");
+    return NE_E_CUDA;
+  }
+  return NE_OK;
 }
 
 int ne_stream_synchronize(void* stream) {

@@ -229,6 +229,184 @@ static bool try_staged(const NeInterpDesc& d, const Layout& L, const InterpSourc
   return true;
 }
 
+// ---- tiled variant (round 2) ----------------------------------------------------------------------------
+// ncu on the staged kernel above (7 series: 0.149 ms = 48 % of the copy peak; 525 instructions per warp, issue slots 74 %
+// busy, DRAM 34 %): it is instruction-issue bound — 8 LDS.32 + 14 separately rounded Float32 operations + a Float64 time
+// blend per value, and per 256 outputs one window search (two block reductions) and one staging pass.  This kernel keeps
+// the staging idea and changes its granularity:
+//   * a block owns a tile of 256 columns x TR rows of the exchange grid: the rows of a tile fall into the same two or three
+//     source rows, so ONE window search and ONE staging pass serve TR x 256 outputs;
+//   * the window is stored cell-major: all series and both time levels of a source cell are contiguous (16-byte chunks
+//     of {series a level 1, a level 2, series b level 1, b level 2} for Float32 data), cells padded to an odd number of
+//     chunks (conflict-free for the ~6 neighbouring cells a warp touches): a corner of two series and both levels is one
+//     LDS.128 — 20 shared-memory loads per point instead of 72 for 9 series.
+// Same __*_rn sequence per value as the other two kernels: bit-identical results (tested).  Measured on C4 (B200, ms per
+// launch; staged / tiles of 1 / 2 / 4 rows): 7 series 0.149 / 0.177 / 0.155 / 0.160, merged 9 series (step time) 1.684 /
+// 1.734 / 1.702 / 1.729, 2 series 0.101 / 0.099 / 0.080 / 0.087.  The per-row state of a tile (interpolators of TR points)
+// costs registers — 48 / 64 against 40, i.e. 5 / 4 resident blocks per SM against 8 — and that outweighs the instructions
+// saved wherever there are many series; the tiled kernel therefore only takes launches of at most two series (a radiation
+// component on its own source grid), two rows per tile.
+// (cp.async.bulk.tensor for the staging copy: the row pitch of the source planes is (Nx + 2 Hx) x 4 B = 2584 B for JRA55, not
+// a multiple of 16 B, so cuTensorMapEncodeTiled rejects the array as the host model lays it out; 1-D cp.async.bulk with
+// 16-byte over-fetch would replace ~150 of the ~4800 warp-instructions a block issues: not where the time is.)
+constexpr int TILE_ROWS = 2;
+
+template <class AT> struct TileVec;
+template <> struct TileVec<float> { using type = float4; static constexpr int SERIES = 2; };
+template <> struct TileVec<double> { using type = double2; static constexpr int SERIES = 1; };
+template <class AT> __device__ __forceinline__ AT tile_get(const typename TileVec<AT>::type& v, int k);
+template <> __device__ __forceinline__ float tile_get<float>(const float4& v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
+template <> __device__ __forceinline__ double tile_get<double>(const double2& v, int k) { return k == 0 ? v.x : v.y; }
+
+template <class AT, int NS> struct TileGeom {
+  static constexpr int SPC = TileVec<AT>::SERIES;                 // series per 16-byte chunk
+  static constexpr int CHUNKS = (NS + SPC - 1) / SPC;
+  static constexpr int STRIDE = CHUNKS | 1;                       // chunks per cell, odd
+  static constexpr int CELLS = STG_W * STG_H;
+  static constexpr size_t BYTES = (size_t)CELLS * STRIDE * 16;
+};
+
+template <class FT, class AT, class TT, int NS, int TR>
+__global__ void __launch_bounds__(256, 5)
+interp_tile_kernel(const __grid_constant__ NeInterpDesc d, const __grid_constant__ Layout L,
+                   const __grid_constant__ InterpSource S, const __grid_constant__ StagedPlan<NS> P) {
+  using G = TileGeom<AT, NS>;
+  using V = typename TileVec<AT>::type;
+  __shared__ __align__(16) V win[G::CELLS * G::STRIDE];
+  __shared__ int32_t red[4][8];
+  __shared__ int32_t box[4];
+  const int tid = threadIdx.x;
+  const int32_t tj = blockIdx.x / P.chunks_x;
+  const int32_t li = (blockIdx.x - tj * P.chunks_x) * 256 + tid;
+  const int32_t lj0 = tj * TR;
+  const bool in_x = li < L.ni;
+  int32_t im[TR], ip[TR], jm[TR], jp[TR];
+  AT xi[TR], eta[TR];
+  int64_t idx[TR];
+  int32_t x0 = INT32_MAX, x1 = INT32_MIN, y0 = INT32_MAX, y1 = INT32_MIN;
+#pragma unroll
+  for (int r = 0; r < TR; ++r) {
+    const int32_t lj = min(lj0 + r, L.nj - 1);
+    idx[r] = L.at(L.i_lo + (in_x ? li : L.ni - 1), L.j_lo + lj);
+    const FracPair<AT> fr = load_frac<AT>(d.frac_i, d.frac_j, idx[r]);
+    interpolator<AT>(d.frac_i != nullptr, fr.i, im[r], ip[r], xi[r]);
+    interpolator<AT>(d.frac_j != nullptr, fr.j, jm[r], jp[r], eta[r]);
+    x0 = min(x0, min(im[r], ip[r])); x1 = max(x1, max(im[r], ip[r]));
+    y0 = min(y0, min(jm[r], jp[r])); y1 = max(y1, max(jm[r], jp[r]));
+  }
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+      x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+      y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+      y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = x0; red[1][tid >> 5] = x1; red[2][tid >> 5] = y0; red[3][tid >> 5] = y1; }
+    __syncthreads();
+    if (tid < 4) {
+      int32_t v = red[tid][0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) v = (tid & 1) ? max(v, red[tid][w]) : min(v, red[tid][w]);
+      box[tid] = v;
+    }
+    __syncthreads();
+  }
+  x0 = box[0]; y0 = box[2];
+  const int32_t Wd = box[1] - x0 + 1, Hd = box[3] - y0 + 1;
+  const bool staged = Wd <= STG_W && Hd <= STG_H;
+  const bool same = d.time.same != 0;
+  if (staged) {
+    // thread (g, c) owns window cell (row g, column c): coalesced loads per (series, level) plane, then the cell's chunks
+    const int g = tid >> 6, c = tid & 63;
+    if (g < Hd && c < Wd) {
+      const int64_t o = S.off + x0 + c + (int64_t)(y0 + g) * S.ssx;
+      V* cell = win + (g * STG_W + c) * G::STRIDE;
+#pragma unroll
+      for (int k = 0; k < G::CHUNKS; ++k) {   // a chunk at a time: four loads in flight, no register array of 2 NS values
+        V v;
+        const AT* sa = (const AT*)P.series[k * G::SPC] + o;
+        v.x = __ldg(sa + S.o1);
+        v.y = same ? v.x : __ldg(sa + S.o2);
+        if constexpr (G::SPC == 2) {
+          if (2 * k + 1 < NS) {
+            const AT* sb = (const AT*)P.series[2 * k + 1 < NS ? 2 * k + 1 : 0] + o;
+            v.z = __ldg(sb + S.o1);
+            v.w = same ? v.z : __ldg(sb + S.o2);
+          } else {
+            v.z = v.w = (AT)0;
+          }
+        }
+        cell[k] = v;
+      }
+    }
+    __syncthreads();
+  }
+  if (!in_x) return;
+  const TT nt = (TT)d.time.frac;
+  using W = decltype(AT() * TT());
+  const W cnt = (W)sub_rn((TT)1, nt);
+#pragma unroll
+  for (int r = 0; r < TR; ++r) {
+    if (lj0 + r >= L.nj) break;
+    const AT cx = sub_rn((AT)1, xi[r]), cy = sub_rn((AT)1, eta[r]);
+    const AT w1 = mul_rn(cx, cy), w3 = mul_rn(cx, eta[r]), w5 = mul_rn(xi[r], cy), w7 = mul_rn(xi[r], eta[r]);
+    if (staged) {
+      const V* c_mm = win + ((jm[r] - y0) * STG_W + (im[r] - x0)) * G::STRIDE;
+      const V* c_mp = win + ((jp[r] - y0) * STG_W + (im[r] - x0)) * G::STRIDE;
+      const V* c_pm = win + ((jm[r] - y0) * STG_W + (ip[r] - x0)) * G::STRIDE;
+      const V* c_pp = win + ((jp[r] - y0) * STG_W + (ip[r] - x0)) * G::STRIDE;
+#pragma unroll
+      for (int k = 0; k < G::CHUNKS; ++k) {
+        const V mm = c_mm[k], mp = c_mp[k], pm = c_pm[k], pp = c_pp[k];
+#pragma unroll
+        for (int q = 0; q < G::SPC; ++q) {
+          const int sidx = k * G::SPC + q;
+          if (sidx >= NS) break;
+          const AT p1 = add_rn(add_rn(add_rn(mul_rn(w1, tile_get<AT>(mm, 2 * q)), mul_rn(w3, tile_get<AT>(mp, 2 * q))),
+                                      mul_rn(w5, tile_get<AT>(pm, 2 * q))), mul_rn(w7, tile_get<AT>(pp, 2 * q)));
+          W val;
+          if (same) val = (W)p1;
+          else {
+            const AT p2 = add_rn(add_rn(add_rn(mul_rn(w1, tile_get<AT>(mm, 2 * q + 1)), mul_rn(w3, tile_get<AT>(mp, 2 * q + 1))),
+                                        mul_rn(w5, tile_get<AT>(pm, 2 * q + 1))), mul_rn(w7, tile_get<AT>(pp, 2 * q + 1)));
+            val = add_rn(mul_rn((W)p2, (W)nt), mul_rn((W)p1, cnt));
+          }
+          ((FT*)P.out[sidx])[idx[r]] = (FT)val;
+          if (sidx == P.potential_series) ((FT*)d.potential)[idx[r]] = div_rn((FT)val, (FT)d.ocean_reference_density);
+        }
+      }
+    } else {
+      InterpPoint<AT> p;
+      p.w1 = w1; p.w3 = w3; p.w5 = w5; p.w7 = w7;
+      p.o_mm = S.off + im[r] + jm[r] * S.ssx;
+      p.o_mp = S.off + im[r] + jp[r] * S.ssx;
+      p.o_pm = S.off + ip[r] + jm[r] * S.ssx;
+      p.o_pp = S.off + ip[r] + jp[r] * S.ssx;
+#pragma unroll
+      for (int sidx = 0; sidx < NS; ++sidx) {
+        const W val = interp_series<AT, TT>((const AT*)P.series[sidx], p, S, nt, same);
+        ((FT*)P.out[sidx])[idx[r]] = (FT)val;
+        if (sidx == P.potential_series) ((FT*)d.potential)[idx[r]] = div_rn((FT)val, (FT)d.ocean_reference_density);
+      }
+    }
+  }
+}
+
+template <class FT, class AT, class TT, int NS>
+static bool try_tiled(const NeInterpDesc& d, const Layout& L, const InterpSource& S, cudaStream_t stream) {
+  const char* v1 = std::getenv("NE_B200_INTERP_STAGED_V1");
+  if (v1 && v1[0] == '1') return false;
+  StagedPlan<NS> P;
+  if (!make_staged_plan<NS>(d, L, P)) return false;
+  if (NS > 2) return false;                                       // see the measurements above
+  // the tile's rows must share source rows: exchange grid at least TILE_ROWS times finer in y than the source
+  if (d.grid.ny < TILE_ROWS * d.src_ny) return false;
+  const int64_t tiles_y = (L.nj + TILE_ROWS - 1) / TILE_ROWS;
+  interp_tile_kernel<FT, AT, TT, NS, TILE_ROWS><<<(unsigned)((int64_t)P.chunks_x * tiles_y), 256, 0, stream>>>(d, L, S, P);
+  return true;
+}
+
 // ---- fractional indices ---------------------------------------------------------------------------
 template <class T> __device__ __forceinline__ T m_fmod(T a, T b);
 template <> __device__ __forceinline__ double m_fmod<double>(double a, double b) { return fmod(a, b); }
@@ -292,7 +470,7 @@ static int launch_interp(const NeInterpDesc& d, cudaStream_t stream) {
     if (active == 9) done = try_staged<FT, AT, TT, 9>(d, L, S, stream);   // atmosphere + radiation merged (ne_fused.cu)
     else if (active == 7) done = try_staged<FT, AT, TT, 7>(d, L, S, stream);
     else if (active == 5) done = try_staged<FT, AT, TT, 5>(d, L, S, stream);
-    else if (active == 2) done = try_staged<FT, AT, TT, 2>(d, L, S, stream);
+    else if (active == 2) done = try_tiled<FT, AT, TT, 2>(d, L, S, stream) || try_staged<FT, AT, TT, 2>(d, L, S, stream);
     if (done) {
       NE_CUDA_CHECK_LAUNCH("ne_interp_state(staged)");
       return NE_OK;

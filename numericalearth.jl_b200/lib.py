@@ -88,6 +88,17 @@ class Library:
     def device_count(self):
         return self.dll.ne_device_count()
 
+    def diag_allreduce(self, nccl_comm, sums_ptr, n, stream=0):
+        """ne_diag_allreduce_f64: in-place NCCL sum of `n` device doubles over the ranks of the caller's ncclComm_t
+        (an integer handle), enqueued on `stream`."""
+        self.dll.ne_diag_allreduce_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        rc = self.dll.ne_diag_allreduce_f64(C.c_void_p(nccl_comm), C.c_void_p(sums_ptr), C.c_int32(n), C.c_void_p(stream))
+        if rc != 0:
+            if rc == A.NE_E_NO_VARIANT:
+                from .formulations import NoKernelVariantError
+                raise NoKernelVariantError(self.last_error())
+            raise NeError(rc, self.last_error())
+
     def count_solve_ops(self, desc, stream=0):
         """FP64 instructions one launch of the a–o solve executes on `desc` (ne_count_solve_ops_f64): dict of thread-level
         counts.  Synchronises."""

@@ -4,11 +4,17 @@
 // path, used only as the checker by tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs.  Nothing in the product package may call it.
 //
-// PARITY STATUS: "parity unpinned" at the last-ulp level.  Julia is absent from this
-// container, so the reference itself cannot be run; the oracle is pinned by (a) every
-// known-answer / analytic test the reference's own test-suite holds for this path
-// (tests/test_oracle_reference_kats.py cites them one by one) and (b) line-by-line review
-// against the cited source.  The arithmetic that lives in third-party packages that are
+// PARITY STATUS: pinned by (a) every known-answer / analytic test the reference's own
+// test-suite holds for this path (tests/test_oracle_reference_kats.py cites them one by
+// one; the reference has no golden vectors for converged fluxes: test/test_surface_fluxes.jl:
+// 425-499 is commented out) and (b) an INDEPENDENT restatement in 50-digit arithmetic written
+// from the reference's documentation (oracle/pin/reference_mp.py, no text shared with this
+// file; tests/test_oracle_independent_pin.py: every function within a few ulp, whole fixed
+// points to 1e-12 with equal trip counts; profiles/r02_oracle_pin.jsonl).  NOT pinned against
+// outputs of the reference itself: Julia is absent from this container, so it cannot be run
+// here ("parity unpinned" in that sense); julia/dump_reference.jl produces those outputs from
+// the same raw inputs on any machine that has Julia + NumericalEarth, and
+// tests/golden/make_golden.py diffs them.  The arithmetic that lives in third-party packages that are
 // NOT under /root/reference is restated from their published algorithms and flagged
 // [3rd-party] below:
 //   Thermodynamics.jl  (compat "0.15.3, 1", Project.toml:113)  — saturation_vapor_pressure,
