@@ -560,7 +560,9 @@ typedef struct NeHostStepDesc {
  *     -> read_data (src/DataWrangling/set_region_data.jl:162-163): file index = grid index + BoundingBoxOffset (di, dj),
  *        lat-axis mangling (mangle, :50-53: ShiftSouth reads j - 1, AverageNorthSouth averages j and j + 1; indices
  *        clamped to the file extent), missing value -> NaN, then convert_units (_set_region_kernel!, :200-205;
- *        src/DataWrangling/metadata_field.jl:486-525).  Column regions (a blend of four file cells into one) stay with the host.
+ *        src/DataWrangling/metadata_field.jl:486-525).  A Column region (region_kind = NE_REGION_COLUMN: a 1 x 1 series whose
+ *        value is the NaN-aware blend of the four file cells around a point, blend(::Linear / ::Nearest), :168-193, with the
+ *        bracketing indices and weights of region_info(::Column), :113-118, resolved by the host) goes through the same pass.
  *     -> interior of the slot, then fill_halo_regions!(fts): periodic in x (test/test_jra55.jl:40-47: fts[Nx+1,..] ==
  *        fts[1,..]) or mirrored when the source grid is bounded in x, mirrored (zero-flux) in y.
  * Which time index lives in which slot, and what to prefetch, is host policy (the binding's; series_window.py here). */
@@ -568,6 +570,8 @@ typedef struct NeHostStepDesc {
 enum { NE_CONV_NONE = 0, NE_CONV_NEGATE = 1, NE_CONV_ADD = 2, NE_CONV_SUB = 3, NE_CONV_MUL = 4, NE_CONV_DIV = 5,
        NE_CONV_MUL_DIV = 6 };   /* d, -d, d + a, d - a, d * a, d / a, d * a / b: each one rounding in the series eltype */
 enum { NE_MANGLE_NONE = 0, NE_MANGLE_SHIFT_SOUTH = 1, NE_MANGLE_AVERAGE_NORTH_SOUTH = 2 };
+enum { NE_REGION_BOX = 0, NE_REGION_COLUMN = 1 };        /* whole globe / BoundingBox (di, dj) | Column             */
+enum { NE_COLUMN_LINEAR = 0, NE_COLUMN_NEAREST = 1 };    /* Column(...; interpolation = Linear() | Nearest())       */
 typedef struct NeSeriesRingDesc {
   int32_t n_series;            /* series that share the time axis (<= NE_RING_MAX_SERIES)          */
   int32_t n_slots;             /* Nt_mem: slices each ring holds                                    */
@@ -584,6 +588,13 @@ typedef struct NeSeriesRingDesc {
    * raw_ny == ny - 1 => ShiftSouth, raw_ny == ny + 1 => AverageNorthSouth).                                      */
   int64_t raw_nx, raw_ny, di, dj;
   int32_t mangling[NE_RING_MAX_SERIES];    /* NE_MANGLE_*                                           */
+  /* Column region (ColumnInfo, set_region_data.jl:79-87; nx = ny = 1): 0-based bracketing file indices (i_plus wraps to 0
+   * across the periodic seam), blend weights in [0, 1] (rounded to `dtype` before use, as ColumnInfo holds them in the
+   * target's element type) and the interpolation kind.                                                             */
+  int32_t region_kind;                     /* NE_REGION_*                                           */
+  int32_t column_interpolation;            /* NE_COLUMN_*                                           */
+  int64_t col_i_minus, col_i_plus, col_j_minus, col_j_plus;
+  double col_wx, col_wy;
 } NeSeriesRingDesc;
 
 /* ---- entry points ---------------------------------------------------------------------- */

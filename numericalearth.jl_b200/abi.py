@@ -35,6 +35,8 @@ NE_DEGREES_CELSIUS, NE_DEGREES_KELVIN = range(2)
 NE_ALBEDO_CONSTANT, NE_ALBEDO_LATITUDE_DEPENDENT, NE_ALBEDO_FIELD, NE_ALBEDO_TABULATED, NE_ALBEDO_SEA_ICE = range(5)
 NE_SIO_ICE_BATH, NE_SIO_THREE_EQUATION, NE_SIO_FREEZE_ONLY = range(3)
 NE_USTAR_CONSTANT, NE_USTAR_MOMENTUM_BASED = range(2)
+NE_REGION_BOX, NE_REGION_COLUMN = range(2)
+NE_COLUMN_LINEAR, NE_COLUMN_NEAREST = range(2)
 
 i32, i64, f64, vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
 
@@ -295,7 +297,10 @@ class NeSeriesRingDesc(C.Structure):
                 ("ring", vp * NE_RING_MAX_SERIES), ("conv_kind", i32 * NE_RING_MAX_SERIES),
                 ("conv_a", C.c_double * NE_RING_MAX_SERIES), ("conv_b", C.c_double * NE_RING_MAX_SERIES),
                 ("has_missing", i32 * NE_RING_MAX_SERIES), ("missing_value", C.c_double * NE_RING_MAX_SERIES),
-                ("raw_nx", i64), ("raw_ny", i64), ("di", i64), ("dj", i64), ("mangling", i32 * NE_RING_MAX_SERIES)]
+                ("raw_nx", i64), ("raw_ny", i64), ("di", i64), ("dj", i64), ("mangling", i32 * NE_RING_MAX_SERIES),
+                ("region_kind", i32), ("column_interpolation", i32),
+                ("col_i_minus", i64), ("col_i_plus", i64), ("col_j_minus", i64), ("col_j_plus", i64),
+                ("col_wx", C.c_double), ("col_wy", C.c_double)]
 
 
 STRUCTS = {c.__name__: c for c in [

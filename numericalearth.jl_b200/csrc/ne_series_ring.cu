@@ -41,6 +41,9 @@ struct SlotFillArgs {
   long long nx, ny, hx, hy;
   long long raw_nx, raw_ny, di, dj;
   int periodic_x;
+  int region_kind, column_interpolation;
+  long long col_im, col_ip, col_jm, col_jp;
+  double col_wx, col_wy;
 };
 
 // mirrored (zero-flux) halo index: halo cell -k (k = 1..h) takes interior cell k - 1; n - 1 + k takes n - k
@@ -48,6 +51,53 @@ __device__ __forceinline__ long long mirror_index(long long i, long long n) {
   if (i < 0) i = -i - 1;
   if (i >= n) i = 2 * n - 1 - i;
   return min(max(i, 0LL), n - 1);
+}
+
+// mangle + nan_convert_missing (set_region_data.jl:48-53, :162-163): file indices clamped to the file extent, ShiftSouth reads
+// j - 1, AverageNorthSouth averages j and j + 1, the missing value becomes NaN
+template <typename T>
+__device__ __forceinline__ T ring_read(const T* __restrict__ raw, const SlotFillArgs& a, int mg, long long fi, long long fj, bool hm, T mv) {
+  const long long ii = min(max(fi, 0LL), a.raw_nx - 1);
+  if (mg == NE_MANGLE_SHIFT_SOUTH) fj -= 1;
+  const long long j0 = min(max(fj, 0LL), a.raw_ny - 1);
+  T v = raw[j0 * a.raw_nx + ii];
+  if (mg == NE_MANGLE_AVERAGE_NORTH_SOUTH) {
+    const long long j1 = min(max(fj + 1, 0LL), a.raw_ny - 1);
+    v = (v + raw[j1 * a.raw_nx + ii]) / (T)2;
+  }
+  if (hm && v == mv) v = (T)NAN;
+  return v;
+}
+
+// blend(::Linear) / blend(::Nearest) of a Column region (set_region_data.jl:168-193): land corners (NaN) are dropped and the
+// weights renormalised over the wet ones; NaN only when all four are land.  Every operation in the series element type, in
+// the reference's order (this translation unit is compiled without FMA contraction of these expressions: explicit
+// intrinsics below).
+template <typename T> __device__ __forceinline__ T t_mul(T x, T y);
+template <> __device__ __forceinline__ float t_mul<float>(float x, float y) { return __fmul_rn(x, y); }
+template <> __device__ __forceinline__ double t_mul<double>(double x, double y) { return __dmul_rn(x, y); }
+template <typename T> __device__ __forceinline__ T t_add(T x, T y);
+template <> __device__ __forceinline__ float t_add<float>(float x, float y) { return __fadd_rn(x, y); }
+template <> __device__ __forceinline__ double t_add<double>(double x, double y) { return __dadd_rn(x, y); }
+
+template <typename T>
+__device__ __forceinline__ T column_blend(const T* __restrict__ raw, const SlotFillArgs& a, int mg, bool hm, T mv) {
+  const T wx = (T)a.col_wx, wy = (T)a.col_wy;
+  if (a.column_interpolation == NE_COLUMN_NEAREST) {
+    const long long i = wx >= (T)0.5 ? a.col_ip : a.col_im, j = wy >= (T)0.5 ? a.col_jp : a.col_jm;
+    const T near = ring_read<T>(raw, a, mg, i, j, hm, mv);
+    if (!isnan(near)) return near;        // the closest corner is land: fall back to the NaN-aware linear blend
+  }
+  const T d00 = ring_read<T>(raw, a, mg, a.col_im, a.col_jm, hm, mv), d10 = ring_read<T>(raw, a, mg, a.col_ip, a.col_jm, hm, mv);
+  const T d01 = ring_read<T>(raw, a, mg, a.col_im, a.col_jp, hm, mv), d11 = ring_read<T>(raw, a, mg, a.col_ip, a.col_jp, hm, mv);
+  const T cx = t_add<T>((T)1, -wx), cy = t_add<T>((T)1, -wy);
+  const T w00 = isnan(d00) ? (T)0 : t_mul<T>(cx, cy), w10 = isnan(d10) ? (T)0 : t_mul<T>(wx, cy);
+  const T w01 = isnan(d01) ? (T)0 : t_mul<T>(cx, wy), w11 = isnan(d11) ? (T)0 : t_mul<T>(wx, wy);
+  const T sw = t_add<T>(t_add<T>(t_add<T>(w00, w10), w01), w11);
+  const T num = t_add<T>(t_add<T>(t_add<T>(t_mul<T>(w00, isnan(d00) ? (T)0 : d00), t_mul<T>(w10, isnan(d10) ? (T)0 : d10)),
+                                  t_mul<T>(w01, isnan(d01) ? (T)0 : d01)), t_mul<T>(w11, isnan(d11) ? (T)0 : d11));
+  if (sw == (T)0) return (T)NAN;
+  return num / sw;
 }
 
 // One thread per ring-slice element (interior and halos), blockIdx.y = series.  Each element is ONE read of the raw
@@ -73,18 +123,9 @@ __global__ void __launch_bounds__(256) slot_fill_kernel(const SlotFillArgs a) {
       i = mirror_index(i, a.nx);
     }
     j = mirror_index(j, a.ny);
-    // read_data: region offset, lat-axis mangling with indices clamped to the file extent, missing -> NaN
-    const long long ii = min(max(i + a.di, 0LL), a.raw_nx - 1);
-    long long jj = j + a.dj;
-    const int mg = a.mangling[s];
-    if (mg == NE_MANGLE_SHIFT_SOUTH) jj -= 1;
-    const long long j0 = min(max(jj, 0LL), a.raw_ny - 1);
-    T v = raw[j0 * a.raw_nx + ii];
-    if (mg == NE_MANGLE_AVERAGE_NORTH_SOUTH) {
-      const long long j1 = min(max(jj + 1, 0LL), a.raw_ny - 1);
-      v = (v + raw[j1 * a.raw_nx + ii]) / (T)2;
-    }
-    if (hm && v == mv) v = (T)NAN;
+    T v;
+    if (a.region_kind == NE_REGION_COLUMN) v = column_blend<T>(raw, a, a.mangling[s], hm, mv);
+    else v = ring_read<T>(raw, a, a.mangling[s], i + a.di, j + a.dj, hm, mv);   // read_data(…, ::BoundingBoxOffset, …)
     switch (kind) {
       case NE_CONV_NEGATE: v = -v; break;
       case NE_CONV_ADD: v = v + ca; break;
@@ -117,6 +158,17 @@ int ne_series_ring_create(void** handle, const NeSeriesRingDesc* d) {
     NE_REQUIRE(d->mangling[k] >= NE_MANGLE_NONE && d->mangling[k] <= NE_MANGLE_AVERAGE_NORTH_SOUTH, "series ring: unknown mangling");
   }
   NE_REQUIRE(d->raw_nx >= 0 && d->raw_ny >= 0 && d->di >= 0 && d->dj >= 0, "series ring: negative raw extent or region offset");
+  NE_REQUIRE(d->region_kind == NE_REGION_BOX || d->region_kind == NE_REGION_COLUMN, "series ring: unknown region kind");
+  if (d->region_kind == NE_REGION_COLUMN) {
+    const int64_t rnx = d->raw_nx ? d->raw_nx : d->nx, rny = d->raw_ny ? d->raw_ny : d->ny;
+    NE_REQUIRE(d->nx == 1 && d->ny == 1, "series ring: a Column region fills a 1 x 1 series");
+    NE_REQUIRE(d->column_interpolation == NE_COLUMN_LINEAR || d->column_interpolation == NE_COLUMN_NEAREST,
+               "series ring: unknown Column interpolation");
+    NE_REQUIRE(d->col_i_minus >= 0 && d->col_i_minus < rnx && d->col_i_plus >= 0 && d->col_i_plus < rnx &&
+               d->col_j_minus >= 0 && d->col_j_minus < rny && d->col_j_plus >= 0 && d->col_j_plus < rny,
+               "series ring: Column bracketing indices outside the raw slice");
+    NE_REQUIRE(d->col_wx >= 0 && d->col_wx <= 1 && d->col_wy >= 0 && d->col_wy <= 1, "series ring: Column weights outside [0, 1]");
+  }
   ne::SeriesRing* r = new ne::SeriesRing();
   r->d = *d;
   r->copy = nullptr;
@@ -183,6 +235,9 @@ int ne_series_ring_load(void* handle, int32_t slot, const void* const* host_raw)
   }
   a.raw_nx = d.raw_nx; a.raw_ny = d.raw_ny; a.di = d.di; a.dj = d.dj;
   a.nx = d.nx; a.ny = d.ny; a.hx = d.hx; a.hy = d.hy; a.periodic_x = d.periodic_x;
+  a.region_kind = d.region_kind; a.column_interpolation = d.column_interpolation;
+  a.col_im = d.col_i_minus; a.col_ip = d.col_i_plus; a.col_jm = d.col_j_minus; a.col_jp = d.col_j_plus;
+  a.col_wx = d.col_wx; a.col_wy = d.col_wy;
   const long long elems = (long long)(d.nx + 2 * d.hx) * (d.ny + 2 * d.hy);
   const unsigned bx = (unsigned)std::min<long long>((elems + 255) / 256, 148LL * 8);
   dim3 grid(bx, (unsigned)d.n_series);

@@ -114,6 +114,50 @@ class WindowPolicy:
         return loads
 
 
+def infer_longitudinal_period(lon_centers):
+    """360 if the file's longitudes span the full globe (cyclic), else None (set_region_data.jl:121-126)."""
+    lam = np.asarray(lon_centers, dtype=np.float64)
+    if lam.size < 2:
+        return None
+    delta = lam[1] - lam[0]
+    span = lam[-1] - lam[0] + delta
+    return 360 if np.isclose(span, 360.0) else None
+
+
+def bracket_with_weight(coords, x, period=None):
+    """Cyclic-aware bracketing of `x` by cell centres (set_region_data.jl:130-150): 1-based (i_minus, i_plus, w) as the
+    reference returns them; with `period`, the cell between coords[end] and coords[1] + period is the wrap cell (n, 1, w)."""
+    c = np.asarray(coords, dtype=np.float64)
+    n = c.size
+    if n <= 1:
+        return 1, 1, 0.0
+    x = float(x)
+    if period is not None:
+        x = c[0] + np.mod(x - c[0], period)
+        if x > c[-1]:
+            delta = (c[0] + period) - c[-1]
+            return n, 1, float(np.clip((x - c[-1]) / delta, 0.0, 1.0))
+    ip = int(np.searchsorted(c, x, side="left")) + 1        # searchsortedfirst, 1-based
+    ip = min(max(ip, 2), n)
+    im = ip - 1
+    delta = c[ip - 1] - c[im - 1]
+    w = 0.0 if delta == 0 else (x - c[im - 1]) / delta
+    return im, ip, float(np.clip(w, 0.0, 1.0))
+
+
+class ColumnRegion:
+    """DataWrangling.Column(longitude, latitude; interpolation = Linear() | Nearest()) resolved against a file's cell centres
+    (region_info(::Column), set_region_data.jl:113-118): what the ring's slot fill needs to blend four file cells into the one
+    cell of a column series."""
+
+    def __init__(self, lon_centers, lat_centers, longitude, latitude, interpolation="linear"):
+        if interpolation not in ("linear", "nearest"):
+            raise ValueError("Column interpolation is 'linear' or 'nearest'")
+        self.i_minus, self.i_plus, self.wx = bracket_with_weight(lon_centers, longitude, period=infer_longitudinal_period(lon_centers))
+        self.j_minus, self.j_plus, self.wy = bracket_with_weight(lat_centers, latitude)   # latitude is never cyclic
+        self.interpolation = interpolation
+
+
 class SeriesWindow:
     """Device rings of the series of one prescribed component (all on one source grid and one time axis).
 
@@ -126,7 +170,7 @@ class SeriesWindow:
     """
 
     def __init__(self, backend, lib, grid, times, raw, n_slots=4, time_indexing="cyclical", conversions=None,
-                 missing_values=None, periodic_x=True, lookahead=None, region_offset=(0, 0)):
+                 missing_values=None, periodic_x=True, lookahead=None, region_offset=(0, 0), column=None):
         if not backend.is_device:
             raise RuntimeError("SeriesWindow needs the CUDA library and device arrays (there is no CPU fallback)")
         self.backend, self.lib, self.grid = backend, lib, grid
@@ -150,14 +194,23 @@ class SeriesWindow:
         raw_ny, raw_nx = raw_shape[1:]
         # mangling_for (src/DataWrangling/set_region_data.jl:153-158): a file with one latitude less / more than the grid
         whole = tuple(region_offset) == (0, 0)
-        mangling = A.NE_MANGLE_SHIFT_SOUTH if whole and raw_ny == grid.ny - 1 else \
-            A.NE_MANGLE_AVERAGE_NORTH_SOUTH if whole and raw_ny == grid.ny + 1 else A.NE_MANGLE_NONE
+        mangling = A.NE_MANGLE_SHIFT_SOUTH if whole and column is None and raw_ny == grid.ny - 1 else \
+            A.NE_MANGLE_AVERAGE_NORTH_SOUTH if whole and column is None and raw_ny == grid.ny + 1 else A.NE_MANGLE_NONE
         self.mangling = mangling
         self.series = {k: backend.zeros((self.n_slots,) + tuple(grid.shape), grid.FT) for k in self.names}
         d = self.desc = A.NeSeriesRingDesc()
         d.n_series, d.n_slots, d.dtype, d.periodic_x = len(self.names), self.n_slots, A.NE_F64 if grid.FT == "f64" else A.NE_F32, int(periodic_x)
         d.nx, d.ny, d.hx, d.hy = grid.nx, grid.ny, grid.hx, grid.hy
         d.raw_nx, d.raw_ny, d.di, d.dj = raw_nx, raw_ny, int(region_offset[0]), int(region_offset[1])
+        if column is not None:    # a ColumnRegion: the series is 1 x 1, its value the blend of four file cells
+            if (grid.nx, grid.ny) != (1, 1):
+                raise ValueError("a Column region fills a 1 x 1 series")
+            d.region_kind = A.NE_REGION_COLUMN
+            d.column_interpolation = A.NE_COLUMN_NEAREST if column.interpolation == "nearest" else A.NE_COLUMN_LINEAR
+            d.col_i_minus, d.col_i_plus = column.i_minus - 1, column.i_plus - 1
+            d.col_j_minus, d.col_j_plus = column.j_minus - 1, column.j_plus - 1
+            npf = np.float64 if grid.FT == "f64" else np.float32
+            d.col_wx, d.col_wy = float(npf(column.wx)), float(npf(column.wy))   # ColumnInfo holds FT(wx), FT(wy)
         for i, k in enumerate(self.names):
             d.ring[i] = backend.ptr(self.series[k])
             d.mangling[i] = mangling

@@ -1263,16 +1263,47 @@ static void series_slot_fill(const NeSeriesRingDesc& d, int k, const T* raw, T* 
     j = std::min(std::max<int64_t>(j, 0), rny - 1);
     return raw[j * rnx + i];
   };
+  // mangle + nan_convert_missing of one file cell (:48-53, :162-163)
+  auto read = [&](int64_t fi, int64_t fj) -> T {
+    T v;
+    switch (d.mangling[k]) {
+      case NE_MANGLE_SHIFT_SOUTH: v = file(fi, fj - 1); break;
+      case NE_MANGLE_AVERAGE_NORTH_SOUTH: { volatile T sum = file(fi, fj) + file(fi, fj + 1); v = sum / (T)2; break; }
+      default: v = file(fi, fj); break;
+    }
+    if (d.has_missing[k] && v == mv) v = std::numeric_limits<T>::quiet_NaN();
+    return v;
+  };
+  // blend(::Linear, …) (:168-187): NaN corners dropped, weights renormalised; blend(::Nearest, …) (:189-195)
+  auto blend_linear = [&]() -> T {
+    const T wx = (T)d.col_wx, wy = (T)d.col_wy;
+    const T d00 = read(d.col_i_minus, d.col_j_minus), d10 = read(d.col_i_plus, d.col_j_minus);
+    const T d01 = read(d.col_i_minus, d.col_j_plus), d11 = read(d.col_i_plus, d.col_j_plus);
+    volatile T cx = (T)1 - wx, cy = (T)1 - wy;
+    volatile T p00 = cx * cy, p10 = wx * cy, p01 = cx * wy, p11 = wx * wy;
+    volatile T w00 = p00 * (T)!std::isnan(d00), w10 = p10 * (T)!std::isnan(d10);
+    volatile T w01 = p01 * (T)!std::isnan(d01), w11 = p11 * (T)!std::isnan(d11);
+    volatile T s1 = w00 + w10; volatile T s2 = s1 + w01; volatile T sw = s2 + w11;
+    volatile T t00 = w00 * (std::isnan(d00) ? (T)0 : d00), t10 = w10 * (std::isnan(d10) ? (T)0 : d10);
+    volatile T t01 = w01 * (std::isnan(d01) ? (T)0 : d01), t11 = w11 * (std::isnan(d11) ? (T)0 : d11);
+    volatile T n1 = t00 + t10; volatile T n2 = n1 + t01; volatile T num = n2 + t11;
+    if (sw == (T)0) return std::numeric_limits<T>::quiet_NaN();
+    return num / sw;
+  };
   for (int64_t j = 0; j < d.ny; ++j)
     for (int64_t i = 0; i < d.nx; ++i) {
-      const int64_t fi = i + d.di, fj = j + d.dj;     // read_data(…, ::BoundingBoxOffset, …) (:163)
       T v;
-      switch (d.mangling[k]) {
-        case NE_MANGLE_SHIFT_SOUTH: v = file(fi, fj - 1); break;
-        case NE_MANGLE_AVERAGE_NORTH_SOUTH: { volatile T sum = file(fi, fj) + file(fi, fj + 1); v = sum / (T)2; break; }
-        default: v = file(fi, fj); break;
+      if (d.region_kind == NE_REGION_COLUMN) {       // read_data(…, ::ColumnInfo, …) (:164)
+        if (d.column_interpolation == NE_COLUMN_NEAREST) {
+          const T wx = (T)d.col_wx, wy = (T)d.col_wy;
+          v = read(wx >= (T)0.5 ? d.col_i_plus : d.col_i_minus, wy >= (T)0.5 ? d.col_j_plus : d.col_j_minus);
+          if (std::isnan(v)) v = blend_linear();
+        } else {
+          v = blend_linear();
+        }
+      } else {
+        v = read(i + d.di, j + d.dj);                // read_data(…, ::BoundingBoxOffset, …) (:163)
       }
-      if (d.has_missing[k] && v == mv) v = std::numeric_limits<T>::quiet_NaN();
       switch (d.conv_kind[k]) {
         case NE_CONV_NEGATE: v = -v; break;
         case NE_CONV_ADD: v = v + a; break;

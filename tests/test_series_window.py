@@ -17,7 +17,8 @@ import pytest
 import ne_b200
 from ne_b200 import abi as A
 from numericalearth_jl_b200 import synthetic
-from numericalearth_jl_b200.series_window import CONVERSIONS, SeriesWindow, WindowPolicy
+from numericalearth_jl_b200.series_window import (CONVERSIONS, ColumnRegion, SeriesWindow, WindowPolicy, bracket_with_weight,
+                                                   infer_longitudinal_period)
 
 NPD = {"f64": np.float64, "f32": np.float32}
 
@@ -410,6 +411,113 @@ def test_oracle_slot_fill_against_numpy_for_random_shapes_regions_and_manglings(
 
 
 # ------------------------------------------------------------------------------------------------- device
+
+# ------------------------------------------------------------------------------------------------- Column regions (CPU)
+def test_bracket_with_weight_known_answers_of_the_reference():
+    """test/test_column_field.jl:18-66 (non-cyclic and cyclic wrap)."""
+    coords = [0.5, 1.5, 2.5, 3.5]
+    im, ip, w = bracket_with_weight(coords, 2.0)
+    assert (im, ip) == (2, 3) and w == pytest.approx(0.5)
+    assert bracket_with_weight(coords, -1.0) == (1, 2, 0.0)       # off-grid below: first interval
+    assert bracket_with_weight(coords, 5.0) == (3, 4, 1.0)        # off-grid above: last interval
+    im, ip, w = bracket_with_weight(coords, 3.5)
+    assert (im, ip) == (3, 4) and w == pytest.approx(1.0)
+    assert bracket_with_weight([7.5], 7.5) == (1, 1, 0.0)         # single-cell axis
+    assert bracket_with_weight([7.5], 99.0) == (1, 1, 0.0)
+    coords = np.arange(0.5, 360.0, 1.0)
+    n = len(coords)
+    im, ip, w = bracket_with_weight(coords, 180.0, period=360)
+    assert (im, ip) == (180, 181) and w == pytest.approx(0.5)
+    im, ip, w = bracket_with_weight(coords, 359.99, period=360)    # the wrap cell
+    assert (im, ip) == (n, 1) and 0 < w < 1
+    im, ip, w = bracket_with_weight(coords, 360.5, period=360)     # past the period: wrapped back
+    assert im == 1 and ip == 2
+
+
+def test_infer_longitudinal_period_known_answers_of_the_reference():
+    """test/test_column_field.jl:68-73."""
+    assert infer_longitudinal_period(np.arange(0.5, 360.0, 1.0)) == 360
+    assert infer_longitudinal_period(np.arange(-179.75, 180.0, 0.5)) == 360
+    assert infer_longitudinal_period([10.0, 11.0, 12.0]) is None
+    assert infer_longitudinal_period([100.0]) is None
+
+
+def _column_desc(FT, raw_nx, raw_ny, im, ip, jm, jp, wx, wy, kind="linear", hx=0, hy=0, missing=None, conv=None):
+    d = _ring_desc(FT, 1, 1, hx, hy, conv=conv, missing=missing)
+    d.raw_nx, d.raw_ny = raw_nx, raw_ny
+    d.region_kind = A.NE_REGION_COLUMN
+    d.column_interpolation = A.NE_COLUMN_NEAREST if kind == "nearest" else A.NE_COLUMN_LINEAR
+    d.col_i_minus, d.col_i_plus, d.col_j_minus, d.col_j_plus = im - 1, ip - 1, jm - 1, jp - 1   # the ABI is 0-based
+    d.col_wx, d.col_wy = float(NPD[FT](wx)), float(NPD[FT](wy))
+    return d
+
+
+def test_column_blend_known_answers_of_the_reference(oracle_lib):
+    """test/test_column_field.jl:75-115: data = reshape(Float32[1 2; 3 4], 2, 2, 1), data[i, j]; our raw[j, i]."""
+    full = np.array([[1, 2], [3, 4]], np.float32).T
+    part = np.array([[1, 2], [3, np.nan]], np.float32).T
+    allnan = np.full((2, 2), np.nan, np.float32)
+    lin = _column_desc("f32", 2, 2, 1, 2, 1, 2, 0.5, 0.5)
+    assert _oracle_fill(oracle_lib, lin, full, "f32")[0, 0] == np.float32(2.5)
+    assert np.isnan(_oracle_fill(oracle_lib, lin, allnan, "f32")[0, 0])
+    assert _oracle_fill(oracle_lib, lin, part, "f32")[0, 0] == pytest.approx(2.0, rel=1e-6)     # renormalised over three corners
+    miss = part.copy()
+    miss[np.isnan(miss)] = -9999.0                                                                # `missing` in the file
+    assert _oracle_fill(oracle_lib, _column_desc("f32", 2, 2, 1, 2, 1, 2, 0.5, 0.5, missing=-9999.0), miss, "f32")[0, 0] == \
+        pytest.approx(2.0, rel=1e-6)
+    assert _oracle_fill(oracle_lib, _column_desc("f32", 2, 2, 1, 2, 1, 2, 0.7, 0.7, "nearest"), full, "f32")[0, 0] == 4.0
+    assert _oracle_fill(oracle_lib, _column_desc("f32", 2, 2, 1, 2, 1, 2, 0.3, 0.3, "nearest"), full, "f32")[0, 0] == 1.0
+    # the closest corner is land: Nearest falls back to the NaN-aware linear blend (set_region_data.jl:189-195)
+    want = _oracle_fill(oracle_lib, _column_desc("f32", 2, 2, 1, 2, 1, 2, 0.7, 0.7), part, "f32")[0, 0]
+    assert _oracle_fill(oracle_lib, _column_desc("f32", 2, 2, 1, 2, 1, 2, 0.7, 0.7, "nearest"), part, "f32")[0, 0] == want
+    assert np.isfinite(want)
+
+
+def _numpy_blend(raw, c, FT, kind, missing=None):
+    """blend(::Linear / ::Nearest) written from the reference's docstring, one numpy scalar operation per rounding."""
+    T = NPD[FT]
+    v = np.array(raw, dtype=T)
+    if missing is not None:
+        v[v == T(missing)] = np.nan
+    wx, wy = T(c.wx), T(c.wy)
+    corners = [(c.i_minus, c.j_minus, (T(1) - wx) * (T(1) - wy)), (c.i_plus, c.j_minus, wx * (T(1) - wy)),
+               (c.i_minus, c.j_plus, (T(1) - wx) * wy), (c.i_plus, c.j_plus, wx * wy)]
+    if kind == "nearest":
+        near = v[(c.j_plus if wy >= T(0.5) else c.j_minus) - 1, (c.i_plus if wx >= T(0.5) else c.i_minus) - 1]
+        if not np.isnan(near):
+            return near
+    sw, num = None, None
+    for i, j, w in corners:
+        d = v[j - 1, i - 1]
+        w = T(0) if np.isnan(d) else w
+        t = w * (T(0) if np.isnan(d) else d)
+        sw = w if sw is None else sw + w
+        num = t if num is None else num + t
+    return T(np.nan) if sw == 0 else num / sw
+
+
+@pytest.mark.parametrize("FT", ["f32", "f64"])
+@pytest.mark.parametrize("kind", ["linear", "nearest"])
+def test_oracle_column_fill_against_numpy_for_random_points_and_coasts(oracle_lib, FT, kind):
+    rng = np.random.default_rng(5)
+    nx, ny = 48, 24
+    lon, lat = (np.arange(nx) + 0.5) * 360.0 / nx, -90.0 + (np.arange(ny) + 0.5) * 180.0 / ny
+    seen_nan = seen_wrap = 0
+    for trial in range(200):
+        raw = rng.normal(12.0, 9.0, (ny, nx)).astype(NPD[FT])
+        raw[rng.random((ny, nx)) < 0.35] = NPD[FT](-9999.0)
+        c = ColumnRegion(lon, lat, rng.uniform(-400.0, 400.0), rng.uniform(-95.0, 95.0), interpolation=kind)
+        seen_wrap += (c.i_minus, c.i_plus) == (nx, 1)
+        d = _column_desc(FT, nx, ny, c.i_minus, c.i_plus, c.j_minus, c.j_plus, c.wx, c.wy, kind, hx=2, hy=1, missing=-9999.0,
+                         conv="Celsius")
+        got = _oracle_fill(oracle_lib, d, raw, FT)
+        b = _numpy_blend(raw, c, FT, kind, -9999.0)
+        want = b + NPD[FT](273.15)
+        assert np.array_equal(got, np.full_like(got, want), equal_nan=True), trial     # one value: interior and every halo cell
+        seen_nan += bool(np.isnan(want))
+    assert seen_nan > 0 and seen_wrap > 0
+
+
 def _window_case(backend, lib, FT, atm_FT, nt, n_slots, seed_offset=0):
     """Two identically seeded interfaces: `full` reads the series fully in memory (halos filled the reference's way),
     `win` reads device rings fed from the raw slices."""
@@ -544,6 +652,40 @@ def test_ring_slot_fill_with_mangling_and_regions_matches_the_oracle(cuda_backen
         assert np.array_equal(ring[w.policy.where[n]], want, equal_nan=True), n
         assert np.isnan(want).any() and np.isfinite(want).any()
     w.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("FT", ["f32", "f64"])
+@pytest.mark.parametrize("kind", ["linear", "nearest"])
+def test_ring_slot_fill_of_a_column_region_matches_the_oracle(cuda_backend, cuda_lib, oracle_lib, FT, kind):
+    """Column(lon, lat; interpolation): a 1 x 1 series whose value is the NaN-aware blend of four file cells
+    (set_region_data.jl:113-118, :164-195), through the ring like any other region."""
+    import torch
+    rng = np.random.default_rng(21)
+    nx, ny, nt = 90, 45, 3
+    lon, lat = (np.arange(nx) + 0.5) * 4.0, -90.0 + (np.arange(ny) + 0.5) * 4.0
+    seen_nan = seen_finite = 0
+    for point in [(12.0, -50.0), (359.3, 10.0), (-61.5, 18.0), (181.0, 89.9), (77.7, -33.3), (3.0, 0.2)]:
+        raw = {"T": rng.normal(10, 8, (nt, ny, nx)).astype(NPD[FT]), "S": rng.normal(35, 1, (nt, ny, nx)).astype(NPD[FT])}
+        for v in raw.values():
+            v[rng.random(v.shape) < 0.4] = NPD[FT](-9999.0)
+        col = ColumnRegion(lon, lat, *point, interpolation=kind)
+        src = ne_b200.LatLonSourceGrid(nx=1, ny=1, hx=1, hy=1, FT=FT, lam_nodes=[point[0]], phi_nodes=[point[1]])
+        w = SeriesWindow(cuda_backend, cuda_lib, src, np.arange(nt) * 3600.0, raw, n_slots=2, conversions={"T": "Celsius"},
+                         missing_values={"T": -9999.0, "S": -9999.0}, column=col)
+        w.time_interp(1800.0, cuda_backend.stream())
+        torch.cuda.synchronize()
+        for k, name in enumerate(("T", "S")):
+            ring = cuda_backend.to_numpy(w[name])
+            for n in (1, 2):
+                want = np.full((3, 3), -777.0, NPD[FT])
+                assert oracle_lib.dll.neo_series_slot_fill(C.addressof(w.desc), k, np.ascontiguousarray(raw[name][n - 1]).ctypes.data,
+                                                           want.ctypes.data) == 0
+                assert np.array_equal(ring[w.policy.where[n]], want, equal_nan=True), (point, name, n)
+                seen_nan += bool(np.isnan(want).any())
+                seen_finite += bool(np.isfinite(want).all())
+        w.close()
+    assert seen_finite > 0 and seen_nan > 0
 
 
 @pytest.mark.gpu
