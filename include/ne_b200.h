@@ -169,7 +169,9 @@ typedef struct NeStabilityProfile {
 } NeStabilityProfile;
 
 /* roughness lengths (roughness_lengths.jl) */
-enum { NE_ROUGH_CONSTANT = 0, NE_ROUGH_MOMENTUM = 1, NE_ROUGH_SCALAR = 2 };
+enum { NE_ROUGH_CONSTANT = 0, NE_ROUGH_MOMENTUM = 1, NE_ROUGH_SCALAR = 2,
+       NE_ROUGH_LAND = 3 };   /* LandRoughnessLength :21-39: resolved per cell from the land model's roughness field
+                                 (local_roughness_length, similarity_theory_turbulent_fluxes.jl:265-278), then a constant */
 enum { NE_WAVE_CONSTANT = 0, NE_WAVE_WIND_DEPENDENT = 1 };          /* :56-75  */
 enum { NE_VISC_CONSTANT = 0, NE_VISC_TEMPERATURE_DEPENDENT = 1 };   /* :149-189 */
 typedef struct NeRoughnessLength {
@@ -184,6 +186,8 @@ typedef struct NeRoughnessLength {
   double nu;           /* constant viscosity                                                   */
   double nu_C[4];      /* TemperatureDependentAirViscosity C0..C3                              */
   double reynolds_A, reynolds_b; /* ReynoldsScalingFunction :212-231                           */
+  double land_multiplier, land_minimum_roughness_length; /* NE_ROUGH_LAND: max(multiplier max(field, minimum), minimum);
+                                                            no field (the land model provides none): the minimum stands in */
 } NeRoughnessLength;
 
 /* subgrid velocities (similarity_theory_turbulent_fluxes.jl:45-98) */
@@ -224,6 +228,7 @@ typedef struct NeLargeYeager {      /* :82-108, 288-340 */
 } NeLargeYeager;
 
 enum { NE_FLUX_SIMILARITY_THEORY = 0, NE_FLUX_COEFFICIENT_BASED = 1, NE_FLUX_LARGE_YEAGER = 2 };
+enum { NE_DISPLACEMENT_CONSTANT = 0, NE_DISPLACEMENT_LAND = 1 };
 typedef struct NeFluxFormulation {
   int32_t kind;
   int32_t similarity_form;
@@ -233,6 +238,9 @@ typedef struct NeFluxFormulation {
   NeStabilityProfile psi_momentum, psi_temperature, psi_water_vapor;
   NeRoughnessLength ell_momentum, ell_temperature, ell_water_vapor;
   double zero_plane_displacement;
+  int32_t zero_plane_displacement_kind;  /* NE_DISPLACEMENT_*: a Number | LandZeroPlaneDisplacement() (roughness_lengths.jl:44-51),
+                                            read per cell from the land model's field, 0 without one (:296-303)         */
+  int32_t pad_;
   /* CoefficientBasedFluxes :142-145 (tuple/SimilarityScales of constants or polynomial) */
   NeTransferCoefficient coefficients[3];
   NeLargeYeager large_yeager;
@@ -406,6 +414,10 @@ typedef struct NeAtmosLandDesc {
   void *interface_temperature;
   void *friction_velocity, *temperature_scale, *water_vapor_scale;
   int32_t* iterations;
+  /* atmosphere_land_surface_properties(land_state) (:114-115): per-cell fields a land model may provide (SlabLand provides
+   * none: NULL = `hasproperty` is false).  Read by NE_ROUGH_LAND roughness lengths (momentum slot: the first; temperature
+   * and water-vapor slots: the second) and by NE_DISPLACEMENT_LAND.  Exchange dtype, exchange-grid layout.               */
+  const void *momentum_roughness_length, *scalar_roughness_length, *zero_plane_displacement;
 } NeAtmosLandDesc;
 
 /* ---- sea-ice–ocean fluxes (sea_ice_ocean_fluxes.jl:20-226, freezing_limited_ocean_temperature.jl:73-118) */

@@ -58,7 +58,8 @@ using NumericalEarth.EarthSystemModels.InterfaceComputations
 using NumericalEarth.EarthSystemModels.InterfaceComputations:
     ComponentExchanger, ComponentInterfaces, AtmosphereInterface, SeaIceOceanInterface, computed_fluxes, ZeroFluxes,
     SimilarityTheoryFluxes, CoefficientBasedFluxes, ConvergenceStopCriteria, FixedIterations, SimilarityScales,
-    MomentumRoughnessLength, ScalarRoughnessLength, ReynoldsScalingFunction, WindDependentWaveFormulation,
+    MomentumRoughnessLength, ScalarRoughnessLength, LandRoughnessLength, LandZeroPlaneDisplacement, ReynoldsScalingFunction,
+    WindDependentWaveFormulation,
     TemperatureDependentAirViscosity, ConvectiveGustiness, SubgridVelocityCorrection,
     EdsonMomentumStabilityFunction, EdsonScalarStabilityFunction, ShebaMomentumStabilityFunction, ShebaScalarStabilityFunction,
     PaulsonMomentumStabilityFunction, PaulsonScalarStabilityFunction, LinearStableStabilityFunction, SplitStabilityFunction,
@@ -215,22 +216,31 @@ wave_fields(ℂg::Number) = (wave_kind = NE_WAVE_CONSTANT, wave_constant = Float
 wave_fields(w::WindDependentWaveFormulation) = (wave_kind = NE_WAVE_WIND_DEPENDENT, wave_constant = 0.0, wave_Umax = Float64(w.Umax), wave_C1 = Float64(w.ℂ₁), wave_C2 = Float64(w.ℂ₂))
 wave_fields(w) = no_variant("wave_formulation", w)
 
-roughness_length(ℓ::Number) = NeRoughnessLength(kind = NE_ROUGH_CONSTANT, constant = Float64(ℓ), visc_dtype = NE_F64)
-function roughness_length(ℓ::MomentumRoughnessLength)
+roughness_length(ℓ::Number; land = false) = NeRoughnessLength(kind = NE_ROUGH_CONSTANT, constant = Float64(ℓ), visc_dtype = NE_F64)
+function roughness_length(ℓ::MomentumRoughnessLength; land = false)
     v, w = viscosity_fields(ℓ.air_kinematic_viscosity), wave_fields(ℓ.wave_formulation)
     return NeRoughnessLength(kind = NE_ROUGH_MOMENTUM, wave_kind = w.wave_kind, visc_kind = v.visc_kind, visc_dtype = v.visc_dtype,
                              gravitational_acceleration = Float64(ℓ.gravitational_acceleration), wave_constant = w.wave_constant,
                              smooth_wall_parameter = Float64(ℓ.smooth_wall_parameter), wave_Umax = w.wave_Umax, wave_C1 = w.wave_C1,
                              wave_C2 = w.wave_C2, maximum_roughness_length = Float64(ℓ.maximum_roughness_length), nu = v.nu, nu_C = v.nu_C)
 end
-function roughness_length(ℓ::ScalarRoughnessLength)
+function roughness_length(ℓ::ScalarRoughnessLength; land = false)
     v = viscosity_fields(ℓ.air_kinematic_viscosity)
     s = ℓ.reynolds_number_scaling_function
     s isa ReynoldsScalingFunction || no_variant("reynolds_number_scaling_function", s)
     return NeRoughnessLength(kind = NE_ROUGH_SCALAR, visc_kind = v.visc_kind, visc_dtype = v.visc_dtype, nu = v.nu, nu_C = v.nu_C,
                              maximum_roughness_length = Float64(ℓ.maximum_roughness_length), reynolds_A = Float64(s.A), reynolds_b = Float64(s.b))
 end
-roughness_length(ℓ) = no_variant("roughness length", ℓ)     # closures ℓ(u★, …) (roughness_lengths.jl:192) and land field models
+# LandRoughnessLength (roughness_lengths.jl:21-39): a marker the atmosphere–land kernel resolves per cell from the land model's
+# roughness field (NeAtmosLandDesc.momentum_roughness_length / scalar_roughness_length).  Over the ocean and sea ice the interior
+# properties carry no such field and local_roughness_length returns max(multiplier * minimum, minimum)
+# (similarity_theory_turbulent_fluxes.jl:265-278): `land = false` passes that constant.
+function roughness_length(ℓ::LandRoughnessLength{T}; land = false) where T
+    land && return NeRoughnessLength(kind = NE_ROUGH_LAND, visc_dtype = NE_F64, land_multiplier = Float64(ℓ.multiplier),
+                                     land_minimum_roughness_length = Float64(ℓ.minimum_roughness_length))
+    return roughness_length(max(ℓ.multiplier * ℓ.minimum_roughness_length, ℓ.minimum_roughness_length))
+end
+roughness_length(ℓ; land = false) = no_variant("roughness length", ℓ)     # closures ℓ(u★, …) (roughness_lengths.jl:192)
 
 # subgrid velocities (similarity_theory_turbulent_fluxes.jl:45-98)
 sgs_slot(::Nothing) = (NE_SGS_NONE, 0.0)
@@ -265,20 +275,26 @@ similarity_form(::LogarithmicSimilarityProfile) = NE_PROFILE_LOGARITHMIC
 similarity_form(::COARELogarithmicSimilarityProfile) = NE_PROFILE_COARE
 similarity_form(f) = no_variant("similarity_form", f)
 
-function flux_formulation(f::SimilarityTheoryFluxes)
+# `land = true` (the atmosphere–land descriptor) keeps the per-cell land markers; elsewhere they collapse to constants
+function flux_formulation(f::SimilarityTheoryFluxes; land = false)
     ψ, ℓ = f.stability_functions, f.roughness_lengths
     d = f.zero_plane_displacement
+    d_kind = NE_DISPLACEMENT_CONSTANT
+    if d isa LandZeroPlaneDisplacement        # local_zero_plane_displacement (:296-303): 0 without a land field
+        d, d_kind = 0, land ? NE_DISPLACEMENT_LAND : NE_DISPLACEMENT_CONSTANT
+    end
     d isa Number || no_variant("zero_plane_displacement", d)
     return NeFluxFormulation(kind = NE_FLUX_SIMILARITY_THEORY, similarity_form = similarity_form(f.similarity_form),
                              von_karman_constant = Float64(f.von_karman_constant), subgrid_velocities = subgrid_velocity(f.subgrid_velocities),
                              psi_momentum = stability_profile(ψ.momentum), psi_temperature = stability_profile(ψ.temperature),
                              psi_water_vapor = stability_profile(ψ.water_vapor),
-                             ell_momentum = roughness_length(ℓ.momentum), ell_temperature = roughness_length(ℓ.temperature),
-                             ell_water_vapor = roughness_length(ℓ.water_vapor), zero_plane_displacement = Float64(d),
+                             ell_momentum = roughness_length(ℓ.momentum; land), ell_temperature = roughness_length(ℓ.temperature; land),
+                             ell_water_vapor = roughness_length(ℓ.water_vapor; land), zero_plane_displacement = Float64(d),
+                             zero_plane_displacement_kind = d_kind,
                              stop = stop_criteria(f.solver_stop_criteria))
 end
 
-function flux_formulation(f::CoefficientBasedFluxes)
+function flux_formulation(f::CoefficientBasedFluxes; land = false)
     c = f.transfer_coefficients
     if c isa LargeYeagerTransferCoefficients       # coefficient_based_turbulent_fluxes.jl:82-108, 288-340
         ψ = c.stability_functions
@@ -292,7 +308,7 @@ function flux_formulation(f::CoefficientBasedFluxes)
     coefficients = (transfer_coefficient(c.momentum), transfer_coefficient(c.temperature), transfer_coefficient(c.water_vapor))
     return NeFluxFormulation(kind = NE_FLUX_COEFFICIENT_BASED, coefficients = coefficients, stop = stop_criteria(f.solver_stop_criteria))
 end
-flux_formulation(f) = no_variant("flux formulation", f)
+flux_formulation(f; land = false) = no_variant("flux formulation", f)
 
 # InterfaceProperties (interface_states.jl:8-12, 20-74, 236-277, 284-301, 330-398)
 phase_of(::AtmosphericThermodynamics.Liquid) = NE_PHASE_LIQUID

@@ -18,7 +18,8 @@ NE_DIAG_MAX_FIELDS = 16
 # stability functions
 (NE_PSI_ZERO, NE_PSI_EDSON_MOMENTUM, NE_PSI_EDSON_SCALAR, NE_PSI_SHEBA_MOMENTUM, NE_PSI_SHEBA_SCALAR,
  NE_PSI_PAULSON_MOMENTUM, NE_PSI_PAULSON_SCALAR, NE_PSI_LINEAR_STABLE) = range(8)
-NE_ROUGH_CONSTANT, NE_ROUGH_MOMENTUM, NE_ROUGH_SCALAR = range(3)
+NE_ROUGH_CONSTANT, NE_ROUGH_MOMENTUM, NE_ROUGH_SCALAR, NE_ROUGH_LAND = range(4)
+NE_DISPLACEMENT_CONSTANT, NE_DISPLACEMENT_LAND = range(2)
 NE_WAVE_CONSTANT, NE_WAVE_WIND_DEPENDENT = range(2)
 NE_VISC_CONSTANT, NE_VISC_TEMPERATURE_DEPENDENT = range(2)
 NE_SGS_NONE, NE_SGS_CONSTANT, NE_SGS_CONVECTIVE = range(3)
@@ -91,7 +92,8 @@ class NeRoughnessLength(C.Structure):
     _fields_ = [("kind", i32), ("wave_kind", i32), ("visc_kind", i32), ("visc_dtype", i32), ("constant", f64),
                 ("gravitational_acceleration", f64), ("wave_constant", f64), ("smooth_wall_parameter", f64),
                 ("wave_Umax", f64), ("wave_C1", f64), ("wave_C2", f64), ("maximum_roughness_length", f64),
-                ("nu", f64), ("nu_C", f64 * 4), ("reynolds_A", f64), ("reynolds_b", f64)]
+                ("nu", f64), ("nu_C", f64 * 4), ("reynolds_A", f64), ("reynolds_b", f64),
+                ("land_multiplier", f64), ("land_minimum_roughness_length", f64)]
 
 
 class NeSubgridVelocity(C.Structure):
@@ -126,7 +128,8 @@ class NeFluxFormulation(C.Structure):
                 ("psi_water_vapor", NeStabilityProfile),
                 ("ell_momentum", NeRoughnessLength), ("ell_temperature", NeRoughnessLength),
                 ("ell_water_vapor", NeRoughnessLength),
-                ("zero_plane_displacement", f64), ("coefficients", NeTransferCoefficient * 3),
+                ("zero_plane_displacement", f64), ("zero_plane_displacement_kind", i32), ("pad_", i32),
+                ("coefficients", NeTransferCoefficient * 3),
                 ("large_yeager", NeLargeYeager), ("stop", NeStopCriteria)]
 
 
@@ -211,7 +214,8 @@ class NeAtmosLandDesc(C.Structure):
                 ("properties", NeInterfaceProperties), ("humidity", NeLandHumidity),
                 ("latent_heat", vp), ("sensible_heat", vp), ("water_vapor", vp), ("x_momentum", vp), ("y_momentum", vp),
                 ("interface_temperature", vp),
-                ("friction_velocity", vp), ("temperature_scale", vp), ("water_vapor_scale", vp), ("iterations", vp)]
+                ("friction_velocity", vp), ("temperature_scale", vp), ("water_vapor_scale", vp), ("iterations", vp),
+                ("momentum_roughness_length", vp), ("scalar_roughness_length", vp), ("zero_plane_displacement", vp)]
 
 
 class NeSeaIceOceanDesc(C.Structure):

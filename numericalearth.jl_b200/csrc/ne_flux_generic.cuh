@@ -43,6 +43,11 @@ struct InterfaceSolver {
   // Trailing members: aggregate initialisation of the ocean / sea-ice kernels leaves them null / zero.
   const NeLandHumidity* landq;
   FT land_saturation, land_T;
+  // NE_ROUGH_LAND / NE_DISPLACEMENT_LAND resolved for this cell (local_roughness_lengths, local_zero_plane_displacement,
+  // similarity_theory_turbulent_fluxes.jl:265-303): momentum, temperature, water vapor; displacement.  `land_cell` says the
+  // kernel filled them (ocean / sea-ice kernels never carry the land markers: the entry points resolve them on the host).
+  FT ell_land[3], d_land;
+  int land_cell;
 
   using WT = decltype(FT() + CT());
 
@@ -171,14 +176,18 @@ struct InterfaceSolver {
     using LW = decltype(FT() * VT() * U);
     LW lu, lq, lt;
     if (ff.ell_momentum.kind == NE_ROUGH_CONSTANT) lu = (FT)ff.ell_momentum.constant;
+    else if (ff.ell_momentum.kind == NE_ROUGH_LAND) lu = ell_land[0];
     else lu = momentum_roughness<FT, VT>(ff.ell_momentum, air_viscosity<FT, VT>(ff.ell_momentum, Ts), ustar, U);
     if (ff.ell_water_vapor.kind == NE_ROUGH_CONSTANT) lq = (FT)ff.ell_water_vapor.constant;
+    else if (ff.ell_water_vapor.kind == NE_ROUGH_LAND) lq = ell_land[2];
     else lq = scalar_roughness<FT, VT>(ff.ell_water_vapor, air_viscosity<FT, VT>(ff.ell_water_vapor, Ts), lu, ustar);
     if (flags.scalar_shared) lt = lq;
     else if (ff.ell_temperature.kind == NE_ROUGH_CONSTANT) lt = (FT)ff.ell_temperature.constant;
+    else if (ff.ell_temperature.kind == NE_ROUGH_LAND) lt = ell_land[1];
     else lt = scalar_roughness<FT, VT>(ff.ell_temperature, air_viscosity<FT, VT>(ff.ell_temperature, Ts), lu, ustar);
 
-    auto dh = mx(a.z - (FT)ff.zero_plane_displacement, 2 * lu);  // displaced_profile_height :313
+    const FT d_zero = (land_cell && ff.zero_plane_displacement_kind == NE_DISPLACEMENT_LAND) ? d_land : (FT)ff.zero_plane_displacement;
+    auto dh = mx(a.z - d_zero, 2 * lu);  // displaced_profile_height :313
     FT kappa = (FT)ff.von_karman_constant;
     using BW = decltype(sq(ustar) / (kappa * bstar));
     BW Lstar = (bstar == 0) ? Inf<BW>::v() : sq(ustar) / (kappa * bstar);
@@ -422,6 +431,18 @@ al_flux_kernel(const __grid_constant__ NeAtmosLandDesc d, const __grid_constant_
   s.landq = &d.humidity;
   s.land_saturation = slot_at<FT>(d.saturation, idx);
   s.land_T = Tland;
+  {   // local_atmosphere_land_surface_properties: what the land model provides for this cell
+    const NeRoughnessLength* r[3] = {&d.flux.ell_momentum, &d.flux.ell_temperature, &d.flux.ell_water_vapor};
+    const FT* field[3] = {(const FT*)d.momentum_roughness_length, (const FT*)d.scalar_roughness_length, (const FT*)d.scalar_roughness_length};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const FT lmin = (FT)r[k]->land_minimum_roughness_length;
+      const FT candidate = field[k] ? mx(__ldg(field[k] + idx), lmin) : lmin;
+      s.ell_land[k] = mx((FT)r[k]->land_multiplier * candidate, lmin);
+    }
+    s.d_land = d.zero_plane_displacement ? __ldg((const FT*)d.zero_plane_displacement + idx) : (FT)0;
+    s.land_cell = 1;
+  }
   s.ustar = s.theta_star = s.q_star = (FT)1e-4;              // convert(FT, 1e-4) :204
   s.Ts = Tland;
   s.qs = (FT)s.saturation_specific_humidity(Tland, s.a.p, d.humidity.phase);   // :205

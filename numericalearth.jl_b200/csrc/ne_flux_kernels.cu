@@ -400,14 +400,21 @@ static const SolverTables* solver_tables(const NeFluxFormulation& f, bool f32 = 
 static bool stability_kind_ok(const NeStabilityFn& f) { return f.kind >= NE_PSI_ZERO && f.kind <= NE_PSI_LINEAR_STABLE; }
 static bool profile_ok(const NeStabilityProfile& p) { return stability_kind_ok(p.a) && (!p.split || stability_kind_ok(p.b)); }
 static bool rough_ok(const NeRoughnessLength& r) {
-  if (r.kind < NE_ROUGH_CONSTANT || r.kind > NE_ROUGH_SCALAR) return false;
+  if (r.kind < NE_ROUGH_CONSTANT || r.kind > NE_ROUGH_LAND) return false;
   if (r.wave_kind != NE_WAVE_CONSTANT && r.wave_kind != NE_WAVE_WIND_DEPENDENT) return false;
   if (r.visc_kind != NE_VISC_CONSTANT && r.visc_kind != NE_VISC_TEMPERATURE_DEPENDENT) return false;
   return true;
 }
 
-static int validate_formulation(const NeFluxFormulation& f, const NeInterfaceProperties& ip, bool ice) {
+static int validate_formulation(const NeFluxFormulation& f, const NeInterfaceProperties& ip, bool ice, bool land = false) {
   if (f.kind == NE_FLUX_SIMILARITY_THEORY) {
+    // LandRoughnessLength / LandZeroPlaneDisplacement read the land model's per-cell properties; over the ocean and sea ice
+    // `interior_properties` has no such fields and the markers collapse to constants, which the binding passes as such
+    if (!land && (f.ell_momentum.kind == NE_ROUGH_LAND || f.ell_temperature.kind == NE_ROUGH_LAND ||
+                  f.ell_water_vapor.kind == NE_ROUGH_LAND || f.zero_plane_displacement_kind != NE_DISPLACEMENT_CONSTANT))
+      NE_NO_VARIANT("per-cell land roughness / displacement markers belong to the atmosphere-land interface (pass the resolved constants here)");
+    if (f.zero_plane_displacement_kind != NE_DISPLACEMENT_CONSTANT && f.zero_plane_displacement_kind != NE_DISPLACEMENT_LAND)
+      NE_NO_VARIANT("zero-plane displacement with no kernel variant");
     if (!profile_ok(f.psi_momentum) || !profile_ok(f.psi_temperature) || !profile_ok(f.psi_water_vapor))
       NE_NO_VARIANT("stability function with no kernel variant (user closures are not supported; there is no CPU fallback)");
     if (!rough_ok(f.ell_momentum) || !rough_ok(f.ell_temperature) || !rough_ok(f.ell_water_vapor))
@@ -679,10 +686,13 @@ static int al_entry(const NeAtmosLandDesc* d, void* stream) {
   NE_REQUIRE(d->latent_heat && d->sensible_heat && d->water_vapor && d->x_momentum && d->y_momentum &&
              d->interface_temperature && d->friction_velocity && d->temperature_scale && d->water_vapor_scale,
              "atmosphere-land: null output array");
-  int rc = validate_formulation(d->flux, d->properties, false);
+  int rc = validate_formulation(d->flux, d->properties, false, true);
   if (rc != NE_OK) return rc;
+  // SkinTemperature's flux balance reads reference_density / heat_capacity of the interior properties (interface_states.jl:
+  // 434-457), which atmosphere_land_surface_properties does not provide (atmosphere_land_fluxes.jl:114-115): the reference has
+  // no working method for it either
   if (d->properties.temperature_formulation != NE_TEMP_BULK)
-    NE_NO_VARIANT("atmosphere-land: only BulkTemperature has a kernel variant (the reference's default for land)");
+    NE_NO_VARIANT("atmosphere-land: only BulkTemperature has a kernel variant (the reference's land properties carry no heat capacity / density for a skin-temperature balance)");
   const NeLandHumidity& h = d->humidity;
   if (h.kind < NE_LANDQ_BULK || h.kind > NE_LANDQ_DRY_LAYER)
     NE_NO_VARIANT("land humidity formulation %d has no kernel variant", h.kind);

@@ -167,6 +167,7 @@ inline bool land_fast_path_eligible(const NeFluxFormulation& f, const NeInterfac
   if (std::memcmp(&f.psi_temperature, &f.psi_water_vapor, sizeof(NeStabilityProfile)) != 0) return false;
   if (f.ell_momentum.kind != NE_ROUGH_CONSTANT || f.ell_temperature.kind != NE_ROUGH_CONSTANT ||
       f.ell_water_vapor.kind != NE_ROUGH_CONSTANT) return false;
+  if (f.zero_plane_displacement_kind != NE_DISPLACEMENT_CONSTANT) return false;   // per-cell displacement: generic kernel
   if (f.ell_temperature.constant != f.ell_water_vapor.constant) return false;
   if (!(f.ell_momentum.constant > 0) || !(f.ell_temperature.constant > 0)) return false;
   const NeSubgridVelocity& g = f.subgrid_velocities;

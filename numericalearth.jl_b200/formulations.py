@@ -289,8 +289,30 @@ class ScalarRoughnessLength:  # :93-101
         return r
 
 
+@dataclass
+class LandRoughnessLength:  # roughness_lengths.jl:21-39
+    """The land model's per-cell aerodynamic roughness field as a MOST roughness length (`multiplier` scales it: 0.1 for scalar
+    lengths taken as a tenth of the momentum one).  `minimum_roughness_length = None` is the reference's eps(FT)."""
+    multiplier: float = 1
+    minimum_roughness_length: Any = None
+    FT: str = "f64"
+
+    def pod(self):
+        import numpy as np
+        npf = np.float64 if self.FT == "f64" else np.float32
+        r = A.NeRoughnessLength(kind=A.NE_ROUGH_LAND)
+        lmin = np.finfo(npf).eps if self.minimum_roughness_length is None else self.minimum_roughness_length
+        r.land_multiplier = float(npf(self.multiplier))                 # convert(FT, …) in the constructor (:34-39)
+        r.land_minimum_roughness_length = float(npf(lmin))
+        return r
+
+
+class LandZeroPlaneDisplacement:  # roughness_lengths.jl:44-51
+    """Marker: the zero-plane displacement is the land model's per-cell field (0 where the land model provides none)."""
+
+
 def roughness_pod(ell) -> A.NeRoughnessLength:
-    if isinstance(ell, (MomentumRoughnessLength, ScalarRoughnessLength)):
+    if isinstance(ell, (MomentumRoughnessLength, ScalarRoughnessLength, LandRoughnessLength)):
         return ell.pod()
     if isinstance(ell, (int, float)):  # roughness_length(ℓ::Number, args...) = ℓ (:193)
         r = A.NeRoughnessLength(kind=A.NE_ROUGH_CONSTANT)
@@ -419,9 +441,12 @@ class SimilarityTheoryFluxes:  # :174-214
         if f.ell_momentum.kind == A.NE_ROUGH_SCALAR or f.ell_temperature.kind == A.NE_ROUGH_MOMENTUM \
                 or f.ell_water_vapor.kind == A.NE_ROUGH_MOMENTUM:
             raise NoKernelVariantError("roughness length type not valid in this slot")
-        if not isinstance(self.zero_plane_displacement, (int, float)):
-            raise NoKernelVariantError("LandZeroPlaneDisplacement belongs to the atmosphere-land row (next)")
-        f.zero_plane_displacement = float(self.zero_plane_displacement)
+        if isinstance(self.zero_plane_displacement, LandZeroPlaneDisplacement):
+            f.zero_plane_displacement_kind = A.NE_DISPLACEMENT_LAND
+        elif isinstance(self.zero_plane_displacement, (int, float)):
+            f.zero_plane_displacement = float(self.zero_plane_displacement)
+        else:
+            raise NoKernelVariantError(f"zero_plane_displacement {self.zero_plane_displacement!r} has no kernel variant")
         if isinstance(self.similarity_form, COARELogarithmicSimilarityProfile):
             f.similarity_form = A.NE_PROFILE_COARE
         elif isinstance(self.similarity_form, LogarithmicSimilarityProfile):
@@ -529,10 +554,26 @@ class CoefficientBasedFluxes:  # :218-232
         return f
 
 
-def flux_formulation_pod(ff) -> A.NeFluxFormulation:
-    if isinstance(ff, (SimilarityTheoryFluxes, CoefficientBasedFluxes)):
-        return ff.pod()
-    raise NoKernelVariantError(f"flux formulation {ff!r} has no kernel variant")
+def flux_formulation_pod(ff, land=False, FT="f64") -> A.NeFluxFormulation:
+    """`land = False` (ocean / sea-ice interfaces): the land markers collapse to what local_roughness_length /
+    local_zero_plane_displacement return for interior properties without land fields
+    (similarity_theory_turbulent_fluxes.jl:265-303): max(multiplier * minimum, minimum) in FT, and 0."""
+    if not isinstance(ff, (SimilarityTheoryFluxes, CoefficientBasedFluxes)):
+        raise NoKernelVariantError(f"flux formulation {ff!r} has no kernel variant")
+    f = ff.pod()
+    if not land and f.kind == A.NE_FLUX_SIMILARITY_THEORY:
+        import numpy as np
+        npf = np.float64 if FT == "f64" else np.float32
+        for name in ("ell_momentum", "ell_temperature", "ell_water_vapor"):
+            r = getattr(f, name)
+            if r.kind == A.NE_ROUGH_LAND:
+                lmin = npf(r.land_minimum_roughness_length)
+                c = A.NeRoughnessLength(kind=A.NE_ROUGH_CONSTANT)
+                c.constant = float(max(npf(r.land_multiplier) * lmin, lmin))
+                setattr(f, name, c)
+        if f.zero_plane_displacement_kind == A.NE_DISPLACEMENT_LAND:
+            f.zero_plane_displacement_kind, f.zero_plane_displacement = A.NE_DISPLACEMENT_CONSTANT, 0.0
+    return f
 
 
 # ---------------------------------------------------------------------------------------------

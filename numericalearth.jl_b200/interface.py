@@ -192,6 +192,11 @@ class SlabLandState:
     temperature (Kelvin) and surface saturation, exchange-layout arrays or numbers."""
     T: Any = 288.0
     saturation: Any = 1.0
+    # atmosphere_land_surface_properties(land_state) (atmosphere_land_fluxes.jl:107-115): per-cell fields a land model may
+    # provide for LandRoughnessLength / LandZeroPlaneDisplacement (exchange-layout arrays; None = not provided, as SlabLand)
+    momentum_roughness_length: Any = None
+    scalar_roughness_length: Any = None
+    zero_plane_displacement: Any = None
 
 
 class _Fields:
@@ -579,7 +584,7 @@ class ComponentInterfaces:
         d.radiation = self._surface_radiation("ocean")
         d.thermo = (atm.thermodynamics_parameters if atm else F.AtmosphereThermodynamicsParameters(FT=g.FT)).pod()
         d.gravitational_acceleration = self.g
-        d.flux = F.flux_formulation_pod(self.ao_flux_formulation)
+        d.flux = F.flux_formulation_pod(self.ao_flux_formulation, FT=g.FT)
         d.properties = self.ao_properties.pod()
         d.ocean = self.ocean_properties.pod()
         f = self.ao_fluxes
@@ -610,7 +615,7 @@ class ComponentInterfaces:
         d.radiation = self._surface_radiation("sea_ice")
         d.thermo = (atm.thermodynamics_parameters if atm else F.AtmosphereThermodynamicsParameters(FT=g.FT)).pod()
         d.gravitational_acceleration = self.g
-        d.flux = F.flux_formulation_pod(self.asi_flux_formulation)
+        d.flux = F.flux_formulation_pod(self.asi_flux_formulation, FT=g.FT)
         d.properties = self.asi_properties.pod()
         d.ocean = self.ocean_properties.pod()
         d.sea_ice = self.sea_ice_properties.pod()
@@ -637,7 +642,10 @@ class ComponentInterfaces:
         d.land_temperature, d.saturation = _slot(b, self.slab_land.T), _slot(b, self.slab_land.saturation)
         d.thermo = (atm.thermodynamics_parameters if atm else F.AtmosphereThermodynamicsParameters(FT=g.FT)).pod()
         d.gravitational_acceleration = self.g
-        d.flux = F.flux_formulation_pod(self.al_flux_formulation)
+        d.flux = F.flux_formulation_pod(self.al_flux_formulation, land=True)
+        sl = self.slab_land
+        d.momentum_roughness_length, d.scalar_roughness_length, d.zero_plane_displacement = \
+            _ptr(b, sl.momentum_roughness_length), _ptr(b, sl.scalar_roughness_length), _ptr(b, sl.zero_plane_displacement)
         d.properties = F.InterfaceProperties(F.ImpureSaturationSpecificHumidity(F.Liquid(), None), F.BulkTemperature(),
                                              self.al_velocity).pod()
         d.humidity = F.land_humidity_pod(self.al_humidity)

@@ -820,6 +820,17 @@ void atmosphere_sea_ice(const NeAtmosSeaIceDesc& d) {
 
 // ---- interpolation: Atmospheres/interpolate_atmospheric_state.jl:91-182 + [3rd-party Oceananigans
 // interpolator/_interpolate/time interpolation] ----------------------------------------------------
+// local_roughness_length(::LandRoughnessLength, interior_properties, Val(R)) (similarity_theory_turbulent_fluxes.jl:265-278):
+// the land model's per-cell field, floored, scaled and floored again; the floor alone when the land model has no such field
+template <class FT>
+static void resolve_land_marker(NeRoughnessLength& r, const FT* field, int64_t idx) {
+  if (r.kind != NE_ROUGH_LAND) return;
+  const FT lmin = (FT)r.land_minimum_roughness_length, mult = (FT)r.land_multiplier;
+  const FT candidate = field ? mx(field[idx], lmin) : lmin;
+  r.kind = NE_ROUGH_CONSTANT;
+  r.constant = (double)mx(mult * candidate, lmin);
+}
+
 // ---- _compute_atmosphere_land_interface_state!: atmosphere_land_fluxes.jl:147-251 ------------------------
 template <class FT, class CT, class VT>
 void atmosphere_land(const NeAtmosLandDesc& d) {
@@ -846,7 +857,17 @@ void atmosphere_land(const NeAtmosLandDesc& d) {
       const FT qs0 = (FT)saturation_specific_humidity<CT>(th, Ts, a.p, d.humidity.phase);   // :205
       State<FT> init = {us0, us0, us0, (FT)0, (FT)0, Ts, qs0, land.saturation};
       int iters = 0;
-      State<FT> st = compute_interface_state<FT, CT, VT>(d.flux, d.properties, th, g, init, a, in, rad, medium, false, iters, &land);
+      // local_roughness_lengths / local_zero_plane_displacement (similarity_theory_turbulent_fluxes.jl:265-303): the land
+      // markers resolve to Numbers from this cell's land properties before the iteration sees them
+      NeFluxFormulation flux = d.flux;
+      resolve_land_marker<FT>(flux.ell_momentum, (const FT*)d.momentum_roughness_length, idx);
+      resolve_land_marker<FT>(flux.ell_temperature, (const FT*)d.scalar_roughness_length, idx);
+      resolve_land_marker<FT>(flux.ell_water_vapor, (const FT*)d.scalar_roughness_length, idx);
+      if (flux.zero_plane_displacement_kind == NE_DISPLACEMENT_LAND) {
+        flux.zero_plane_displacement = d.zero_plane_displacement ? (double)((const FT*)d.zero_plane_displacement)[idx] : 0.0;
+        flux.zero_plane_displacement_kind = NE_DISPLACEMENT_CONSTANT;
+      }
+      State<FT> st = compute_interface_state<FT, CT, VT>(flux, d.properties, th, g, init, a, in, rad, medium, false, iters, &land);
       FT ustar = st.ustar, theta_star = st.theta_star, q_star = st.q_star;
       FT du, dv;
       if (d.properties.velocity_formulation == NE_VEL_RELATIVE) { du = a.u - st.u; dv = a.v - st.v; } else { du = a.u; dv = a.v; }

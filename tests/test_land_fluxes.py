@@ -264,3 +264,166 @@ def test_cuda_land_example_configuration(oracle_lib, cuda_backend, cuda_lib):
         b = cuda_backend.to_numpy(getattr(dev.al_fluxes, n))[inner]
         s = float(np.abs(a).max()) or 1.0
         assert np.isfinite(b).all() and np.abs(a - b).max() / s <= 2e-6, f"{n}: {np.abs(a - b).max() / s}"   # Float32 q_sat
+
+
+# ------------------------------------------------------------------------------ per-cell land roughness and displacement
+def _neutral_fluxes(ell=0.1, displacement=0, scalar=None):
+    """The closure of the reference's displacement tests (test/test_slab_land.jl:483-490, 523-529): no stability correction,
+    no gustiness."""
+    s = ell if scalar is None else scalar
+    return F.SimilarityTheoryFluxes(momentum_roughness_length=ell, temperature_roughness_length=s, water_vapor_roughness_length=s,
+                                    zero_plane_displacement=displacement, subgrid_velocities=None, stability_functions=None)
+
+
+def _column(backend, lib, FT, fluxes, wind=5.0, land_T=288.0, fields=None, humidity=None):
+    """Every cell of the grid is the reference's single column: uniform atmosphere (288 K, q = 0.003, 101325 Pa, u = wind),
+    land at land_T, DryLand (saturation 0)."""
+    ci = synthetic.build_case(CFG, backend, FT=FT, atm_FT=FT, lib=lib, with_iterations=True, atmosphere_land_fluxes=fluxes,
+                              atmosphere_land_interface_specific_humidity=humidity or F.BulkHumidity())
+    g = ci.grid
+    npd = np.float64 if FT == "f64" else np.float32
+    full = lambda v: backend.from_numpy(np.full(g.shape, v, npd))   # noqa: E731
+    ci.slab_land = ne_b200.SlabLandState(T=full(land_T), saturation=0.0, **{k: backend.from_numpy(np.asarray(v, npd)) for k, v in (fields or {}).items()})
+    from numericalearth_jl_b200.interface import _Fields
+    Z = lambda: backend.zeros(g.shape, FT)  # noqa: E731
+    ci.al_fluxes = _Fields(latent_heat=Z(), sensible_heat=Z(), water_vapor=Z(), x_momentum=Z(), y_momentum=Z(),
+                           friction_velocity=Z(), temperature_scale=Z(), water_vapor_scale=Z())
+    ci.al_temperature = Z()
+    ci.al_iterations = backend.zeros(g.shape, "i32")
+    ci.initialize()
+    ci.interpolate_state(T_STEP)
+    a = ci.atmos_state
+    a.u, a.v, a.T, a.q, a.p = full(wind), full(0.0), full(288.0), full(0.003), full(101325.0)
+    ci.compute_atmosphere_land_fluxes()
+    return ci
+
+
+def _ustar(ci, backend=None):
+    g = ci.grid
+    v = ci.al_fluxes.friction_velocity
+    v = backend.to_numpy(v) if backend is not None else np.asarray(v)
+    return v[g.hy:g.hy + g.ny, g.hx:g.hx + g.nx]
+
+
+def test_zero_plane_displacement_known_answers_of_the_reference(oracle_lib):
+    """test/test_slab_land.jl:463-508: the similarity profile is evaluated at h - d, floored at twice the roughness length."""
+    host = ne_b200.NumpyHostBackend()
+    ell, wind, kappa = 0.1, 5.0, 0.4
+
+    def ustar(d):
+        ci = _column(host, oracle_lib, "f64", _neutral_fluxes(ell, d), wind)
+        u = _ustar(ci)
+        assert (u == u[0, 0]).all()
+        return float(u[0, 0]), float(ci.atmosphere.surface_layer_height)
+
+    u4, h = ustar(4.0)
+    assert u4 == pytest.approx(kappa / np.log((h - 4) / ell) * wind, rel=1e-12)
+    assert ustar(0.0)[0] == pytest.approx(kappa / np.log(h / ell) * wind, rel=1e-12)
+    assert ustar(6.0)[0] > ustar(3.0)[0] > ustar(0.0)[0]                 # displacement thins the layer, raising the drag
+    assert ustar(2 * h)[0] == pytest.approx(kappa / np.log(2.0) * wind, rel=1e-12)   # floor at 2 l: finite
+
+
+def test_land_markers_resolve_per_cell_like_constants(oracle_lib):
+    """test/test_slab_land.jl:510-549 (LandZeroPlaneDisplacement) and local_roughness_length(::LandRoughnessLength)
+    (similarity_theory_turbulent_fluxes.jl:265-278): a per-cell field reaches the solver as the constant would, bit for bit."""
+    host = ne_b200.NumpyHostBackend()
+    g = synthetic.build_case(CFG, host, lib=oracle_lib).grid
+    # LandZeroPlaneDisplacement with a field of 4 m == the constant 4.0; without a field == 0
+    per_cell = _ustar(_column(host, oracle_lib, "f64", _neutral_fluxes(0.1, F.LandZeroPlaneDisplacement()),
+                              fields={"zero_plane_displacement": np.full(g.shape, 4.0)}))
+    assert np.array_equal(per_cell, _ustar(_column(host, oracle_lib, "f64", _neutral_fluxes(0.1, 4.0))))
+    assert per_cell[0, 0] == pytest.approx(0.4 / np.log((10.0 - 4) / 0.1) * 5.0, rel=1e-12)
+    assert np.array_equal(_ustar(_column(host, oracle_lib, "f64", _neutral_fluxes(0.1, F.LandZeroPlaneDisplacement()))),
+                          _ustar(_column(host, oracle_lib, "f64", _neutral_fluxes(0.1, 0.0))))
+    # LandRoughnessLength: max(multiplier * max(field, minimum), minimum); the scalar slots read the scalar field
+    lm = F.LandRoughnessLength(multiplier=1, minimum_roughness_length=1e-3)
+    ls = F.LandRoughnessLength(multiplier=0.1, minimum_roughness_length=1e-4)
+    fl = F.SimilarityTheoryFluxes(momentum_roughness_length=lm, temperature_roughness_length=ls, water_vapor_roughness_length=ls,
+                                  stability_functions=F.atmosphere_land_stability_functions())
+    z0m, z0s = np.full(g.shape, 0.25), np.full(g.shape, 0.05)
+    z0m[:, ::2] = 1e-5                                                    # below the minimum: floored at 1e-3
+    got = _column(host, oracle_lib, "f64", fl, land_T=294.0, fields={"momentum_roughness_length": z0m, "scalar_roughness_length": z0s})
+    for cols, lu in ((slice(1, None, 2), 0.25), (slice(0, None, 2), 1e-3)):
+        lsc = max(0.1 * 0.05, 1e-4)
+        want = _column(host, oracle_lib, "f64", F.SimilarityTheoryFluxes(
+            momentum_roughness_length=lu, temperature_roughness_length=lsc, water_vapor_roughness_length=lsc,
+            stability_functions=F.atmosphere_land_stability_functions()), land_T=294.0)
+        hx = g.hx % 2
+        sel = slice((cols.start + hx) % 2, None, 2)     # interior column parity after removing the halo
+        for n in got.al_fluxes.names():
+            a = np.asarray(getattr(got.al_fluxes, n))[g.hy:g.hy + g.ny, g.hx:g.hx + g.nx]
+            b = np.asarray(getattr(want.al_fluxes, n))[g.hy:g.hy + g.ny, g.hx:g.hx + g.nx]
+            assert np.array_equal(a[:, sel], b[:, sel]), (n, lu)
+    # a land model that provides no roughness field (SlabLand): the floor stands in, max(multiplier * minimum, minimum)
+    bare = _column(host, oracle_lib, "f64", fl, land_T=294.0)
+    want = _column(host, oracle_lib, "f64", F.SimilarityTheoryFluxes(
+        momentum_roughness_length=1e-3, temperature_roughness_length=1e-4, water_vapor_roughness_length=1e-4,
+        stability_functions=F.atmosphere_land_stability_functions()), land_T=294.0)
+    assert np.array_equal(_ustar(bare), _ustar(want))
+    # larger roughness raises the drag (test/test_slab_land.jl:617-618)
+    assert _ustar(_column(host, oracle_lib, "f64", _neutral_fluxes(0.5)))[0, 0] > _ustar(_column(host, oracle_lib, "f64", _neutral_fluxes(0.05)))[0, 0]
+
+
+def test_land_markers_collapse_to_constants_over_ocean_and_sea_ice():
+    """Over the ocean `interior_properties` has no land fields: LandRoughnessLength returns max(multiplier * minimum, minimum),
+    LandZeroPlaneDisplacement 0 (similarity_theory_turbulent_fluxes.jl:265-303)."""
+    fl = F.SimilarityTheoryFluxes(momentum_roughness_length=F.LandRoughnessLength(multiplier=3, minimum_roughness_length=1e-3),
+                                  temperature_roughness_length=F.LandRoughnessLength(multiplier=0.1, minimum_roughness_length=1e-4),
+                                  water_vapor_roughness_length=1e-4, zero_plane_displacement=F.LandZeroPlaneDisplacement())
+    land = F.flux_formulation_pod(fl, land=True)
+    assert land.ell_momentum.kind == A.NE_ROUGH_LAND and land.zero_plane_displacement_kind == A.NE_DISPLACEMENT_LAND
+    sea = F.flux_formulation_pod(fl)
+    assert sea.ell_momentum.kind == A.NE_ROUGH_CONSTANT and sea.ell_momentum.constant == 3e-3
+    assert sea.ell_temperature.kind == A.NE_ROUGH_CONSTANT and sea.ell_temperature.constant == 1e-4
+    assert sea.zero_plane_displacement_kind == A.NE_DISPLACEMENT_CONSTANT and sea.zero_plane_displacement == 0.0
+    eps32 = F.flux_formulation_pod(F.SimilarityTheoryFluxes(momentum_roughness_length=F.LandRoughnessLength(FT="f32")), FT="f32")
+    assert eps32.ell_momentum.constant == float(np.finfo(np.float32).eps)      # minimum_roughness_length = eps(FT)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("FT", ["f64", "f32"])
+def test_cuda_land_kernel_with_per_cell_roughness_and_displacement(oracle_lib, cuda_backend, cuda_lib, FT):
+    """LandRoughnessLength + LandZeroPlaneDisplacement with random per-cell fields: generic CUDA kernel against the oracle;
+    the displacement marker alone (constant roughness) must leave the work-queue fast path for the generic kernel."""
+    host = ne_b200.NumpyHostBackend()
+    g = synthetic.build_case(CFG, host, lib=oracle_lib).grid
+    rng = np.random.default_rng(404)
+    fields = {"momentum_roughness_length": 10.0 ** rng.uniform(-5, 0.3, g.shape), "scalar_roughness_length": 10.0 ** rng.uniform(-6, -1, g.shape),
+              "zero_plane_displacement": np.where(rng.random(g.shape) < 0.15, rng.uniform(8.0, 25.0, g.shape), rng.uniform(0.0, 6.0, g.shape))}
+    lm, ls = F.LandRoughnessLength(1, 1e-4, FT), F.LandRoughnessLength(0.1, 1e-5, FT)
+    trees = {
+        "markers": F.SimilarityTheoryFluxes(momentum_roughness_length=lm, temperature_roughness_length=ls, water_vapor_roughness_length=ls,
+                                            zero_plane_displacement=F.LandZeroPlaneDisplacement(),
+                                            stability_functions=F.atmosphere_land_stability_functions()),
+        "displacement_only": F.SimilarityTheoryFluxes(momentum_roughness_length=0.1, temperature_roughness_length=0.01, water_vapor_roughness_length=0.01,
+                                                      zero_plane_displacement=F.LandZeroPlaneDisplacement(),
+                                                      stability_functions=F.atmosphere_land_stability_functions()),
+    }
+    tol = 1e-10 if FT == "f64" else 1e-5
+    inner = (slice(g.hy, g.hy + g.ny), slice(g.hx, g.hx + g.nx))
+    for name, fl in trees.items():
+        ref = _column(host, oracle_lib, FT, fl, land_T=292.0, fields=fields, humidity=F.FractionalHumidity(efficiency=0.6))
+        dev = _column(cuda_backend, None, FT, fl, land_T=292.0, fields=fields, humidity=F.FractionalHumidity(efficiency=0.6))
+        cuda_backend.synchronize()
+        ri, di = ref.al_iterations[inner], cuda_backend.to_numpy(dev.al_iterations)[inner]
+        conv = (ri < 100) & (di < 100)
+        assert conv.mean() > 0.9
+        if FT == "f64":
+            assert float((ri != di).mean()) <= 2e-3
+        us = _ustar(ref)
+        assert np.unique(us[conv]).size > 1000, "the per-cell fields did not reach the solver"
+        for n in ref.al_fluxes.names():
+            a = np.asarray(getattr(ref.al_fluxes, n))[inner].astype(np.float64)
+            b = cuda_backend.to_numpy(getattr(dev.al_fluxes, n))[inner].astype(np.float64)
+            s = float(np.nanmax(np.abs(a))) or 1.0
+            assert np.nanmax(np.abs(a - b)[conv]) / s <= tol, f"{name}/{n}: {np.nanmax(np.abs(a - b)[conv]) / s}"
+    # the ocean entry point refuses the markers: the binding passes the collapsed constants there
+    d = dev.atmosphere_ocean_desc()
+    d.flux = F.flux_formulation_pod(trees["markers"], land=True)
+    with pytest.raises(ne_b200.NoKernelVariantError):
+        cuda_lib.call("atmosphere_ocean_fluxes", FT, d, cuda_backend.stream())
+    # SkinTemperature over land has no method in the reference either (no heat capacity in the land properties)
+    d = dev.atmosphere_land_desc()
+    d.properties.temperature_formulation = A.NE_TEMP_SKIN_DIFFUSIVE
+    with pytest.raises(ne_b200.NoKernelVariantError):
+        cuda_lib.call("atmosphere_land_fluxes", FT, d, cuda_backend.stream())
