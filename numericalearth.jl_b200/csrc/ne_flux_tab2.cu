@@ -82,11 +82,73 @@ trip_order_kernel(const uint16_t* __restrict__ hint, const uint32_t n, uint16_t*
 // slowest one had finished — 15 % of the warp slots, ncu `sm__warps_active` 32 % of a possible 37.5 %.)
 // Shape of a CTA: NW warps, REGS registers per thread; everything in dynamic shared memory:
 //   [ solver table | log table per lane class | SL_COUNT columns of NW*32 doubles | parameters of the rare paths ]
-template <int NW> constexpr size_t tab2_smem_bytes() {
-  return sizeof(double) * (fm::TAB_SIZE + 2 * fm::LOG_N * fm::LOG_REP + SL_COUNT * NW * 32) + sizeof(Tab2Rare);
+// PF (opt-in, NE_B200_TAB2_STAGING=1; measured: no gain): the inputs of a warp's NEXT group are staged by cp.async into the thread's own column of ST_COUNT
+// doubles while the current group is being solved — ua, va, Ta, pa, qa, the two uo and two vo values of the cell-centre
+// average, To, So, and one slot of two 32-bit words (the 4-byte words that hold the point's mask byte and the lane's entry of
+// the next permutation row).  A group's prologue then reads shared memory instead of waiting one global-memory latency per
+// group (ncu of the non-staged kernel: 1.7 of its 9 stall cycles per issued instruction were long-scoreboard, nearly all on
+// these loads); nothing is carried in registers across the solve for it.
+enum { ST_UA, ST_VA, ST_TA, ST_PA, ST_QA, ST_UO0, ST_UO1, ST_VO0, ST_VO1, ST_TO, ST_SO, ST_WORDS, ST_COUNT };
+template <int NW, bool PF = false> constexpr size_t tab2_smem_bytes() {
+  return sizeof(double) * (fm::TAB_SIZE + 2 * fm::LOG_N * fm::LOG_REP + (SL_COUNT + (PF ? ST_COUNT : 0)) * NW * 32) + sizeof(Tab2Rare);
 }
 
-template <class CT, bool SORT, class O, int NW, int REGS>
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ int64_t tab2_index(const Layout& L, uint32_t t) {
+  const uint32_t jj = t / (uint32_t)L.ni;
+  return L.at(L.i_lo + (int32_t)(t - jj * (uint32_t)L.ni), L.j_lo + (int32_t)jj);
+}
+
+// request the inputs of point `idx` into the thread's staging column (array slots only: constants are read from the descriptor)
+template <int NT>
+__device__ __forceinline__ void tab2_stage_issue(const NeAtmosOceanDesc& d, const Layout& L, int64_t idx, bool relative, double* st) {
+  cp_async8(st + ST_UA * NT, (const double*)d.ua + idx);
+  cp_async8(st + ST_VA * NT, (const double*)d.va + idx);
+  cp_async8(st + ST_TA * NT, (const double*)d.Ta + idx);
+  cp_async8(st + ST_PA * NT, (const double*)d.pa + idx);
+  cp_async8(st + ST_QA * NT, (const double*)d.qa + idx);
+  if (relative) {
+    if (d.uo.ptr) { cp_async8(st + ST_UO0 * NT, (const double*)d.uo.ptr + idx); cp_async8(st + ST_UO1 * NT, (const double*)d.uo.ptr + idx + 1); }
+    if (d.vo.ptr) { cp_async8(st + ST_VO0 * NT, (const double*)d.vo.ptr + idx); cp_async8(st + ST_VO1 * NT, (const double*)d.vo.ptr + idx + L.sx); }
+  }
+  if (d.To.ptr) cp_async8(st + ST_TO * NT, (const double*)d.To.ptr + idx);
+  if (d.So.ptr) cp_async8(st + ST_SO * NT, (const double*)d.So.ptr + idx);
+  if (d.inactive) {   // the aligned 4-byte word that holds the mask byte (never leaves the byte's own page)
+    const uintptr_t a = (uintptr_t)(d.inactive + idx);
+    cp_async4(reinterpret_cast<uint32_t*>(st + ST_WORDS * NT), reinterpret_cast<const void*>(a & ~(uintptr_t)3));
+  }
+}
+
+// the staged point, exactly as tab2_load forms it
+template <int NT>
+__device__ __forceinline__ void tab2_stage_read(const NeAtmosOceanDesc& d, int64_t idx, bool celsius, bool relative, const double* st,
+                                                Parked& k, double& uo, double& vo, double& So, bool& not_water) {
+  k.du = st[ST_UA * NT]; k.dv = st[ST_VA * NT]; k.Ta = st[ST_TA * NT]; k.pa = st[ST_PA * NT]; k.qa = st[ST_QA * NT];
+  uo = vo = 0;
+  if (relative) {
+    uo = d.uo.ptr ? (st[ST_UO0 * NT] + st[ST_UO1 * NT]) / 2 : d.uo.value;
+    vo = d.vo.ptr ? (st[ST_VO0 * NT] + st[ST_VO1 * NT]) / 2 : d.vo.value;
+  }
+  double To = d.To.ptr ? st[ST_TO * NT] : d.To.value;
+  if (celsius) To = To + 273.15;
+  k.Ts = To;
+  So = d.So.ptr ? st[ST_SO * NT] : d.So.value;
+  not_water = false;
+  if (d.inactive) {
+    const uint32_t w = reinterpret_cast<const uint32_t*>(st + ST_WORDS * NT)[0];
+    not_water = ((w >> (8u * (uint32_t)((uintptr_t)(d.inactive + idx) & 3))) & 0xffu) != 0;
+  }
+}
+
+template <class CT, bool SORT, class O, int NW, int REGS, bool PF = false>
 __global__ void __launch_bounds__(NW * 32) __maxnreg__(REGS)
 ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_constant__ Layout L,
                     const __grid_constant__ Thermo<CT> th, const __grid_constant__ FastParams P,
@@ -98,7 +160,7 @@ ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
   extern __shared__ __align__(16) double tab[];   // fm::TAB_SIZE doubles, then:
   double* const lrep = tab + fm::TAB_SIZE;         // the log table once per lane class (fm::log_pos_rep)
   double* const park = lrep + 2 * fm::LOG_N * fm::LOG_REP;
-  Tab2Rare& rare = *reinterpret_cast<Tab2Rare*>(park + SL_COUNT * NT);
+  Tab2Rare& rare = *reinterpret_cast<Tab2Rare*>(park + (SL_COUNT + (PF ? ST_COUNT : 0)) * NT);   // behind the staging columns
   if (threadIdx.x == 0) { rare.P = P; rare.T = T; }
   for (int k = threadIdx.x; k < fm::TAB_SIZE / 2; k += NT)
     reinterpret_cast<double2*>(tab)[k] = __ldg(reinterpret_cast<const double2*>(gtab) + k);
@@ -122,34 +184,70 @@ ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
     if (lane == 0) v = atomicAdd(next_group, 1u);
     return __shfl_sync(0xffffffffu, v, 0);
   };
-  // the next group index is requested one group ahead, and so is the next group's row of the permutation: their latencies
-  // hide behind the solve in between
+  // Software pipeline over a warp's groups.  Not staged (PF = false): the next group index is requested one group ahead, and so
+  // is the next group's row of the permutation.  Staged (PF): group indices are requested two groups ahead, the permutation row
+  // one and a half (as a cp.async word), the fields of the next group one ahead — every latency hides behind a whole solve.
+  constexpr uint32_t END = 0xffffffffu;
+  double* const st = park + SL_COUNT * NT + tid;                          // staging column (PF)
+  uint32_t* const stw = reinterpret_cast<uint32_t*>(st + ST_WORDS * NT);  // [0] mask word, [1] permutation word
+  auto point_of = [&](uint32_t gg, uint32_t p) {                          // position in the launch range of this lane's point of group gg
+    const uint32_t slot = gg * 32u + (uint32_t)lane;
+    return SORT ? (slot & ~(uint32_t)(W - 1)) + p : slot;
+  };
+  auto stage_perm = [&](uint32_t gg) {                                    // the aligned word that holds perm[gg * 32 + lane]
+    if (SORT) cp_async4(stw + 1, perm + ((gg * 32u + (uint32_t)lane) & ~1u));
+  };
   uint32_t g = grab();
   uint32_t g_next = g < n_groups ? grab() : g;
+  uint32_t g_after = (PF && g_next < n_groups) ? grab() : g_next;
   uint32_t p_cur = (SORT && g < n_groups) ? perm[g * 32u + (uint32_t)lane] : 0u;
+  uint32_t t_cur = g < n_groups ? point_of(g, p_cur) : END;
+  if (PF) {
+    if (t_cur < n) tab2_stage_issue<NT>(d, L, tab2_index(L, t_cur), relative, st);
+    if (g_next < n_groups) stage_perm(g_next);
+    cp_async_commit();
+  }
 #pragma unroll 1
-  while (g < n_groups) {
-    const uint32_t slot = g * 32u + (uint32_t)lane;                       // position in the (sorted) launch range
-    const uint32_t t = SORT ? (slot & ~(uint32_t)(W - 1)) + p_cur : slot;
-    g = g_next;
-    if (g < n_groups) g_next = grab();
-    const uint32_t slot_next = g * 32u + (uint32_t)lane;
-    if (SORT && g < n_groups) p_cur = perm[slot_next];                    // consumed by the next pass
-    // (an L2 prefetch of the next group's ten input lines from here was measured: 1.360 vs 1.351 ms on C4 — the other five
-    // warps of the scheduler already cover a group's load latency; profiles/r02_notes.md)
+  while (t_cur != END) {
+    const uint32_t t = t_cur;
     const bool valid = t < n;
     int64_t idx = 0;
     bool not_water = true;
     Parked k;
     double So = 0;
-    if (valid) {   // the mask and the fields are requested together: one memory latency per group, not two
-      const uint32_t jj = t / (uint32_t)L.ni;
-      idx = L.at(L.i_lo + (int32_t)(t - jj * (uint32_t)L.ni), L.j_lo + (int32_t)jj);
-      const uint8_t mask = d.inactive ? d.inactive[idx] : (uint8_t)0;
+    if (PF) {
+      cp_async_wait_all();
       double uo, vo;
-      tab2_load<true>(d, L, idx, celsius, relative, k, uo, vo, So);
-      not_water = mask != 0;
-      if (!not_water) { k.du -= uo; k.dv -= vo; }   // land: zero_interface_state, Δu = uₐ − 0 (interface_states.jl:800-803)
+      if (valid) {
+        idx = tab2_index(L, t);
+        tab2_stage_read<NT>(d, idx, celsius, relative, st, k, uo, vo, So, not_water);
+        if (!not_water) { k.du -= uo; k.dv -= vo; }
+      }
+      // the next group's point, its fields, the permutation row of the group after it, the index of the one after that
+      t_cur = END;
+      if (g_next < n_groups) {
+        const uint32_t p = SORT ? ((stw[1] >> (16u * ((uint32_t)lane & 1u))) & 0xffffu) : 0u;
+        t_cur = point_of(g_next, p);
+        if (t_cur < n) tab2_stage_issue<NT>(d, L, tab2_index(L, t_cur), relative, st);
+      }
+      if (g_after < n_groups) stage_perm(g_after);
+      cp_async_commit();
+      g_next = g_after;
+      if (g_after < n_groups) g_after = grab();
+    } else {
+      g = g_next;
+      if (g < n_groups) g_next = grab();
+      if (SORT && g < n_groups) p_cur = perm[g * 32u + (uint32_t)lane];   // consumed by the next pass
+      t_cur = g < n_groups ? END - 1u : END;                              // resolved at the bottom, when p_cur has landed
+      // (an L2 prefetch of the next group's ten input lines from here was measured: 1.360 vs 1.351 ms on C4; profiles/r02_notes.md)
+      if (valid) {   // the mask and the fields are requested together: one memory latency per group, not two
+        idx = tab2_index(L, t);
+        const uint8_t mask = d.inactive ? d.inactive[idx] : (uint8_t)0;
+        double uo, vo;
+        tab2_load<true>(d, L, idx, celsius, relative, k, uo, vo, So);
+        not_water = mask != 0;
+        if (!not_water) { k.du -= uo; k.dv -= vo; }   // land: zero_interface_state, Δu = uₐ − 0 (interface_states.jl:800-803)
+      }
     }
     const bool solve = valid && !(not_water && !P.fixed);   // needs_to_converge && not_water: no solve (atmosphere_ocean_fluxes.jl:144)
     const unsigned solving = __ballot_sync(0xffffffffu, solve);   // all 32 lanes are converged here (loop head)
@@ -176,6 +274,7 @@ ao_flux_tab2_kernel(const __grid_constant__ NeAtmosOceanDesc d, const __grid_con
       else if (hint) hint[t] = 0;
       tab2_epilogue<O, CT>(o, d, th, idx, celsius, not_water, k, ustar, theta_star, q_star, iters);
     }
+    if (!PF && t_cur != END) t_cur = point_of(g, p_cur);
   }
   if (!std::is_same<O, fm::OpsPlain>::value) {
     o.flush(counts);
@@ -245,7 +344,7 @@ bool tab2_eligible(const NeAtmosOceanDesc& d, const TabParams& TP) {
   return n > 0 && n < ((int64_t)1 << 31) - TAB2_WINDOW;
 }
 
-template <class CT, int NW, int REGS, int CTAS>
+template <class CT, int NW, int REGS, int CTAS, bool PF = false>
 static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P, const TabParams& TP, const Micro& Mi,
                          const Tab2First& F, const double* tab, cudaStream_t s, unsigned long long* counts, uint16_t* perm, uint16_t* hint, uint32_t n) {
   constexpr int W = TAB2_WINDOW;
@@ -260,17 +359,17 @@ static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastP
   }
   const unsigned grid = tab2_grid(n_windows * (W / 32), NW, CTAS);
   const Thermo<CT> th = Thermo<CT>::make(d.thermo);
-  constexpr size_t smem = tab2_smem_bytes<NW>();
-#define NE_TAB2_GO(SORT, O)                                                                                              \
+  constexpr size_t smem = tab2_smem_bytes<NW, PF>();
+#define NE_TAB2_GO(SORT, O, STAGED)                                                                                      \
   do {                                                                                                                   \
-    if (cudaError_t e = allow_table_smem<ao_flux_tab2_kernel<CT, SORT, O, NW, REGS>>(smem); e != cudaSuccess)            \
+    if (cudaError_t e = allow_table_smem<ao_flux_tab2_kernel<CT, SORT, O, NW, REGS, STAGED>>(smem); e != cudaSuccess)    \
       return cuda_error(e, "ne_atmosphere_ocean_fluxes(tab2: shared memory opt-in)");                                    \
-    ao_flux_tab2_kernel<CT, SORT, O, NW, REGS><<<grid, NW * 32, smem, s>>>(d, L, th, P, TP, Mi, F, tab, perm, hint, counts, counter); \
+    ao_flux_tab2_kernel<CT, SORT, O, NW, REGS, STAGED><<<grid, NW * 32, smem, s>>>(d, L, th, P, TP, Mi, F, tab, perm, hint, counts, counter); \
   } while (0)
   if (counts) {
-    if (perm) NE_TAB2_GO(true, fm::OpsCount); else NE_TAB2_GO(false, fm::OpsCount);
+    if (perm) NE_TAB2_GO(true, fm::OpsCount, false); else NE_TAB2_GO(false, fm::OpsCount, false);
   } else {
-    if (perm) NE_TAB2_GO(true, fm::OpsPlain); else NE_TAB2_GO(false, fm::OpsPlain);
+    if (perm) NE_TAB2_GO(true, fm::OpsPlain, PF); else NE_TAB2_GO(false, fm::OpsPlain, PF);
   }
 #undef NE_TAB2_GO
   NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(tab2)");
@@ -291,14 +390,22 @@ int launch_tab2(const NeAtmosOceanDesc& d, const Layout& L, const FastParams& P,
   const Tab2First F = make_tab2_first(P, TP, host_tab, d.surface_layer_height.value - P.d_zero, TP.log_hd);
   // CTA shape (NE_B200_TAB2_SHAPE; C4: 1.322 / 1.355 / 1.278 ms): 0 = 8 warps x 3 CTAs per SM at 80 registers, 1 = 32 warps x 1 CTA at 64
   // registers (a third more resident warps, but the spills push the L1TEX data pipe to 81 %), 2 = 24 warps x 1 CTA at 80 registers (shipped:
-  // one table per SM instead of three)
+  // one table per SM instead of three), 3 = 28 warps x 1 CTA at 72 registers (25 warps at 80 do not launch: registers are granted per 4 warps)
   const int shape = counts ? 0 : env_int("NE_B200_TAB2_SHAPE", 2);
   const bool f64 = d.thermo.dtype == NE_F64;
 #define NE_TAB2_SHAPE(NW, REGS, CTAS)                                                                            \
   return f64 ? launch_tab2_t<double, NW, REGS, CTAS>(d, L, P, TP, Mi, F, tab, s, counts, perm, hint, n)          \
              : launch_tab2_t<float, NW, REGS, CTAS>(d, L, P, TP, Mi, F, tab, s, counts, perm, hint, n)
   if (shape == 1) { NE_TAB2_SHAPE(32, 64, 1); }
-  if (shape == 2) { NE_TAB2_SHAPE(24, 80, 1); }
+  if (shape == 2) {
+    // cp.async staging of the next group's inputs (PF): bit-identical, measured 1.295 vs 1.289 ms on C4, 0.212 vs 0.201 ms on C2
+    // (profiles/r02_time_ao_j21_staging.log): the other warps of a scheduler already cover a group's load latency.  Opt-in.
+    if (env_flag("NE_B200_TAB2_STAGING"))
+      return f64 ? launch_tab2_t<double, 24, 80, 1, true>(d, L, P, TP, Mi, F, tab, s, counts, perm, hint, n)
+                 : launch_tab2_t<float, 24, 80, 1, true>(d, L, P, TP, Mi, F, tab, s, counts, perm, hint, n);
+    NE_TAB2_SHAPE(24, 80, 1);
+  }
+  if (shape == 3) { NE_TAB2_SHAPE(28, 72, 1); }   // 1.280 vs 1.288 ms on C4: ~5 local-memory accesses per trip eat the extra warps
   NE_TAB2_SHAPE(8, 80, 3);
 #undef NE_TAB2_SHAPE
 }
