@@ -15,6 +15,8 @@ Sources (all relative to /root/reference):
   roughness lengths              docs/src/interface_fluxes.md:236-262 ; roughness_lengths.jl:197-246 (Edson 2013 eq. 28)
   gustiness                      similarity_theory_turbulent_fluxes.jl:36-48, 88-98  (U_G = max(floor, β (J_b h_bl)^{1/3}))
   Edson et al. (2013) ψ_u, ψ_θ   docstring mathematics at similarity_theory_turbulent_fluxes.jl:450-486, 534-570
+  SHEBA / Paulson / linear ψ     the flux–profile relations φ of Grachev et al. (2007), Paulson (1970), Large & Yeager (2004),
+                                 integrated numerically: ψ(ζ) = ∫₀^ζ (1 − φ)/x dx (no closed form shared with the reference)
                                  (= COARE 3.5 psiu_26 / psit_26) with the constants of :487-499, 571-584
   similarity profile, χ          docs/src/interface_fluxes.md:620-690 ; similarity_theory_turbulent_fluxes.jl:239-253, 375-384
   fixed point + stopping rule    compute_interface_state.jl:5-58
@@ -180,6 +182,63 @@ def psi_scalar(zeta, c: EdsonConstants = EdsonConstants()):
         return (1 - f) * kansas + f * conv
     dz = min(_m(c.zmax), _m(c.Ap) * z)
     return -(1 + _m(c.Bp_s) * z) ** _m(c.Cp_s) - _m(c.Bp_s) * (z - _m(c.Dp_s)) * mp.exp(-dz) - _m(c.Ep_s)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The other shipped stability functions, from the FLUX–PROFILE RELATIONS of the papers the reference cites — not from
+# the closed forms it codes (similarity_theory_turbulent_fluxes.jl:636-745).  A stability function is the integral
+#     ψ(ζ) = ∫₀^ζ (1 − φ(x)) / x dx                                   (Paulson 1970, eq. 3; Grachev et al. 2007, eq. 10)
+# of the non-dimensional gradient φ; evaluating that integral numerically at 50 digits shares no algebra with the
+# antiderivatives the reference (and the oracle) use.
+# ----------------------------------------------------------------------------------------------------------------
+def phi_sheba_momentum(x, a=6.5, b=1.3):
+    """Grachev et al. (2007) eq. 9a is φ_m = 1 + a_m ζ (1 + ζ)^{1/3} / (1 + b_m ζ) with a_m = 5, b_m = a_m / 6.5, and their eq. 12
+    is its integral.  The reference evaluates eq. 12 with its fields a = 6.5, b = 1.3 in the places of a_m, b_m
+    (similarity_theory_turbulent_fluxes.jl:636-657), i.e. it integrates φ_m = 1 + 6.5 ζ (1 + ζ)^{1/3} / (1 + 1.3 ζ) — not the
+    φ of its own comment (:642: 1 + a ζ ∛(1 + ζ) / (b + ζ), whose integral is 23 % smaller at small ζ; this pin found the
+    difference).  A drop-in reproduces the reference as coded, so THAT function is the one pinned here."""
+    return 1 + _m(a) * x * mp.cbrt(1 + x) / (1 + _m(b) * x)
+
+
+def phi_sheba_scalar(x, a=5.0, b=5.0, c=3.0):     # eq. 9b: φ_h = 1 + (a ζ + b ζ²) / (1 + c ζ + ζ²)
+    return 1 + (_m(a) * x + _m(b) * x * x) / (1 + _m(c) * x + x * x)
+
+
+def phi_businger_dyer_momentum(x, gamma=16.0):    # Paulson (1970) / Businger–Dyer: φ_m = (1 − γ ζ)^{-1/4}, ζ < 0
+    return (1 - _m(gamma) * x) ** M("-0.25")
+
+
+def phi_businger_dyer_scalar(x, gamma=16.0):      # φ_h = (1 − γ ζ)^{-1/2}, ζ < 0
+    return (1 - _m(gamma) * x) ** M("-0.5")
+
+
+def phi_linear_stable(x, c=5.0, zmax=10.0):       # Large & Yeager (2004): φ = 1 + c ζ, ψ held at its ζ_max value beyond
+    return 1 + _m(c) * x if x <= _m(zmax) else M(1)
+
+
+def psi_from_phi(phi, zeta):
+    """∫₀^ζ (1 − φ(x))/x dx, decade by decade (the integrand is smooth but varies over many scales)."""
+    z = _m(zeta)
+    if z == 0:
+        return M(0)
+    sgn = 1 if z > 0 else -1
+    a = abs(z)
+    edges = [M(0)]
+    e = M("1e-8")
+    while e < a:
+        edges.append(e)
+        e *= 10
+    edges.append(a)
+    f = lambda t: (1 - phi(sgn * t)) / t        # noqa: E731   (dx/x is invariant under x -> -x)
+    return mp.quad(f, edges)
+
+
+def psi_split(stable_phi, unstable_phi, zeta):
+    """SplitStabilityFunction(stable, unstable): the stable function sees max(0, ζ), the unstable one min(0, ζ)."""
+    z = _m(zeta)
+    if z > 0:
+        return psi_from_phi(stable_phi, z) if stable_phi is not None else M(0)
+    return psi_from_phi(unstable_phi, z) if unstable_phi is not None else M(0)
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -72,6 +72,47 @@ def test_edson_stability_functions(oracle_lib, kind):
     assert worst_ulp <= 32.0, worst_ulp     # |ψ| and its terms reach ~10 and each term carries the rounding of its argument: a few tens of eps(1)
 
 
+OTHER_PSI = {
+    # name: (formulation object handed to the oracle, stable φ, unstable φ, range of ζ sampled)
+    "sheba_momentum": (lambda: F.ShebaMomentumStabilityFunction(), R.phi_sheba_momentum, None, (1e-6, 150.0)),
+    "sheba_scalar": (lambda: F.ShebaScalarStabilityFunction(), R.phi_sheba_scalar, None, (1e-6, 150.0)),
+    "paulson_momentum": (lambda: F.PaulsonMomentumStabilityFunction(), None, R.phi_businger_dyer_momentum, (1e-6, 1e5)),
+    "paulson_scalar": (lambda: F.PaulsonScalarStabilityFunction(), None, R.phi_businger_dyer_scalar, (1e-6, 1e5)),
+    "linear_stable": (lambda: F.LinearStableStabilityFunction(), R.phi_linear_stable, None, (1e-6, 40.0)),
+    "sea_ice_momentum": (lambda: F.atmosphere_sea_ice_stability_functions().momentum, R.phi_sheba_momentum, R.phi_businger_dyer_momentum, (1e-6, 1e3)),
+    "sea_ice_scalar": (lambda: F.atmosphere_sea_ice_stability_functions().temperature, R.phi_sheba_scalar, R.phi_businger_dyer_scalar, (1e-6, 1e3)),
+    "large_yeager_momentum": (lambda: F.large_yeager_stability_functions().momentum, R.phi_linear_stable, R.phi_businger_dyer_momentum, (1e-6, 1e3)),
+    "large_yeager_scalar": (lambda: F.large_yeager_stability_functions().temperature, R.phi_linear_stable, R.phi_businger_dyer_scalar, (1e-6, 1e3)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(OTHER_PSI))
+def test_other_stability_functions_against_their_flux_profile_integrals(oracle_lib, name):
+    """SHEBA (Grachev et al. 2007), Paulson (1970), the linear stable function of Large & Yeager (2004) and the two shipped
+    SplitStabilityFunction pairs (sea ice, land / NCAR): the oracle's closed forms against ψ(ζ) = ∫₀^ζ (1 − φ(x))/x dx evaluated
+    numerically at 50 digits from the papers' φ — an antiderivative mis-copied from the reference cannot pass this."""
+    make, stable, unstable, (lo, hi) = OTHER_PSI[name]
+    pod = F.stability_profile_pod(make())
+    rng = np.random.default_rng(abs(hash(name)) % 1000 + 7)
+    n = max(60, N_POINTS // 400)
+    mag = 10.0 ** rng.uniform(np.log10(lo), np.log10(hi), n)
+    sign = np.where(rng.random(n) < 0.5, 1.0, -1.0)
+    if stable is None:
+        sign[: n * 3 // 4] = -1.0        # mostly the side that is not identically zero
+    if unstable is None:
+        sign[: n * 3 // 4] = 1.0
+    worst = 0.0
+    for zz in (sign * mag).tolist() + [0.0]:
+        got = oracle_lib.dll.neo_stability_f64(C.byref(pod), float(zz))
+        ex = R.psi_split(stable, unstable, float(zz))
+        if name == "linear_stable" and zz < 0:
+            ex = mp.mpf(0)
+        rel = float(abs(mp.mpf(got) - ex) / max(mp.mpf(1), abs(ex)))
+        worst = max(worst, rel / 2.220446049250313e-16)
+    _record(f"psi_{name}_vs_integral", points=n + 1, worst_in_eps=worst)
+    assert worst <= 64.0, worst       # closed forms with logs / arctangents of O(1..10) arguments: a few tens of eps(1)
+
+
 def test_saturation_vapor_pressure_and_surface_humidity(oracle_lib):
     rng = np.random.default_rng(103)
     th = F.AtmosphereThermodynamicsParameters(FT="f64").pod()
