@@ -338,6 +338,133 @@ def solve_point(atm, ocean, P: SolverParams = SolverParams(), round_iterate=True
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# atmosphere – sea ice: the same similarity step with the sea-ice stability functions, ice-phase surface humidity and a
+# skin temperature re-solved every trip (docs/src/interface_fluxes.md:679-700: "a four-variable system"; the balance and its
+# linearisation are the comment block of interface_states.jl:459-467)
+# ----------------------------------------------------------------------------------------------------------------
+def psi_closed(kind, zeta):
+    """Antiderivatives of the flux–profile relations above, derived by hand and CHECKED against psi_from_phi to 1e-25 by
+    tests/test_oracle_independent_pin.py (so the whole-solve pin below does not pay a quadrature per trip)."""
+    z = _m(zeta)
+    if kind == "sheba_momentum":                     # ∫ of 1 − φ, φ = 1 + a ζ (1+ζ)^{1/3} / (1 + b ζ): substitute x = (1+ζ)^{1/3}
+        if z <= 0:
+            return M(0)
+        a, b = _m(6.5), _m(1.3)                      # the doubles the reference holds
+        x = mp.cbrt(1 + z)
+        B = -mp.cbrt((b - 1) / b)                    # real cube root of (1 − b)/b < 0
+        r3 = mp.sqrt(3)
+        poly = -3 * a * (x - 1) / b
+        rest = a * B / (2 * b) * (2 * mp.log((x + B) / (1 + B)) - mp.log((x * x - B * x + B * B) / (1 - B + B * B))
+                                  + 2 * r3 * (mp.atan((2 * x - B) / (r3 * B)) - mp.atan((2 - B) / (r3 * B))))
+        return poly + rest
+    if kind == "sheba_scalar":                       # partial fractions of (a ζ + b ζ²)/(ζ (1 + c ζ + ζ²))
+        if z <= 0:
+            return M(0)
+        a, b, c = M(5), M(5), M(3)
+        B = mp.sqrt(c * c - 4)
+        return -b / 2 * mp.log(1 + c * z + z * z) + (b * c / (2 * B) - a / B) * (
+            mp.log((2 * z + c - B) / (2 * z + c + B)) - mp.log((c - B) / (c + B)))
+    if kind == "paulson_momentum":                   # Paulson (1970) eq. 8
+        if z >= 0:
+            return M(0)
+        x = (1 - 16 * z) ** M("0.25")
+        return 2 * mp.log((1 + x) / 2) + mp.log((1 + x * x) / 2) - 2 * mp.atan(x) + mp.pi / 2
+    if kind == "paulson_scalar":                     # Paulson (1970) eq. 9
+        if z >= 0:
+            return M(0)
+        return 2 * mp.log((1 + mp.sqrt(1 - 16 * z)) / 2)
+    raise ValueError(kind)
+
+
+@dataclass
+class SeaIceParams:   # component_interfaces.jl:262-290, 396-418 (defaults of an OceanSeaIceModel); ClimaSeaIce defaults (third party)
+    conductivity: float = 2.0                 # SkinTemperature(ConductiveFlux(k))
+    max_dT: float = 5.0                       # interface_states.jl:360
+    liquidus_slope: float = 0.054             # LinearLiquidus
+    freshwater_melting_celsius: float = 0.0
+    albedo: float = 0.7
+    emissivity: float = 1.0
+    sigma: float = 5.670374419e-8
+
+
+def sea_ice_trip(state, atm, ice, P: SolverParams, I: SeaIceParams, rnd):
+    """state = (u★, θ★, q★, Tₛ, qₛ); atm = (u, v, T, p, q, sw, lw); ice = (S_ocean, hi, hc).  `rnd` rounds to the model's
+    element type where the reference converts (the new Tₛ, qₛ and scales)."""
+    us, ts, qs_star, Ts_prev, q_prev = state
+    ua, va, Ta, pa, qa, sw, lw = atm
+    S_oc, hi, hc = ice
+    th = P.thermo
+    h = _m(P_h(P))
+    rho = pa / (R_mix(qa, th) * Ta)
+    cpm = cp_mix(qa, th)
+    L_sub = _m(th.LH_s0) + (_m(th.cp_v) - _m(th.cp_i)) * (Ta - _m(th.T_0))
+    # flux balance with the upwelling long wave linearised about the previous skin temperature
+    up = _m(I.sigma) * _m(I.emissivity) * Ts_prev ** 4
+    Q_down = -(1 - _m(I.albedo)) * sw - _m(I.emissivity) * lw
+    Q_sensible = -rho * cpm * us * ts
+    Q_latent = -rho * L_sub * us * qs_star
+    Q_a = Q_latent + up + Q_down
+    theta_a = Ta + _m(P.g) * h / cpm
+    dT = theta_a - Ts_prev
+    omega = M(0) if dT == 0 else Q_sensible / dT
+    beta = 4 * up / Ts_prev
+    Rth = hi / _m(I.conductivity)
+    T_bottom = _m(I.freshwater_melting_celsius) - _m(I.liquidus_slope) * S_oc + M("273.15")
+    D = 1 + beta * Rth - omega * Rth
+    T_new = Ts_prev if D == 0 else (T_bottom + beta * Rth * Ts_prev - omega * Rth * theta_a - Q_a * Rth) / D
+    step = max(-_m(I.max_dT), min(_m(I.max_dT), T_new - Ts_prev))
+    T_new = min(Ts_prev + step, _m(I.freshwater_melting_celsius) + M("273.15"))
+    if not hi >= hc:
+        T_new = T_bottom
+    T_new = rnd(T_new)
+    q_new = rnd(q_surface(pa, T_new, 1.0, th, ice=True))
+    # similarity step at the new surface state
+    b = buoyancy_scale(ts, qs_star, T_new, q_new, _m(P.g), th)
+    U = mp.sqrt(ua * ua + va * va + gustiness_squared(us, b, _m(P_hbl(P)), P))     # sea ice at rest (atmosphere_sea_ice_fluxes.jl:96-97)
+    lu = ell_momentum(us, P)
+    ls = ell_scalar(lu, us, P)
+    hh = max(h, 2 * lu)
+    kap = _m(P.kappa)
+
+    def profile(stable, unstable, ell):
+        if b == 0:
+            return mp.log(hh / ell)
+        L = us * us / (kap * b)
+        f = lambda zz: psi_closed(stable, zz) if zz > 0 else psi_closed(unstable, zz)   # noqa: E731
+        return mp.log(hh / ell) - f(hh / L) + f(ell / L)
+
+    cu = kap / profile("sheba_momentum", "paulson_momentum", lu)
+    cs = kap / profile("sheba_scalar", "paulson_scalar", ls)
+    return rnd(cu * U), rnd(cs * (theta_a - T_new)), rnd(cs * (qa - q_new)), T_new, q_new
+
+
+def solve_sea_ice_point(atm, ice, Ts0_kelvin, P: SolverParams = SolverParams(), I: SeaIceParams = SeaIceParams()):
+    """compute_interface_state for one consolidated-or-not ice point; returns (u★, θ★, q★, Tₛ, trips, fluxes)."""
+    rnd = lambda x: _m(float(x))   # noqa: E731
+    atm = tuple(_m(x) for x in atm)
+    ice = tuple(_m(x) for x in ice)
+    th = P.thermo
+    Ts = _m(Ts0_kelvin)
+    s = (_m(9.999999747378752e-05),) * 3 + (Ts, rnd(q_surface(atm[3], Ts, 1.0, th, ice=True)))   # convert(FT, 1f-4): the Float32 literal, widened (atmosphere_sea_ice_fluxes.jl:127)
+    trips = 0
+    while True:
+        new = sea_ice_trip(s, atm, ice, P, I, rnd)
+        trips += 1
+        drift = abs(new[0] - s[0]) + abs(new[1] - s[1]) + abs(new[2] - s[2])
+        s = new
+        if drift < _m(P.tol) or trips >= P.maxiter:
+            break
+    us, ts, qs_, Ts, _ = s
+    ua, va, Ta, pa, qa = atm[:5]
+    rho = pa / (R_mix(qa, th) * Ta)
+    L_sub = _m(th.LH_s0) + (_m(th.cp_v) - _m(th.cp_i)) * (Ta - _m(th.T_0))
+    dU = mp.sqrt(ua * ua + va * va)
+    fluxes = dict(latent_heat=-rho * us * qs_ * L_sub, sensible_heat=-rho * cp_mix(qa, th) * us * ts, water_vapor=-rho * us * qs_,
+                  x_momentum=M(0) if dU == 0 else rho * (-us * us * ua / dU), y_momentum=M(0) if dU == 0 else rho * (-us * us * va / dU))
+    return us, ts, qs_, Ts, trips, fluxes
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # interpolation (Oceananigans, third party: restated from its documented behaviour)
 # ----------------------------------------------------------------------------------------------------------------
 def interpolator(f):

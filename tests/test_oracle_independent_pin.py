@@ -227,3 +227,61 @@ def test_whole_fixed_points_and_fluxes(oracle_lib, host_backend):
     _record("whole fixed points", solves=n, trip_count_mismatches=trip_mismatch, worst_rel_scales=worst_scale, worst_rel_fluxes=worst_flux)
     assert trip_mismatch <= max(1, n // 500), trip_mismatch     # a drift within rounding of tol may flip the last trip
     assert worst_scale <= 1e-10 and worst_flux <= 1e-10, (worst_scale, worst_flux)
+
+
+def test_closed_forms_of_the_pin_equal_their_integrals():
+    """The antiderivatives the sea-ice whole-solve pin uses (reference_mp.psi_closed) against the quadrature of the same φ."""
+    pairs = {"sheba_momentum": R.phi_sheba_momentum, "sheba_scalar": R.phi_sheba_scalar,
+             "paulson_momentum": R.phi_businger_dyer_momentum, "paulson_scalar": R.phi_businger_dyer_scalar}
+    for kind, phi in pairs.items():
+        sgn = 1 if kind.startswith("sheba") else -1
+        for mag in (1e-5, 3e-3, 0.2, 1.7, 30.0, 400.0):
+            z = sgn * mag
+            a, b = R.psi_closed(kind, z), R.psi_from_phi(phi, z)
+            assert abs(a - b) <= mp.mpf("1e-25") * max(1, abs(b)), (kind, z, a, b)
+        assert R.psi_closed(kind, -sgn * 2.0) == 0
+
+
+def test_sea_ice_whole_fixed_points(oracle_lib, host_backend):
+    """Ice-covered points of a synthetic OceanSeaIce case through the oracle's a–si kernel and through the independent
+    restatement (skin-temperature balance with linearised long wave, ice-phase humidity, SHEBA / Paulson profiles, the same
+    stopping rule): trip counts, the skin temperature and the five fluxes."""
+    from numericalearth_jl_b200 import synthetic
+    cfg = dict(nx=72, ny=40, latitude=(-80.0, 80.0), src_nx=64, src_ny=32)
+    ci = synthetic.build_case(cfg, host_backend, FT="f64", atm_FT="f64", sea_ice=True, lib=oracle_lib, with_iterations=True)
+    ci.initialize()
+    ci.interpolate_state(0.37 * 10800.0)
+    g = ci.grid
+    T0 = np.array(ci.sea_ice_state.top_temperature, copy=True)
+    ci.compute_atmosphere_sea_ice_fluxes()
+    conc, inactive = np.asarray(ci.sea_ice_state.concentration), np.asarray(ci.inactive)
+    it = np.asarray(ci.asi_iterations)
+    cand = [(j, i) for j in range(g.hy, g.hy + g.ny) for i in range(g.hx, g.hx + g.nx) if conc[j, i] > 0 and not inactive[j, i]]
+    assert len(cand) > 50
+    rng = np.random.default_rng(9)
+    picks = [cand[k] for k in rng.choice(len(cand), size=min(40, len(cand)), replace=False)]
+    a, r, si = ci.atmos_state, ci.rad_state, ci.sea_ice_state
+    worst_T = worst_flux = 0.0
+    mismatch = maxed = 0
+    for (j, i) in picks:
+        atm = tuple(float(x[j, i]) for x in (a.u, a.v, a.T, a.p, a.q, r.sw, r.lw))
+        ice = (float(ci.ocean_state.S[j, i]), float(si.hi[j, i]), float(si.hc[j, i]))
+        Ts0 = float(np.float64(T0[j, i]) + 273.15)
+        us, ts, qs, Ts, trips, fl = R.solve_sea_ice_point(atm, ice, Ts0)
+        if int(it[j, i]) != trips:
+            mismatch += 1
+            continue
+        if trips >= 100:          # a limit cycle of the rounded iterate: the two orbits need not be in phase
+            maxed += 1
+            continue
+        got_T = float(np.float64(si.top_temperature[j, i]) + 273.15)
+        worst_T = max(worst_T, float(abs(mp.mpf(got_T) - Ts) / Ts))
+        floors = {"latent_heat": 1e-3, "sensible_heat": 1e-3, "water_vapor": 1e-9, "x_momentum": 1e-6, "y_momentum": 1e-6}
+        for name, ex in fl.items():
+            got = float(getattr(ci.asi_fluxes, name)[j, i])
+            worst_flux = max(worst_flux, float(abs(mp.mpf(got) - ex) / max(abs(ex), mp.mpf(floors[name]))))
+    _record("sea-ice whole fixed points", solves=len(picks), trip_count_mismatches=mismatch, at_maxiter=maxed,
+            worst_rel_skin_temperature=worst_T, worst_rel_fluxes=worst_flux)
+    assert mismatch <= 2, mismatch
+    assert len(picks) - mismatch - maxed >= 20
+    assert worst_T <= 1e-12 and worst_flux <= 1e-9, (worst_T, worst_flux)
