@@ -41,6 +41,8 @@ static int launch_queue_hs(const NeAtmosOceanDesc& d, const TabParams& T, const 
                      : std::log(d.surface_layer_height.value - prm.P.d_zero);
   uint32_t* counters = queue_counters();
   NE_REQUIRE(counters != nullptr, "atmosphere-ocean: could not allocate the work-queue counters");
+  if (cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s); e != cudaSuccess)   // see queue_counters()
+    return cuda_error(e, "work-queue kernel (counter reset)");
   const unsigned grid = queue_grid((int64_t)prm.L.ni * prm.L.nj, 8, 3);
   if (cudaError_t e = allow_table_smem<flux_queue_kernel<Problem, 8, 3>>(); e != cudaSuccess) return cuda_error(e, "work-queue kernel (shared memory opt-in)");
   flux_queue_kernel<Problem, 8, 3><<<grid, 256, TAB_SMEM_BYTES, s>>>(prm, tab, queue_theta(), counters);

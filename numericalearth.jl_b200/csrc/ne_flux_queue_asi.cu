@@ -20,6 +20,8 @@ static int launch_asi_queue_hs(const NeAtmosSeaIceDesc& d, const TabParams& T, c
                      : std::log(d.surface_layer_height.value - prm.P.d_zero);
   uint32_t* counters = queue_counters();
   NE_REQUIRE(counters != nullptr, "atmosphere-sea-ice: could not allocate the work-queue counters");
+  if (cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(uint32_t), s); e != cudaSuccess)   // see queue_counters()
+    return cuda_error(e, "work-queue kernel (counter reset)");
   const unsigned grid = queue_grid((int64_t)prm.L.ni * prm.L.nj, 4, 4);
   if (cudaError_t e = allow_table_smem<flux_queue_kernel<Problem, 4, 4>>(); e != cudaSuccess) return cuda_error(e, "work-queue kernel (shared memory opt-in)");
   flux_queue_kernel<Problem, 4, 4><<<grid, 128, TAB_SMEM_BYTES, s>>>(prm, tab, queue_theta(), counters);

@@ -55,9 +55,11 @@ inline FrontF32 make_front_f32(const NeFluxFormulation& flux, double gravitation
   return Q;
 }
 
-// Tile/CTA counters of the work-queue kernel: a per-device pool of zero-initialised {tile, cta} pairs used round
-// robin.  A kernel leaves its pair zeroed (last CTA out), so no per-launch memset is needed and launches can be
-// captured in CUDA graphs; two launches share a pair only if QUEUE_SLOTS launches are in flight at once.
+// Tile/CTA counters of the work-queue kernel: a per-device pool of {tile, cta} pairs used round robin.  A kernel leaves
+// its pair zeroed (last CTA out) AND every launcher zeroes the pair on its own stream right before the launch (a memset
+// node under CUDA-graph capture): a launch that was aborted half-way cannot leave a later one with tile >= n_tiles and no
+// outputs.  Two launches share a pair only if QUEUE_SLOTS launches are in flight at once (or a captured graph, pinned to
+// the pair it was captured with, replays while the live launch that drew the same pair is still running).
 uint32_t* queue_counters();   // ne_flux_queue_ao.cu
 
 // grid of the persistent work-queue kernels: resident CTAs x NE_B200_QUEUE_WAVES, at most one CTA per 32*warps points
