@@ -69,12 +69,12 @@ int ne_device_count(void) {
   return n;
 }
 
-int ne_memcpy_h2d(void* dst, const void* src, uint64_t bytes, void* stream) {
+int ne_memcpy_h2d(void* dst, const void* src, uint64_t bytes, void* stream) { NE_NVTX();
   cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
   return e == cudaSuccess ? NE_OK : ne::cuda_error(e, "ne_memcpy_h2d");
 }
 
-int ne_memcpy_d2h(void* dst, const void* src, uint64_t bytes, void* stream) {
+int ne_memcpy_d2h(void* dst, const void* src, uint64_t bytes, void* stream) { NE_NVTX();
   cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
   return e == cudaSuccess ? NE_OK : ne::cuda_error(e, "ne_memcpy_d2h");
 }
@@ -108,7 +108,7 @@ NcclBinding& nccl_binding() {
 }
 }  // namespace
 
-int ne_diag_allreduce_f64(void* nccl_comm, double* sums, int32_t n, void* stream) {
+int ne_diag_allreduce_f64(void* nccl_comm, double* sums, int32_t n, void* stream) { NE_NVTX();
   NE_REQUIRE(nccl_comm != nullptr && sums != nullptr && n > 0, "diag_allreduce: null communicator / buffer or n <= 0");
   NcclBinding& b = nccl_binding();
   if (!b.all_reduce) {

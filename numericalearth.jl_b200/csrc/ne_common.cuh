@@ -9,9 +9,22 @@
 #include <cstring>
 #include <type_traits>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: a stub until a tool (nsys, ncu --nvtx) injects itself
+
 #include "../../include/ne_b200.h"
 
 namespace ne {
+
+// One NVTX range per C-ABI entry point, named after it: a timeline shows the phases of update_state! (interpolation, the three
+// turbulent-flux solves, sea-ice-ocean, assembly, radiation, ring loads) as the host enqueues them; `ncu --nvtx --nvtx-include`
+// selects the kernels of one phase.  Costs a pointer test per call when no tool is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define NE_NVTX() ::ne::NvtxRange ne_nvtx_range_(__func__)
 
 // ---- error plumbing (thread-local message, negative codes; include/ne_b200.h) ----------------
 void set_error(const char* fmt, ...);

@@ -756,11 +756,11 @@ static int count_solve_ops(const NeAtmosOceanDesc* d, uint64_t* out, void* strea
 }  // namespace ne
 
 extern "C" {
-int ne_count_solve_ops_f64(const NeAtmosOceanDesc* d, uint64_t* out, void* stream) { return ne::count_solve_ops(d, out, stream); }
-int ne_atmosphere_land_fluxes_f64(const NeAtmosLandDesc* d, void* stream) { return ne::al_entry<double>(d, stream); }
-int ne_atmosphere_land_fluxes_f32(const NeAtmosLandDesc* d, void* stream) { return ne::al_entry<float>(d, stream); }
-int ne_atmosphere_ocean_fluxes_f64(const NeAtmosOceanDesc* d, void* stream) { return ne::ao_entry<double>(d, stream); }
-int ne_atmosphere_ocean_fluxes_f32(const NeAtmosOceanDesc* d, void* stream) { return ne::ao_entry<float>(d, stream); }
-int ne_atmosphere_sea_ice_fluxes_f64(const NeAtmosSeaIceDesc* d, void* stream) { return ne::asi_entry<double>(d, stream); }
-int ne_atmosphere_sea_ice_fluxes_f32(const NeAtmosSeaIceDesc* d, void* stream) { return ne::asi_entry<float>(d, stream); }
+int ne_count_solve_ops_f64(const NeAtmosOceanDesc* d, uint64_t* out, void* stream) { NE_NVTX(); return ne::count_solve_ops(d, out, stream); }
+int ne_atmosphere_land_fluxes_f64(const NeAtmosLandDesc* d, void* stream) { NE_NVTX(); return ne::al_entry<double>(d, stream); }
+int ne_atmosphere_land_fluxes_f32(const NeAtmosLandDesc* d, void* stream) { NE_NVTX(); return ne::al_entry<float>(d, stream); }
+int ne_atmosphere_ocean_fluxes_f64(const NeAtmosOceanDesc* d, void* stream) { NE_NVTX(); return ne::ao_entry<double>(d, stream); }
+int ne_atmosphere_ocean_fluxes_f32(const NeAtmosOceanDesc* d, void* stream) { NE_NVTX(); return ne::ao_entry<float>(d, stream); }
+int ne_atmosphere_sea_ice_fluxes_f64(const NeAtmosSeaIceDesc* d, void* stream) { NE_NVTX(); return ne::asi_entry<double>(d, stream); }
+int ne_atmosphere_sea_ice_fluxes_f32(const NeAtmosSeaIceDesc* d, void* stream) { NE_NVTX(); return ne::asi_entry<float>(d, stream); }
 }

@@ -86,8 +86,8 @@ static int fused_step(const NeFusedStepDesc* d, void* stream, bool f64) {
   return NE_OK;
 }
 
-int ne_fused_interface_step_f64(const NeFusedStepDesc* d, void* stream) { return fused_step(d, stream, true); }
-int ne_fused_interface_step_f32(const NeFusedStepDesc* d, void* stream) { return fused_step(d, stream, false); }
-int ne_interp_and_ao_fluxes_f64(const NeFusedStepDesc* d, void* stream) { return interp_and_ao(d, stream, true); }
-int ne_interp_and_ao_fluxes_f32(const NeFusedStepDesc* d, void* stream) { return interp_and_ao(d, stream, false); }
+int ne_fused_interface_step_f64(const NeFusedStepDesc* d, void* stream) { NE_NVTX(); return fused_step(d, stream, true); }
+int ne_fused_interface_step_f32(const NeFusedStepDesc* d, void* stream) { NE_NVTX(); return fused_step(d, stream, false); }
+int ne_interp_and_ao_fluxes_f64(const NeFusedStepDesc* d, void* stream) { NE_NVTX(); return interp_and_ao(d, stream, true); }
+int ne_interp_and_ao_fluxes_f32(const NeFusedStepDesc* d, void* stream) { NE_NVTX(); return interp_and_ao(d, stream, false); }
 }

@@ -525,8 +525,8 @@ static int frac_entry(const NeFracIndexDesc* d, void* stream) {
 }  // namespace ne
 
 extern "C" {
-int ne_interp_state_f64(const NeInterpDesc* d, void* stream) { return ne::interp_entry<double>(d, stream); }
-int ne_interp_state_f32(const NeInterpDesc* d, void* stream) { return ne::interp_entry<float>(d, stream); }
-int ne_frac_indices_f64(const NeFracIndexDesc* d, void* stream) { return ne::frac_entry<double>(d, stream); }
-int ne_frac_indices_f32(const NeFracIndexDesc* d, void* stream) { return ne::frac_entry<float>(d, stream); }
+int ne_interp_state_f64(const NeInterpDesc* d, void* stream) { NE_NVTX(); return ne::interp_entry<double>(d, stream); }
+int ne_interp_state_f32(const NeInterpDesc* d, void* stream) { NE_NVTX(); return ne::interp_entry<float>(d, stream); }
+int ne_frac_indices_f64(const NeFracIndexDesc* d, void* stream) { NE_NVTX(); return ne::frac_entry<double>(d, stream); }
+int ne_frac_indices_f32(const NeFracIndexDesc* d, void* stream) { NE_NVTX(); return ne::frac_entry<float>(d, stream); }
 }

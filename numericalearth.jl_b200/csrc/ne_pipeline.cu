@@ -197,10 +197,10 @@ int ne_host_pipeline_destroy(void* handle) {
   return NE_OK;
 }
 
-int ne_host_pipelined_step_f64(void* handle, const NeHostStepDesc* d, void* stream) {
+int ne_host_pipelined_step_f64(void* handle, const NeHostStepDesc* d, void* stream) { NE_NVTX();
   return ne::pipelined_step((ne::HostPipeline*)handle, d, stream, true);
 }
-int ne_host_pipelined_step_f32(void* handle, const NeHostStepDesc* d, void* stream) {
+int ne_host_pipelined_step_f32(void* handle, const NeHostStepDesc* d, void* stream) { NE_NVTX();
   return ne::pipelined_step((ne::HostPipeline*)handle, d, stream, false);
 }
 

@@ -210,7 +210,7 @@ int ne_series_ring_destroy(void* handle) {
   return NE_OK;
 }
 
-int ne_series_ring_load(void* handle, int32_t slot, const void* const* host_raw) {
+int ne_series_ring_load(void* handle, int32_t slot, const void* const* host_raw) { NE_NVTX();
   ne::SeriesRing* r = (ne::SeriesRing*)handle;
   NE_REQUIRE(r != nullptr && host_raw != nullptr, "series ring load: null argument");
   const NeSeriesRingDesc& d = r->d;
@@ -249,7 +249,7 @@ int ne_series_ring_load(void* handle, int32_t slot, const void* const* host_raw)
   return NE_OK;
 }
 
-int ne_series_ring_acquire(void* handle, int32_t slot, void* compute_stream) {
+int ne_series_ring_acquire(void* handle, int32_t slot, void* compute_stream) { NE_NVTX();
   ne::SeriesRing* r = (ne::SeriesRing*)handle;
   NE_REQUIRE(r != nullptr, "series ring acquire: null handle");
   NE_REQUIRE(slot >= 0 && slot < r->d.n_slots, "series ring acquire: slot out of range");
@@ -258,7 +258,7 @@ int ne_series_ring_acquire(void* handle, int32_t slot, void* compute_stream) {
   return NE_OK;
 }
 
-int ne_series_ring_release(void* handle, void* compute_stream) {
+int ne_series_ring_release(void* handle, void* compute_stream) { NE_NVTX();
   ne::SeriesRing* r = (ne::SeriesRing*)handle;
   NE_REQUIRE(r != nullptr, "series ring release: null handle");
   NE_CUDA_TRY(cudaEventRecord(r->released, (cudaStream_t)compute_stream), "series ring release");

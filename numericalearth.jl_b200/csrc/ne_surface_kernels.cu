@@ -445,51 +445,51 @@ int post_solve_f32(const NeFusedStepDesc* d, void* stream) { return post_solve<f
 }  // namespace ne
 
 extern "C" {
-int ne_sea_ice_ocean_fluxes_f64(const NeSeaIceOceanDesc* d, void* s) { return ne::sio_entry<double>(d, s); }
-int ne_sea_ice_ocean_fluxes_f32(const NeSeaIceOceanDesc* d, void* s) { return ne::sio_entry<float>(d, s); }
+int ne_sea_ice_ocean_fluxes_f64(const NeSeaIceOceanDesc* d, void* s) { NE_NVTX(); return ne::sio_entry<double>(d, s); }
+int ne_sea_ice_ocean_fluxes_f32(const NeSeaIceOceanDesc* d, void* s) { NE_NVTX(); return ne::sio_entry<float>(d, s); }
 
-int ne_sea_ice_ocean_stress_f64(const NeSeaIceOceanStressDesc* d, void* s) {
+int ne_sea_ice_ocean_stress_f64(const NeSeaIceOceanStressDesc* d, void* s) { NE_NVTX();
   NE_REQUIRE(d && d->ui && d->vi && d->uo && d->vo && d->x_momentum && d->y_momentum, "stress: null array");
   return ne::launch_points(ne::sea_ice_ocean_stress_kernel<double>, *d, 1, 1, (cudaStream_t)s, "ne_sea_ice_ocean_stress");
 }
-int ne_sea_ice_ocean_stress_f32(const NeSeaIceOceanStressDesc* d, void* s) {
+int ne_sea_ice_ocean_stress_f32(const NeSeaIceOceanStressDesc* d, void* s) { NE_NVTX();
   NE_REQUIRE(d && d->ui && d->vi && d->uo && d->vo && d->x_momentum && d->y_momentum, "stress: null array");
   return ne::launch_points(ne::sea_ice_ocean_stress_kernel<float>, *d, 1, 1, (cudaStream_t)s, "ne_sea_ice_ocean_stress");
 }
-int ne_assemble_net_ocean_fluxes_f64(const NeAssembleOceanDesc* d, void* s) {
+int ne_assemble_net_ocean_fluxes_f64(const NeAssembleOceanDesc* d, void* s) { NE_NVTX();
   NE_REQUIRE(d && d->tau_x && d->tau_y && d->JT && d->JS && d->Jw && d->JH, "assemble ocean: null output");
   return ne::launch_points(ne::assemble_ocean_kernel<double>, *d, 1, 0, (cudaStream_t)s, "ne_assemble_net_ocean_fluxes");
 }
-int ne_assemble_net_ocean_fluxes_f32(const NeAssembleOceanDesc* d, void* s) {
+int ne_assemble_net_ocean_fluxes_f32(const NeAssembleOceanDesc* d, void* s) { NE_NVTX();
   NE_REQUIRE(d && d->tau_x && d->tau_y && d->JT && d->JS && d->Jw && d->JH, "assemble ocean: null output");
   return ne::launch_points(ne::assemble_ocean_kernel<float>, *d, 1, 0, (cudaStream_t)s, "ne_assemble_net_ocean_fluxes");
 }
-int ne_assemble_net_sea_ice_fluxes_f64(const NeAssembleSeaIceDesc* d, void* s) {
+int ne_assemble_net_sea_ice_fluxes_f64(const NeAssembleSeaIceDesc* d, void* s) { NE_NVTX();
   NE_REQUIRE(d && d->top_heat && d->top_snowfall && d->top_u && d->top_v && d->bottom_heat, "assemble sea ice: null output");
   return ne::launch_points(ne::assemble_sea_ice_kernel<double>, *d, 1, 0, (cudaStream_t)s, "ne_assemble_net_sea_ice_fluxes");
 }
-int ne_assemble_net_sea_ice_fluxes_f32(const NeAssembleSeaIceDesc* d, void* s) {
+int ne_assemble_net_sea_ice_fluxes_f32(const NeAssembleSeaIceDesc* d, void* s) { NE_NVTX();
   NE_REQUIRE(d && d->top_heat && d->top_snowfall && d->top_u && d->top_v && d->bottom_heat, "assemble sea ice: null output");
   return ne::launch_points(ne::assemble_sea_ice_kernel<float>, *d, 1, 0, (cudaStream_t)s, "ne_assemble_net_sea_ice_fluxes");
 }
-int ne_apply_radiative_fluxes_f64(const NeApplyRadiationDesc* d, void* s) {
+int ne_apply_radiative_fluxes_f64(const NeApplyRadiationDesc* d, void* s) { NE_NVTX();
   NE_REQUIRE(d && d->surface_temperature && d->heat_flux && d->upwelling_longwave && d->downwelling_longwave && d->downwelling_shortwave, "apply radiation: null array");
   NE_REQUIRE(!d->two_color || d->two_color_surface_flux, "apply radiation: two_color without surface_flux array");
   return ne::launch_points(ne::apply_radiation_kernel<double>, *d, 0, 0, (cudaStream_t)s, "ne_apply_radiative_fluxes");
 }
-int ne_apply_radiative_fluxes_f32(const NeApplyRadiationDesc* d, void* s) {
+int ne_apply_radiative_fluxes_f32(const NeApplyRadiationDesc* d, void* s) { NE_NVTX();
   NE_REQUIRE(d && d->surface_temperature && d->heat_flux && d->upwelling_longwave && d->downwelling_longwave && d->downwelling_shortwave, "apply radiation: null array");
   NE_REQUIRE(!d->two_color || d->two_color_surface_flux, "apply radiation: two_color without surface_flux array");
   return ne::launch_points(ne::apply_radiation_kernel<float>, *d, 0, 0, (cudaStream_t)s, "ne_apply_radiative_fluxes");
 }
-int ne_correct_atmosphere_elevation_f64(const NeElevationCorrectionDesc* d, void* s) {
+int ne_correct_atmosphere_elevation_f64(const NeElevationCorrectionDesc* d, void* s) { NE_NVTX();
   NE_REQUIRE(d && d->T && d->p && d->elevation_difference, "elevation correction: null array");
   return ne::launch_points(ne::elevation_correction_kernel<double>, *d, 0, 0, (cudaStream_t)s, "ne_correct_atmosphere_elevation");
 }
-int ne_correct_atmosphere_elevation_f32(const NeElevationCorrectionDesc* d, void* s) {
+int ne_correct_atmosphere_elevation_f32(const NeElevationCorrectionDesc* d, void* s) { NE_NVTX();
   NE_REQUIRE(d && d->T && d->p && d->elevation_difference, "elevation correction: null array");
   return ne::launch_points(ne::elevation_correction_kernel<float>, *d, 0, 0, (cudaStream_t)s, "ne_correct_atmosphere_elevation");
 }
-int ne_diag_reduce_f64(const NeDiagDesc* d, void* s) { return ne::diag_entry<double>(d, s); }
-int ne_diag_reduce_f32(const NeDiagDesc* d, void* s) { return ne::diag_entry<float>(d, s); }
+int ne_diag_reduce_f64(const NeDiagDesc* d, void* s) { NE_NVTX(); return ne::diag_entry<double>(d, s); }
+int ne_diag_reduce_f32(const NeDiagDesc* d, void* s) { NE_NVTX(); return ne::diag_entry<float>(d, s); }
 }
