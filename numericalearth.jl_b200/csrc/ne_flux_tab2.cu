@@ -135,6 +135,69 @@ trip_order_counting_kernel(const uint16_t* __restrict__ hint, const uint32_t n, 
   }
 }
 
+// Third form (shipped): counting sort on (trip count, table record / 4) — 11 bits — with a shared-memory histogram.  ncu of
+// the solve under the two orderings above (C4, cold): sorted on (trips, record) 1167 us with 25 M shared-memory bank
+// conflicts, sorted on trips alone 1222 us with 76 M: a ψ-table record is 11 chunks of 16 bytes, so the lanes of a quarter
+// warp collide exactly when their records differ by a multiple of 8 — lanes within 8 consecutive records never do.  Classes
+// of 4 consecutive records keep a group's lanes inside such a span at a fifth of the bitonic network's cost:
+//   1. rank of an element within its key = what a shared-memory atomicAdd on cnt[key] returns (one atomic per key class of a
+//      warp, the lanes of a class ranked by match.any);
+//   2. exclusive scan over the 2048 counters (8 per thread);
+//   3. element -> position off[key] + rank.
+// The order inside a key class depends on the order the atomics land in: the permutation is not reproducible from run to
+// run — the results are (which lane computes a point does not change its arithmetic; tested bit for bit).
+template <int W>
+__global__ void __launch_bounds__(W / 4)
+trip_order_histogram_kernel(const uint16_t* __restrict__ hint, const uint32_t n, uint16_t* __restrict__ perm) {
+  static_assert(W == 1024, "256 threads, 4 elements and 8 counters each");
+  constexpr int NT = W / 4, REC_SHIFT = 2, REC_CLASS_BITS = TAB2_REC_BITS - REC_SHIFT;
+  constexpr int NKEY = 1 << (TAB2_TRIP_BITS + REC_CLASS_BITS);
+  static_assert(NKEY == 8 * NT, "8 counters per thread");
+  __shared__ __align__(16) uint32_t cnt[NKEY];
+  __shared__ uint32_t warp_tot[NT / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t t0 = blockIdx.x * (uint32_t)W;
+  reinterpret_cast<uint4*>(cnt)[2 * tid] = make_uint4(0u, 0u, 0u, 0u);
+  reinterpret_cast<uint4*>(cnt)[2 * tid + 1] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  uint32_t key[4], rank[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t t = t0 + (uint32_t)(tid + NT * k);
+    const uint32_t h = t < n ? (uint32_t)hint[t] : 0xffffu;     // beyond the launch range: the last key
+    key[k] = (((h >> TAB2_REC_BITS) & ((1u << TAB2_TRIP_BITS) - 1u)) << REC_CLASS_BITS) | ((h & ((1u << TAB2_REC_BITS) - 1u)) >> REC_SHIFT);
+    // one atomic per key class of the warp (lanes that hold the same key are ranked by match.any): 32 lanes on one key
+    // would otherwise serialise on one shared-memory word
+    const unsigned same = __match_any_sync(0xffffffffu, key[k]);
+    const int leader = __ffs(same) - 1;
+    uint32_t first = 0;
+    if (lane == leader) first = atomicAdd(&cnt[key[k]], (uint32_t)__popc(same));
+    rank[k] = __shfl_sync(0xffffffffu, first, leader) + (uint32_t)__popc(same & ((1u << lane) - 1u));
+  }
+  __syncthreads();
+  uint4 a = reinterpret_cast<const uint4*>(cnt)[2 * tid], b = reinterpret_cast<const uint4*>(cnt)[2 * tid + 1];
+  const uint32_t local = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+  uint32_t incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  uint32_t base = incl - local;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) base += (w < warp) ? warp_tot[w] : 0u;
+  uint4 oa, ob;
+  oa.x = base; oa.y = oa.x + a.x; oa.z = oa.y + a.y; oa.w = oa.z + a.z;
+  ob.x = oa.w + a.w; ob.y = ob.x + b.x; ob.z = ob.y + b.y; ob.w = ob.z + b.z;
+  reinterpret_cast<uint4*>(cnt)[2 * tid] = oa;      // each thread overwrites only the counters it has read
+  reinterpret_cast<uint4*>(cnt)[2 * tid + 1] = ob;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) perm[t0 + cnt[key[k]] + rank[k]] = (uint16_t)(tid + NT * k);
+}
+
 // 8 warps per CTA, 3 CTAs per SM (80 registers), persistent: a CTA stages the table once; its warps then draw groups of 32
 // sorted points from a global counter until the launch range is exhausted and never synchronise.  (Round 2 first shipped
 // one 1024-point window per CTA: the table was staged 7100 times per C4 launch and a CTA's fast warps idled until its
@@ -413,8 +476,10 @@ static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastP
   if (cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s); e != cudaSuccess)
     return cuda_error(e, "ne_atmosphere_ocean_fluxes(tab2: counter reset)");
   if (perm) {
-    if (env_flag("NE_B200_TAB2_BITONIC")) trip_order_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm);   // (trips, record) order
-    else trip_order_counting_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm);
+    const int order = env_int("NE_B200_TAB2_ORDER", 2);   // 0: bitonic (trips, record); 1: stable counting sort on trips; 2: histogram on (trips, record / 4)
+    if (order == 0) trip_order_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm);
+    else if (order == 1) trip_order_counting_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm);
+    else trip_order_histogram_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm);
     NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(trip order)");
   }
   const unsigned grid = tab2_grid(n_windows * (W / 32), NW, CTAS);
