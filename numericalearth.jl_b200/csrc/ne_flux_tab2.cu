@@ -148,7 +148,7 @@ trip_order_counting_kernel(const uint16_t* __restrict__ hint, const uint32_t n, 
 // run — the results are (which lane computes a point does not change its arithmetic; tested bit for bit).
 template <int W>
 __global__ void __launch_bounds__(W / 4)
-trip_order_histogram_kernel(const uint16_t* __restrict__ hint, const uint32_t n, uint16_t* __restrict__ perm) {
+trip_order_histogram_kernel(const uint16_t* __restrict__ hint, const uint32_t n, uint16_t* __restrict__ perm, const int descending) {
   static_assert(W == 1024, "256 threads, 4 elements and 8 counters each");
   constexpr int NT = W / 4, REC_SHIFT = 2, REC_CLASS_BITS = TAB2_REC_BITS - REC_SHIFT;
   constexpr int NKEY = 1 << (TAB2_TRIP_BITS + REC_CLASS_BITS);
@@ -165,7 +165,11 @@ trip_order_histogram_kernel(const uint16_t* __restrict__ hint, const uint32_t n,
   for (int k = 0; k < 4; ++k) {
     const uint32_t t = t0 + (uint32_t)(tid + NT * k);
     const uint32_t h = t < n ? (uint32_t)hint[t] : 0xffffu;     // beyond the launch range: the last key
-    key[k] = (((h >> TAB2_REC_BITS) & ((1u << TAB2_TRIP_BITS) - 1u)) << REC_CLASS_BITS) | ((h & ((1u << TAB2_REC_BITS) - 1u)) >> REC_SHIFT);
+    uint32_t trips = (h >> TAB2_REC_BITS) & ((1u << TAB2_TRIP_BITS) - 1u);
+    // descending: a window's longest groups are drawn first, so the groups drawn last in a launch — the ones the kernel's tail
+    // waits for — are its shortest
+    if (descending && t < n) trips = ((1u << TAB2_TRIP_BITS) - 1u) - trips;
+    key[k] = (trips << REC_CLASS_BITS) | ((h & ((1u << TAB2_REC_BITS) - 1u)) >> REC_SHIFT);
     // one atomic per key class of the warp (lanes that hold the same key are ranked by match.any): 32 lanes on one key
     // would otherwise serialise on one shared-memory word
     const unsigned same = __match_any_sync(0xffffffffu, key[k]);
@@ -455,8 +459,11 @@ static unsigned tab2_grid(uint32_t n_groups, int warps, int ctas_per_sm) {
   int sms = 148, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const uint32_t ctas_needed = (n_groups + warps - 1) / warps;
-  return std::max(1u, std::min<uint32_t>(ctas_needed, (uint32_t)(sms * ctas_per_sm)));
+  // one CTA per SM as soon as there is a group for each: a small launch is latency-bound (a lone warp runs a trip in ~1.5 us, six
+  // warps on a scheduler already contend for issue slots), so its groups are spread over all SMs instead of packed 24 to a CTA
+  // (C1, 1720 groups: 71 -> 45 us); warps that draw nothing exit at once
+  (void)warps;
+  return std::max(1u, std::min<uint32_t>(n_groups, (uint32_t)(sms * ctas_per_sm)));
 }
 
 bool tab2_eligible(const NeAtmosOceanDesc& d, const TabParams& TP) {
@@ -479,7 +486,7 @@ static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastP
     const int order = env_int("NE_B200_TAB2_ORDER", 2);   // 0: bitonic (trips, record); 1: stable counting sort on trips; 2: histogram on (trips, record / 4)
     if (order == 0) trip_order_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm);
     else if (order == 1) trip_order_counting_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm);
-    else trip_order_histogram_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm);
+    else trip_order_histogram_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm, env_int("NE_B200_TAB2_DESCENDING", 0));
     NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(trip order)");
   }
   const unsigned grid = tab2_grid(n_windows * (W / 32), NW, CTAS);
