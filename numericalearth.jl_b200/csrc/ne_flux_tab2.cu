@@ -148,7 +148,8 @@ trip_order_counting_kernel(const uint16_t* __restrict__ hint, const uint32_t n, 
 // run — the results are (which lane computes a point does not change its arithmetic; tested bit for bit).
 template <int W>
 __global__ void __launch_bounds__(W / 4)
-trip_order_histogram_kernel(const uint16_t* __restrict__ hint, const uint32_t n, uint16_t* __restrict__ perm, const int descending) {
+trip_order_histogram_kernel(const uint16_t* __restrict__ hint, const uint32_t n, uint16_t* __restrict__ perm, const int descending,
+                            uint32_t* __restrict__ group_counter) {
   static_assert(W == 1024, "256 threads, 4 elements and 8 counters each");
   constexpr int NT = W / 4, REC_SHIFT = 2, REC_CLASS_BITS = TAB2_REC_BITS - REC_SHIFT;
   constexpr int NKEY = 1 << (TAB2_TRIP_BITS + REC_CLASS_BITS);
@@ -157,6 +158,7 @@ trip_order_histogram_kernel(const uint16_t* __restrict__ hint, const uint32_t n,
   __shared__ uint32_t warp_tot[NT / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t t0 = blockIdx.x * (uint32_t)W;
+  if (blockIdx.x == 0 && tid == 0) *group_counter = 0u;   // the solve's group queue: reset here instead of by a memset node of its own
   reinterpret_cast<uint4*>(cnt)[2 * tid] = make_uint4(0u, 0u, 0u, 0u);
   reinterpret_cast<uint4*>(cnt)[2 * tid + 1] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
@@ -480,13 +482,14 @@ static int launch_tab2_t(const NeAtmosOceanDesc& d, const Layout& L, const FastP
   const uint32_t n_windows = (n + W - 1) / W;
   uint32_t* counter = tab2_counter();
   NE_REQUIRE(counter != nullptr, "atmosphere-ocean: could not allocate the group counter");
-  if (cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s); e != cudaSuccess)
-    return cuda_error(e, "ne_atmosphere_ocean_fluxes(tab2: counter reset)");
+  const int order = env_int("NE_B200_TAB2_ORDER", 2);   // 0: bitonic (trips, record); 1: stable counting sort on trips; 2: histogram on (trips, record / 4)
+  if (!perm || order == 0 || order == 1)                // the shipped ordering pass resets the counter itself
+    if (cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), s); e != cudaSuccess)
+      return cuda_error(e, "ne_atmosphere_ocean_fluxes(tab2: counter reset)");
   if (perm) {
-    const int order = env_int("NE_B200_TAB2_ORDER", 2);   // 0: bitonic (trips, record); 1: stable counting sort on trips; 2: histogram on (trips, record / 4)
     if (order == 0) trip_order_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm);
     else if (order == 1) trip_order_counting_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm);
-    else trip_order_histogram_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm, env_int("NE_B200_TAB2_DESCENDING", 0));
+    else trip_order_histogram_kernel<W><<<n_windows, W / 4, 0, s>>>(hint, n, perm, env_int("NE_B200_TAB2_DESCENDING", 0), counter);
     NE_CUDA_CHECK_LAUNCH("ne_atmosphere_ocean_fluxes(trip order)");
   }
   const unsigned grid = tab2_grid(n_windows * (W / 32), NW, CTAS);
