@@ -17,6 +17,7 @@
 #pragma once
 
 #include "ne_flux_queue.cuh"
+#include "ne_flux_tab2.cuh"   // tab2_surface_humidity: q_sat from the branch-free log / exp (same rounding rules as the a-o prologue)
 
 namespace ne {
 
@@ -146,11 +147,19 @@ struct AsiProblem {
     const FT Qv = -s.rho_L * s.ustar * s.q_star;
     const FT dT = s.theta_a - Tsm;
     const FT Qa = Qv + lw_up + s.Qd;
-    const FT Oc = (dT == 0) ? (FT)0 : QT / dT;
-    const FT beta = 4 * lw_up / Tsm;
+    // Float64 model: the three quotients of the balance through the reciprocal-based division (≲ 1 ulp; a sea-ice point's
+    // solve is a chain of up to 100 dependent trips and the kernel's time is the latency of its slowest points, so every
+    // IEEE division — ~35 dependent instructions — is on the critical path); arguments that would not be normal numbers
+    // (ΔT = 0, D = 0) are replaced by the selects below exactly as in the reference
+    auto quot = [](FT a, FT b) -> FT {
+      if constexpr (F32) return a / b;
+      else return (b == 0) ? a / b : (FT)fm::div((double)a, (double)b);
+    };
+    const FT Oc = (dT == 0) ? (FT)0 : quot(QT, dT);
+    const FT beta = quot(4 * lw_up, Tsm);
     const FT R = s.R;
     const FT D = 1 + beta * R - Oc * R;
-    FT Tstar = (s.Tb + beta * R * Tsm - Oc * R * s.theta_a - Qa * R) / D;
+    FT Tstar = quot(s.Tb + beta * R * Tsm - Oc * R * s.theta_a - Qa * R, D);
     Tstar = (D == 0) ? Tsm : Tstar;
     Tstar = (Tstar != Tstar) ? Tsm : Tstar;
     const FT maxdT = (FT)ip.max_dT;
@@ -161,10 +170,18 @@ struct AsiProblem {
   __device__ static __forceinline__ FT trip(const Params& p, const double* tab, Point& s, int) {
     const NeInterfaceProperties& ip = p.d.properties;
     if (ip.temperature_formulation != NE_TEMP_BULK) s.Ts = skin_temperature(p, s);
-    const FT qs = surface_specific_humidity<FT, CT>(ip, p.th, s.ap, s.Ts, (FT)0);   // humidity scalar 0 over ice (:737)
-    const FT Tv = p.th.virtual_temperature(s.Ts, qs);
+    FT qs, Tv;
     typename QPointOf<FT>::type f;
-    f.gTv = gravity(p) / Tv;
+    if constexpr (F32) {
+      qs = surface_specific_humidity<FT, CT>(ip, p.th, s.ap, s.Ts, (FT)0);   // humidity scalar 0 over ice (:737)
+      Tv = p.th.virtual_temperature(s.Ts, qs);
+      f.gTv = gravity(p) / Tv;
+    } else {   // q_sat(Tₛ) is re-evaluated every trip: the power and the exponential from the branch-free log / exp
+      fm::OpsPlain o;
+      qs = tab2_surface_humidity(o, ip, p.th, p.T, tab, (double)s.ap, (double)s.Ts, 0.0);
+      Tv = fm::div(s.Ts * p.th.gas_constant_air(qs), (double)p.th.R_d);          // virtual_temperature
+      f.gTv = fm::div((double)gravity(p), Tv);
+    }
     f.c1 = 1 + p.th.delta * qs;
     f.c2 = p.th.delta * Tv;
     f.dudv2 = s.dudv2; f.h_bl = s.h_bl; f.hd = s.hd; f.log_hd = s.log_hd;
