@@ -404,6 +404,40 @@ def _ao_outputs(ci, backend):
     return out
 
 
+@pytest.mark.parametrize("setting", ["NE_B200_TAB2_ORDER=0", "NE_B200_TAB2_ORDER=1", "NE_B200_TAB2_ORDER=2",
+                                     "NE_B200_TAB2_ORDER=2,NE_B200_TAB2_DESCENDING=1", "NE_B200_TAB2_STAGING=1", "NE_B200_TAB2_SHAPE=0",
+                                     "NE_B200_TAB2_SHAPE=3"])
+def test_trip_ordering_passes_and_launch_shapes_do_not_change_a_bit(cuda_backend, cuda_lib, monkeypatch, setting):
+    """Which lane of which warp computes a point must not change its arithmetic: the three ordering passes of the round-2 solve
+    (bitonic network on (trips, record), stable counting sort on trips, histogram on (trips, record / 4) — whose permutation is
+    not even reproducible from run to run), the descending draw order, the cp.async staging and the other CTA shapes against
+    the launch in memory order, every output and the trip counts bit for bit.  A permutation that lost or doubled a point would
+    leave a point unwritten (NaN-filled beforehand) or fail the comparison."""
+    dev = synthetic.build_case("C2", cuda_backend, FT="f64", atm_FT="f32", with_iterations=True)
+    dev.initialize()
+    dev.interpolate_state(T_STEP)
+    monkeypatch.setenv("NE_B200_TAB2_NO_ORDER", "1")
+    dev.compute_atmosphere_ocean_fluxes()
+    cuda_backend.synchronize()
+    plain = _ao_outputs(dev, cuda_backend)
+    monkeypatch.delenv("NE_B200_TAB2_NO_ORDER")
+    for kv in setting.split(","):
+        k, v = kv.split("=")
+        monkeypatch.setenv(k, v)
+    for step in range(3):      # the first ordered launch sorts on the hints the launches before it left, the later ones on their own
+        for n in dev.ao_fluxes.names():
+            getattr(dev.ao_fluxes, n).fill_(float("nan"))
+        dev.ao_iterations.fill_(-1)
+        dev.compute_atmosphere_ocean_fluxes()
+        cuda_backend.synchronize()
+        got = _ao_outputs(dev, cuda_backend)
+        g = dev.grid
+        for n, a in plain.items():
+            x, y = g.interior(a), g.interior(got[n])
+            assert np.array_equal(x, y, equal_nan=True), f"{setting}, launch {step}: {n} differs at {int((x != y).sum())} points"
+        assert not np.isnan(g.interior(got["friction_velocity"])).any()
+
+
 @pytest.mark.parametrize("atm_FT", ["f64", "f32"])
 @pytest.mark.parametrize("theta", ["0", "8", "20"])
 def test_work_queue_kernel_equals_one_thread_per_point_kernel_bitwise(cuda_backend, cuda_lib, monkeypatch, atm_FT, theta):
