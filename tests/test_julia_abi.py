@@ -163,3 +163,75 @@ def test_extension_delimiters_balance():
     opens += len(re.findall(r"=\s*(?:if|begin|let|try)\b", code))
     ends = len(re.findall(r"\bend\b", code))
     assert opens == ends, f"block openers {opens} vs `end` {ends}"
+
+
+def _c_prototypes():
+    """name -> (return type, [parameter types]) of every entry point declared in include/ne_b200.h, in a canonical spelling."""
+    import re
+    text = open(os.path.join(ROOT, "include", "ne_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"^\s*(int|int64_t|const char\*)\s+(ne_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text, flags=re.M):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        params = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = re.sub(r"\s+", " ", a.strip())
+                if re.match(r"const (Ne\w+)\s*\*", a):
+                    params.append("struct:" + re.match(r"const (Ne\w+)\s*\*", a).group(1))
+                elif a.startswith("const char*") or a.startswith("const char *"):
+                    params.append("cstring")
+                elif "*" in a:
+                    params.append("pointer")
+                elif a.startswith("int32_t"):
+                    params.append("i32")
+                elif a.startswith("int64_t"):
+                    params.append("i64")
+                elif a.startswith("uint64_t"):
+                    params.append("u64")
+                else:
+                    raise AssertionError(f"unparsed parameter {a!r} of {name}")
+        protos[name] = ({"int": "i32", "int64_t": "i64", "const char*": "cstring"}[ret], params)
+    return protos
+
+
+_JULIA_TYPES = {"Cint": "i32", "Int32": "i32", "Int64": "i64", "UInt64": "u64", "Cstring": "cstring", "Ptr{Cvoid}": "pointer",
+                "Ptr{Float64}": "pointer", "Ptr{Ptr{Cvoid}}": "pointer"}
+
+
+def test_every_ccall_matches_the_c_prototype_it_binds():
+    """Return type, arity and argument kinds of every `ccall` in the extension against the prototype in include/ne_b200.h:
+    `Ref{NeX}` must face `const NeX*` of the SAME struct, integers must have the declared width, both precisions of an
+    `entry("ne_…", grid)` call must exist with the same signature."""
+    import re
+    src = open(os.path.join(ROOT, "julia", "ext", "NumericalEarthB200Ext.jl")).read()
+    protos = _c_prototypes()
+    assert len(protos) >= 45
+    calls = re.findall(r'ccall\(\((:ne_[a-z0-9_]+|entry\("ne_[a-z0-9_]+", grid\)), (?:path|libne\[\])\), (\w+),\s*\(([^)]*)\)', src)
+    assert len(calls) == len(re.findall(r"\bccall\(", src)) and len(calls) >= 19, len(calls)     # every ccall was parsed
+    seen = set()
+    for target, ret, argt in calls:
+        if target.startswith(":"):
+            names = [target[1:]]
+        else:
+            stem = re.match(r'entry\("(ne_[a-z0-9_]+)"', target).group(1)
+            names = [stem + "_f64", stem + "_f32"]
+        jargs = [a.strip() for a in argt.split(",") if a.strip()]
+        for name in names:
+            assert name in protos, f"ccall of {name}: no such prototype in the header"
+            cret, cparams = protos[name]
+            assert _JULIA_TYPES[ret] == cret, f"{name}: Julia return type {ret} vs C {cret}"
+            assert len(jargs) == len(cparams), f"{name}: {len(jargs)} ccall arguments vs {len(cparams)} C parameters"
+            for ja, cp in zip(jargs, cparams):
+                m = re.match(r"Ref\{(Ne\w+)\}", ja)
+                if m:
+                    assert cp == "struct:" + m.group(1), f"{name}: Julia passes {ja}, C expects {cp}"
+                else:
+                    assert ja in _JULIA_TYPES, f"{name}: unknown Julia argument type {ja}"
+                    assert _JULIA_TYPES[ja] == cp, f"{name}: Julia passes {ja}, C expects {cp}"
+            seen.add(name)
+    # the path's entry points are all bound
+    for stem in ("ne_frac_indices", "ne_interp_state", "ne_atmosphere_ocean_fluxes", "ne_atmosphere_sea_ice_fluxes", "ne_sea_ice_ocean_fluxes",
+                 "ne_sea_ice_ocean_stress", "ne_assemble_net_ocean_fluxes", "ne_assemble_net_sea_ice_fluxes", "ne_apply_radiative_fluxes",
+                 "ne_correct_atmosphere_elevation", "ne_diag_reduce"):
+        assert stem + "_f64" in seen and stem + "_f32" in seen, stem
